@@ -1,0 +1,237 @@
+/*
+ * sph_b200.h -- C ABI of libsph_b200, the B200-native (sm_100a) replacement for the particle hot
+ * path of KIYOYOZU/SPH-Poiseuille-Flow.  Plain C, plain pointers and sizes, no torch / CUDA types.
+ *
+ * What it replaces (reference file:line):
+ *   - the gateway of mex/sph_neighbor_search_mex.c:185-421          -> sphb_neighbor_search*
+ *   - the eight string-dispatched modes of mex/sph_physics_mex.c:1745-1772
+ *       density_correction  :95-374    -> sphb_density_correction
+ *       viscous_force       :396-550   -> sphb_viscous_force
+ *       transport_correction:569-714   -> sphb_transport_correction
+ *       integration_1st     :736-967   -> sphb_integration_1st
+ *       integration_2nd     :987-1119  -> sphb_integration_2nd
+ *       integration_verlet  :1316-1469 -> sphb_integration_verlet
+ *       advance_shell_step  :1490-1639 -> sphb_advance_shell_step
+ *       wall_shear_monitor  :1653-1743 -> sphb_wall_shear_monitor
+ *   - the main-loop body of SPH_Poiseuille.m:250-283 (+ :519-577)   -> sphb_ctx_* (device-resident)
+ *
+ * Two families of entry points:
+ *   1. STATELESS ("MEX path").  Host pointers in, host pointers out, nothing persists: exactly the
+ *      contract of the reference's MEX files.  Array arguments are passed as
+ *      sphb_mat views (pointer + MATLAB dims) so that every size check the reference performs -- and
+ *      the MATLAB error identifier it raises -- is reproduced inside the library; the MEX shims in
+ *      sph-poiseuille-flow_b200/mex/ only unpack prhs[] and pack plhs[].
+ *   2. DEVICE-RESIDENT context.  State lives in HBM across steps; the neighbour list is a CSR built
+ *      on the device; one call advances whole reference steps (or dual-criteria outer/inner steps).
+ *      This is what the standalone driver and bench.py run.
+ *
+ * Error model: every function returns 0 on success, non-zero on failure, never exits/aborts.  After a
+ * failure sphb_last_error_id() holds the MATLAB identifier the reference would have raised
+ * ("SPH:Neighbor:count", "SPH:Physics:viscous:vel", ...) or "SPHB:*" for
+ * conditions the reference cannot have (CUDA failures, capacity), and sphb_last_error_msg() a text.
+ * Both are thread-local.  There is NO CPU fallback: without a usable CUDA device every compute entry
+ * point fails with SPHB:cuda.
+ *
+ * Conventions: matrices are column-major [m x n] doubles as MATLAB stores them; particle indices in
+ * pair lists are 1-based doubles; fluid particles are rows 0..n_fluid-1, wall particles follow.
+ */
+#ifndef SPH_B200_H
+#define SPH_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SPHB_API __attribute__((visibility("default")))
+#else
+#define SPHB_API
+#endif
+
+#define SPHB_VERSION 100
+
+/* A borrowed, read-only view of a MATLAB double matrix (mxGetDoubles / mxGetM / mxGetN). */
+typedef struct sphb_mat {
+    const double *p;
+    size_t m;
+    size_t n;
+} sphb_mat;
+
+/* ----------------------------------------- errors ----------------------------------------- */
+SPHB_API const char *sphb_last_error_id(void);
+SPHB_API const char *sphb_last_error_msg(void);
+SPHB_API int sphb_version(void);
+/* 0 when a CUDA device is usable, else non-zero (and the last error says why). */
+SPHB_API int sphb_device_check(void);
+
+/* ============================== 1. stateless MEX-path entry points ============================== */
+
+/*
+ * Neighbour search, replaces mexFunction of mex/sph_neighbor_search_mex.c:185-421.
+ * Call sphb_neighbor_search() -> *n_pairs, allocate 7 arrays of *n_pairs doubles (the MEX shim uses
+ * mxCreateDoubleMatrix), then sphb_neighbor_fetch() copies device results straight into them and
+ * releases the handle.  sphb_neighbor_release() drops a handle without fetching.
+ * Output order and values are those of the reference (i ascending, its 3x3 walk order, its
+ * real/ghost-entry arithmetic): pair_i/pair_j 1-based, dx = x_i - x_j minimum-image.
+ * Errors: SPH:Neighbor:pos | count | param | entryCapacity (nb:223-242, 94).
+ */
+typedef struct sphb_pairs sphb_pairs;
+SPHB_API int sphb_neighbor_search(sphb_mat pos, int n_fluid, int n_total, double h, double DL,
+                                  sphb_pairs **handle, size_t *n_pairs);
+SPHB_API int sphb_neighbor_fetch(sphb_pairs *handle, double *pair_i, double *pair_j, double *dx, double *dy,
+                                 double *r, double *W, double *dW);
+SPHB_API void sphb_neighbor_release(sphb_pairs *handle);
+
+/* density_correction (ph:95-374).  Out: rho[n_total], Vol[n_total], B[n_total x 4]. */
+SPHB_API int sphb_density_correction(sphb_mat pair_i, sphb_mat pair_j, sphb_mat dx, sphb_mat dy, sphb_mat r,
+                                     sphb_mat W, sphb_mat dW, sphb_mat mass, int n_fluid, int n_total,
+                                     double rho0, double h, double inv_sigma0, double *rho, double *Vol,
+                                     double *B);
+
+/* viscous_force (ph:396-550).  Out: force[n_total x 2].  (mass is size-checked, unused: ph:547.) */
+SPHB_API int sphb_viscous_force(sphb_mat pair_i, sphb_mat pair_j, sphb_mat dx, sphb_mat dy, sphb_mat r,
+                                sphb_mat dW, sphb_mat vel, sphb_mat Vol, sphb_mat B, double mu, double h,
+                                int n_fluid, int n_total, sphb_mat mass, sphb_mat wall_vel, double *force);
+
+/* transport_correction (ph:569-714).  has_coeff = 0 selects the MEX default 0.2 (ph:584). */
+SPHB_API int sphb_transport_correction(sphb_mat pair_i, sphb_mat pair_j, sphb_mat dx, sphb_mat dy, sphb_mat r,
+                                       sphb_mat dW, sphb_mat Vol, sphb_mat B, sphb_mat pos, double h,
+                                       int n_fluid, int n_total, int has_coeff, double transport_coeff,
+                                       double *pos_out);
+
+/* integration_1st (ph:736-967).  Out: rho, p [n_total]; pos, force [n_total x 2]; drho_dt [n_total]. */
+SPHB_API int sphb_integration_1st(sphb_mat pair_i, sphb_mat pair_j, sphb_mat dx, sphb_mat dy, sphb_mat r,
+                                  sphb_mat dW, sphb_mat Vol, sphb_mat B, sphb_mat rho, sphb_mat mass,
+                                  sphb_mat pos, sphb_mat vel, sphb_mat drho_dt, sphb_mat force_prior, double dt,
+                                  int n_fluid, int n_total, double rho0, double p0, double c_f,
+                                  sphb_mat wall_vel, double *rho_out, double *p_out, double *pos_out,
+                                  double *force_out, double *drho_out);
+
+/* integration_2nd (ph:987-1119).  Out: pos [n_total x 2], drho_dt [n_total], zeros [n_total x 2]. */
+SPHB_API int sphb_integration_2nd(sphb_mat pair_i, sphb_mat pair_j, sphb_mat dx, sphb_mat dy, sphb_mat r,
+                                  sphb_mat dW, sphb_mat Vol, sphb_mat rho, sphb_mat pos, sphb_mat vel, double dt,
+                                  int n_fluid, int n_total, sphb_mat wall_vel, double *pos_out,
+                                  double *drho_out, double *zeros_out);
+
+/* integration_verlet (ph:1316-1469).  Out: rho, p, pos, vel, drho_dt, force. */
+SPHB_API int sphb_integration_verlet(sphb_mat pair_i, sphb_mat pair_j, sphb_mat dx, sphb_mat dy, sphb_mat r,
+                                     sphb_mat dW, sphb_mat Vol, sphb_mat B, sphb_mat rho, sphb_mat mass,
+                                     sphb_mat pos, sphb_mat vel, sphb_mat drho_dt, sphb_mat force_prior,
+                                     double dt, int n_fluid, int n_total, double rho0, double p0, double c_f,
+                                     sphb_mat wall_vel, double *rho_out, double *p_out, double *pos_out,
+                                     double *vel_out, double *drho_out, double *force_out);
+
+/* advance_shell_step (ph:1490-1639).  Out: rho, p, pos, vel, drho_dt, force, force_prior, Vol, B. */
+SPHB_API int sphb_advance_shell_step(sphb_mat pair_i, sphb_mat pair_j, sphb_mat dx, sphb_mat dy, sphb_mat r,
+                                     sphb_mat W, sphb_mat dW, sphb_mat mass, sphb_mat pos, sphb_mat vel,
+                                     sphb_mat wall_vel, sphb_mat rho, sphb_mat drho_dt, double dt, int n_fluid,
+                                     int n_total, double rho0, double p0, double c_f, double mu, double h,
+                                     double inv_sigma0, double gravity_g, double *rho_out, double *p_out,
+                                     double *pos_out, double *vel_out, double *drho_out, double *force_out,
+                                     double *force_prior_out, double *Vol_out, double *B_out);
+
+/* wall_shear_monitor (ph:1653-1743).  n_total is inferred from Vol (ph:1692).  Out: two scalars. */
+SPHB_API int sphb_wall_shear_monitor(sphb_mat pair_i, sphb_mat pair_j, sphb_mat dx, sphb_mat dy, sphb_mat r,
+                                     sphb_mat dW, sphb_mat pos, sphb_mat vel, sphb_mat wall_vel, sphb_mat Vol,
+                                     sphb_mat B, int n_fluid, double DL, double DH, double mu, double h,
+                                     double *tau_bottom, double *tau_top);
+
+/* ================================ 2. device-resident context ================================ */
+
+typedef struct sphb_ctx sphb_ctx;
+
+/* Physical / numerical parameters of one channel (SPH_Poiseuille.m:47-80 after derivation). */
+typedef struct sphb_params {
+    int n_fluid;
+    int n_total;
+    double DL, DH, dp, h;
+    double rho0, p0, c_f, mu, gravity_g, inv_sigma0;
+    double transport_coeff;   /* 0.30 in the script (m:77) */
+    int sort_interval;        /* cell sort every sort_interval steps, not at step 1 (m:272); <=0: never */
+    int device;               /* CUDA device ordinal; -1 = current device */
+    int max_neighbors_hint;   /* 0 = default; sizes the CSR when the exact count is not known yet */
+} sphb_params;
+
+SPHB_API int sphb_ctx_create(const sphb_params *prm, sphb_ctx **ctx);
+SPHB_API void sphb_ctx_destroy(sphb_ctx *ctx);
+
+/* Host (pageable or pinned) column-major arrays; any pointer may be NULL = leave untouched. */
+SPHB_API int sphb_ctx_upload(sphb_ctx *ctx, const double *pos, const double *vel, const double *rho,
+                             const double *drho_dt, const double *mass, const double *wall_vel);
+SPHB_API int sphb_ctx_download(sphb_ctx *ctx, double *pos, double *vel, double *rho, double *p, double *drho_dt,
+                               double *force, double *force_prior, double *Vol, double *B);
+/* Override/inspect the clock (restart). */
+SPHB_API int sphb_ctx_set_time(sphb_ctx *ctx, double t, long long step);
+
+/* Neighbour list (N1-N6): counting sort by 2h cell, ghost entries, dedup, CSR.  */
+SPHB_API int sphb_ctx_neighbor_build(sphb_ctx *ctx);
+SPHB_API int sphb_ctx_neighbor_count(sphb_ctx *ctx, size_t *n_half_pairs, size_t *n_csr_entries);
+/* The reference's half-pair COO list (same order/values as sphb_neighbor_search), 7 x n_half_pairs. */
+SPHB_API int sphb_ctx_neighbor_export_pairs(sphb_ctx *ctx, double *pair_i, double *pair_j, double *dx,
+                                            double *dy, double *r, double *W, double *dW);
+/* The full (gather) CSR: row_ptr[n_fluid+1], col[n_csr_entries] (0-based j, ascending per row). */
+SPHB_API int sphb_ctx_neighbor_export_csr(sphb_ctx *ctx, int *row_ptr, int *col);
+
+/* Single operators on the resident state (for operator-level parity tests; P1-P8). */
+SPHB_API int sphb_ctx_density_correction(sphb_ctx *ctx);              /* -> rho, Vol, B */
+SPHB_API int sphb_ctx_eos(sphb_ctx *ctx);                             /* p = p0 (rho/rho0 - 1), wall 0 (m:172-173) */
+SPHB_API int sphb_ctx_viscous_force(sphb_ctx *ctx, int add_gravity);  /* -> force_prior (+ m*g on x) */
+SPHB_API int sphb_ctx_transport_correction(sphb_ctx *ctx);            /* pos += shift */
+SPHB_API int sphb_ctx_integration_verlet(sphb_ctx *ctx, double dt);   /* dt <= 0: use the device dt */
+SPHB_API int sphb_ctx_wall_shear(sphb_ctx *ctx, double *tau_bottom, double *tau_top);
+SPHB_API int sphb_ctx_periodic_wrap(sphb_ctx *ctx);
+SPHB_API int sphb_ctx_sort_by_cell(sphb_ctx *ctx);                    /* m:529-568, unconditional */
+
+/* Status of the resident run, read back from the device (one small D2H). */
+typedef struct sphb_status {
+    double t;
+    double dt;            /* last step's dt */
+    double vmax;          /* max |v| over fluid rows after the last step */
+    double tau_bottom, tau_top;
+    long long step;
+    long long n_half_pairs;
+    long long n_csr_entries;
+    int error_flags;      /* device-side flags: 1 CSR capacity, 2 cell capacity, 4 dedup capacity, 8 non-finite */
+} sphb_status;
+SPHB_API int sphb_ctx_status(sphb_ctx *ctx, sphb_status *out);
+
+/*
+ * One pass of the reference main-loop body (SPH_Poiseuille.m:251-283): density+KGC, viscous(+g),
+ * transport, dt = min(acoustic, viscous, body, remain), Verlet, wrap, wall velocity zeroing,
+ * cell sort when due, neighbour rebuild, wall-shear monitor.  `remain` as in m:252 (use a huge value
+ * for "no output point pending").  Requires a neighbour list (sphb_ctx_neighbor_build) and is
+ * asynchronous: call sphb_ctx_status()/download to synchronise.
+ */
+SPHB_API int sphb_ctx_step(sphb_ctx *ctx, double remain);
+/* Reference schedule until t >= t_target - 1e-12 (m:250) or max_steps; returns steps done. */
+SPHB_API int sphb_ctx_run_until(sphb_ctx *ctx, double t_target, double t_end, long long max_steps,
+                                long long *steps_done);
+/*
+ * Dual-criteria schedule (README.md:61-65; no reference code at HEAD -- "parity unpinned"): n_outer
+ * outer steps, each = density+KGC, viscous(+g), transport on the current list, then n_inner acoustic
+ * Verlet substeps (dt = min(acoustic, viscous, body)) with immediate wrap, then [sort], list rebuild,
+ * shear monitor.  n_inner = 1 reproduces sphb_ctx_step with remain = inf.  Runs as a CUDA graph.
+ */
+SPHB_API int sphb_ctx_run_dual(sphb_ctx *ctx, int n_outer, int n_inner);
+
+/* x-/bin-averaged u(y) of the fluid rows (m:579-605).  x0 < 0: all fluid rows (full-length profile). */
+SPHB_API int sphb_ctx_profile(sphb_ctx *ctx, double x0, double half_width, int n_bins, double *u_mean,
+                              double *count);
+
+/* Device timing of the phases of the last sphb_ctx_step / run (ms, CUDA events). */
+typedef struct sphb_timing {
+    float neighbor_ms, density_ms, visc_transport_ms, verlet_ms, shear_ms, sort_ms, total_ms;
+    long long launches;   /* kernels launched by this context since creation */
+} sphb_timing;
+SPHB_API int sphb_ctx_timing(sphb_ctx *ctx, sphb_timing *out);
+SPHB_API int sphb_ctx_enable_timing(sphb_ctx *ctx, int on);
+/* The CUDA stream the context launches on (as a void* cudaStream_t), for event timing by callers. */
+SPHB_API void *sphb_ctx_stream(sphb_ctx *ctx);
+SPHB_API int sphb_ctx_sync(sphb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPH_B200_H */

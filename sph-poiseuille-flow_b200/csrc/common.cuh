@@ -1,0 +1,126 @@
+// common.cuh -- shared declarations of libsph_b200 (sm_100a).  Internal header, not part of the ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sph_b200.h"
+
+namespace sphb {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing (thread-local last error, MATLAB-style identifiers)
+// ------------------------------------------------------------------------------------------------
+int set_error(const char *id, const char *fmt, ...);
+void clear_error();
+const char *last_error_id();
+const char *last_error_msg();
+
+#define SPHB_CUDA(call)                                                                           \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return ::sphb::set_error("SPHB:cuda", "%s failed: %s (%s:%d)", #call,                 \
+                                     cudaGetErrorString(e__), __FILE__, __LINE__);                \
+    } while (0)
+
+#define SPHB_REQUIRE(cond, id, msg)                      \
+    do {                                                 \
+        if (!(cond)) return ::sphb::set_error(id, msg);  \
+    } while (0)
+
+#define SPHB_TRY(expr)          \
+    do {                        \
+        int rc__ = (expr);      \
+        if (rc__) return rc__;  \
+    } while (0)
+
+int ensure_device();   // 0 when a CUDA device is usable (sets SPHB:cuda otherwise)
+
+// ------------------------------------------------------------------------------------------------
+// device buffers: grow-only, reused across calls (stateless path) or owned by a context
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t need);   // grow-only; contents are NOT preserved on growth
+    void release();
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+// 2x2 kernel-gradient-correction matrix of one particle, one 32-byte record (two 128-bit loads)
+struct __align__(32) Mat2 {
+    double b11, b12, b21, b22;
+};
+
+constexpr int kBlock = 128;
+inline unsigned grid_for(size_t n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
+
+// device error flags (sphb_status.error_flags)
+enum : int { kErrCsrCap = 1, kErrCellCap = 2, kErrSeenCap = 4, kErrNonFinite = 8 };
+
+// ------------------------------------------------------------------------------------------------
+// cell grid descriptor, lives in device memory, written by the grid-setup kernel (nb:244-258)
+// ------------------------------------------------------------------------------------------------
+struct GridDesc {
+    double y_min, y_max;
+    double cell;       // 2h
+    int ncx, ncy, ncells;
+    int n_entries;     // real + ghost entries
+    long long ymin_key, ymax_key;   // ordered-integer images used by the atomic min/max reduction
+};
+
+// ------------------------------------------------------------------------------------------------
+// neighbour-list storage shared by the stateless search and the resident context
+// ------------------------------------------------------------------------------------------------
+struct NeighborWork {
+    int n_fluid = 0, n_total = 0;
+    double h = 0, DL = 0;
+    int cell_cap = 0;            // allocated cells
+    size_t half_cap = 0;         // allocated half-pair slots
+    size_t csr_cap = 0;          // allocated full-CSR slots
+    DevBuf grid;                 // GridDesc
+    DevBuf flags;                // int error flags
+    DevBuf snap;                 // double2 [n_total]   wrapped x, y at build time
+    DevBuf cell_of;              // int [n_total]       home cell of the real entry
+    DevBuf cell_cnt;             // int [cell_cap+1]
+    DevBuf cell_start;           // int [cell_cap+1]
+    DevBuf cell_fill;            // int [cell_cap]
+    DevBuf ent_key;              // int [3*n_total]     (particle << 3) | (multi << 2) | kind
+    DevBuf ent_pos;              // double2 [3*n_total] entry coordinates (ghosts shifted by -+DL)
+    DevBuf half_cnt;             // int [n_fluid+1]
+    DevBuf half_ptr;             // int [n_fluid+1]
+    DevBuf half_col;             // uint [half_cap]     j | kind << 30
+    DevBuf row_cnt;              // int [n_fluid+1]
+    DevBuf row_ptr;              // int [n_fluid+1]
+    DevBuf row_fill;             // int [n_fluid]
+    DevBuf col;                  // uint [csr_cap]      j | (shift code) << 30
+    DevBuf scan_tmp;             // scan workspace
+    DevBuf totals;               // int[4]: n_half, n_csr (device), read back on demand
+    void release_all();
+};
+
+// neighbor.cu (compiled with -fmad=false: bit-exact accept tests)
+int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL, double y_min_hint,
+                  double y_max_hint, int max_nbr_hint);
+int neighbor_build(NeighborWork &w, const double2 *pos, bool want_full_csr, cudaStream_t st, long long *launches);
+int neighbor_export_pairs(NeighborWork &w, size_t n_half, double *pair_i, double *pair_j, double *dx, double *dy,
+                          double *r, double *W, double *dW, cudaStream_t st);   // device pointers
+
+// scan.cu
+int exclusive_scan_i32(const int *in, int *out, size_t n, DevBuf &tmp, int *total_out_dev, cudaStream_t st,
+                       long long *launches);
+
+// pack/unpack helpers (misc.cu)
+void launch_pack2(const double *col_major, double2 *out, int n, cudaStream_t st);     // [n x 2] -> double2[n]
+void launch_unpack2(const double2 *in, double *col_major, int n, cudaStream_t st);
+void launch_pack4(const double *col_major, Mat2 *out, int n, cudaStream_t st);        // [n x 4] -> Mat2[n]
+void launch_unpack4(const Mat2 *in, double *col_major, int n, cudaStream_t st);
+
+}  // namespace sphb

@@ -1,0 +1,709 @@
+// context.cu -- the device-resident channel: state in HBM, neighbour CSR, one-call time steps.
+//
+// Restates the hot slice of SPH_Poiseuille.m (row S1 of SURVEY.md 8(a)): the main-loop body m:250-283
+// with verlet_time_step m:519-527, periodic_bounding m:570-577, sort_particles_by_cell m:529-568 and
+// the S5 initialisation m:165-173, as a fixed sequence of kernel launches on one stream; the time
+// step, max|v|, clock and monitors stay on the device (DevScalars), so a step needs no host round trip.
+#include "common.cuh"
+#include "ops_csr.cuh"
+#include "sort.cuh"
+
+#include <cmath>
+#include <limits>
+
+using namespace sphb;
+
+struct sphb_ctx {
+    sphb_params prm{};
+    PhysParams P{};
+    int device = 0;
+    cudaStream_t st = nullptr;
+    // state (+ alternates for the cell-sort permutation)
+    DevBuf pos, vel, vel_new, wall_vel, force, force_prior, rho, p, drho_dt, mass, Vol, B;
+    DevBuf a_pos, a_vel, a_wall_vel, a_force, a_force_prior, a_rho, a_p, a_drho_dt, a_mass, a_Vol, a_B;
+    DevBuf scalars, shear_partials, stage, prof;
+    NeighborWork nw;
+    SortWork sw;
+    bool have_list = false;
+    bool planned = false;
+    double y_lo = 0, y_hi = 0;
+    long long h_step = 0;        // host mirror of the step counter (sort cadence, m:272)
+    long long launches = 0;
+    // pinned host mirror for status read-back
+    DevScalars *h_scalars = nullptr;
+    int *h_ints = nullptr;
+    // phase timing
+    bool timing = false;
+    cudaEvent_t ev[8]{};
+    sphb_timing last_timing{};
+    // cached graphs for the dual-criteria schedule: [0] without, [1] with cell sort
+    cudaGraphExec_t graph[2]{nullptr, nullptr};
+    int graph_inner = -1;
+    long long graph_launches = 0;
+    long long outer_count = 0;
+
+    StateView view() const
+    {
+        StateView S;
+        S.pos = pos.as<double2>();
+        S.vel = vel.as<double2>();
+        S.vel_new = vel_new.as<double2>();
+        S.wall_vel = wall_vel.as<double2>();
+        S.force = force.as<double2>();
+        S.force_prior = force_prior.as<double2>();
+        S.rho = rho.as<double>();
+        S.p = p.as<double>();
+        S.drho_dt = drho_dt.as<double>();
+        S.mass = mass.as<double>();
+        S.Vol = Vol.as<double>();
+        S.B = B.as<Mat2>();
+        S.snap = nw.snap.as<double2>();
+        S.row_ptr = nw.row_ptr.as<int>();
+        S.col = nw.col.as<unsigned>();
+        return S;
+    }
+    DevScalars *sc() const { return scalars.as<DevScalars>(); }
+};
+
+namespace {
+
+__global__ void k_fill(double *p, double v, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_fill_identity(Mat2 *B, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        Mat2 m;
+        m.b11 = 1.0;
+        m.b12 = 0.0;
+        m.b21 = 0.0;
+        m.b22 = 1.0;
+        B[i] = m;
+    }
+}
+__global__ void k_vol_from_mass(const double *mass, const double *rho, double *Vol, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) Vol[i] = mass[i] / rho[i];   // m:120
+}
+__global__ void k_eos(const double *rho, double *p, int nf, int nt, double rho0, double p0)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nt) p[i] = i < nf ? p0 * (rho[i] / rho0 - 1.0) : 0.0;   // m:172-173
+}
+__global__ void k_set_clock(DevScalars *sc, double t, long long step)
+{
+    sc->t = t;
+    sc->step = step;
+}
+__global__ void k_zero_wall_vel(double2 *vel, int nf, int nt)
+{
+    const int i = nf + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nt) vel[i] = make_double2(0.0, 0.0);   // m:270
+}
+
+int bind_device(sphb_ctx *c)
+{
+    SPHB_CUDA(cudaSetDevice(c->device));
+    return 0;
+}
+
+void drop_graphs(sphb_ctx *c)
+{
+    for (int k = 0; k < 2; ++k) {
+        if (c->graph[k]) cudaGraphExecDestroy(c->graph[k]);
+        c->graph[k] = nullptr;
+    }
+    c->graph_inner = -1;
+}
+
+int plan_lists(sphb_ctx *c, double y_lo, double y_hi)
+{
+    const sphb_params &p = c->prm;
+    SPHB_TRY(neighbor_plan(c->nw, p.n_fluid, p.n_total, p.h, p.DL, y_lo, y_hi, p.max_neighbors_hint));
+    SPHB_TRY(sort_plan(c->sw, p.n_fluid, p.DL, p.h, y_hi - y_lo));
+    c->planned = true;
+    c->y_lo = y_lo;
+    c->y_hi = y_hi;
+    return 0;
+}
+
+// ---- pieces of one step ------------------------------------------------------------------------
+int do_density(sphb_ctx *c)
+{
+    const StateView S = c->view();
+    SPHB_TRY(csr_density(c->P, S, c->st));
+    SPHB_TRY(csr_kgc(c->P, S, c->st));
+    c->launches += 2;
+    return 0;
+}
+
+int do_sort(sphb_ctx *c)
+{
+    const int nf = c->prm.n_fluid, nt = c->prm.n_total;
+    if (nf <= 0 || nf >= nt) return 0;   // m:535-537
+    SPHB_TRY(sort_permutation(c->sw, c->pos.as<double2>(), nf, c->prm.DL, c->prm.h, c->sc(), c->nw.flags.as<int>(),
+                              c->st, &c->launches));
+    PermuteArrays A;
+    DevBuf *in2[] = {&c->pos, &c->vel, &c->wall_vel, &c->force_prior, &c->force};
+    DevBuf *out2[] = {&c->a_pos, &c->a_vel, &c->a_wall_vel, &c->a_force_prior, &c->a_force};
+    DevBuf *in1[] = {&c->rho, &c->mass, &c->drho_dt, &c->p, &c->Vol};
+    DevBuf *out1[] = {&c->a_rho, &c->a_mass, &c->a_drho_dt, &c->a_p, &c->a_Vol};
+    for (int k = 0; k < PermuteArrays::kN2; ++k) {
+        A.in2[k] = in2[k]->as<double2>();
+        A.out2[k] = out2[k]->as<double2>();
+    }
+    for (int k = 0; k < PermuteArrays::kN1; ++k) {
+        A.in1[k] = in1[k]->as<double>();
+        A.out1[k] = out1[k]->as<double>();
+    }
+    A.inB = c->B.as<Mat2>();
+    A.outB = c->a_B.as<Mat2>();
+    SPHB_TRY(sort_apply(c->sw, nf, nt, A, c->st, &c->launches));
+    for (int k = 0; k < PermuteArrays::kN2; ++k) std::swap(*in2[k], *out2[k]);
+    for (int k = 0; k < PermuteArrays::kN1; ++k) std::swap(*in1[k], *out1[k]);
+    std::swap(c->B, c->a_B);
+    c->have_list = false;
+    return 0;
+}
+
+int do_neighbor(sphb_ctx *c)
+{
+    SPHB_TRY(neighbor_build(c->nw, c->pos.as<double2>(), true, c->st, &c->launches));
+    c->have_list = true;
+    return 0;
+}
+
+int do_shear(sphb_ctx *c)
+{
+    SPHB_TRY(csr_wall_shear(c->P, c->view(), c->sc(), c->shear_partials.as<double>(), c->st));
+    c->launches += 2;
+    return 0;
+}
+
+int do_substep(sphb_ctx *c, double remain, double fixed_dt, bool wrap)
+{
+    const StateView S = c->view();
+    SPHB_TRY(csr_time_step(c->P, c->sc(), remain, fixed_dt, c->st));
+    SPHB_TRY(csr_pressure(c->P, S, c->sc(), c->st));
+    SPHB_TRY(csr_continuity(c->P, S, c->sc(), wrap, c->st));
+    SPHB_TRY(csr_advance_clock(c->sc(), c->st));
+    c->launches += 4;
+    return 0;
+}
+
+void tick(sphb_ctx *c, int k)
+{
+    if (c->timing) cudaEventRecord(c->ev[k], c->st);
+}
+
+}  // namespace
+
+extern "C" {
+
+SPHB_API int sphb_ctx_create(const sphb_params *prm, sphb_ctx **out)
+{
+    clear_error();
+    if (!prm || !out) return set_error("SPHB:arg", "null argument");
+    *out = nullptr;
+    SPHB_REQUIRE(prm->n_total > 0 && prm->n_fluid > 0 && prm->n_fluid <= prm->n_total, "SPH:Neighbor:count",
+                 "Invalid n_fluid/n_total or inconsistent pos size.");
+    SPHB_REQUIRE(prm->h > 0.0 && prm->DL > 0.0, "SPH:Neighbor:param", "h and DL must be positive.");
+    SPHB_REQUIRE(prm->rho0 > 0.0, "SPH:Physics:density:param", "rho0 and h must be positive.");
+    SPHB_TRY(ensure_device());
+    sphb_ctx *c = new sphb_ctx();
+    c->prm = *prm;
+    if (prm->device >= 0) c->device = prm->device;
+    else if (cudaGetDevice(&c->device) != cudaSuccess) c->device = 0;
+    int rc = [&]() -> int {
+        SPHB_TRY(bind_device(c));
+        SPHB_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+        const size_t nt = (size_t)prm->n_total;
+        PhysParams &P = c->P;
+        P.nf = prm->n_fluid;
+        P.nt = prm->n_total;
+        P.h = prm->h;
+        P.DL = prm->DL;
+        P.DH = prm->DH;
+        P.rho0 = prm->rho0;
+        P.p0 = prm->p0;
+        P.c_f = prm->c_f;
+        P.mu = prm->mu;
+        P.nu = prm->mu / prm->rho0;   // m:80
+        P.g = prm->gravity_g;
+        P.inv_sigma0 = prm->inv_sigma0;
+        P.transport_coeff = prm->transport_coeff;
+        P.sigma = 10.0 / (7.0 * 3.14159265358979323846 * prm->h * prm->h);
+        DevBuf *v2[] = {&c->pos, &c->vel, &c->vel_new, &c->wall_vel, &c->force, &c->force_prior,
+                        &c->a_pos, &c->a_vel, &c->a_wall_vel, &c->a_force, &c->a_force_prior};
+        for (DevBuf *b : v2) {
+            SPHB_TRY(b->reserve(nt * sizeof(double2)));
+            SPHB_CUDA(cudaMemsetAsync(b->p, 0, nt * sizeof(double2), c->st));
+        }
+        DevBuf *v1[] = {&c->rho, &c->p, &c->drho_dt, &c->mass, &c->Vol, &c->a_rho, &c->a_p, &c->a_drho_dt,
+                        &c->a_mass, &c->a_Vol};
+        for (DevBuf *b : v1) {
+            SPHB_TRY(b->reserve(nt * sizeof(double)));
+            SPHB_CUDA(cudaMemsetAsync(b->p, 0, nt * sizeof(double), c->st));
+        }
+        SPHB_TRY(c->B.reserve(nt * sizeof(Mat2)));
+        SPHB_TRY(c->a_B.reserve(nt * sizeof(Mat2)));
+        SPHB_TRY(c->scalars.reserve(sizeof(DevScalars)));
+        SPHB_CUDA(cudaMemsetAsync(c->scalars.p, 0, sizeof(DevScalars), c->st));
+        SPHB_TRY(c->shear_partials.reserve(2 * (size_t)kShearPartialBlocks * sizeof(double)));
+        SPHB_TRY(c->stage.reserve(4 * nt * sizeof(double)));
+        k_fill<<<grid_for(nt), kBlock, 0, c->st>>>(c->rho.as<double>(), prm->rho0, (int)nt);
+        k_fill_identity<<<grid_for(nt), kBlock, 0, c->st>>>(c->B.as<Mat2>(), (int)nt);
+        SPHB_CUDA(cudaMallocHost((void **)&c->h_scalars, sizeof(DevScalars)));
+        SPHB_CUDA(cudaMallocHost((void **)&c->h_ints, 8 * sizeof(int)));
+        for (auto &e : c->ev) SPHB_CUDA(cudaEventCreate(&e));
+        SPHB_CUDA(cudaStreamSynchronize(c->st));
+        return 0;
+    }();
+    if (rc) {
+        sphb_ctx_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+
+SPHB_API void sphb_ctx_destroy(sphb_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->st) cudaStreamSynchronize(c->st);
+    drop_graphs(c);
+    DevBuf *all[] = {&c->pos, &c->vel, &c->vel_new, &c->wall_vel, &c->force, &c->force_prior, &c->rho, &c->p,
+                     &c->drho_dt, &c->mass, &c->Vol, &c->B, &c->a_pos, &c->a_vel, &c->a_wall_vel, &c->a_force,
+                     &c->a_force_prior, &c->a_rho, &c->a_p, &c->a_drho_dt, &c->a_mass, &c->a_Vol, &c->a_B,
+                     &c->scalars, &c->shear_partials, &c->stage, &c->prof};
+    for (DevBuf *b : all) b->release();
+    c->nw.release_all();
+    c->sw.release_all();
+    if (c->h_scalars) cudaFreeHost(c->h_scalars);
+    if (c->h_ints) cudaFreeHost(c->h_ints);
+    for (auto &e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+}
+
+SPHB_API int sphb_ctx_upload(sphb_ctx *c, const double *pos, const double *vel, const double *rho,
+                             const double *drho_dt, const double *mass, const double *wall_vel)
+{
+    clear_error();
+    if (!c) return set_error("SPHB:arg", "null context");
+    SPHB_TRY(bind_device(c));
+    const int nt = c->prm.n_total;
+    const size_t n = (size_t)nt;
+    double *stage = c->stage.as<double>();
+    auto up2 = [&](const double *src, DevBuf &dst) -> int {
+        SPHB_CUDA(cudaMemcpyAsync(stage, src, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        launch_pack2(stage, dst.as<double2>(), nt, c->st);
+        SPHB_CUDA(cudaStreamSynchronize(c->st));   // `stage` is reused by the next array
+        return 0;
+    };
+    if (pos) {
+        SPHB_TRY(up2(pos, c->pos));
+        double lo = pos[n], hi = pos[n];
+        for (size_t i = 1; i < n; ++i) {   // capacity planning only; the grid itself is derived on the device
+            lo = pos[n + i] < lo ? pos[n + i] : lo;
+            hi = pos[n + i] > hi ? pos[n + i] : hi;
+        }
+        if (!c->planned || lo < c->y_lo || hi > c->y_hi) {
+            drop_graphs(c);
+            SPHB_TRY(plan_lists(c, lo, hi));
+        }
+        c->have_list = false;
+    }
+    if (vel) SPHB_TRY(up2(vel, c->vel));
+    if (wall_vel) SPHB_TRY(up2(wall_vel, c->wall_vel));
+    if (rho) SPHB_CUDA(cudaMemcpyAsync(c->rho.p, rho, n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    if (drho_dt) SPHB_CUDA(cudaMemcpyAsync(c->drho_dt.p, drho_dt, n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    if (mass) SPHB_CUDA(cudaMemcpyAsync(c->mass.p, mass, n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    if (mass || rho)
+        k_vol_from_mass<<<grid_for(n), kBlock, 0, c->st>>>(c->mass.as<double>(), c->rho.as<double>(),
+                                                           c->Vol.as<double>(), nt);
+    if (vel) SPHB_TRY(csr_vmax(c->P, c->vel.as<double2>(), c->sc(), c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+SPHB_API int sphb_ctx_download(sphb_ctx *c, double *pos, double *vel, double *rho, double *p, double *drho_dt,
+                               double *force, double *force_prior, double *Vol, double *B)
+{
+    clear_error();
+    if (!c) return set_error("SPHB:arg", "null context");
+    SPHB_TRY(bind_device(c));
+    const int nt = c->prm.n_total;
+    const size_t n = (size_t)nt;
+    double *stage = c->stage.as<double>();
+    auto down2 = [&](const DevBuf &src, double *dst) -> int {
+        launch_unpack2(src.as<double2>(), stage, nt, c->st);
+        SPHB_CUDA(cudaMemcpyAsync(dst, stage, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        SPHB_CUDA(cudaStreamSynchronize(c->st));
+        return 0;
+    };
+    if (pos) SPHB_TRY(down2(c->pos, pos));
+    if (vel) SPHB_TRY(down2(c->vel, vel));
+    if (force) SPHB_TRY(down2(c->force, force));
+    if (force_prior) SPHB_TRY(down2(c->force_prior, force_prior));
+    if (B) {
+        launch_unpack4(c->B.as<Mat2>(), stage, nt, c->st);
+        SPHB_CUDA(cudaMemcpyAsync(B, stage, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        SPHB_CUDA(cudaStreamSynchronize(c->st));
+    }
+    if (rho) SPHB_CUDA(cudaMemcpyAsync(rho, c->rho.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    if (p) SPHB_CUDA(cudaMemcpyAsync(p, c->p.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    if (drho_dt) SPHB_CUDA(cudaMemcpyAsync(drho_dt, c->drho_dt.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    if (Vol) SPHB_CUDA(cudaMemcpyAsync(Vol, c->Vol.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+SPHB_API int sphb_ctx_set_time(sphb_ctx *c, double t, long long step)
+{
+    clear_error();
+    if (!c) return set_error("SPHB:arg", "null context");
+    SPHB_TRY(bind_device(c));
+    k_set_clock<<<1, 1, 0, c->st>>>(c->sc(), t, step);
+    c->h_step = step;
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+SPHB_API int sphb_ctx_neighbor_build(sphb_ctx *c)
+{
+    clear_error();
+    if (!c) return set_error("SPHB:arg", "null context");
+    SPHB_TRY(bind_device(c));
+    if (!c->planned) return set_error("SPHB:state", "upload positions before building the neighbour list");
+    return do_neighbor(c);
+}
+
+SPHB_API int sphb_ctx_neighbor_count(sphb_ctx *c, size_t *n_half, size_t *n_csr)
+{
+    clear_error();
+    if (!c) return set_error("SPHB:arg", "null context");
+    SPHB_TRY(bind_device(c));
+    if (!c->have_list) return set_error("SPHB:state", "no neighbour list");
+    SPHB_CUDA(cudaMemcpyAsync(c->h_ints, c->nw.totals.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaMemcpyAsync(c->h_ints + 2, c->nw.flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    if (n_half) *n_half = (size_t)c->h_ints[0];
+    if (n_csr) *n_csr = (size_t)c->h_ints[1];
+    if (c->h_ints[2] & (kErrCsrCap | kErrCellCap | kErrSeenCap))
+        return set_error("SPH:Neighbor:entryCapacity", "neighbour list capacity exceeded (flags=%d)", c->h_ints[2]);
+    return 0;
+}
+
+SPHB_API int sphb_ctx_neighbor_export_pairs(sphb_ctx *c, double *pair_i, double *pair_j, double *dx, double *dy,
+                                            double *r, double *W, double *dW)
+{
+    clear_error();
+    size_t nh = 0;
+    SPHB_TRY(sphb_ctx_neighbor_count(c, &nh, nullptr));
+    if (nh == 0) return 0;
+    DevBuf tmp;
+    SPHB_TRY(tmp.reserve(7 * nh * sizeof(double)));
+    double *d = tmp.as<double>();
+    int rc = neighbor_export_pairs(c->nw, nh, d, d + nh, d + 2 * nh, d + 3 * nh, d + 4 * nh, d + 5 * nh, d + 6 * nh,
+                                   c->st);
+    double *dst[7] = {pair_i, pair_j, dx, dy, r, W, dW};
+    for (int k = 0; k < 7 && !rc; ++k) {
+        if (!dst[k]) continue;
+        if (cudaMemcpyAsync(dst[k], d + k * nh, nh * sizeof(double), cudaMemcpyDeviceToHost, c->st) != cudaSuccess)
+            rc = set_error("SPHB:cuda", "pair export copy failed");
+    }
+    if (cudaStreamSynchronize(c->st) != cudaSuccess && !rc) rc = set_error("SPHB:cuda", "pair export failed");
+    c->launches += 1;
+    tmp.release();
+    return rc;
+}
+
+SPHB_API int sphb_ctx_neighbor_export_csr(sphb_ctx *c, int *row_ptr, int *col)
+{
+    clear_error();
+    size_t nc = 0;
+    SPHB_TRY(sphb_ctx_neighbor_count(c, nullptr, &nc));
+    const size_t nf = (size_t)c->prm.n_fluid;
+    if (row_ptr)
+        SPHB_CUDA(cudaMemcpyAsync(row_ptr, c->nw.row_ptr.p, (nf + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    if (col && nc)
+        SPHB_CUDA(cudaMemcpyAsync(col, c->nw.col.p, nc * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    if (col)
+        for (size_t k = 0; k < nc; ++k) col[k] &= 0x3fffffff;   // strip the periodic-image code
+    return 0;
+}
+
+#define CTX_ENTER(need_list)                                                                   \
+    clear_error();                                                                             \
+    if (!c) return set_error("SPHB:arg", "null context");                                      \
+    SPHB_TRY(bind_device(c));                                                                  \
+    if ((need_list) && !c->have_list) return set_error("SPHB:state", "no neighbour list: call sphb_ctx_neighbor_build")
+
+SPHB_API int sphb_ctx_density_correction(sphb_ctx *c)
+{
+    CTX_ENTER(true);
+    return do_density(c);
+}
+
+SPHB_API int sphb_ctx_eos(sphb_ctx *c)
+{
+    CTX_ENTER(false);
+    k_eos<<<grid_for(c->prm.n_total), kBlock, 0, c->st>>>(c->rho.as<double>(), c->p.as<double>(), c->prm.n_fluid,
+                                                          c->prm.n_total, c->prm.rho0, c->prm.p0);
+    c->launches += 1;
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+SPHB_API int sphb_ctx_viscous_force(sphb_ctx *c, int add_gravity)
+{
+    CTX_ENTER(true);
+    c->launches += 1;
+    return csr_visc_transport(c->P, c->view(), true, add_gravity != 0, false, c->st);
+}
+
+SPHB_API int sphb_ctx_transport_correction(sphb_ctx *c)
+{
+    CTX_ENTER(true);
+    c->launches += 1;
+    return csr_visc_transport(c->P, c->view(), false, false, true, c->st);
+}
+
+SPHB_API int sphb_ctx_integration_verlet(sphb_ctx *c, double dt)
+{
+    CTX_ENTER(true);
+    const StateView S = c->view();
+    SPHB_TRY(csr_time_step(c->P, c->sc(), std::numeric_limits<double>::infinity(), dt, c->st));
+    SPHB_TRY(csr_pressure(c->P, S, c->sc(), c->st));
+    SPHB_TRY(csr_continuity(c->P, S, c->sc(), false, c->st));
+    c->launches += 3;
+    return 0;
+}
+
+SPHB_API int sphb_ctx_wall_shear(sphb_ctx *c, double *tau_bottom, double *tau_top)
+{
+    CTX_ENTER(true);
+    SPHB_TRY(do_shear(c));
+    SPHB_CUDA(cudaMemcpyAsync(c->h_scalars, c->sc(), sizeof(DevScalars), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    if (tau_bottom) *tau_bottom = c->h_scalars->tau_bottom;
+    if (tau_top) *tau_top = c->h_scalars->tau_top;
+    return 0;
+}
+
+SPHB_API int sphb_ctx_periodic_wrap(sphb_ctx *c)
+{
+    CTX_ENTER(false);
+    c->launches += 1;
+    return csr_wrap(c->P, c->pos.as<double2>(), c->st);
+}
+
+SPHB_API int sphb_ctx_sort_by_cell(sphb_ctx *c)
+{
+    CTX_ENTER(false);
+    if (!c->planned) return set_error("SPHB:state", "upload positions first");
+    drop_graphs(c);
+    return do_sort(c);
+}
+
+SPHB_API int sphb_ctx_status(sphb_ctx *c, sphb_status *out)
+{
+    CTX_ENTER(false);
+    if (!out) return set_error("SPHB:arg", "null output");
+    SPHB_CUDA(cudaMemcpyAsync(c->h_scalars, c->sc(), sizeof(DevScalars), cudaMemcpyDeviceToHost, c->st));
+    c->h_ints[0] = c->h_ints[1] = c->h_ints[2] = 0;
+    if (c->planned) {
+        SPHB_CUDA(cudaMemcpyAsync(c->h_ints, c->nw.totals.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        SPHB_CUDA(cudaMemcpyAsync(c->h_ints + 2, c->nw.flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    }
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    SPHB_CUDA(cudaGetLastError());
+    out->t = c->h_scalars->t;
+    out->dt = c->h_scalars->dt;
+    out->vmax = c->h_scalars->vmax;
+    out->tau_bottom = c->h_scalars->tau_bottom;
+    out->tau_top = c->h_scalars->tau_top;
+    out->step = c->h_scalars->step;
+    out->n_half_pairs = c->have_list ? c->h_ints[0] : 0;
+    out->n_csr_entries = c->have_list ? c->h_ints[1] : 0;
+    out->error_flags = c->h_ints[2];
+    return 0;
+}
+
+// One pass of the reference main-loop body, m:251-283.
+SPHB_API int sphb_ctx_step(sphb_ctx *c, double remain)
+{
+    CTX_ENTER(true);
+    const StateView S = c->view();
+    c->h_step += 1;
+    tick(c, 0);
+    SPHB_TRY(do_density(c));                                                          // m:254-255
+    tick(c, 1);
+    SPHB_TRY(csr_visc_transport(c->P, S, true, true, true, c->st));                   // m:256-257
+    c->launches += 1;
+    tick(c, 2);
+    SPHB_TRY(do_substep(c, remain, 0.0, true));                                       // m:259-269
+    tick(c, 3);
+    const int si = c->prm.sort_interval;
+    if (si > 0 && c->h_step % si == 0 && c->h_step != 1) SPHB_TRY(do_sort(c));        // m:272-278
+    tick(c, 4);
+    SPHB_TRY(do_neighbor(c));                                                         // m:280
+    tick(c, 5);
+    SPHB_TRY(do_shear(c));                                                            // m:281-283
+    tick(c, 6);
+    return 0;
+}
+
+SPHB_API int sphb_ctx_run_until(sphb_ctx *c, double t_target, double t_end, long long max_steps,
+                                long long *steps_done)
+{
+    CTX_ENTER(true);
+    long long n = 0;
+    sphb_status s;
+    SPHB_TRY(sphb_ctx_status(c, &s));
+    while (s.t < t_target - 1e-12 && (max_steps <= 0 || n < max_steps)) {   // m:250
+        const double remain = fmin(t_target - s.t, t_end - s.t);           // m:252
+        SPHB_TRY(sphb_ctx_step(c, remain));
+        SPHB_TRY(sphb_ctx_status(c, &s));
+        ++n;
+        if (s.error_flags) return set_error("SPHB:capacity", "device error flags %d at step %lld", s.error_flags, s.step);
+        if (s.dt < 1e-14) return set_error("SPHB:diverged", "time step collapsed (dt=%g) at t=%g step=%lld", s.dt, s.t, s.step);   // m:260-263
+    }
+    if (steps_done) *steps_done = n;
+    return 0;
+}
+
+namespace {
+
+int enqueue_outer(sphb_ctx *c, int n_inner, bool with_sort)
+{
+    const double inf = std::numeric_limits<double>::infinity();
+    SPHB_TRY(do_density(c));
+    SPHB_TRY(csr_visc_transport(c->P, c->view(), true, true, true, c->st));
+    c->launches += 1;
+    for (int s = 0; s < n_inner; ++s) SPHB_TRY(do_substep(c, inf, 0.0, true));
+    if (with_sort) SPHB_TRY(do_sort(c));
+    SPHB_TRY(do_neighbor(c));
+    SPHB_TRY(do_shear(c));
+    return 0;
+}
+
+}  // namespace
+
+// Dual-criteria schedule as a replayed CUDA graph (one graph per outer step).
+SPHB_API int sphb_ctx_run_dual(sphb_ctx *c, int n_outer, int n_inner)
+{
+    CTX_ENTER(true);
+    if (n_inner < 1 || n_outer < 0) return set_error("SPHB:arg", "n_inner >= 1 and n_outer >= 0 required");
+    const int si = c->prm.sort_interval;
+    if (c->graph_inner != n_inner) drop_graphs(c);
+    for (int o = 0; o < n_outer; ++o) {
+        c->outer_count += 1;
+        const bool with_sort = si > 0 && c->outer_count % si == 0 && c->outer_count != 1;
+        if (with_sort) {
+            // the permutation swaps buffer pointers: run eagerly, then re-capture on the new pointers
+            drop_graphs(c);
+            SPHB_TRY(enqueue_outer(c, n_inner, true));
+            continue;
+        }
+        if (!c->graph[0]) {
+            const long long l0 = c->launches;
+            cudaGraph_t g = nullptr;
+            SPHB_CUDA(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+            int rc = enqueue_outer(c, n_inner, false);
+            cudaError_t e = cudaStreamEndCapture(c->st, &g);
+            if (rc) {
+                if (g) cudaGraphDestroy(g);
+                return rc;
+            }
+            if (e != cudaSuccess) return set_error("SPHB:cuda", "graph capture failed: %s", cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&c->graph[0], g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return set_error("SPHB:cuda", "graph instantiate failed: %s", cudaGetErrorString(e));
+            c->graph_inner = n_inner;
+            c->graph_launches = c->launches - l0;
+            c->launches = l0;
+        }
+        SPHB_CUDA(cudaGraphLaunch(c->graph[0], c->st));
+        c->launches += c->graph_launches;
+    }
+    c->h_step += (long long)n_outer * n_inner;
+    return 0;
+}
+
+SPHB_API int sphb_ctx_profile(sphb_ctx *c, double x0, double half_width, int n_bins, double *u_mean, double *count)
+{
+    CTX_ENTER(false);
+    if (n_bins < 1 || !u_mean) return set_error("SPHB:arg", "bad profile arguments");
+    std::vector<double> edges((size_t)n_bins + 1), host(2 * (size_t)n_bins);
+    for (int k = 0; k <= n_bins; ++k)   // linspace(0, DH, n_bins + 1), m:581
+        edges[k] = (k == n_bins) ? c->prm.DH : 0.0 + (double)k * ((c->prm.DH - 0.0) / (double)n_bins);
+    SPHB_TRY(c->prof.reserve((3 * (size_t)n_bins + 1) * sizeof(double)));
+    double *d_edges = c->prof.as<double>(), *d_sum = d_edges + n_bins + 1, *d_cnt = d_sum + n_bins;
+    SPHB_CUDA(cudaMemcpyAsync(d_edges, edges.data(), edges.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    SPHB_CUDA(cudaMemsetAsync(d_sum, 0, 2 * (size_t)n_bins * sizeof(double), c->st));
+    SPHB_TRY(csr_profile(c->P, c->view(), x0, half_width, n_bins, d_edges, d_sum, d_cnt, c->st));
+    c->launches += 1;
+    SPHB_CUDA(cudaMemcpyAsync(host.data(), d_sum, host.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    for (int k = 0; k < n_bins; ++k) {
+        const double cnt = host[(size_t)n_bins + k];
+        u_mean[k] = cnt > 0.0 ? host[k] / cnt : std::numeric_limits<double>::quiet_NaN();   // m:588-589
+        if (count) count[k] = cnt;
+    }
+    return 0;
+}
+
+SPHB_API int sphb_ctx_enable_timing(sphb_ctx *c, int on)
+{
+    CTX_ENTER(false);
+    c->timing = on != 0;
+    return 0;
+}
+
+SPHB_API int sphb_ctx_timing(sphb_ctx *c, sphb_timing *out)
+{
+    CTX_ENTER(false);
+    if (!out) return set_error("SPHB:arg", "null output");
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    sphb_timing t{};
+    if (c->timing) {
+        float ms[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < 6; ++k)
+            if (cudaEventElapsedTime(&ms[k], c->ev[k], c->ev[k + 1]) != cudaSuccess) {
+                ms[k] = 0.f;
+                (void)cudaGetLastError();
+            }
+        t.density_ms = ms[0];
+        t.visc_transport_ms = ms[1];
+        t.verlet_ms = ms[2];
+        t.sort_ms = ms[3];
+        t.neighbor_ms = ms[4];
+        t.shear_ms = ms[5];
+        t.total_ms = ms[0] + ms[1] + ms[2] + ms[3] + ms[4] + ms[5];
+    }
+    t.launches = c->launches;
+    *out = t;
+    return 0;
+}
+
+SPHB_API void *sphb_ctx_stream(sphb_ctx *c) { return c ? (void *)c->st : nullptr; }
+
+SPHB_API int sphb_ctx_sync(sphb_ctx *c)
+{
+    CTX_ENTER(false);
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

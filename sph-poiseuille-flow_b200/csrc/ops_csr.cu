@@ -1,0 +1,560 @@
+// ops_csr.cu -- fp64 physics operators of the DEVICE-RESIDENT path as per-particle gathers over the
+// CSR neighbour list (rows P1-P9 and the epilogues of S1 in SURVEY.md 8(a)).
+//
+// One thread owns one particle and walks its CSR row; every pair is therefore evaluated from both
+// ends, there are no atomics and the sums are deterministic.  All the reference's pair formulas are
+// symmetric under (i <-> j, e -> -e) (ph:262-291, 502-520, 667-685, 891-925, 1091-1099), so the
+// gather uses one formula per entry with e pointing from j to i.
+//
+// Geometry is FROZEN at list-build time, as in the reference, where every mode consumes the pair
+// cache computed by the neighbour search: dx = (x_i - x_j) + shift*DL from the
+// position snapshot `snap` and the image code stored in the top two bits of each CSR entry.
+//
+// Fusion: viscous + transport share one row walk (same inputs B_j, Vol_j); the pressure kernel
+// recomputes the neighbour's half-step density/pressure inline (ph:857-862) and its epilogue does the
+// velocity kick and the full position update (ph:1400-1404, 863-864, 1066-1069); the continuity
+// kernel's epilogue finishes density/EOS (ph:1440-1446), wraps x (m:570-577) and feeds the grid-wide
+// max|v| reduction (warp shuffle + one atomicMax per warp) that the next dt is computed from on the
+// device (m:519-527).
+#include "ops_csr.cuh"
+#include "physmath.cuh"
+
+namespace sphb {
+
+namespace {
+
+constexpr unsigned kIdMask = 0x3fffffffu;
+
+struct Geo {
+    double dx, dy, r;
+};
+
+__device__ __forceinline__ Geo pair_geometry(double2 pi, double2 pj, unsigned entry, double DL)
+{
+    Geo g;
+    const double sh = (double)((int)(entry >> 30) - 1);
+    g.dx = (pi.x - pj.x) + sh * DL;
+    g.dy = pi.y - pj.y;
+    g.r = sqrt(g.dx * g.dx + g.dy * g.dy);
+    return g;
+}
+
+// cubic spline, nb:116-133 (r < 2h is guaranteed by the list)
+__device__ __forceinline__ double spline_W(double r, double h, double sigma)
+{
+    const double q = r / h;
+    if (q < 1.0) return sigma * (1.0 - 1.5 * q * q + 0.75 * q * q * q);
+    const double t = 2.0 - q;
+    return t > 0.0 ? sigma * 0.25 * t * t * t : 0.0;
+}
+__device__ __forceinline__ double spline_dW(double r, double h, double sigma)
+{
+    const double q = r / h;
+    if (q < 1.0) return sigma * (-3.0 * q + 2.25 * q * q) / h;
+    const double t = 2.0 - q;
+    return t > 0.0 ? -sigma * 0.75 * t * t / h : 0.0;
+}
+
+// ---------------------------------------------------------------- P1 pass 1: sigma sums -> rho, Vol
+__global__ void __launch_bounds__(kBlock) k_density(PhysParams P, StateView S)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.nt) return;
+    const double m_i = S.mass[i];
+    if (i >= P.nf) {   // wall rows: rho = rho0 (ph:214-216), Vol = m/rho0
+        S.rho[i] = P.rho0;
+        S.Vol[i] = m_i / P.rho0;
+        return;
+    }
+    const double2 pi = S.snap[i];
+    double s_in = P.sigma;   // W(0), ph:178-181
+    double s_ct = 0.0;
+    const int e = S.row_ptr[i + 1];
+    for (int k = S.row_ptr[i]; k < e; ++k) {
+        const unsigned c = S.col[k];
+        const int j = (int)(c & kIdMask);
+        const Geo g = pair_geometry(pi, S.snap[j], c, P.DL);
+        const double W = spline_W(g.r, P.h, P.sigma);
+        if (j < P.nf) s_in += W;
+        else s_ct += W * (S.mass[j] / P.rho0);
+    }
+    double rho = s_in * P.rho0 * P.inv_sigma0;
+    rho += s_ct * P.rho0 * P.rho0 * P.inv_sigma0 / m_i;
+    if (rho <= 1e-12) rho = P.rho0;
+    S.rho[i] = rho;
+    S.Vol[i] = m_i / rho;
+}
+
+// ---------------------------------------------------------------- P1 pass 2: A -> B (ph:239-366)
+__global__ void __launch_bounds__(kBlock) k_kgc(PhysParams P, StateView S)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.nt) return;
+    Mat2 B;
+    B.b11 = 1.0;
+    B.b12 = 0.0;
+    B.b21 = 0.0;
+    B.b22 = 1.0;
+    if (i < P.nf) {
+        const double2 pi = S.snap[i];
+        double a11 = 0.0, a12 = 0.0, a21 = 0.0, a22 = 0.0;
+        const int e = S.row_ptr[i + 1];
+        for (int k = S.row_ptr[i]; k < e; ++k) {
+            const unsigned c = S.col[k];
+            const int j = (int)(c & kIdMask);
+            const Geo g = pair_geometry(pi, S.snap[j], c, P.DL);
+            if (g.r <= 1e-12) continue;
+            const double f = spline_dW(g.r, P.h, P.sigma) * S.Vol[j];
+            const double ex = g.dx / g.r, ey = g.dy / g.r;
+            a11 -= g.dx * (f * ex);
+            a12 -= g.dx * (f * ey);
+            a21 -= g.dy * (f * ex);
+            a22 -= g.dy * (f * ey);
+        }
+        kgc_from_A(a11, a12, a21, a22, B.b11, B.b12, B.b21, B.b22);
+    }
+    S.B[i] = B;
+}
+
+// ---------------------------------------------------------------- P2 + P3 fused (ph:469-545, 636-710)
+template <bool VISC, bool TRANSP>
+__global__ void __launch_bounds__(kBlock) k_visc_transport(PhysParams P, StateView S, int add_gravity)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.nt) return;
+    if (i >= P.nf) {
+        if (VISC) S.force_prior[i] = make_double2(0.0, 0.0);
+        return;
+    }
+    const double2 pi = S.snap[i];
+    const double2 vi = S.vel[i];
+    const Mat2 Bi = S.B[i];
+    const double Vi = S.Vol[i];
+    double ax = 0.0, ay = 0.0, ix = 0.0, iy = 0.0;
+    const int e = S.row_ptr[i + 1];
+    for (int k = S.row_ptr[i]; k < e; ++k) {
+        const unsigned c = S.col[k];
+        const int j = (int)(c & kIdMask);
+        const Geo g = pair_geometry(pi, S.snap[j], c, P.DL);
+        if (g.r <= 1e-12) continue;
+        const double ex = g.dx / g.r, ey = g.dy / g.r;
+        const double dW = spline_dW(g.r, P.h, P.sigma);
+        const double Vj = S.Vol[j];
+        if (j < P.nf) {
+            const Mat2 Bj = S.B[j];
+            const double s11 = Bi.b11 + Bj.b11, s12 = Bi.b12 + Bj.b12;
+            const double s21 = Bi.b21 + Bj.b21, s22 = Bi.b22 + Bj.b22;
+            const double tx = s11 * ex + s12 * ey, ty = s21 * ex + s22 * ey;
+            if (VISC) {
+                const double2 vj = S.vel[j];
+                const double eBe = ex * tx + ey * ty;
+                const double cf = eBe * P.mu * dW * Vj / (g.r + 0.01 * P.h);
+                ax += cf * (vi.x - vj.x);
+                ay += cf * (vi.y - vj.y);
+            }
+            if (TRANSP) {
+                const double ci = -dW * Vj;
+                ix += ci * tx;
+                iy += ci * ty;
+            }
+        } else {
+            const double tx = Bi.b11 * ex + Bi.b12 * ey, ty = Bi.b21 * ex + Bi.b22 * ey;
+            if (VISC) {
+                const double2 wj = S.wall_vel[j];
+                const double eBe = ex * tx + ey * ty;
+                const double cf = 4.0 * eBe * P.mu * dW * Vj / (g.r + 0.01 * P.h);   // no-slip mirror, ph:526
+                ax += cf * (vi.x - wj.x);
+                ay += cf * (vi.y - wj.y);
+            }
+            if (TRANSP) {
+                const double ci = -2.0 * dW * Vj;   // ph:690
+                ix += ci * tx;
+                iy += ci * ty;
+            }
+        }
+    }
+    if (VISC) {
+        double fx = ax * Vi, fy = ay * Vi;
+        if (add_gravity) fx += S.mass[i] * P.g;   // m:392
+        S.force_prior[i] = make_double2(fx, fy);
+    }
+    if (TRANSP) {
+        const double n2 = ix * ix + iy * iy;
+        double lim = 100.0 * n2 / (P.h * P.h);
+        const double scale = P.transport_coeff * P.h * P.h;
+        if (lim > 1.0) lim = 1.0;
+        if (lim < 0.0) lim = 0.0;
+        double2 x = S.pos[i];
+        x.x += scale * lim * ix;
+        x.y += scale * lim * iy;
+        S.pos[i] = x;
+    }
+}
+
+// ---------------------------------------------------------------- dt on the device (m:519-527)
+__global__ void k_time_step(PhysParams P, DevScalars *sc, double remain, double fixed_dt)
+{
+    double dt;
+    if (fixed_dt > 0.0) {
+        dt = fixed_dt;
+    } else {
+        const double vmax = sc->vmax;
+        const double dt_a = 0.25 * P.h / fmax(P.c_f + vmax, 1e-12);
+        const double dt_v = 0.125 * P.h * P.h / fmax(P.nu, 1e-12);
+        const double dt_b = 0.25 * sqrt(P.h / fmax(fabs(P.g), 1e-12));
+        dt = fmin(fmin(dt_a, dt_v), fmin(dt_b, remain));
+        dt = fmax(dt, 1e-12);
+    }
+    sc->dt = dt;
+    sc->vmax_bits = 0ull;
+}
+
+__global__ void k_advance_clock(DevScalars *sc)
+{
+    sc->t += sc->dt;
+    sc->step += 1;
+    sc->vmax = __longlong_as_double((long long)sc->vmax_bits);
+}
+
+__device__ __forceinline__ double half_step_rho(double rho, double drho, double dt, double rho0)
+{
+    double r = rho + 0.5 * dt * drho;   // ph:858
+    if (r < 1e-10) r = rho0;            // ph:859-861
+    return r;
+}
+
+// ---------------------------------------------------------------- P4 + velocity kick + position update
+__global__ void __launch_bounds__(kBlock) k_pressure(PhysParams P, StateView S, const DevScalars *__restrict__ sc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.nt) return;
+    if (i >= P.nf) {   // wall rows: force 0, velocity 0 (ph:958-962, 1405-1408)
+        S.force[i] = make_double2(0.0, 0.0);
+        S.vel_new[i] = make_double2(0.0, 0.0);
+        return;
+    }
+    const double dt = sc->dt;
+    const double2 pi = S.snap[i];
+    const double2 vi = S.vel[i];
+    const Mat2 Bi = S.B[i];
+    const double Vi = S.Vol[i], m_i = S.mass[i];
+    const double2 fp = S.force_prior[i];
+    const double rho_i = half_step_rho(S.rho[i], S.drho_dt[i], dt, P.rho0);
+    const double p_i = P.p0 * (rho_i / P.rho0 - 1.0);   // ph:862
+    double fx = 0.0, fy = 0.0;
+    const int e = S.row_ptr[i + 1];
+    for (int k = S.row_ptr[i]; k < e; ++k) {
+        const unsigned c = S.col[k];
+        const int j = (int)(c & kIdMask);
+        const Geo g = pair_geometry(pi, S.snap[j], c, P.DL);
+        if (g.r <= 1e-12) continue;
+        const double ex = g.dx / g.r, ey = g.dy / g.r;
+        const double gj = spline_dW(g.r, P.h, P.sigma) * S.Vol[j];
+        if (j < P.nf) {
+            const double rho_j = half_step_rho(S.rho[j], S.drho_dt[j], dt, P.rho0);
+            const double p_j = P.p0 * (rho_j / P.rho0 - 1.0);
+            const double2 vj = S.vel[j];
+            const Mat2 Bj = S.B[j];
+            const double rho_bar = 0.5 * (rho_i + rho_j);
+            const double ul = vi.x * ex + vi.y * ey;
+            const double ur = vj.x * ex + vj.y * ey;
+            double comp = ul - ur;
+            if (comp < 0.0) comp = 0.0;
+            const double beta = fmin(3.0 * comp, P.c_f);   // ph:1121-1129
+            const double p_star = 0.5 * (p_i + p_j) + 0.5 * beta * rho_bar * (ul - ur);
+            const double p_face = 0.5 * (0.5 * (p_i + p_j) + p_star);
+            const double tx = p_face * ((Bi.b11 + Bj.b11) * ex + (Bi.b12 + Bj.b12) * ey);
+            const double ty = p_face * ((Bi.b21 + Bj.b21) * ex + (Bi.b22 + Bj.b22) * ey);
+            fx -= tx * gj;
+            fy -= ty * gj;
+        } else {
+            const double ax = fp.x / m_i, ay = fp.y / m_i;
+            const double ext = -(ax * ex + ay * ey);
+            const double pw = p_i + rho_i * g.r * fmax(0.0, ext);   // virtual wall pressure, ph:934
+            const double tx = Bi.b11 * ex + Bi.b12 * ey, ty = Bi.b21 * ex + Bi.b22 * ey;
+            fx -= (p_i + pw) * gj * tx;
+            fy -= (p_i + pw) * gj * ty;
+        }
+    }
+    fx *= Vi;
+    fy *= Vi;
+    S.force[i] = make_double2(fx, fy);
+    const double inv_m = 1.0 / m_i;
+    double2 vn;
+    vn.x = vi.x + (fp.x + fx) * inv_m * dt;   // ph:1402-1403
+    vn.y = vi.y + (fp.y + fy) * inv_m * dt;
+    S.vel_new[i] = vn;
+    double2 x = S.pos[i];
+    x.x += 0.5 * dt * vi.x;   // ph:863-864
+    x.y += 0.5 * dt * vi.y;
+    x.x += 0.5 * dt * vn.x;   // ph:1067-1068
+    x.y += 0.5 * dt * vn.y;
+    S.pos[i] = x;
+}
+
+__device__ __forceinline__ double wrap_x(double x, double DL)   // MATLAB mod(x, DL), m:573
+{
+    double m = fmod(x, DL);
+    if (m < 0.0) m += DL;
+    return m;
+}
+
+// ---------------------------------------------------------------- P5 + density/EOS finish + wrap + max|v|
+__global__ void __launch_bounds__(kBlock) k_continuity(PhysParams P, StateView S, DevScalars *sc, int do_wrap)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double speed = 0.0;
+    if (i < P.nf) {
+        const double dt = sc->dt;
+        const double2 pi = S.snap[i];
+        const double2 vi = S.vel_new[i];
+        double rate = 0.0;
+        const int e = S.row_ptr[i + 1];
+        for (int k = S.row_ptr[i]; k < e; ++k) {
+            const unsigned c = S.col[k];
+            const int j = (int)(c & kIdMask);
+            const Geo g = pair_geometry(pi, S.snap[j], c, P.DL);
+            if (g.r <= 1e-12) continue;
+            const double ex = g.dx / g.r, ey = g.dy / g.r;
+            const double gj = spline_dW(g.r, P.h, P.sigma) * S.Vol[j];
+            double u;
+            if (j < P.nf) {
+                const double2 vj = S.vel_new[j];
+                u = (vi.x - vj.x) * ex + (vi.y - vj.y) * ey;
+            } else {
+                const double2 wj = S.wall_vel[j];
+                const double mx = 2.0 * wj.x - vi.x, my = 2.0 * wj.y - vi.y;   // mirrored velocity, ph:1101-1102
+                u = (vi.x - mx) * ex + (vi.y - my) * ey;
+            }
+            rate += u * gj;
+        }
+        const double rho_h = half_step_rho(S.rho[i], S.drho_dt[i], dt, P.rho0);
+        const double drho = rate * rho_h;          // ph:1112
+        double rho = rho_h + drho * (0.5 * dt);    // ph:1441
+        if (rho < 1e-10) rho = P.rho0;
+        S.drho_dt[i] = drho;
+        S.rho[i] = rho;
+        S.p[i] = P.p0 * (rho / P.rho0 - 1.0);
+        if (do_wrap) {
+            double2 x = S.pos[i];
+            x.x = wrap_x(x.x, P.DL);
+            S.pos[i] = x;
+        }
+        S.vel[i] = vi;   // nobody reads `vel` in this kernel (neighbours read vel_new): commit in place
+        speed = sqrt(vi.x * vi.x + vi.y * vi.y);
+    } else if (i < P.nt) {
+        S.drho_dt[i] = 0.0;   // ph:1114-1116
+        S.p[i] = 0.0;         // ph:1449
+        S.vel[i] = make_double2(0.0, 0.0);   // ph:1405-1408, m:270
+    }
+    // grid-wide max |v| over fluid rows: warp shuffle, then one atomicMax per warp
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) speed = fmax(speed, __shfl_xor_sync(0xffffffffu, speed, d));
+    if ((threadIdx.x & 31) == 0 && speed > 0.0)
+        atomicMax(&sc->vmax_bits, (unsigned long long)__double_as_longlong(speed));
+}
+
+__global__ void __launch_bounds__(256) k_vmax(int nf, const double2 *__restrict__ vel, DevScalars *sc)
+{
+    double speed = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += gridDim.x * blockDim.x) {
+        const double2 v = vel[i];
+        speed = fmax(speed, sqrt(v.x * v.x + v.y * v.y));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) speed = fmax(speed, __shfl_xor_sync(0xffffffffu, speed, d));
+    if ((threadIdx.x & 31) == 0 && speed > 0.0)
+        atomicMax(&sc->vmax_bits, (unsigned long long)__double_as_longlong(speed));
+}
+__global__ void k_vmax_reset(DevScalars *sc) { sc->vmax_bits = 0ull; }
+__global__ void k_vmax_commit(DevScalars *sc) { sc->vmax = __longlong_as_double((long long)sc->vmax_bits); }
+
+__global__ void __launch_bounds__(kBlock) k_wrap(int nf, double DL, double2 *pos)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    double2 x = pos[i];
+    x.x = wrap_x(x.x, DL);
+    pos[i] = x;
+}
+
+// ---------------------------------------------------------------- P8 wall shear (ph:1713-1742)
+// Rows are sorted by j, so the wall entries (j >= n_fluid) sit at the end of each row.
+__global__ void __launch_bounds__(256) k_wall_shear(PhysParams P, StateView S, double *partials)
+{
+    double sb = 0.0, st = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.nf; i += gridDim.x * blockDim.x) {
+        const int s = S.row_ptr[i];
+        int k = S.row_ptr[i + 1] - 1;
+        if (k < s || (int)(S.col[k] & kIdMask) < P.nf) continue;
+        const double2 pi = S.snap[i];
+        const double vx = S.vel[i].x;
+        const Mat2 Bi = S.B[i];
+        const double Vi = S.Vol[i];
+        for (; k >= s; --k) {
+            const unsigned c = S.col[k];
+            const int j = (int)(c & kIdMask);
+            if (j < P.nf) break;
+            const double2 pj = S.snap[j];
+            const Geo g = pair_geometry(pi, pj, c, P.DL);
+            if (g.r <= 1e-12) continue;
+            const double ex = g.dx / g.r, ey = g.dy / g.r;
+            const double eBe = ex * (Bi.b11 * ex + Bi.b12 * ey) + ey * (Bi.b21 * ex + Bi.b22 * ey);
+            const double dvx = vx - S.wall_vel[j].x;
+            const double f = 4.0 * P.mu * eBe * spline_dW(g.r, P.h, P.sigma) * S.Vol[j] * dvx / (g.r + 0.01 * P.h) * Vi;
+            if (pj.y <= 0.0) sb += f;
+            else if (pj.y >= P.DH) st += f;
+        }
+    }
+    __shared__ double shb[256], sht[256];
+    shb[threadIdx.x] = sb;
+    sht[threadIdx.x] = st;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if (threadIdx.x < d) {
+            shb[threadIdx.x] += shb[threadIdx.x + d];
+            sht[threadIdx.x] += sht[threadIdx.x + d];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = shb[0];
+        partials[gridDim.x + blockIdx.x] = sht[0];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_wall_shear_final(const double *partials, int nblocks, double DL,
+                                                         DevScalars *sc)
+{
+    __shared__ double shb[256], sht[256];
+    double sb = 0.0, st = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) {
+        sb += partials[b];
+        st += partials[nblocks + b];
+    }
+    shb[threadIdx.x] = sb;
+    sht[threadIdx.x] = st;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if (threadIdx.x < d) {
+            shb[threadIdx.x] += shb[threadIdx.x + d];
+            sht[threadIdx.x] += sht[threadIdx.x + d];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        sc->tau_bottom = -shb[0] / DL;
+        sc->tau_top = -sht[0] / DL;
+    }
+}
+
+// ---------------------------------------------------------------- binned u(y) monitor (m:579-605)
+__global__ void __launch_bounds__(kBlock) k_profile(PhysParams P, StateView S, double x0, double half_width,
+                                                   int n_bins, const double *__restrict__ edges, double *sum,
+                                                   double *cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.nf) return;
+    const double2 x = S.pos[i];
+    if (x0 >= 0.0) {
+        const double xw = wrap_x(x.x, P.DL);
+        double d = fabs(xw - x0);
+        d = fmin(d, P.DL - d);
+        if (!(d <= half_width)) return;
+    }
+    const double y = x.y;
+    if (!(y >= edges[0] && y <= edges[n_bins])) return;   // discretize(): out of range dropped
+    int b = (int)floor((y - edges[0]) / (edges[n_bins] - edges[0]) * n_bins);
+    if (b < 0) b = 0;
+    if (b > n_bins - 1) b = n_bins - 1;
+    while (b > 0 && y < edges[b]) --b;
+    while (b < n_bins - 1 && y >= edges[b + 1]) ++b;
+    atomicAdd(&sum[b], S.vel[i].x);
+    atomicAdd(&cnt[b], 1.0);
+}
+
+}  // namespace
+
+// ================================================================================================
+int csr_density(const PhysParams &P, const StateView &S, cudaStream_t st)
+{
+    k_density<<<grid_for(P.nt), kBlock, 0, st>>>(P, S);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_kgc(const PhysParams &P, const StateView &S, cudaStream_t st)
+{
+    k_kgc<<<grid_for(P.nt), kBlock, 0, st>>>(P, S);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_visc_transport(const PhysParams &P, const StateView &S, bool do_visc, bool add_gravity, bool do_transport,
+                       cudaStream_t st)
+{
+    const unsigned g = grid_for(P.nt);
+    if (do_visc && do_transport) k_visc_transport<true, true><<<g, kBlock, 0, st>>>(P, S, add_gravity ? 1 : 0);
+    else if (do_visc) k_visc_transport<true, false><<<g, kBlock, 0, st>>>(P, S, add_gravity ? 1 : 0);
+    else if (do_transport) k_visc_transport<false, true><<<g, kBlock, 0, st>>>(P, S, 0);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_time_step(const PhysParams &P, DevScalars *sc, double remain, double fixed_dt, cudaStream_t st)
+{
+    k_time_step<<<1, 1, 0, st>>>(P, sc, remain, fixed_dt);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_pressure(const PhysParams &P, const StateView &S, const DevScalars *sc, cudaStream_t st)
+{
+    k_pressure<<<grid_for(P.nt), kBlock, 0, st>>>(P, S, sc);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool wrap, cudaStream_t st)
+{
+    k_continuity<<<grid_for(P.nt), kBlock, 0, st>>>(P, S, sc, wrap ? 1 : 0);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_advance_clock(DevScalars *sc, cudaStream_t st)
+{
+    k_advance_clock<<<1, 1, 0, st>>>(sc);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_vmax(const PhysParams &P, const double2 *vel, DevScalars *sc, cudaStream_t st)
+{
+    int blocks = (P.nf + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    k_vmax_reset<<<1, 1, 0, st>>>(sc);
+    k_vmax<<<blocks, 256, 0, st>>>(P.nf, vel, sc);
+    k_vmax_commit<<<1, 1, 0, st>>>(sc);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_wrap(const PhysParams &P, double2 *pos, cudaStream_t st)
+{
+    k_wrap<<<grid_for(P.nf), kBlock, 0, st>>>(P.nf, P.DL, pos);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_wall_shear(const PhysParams &P, const StateView &S, DevScalars *sc, double *partials, cudaStream_t st)
+{
+    int blocks = (P.nf + 255) / 256;
+    if (blocks > kShearPartialBlocks) blocks = kShearPartialBlocks;
+    if (blocks < 1) blocks = 1;
+    k_wall_shear<<<blocks, 256, 0, st>>>(P, S, partials);
+    k_wall_shear_final<<<1, 256, 0, st>>>(partials, blocks, P.DL, sc);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_profile(const PhysParams &P, const StateView &S, double x0, double half_width, int n_bins,
+                const double *edges_dev, double *sum_dev, double *cnt_dev, cudaStream_t st)
+{
+    k_profile<<<grid_for(P.nf), kBlock, 0, st>>>(P, S, x0, half_width, n_bins, edges_dev, sum_dev, cnt_dev);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace sphb

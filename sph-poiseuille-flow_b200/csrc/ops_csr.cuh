@@ -1,0 +1,53 @@
+// ops_csr.cuh -- device-resident state views and launchers of the CSR gather kernels (ops_csr.cu).
+#pragma once
+#include "common.cuh"
+
+namespace sphb {
+
+// Scalars that live in device memory so that no step needs a host round trip.
+struct DevScalars {
+    double t;
+    double dt;
+    double vmax;                    // max |v| over fluid rows, as of the last reduction
+    double tau_bottom, tau_top;
+    unsigned long long vmax_bits;   // running atomicMax target (bit image of a non-negative double)
+    long long step;
+    double y0_fluid;                // min fluid y (cell sort key origin, m:565)
+    long long y0_key;
+    long long pad;
+};
+
+struct PhysParams {
+    int nf, nt;
+    double h, DL, DH, rho0, p0, c_f, mu, nu, g, inv_sigma0, transport_coeff;
+    double sigma;    // 10/(7 pi h^2)
+};
+
+// SoA state in HBM.  2-vectors are double2 (one 128-bit load per particle), B is one 32-byte record.
+struct StateView {
+    double2 *pos, *vel, *vel_new, *wall_vel, *force, *force_prior;
+    double *rho, *p, *drho_dt, *mass, *Vol;
+    Mat2 *B;
+    // neighbour structures (frozen geometry = positions at list-build time)
+    const double2 *snap;
+    const int *row_ptr;
+    const unsigned *col;
+};
+
+int csr_density(const PhysParams &P, const StateView &S, cudaStream_t st);                       // P1 pass 1
+int csr_kgc(const PhysParams &P, const StateView &S, cudaStream_t st);                           // P1 pass 2
+int csr_visc_transport(const PhysParams &P, const StateView &S, bool do_visc, bool add_gravity, bool do_transport,
+                       cudaStream_t st);                                                         // P2 + P3
+// dt = min(acoustic, viscous, body, remain) from the device vmax (m:519-527); fixed_dt > 0 overrides
+int csr_time_step(const PhysParams &P, DevScalars *sc, double remain, double fixed_dt, cudaStream_t st);
+int csr_pressure(const PhysParams &P, const StateView &S, const DevScalars *sc, cudaStream_t st);    // P4 + kick
+int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool wrap, cudaStream_t st);  // P5 + finish
+int csr_advance_clock(DevScalars *sc, cudaStream_t st);                                          // t += dt, step++, vmax
+int csr_vmax(const PhysParams &P, const double2 *vel, DevScalars *sc, cudaStream_t st);          // standalone reduction
+int csr_wrap(const PhysParams &P, double2 *pos, cudaStream_t st);                                // m:570-577
+int csr_wall_shear(const PhysParams &P, const StateView &S, DevScalars *sc, double *partials, cudaStream_t st);  // P8
+int csr_profile(const PhysParams &P, const StateView &S, double x0, double half_width, int n_bins,
+                const double *edges_dev, double *sum_dev, double *cnt_dev, cudaStream_t st);
+constexpr int kShearPartialBlocks = 148 * 8;
+
+}  // namespace sphb
