@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- particle-substeps/s of the SPH particle loop (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--inner I] [--impl b200|reference]
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): the dp = 0.0025,
+DL = 3, DH = 1 periodic channel (480 000 fluid + 9 600 wall particles), seeded synthetic developed
+state.  One bench "step" = one OUTER step of the particle loop: kernel-sum density + KGC, viscous
+(+ body) force, transport-velocity shift, `--inner` acoustic Verlet substeps (device dt, immediate
+periodic wrap), [cell sort when due], neighbour-list rebuild, wall-shear monitor.  The default
+--inner 1 is exactly one pass of the reference main loop (SPH_Poiseuille.m:250-283), the only
+schedule the reference has at HEAD and -- at the reference's mu = 0.1 and dp = 0.0025, where the
+viscous limit 0.125 h^2/nu is below the acoustic one -- also what a dual-criteria scheduler
+degenerates to (freezing the viscous force over several substeps is unstable there).  A
+particle-substep is one integration_verlet application to one particle; value = n_total * inner *
+steps * ranks / time, so all outer-step work (list rebuild included) is amortised into the number.
+
+Multi-GPU (launched by torchrun, one rank per GPU): independent channels, one per rank, no
+data-path collective ("scaling": "weak").  Timing: CUDA events on the library's stream, barrier +
+synchronize on both sides, max over ranks.
+
+Lines printed: ONE JSON line on rank 0 (see the task contract: value, e2e, roofline, cpu_baseline,
+clocks, gpu_launches).  `--impl reference` times the reference's own OpenMP C code (oracle/_ref,
+built unmodified from the reference sources; the plain-C port when that is absent) on the host cores
+with the same schedule.  The oracle is used ONLY for that arm and for the cpu_baseline leg.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particle-substeps/s"
+ALG_BYTES_SUBSTEP = 184           # P6 contract, 112 B read + 72 B written per particle
+# per-particle algorithmic bytes of each kernel (inputs read once + outputs written once, fp64)
+ALG_BYTES_KERNEL = {
+    "pressure": 112 + 48,          # pos vel rho drho F_prior Vol B mass -> force, v_new, pos
+    "continuity": 56 + 56,         # v_new Vol rho drho pos -> rho p drho pos vel
+    "density": 24 + 16,            # snapshot pos, mass -> rho, Vol
+    "kgc": 24 + 32,                # snapshot pos, Vol -> B
+    "visc_transport": 88 + 32,     # vel Vol B pos wall_vel -> force_prior, pos
+    "nbr_walk_count": 16 + 8,      # snapshot pos -> two counts
+    "nbr_walk_fill": 16 + 86,      # pos -> ~20.5 x 4 B CSR + row pointer
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--inner", type=int, default=1, help="acoustic substeps per outer step (1 = reference loop)")
+    ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
+    ap.add_argument("--dp", type=float, default=0.0025)
+    ap.add_argument("--DL", type=float, default=3.0)
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--profile-steps", type=int, default=5)
+    ap.add_argument("--cpu-baseline-steps", type=int, default=2, help="outer steps of the CPU sample (0 = skip)")
+    ap.add_argument("--seed", type=int, default=12345)
+    return ap.parse_args()
+
+
+def load_product():
+    from __graft_entry__ import load_product as lp
+    return lp()
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def workload_name(cfg, pt, inner):
+    return (f"dp={cfg.dp:g} DL={cfg.DL:g} DH={cfg.DH:g} channel, {pt.n_fluid}+{pt.n_total - pt.n_fluid} particles, "
+            f"{inner} acoustic substeps per outer step")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md: sample DURING the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference (oracle/_ref or the port) on the same state and schedule
+# ------------------------------------------------------------------------------------------------
+def cpu_run(cfg, pt, inner, n_steps, n_warm):
+    """Times n_steps outer steps of the dual schedule through the CPU oracle.  Returns (particle-
+    substeps/s, kind, threads, seconds)."""
+    threads = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(threads)   # before libgomp loads
+    from oracle import host as H
+    if not (os.path.exists(H.REF_SO) or os.path.exists(H.PORT_SO)):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "all"], check=True, capture_output=True)
+    be = H.best_backend()
+    prm = H.derive_params(DL=cfg.DL, DH=cfg.DH, dp=cfg.dp, rho0=cfg.rho0, mu=cfg.mu, U_bulk=cfg.U_bulk, c_f=cfg.c_f,
+                          sort_interval=cfg.sort_interval, transport_coeff=cfg.transport_coeff)
+    st = H.init_particles(prm)
+    for f in ("pos", "vel", "rho", "drho_dt", "mass", "wall_vel"):
+        setattr(st, f, getattr(pt, f).copy(order="F"))
+    H.initialise(be, st, prm)
+    for _ in range(n_warm):
+        H.dual_outer_step(be, st, prm, inner)
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        H.dual_outer_step(be, st, prm, inner)
+    dt = time.perf_counter() - t0
+    return st.n_total * inner * n_steps / dt, be.kind, threads, dt
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    lp = load_product()
+    cfg = lp.ChannelConfig(DL=args.DL, dp=args.dp).derive()
+    # bounded sample: shrink the channel length (same dp, same physics, per-particle cost unchanged)
+    # until (steps + warmup) outer steps fit in ~150 s at ~1.2e-6 s per particle-substep-equivalent
+    DL = cfg.DL
+    est = lambda L: (args.steps + args.warmup) * (L / cfg.dp) * (cfg.DH / cfg.dp + 8) * (2.0e-6 + 0.35e-6 * args.inner)  # noqa: E731
+    while est(DL) > 150.0 and DL > 0.3:
+        DL *= 0.5
+    cfg_s = lp.ChannelConfig(DL=DL, dp=args.dp).derive()
+    pt = lp.channel_setup.developed(cfg_s, seed=args.seed)
+    value, kind, threads, secs = cpu_run(cfg_s, pt, args.inner, args.steps, args.warmup)
+    sample = (f"{args.steps} outer steps x {args.inner} substeps of the dp={cfg_s.dp:g} channel "
+              f"{'at full length' if DL == cfg.DL else f'shortened to DL={cfg_s.DL:g}'} ({pt.n_total} particles)")
+    full = lp.channel_setup.lattice(cfg)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "particle-substeps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(cfg, full, args.inner), "inner_substeps": args.inner,
+                   "list_rebuild": "every outer step", "parallelism": "OpenMP host threads"},
+        "cpu_baseline": {"value": value, "unit": "particle-substeps/s", "cores": threads, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "particle-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
+def b200_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (libsph_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    lp = load_product()
+    cfg = lp.ChannelConfig(DL=args.DL, dp=args.dp).derive()
+    pt = lp.channel_setup.developed(cfg, seed=args.seed + rank)     # one independent channel per rank
+    nt, inner, K, W = pt.n_total, args.inner, args.steps, args.warmup
+    ch = lp.channel_from_config(cfg, pt, device=local_rank)
+    ch.initialise()
+    stream = torch.cuda.ExternalStream(ch.stream, device=torch.device("cuda", local_rank))
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    # ---- device-resident throughput ----------------------------------------------------------------
+    ch.run_dual(max(W, 3), inner)
+    ch.sync()
+    l0 = ch.timing()["launches"]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    with torch.cuda.stream(stream):
+        for k in range(K):
+            if flush is not None:
+                flush.zero_()                     # > L2 (126 MB): the next step starts from HBM
+            ev[k][0].record(stream)
+            ch.run_dual(1, inner)
+            ev[k][1].record(stream)
+    ch.sync()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+    launches = ch.timing()["launches"] - l0
+    st = ch.status()
+    if st["error_flags"] or not np.isfinite(st["vmax"]) or st["vmax"] > 10 * cfg.U_max:
+        raise SystemExit(f"bench.py: run invalid (flags={st['error_flags']}, vmax={st['vmax']})")
+    value = world * nt * inner * K / (ms_total * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers --------------------------------------------
+    Ke = max(1, min(args.e2e_steps, K))
+    host = {k: torch.empty(shape, dtype=torch.float64).pin_memory().numpy()
+            for k, shape in (("pos", (2, nt)), ("vel", (2, nt)), ("rho", (nt,)), ("drho_dt", (nt,)))}
+    host = {k: (v.T if v.ndim == 2 else v) for k, v in host.items()}      # [nt, 2] column-major views
+    d = ch.download(("pos", "vel", "rho", "drho_dt"))
+    for k in host:
+        host[k][...] = d[k]
+    out_fields = ("pos", "vel", "rho", "p", "drho_dt", "force")
+
+    def e2e_step():
+        ch.upload(pos=host["pos"], vel=host["vel"], rho=host["rho"], drho_dt=host["drho_dt"])
+        ch.neighbor_build()
+        ch.run_dual(1, inner)
+        o = ch.download(out_fields)
+        for k in host:
+            host[k][...] = o[k]
+        return o
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * nt * inner * Ke / e2e_s
+    h2d = nt * (16 + 16 + 8 + 8)
+    d2h = nt * (16 + 16 + 8 + 8 + 8 + 16)
+
+    # ---- per-kernel device time, CUDA events on the launching stream (eager launches) --------------
+    roof = None
+    kernels = {}
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        ch.kernel_profile(enable=1, reset=True)
+        ch.run_dual(max(1, args.profile_steps), inner)
+        prof = ch.kernel_profile(enable=0, reset=True)
+        total = sum(ms for ms, _ in prof.values()) or 1.0
+        for name, (ms, calls) in prof.items():
+            if calls:
+                kernels[name] = {"ms_per_call": ms / calls, "calls": calls, "share": ms / total}
+        top = max((n for n in kernels if n in ALG_BYTES_KERNEL), key=lambda n: kernels[n]["share"])
+        per_launch_bytes = ALG_BYTES_KERNEL[top] * nt
+        achieved = per_launch_bytes / (kernels[top]["ms_per_call"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_particle": ALG_BYTES_KERNEL[top], "ms_per_launch": kernels[top]["ms_per_call"],
+                "share_of_step": kernels[top]["share"],
+                "step_frac": (value / world) * ALG_BYTES_SUBSTEP / (hbm * 1e9)}
+        # the Verlet substep alone (time_step + pressure + continuity + clock), outer-step work excluded
+        sub_ms = sum(kernels[n]["ms_per_call"] for n in ("time_step", "pressure", "continuity", "clock") if n in kernels)
+        roof["substep_kernels_only"] = {"ms": sub_ms, "value": nt / (sub_ms * 1e-3),
+                                        "frac": nt / (sub_ms * 1e-3) * ALG_BYTES_SUBSTEP / (hbm * 1e9)}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_baseline_steps > 0:
+        v, kind, threads, secs = cpu_run(cfg, pt, inner, args.cpu_baseline_steps, 1)
+        cpu = {"value": v, "unit": "particle-substeps/s", "cores": threads, "kind": kind,
+               "sample": f"{args.cpu_baseline_steps} outer steps x {inner} substeps of the same {nt}-particle state "
+                         f"({secs:.1f} s, 1 warm-up step)"}
+    total_launches = sum_over_ranks(float(launches))
+    ch.close()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "particle-substeps/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, pt, inner), "inner_substeps": inner,
+                       "list_rebuild": "every outer step (device counting sort + CSR)",
+                       "cell_sort_interval": cfg.sort_interval,
+                       "l2": ("256 MiB memset between timed steps" if flush is not None else
+                              "no flush: consecutive steps of one simulation"),
+                       "parallelism": f"{world} independent channel(s), one per GPU"},
+            "e2e": {"value": e2e_value, "unit": "particle-substeps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": Ke,
+                    "path": "sphb_ctx_upload -> neighbor_build -> run_dual(1, inner) -> sphb_ctx_download, pinned host"},
+            "gpu_launches": int(total_launches),
+            "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
+            "final_state": {"vmax": st["vmax"], "n_half_pairs": st["n_half_pairs"], "t": st["t"]},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -227,6 +227,20 @@ typedef struct sphb_timing {
 } sphb_timing;
 SPHB_API int sphb_ctx_timing(sphb_ctx *ctx, sphb_timing *out);
 SPHB_API int sphb_ctx_enable_timing(sphb_ctx *ctx, int on);
+/*
+ * Per-kernel device time of the resident path, measured with CUDA events recorded on the context's
+ * stream around every kernel (group) while enabled.  While enabled, sphb_ctx_run_dual launches its
+ * kernels eagerly instead of replaying a CUDA graph.  enable: 1 on, 0 off, -1 unchanged; reset != 0
+ * zeroes the accumulators after reporting.  `calls` counts timed scopes, not individual launches.
+ */
+#define SPHB_KPROF_SLOTS 24
+typedef struct sphb_kprof {
+    int n;                               /* slots in use */
+    const char *name[SPHB_KPROF_SLOTS];  /* static strings: "pressure", "continuity", "nbr_walk_fill", ... */
+    double ms[SPHB_KPROF_SLOTS];         /* accumulated device time */
+    long long calls[SPHB_KPROF_SLOTS];
+} sphb_kprof;
+SPHB_API int sphb_ctx_kernel_profile(sphb_ctx *ctx, int enable, int reset, sphb_kprof *out);
 /* The CUDA stream the context launches on (as a void* cudaStream_t), for event timing by callers. */
 SPHB_API void *sphb_ctx_stream(sphb_ctx *ctx);
 SPHB_API int sphb_ctx_sync(sphb_ctx *ctx);

@@ -105,6 +105,7 @@ class State:
     n_total: int
     t: float = 0.0
     step: int = 0
+    outer: int = 0          # outer-step counter of the dual-criteria schedule
     tau_bottom: float = 0.0
     tau_top: float = 0.0
     pairs: tuple | None = None   # (pair_i, pair_j, dx, dy, r, W, dW)
@@ -402,6 +403,47 @@ def reference_step(be, st: State, prm: Params, remain: float = math.inf, do_sort
                         nf, prm.DL, prm.DH, prm.mu, prm.h, nargout=2)
     st.tau_bottom, st.tau_top = float(np.ravel(tb)[0]), float(np.ravel(tt)[0])
     return dt
+
+
+def dual_outer_step(be, st: State, prm: Params, n_inner: int, do_sort: bool = True):
+    """One OUTER step of the dual-criteria schedule the reference README describes (README.md:61-65; no
+    code at HEAD, so this is a composition of the pinned operators, not a pinned schedule): density +
+    KGC, viscous (+ m g), transport on the current list, then `n_inner` integration_verlet substeps on
+    the SAME (frozen) pair list, each with dt = verlet_time_step(...) and an immediate periodic wrap,
+    then [cell sort], list rebuild, shear monitor.  n_inner = 1 is exactly reference_step(remain=inf).
+    Returns the list of inner dts."""
+    nf, nt = st.n_fluid, st.n_total
+    pi, pj, dx, dy, r, W, dW = st.pairs
+    st.rho, st.Vol, st.B = be.physics("density_correction", pi, pj, dx, dy, r, W, dW, st.mass, nf, nt,
+                                      prm.rho0, prm.h, prm.inv_sigma0, nargout=3)
+    (fp,) = be.physics("viscous_force", pi, pj, dx, dy, r, dW, st.vel, st.Vol, st.B, prm.mu, prm.h, nf, nt,
+                       st.mass, st.wall_vel, nargout=1)
+    fp[:nf, 0] = fp[:nf, 0] + st.mass[:nf] * prm.gravity_g
+    fp[nf:, :] = 0.0
+    st.force_prior = fp
+    (st.pos,) = be.physics("transport_correction", pi, pj, dx, dy, r, dW, st.Vol, st.B, st.pos, prm.h, nf, nt,
+                           prm.transport_coeff, nargout=1)
+    dts = []
+    for _ in range(n_inner):
+        dt = verlet_time_step(st.vel[:nf], prm.c_f, prm.h, prm.nu, prm.gravity_g, math.inf)
+        st.rho, st.p, st.pos, st.vel, st.drho_dt, st.force = be.physics(
+            "integration_verlet", pi, pj, dx, dy, r, dW, st.Vol, st.B, st.rho, st.mass, st.pos, st.vel, st.drho_dt,
+            st.force_prior, dt, nf, nt, prm.rho0, prm.p0, prm.c_f, st.wall_vel, nargout=6)
+        st.t += dt
+        st.step += 1
+        periodic_bounding(st.pos, nf, prm.DL)
+        st.vel[nf:, :] = 0.0
+        dts.append(dt)
+    st.outer += 1
+    if do_sort and prm.sort_interval > 0 and st.outer % prm.sort_interval == 0 and st.outer != 1:
+        perm = sort_permutation(st.pos, nf, nt, prm.DL, prm.h)
+        for name in ("pos", "vel", "rho", "mass", "wall_vel", "drho_dt", "force_prior", "force", "p", "Vol", "B"):
+            setattr(st, name, np.asfortranarray(getattr(st, name)[perm]))
+    pi, pj, dx, dy, r, W, dW = build_neighbor_cache(be, st, prm)
+    tb, tt = be.physics("wall_shear_monitor", pi, pj, dx, dy, r, dW, st.pos, st.vel, st.wall_vel, st.Vol, st.B,
+                        nf, prm.DL, prm.DH, prm.mu, prm.h, nargout=2)
+    st.tau_bottom, st.tau_top = float(np.ravel(tb)[0]), float(np.ravel(tt)[0])
+    return dts
 
 
 # ------------------------------------------------------------------------------------------------

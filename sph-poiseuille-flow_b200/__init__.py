@@ -25,6 +25,9 @@ from dataclasses import dataclass
 
 import numpy as np
 
+from . import channel_setup  # noqa: F401  (host-side set-up mirror of SPH_Poiseuille.m S2/S3)
+from .channel_setup import ChannelConfig  # noqa: F401
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsph_b200.so")
 
@@ -62,6 +65,10 @@ class _Timing(C.Structure):
     _fields_ = [("neighbor_ms", C.c_float), ("density_ms", C.c_float), ("visc_transport_ms", C.c_float),
                 ("verlet_ms", C.c_float), ("shear_ms", C.c_float), ("sort_ms", C.c_float), ("total_ms", C.c_float),
                 ("launches", C.c_longlong)]
+
+
+class _KProf(C.Structure):
+    _fields_ = [("n", C.c_int), ("name", C.c_char_p * 24), ("ms", C.c_double * 24), ("calls", C.c_longlong * 24)]
 
 
 _lib = None
@@ -429,9 +436,27 @@ class Channel:
     def sync(self):
         _check(lib().sphb_ctx_sync(self._ctx))
 
+    def kernel_profile(self, enable: int = -1, reset: bool = False) -> dict:
+        """Per-kernel device time (CUDA events on the context stream): {name: (ms_total, calls)}."""
+        k = _KProf()
+        _check(lib().sphb_ctx_kernel_profile(self._ctx, C.c_int(enable), C.c_int(1 if reset else 0), C.byref(k)))
+        return {k.name[i].decode(): (k.ms[i], k.calls[i]) for i in range(k.n)}
+
     @property
     def stream(self) -> int:
         return int(lib().sphb_ctx_stream(self._ctx) or 0)
+
+
+def channel_from_config(cfg, particles, **overrides) -> Channel:
+    """Channel for a channel_setup.ChannelConfig (after .derive()) and its Particles, state uploaded."""
+    kw = dict(n_fluid=particles.n_fluid, n_total=particles.n_total, DL=cfg.DL, DH=cfg.DH, dp=cfg.dp, h=cfg.h,
+              rho0=cfg.rho0, p0=cfg.p0, c_f=cfg.c_f, mu=cfg.mu, gravity_g=cfg.gravity_g, inv_sigma0=cfg.inv_sigma0,
+              transport_coeff=cfg.transport_coeff, sort_interval=cfg.sort_interval)
+    kw.update(overrides)
+    ch = Channel(ChannelParams(**kw))
+    ch.upload(pos=particles.pos, vel=particles.vel, rho=particles.rho, drho_dt=particles.drho_dt,
+              mass=particles.mass, wall_vel=particles.wall_vel)
+    return ch
 
 
 def channel_from_oracle_params(prm, n_fluid: int, n_total: int, **overrides) -> Channel:

@@ -106,10 +106,50 @@ struct NeighborWork {
     void release_all();
 };
 
+// ------------------------------------------------------------------------------------------------
+// per-kernel device timing (CUDA events on the launching stream); off unless a caller enables it
+// ------------------------------------------------------------------------------------------------
+enum ProfId : int {
+    kPfNbrGrid = 0, kPfNbrBin, kPfNbrScan, kPfNbrScatter, kPfNbrCanon, kPfNbrWalkCount, kPfNbrWalkFill,
+    kPfNbrRowSort, kPfDensity, kPfKgc, kPfViscTransp, kPfTimeStep, kPfPressure, kPfContinuity, kPfClock,
+    kPfShear, kPfSort, kPfCount
+};
+const char *prof_name(int id);
+
+struct Prof {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    struct Rec { int id; size_t e0, e1; };
+    std::vector<Rec> recs;
+    double ms[kPfCount] = {};
+    long long n[kPfCount] = {};
+    size_t grab();
+    void begin(int id, cudaStream_t st);
+    void end(cudaStream_t st);
+    int collect(cudaStream_t st);   // synchronises the stream, folds the open records into ms[]/n[]
+    void reset();
+    void release();
+};
+
+struct ProfScope {
+    Prof *p;
+    cudaStream_t st;
+    ProfScope(Prof *prof, int id, cudaStream_t s) : p(prof && prof->on ? prof : nullptr), st(s)
+    {
+        if (p) p->begin(id, st);
+    }
+    ~ProfScope()
+    {
+        if (p) p->end(st);
+    }
+};
+
 // neighbor.cu (compiled with -fmad=false: bit-exact accept tests)
 int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL, double y_min_hint,
                   double y_max_hint, int max_nbr_hint);
-int neighbor_build(NeighborWork &w, const double2 *pos, bool want_full_csr, cudaStream_t st, long long *launches);
+int neighbor_build(NeighborWork &w, const double2 *pos, bool want_full_csr, cudaStream_t st, long long *launches,
+                   Prof *prof = nullptr);
 int neighbor_export_pairs(NeighborWork &w, size_t n_half, double *pair_i, double *pair_j, double *dx, double *dy,
                           double *r, double *W, double *dW, cudaStream_t st);   // device pointers
 

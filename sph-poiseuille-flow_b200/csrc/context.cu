@@ -36,6 +36,7 @@ struct sphb_ctx {
     bool timing = false;
     cudaEvent_t ev[8]{};
     sphb_timing last_timing{};
+    Prof kprof;                  // per-kernel event timing (sphb_ctx_kernel_profile)
     // cached graphs for the dual-criteria schedule: [0] without, [1] with cell sort
     cudaGraphExec_t graph[2]{nullptr, nullptr};
     int graph_inner = -1;
@@ -135,9 +136,23 @@ int plan_lists(sphb_ctx *c, double y_lo, double y_hi)
 int do_density(sphb_ctx *c)
 {
     const StateView S = c->view();
-    SPHB_TRY(csr_density(c->P, S, c->st));
-    SPHB_TRY(csr_kgc(c->P, S, c->st));
+    {
+        ProfScope ps(&c->kprof, kPfDensity, c->st);
+        SPHB_TRY(csr_density(c->P, S, c->st));
+    }
+    {
+        ProfScope ps(&c->kprof, kPfKgc, c->st);
+        SPHB_TRY(csr_kgc(c->P, S, c->st));
+    }
     c->launches += 2;
+    return 0;
+}
+
+int do_visc_transport(sphb_ctx *c, bool visc, bool gravity, bool transport)
+{
+    ProfScope ps(&c->kprof, kPfViscTransp, c->st);
+    SPHB_TRY(csr_visc_transport(c->P, c->view(), visc, gravity, transport, c->st));
+    c->launches += 1;
     return 0;
 }
 
@@ -145,6 +160,7 @@ int do_sort(sphb_ctx *c)
 {
     const int nf = c->prm.n_fluid, nt = c->prm.n_total;
     if (nf <= 0 || nf >= nt) return 0;   // m:535-537
+    ProfScope ps(&c->kprof, kPfSort, c->st);
     SPHB_TRY(sort_permutation(c->sw, c->pos.as<double2>(), nf, c->prm.DL, c->prm.h, c->sc(), c->nw.flags.as<int>(),
                               c->st, &c->launches));
     PermuteArrays A;
@@ -172,13 +188,14 @@ int do_sort(sphb_ctx *c)
 
 int do_neighbor(sphb_ctx *c)
 {
-    SPHB_TRY(neighbor_build(c->nw, c->pos.as<double2>(), true, c->st, &c->launches));
+    SPHB_TRY(neighbor_build(c->nw, c->pos.as<double2>(), true, c->st, &c->launches, &c->kprof));
     c->have_list = true;
     return 0;
 }
 
 int do_shear(sphb_ctx *c)
 {
+    ProfScope ps(&c->kprof, kPfShear, c->st);
     SPHB_TRY(csr_wall_shear(c->P, c->view(), c->sc(), c->shear_partials.as<double>(), c->st));
     c->launches += 2;
     return 0;
@@ -187,10 +204,22 @@ int do_shear(sphb_ctx *c)
 int do_substep(sphb_ctx *c, double remain, double fixed_dt, bool wrap)
 {
     const StateView S = c->view();
-    SPHB_TRY(csr_time_step(c->P, c->sc(), remain, fixed_dt, c->st));
-    SPHB_TRY(csr_pressure(c->P, S, c->sc(), c->st));
-    SPHB_TRY(csr_continuity(c->P, S, c->sc(), wrap, c->st));
-    SPHB_TRY(csr_advance_clock(c->sc(), c->st));
+    {
+        ProfScope ps(&c->kprof, kPfTimeStep, c->st);
+        SPHB_TRY(csr_time_step(c->P, c->sc(), remain, fixed_dt, c->st));
+    }
+    {
+        ProfScope ps(&c->kprof, kPfPressure, c->st);
+        SPHB_TRY(csr_pressure(c->P, S, c->sc(), c->st));
+    }
+    {
+        ProfScope ps(&c->kprof, kPfContinuity, c->st);
+        SPHB_TRY(csr_continuity(c->P, S, c->sc(), wrap, c->st));
+    }
+    {
+        ProfScope ps(&c->kprof, kPfClock, c->st);
+        SPHB_TRY(csr_advance_clock(c->sc(), c->st));
+    }
     c->launches += 4;
     return 0;
 }
@@ -284,6 +313,7 @@ SPHB_API void sphb_ctx_destroy(sphb_ctx *c)
     for (DevBuf *b : all) b->release();
     c->nw.release_all();
     c->sw.release_all();
+    c->kprof.release();
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
     if (c->h_ints) cudaFreeHost(c->h_ints);
     for (auto &e : c->ev)
@@ -467,15 +497,13 @@ SPHB_API int sphb_ctx_eos(sphb_ctx *c)
 SPHB_API int sphb_ctx_viscous_force(sphb_ctx *c, int add_gravity)
 {
     CTX_ENTER(true);
-    c->launches += 1;
-    return csr_visc_transport(c->P, c->view(), true, add_gravity != 0, false, c->st);
+    return do_visc_transport(c, true, add_gravity != 0, false);
 }
 
 SPHB_API int sphb_ctx_transport_correction(sphb_ctx *c)
 {
     CTX_ENTER(true);
-    c->launches += 1;
-    return csr_visc_transport(c->P, c->view(), false, false, true, c->st);
+    return do_visc_transport(c, false, false, true);
 }
 
 SPHB_API int sphb_ctx_integration_verlet(sphb_ctx *c, double dt)
@@ -543,13 +571,11 @@ SPHB_API int sphb_ctx_status(sphb_ctx *c, sphb_status *out)
 SPHB_API int sphb_ctx_step(sphb_ctx *c, double remain)
 {
     CTX_ENTER(true);
-    const StateView S = c->view();
     c->h_step += 1;
     tick(c, 0);
     SPHB_TRY(do_density(c));                                                          // m:254-255
     tick(c, 1);
-    SPHB_TRY(csr_visc_transport(c->P, S, true, true, true, c->st));                   // m:256-257
-    c->launches += 1;
+    SPHB_TRY(do_visc_transport(c, true, true, true));                                 // m:256-257
     tick(c, 2);
     SPHB_TRY(do_substep(c, remain, 0.0, true));                                       // m:259-269
     tick(c, 3);
@@ -588,8 +614,7 @@ int enqueue_outer(sphb_ctx *c, int n_inner, bool with_sort)
 {
     const double inf = std::numeric_limits<double>::infinity();
     SPHB_TRY(do_density(c));
-    SPHB_TRY(csr_visc_transport(c->P, c->view(), true, true, true, c->st));
-    c->launches += 1;
+    SPHB_TRY(do_visc_transport(c, true, true, true));
     for (int s = 0; s < n_inner; ++s) SPHB_TRY(do_substep(c, inf, 0.0, true));
     if (with_sort) SPHB_TRY(do_sort(c));
     SPHB_TRY(do_neighbor(c));
@@ -613,6 +638,12 @@ SPHB_API int sphb_ctx_run_dual(sphb_ctx *c, int n_outer, int n_inner)
             // the permutation swaps buffer pointers: run eagerly, then re-capture on the new pointers
             drop_graphs(c);
             SPHB_TRY(enqueue_outer(c, n_inner, true));
+            if (c->kprof.on) SPHB_TRY(c->kprof.collect(c->st));
+            continue;
+        }
+        if (c->kprof.on) {   // per-kernel events cannot live inside a replayed graph: run this outer step eagerly
+            SPHB_TRY(enqueue_outer(c, n_inner, false));
+            SPHB_TRY(c->kprof.collect(c->st));
             continue;
         }
         if (!c->graph[0]) {
@@ -693,6 +724,23 @@ SPHB_API int sphb_ctx_timing(sphb_ctx *c, sphb_timing *out)
     }
     t.launches = c->launches;
     *out = t;
+    return 0;
+}
+
+SPHB_API int sphb_ctx_kernel_profile(sphb_ctx *c, int enable, int reset, sphb_kprof *out)
+{
+    CTX_ENTER(false);
+    SPHB_TRY(c->kprof.collect(c->st));
+    if (out) {
+        out->n = kPfCount;
+        for (int k = 0; k < SPHB_KPROF_SLOTS; ++k) {
+            out->name[k] = k < kPfCount ? prof_name(k) : "";
+            out->ms[k] = k < kPfCount ? c->kprof.ms[k] : 0.0;
+            out->calls[k] = k < kPfCount ? c->kprof.n[k] : 0;
+        }
+    }
+    if (reset) c->kprof.reset();
+    if (enable >= 0) c->kprof.on = enable != 0;
     return 0;
 }
 

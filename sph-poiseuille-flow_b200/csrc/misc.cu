@@ -41,6 +41,70 @@ int ensure_device()
     return 0;
 }
 
+const char *prof_name(int id)
+{
+    static const char *names[kPfCount] = {"nbr_grid", "nbr_bin_count", "nbr_scan", "nbr_scatter", "nbr_cell_canon",
+                                          "nbr_walk_count", "nbr_walk_fill", "nbr_row_sort", "density", "kgc",
+                                          "visc_transport", "time_step", "pressure", "continuity", "clock",
+                                          "wall_shear", "cell_sort"};
+    return (id >= 0 && id < kPfCount) ? names[id] : "?";
+}
+
+size_t Prof::grab()
+{
+    if (used == pool.size()) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        pool.push_back(e);
+    }
+    return used++;
+}
+void Prof::begin(int id, cudaStream_t st)
+{
+    Rec r;
+    r.id = id;
+    r.e0 = grab();
+    r.e1 = grab();
+    cudaEventRecord(pool[r.e0], st);
+    recs.push_back(r);
+}
+void Prof::end(cudaStream_t st)
+{
+    if (!recs.empty()) cudaEventRecord(pool[recs.back().e1], st);
+}
+int Prof::collect(cudaStream_t st)
+{
+    SPHB_CUDA(cudaStreamSynchronize(st));
+    for (const Rec &r : recs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, pool[r.e0], pool[r.e1]) == cudaSuccess) {
+            ms[r.id] += (double)t;
+            n[r.id] += 1;
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
+    recs.clear();
+    used = 0;
+    return 0;
+}
+void Prof::reset()
+{
+    for (int k = 0; k < kPfCount; ++k) {
+        ms[k] = 0.0;
+        n[k] = 0;
+    }
+    recs.clear();
+    used = 0;
+}
+void Prof::release()
+{
+    for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    pool.clear();
+    recs.clear();
+    used = 0;
+}
+
 int DevBuf::reserve(size_t need)
 {
     if (need <= bytes && p) return 0;

@@ -254,11 +254,17 @@ __global__ void __launch_bounds__(kBlock) k_half_walk(NbrParams P, const GridDes
     for (int oy = -1; oy <= 1; ++oy) {
         const int cy = cyi + oy;
         if (cy < 0 || cy >= ncy) continue;
+        int cx_prev[2] = {-1, -1};
         for (int ox = -1; ox <= 1; ++ox) {
             int cx = cxi + ox;
             if (cx < 0) cx += ncx;
             else if (cx >= ncx) cx -= ncx;
             if (cx < 0 || cx >= ncx) continue;
+            // n_cell_x <= 2: the wrapped stencil revisits a column.  The reference re-walks it, but
+            // every entry it accepted is already in seen_neighbor and every entry it rejected is
+            // rejected again by the same arithmetic (nb:342-372), so the revisit emits nothing.
+            if (cx == cx_prev[0] || cx == cx_prev[1]) continue;
+            cx_prev[ox == -1 ? 0 : 1] = cx;
             const int cid = cy * ncx + cx;
             const int s = cell_start[cid];
             for (int e = cell_start[cid + 1] - 1; e >= s; --e) {
@@ -472,7 +478,8 @@ int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL
 // Builds the lists from `pos` (device, double2[n_total]).  When a capacity is exceeded the build stops
 // after the counting pass, synchronises, grows the buffer and continues (stateless path and first
 // resident build); in steady state no host synchronisation happens.
-int neighbor_build(NeighborWork &w, const double2 *pos, bool want_full_csr, cudaStream_t st, long long *launches)
+int neighbor_build(NeighborWork &w, const double2 *pos, bool want_full_csr, cudaStream_t st, long long *launches,
+                   Prof *prof)
 {
     NbrParams P = make_params(w);
     GridDesc *g = w.grid.as<GridDesc>();
@@ -480,35 +487,56 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool want_full_csr, cuda
     const int nt = w.n_total, nf = w.n_fluid;
     long long nl = 0;
 
-    k_grid_init<<<1, 1, 0, st>>>(g);
     {
+        ProfScope ps(prof, kPfNbrGrid, st);
+        k_grid_init<<<1, 1, 0, st>>>(g);
         int blocks = (nt + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
         k_yrange<<<blocks, 256, 0, st>>>(pos, nt, g);
+        k_grid_setup<<<1, 1, 0, st>>>(g, P, flags);
+        SPHB_CUDA(cudaMemsetAsync(w.cell_cnt.p, 0, ((size_t)w.cell_cap + 1) * sizeof(int), st));
+        SPHB_CUDA(cudaMemsetAsync(w.cell_fill.p, 0, ((size_t)w.cell_cap + 1) * sizeof(int), st));
     }
-    k_grid_setup<<<1, 1, 0, st>>>(g, P, flags);
-    SPHB_CUDA(cudaMemsetAsync(w.cell_cnt.p, 0, ((size_t)w.cell_cap + 1) * sizeof(int), st));
-    SPHB_CUDA(cudaMemsetAsync(w.cell_fill.p, 0, ((size_t)w.cell_cap + 1) * sizeof(int), st));
-    k_bin_count<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.snap.as<double2>(), w.cell_of.as<int>(),
-                                                 w.cell_cnt.as<int>());
+    {
+        ProfScope ps(prof, kPfNbrBin, st);
+        k_bin_count<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.snap.as<double2>(), w.cell_of.as<int>(),
+                                                     w.cell_cnt.as<int>());
+    }
     nl += 4;
-    SPHB_TRY(exclusive_scan_i32(w.cell_cnt.as<int>(), w.cell_start.as<int>(), (size_t)w.cell_cap, w.scan_tmp,
-                                &g->n_entries, st, &nl));
-    k_scatter<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.cell_start.as<int>(), w.cell_fill.as<int>(),
-                                               w.ent_key.as<int>(), w.ent_pos.as<double2>());
-    k_cell_canon<<<grid_for((size_t)w.cell_cap), kBlock, 0, st>>>(g, w.cell_start.as<int>(), w.ent_key.as<int>(),
-                                                                  w.ent_pos.as<double2>());
+    {
+        ProfScope ps(prof, kPfNbrScan, st);
+        SPHB_TRY(exclusive_scan_i32(w.cell_cnt.as<int>(), w.cell_start.as<int>(), (size_t)w.cell_cap, w.scan_tmp,
+                                    &g->n_entries, st, &nl));
+    }
+    {
+        ProfScope ps(prof, kPfNbrScatter, st);
+        k_scatter<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.cell_start.as<int>(), w.cell_fill.as<int>(),
+                                                   w.ent_key.as<int>(), w.ent_pos.as<double2>());
+    }
+    {
+        ProfScope ps(prof, kPfNbrCanon, st);
+        k_cell_canon<<<grid_for((size_t)w.cell_cap), kBlock, 0, st>>>(g, w.cell_start.as<int>(), w.ent_key.as<int>(),
+                                                                      w.ent_pos.as<double2>());
+    }
     nl += 2;
 
-    if (want_full_csr) SPHB_CUDA(cudaMemsetAsync(w.row_cnt.p, 0, ((size_t)nf + 1) * sizeof(int), st));
-    k_half_walk<false><<<grid_for(nf), kBlock, 0, st>>>(
-        P, g, w.snap.as<double2>(), w.cell_of.as<int>(), w.cell_start.as<int>(), w.ent_key.as<int>(),
-        w.ent_pos.as<double2>(), w.half_cnt.as<int>(), w.row_cnt.as<int>(), nullptr, nullptr, nullptr, nullptr,
-        nullptr, want_full_csr ? 1 : 0, flags);
+    {
+        ProfScope ps(prof, kPfNbrWalkCount, st);
+        if (want_full_csr) SPHB_CUDA(cudaMemsetAsync(w.row_cnt.p, 0, ((size_t)nf + 1) * sizeof(int), st));
+        k_half_walk<false><<<grid_for(nf), kBlock, 0, st>>>(
+            P, g, w.snap.as<double2>(), w.cell_of.as<int>(), w.cell_start.as<int>(), w.ent_key.as<int>(),
+            w.ent_pos.as<double2>(), w.half_cnt.as<int>(), w.row_cnt.as<int>(), nullptr, nullptr, nullptr, nullptr,
+            nullptr, want_full_csr ? 1 : 0, flags);
+    }
     nl += 1;
-    SPHB_TRY(exclusive_scan_i32(w.half_cnt.as<int>(), w.half_ptr.as<int>(), (size_t)nf, w.scan_tmp, nullptr, st, &nl));
-    if (want_full_csr)
-        SPHB_TRY(exclusive_scan_i32(w.row_cnt.as<int>(), w.row_ptr.as<int>(), (size_t)nf, w.scan_tmp, nullptr, st, &nl));
+    {
+        ProfScope ps(prof, kPfNbrScan, st);
+        SPHB_TRY(exclusive_scan_i32(w.half_cnt.as<int>(), w.half_ptr.as<int>(), (size_t)nf, w.scan_tmp, nullptr, st,
+                                    &nl));
+        if (want_full_csr)
+            SPHB_TRY(exclusive_scan_i32(w.row_cnt.as<int>(), w.row_ptr.as<int>(), (size_t)nf, w.scan_tmp, nullptr, st,
+                                        &nl));
+    }
 
     // capacity: known-sufficient in steady state; otherwise read the totals back once and grow
     bool need_sync = (w.half_cap == 0) || (want_full_csr && w.csr_cap == 0);
@@ -538,13 +566,17 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool want_full_csr, cuda
         nl += 1;
     }
 
-    if (want_full_csr) SPHB_CUDA(cudaMemsetAsync(w.row_fill.p, 0, ((size_t)nf + 1) * sizeof(int), st));
-    k_half_walk<true><<<grid_for(nf), kBlock, 0, st>>>(
-        P, g, w.snap.as<double2>(), w.cell_of.as<int>(), w.cell_start.as<int>(), w.ent_key.as<int>(),
-        w.ent_pos.as<double2>(), nullptr, nullptr, w.half_ptr.as<int>(), w.row_ptr.as<int>(), w.row_fill.as<int>(),
-        w.half_col.as<unsigned>(), w.col.as<unsigned>(), want_full_csr ? 1 : 0, flags);
+    {
+        ProfScope ps(prof, kPfNbrWalkFill, st);
+        if (want_full_csr) SPHB_CUDA(cudaMemsetAsync(w.row_fill.p, 0, ((size_t)nf + 1) * sizeof(int), st));
+        k_half_walk<true><<<grid_for(nf), kBlock, 0, st>>>(
+            P, g, w.snap.as<double2>(), w.cell_of.as<int>(), w.cell_start.as<int>(), w.ent_key.as<int>(),
+            w.ent_pos.as<double2>(), nullptr, nullptr, w.half_ptr.as<int>(), w.row_ptr.as<int>(),
+            w.row_fill.as<int>(), w.half_col.as<unsigned>(), w.col.as<unsigned>(), want_full_csr ? 1 : 0, flags);
+    }
     nl += 1;
     if (want_full_csr) {
+        ProfScope ps(prof, kPfNbrRowSort, st);
         k_row_sort<<<grid_for(nf), kBlock, 0, st>>>(nf, w.row_ptr.as<int>(), w.csr_cap, w.col.as<unsigned>());
         nl += 1;
     }

@@ -1,0 +1,44 @@
+"""Shared helpers of the parity tests."""
+import numpy as np
+
+PAIR_NAMES = ("pair_i", "pair_j", "dx", "dy", "r", "W", "dW")
+
+# One-step field gate of BASELINE.json's north_star ("within 1e-11 relative in fp64"), applied as a
+# MAX-NORM relative error per output field: ||x - x_ref||_inf / ||x_ref||_inf.  A point-wise relative
+# gate is failed by the reference against itself (1 vs 8 OpenMP threads reaches 3.6e-11 point-wise,
+# <= 5e-14 in max-norm).
+TOL = 1e-11
+
+
+def maxnorm_rel(got, want):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, f"shape {got.shape} != {want.shape}"
+    if want.size == 0:
+        return 0.0
+    err = float(np.max(np.abs(got - want)))
+    scale = float(np.max(np.abs(want)))
+    if scale == 0.0:
+        return 0.0 if err == 0.0 else np.inf
+    return err / scale
+
+
+def assert_close(got, want, name, tol=TOL):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    if got.ndim == 2 and got.shape[1] == 1 and want.ndim == 1:
+        got = got.ravel()
+    assert np.all(np.isfinite(got)), f"{name}: non-finite values"
+    e = maxnorm_rel(got, want)
+    assert e <= tol, f"{name}: max-norm relative error {e:.3e} > {tol:g}"
+
+
+def pairs_as_sets(pairs, n_fluid):
+    """Sorted (i, j) index set, fluid-fluid normalised to i < j (gate G1)."""
+    i = pairs[0].astype(np.int64)
+    j = pairs[1].astype(np.int64)
+    ff = j <= n_fluid
+    lo = np.where(ff, np.minimum(i, j), i)
+    hi = np.where(ff, np.maximum(i, j), j)
+    key = lo * (1 << 32) + hi
+    return np.sort(key).tobytes()

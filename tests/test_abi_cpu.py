@@ -1,0 +1,89 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/sph_b200.h declares, keeps the reference's argument-count / error-identifier contract on the
+host side, and refuses to compute without a CUDA device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_product
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sph_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"SPHB_API\s+[^;{]*?\b(sphb_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    sphb = load_product()
+    L = sphb.lib()
+    names = _declared_symbols()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(L, n), f"libsph_b200.so does not export {n}"
+    assert L.sphb_version() == 100
+
+
+def test_no_cpu_fallback_without_device():
+    sphb = load_product()
+    if sphb.device_available():
+        pytest.skip("a CUDA device is present")
+    pos = np.zeros((4, 2), order="F")
+    with pytest.raises(sphb.SphError) as e:
+        sphb.sph_neighbor_search_mex(pos, 2, 4, 0.1, 1.0)
+    assert e.value.identifier == "SPHB:cuda"
+    with pytest.raises(sphb.SphError) as e:
+        sphb.Channel(sphb.ChannelParams(n_fluid=2, n_total=4, DL=1.0, DH=1.0, dp=0.1, h=0.13, rho0=1.0, p0=100.0,
+                                        c_f=10.0, mu=0.1, gravity_g=0.8, inv_sigma0=0.01))
+    assert e.value.identifier == "SPHB:cuda"
+
+
+def test_gateway_argument_count_identifiers():
+    """nrhs/nlhs identifiers of the two gateways (nb:216-221, ph:1749-1770 and each mode's header)."""
+    sphb = load_product()
+    with pytest.raises(sphb.SphError) as e:
+        sphb.sph_neighbor_search_mex(np.zeros((4, 2)), 2, 4, 0.1)
+    assert e.value.identifier == "SPH:Neighbor:nrhs"
+    with pytest.raises(sphb.SphError) as e:
+        sphb.sph_neighbor_search_mex(np.zeros((4, 2)), 2, 4, 0.1, 1.0, nargout=3)
+    assert e.value.identifier == "SPH:Neighbor:nlhs"
+    with pytest.raises(sphb.SphError) as e:
+        sphb.sph_physics_shell_mex("no_such_mode", nargout=1)
+    assert e.value.identifier == "SPH:Physics:mode"
+    with pytest.raises(sphb.SphError) as e:
+        sphb.sph_physics_shell_mex(3.0, nargout=1)
+    assert e.value.identifier == "SPH:Physics:mode"
+    for mode, tag, nout in (("density_correction", "density", 3), ("viscous_force", "viscous", 1),
+                            ("transport_correction", "transport", 1), ("integration_1st", "int1", 5),
+                            ("integration_2nd", "int2", 3), ("integration_verlet", "verlet", 6),
+                            ("advance_shell_step", "advance", 9), ("wall_shear_monitor", "wallshear", 2)):
+        with pytest.raises(sphb.SphError) as e:
+            sphb.sph_physics_shell_mex(mode, 1.0, 2.0, nargout=nout)
+        assert e.value.identifier == f"SPH:Physics:{tag}:nrhs"
+
+
+def test_stateless_validation_identifiers_precede_device_use():
+    """Size checks that the reference performs before touching data are reproduced inside the library
+    and fire before any CUDA call (so they are testable without a GPU)."""
+    sphb = load_product()
+    pos = np.zeros((4, 2), order="F")
+    with pytest.raises(sphb.SphError) as e:
+        sphb.sph_neighbor_search_mex(pos, 2, 5, 0.1, 1.0)          # n_total != rows(pos)
+    assert e.value.identifier == "SPH:Neighbor:count"
+    with pytest.raises(sphb.SphError) as e:
+        sphb.sph_neighbor_search_mex(pos, 2, 4, -0.1, 1.0)
+    assert e.value.identifier == "SPH:Neighbor:param"
+    with pytest.raises(sphb.SphError) as e:
+        sphb.sph_neighbor_search_mex(np.zeros((4, 3), order="F"), 2, 4, 0.1, 1.0)
+    assert e.value.identifier == "SPH:Neighbor:pos"
+
+
+def test_struct_layouts_match_header():
+    """ctypes mirrors of sphb_params / sphb_status / sphb_timing have the C sizes (x86-64 SysV)."""
+    sphb = load_product()
+    assert ctypes.sizeof(sphb._Params) == 2 * 4 + 11 * 8 + 3 * 4 + 4   # ints, doubles, ints + tail pad
+    assert ctypes.sizeof(sphb._Status) == 5 * 8 + 3 * 8 + 8
+    assert ctypes.sizeof(sphb._Mat) == 24
