@@ -65,7 +65,7 @@ def parse_args():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--profile-steps", type=int, default=5)
-    ap.add_argument("--cpu-baseline-steps", type=int, default=2, help="outer steps of the CPU sample (0 = skip)")
+    ap.add_argument("--cpu-baseline-steps", type=int, default=20, help="outer steps of the CPU sample (0 = skip)")
     ap.add_argument("--seed", type=int, default=12345)
     return ap.parse_args()
 
