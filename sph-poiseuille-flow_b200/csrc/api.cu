@@ -150,7 +150,6 @@ SPHB_API int sphb_neighbor_search(sphb_mat pos, int n_fluid, int n_total, double
         hi = pos.p[n + i] > hi ? pos.p[n + i] : hi;
     }
     SPHB_TRY(neighbor_plan(g.nw, n_fluid, n_total, h, DL, lo, hi, 0));
-    g.nw.half_cap = 0;   // force exact sizing: the stateless path may see any input
     SPHB_CUDA(cudaMemsetAsync(g.nw.flags.p, 0, sizeof(int), g.st));
     Bump b;
     SPHB_TRY(open_arena(g, pad4(2 * n), b));
@@ -158,7 +157,8 @@ SPHB_API int sphb_neighbor_search(sphb_mat pos, int n_fluid, int n_total, double
     SPHB_TRY(upload(g, b, pos.p, 2 * n, &d_pos));
     SPHB_TRY(g.pos2.reserve(n * sizeof(double2)));
     launch_pack2(d_pos, g.pos2.as<double2>(), n_total, g.st);
-    SPHB_TRY(neighbor_build(g.nw, g.pos2.as<double2>(), false, g.st, nullptr));
+    // half list only (the reference's own), ELL grown to the longest row: any input is legal here
+    SPHB_TRY(neighbor_build(g.nw, g.pos2.as<double2>(), true, true, g.st, nullptr));
     int host[3] = {0, 0, 0};
     SPHB_CUDA(cudaMemcpyAsync(host, g.nw.totals.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, g.st));
     SPHB_CUDA(cudaMemcpyAsync(host + 2, g.nw.flags.p, sizeof(int), cudaMemcpyDeviceToHost, g.st));

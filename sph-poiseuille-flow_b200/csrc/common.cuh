@@ -83,8 +83,9 @@ struct NeighborWork {
     int n_fluid = 0, n_total = 0;
     double h = 0, DL = 0;
     int cell_cap = 0;            // allocated cells
-    size_t half_cap = 0;         // allocated half-pair slots
-    size_t csr_cap = 0;          // allocated full-CSR slots
+    int ell_cap = 0;             // allocated ELL rows (longest storable neighbour row)
+    size_t ell_stride = 0;       // n_fluid rounded up to 32
+    bool half_only = false;      // the last build kept only the reference's half list
     DevBuf grid;                 // GridDesc
     DevBuf flags;                // int error flags
     DevBuf snap;                 // double2 [n_total]   wrapped x, y at build time
@@ -94,24 +95,22 @@ struct NeighborWork {
     DevBuf cell_fill;            // int [cell_cap]
     DevBuf ent_key;              // int [3*n_total]     (particle << 3) | (multi << 2) | kind
     DevBuf ent_pos;              // double2 [3*n_total] entry coordinates (ghosts shifted by -+DL)
-    DevBuf half_cnt;             // int [n_fluid+1]
-    DevBuf half_ptr;             // int [n_fluid+1]
-    DevBuf half_col;             // uint [half_cap]     j | kind << 30
-    DevBuf row_cnt;              // int [n_fluid+1]
-    DevBuf row_ptr;              // int [n_fluid+1]
-    DevBuf row_fill;             // int [n_fluid]
-    DevBuf col;                  // uint [csr_cap]      j | (shift code) << 30
+    DevBuf ell_cnt;              // int [n_fluid]       neighbours of each fluid particle
+    DevBuf ell_col;              // uint [ell_cap * ell_stride], column-major: col[k * stride + i]
+                                 //   j (28 bits) | entry kind (2) | minimum-image shift + 1 (2)
+    DevBuf half_cnt, half_ptr;   // int [n_fluid+1]     export only (reference half-pair list)
     DevBuf scan_tmp;             // scan workspace
-    DevBuf totals;               // int[4]: n_half, n_csr (device), read back on demand
+    DevBuf totals;               // int[4]: n_half, n_full, longest row (device), read back on demand
     void release_all();
 };
+constexpr int kDefaultEllRows = 48;
 
 // ------------------------------------------------------------------------------------------------
 // per-kernel device timing (CUDA events on the launching stream); off unless a caller enables it
 // ------------------------------------------------------------------------------------------------
 enum ProfId : int {
-    kPfNbrGrid = 0, kPfNbrBin, kPfNbrScan, kPfNbrScatter, kPfNbrCanon, kPfNbrWalkCount, kPfNbrWalkFill,
-    kPfNbrRowSort, kPfDensity, kPfKgc, kPfViscTransp, kPfTimeStep, kPfPressure, kPfContinuity, kPfClock,
+    kPfNbrGrid = 0, kPfNbrBin, kPfNbrScan, kPfNbrScatter, kPfNbrCanon, kPfNbrWalk,
+    kPfDensity, kPfKgc, kPfViscTransp, kPfTimeStep, kPfPressure, kPfContinuity, kPfClock,
     kPfShear, kPfSort, kPfCount
 };
 const char *prof_name(int id);
@@ -148,8 +147,9 @@ struct ProfScope {
 // neighbor.cu (compiled with -fmad=false: bit-exact accept tests)
 int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL, double y_min_hint,
                   double y_max_hint, int max_nbr_hint);
-int neighbor_build(NeighborWork &w, const double2 *pos, bool want_full_csr, cudaStream_t st, long long *launches,
-                   Prof *prof = nullptr);
+int neighbor_reserve_ell(NeighborWork &w, int rows);
+int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exact, cudaStream_t st,
+                   long long *launches, Prof *prof = nullptr);
 int neighbor_export_pairs(NeighborWork &w, size_t n_half, double *pair_i, double *pair_j, double *dx, double *dy,
                           double *r, double *W, double *dW, cudaStream_t st);   // device pointers
 

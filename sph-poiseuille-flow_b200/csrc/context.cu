@@ -8,6 +8,7 @@
 #include "ops_csr.cuh"
 #include "sort.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <limits>
 
@@ -21,10 +22,11 @@ struct sphb_ctx {
     // state (+ alternates for the cell-sort permutation)
     DevBuf pos, vel, vel_new, wall_vel, force, force_prior, rho, p, drho_dt, mass, Vol, B;
     DevBuf a_pos, a_vel, a_wall_vel, a_force, a_force_prior, a_rho, a_p, a_drho_dt, a_mass, a_Vol, a_B;
-    DevBuf scalars, shear_partials, stage, prof;
+    DevBuf scalars, shear_partials, stage, prof, rp_half;
     NeighborWork nw;
     SortWork sw;
     bool have_list = false;
+    bool list_sized = false;     // the ELL has been grown to the longest row seen at the first build
     bool planned = false;
     double y_lo = 0, y_hi = 0;
     long long h_step = 0;        // host mirror of the step counter (sort cadence, m:272)
@@ -58,9 +60,12 @@ struct sphb_ctx {
         S.mass = mass.as<double>();
         S.Vol = Vol.as<double>();
         S.B = B.as<Mat2>();
+        S.rp_half = rp_half.as<double2>();
         S.snap = nw.snap.as<double2>();
-        S.row_ptr = nw.row_ptr.as<int>();
-        S.col = nw.col.as<unsigned>();
+        S.ell_cnt = nw.ell_cnt.as<int>();
+        S.ell_col = nw.ell_col.as<unsigned>();
+        S.ell_stride = nw.ell_stride;
+        S.ell_cap = nw.ell_cap;
         return S;
     }
     DevScalars *sc() const { return scalars.as<DevScalars>(); }
@@ -188,7 +193,15 @@ int do_sort(sphb_ctx *c)
 
 int do_neighbor(sphb_ctx *c)
 {
-    SPHB_TRY(neighbor_build(c->nw, c->pos.as<double2>(), true, c->st, &c->launches, &c->kprof));
+    // the first build sizes the ELL exactly (one host round trip); later builds only raise the flag
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    (void)cudaStreamIsCapturing(c->st, &cap);
+    const bool exact = !c->list_sized && cap == cudaStreamCaptureStatusNone;
+    SPHB_TRY(neighbor_build(c->nw, c->pos.as<double2>(), false, exact, c->st, &c->launches, &c->kprof));
+    if (exact) {
+        c->list_sized = true;
+        drop_graphs(c);   // the ELL may have moved
+    }
     c->have_list = true;
     return 0;
 }
@@ -206,7 +219,7 @@ int do_substep(sphb_ctx *c, double remain, double fixed_dt, bool wrap)
     const StateView S = c->view();
     {
         ProfScope ps(&c->kprof, kPfTimeStep, c->st);
-        SPHB_TRY(csr_time_step(c->P, c->sc(), remain, fixed_dt, c->st));
+        SPHB_TRY(csr_time_step(c->P, S, c->sc(), remain, fixed_dt, c->st));
     }
     {
         ProfScope ps(&c->kprof, kPfPressure, c->st);
@@ -266,6 +279,9 @@ SPHB_API int sphb_ctx_create(const sphb_params *prm, sphb_ctx **out)
         P.inv_sigma0 = prm->inv_sigma0;
         P.transport_coeff = prm->transport_coeff;
         P.sigma = 10.0 / (7.0 * 3.14159265358979323846 * prm->h * prm->h);
+        P.inv_h = 1.0 / prm->h;
+        P.sigma_h = P.sigma / prm->h;
+        P.inv_rho0 = 1.0 / prm->rho0;
         DevBuf *v2[] = {&c->pos, &c->vel, &c->vel_new, &c->wall_vel, &c->force, &c->force_prior,
                         &c->a_pos, &c->a_vel, &c->a_wall_vel, &c->a_force, &c->a_force_prior};
         for (DevBuf *b : v2) {
@@ -278,6 +294,8 @@ SPHB_API int sphb_ctx_create(const sphb_params *prm, sphb_ctx **out)
             SPHB_TRY(b->reserve(nt * sizeof(double)));
             SPHB_CUDA(cudaMemsetAsync(b->p, 0, nt * sizeof(double), c->st));
         }
+        SPHB_TRY(c->rp_half.reserve(nt * sizeof(double2)));
+        SPHB_CUDA(cudaMemsetAsync(c->rp_half.p, 0, nt * sizeof(double2), c->st));
         SPHB_TRY(c->B.reserve(nt * sizeof(Mat2)));
         SPHB_TRY(c->a_B.reserve(nt * sizeof(Mat2)));
         SPHB_TRY(c->scalars.reserve(sizeof(DevScalars)));
@@ -309,7 +327,7 @@ SPHB_API void sphb_ctx_destroy(sphb_ctx *c)
     DevBuf *all[] = {&c->pos, &c->vel, &c->vel_new, &c->wall_vel, &c->force, &c->force_prior, &c->rho, &c->p,
                      &c->drho_dt, &c->mass, &c->Vol, &c->B, &c->a_pos, &c->a_vel, &c->a_wall_vel, &c->a_force,
                      &c->a_force_prior, &c->a_rho, &c->a_p, &c->a_drho_dt, &c->a_mass, &c->a_Vol, &c->a_B,
-                     &c->scalars, &c->shear_partials, &c->stage, &c->prof};
+                     &c->scalars, &c->shear_partials, &c->stage, &c->prof, &c->rp_half};
     for (DevBuf *b : all) b->release();
     c->nw.release_all();
     c->sw.release_all();
@@ -461,14 +479,27 @@ SPHB_API int sphb_ctx_neighbor_export_csr(sphb_ctx *c, int *row_ptr, int *col)
     clear_error();
     size_t nc = 0;
     SPHB_TRY(sphb_ctx_neighbor_count(c, nullptr, &nc));
-    const size_t nf = (size_t)c->prm.n_fluid;
-    if (row_ptr)
-        SPHB_CUDA(cudaMemcpyAsync(row_ptr, c->nw.row_ptr.p, (nf + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->st));
-    if (col && nc)
-        SPHB_CUDA(cudaMemcpyAsync(col, c->nw.col.p, nc * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    const size_t nf = (size_t)c->prm.n_fluid, stride = c->nw.ell_stride;
+    const int cap = c->nw.ell_cap;
+    std::vector<int> cnt(nf);
+    std::vector<unsigned> ell((size_t)cap * stride);
+    SPHB_CUDA(cudaMemcpyAsync(cnt.data(), c->nw.ell_cnt.p, nf * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaMemcpyAsync(ell.data(), c->nw.ell_col.p, ell.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
     SPHB_CUDA(cudaStreamSynchronize(c->st));
-    if (col)
-        for (size_t k = 0; k < nc; ++k) col[k] &= 0x3fffffff;   // strip the periodic-image code
+    // export path (not hot): ELL rows -> CSR with ascending j, image codes stripped
+    size_t o = 0;
+    std::vector<int> row;
+    for (size_t i = 0; i < nf; ++i) {
+        if (row_ptr) row_ptr[i] = (int)o;
+        const int n = cnt[i] < cap ? cnt[i] : cap;
+        row.resize((size_t)n);
+        for (int k = 0; k < n; ++k) row[(size_t)k] = (int)(ell[(size_t)k * stride + i] & 0x0fffffffu);
+        std::sort(row.begin(), row.end());
+        if (col)
+            for (int k = 0; k < n; ++k) col[o + (size_t)k] = row[(size_t)k];
+        o += (size_t)n;
+    }
+    if (row_ptr) row_ptr[nf] = (int)o;
     return 0;
 }
 
@@ -510,7 +541,7 @@ SPHB_API int sphb_ctx_integration_verlet(sphb_ctx *c, double dt)
 {
     CTX_ENTER(true);
     const StateView S = c->view();
-    SPHB_TRY(csr_time_step(c->P, c->sc(), std::numeric_limits<double>::infinity(), dt, c->st));
+    SPHB_TRY(csr_time_step(c->P, S, c->sc(), std::numeric_limits<double>::infinity(), dt, c->st));
     SPHB_TRY(csr_pressure(c->P, S, c->sc(), c->st));
     SPHB_TRY(csr_continuity(c->P, S, c->sc(), false, c->st));
     c->launches += 3;

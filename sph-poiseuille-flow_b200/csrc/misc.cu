@@ -44,7 +44,7 @@ int ensure_device()
 const char *prof_name(int id)
 {
     static const char *names[kPfCount] = {"nbr_grid", "nbr_bin_count", "nbr_scan", "nbr_scatter", "nbr_cell_canon",
-                                          "nbr_walk_count", "nbr_walk_fill", "nbr_row_sort", "density", "kgc",
+                                          "nbr_walk", "density", "kgc",
                                           "visc_transport", "time_step", "pressure", "continuity", "clock",
                                           "wall_shear", "cell_sort"};
     return (id >= 0 && id < kPfCount) ? names[id] : "?";

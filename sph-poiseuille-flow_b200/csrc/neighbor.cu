@@ -12,14 +12,14 @@
 //   k_bin_count     wrap, bin, count real + ghost entries per cell (nb:270-296) + position snapshot
 //   scan            cell_start
 //   k_scatter       entry records into their cell ranges (atomic slot), then
-//   k_cell_canon    each cell's range sorted by insertion key: the reference's linked list is walked
-//                   "last inserted first", i.e. in DEcreasing (particle, real<ghost-<ghost+) order
-//   k_half_walk<0>  per fluid particle: 3x3 walk in the reference's order with its skip rules, dedup of
-//                   real/ghost duplicates (seen_neighbor, nb:342,383) -> counts for both lists
-//   scan x2         half_ptr (the reference's half-pair list as CSR-by-i) and row_ptr (full CSR)
-//   k_half_walk<1>  same walk, fills half_col and scatters both directions into the full CSR
-//   k_row_sort      full rows sorted by j (deterministic order, monotone gathers)
-//   k_export_pairs  half list -> the 7 MEX output columns (nb:375-381), same arithmetic as the walk
+//   k_cell_canon    each cell's range sorted by DEcreasing insertion key: the reference's linked list
+//                   is walked "last inserted first", so a forward scan of the range is its walk order
+//   k_walk          ONE pass per fluid particle over its 3x3 stencil in the reference's order with its
+//                   skip rules and its real/ghost dedup (seen_neighbor, nb:342,383), writing the row
+//                   straight into an ELL (column-major, coalesced for the gather kernels): no count
+//                   pass, no scatter atomics, no row sort
+//   k_half_count / scan / k_export_pairs   (MEX export only) the reference's half-pair COO list, same
+//                   order, same bits (nb:375-381)
 #include "common.cuh"
 
 #include <cmath>
@@ -29,8 +29,7 @@ namespace sphb {
 
 namespace {
 
-constexpr unsigned kIdMask = 0x3fffffffu;
-constexpr int kSeenCap = 64;
+constexpr unsigned kIdMask = 0x0fffffffu;
 
 struct NbrParams {
     int n_fluid, n_total;
@@ -40,8 +39,11 @@ struct NbrParams {
     double cell;      // 2.0 * h                         nb:253
     double cutoff;    // r_cut * h = 2.0 * h             nb:264
     double rc2;       // (r_cut*h) * (r_cut*h)           nb:306
+    double rc2_safe;  // rc2 (1 - 1e-12): below it the kernel-support test cannot fail
+    double half_DL;   // 0.5 * DL                        nb:359
     double sigma;     // 10 / (7 pi h h)                 nb:119
-    size_t half_cap, csr_cap;
+    int ell_cap;      // rows of the ELL (longest storable neighbour row)
+    size_t ell_stride;
 };
 
 __device__ __forceinline__ long long ordered_key(double d)
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(kBlock) k_scatter(const double2 *__restrict__ 
     }
 }
 
-// insertion sort of one cell's entries by key (ascending = the reference's insertion order)
+// insertion sort of one cell's entries by DEcreasing key (= the order the reference's list is walked in)
 __global__ void __launch_bounds__(kBlock) k_cell_canon(const GridDesc *__restrict__ g,
                                                       const int *__restrict__ cell_start,
                                                       int *__restrict__ ent_key, double2 *__restrict__ ent_pos)
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(kBlock) k_cell_canon(const GridDesc *__restric
         const int key = ent_key[a];
         const double2 p = ent_pos[a];
         int b = a - 1;
-        while (b >= s && ent_key[b] > key) {
+        while (b >= s && ent_key[b] < key) {
             ent_key[b + 1] = ent_key[b];
             ent_pos[b + 1] = ent_pos[b];
             --b;
@@ -224,142 +226,206 @@ __global__ void __launch_bounds__(kBlock) k_cell_canon(const GridDesc *__restric
     }
 }
 
-// The 3x3 walk of nb:312-392 for fluid particle i.  FILL = false: count; FILL = true: write lists.
-template <bool FILL>
-__global__ void __launch_bounds__(kBlock) k_half_walk(NbrParams P, const GridDesc *__restrict__ g,
-                                                     const double2 *__restrict__ snap,
-                                                     const int *__restrict__ cell_of,
-                                                     const int *__restrict__ cell_start,
-                                                     const int *__restrict__ ent_key,
-                                                     const double2 *__restrict__ ent_pos,
-                                                     int *__restrict__ half_cnt, int *__restrict__ row_cnt,
-                                                     const int *__restrict__ half_ptr,
-                                                     const int *__restrict__ row_ptr, int *__restrict__ row_fill,
-                                                     unsigned *__restrict__ half_col, unsigned *__restrict__ col,
-                                                     int want_csr, int *__restrict__ flags)
+// nb:357-372 for "particle a (wrapped xa, ya) meets an entry at (ex, ey)": minimum image, cut-off and
+// kernel-support tests with the reference's arithmetic.  m = -1/0/+1 is the minimum-image shift.
+__device__ __forceinline__ bool accept_entry(double xa, double ya, double ex, double ey, const NbrParams &P, int &m)
+{
+    double dx = xa - ex;
+    m = 0;
+    if (dx > P.half_DL) {
+        dx -= P.DL;
+        m = -1;
+    } else if (dx < -P.half_DL) {
+        dx += P.DL;
+        m = 1;
+    }
+    const double dy = ya - ey;
+    const double r2 = dx * dx + dy * dy;
+    if (!(r2 > 1e-24 && r2 < P.rc2)) return false;
+    // r2 < rc2 (1 - 1e-12) guarantees fl(fl(sqrt(r2)) / h) < 2, i.e. W > 0 (nb:116-133, 372); only the
+    // last 1e-12 below the cut-off needs the reference's sqrt / divide / spline evaluated exactly
+    if (r2 < P.rc2_safe) return true;
+    const double r = sqrt(r2);
+    double W, dW;
+    spline2d(r, P.h, P.sigma, W, dW);
+    return W > 0.0 || fabs(dW) > 0.0;
+}
+
+// Entries of one particle as the reference inserts them (nb:278-295), from its wrapped position and
+// home cell: kind 0 real, 1 ghost at x - DL, 2 ghost at x + DL.
+struct Entries {
+    double x[3];
+    int cx[3];     // -1: not inserted
+    int cy;
+};
+__device__ __forceinline__ Entries entries_of(double xw, int home, const NbrParams &P)
+{
+    Entries E;
+    const int cx = home % P.ncx;
+    E.cy = home / P.ncx;
+    E.x[0] = xw;
+    E.cx[0] = cx;
+    E.x[1] = xw - P.DL;
+    E.cx[1] = -1;
+    E.x[2] = xw + P.DL;
+    E.cx[2] = -1;
+    if (xw > P.DL - P.cutoff) {
+        const int g = wrap_col((int)floor(E.x[1] / P.cell), P.ncx);
+        if (g != cx) E.cx[1] = g;
+    }
+    if (xw < P.cutoff) {
+        const int g = wrap_col((int)floor(E.x[2] / P.cell), P.ncx);
+        if (g != cx) E.cx[2] = g;
+    }
+    return E;
+}
+
+// The reference stores a fluid-fluid pair once, found by the LOWER index's walk (nb:353).  When ghost
+// entries are involved the two ends do not round dx identically, so the higher index replays the
+// lower one's walk restricted to its own entries: cells in (oy, ox) order, within a cell the
+// higher-kind entry first (list order = reverse insertion), first accepted entry wins.  Returns the
+// image shift of x_high as seen from the low particle, or 2 when the pair is not accepted.
+__device__ int replay_low_walk(double xl, double yl, int home_l, double xh, double yh, int home_h, int ncy,
+                               const NbrParams &P)
+{
+    const Entries E = entries_of(xh, home_h, P);
+    const int cxl = home_l % P.ncx, cyl = home_l / P.ncx;
+    if (E.cy < cyl - 1 || E.cy > cyl + 1 || E.cy < 0 || E.cy >= ncy) return 2;
+    int cx_prev[2] = {-1, -1};
+    for (int ox = -1; ox <= 1; ++ox) {
+        int cx = cxl + ox;
+        if (cx < 0) cx += P.ncx;
+        else if (cx >= P.ncx) cx -= P.ncx;
+        if (cx < 0 || cx >= P.ncx) continue;
+        if (cx == cx_prev[0] || cx == cx_prev[1]) continue;
+        cx_prev[ox == -1 ? 0 : 1] = cx;
+#pragma unroll
+        for (int kind = 2; kind >= 0; --kind) {
+            if (E.cx[kind] != cx) continue;
+            int m;
+            if (accept_entry(xl, yl, E.x[kind], yh, P, m)) return m + (kind == 1 ? 1 : (kind == 2 ? -1 : 0));
+        }
+    }
+    return 2;
+}
+
+// ELL entry: j (28 bits) | entry kind (2 bits) | minimum-image shift + 1 (2 bits).  The shift of x_j
+// as seen from the row's particle is  (m) + (kind == 1) - (kind == 2).
+__device__ __forceinline__ unsigned ell_pack(int j, int kind, int m)
+{
+    return (unsigned)j | ((unsigned)kind << 28) | ((unsigned)(m + 1) << 30);
+}
+
+// One pass over the 3x3 stencil of fluid particle i (nb:312-392), the reference's walk order.
+//   HALF = true : the reference's own list (fluid-fluid pairs only from the lower index) -- MEX export
+//   HALF = false: the full gather list: every neighbour of i, fluid-fluid pairs decided by the lower
+//                 index exactly as the reference decides them (symmetric closure of its list)
+// Output: ELL, column-major: col[k * stride + i], k < cnt[i]; rows keep the walk order, so dropping the
+// (fluid j < i) entries of a full row gives the reference's emission order.  No atomics, no sort.
+template <bool HALF>
+__global__ void __launch_bounds__(kBlock) k_walk(NbrParams P, const GridDesc *__restrict__ g,
+                                                const double2 *__restrict__ snap, const int *__restrict__ cell_of,
+                                                const int *__restrict__ cell_start,
+                                                const int *__restrict__ ent_key,
+                                                const double2 *__restrict__ ent_pos, unsigned *col,
+                                                int *__restrict__ cnt, int *__restrict__ totals,
+                                                int *__restrict__ flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int count = 0, n_half = 0;
+    if (i < P.n_fluid) {
+        const int ncx = P.ncx, ncy = g->ncy;
+        const double2 pi = snap[i];
+        const int home = cell_of[i];
+        const int cxi = home % ncx, cyi = home / ncx;
+        const size_t stride = P.ell_stride;
+        // does i itself own ghost entries?  (then a lower fluid index may have met one of them)
+        const bool i_multi = (pi.x > P.DL - P.cutoff || pi.x < P.cutoff) && ncx > 1;
+
+        for (int oy = -1; oy <= 1; ++oy) {
+            const int cy = cyi + oy;
+            if (cy < 0 || cy >= ncy) continue;
+            int cx_prev[2] = {-1, -1};
+            for (int ox = -1; ox <= 1; ++ox) {
+                int cx = cxi + ox;
+                if (cx < 0) cx += ncx;
+                else if (cx >= ncx) cx -= ncx;
+                if (cx < 0 || cx >= ncx) continue;
+                // n_cell_x <= 2: the wrapped stencil revisits a column.  The reference re-walks it, but
+                // every entry it accepted is already in seen_neighbor and every entry it rejected is
+                // rejected again by the same arithmetic (nb:342-372), so the revisit emits nothing.
+                if (cx == cx_prev[0] || cx == cx_prev[1]) continue;
+                cx_prev[ox == -1 ? 0 : 1] = cx;
+                const int cid = cy * ncx + cx;
+                const int e_end = cell_start[cid + 1];
+                for (int e = cell_start[cid]; e < e_end; ++e) {   // entries are stored last-inserted first
+                    const int key = ent_key[e];
+                    const int j = key >> 3;
+                    if (j == i) continue;
+                    const bool low_fluid = j < P.n_fluid && j < i;
+                    if (HALF && low_fluid) continue;                       // nb:353
+                    const bool seam = (key & 4) || (low_fluid && i_multi);
+                    if (seam) {   // seen_neighbor (nb:342): j may already be in the row through another entry
+                        bool dup = false;
+                        const int lim = count < P.ell_cap ? count : P.ell_cap;
+                        for (int q = 0; q < lim; ++q) dup |= ((int)(col[(size_t)q * stride + i] & kIdMask) == j);
+                        if (dup) continue;
+                    }
+                    int kind = key & 3, m;
+                    if (low_fluid && seam) {
+                        const double2 pj = snap[j];
+                        const int sh = replay_low_walk(pj.x, pj.y, cell_of[j], pi.x, pi.y, home, ncy, P);
+                        if (sh == 2) continue;
+                        kind = 0;
+                        m = -sh;
+                    } else {
+                        const double2 pe = ent_pos[e];
+                        if (!accept_entry(pi.x, pi.y, pe.x, pe.y, P, m)) continue;
+                    }
+                    if (count < P.ell_cap) col[(size_t)count * stride + i] = ell_pack(j, kind, m);
+                    ++count;
+                    n_half += low_fluid ? 0 : 1;
+                }
+            }
+        }
+        cnt[i] = count;
+    }
+    // totals: half pairs, full entries, longest row (capacity check)
+    int mx = count;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        n_half += __shfl_xor_sync(0xffffffffu, n_half, d);
+        count += __shfl_xor_sync(0xffffffffu, count, d);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_half) atomicAdd(&totals[0], n_half);
+        if (count) atomicAdd(&totals[1], count);
+        if (mx) atomicMax(&totals[2], mx);
+        if (mx > P.ell_cap) atomicOr(flags, kErrCsrCap);
+    }
+}
+
+// rows of the reference's half list inside a FULL row set: count of entries with j wall or j > i
+__global__ void __launch_bounds__(kBlock) k_half_count(NbrParams P, const unsigned *__restrict__ col,
+                                                      const int *__restrict__ cnt, int *__restrict__ half_cnt)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_fluid) return;
-    const int ncx = P.ncx, ncy = g->ncy;
-    const double2 pi = snap[i];
-    const int home = cell_of[i];
-    const int cxi = home % ncx, cyi = home / ncx;
-    const double half_DL = 0.5 * P.DL;
-    int seen[kSeenCap];
-    int nseen = 0;
-    int count = 0;
-    size_t hbase = 0;
-    if (FILL) hbase = (size_t)half_ptr[i];
-
-    for (int oy = -1; oy <= 1; ++oy) {
-        const int cy = cyi + oy;
-        if (cy < 0 || cy >= ncy) continue;
-        int cx_prev[2] = {-1, -1};
-        for (int ox = -1; ox <= 1; ++ox) {
-            int cx = cxi + ox;
-            if (cx < 0) cx += ncx;
-            else if (cx >= ncx) cx -= ncx;
-            if (cx < 0 || cx >= ncx) continue;
-            // n_cell_x <= 2: the wrapped stencil revisits a column.  The reference re-walks it, but
-            // every entry it accepted is already in seen_neighbor and every entry it rejected is
-            // rejected again by the same arithmetic (nb:342-372), so the revisit emits nothing.
-            if (cx == cx_prev[0] || cx == cx_prev[1]) continue;
-            cx_prev[ox == -1 ? 0 : 1] = cx;
-            const int cid = cy * ncx + cx;
-            const int s = cell_start[cid];
-            for (int e = cell_start[cid + 1] - 1; e >= s; --e) {
-                const int key = ent_key[e];
-                const int j = key >> 3;
-                if (j == i) continue;
-                if (key & 4) {   // particle j owns ghost entries: it may already have been accepted
-                    bool dup = false;
-                    for (int q = 0; q < nseen; ++q) dup |= (seen[q] == j);
-                    if (dup) continue;
-                }
-                if (j < P.n_fluid && j < i) continue;   // fluid-fluid pairs stored once, i < j (nb:353)
-                const double2 pe = ent_pos[e];
-                double dx = pi.x - pe.x;
-                int m = 0;                               // minimum image (nb:359-363)
-                if (dx > half_DL) {
-                    dx -= P.DL;
-                    m = -1;
-                } else if (dx < -half_DL) {
-                    dx += P.DL;
-                    m = 1;
-                }
-                const double dy = pi.y - pe.y;
-                const double r2 = dx * dx + dy * dy;
-                if (!(r2 > 1e-24 && r2 < P.rc2)) continue;
-                const double r = sqrt(r2);
-                double W, dW;
-                spline2d(r, P.h, P.sigma, W, dW);
-                if (!(W > 0.0 || fabs(dW) > 0.0)) continue;
-                // ---- accepted ----
-                const int kind = key & 3;
-                if (key & 4) {
-                    if (nseen < kSeenCap) seen[nseen++] = j;
-                    else atomicOr(flags, kErrSeenCap);
-                }
-                if (FILL) {
-                    const size_t hp = hbase + count;
-                    if (hp < P.half_cap) half_col[hp] = (unsigned)j | ((unsigned)kind << 30);
-                    if (want_csr) {
-                        // image shift of x_j as seen from i: ghost kind 1 sits at x_j - DL, kind 2 at x_j + DL
-                        const int sh = m + (kind == 1 ? 1 : (kind == 2 ? -1 : 0));
-                        const size_t a = (size_t)row_ptr[i] + atomicAdd(&row_fill[i], 1);
-                        if (a < P.csr_cap) col[a] = (unsigned)j | ((unsigned)(sh + 1) << 30);
-                        if (j < P.n_fluid) {
-                            const size_t b = (size_t)row_ptr[j] + atomicAdd(&row_fill[j], 1);
-                            if (b < P.csr_cap) col[b] = (unsigned)i | ((unsigned)(1 - sh) << 30);
-                        }
-                    }
-                } else if (want_csr && j < P.n_fluid) {
-                    atomicAdd(&row_cnt[j], 1);
-                }
-                ++count;
-            }
-        }
+    const int n = min(cnt[i], P.ell_cap);
+    int c = 0;
+    for (int k = 0; k < n; ++k) {
+        const int j = (int)(col[(size_t)k * P.ell_stride + i] & kIdMask);
+        c += (j >= P.n_fluid || j > i) ? 1 : 0;
     }
-    if (!FILL) {
-        half_cnt[i] = count;
-        if (want_csr) atomicAdd(&row_cnt[i], count);
-    }
-}
-
-__global__ void k_check_caps(NbrParams P, const int *__restrict__ half_ptr, const int *__restrict__ row_ptr,
-                             int want_csr, int *__restrict__ totals, int *__restrict__ flags)
-{
-    const int nh = half_ptr[P.n_fluid];
-    const int nc = want_csr ? row_ptr[P.n_fluid] : 0;
-    totals[0] = nh;
-    totals[1] = nc;
-    if ((size_t)nh > P.half_cap || (size_t)nc > P.csr_cap) atomicOr(flags, kErrCsrCap);
-}
-
-__global__ void __launch_bounds__(kBlock) k_row_sort(int n_fluid, const int *__restrict__ row_ptr, size_t csr_cap,
-                                                    unsigned *__restrict__ col)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_fluid) return;
-    const size_t s = (size_t)row_ptr[i];
-    size_t e = (size_t)row_ptr[i + 1];
-    if (e > csr_cap) e = csr_cap;
-    for (size_t a = s + 1; a < e; ++a) {
-        const unsigned v = col[a];
-        const unsigned key = v & kIdMask;
-        size_t b = a;
-        while (b > s && (col[b - 1] & kIdMask) > key) {
-            col[b] = col[b - 1];
-            --b;
-        }
-        col[b] = v;
-    }
+    half_cnt[i] = c;
 }
 
 // nb:357-381 re-evaluated for the stored (j, kind): identical operations, identical bits
 __global__ void __launch_bounds__(kBlock) k_export_pairs(NbrParams P, const double2 *__restrict__ snap,
+                                                        const unsigned *__restrict__ col,
+                                                        const int *__restrict__ cnt,
                                                         const int *__restrict__ half_ptr,
-                                                        const unsigned *__restrict__ half_col,
                                                         double *__restrict__ pair_i, double *__restrict__ pair_j,
                                                         double *__restrict__ odx, double *__restrict__ ody,
                                                         double *__restrict__ orr, double *__restrict__ oW,
@@ -368,28 +434,30 @@ __global__ void __launch_bounds__(kBlock) k_export_pairs(NbrParams P, const doub
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_fluid) return;
     const double2 pi = snap[i];
-    const double half_DL = 0.5 * P.DL;
-    const int s = half_ptr[i], e = half_ptr[i + 1];
-    for (int k = s; k < e; ++k) {
-        const unsigned v = half_col[k];
+    const int n = min(cnt[i], P.ell_cap);
+    size_t o = (size_t)half_ptr[i];
+    for (int k = 0; k < n; ++k) {
+        const unsigned v = col[(size_t)k * P.ell_stride + i];
         const int j = (int)(v & kIdMask);
-        const int kind = (int)(v >> 30);
+        if (j < P.n_fluid && j < i) continue;
+        const int kind = (int)((v >> 28) & 3u);
         const double2 pj = snap[j];
         const double ex = kind == 0 ? pj.x : (kind == 1 ? pj.x - P.DL : pj.x + P.DL);
         double dx = pi.x - ex;
-        if (dx > half_DL) dx -= P.DL;
-        else if (dx < -half_DL) dx += P.DL;
+        if (dx > P.half_DL) dx -= P.DL;
+        else if (dx < -P.half_DL) dx += P.DL;
         const double dy = pi.y - pj.y;
         const double r = sqrt(dx * dx + dy * dy);
         double W, dW;
         spline2d(r, P.h, P.sigma, W, dW);
-        pair_i[k] = (double)(i + 1);
-        pair_j[k] = (double)(j + 1);
-        odx[k] = dx;
-        ody[k] = dy;
-        orr[k] = r;
-        oW[k] = W;
-        odW[k] = dW;
+        pair_i[o] = (double)(i + 1);
+        pair_j[o] = (double)(j + 1);
+        odx[o] = dx;
+        ody[o] = dy;
+        orr[o] = r;
+        oW[o] = W;
+        odW[o] = dW;
+        ++o;
     }
 }
 
@@ -404,13 +472,15 @@ NbrParams make_params(const NeighborWork &w)
     P.cell = 2.0 * w.h;
     P.cutoff = 2.0 * w.h;
     P.rc2 = (2.0 * w.h) * (2.0 * w.h);
+    P.rc2_safe = P.rc2 * (1.0 - 1e-12);
+    P.half_DL = 0.5 * w.DL;
     P.sigma = 10.0 / (7.0 * pi * w.h * w.h);
     int ncx = (int)std::ceil(w.DL / P.cell);   // nb:254
     if (ncx < 1) ncx = 1;
     P.ncx = ncx;
     P.cell_cap = w.cell_cap;
-    P.half_cap = w.half_cap;
-    P.csr_cap = w.csr_cap;
+    P.ell_cap = w.ell_cap;
+    P.ell_stride = w.ell_stride;
     return P;
 }
 
@@ -419,8 +489,17 @@ NbrParams make_params(const NeighborWork &w)
 void NeighborWork::release_all()
 {
     DevBuf *all[] = {&grid, &flags, &snap, &cell_of, &cell_cnt, &cell_start, &cell_fill, &ent_key, &ent_pos,
-                     &half_cnt, &half_ptr, &half_col, &row_cnt, &row_ptr, &row_fill, &col, &scan_tmp, &totals};
+                     &ell_cnt, &ell_col, &half_cnt, &half_ptr, &scan_tmp, &totals};
     for (DevBuf *b : all) b->release();
+}
+
+int neighbor_reserve_ell(NeighborWork &w, int rows)
+{
+    if (rows <= w.ell_cap && w.ell_col.p) return 0;
+    w.ell_stride = ((size_t)w.n_fluid + 31) & ~(size_t)31;
+    SPHB_TRY(w.ell_col.reserve((size_t)rows * w.ell_stride * sizeof(unsigned)));
+    w.ell_cap = rows;
+    return 0;
 }
 
 // Size every buffer whose size is known a priori.  y hints bound the cell rows (a fluid particle
@@ -428,6 +507,7 @@ void NeighborWork::release_all()
 int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL, double y_min_hint,
                   double y_max_hint, int max_nbr_hint)
 {
+    const bool resized = n_fluid != w.n_fluid;
     w.n_fluid = n_fluid;
     w.n_total = n_total;
     w.h = h;
@@ -455,31 +535,20 @@ int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL
     SPHB_TRY(w.cell_fill.reserve(((size_t)w.cell_cap + 1) * sizeof(int)));
     SPHB_TRY(w.ent_key.reserve(3 * nt * sizeof(int)));
     SPHB_TRY(w.ent_pos.reserve(3 * nt * sizeof(double2)));
-    SPHB_TRY(w.half_cnt.reserve((nf + 1) * sizeof(int)));
-    SPHB_TRY(w.half_ptr.reserve((nf + 1) * sizeof(int)));
-    SPHB_TRY(w.row_cnt.reserve((nf + 1) * sizeof(int)));
-    SPHB_TRY(w.row_ptr.reserve((nf + 1) * sizeof(int)));
-    SPHB_TRY(w.row_fill.reserve((nf + 1) * sizeof(int)));
-    if (max_nbr_hint > 0) {
-        const size_t csr = nf * (size_t)max_nbr_hint;
-        const size_t half = nf * (size_t)((max_nbr_hint + 1) / 2 + 4);
-        if (csr > w.csr_cap) {
-            SPHB_TRY(w.col.reserve(csr * sizeof(unsigned)));
-            w.csr_cap = csr;
-        }
-        if (half > w.half_cap) {
-            SPHB_TRY(w.half_col.reserve(half * sizeof(unsigned)));
-            w.half_cap = half;
-        }
+    SPHB_TRY(w.ell_cnt.reserve((nf + 1) * sizeof(int)));
+    if (resized) {
+        w.ell_cap = 0;   // the stride depends on n_fluid
+        w.ell_col.release();
     }
+    SPHB_TRY(neighbor_reserve_ell(w, max_nbr_hint > 0 ? max_nbr_hint : kDefaultEllRows));
     return 0;
 }
 
-// Builds the lists from `pos` (device, double2[n_total]).  When a capacity is exceeded the build stops
-// after the counting pass, synchronises, grows the buffer and continues (stateless path and first
-// resident build); in steady state no host synchronisation happens.
-int neighbor_build(NeighborWork &w, const double2 *pos, bool want_full_csr, cudaStream_t st, long long *launches,
-                   Prof *prof)
+// Builds the list from `pos` (device, double2[n_total]).  A row longer than the ELL raises the
+// capacity flag; with `exact` the build then synchronises, grows the ELL to the longest row and walks
+// again (stateless path and the first resident build); in steady state there is no host round trip.
+int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exact, cudaStream_t st,
+                   long long *launches, Prof *prof)
 {
     NbrParams P = make_params(w);
     GridDesc *g = w.grid.as<GridDesc>();
@@ -520,79 +589,56 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool want_full_csr, cuda
     }
     nl += 2;
 
-    {
-        ProfScope ps(prof, kPfNbrWalkCount, st);
-        if (want_full_csr) SPHB_CUDA(cudaMemsetAsync(w.row_cnt.p, 0, ((size_t)nf + 1) * sizeof(int), st));
-        k_half_walk<false><<<grid_for(nf), kBlock, 0, st>>>(
-            P, g, w.snap.as<double2>(), w.cell_of.as<int>(), w.cell_start.as<int>(), w.ent_key.as<int>(),
-            w.ent_pos.as<double2>(), w.half_cnt.as<int>(), w.row_cnt.as<int>(), nullptr, nullptr, nullptr, nullptr,
-            nullptr, want_full_csr ? 1 : 0, flags);
-    }
-    nl += 1;
-    {
-        ProfScope ps(prof, kPfNbrScan, st);
-        SPHB_TRY(exclusive_scan_i32(w.half_cnt.as<int>(), w.half_ptr.as<int>(), (size_t)nf, w.scan_tmp, nullptr, st,
-                                    &nl));
-        if (want_full_csr)
-            SPHB_TRY(exclusive_scan_i32(w.row_cnt.as<int>(), w.row_ptr.as<int>(), (size_t)nf, w.scan_tmp, nullptr, st,
-                                        &nl));
-    }
-
-    // capacity: known-sufficient in steady state; otherwise read the totals back once and grow
-    bool need_sync = (w.half_cap == 0) || (want_full_csr && w.csr_cap == 0);
-    if (!need_sync) {
-        k_check_caps<<<1, 1, 0, st>>>(P, w.half_ptr.as<int>(), w.row_ptr.as<int>(), want_full_csr ? 1 : 0,
-                                      w.totals.as<int>(), flags);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        ProfScope ps(prof, kPfNbrWalk, st);
+        SPHB_CUDA(cudaMemsetAsync(w.totals.p, 0, 4 * sizeof(int), st));
+        if (half_only)
+            k_walk<true><<<grid_for(nf), kBlock, 0, st>>>(P, g, w.snap.as<double2>(), w.cell_of.as<int>(),
+                                                          w.cell_start.as<int>(), w.ent_key.as<int>(),
+                                                          w.ent_pos.as<double2>(), w.ell_col.as<unsigned>(),
+                                                          w.ell_cnt.as<int>(), w.totals.as<int>(), flags);
+        else
+            k_walk<false><<<grid_for(nf), kBlock, 0, st>>>(P, g, w.snap.as<double2>(), w.cell_of.as<int>(),
+                                                           w.cell_start.as<int>(), w.ent_key.as<int>(),
+                                                           w.ent_pos.as<double2>(), w.ell_col.as<unsigned>(),
+                                                           w.ell_cnt.as<int>(), w.totals.as<int>(), flags);
         nl += 1;
-    } else {
-        int nh = 0, nc = 0;
-        SPHB_CUDA(cudaMemcpyAsync(&nh, w.half_ptr.as<int>() + nf, sizeof(int), cudaMemcpyDeviceToHost, st));
-        if (want_full_csr)
-            SPHB_CUDA(cudaMemcpyAsync(&nc, w.row_ptr.as<int>() + nf, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (!exact || attempt == 1) break;
+        int host[4] = {0, 0, 0, 0};
+        SPHB_CUDA(cudaMemcpyAsync(host, w.totals.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         SPHB_CUDA(cudaStreamSynchronize(st));
-        const size_t half_need = (size_t)nh + (size_t)nh / 4 + 1024;   // 25 % head-room for later rebuilds
-        const size_t csr_need = (size_t)nc + (size_t)nc / 4 + 1024;
-        if (half_need > w.half_cap) {
-            SPHB_TRY(w.half_col.reserve(half_need * sizeof(unsigned)));
-            w.half_cap = half_need;
-        }
-        if (want_full_csr && csr_need > w.csr_cap) {
-            SPHB_TRY(w.col.reserve(csr_need * sizeof(unsigned)));
-            w.csr_cap = csr_need;
-        }
+        if (host[2] <= w.ell_cap) break;
+        // grow to the longest row (+ head-room for later rebuilds) and walk again
+        SPHB_TRY(neighbor_reserve_ell(w, host[2] + host[2] / 4 + 4));
+        int f = 0;
+        SPHB_CUDA(cudaMemcpyAsync(&f, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SPHB_CUDA(cudaStreamSynchronize(st));
+        f &= ~kErrCsrCap;
+        SPHB_CUDA(cudaMemcpyAsync(flags, &f, sizeof(int), cudaMemcpyHostToDevice, st));
+        SPHB_CUDA(cudaStreamSynchronize(st));
         P = make_params(w);
-        k_check_caps<<<1, 1, 0, st>>>(P, w.half_ptr.as<int>(), w.row_ptr.as<int>(), want_full_csr ? 1 : 0,
-                                      w.totals.as<int>(), flags);
-        nl += 1;
     }
-
-    {
-        ProfScope ps(prof, kPfNbrWalkFill, st);
-        if (want_full_csr) SPHB_CUDA(cudaMemsetAsync(w.row_fill.p, 0, ((size_t)nf + 1) * sizeof(int), st));
-        k_half_walk<true><<<grid_for(nf), kBlock, 0, st>>>(
-            P, g, w.snap.as<double2>(), w.cell_of.as<int>(), w.cell_start.as<int>(), w.ent_key.as<int>(),
-            w.ent_pos.as<double2>(), nullptr, nullptr, w.half_ptr.as<int>(), w.row_ptr.as<int>(),
-            w.row_fill.as<int>(), w.half_col.as<unsigned>(), w.col.as<unsigned>(), want_full_csr ? 1 : 0, flags);
-    }
-    nl += 1;
-    if (want_full_csr) {
-        ProfScope ps(prof, kPfNbrRowSort, st);
-        k_row_sort<<<grid_for(nf), kBlock, 0, st>>>(nf, w.row_ptr.as<int>(), w.csr_cap, w.col.as<unsigned>());
-        nl += 1;
-    }
+    w.half_only = half_only;
     SPHB_CUDA(cudaGetLastError());
     if (launches) *launches += nl;
     return 0;
 }
 
+// The reference's half-pair COO list from the ELL rows (device output pointers, n_half slots each).
 int neighbor_export_pairs(NeighborWork &w, size_t n_half, double *pair_i, double *pair_j, double *dx, double *dy,
                           double *r, double *W, double *dW, cudaStream_t st)
 {
     (void)n_half;
     NbrParams P = make_params(w);
-    k_export_pairs<<<grid_for(w.n_fluid), kBlock, 0, st>>>(P, w.snap.as<double2>(), w.half_ptr.as<int>(),
-                                                           w.half_col.as<unsigned>(), pair_i, pair_j, dx, dy, r, W,
-                                                           dW);
+    const size_t nf = (size_t)w.n_fluid;
+    SPHB_TRY(w.half_cnt.reserve((nf + 1) * sizeof(int)));
+    SPHB_TRY(w.half_ptr.reserve((nf + 1) * sizeof(int)));
+    k_half_count<<<grid_for(nf), kBlock, 0, st>>>(P, w.ell_col.as<unsigned>(), w.ell_cnt.as<int>(),
+                                                  w.half_cnt.as<int>());
+    SPHB_TRY(exclusive_scan_i32(w.half_cnt.as<int>(), w.half_ptr.as<int>(), nf, w.scan_tmp, nullptr, st, nullptr));
+    k_export_pairs<<<grid_for(nf), kBlock, 0, st>>>(P, w.snap.as<double2>(), w.ell_col.as<unsigned>(),
+                                                    w.ell_cnt.as<int>(), w.half_ptr.as<int>(), pair_i, pair_j, dx, dy,
+                                                    r, W, dW);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -1,5 +1,5 @@
 // ops_csr.cu -- fp64 physics operators of the DEVICE-RESIDENT path as per-particle gathers over the
-// CSR neighbour list (rows P1-P9 and the epilogues of S1 in SURVEY.md 8(a)).
+// ELL neighbour list (column-major, so a warp's k-th neighbour indices are one coalesced load) (rows P1-P9 and the epilogues of S1 in SURVEY.md 8(a)).
 //
 // One thread owns one particle and walks its CSR row; every pair is therefore evaluated from both
 // ends, there are no atomics and the sums are deterministic.  All the reference's pair formulas are
@@ -8,7 +8,7 @@
 //
 // Geometry is FROZEN at list-build time, as in the reference, where every mode consumes the pair
 // cache computed by the neighbour search: dx = (x_i - x_j) + shift*DL from the
-// position snapshot `snap` and the image code stored in the top two bits of each CSR entry.
+// position snapshot `snap` and the image code stored in the top four bits of each list entry.
 //
 // Fusion: viscous + transport share one row walk (same inputs B_j, Vol_j); the pressure kernel
 // recomputes the neighbour's half-step density/pressure inline (ph:857-862) and its epilogue does the
@@ -23,37 +23,53 @@ namespace sphb {
 
 namespace {
 
-constexpr unsigned kIdMask = 0x3fffffffu;
+constexpr unsigned kIdMask = 0x0fffffffu;
 
+// Geometry of one list entry, recomputed from the position snapshot (16 B gathered per neighbour
+// instead of the reference's 40 B cached per pair): e points from j to i, g.dW is dW/dr.
 struct Geo {
-    double dx, dy, r;
+    double dx, dy, r, ex, ey;
 };
 
-__device__ __forceinline__ Geo pair_geometry(double2 pi, double2 pj, unsigned entry, double DL)
+__device__ __forceinline__ int entry_j(unsigned c) { return (int)(c & kIdMask); }
+
+__device__ __forceinline__ Geo pair_geometry(double2 pi, double2 pj, unsigned c, const PhysParams &P)
 {
     Geo g;
-    const double sh = (double)((int)(entry >> 30) - 1);
-    g.dx = (pi.x - pj.x) + sh * DL;
+    const int kind = (int)((c >> 28) & 3u);
+    const int sh = (int)(c >> 30) - 1 + (kind == 1 ? 1 : 0) - (kind == 2 ? 1 : 0);
+    const double shift = sh == 0 ? 0.0 : (sh > 0 ? P.DL : -P.DL);
+    g.dx = (pi.x - pj.x) + shift;
     g.dy = pi.y - pj.y;
-    g.r = sqrt(g.dx * g.dx + g.dy * g.dy);
+    const double r2 = g.dx * g.dx + g.dy * g.dy;
+    const double inv_r = fast_rsqrt(r2);
+    g.r = r2 * inv_r;
+    g.ex = g.dx * inv_r;
+    g.ey = g.dy * inv_r;
     return g;
 }
 
 // cubic spline, nb:116-133 (r < 2h is guaranteed by the list)
-__device__ __forceinline__ double spline_W(double r, double h, double sigma)
+__device__ __forceinline__ double spline_W(double r, const PhysParams &P)
 {
-    const double q = r / h;
-    if (q < 1.0) return sigma * (1.0 - 1.5 * q * q + 0.75 * q * q * q);
-    const double t = 2.0 - q;
-    return t > 0.0 ? sigma * 0.25 * t * t * t : 0.0;
+    const double q = r * P.inv_h;
+    if (q < 1.0) return P.sigma * (1.0 - q * q * (1.5 - 0.75 * q));
+    const double t = fmax(2.0 - q, 0.0);
+    return 0.25 * P.sigma * t * t * t;
 }
-__device__ __forceinline__ double spline_dW(double r, double h, double sigma)
+__device__ __forceinline__ double spline_dW(double r, const PhysParams &P)
 {
-    const double q = r / h;
-    if (q < 1.0) return sigma * (-3.0 * q + 2.25 * q * q) / h;
-    const double t = 2.0 - q;
-    return t > 0.0 ? -sigma * 0.75 * t * t / h : 0.0;
+    const double q = r * P.inv_h;
+    if (q < 1.0) return P.sigma_h * q * (2.25 * q - 3.0);
+    const double t = fmax(2.0 - q, 0.0);
+    return -0.75 * P.sigma_h * t * t;
 }
+
+#define SPHB_FOR_NEIGHBOURS(i, k, c)                                                     \
+    const int n_nb__ = min(S.ell_cnt[i], S.ell_cap);                                     \
+    const unsigned *col__ = S.ell_col + (i);                                             \
+    for (int k = 0; k < n_nb__; ++k)                                                     \
+        if (unsigned c = col__[(size_t)k * S.ell_stride]; true)
 
 // ---------------------------------------------------------------- P1 pass 1: sigma sums -> rho, Vol
 __global__ void __launch_bounds__(kBlock) k_density(PhysParams P, StateView S)
@@ -69,14 +85,13 @@ __global__ void __launch_bounds__(kBlock) k_density(PhysParams P, StateView S)
     const double2 pi = S.snap[i];
     double s_in = P.sigma;   // W(0), ph:178-181
     double s_ct = 0.0;
-    const int e = S.row_ptr[i + 1];
-    for (int k = S.row_ptr[i]; k < e; ++k) {
-        const unsigned c = S.col[k];
-        const int j = (int)(c & kIdMask);
-        const Geo g = pair_geometry(pi, S.snap[j], c, P.DL);
-        const double W = spline_W(g.r, P.h, P.sigma);
+    SPHB_FOR_NEIGHBOURS(i, k, c)
+    {
+        const int j = entry_j(c);
+        const Geo g = pair_geometry(pi, S.snap[j], c, P);
+        const double W = spline_W(g.r, P);
         if (j < P.nf) s_in += W;
-        else s_ct += W * (S.mass[j] / P.rho0);
+        else s_ct += W * (S.mass[j] * P.inv_rho0);
     }
     double rho = s_in * P.rho0 * P.inv_sigma0;
     rho += s_ct * P.rho0 * P.rho0 * P.inv_sigma0 / m_i;
@@ -98,18 +113,17 @@ __global__ void __launch_bounds__(kBlock) k_kgc(PhysParams P, StateView S)
     if (i < P.nf) {
         const double2 pi = S.snap[i];
         double a11 = 0.0, a12 = 0.0, a21 = 0.0, a22 = 0.0;
-        const int e = S.row_ptr[i + 1];
-        for (int k = S.row_ptr[i]; k < e; ++k) {
-            const unsigned c = S.col[k];
-            const int j = (int)(c & kIdMask);
-            const Geo g = pair_geometry(pi, S.snap[j], c, P.DL);
-            if (g.r <= 1e-12) continue;
-            const double f = spline_dW(g.r, P.h, P.sigma) * S.Vol[j];
-            const double ex = g.dx / g.r, ey = g.dy / g.r;
-            a11 -= g.dx * (f * ex);
-            a12 -= g.dx * (f * ey);
-            a21 -= g.dy * (f * ex);
-            a22 -= g.dy * (f * ey);
+        SPHB_FOR_NEIGHBOURS(i, k, c)
+        {
+            const int j = entry_j(c);
+            const Geo g = pair_geometry(pi, S.snap[j], c, P);
+            if (!(g.r > 1e-12)) continue;
+            const double f = spline_dW(g.r, P) * S.Vol[j];
+            const double fx = f * g.ex, fy = f * g.ey;
+            a11 -= g.dx * fx;
+            a12 -= g.dx * fy;
+            a21 -= g.dy * fx;
+            a22 -= g.dy * fy;
         }
         kgc_from_A(a11, a12, a21, a22, B.b11, B.b12, B.b21, B.b22);
     }
@@ -130,47 +144,43 @@ __global__ void __launch_bounds__(kBlock) k_visc_transport(PhysParams P, StateVi
     const double2 vi = S.vel[i];
     const Mat2 Bi = S.B[i];
     const double Vi = S.Vol[i];
+    const double h001 = 0.01 * P.h;
     double ax = 0.0, ay = 0.0, ix = 0.0, iy = 0.0;
-    const int e = S.row_ptr[i + 1];
-    for (int k = S.row_ptr[i]; k < e; ++k) {
-        const unsigned c = S.col[k];
-        const int j = (int)(c & kIdMask);
-        const Geo g = pair_geometry(pi, S.snap[j], c, P.DL);
-        if (g.r <= 1e-12) continue;
-        const double ex = g.dx / g.r, ey = g.dy / g.r;
-        const double dW = spline_dW(g.r, P.h, P.sigma);
-        const double Vj = S.Vol[j];
+    SPHB_FOR_NEIGHBOURS(i, k, c)
+    {
+        const int j = entry_j(c);
+        const Geo g = pair_geometry(pi, S.snap[j], c, P);
+        if (!(g.r > 1e-12)) continue;
+        const double ex = g.ex, ey = g.ey;
+        const double gj = spline_dW(g.r, P) * S.Vol[j];
+        double tx, ty, wv, wt;
+        double2 vj;
         if (j < P.nf) {
             const Mat2 Bj = S.B[j];
             const double s11 = Bi.b11 + Bj.b11, s12 = Bi.b12 + Bj.b12;
             const double s21 = Bi.b21 + Bj.b21, s22 = Bi.b22 + Bj.b22;
-            const double tx = s11 * ex + s12 * ey, ty = s21 * ex + s22 * ey;
-            if (VISC) {
-                const double2 vj = S.vel[j];
-                const double eBe = ex * tx + ey * ty;
-                const double cf = eBe * P.mu * dW * Vj / (g.r + 0.01 * P.h);
-                ax += cf * (vi.x - vj.x);
-                ay += cf * (vi.y - vj.y);
-            }
-            if (TRANSP) {
-                const double ci = -dW * Vj;
-                ix += ci * tx;
-                iy += ci * ty;
-            }
+            tx = s11 * ex + s12 * ey;
+            ty = s21 * ex + s22 * ey;
+            wv = 1.0;
+            wt = 1.0;
+            if (VISC) vj = S.vel[j];
         } else {
-            const double tx = Bi.b11 * ex + Bi.b12 * ey, ty = Bi.b21 * ex + Bi.b22 * ey;
-            if (VISC) {
-                const double2 wj = S.wall_vel[j];
-                const double eBe = ex * tx + ey * ty;
-                const double cf = 4.0 * eBe * P.mu * dW * Vj / (g.r + 0.01 * P.h);   // no-slip mirror, ph:526
-                ax += cf * (vi.x - wj.x);
-                ay += cf * (vi.y - wj.y);
-            }
-            if (TRANSP) {
-                const double ci = -2.0 * dW * Vj;   // ph:690
-                ix += ci * tx;
-                iy += ci * ty;
-            }
+            tx = Bi.b11 * ex + Bi.b12 * ey;
+            ty = Bi.b21 * ex + Bi.b22 * ey;
+            wv = 4.0;   // no-slip mirror, ph:526
+            wt = 2.0;   // ph:690
+            if (VISC) vj = S.wall_vel[j];
+        }
+        if (VISC) {
+            const double eBe = ex * tx + ey * ty;
+            const double cf = wv * eBe * P.mu * gj * fast_rcp(g.r + h001);
+            ax += cf * (vi.x - vj.x);
+            ay += cf * (vi.y - vj.y);
+        }
+        if (TRANSP) {
+            const double ci = -wt * gj;
+            ix += ci * tx;
+            iy += ci * ty;
         }
     }
     if (VISC) {
@@ -191,8 +201,18 @@ __global__ void __launch_bounds__(kBlock) k_visc_transport(PhysParams P, StateVi
     }
 }
 
-// ---------------------------------------------------------------- dt on the device (m:519-527)
-__global__ void k_time_step(PhysParams P, DevScalars *sc, double remain, double fixed_dt)
+__device__ __forceinline__ double half_step_rho(double rho, double drho, double dt, double rho0)
+{
+    double r = rho + 0.5 * dt * drho;   // ph:858
+    if (r < 1e-10) r = rho0;            // ph:859-861
+    return r;
+}
+
+// ---------------------------------------------------------------- dt on the device (m:519-527) and the
+// half-step density / pressure of every particle (ph:857-862), which the pressure gather reads per
+// neighbour.  Every thread derives the same dt from the device vmax; thread 0 publishes it.
+__global__ void __launch_bounds__(kBlock) k_time_step(PhysParams P, StateView S, DevScalars *sc, double remain,
+                                                     double fixed_dt)
 {
     double dt;
     if (fixed_dt > 0.0) {
@@ -205,8 +225,15 @@ __global__ void k_time_step(PhysParams P, DevScalars *sc, double remain, double 
         dt = fmin(fmin(dt_a, dt_v), fmin(dt_b, remain));
         dt = fmax(dt, 1e-12);
     }
-    sc->dt = dt;
-    sc->vmax_bits = 0ull;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        sc->dt = dt;
+        sc->vmax_bits = 0ull;
+    }
+    if (i < P.nf) {
+        const double rho_h = half_step_rho(S.rho[i], S.drho_dt[i], dt, P.rho0);
+        S.rp_half[i] = make_double2(rho_h, P.p0 * (rho_h / P.rho0 - 1.0));   // ph:862
+    }
 }
 
 __global__ void k_advance_clock(DevScalars *sc)
@@ -214,13 +241,6 @@ __global__ void k_advance_clock(DevScalars *sc)
     sc->t += sc->dt;
     sc->step += 1;
     sc->vmax = __longlong_as_double((long long)sc->vmax_bits);
-}
-
-__device__ __forceinline__ double half_step_rho(double rho, double drho, double dt, double rho0)
-{
-    double r = rho + 0.5 * dt * drho;   // ph:858
-    if (r < 1e-10) r = rho0;            // ph:859-861
-    return r;
 }
 
 // ---------------------------------------------------------------- P4 + velocity kick + position update
@@ -239,50 +259,44 @@ __global__ void __launch_bounds__(kBlock) k_pressure(PhysParams P, StateView S, 
     const Mat2 Bi = S.B[i];
     const double Vi = S.Vol[i], m_i = S.mass[i];
     const double2 fp = S.force_prior[i];
-    const double rho_i = half_step_rho(S.rho[i], S.drho_dt[i], dt, P.rho0);
-    const double p_i = P.p0 * (rho_i / P.rho0 - 1.0);   // ph:862
+    const double2 rpi = S.rp_half[i];
+    const double rho_i = rpi.x, p_i = rpi.y;
+    const double inv_m = 1.0 / m_i;
+    const double wax = fp.x * inv_m, way = fp.y * inv_m;   // a = F_prior / m, ph:929-930
     double fx = 0.0, fy = 0.0;
-    const int e = S.row_ptr[i + 1];
-    for (int k = S.row_ptr[i]; k < e; ++k) {
-        const unsigned c = S.col[k];
-        const int j = (int)(c & kIdMask);
-        const Geo g = pair_geometry(pi, S.snap[j], c, P.DL);
-        if (g.r <= 1e-12) continue;
-        const double ex = g.dx / g.r, ey = g.dy / g.r;
-        const double gj = spline_dW(g.r, P.h, P.sigma) * S.Vol[j];
+    SPHB_FOR_NEIGHBOURS(i, k, c)
+    {
+        const int j = entry_j(c);
+        const Geo g = pair_geometry(pi, S.snap[j], c, P);
+        if (!(g.r > 1e-12)) continue;
+        const double ex = g.ex, ey = g.ey;
+        const double gj = spline_dW(g.r, P) * S.Vol[j];
         if (j < P.nf) {
-            const double rho_j = half_step_rho(S.rho[j], S.drho_dt[j], dt, P.rho0);
-            const double p_j = P.p0 * (rho_j / P.rho0 - 1.0);
+            const double2 rpj = S.rp_half[j];
             const double2 vj = S.vel[j];
             const Mat2 Bj = S.B[j];
-            const double rho_bar = 0.5 * (rho_i + rho_j);
-            const double ul = vi.x * ex + vi.y * ey;
-            const double ur = vj.x * ex + vj.y * ey;
-            double comp = ul - ur;
-            if (comp < 0.0) comp = 0.0;
-            const double beta = fmin(3.0 * comp, P.c_f);   // ph:1121-1129
-            const double p_star = 0.5 * (p_i + p_j) + 0.5 * beta * rho_bar * (ul - ur);
-            const double p_face = 0.5 * (0.5 * (p_i + p_j) + p_star);
-            const double tx = p_face * ((Bi.b11 + Bj.b11) * ex + (Bi.b12 + Bj.b12) * ey);
-            const double ty = p_face * ((Bi.b21 + Bj.b21) * ex + (Bi.b22 + Bj.b22) * ey);
-            fx -= tx * gj;
-            fy -= ty * gj;
+            const double rho_bar = 0.5 * (rho_i + rpj.x);
+            const double du = (vi.x - vj.x) * ex + (vi.y - vj.y) * ey;   // u_l - u_r
+            const double beta = fmin(3.0 * fmax(du, 0.0), P.c_f);        // ph:1121-1129
+            const double p_avg = 0.5 * (p_i + rpj.y);
+            const double p_star = p_avg + 0.5 * beta * rho_bar * du;
+            const double pg = 0.5 * (p_avg + p_star) * gj;
+            fx -= pg * ((Bi.b11 + Bj.b11) * ex + (Bi.b12 + Bj.b12) * ey);
+            fy -= pg * ((Bi.b21 + Bj.b21) * ex + (Bi.b22 + Bj.b22) * ey);
         } else {
-            const double ax = fp.x / m_i, ay = fp.y / m_i;
-            const double ext = -(ax * ex + ay * ey);
+            const double ext = -(wax * ex + way * ey);
             const double pw = p_i + rho_i * g.r * fmax(0.0, ext);   // virtual wall pressure, ph:934
-            const double tx = Bi.b11 * ex + Bi.b12 * ey, ty = Bi.b21 * ex + Bi.b22 * ey;
-            fx -= (p_i + pw) * gj * tx;
-            fy -= (p_i + pw) * gj * ty;
+            const double pg = (p_i + pw) * gj;
+            fx -= pg * (Bi.b11 * ex + Bi.b12 * ey);
+            fy -= pg * (Bi.b21 * ex + Bi.b22 * ey);
         }
     }
     fx *= Vi;
     fy *= Vi;
     S.force[i] = make_double2(fx, fy);
-    const double inv_m = 1.0 / m_i;
     double2 vn;
-    vn.x = vi.x + (fp.x + fx) * inv_m * dt;   // ph:1402-1403
-    vn.y = vi.y + (fp.y + fy) * inv_m * dt;
+    vn.x = vi.x + (fp.x + fx) / m_i * dt;   // ph:1402-1403
+    vn.y = vi.y + (fp.y + fy) / m_i * dt;
     S.vel_new[i] = vn;
     double2 x = S.pos[i];
     x.x += 0.5 * dt * vi.x;   // ph:863-864
@@ -294,6 +308,7 @@ __global__ void __launch_bounds__(kBlock) k_pressure(PhysParams P, StateView S, 
 
 __device__ __forceinline__ double wrap_x(double x, double DL)   // MATLAB mod(x, DL), m:573
 {
+    if (x >= 0.0 && x < DL) return x;
     double m = fmod(x, DL);
     if (m < 0.0) m += DL;
     return m;
@@ -309,26 +324,25 @@ __global__ void __launch_bounds__(kBlock) k_continuity(PhysParams P, StateView S
         const double2 pi = S.snap[i];
         const double2 vi = S.vel_new[i];
         double rate = 0.0;
-        const int e = S.row_ptr[i + 1];
-        for (int k = S.row_ptr[i]; k < e; ++k) {
-            const unsigned c = S.col[k];
-            const int j = (int)(c & kIdMask);
-            const Geo g = pair_geometry(pi, S.snap[j], c, P.DL);
-            if (g.r <= 1e-12) continue;
-            const double ex = g.dx / g.r, ey = g.dy / g.r;
-            const double gj = spline_dW(g.r, P.h, P.sigma) * S.Vol[j];
-            double u;
+        SPHB_FOR_NEIGHBOURS(i, k, c)
+        {
+            const int j = entry_j(c);
+            const Geo g = pair_geometry(pi, S.snap[j], c, P);
+            if (!(g.r > 1e-12)) continue;
+            const double gj = spline_dW(g.r, P) * S.Vol[j];
+            double ux, uy;
             if (j < P.nf) {
                 const double2 vj = S.vel_new[j];
-                u = (vi.x - vj.x) * ex + (vi.y - vj.y) * ey;
+                ux = vi.x - vj.x;
+                uy = vi.y - vj.y;
             } else {
                 const double2 wj = S.wall_vel[j];
-                const double mx = 2.0 * wj.x - vi.x, my = 2.0 * wj.y - vi.y;   // mirrored velocity, ph:1101-1102
-                u = (vi.x - mx) * ex + (vi.y - my) * ey;
+                ux = vi.x - (2.0 * wj.x - vi.x);   // mirrored velocity, ph:1101-1102
+                uy = vi.y - (2.0 * wj.y - vi.y);
             }
-            rate += u * gj;
+            rate += (ux * g.ex + uy * g.ey) * gj;
         }
-        const double rho_h = half_step_rho(S.rho[i], S.drho_dt[i], dt, P.rho0);
+        const double rho_h = S.rp_half[i].x;
         const double drho = rate * rho_h;          // ph:1112
         double rho = rho_h + drho * (0.5 * dt);    // ph:1441
         if (rho < 1e-10) rho = P.rho0;
@@ -379,29 +393,29 @@ __global__ void __launch_bounds__(kBlock) k_wrap(int nf, double DL, double2 *pos
 }
 
 // ---------------------------------------------------------------- P8 wall shear (ph:1713-1742)
-// Rows are sorted by j, so the wall entries (j >= n_fluid) sit at the end of each row.
+// Only wall particles at y <= 0 or y >= DH count (ph:1731-1736) and the pair distance is < 2h, so a
+// fluid particle with 2h <= y <= DH - 2h cannot contribute: those rows are skipped unread.
 __global__ void __launch_bounds__(256) k_wall_shear(PhysParams P, StateView S, double *partials)
 {
     double sb = 0.0, st = 0.0;
+    const double band = 2.0 * P.h;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.nf; i += gridDim.x * blockDim.x) {
-        const int s = S.row_ptr[i];
-        int k = S.row_ptr[i + 1] - 1;
-        if (k < s || (int)(S.col[k] & kIdMask) < P.nf) continue;
         const double2 pi = S.snap[i];
+        if (pi.y >= band && pi.y <= P.DH - band) continue;
         const double vx = S.vel[i].x;
         const Mat2 Bi = S.B[i];
         const double Vi = S.Vol[i];
-        for (; k >= s; --k) {
-            const unsigned c = S.col[k];
-            const int j = (int)(c & kIdMask);
-            if (j < P.nf) break;
+        SPHB_FOR_NEIGHBOURS(i, k, c)
+        {
+            const int j = entry_j(c);
+            if (j < P.nf) continue;
             const double2 pj = S.snap[j];
-            const Geo g = pair_geometry(pi, pj, c, P.DL);
-            if (g.r <= 1e-12) continue;
-            const double ex = g.dx / g.r, ey = g.dy / g.r;
+            const Geo g = pair_geometry(pi, pj, c, P);
+            if (!(g.r > 1e-12)) continue;
+            const double ex = g.ex, ey = g.ey;
             const double eBe = ex * (Bi.b11 * ex + Bi.b12 * ey) + ey * (Bi.b21 * ex + Bi.b22 * ey);
             const double dvx = vx - S.wall_vel[j].x;
-            const double f = 4.0 * P.mu * eBe * spline_dW(g.r, P.h, P.sigma) * S.Vol[j] * dvx / (g.r + 0.01 * P.h) * Vi;
+            const double f = 4.0 * P.mu * eBe * spline_dW(g.r, P) * S.Vol[j] * dvx / (g.r + 0.01 * P.h) * Vi;
             if (pj.y <= 0.0) sb += f;
             else if (pj.y >= P.DH) st += f;
         }
@@ -498,9 +512,10 @@ int csr_visc_transport(const PhysParams &P, const StateView &S, bool do_visc, bo
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
-int csr_time_step(const PhysParams &P, DevScalars *sc, double remain, double fixed_dt, cudaStream_t st)
+int csr_time_step(const PhysParams &P, const StateView &S, DevScalars *sc, double remain, double fixed_dt,
+                  cudaStream_t st)
 {
-    k_time_step<<<1, 1, 0, st>>>(P, sc, remain, fixed_dt);
+    k_time_step<<<grid_for(P.nf), kBlock, 0, st>>>(P, S, sc, remain, fixed_dt);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }

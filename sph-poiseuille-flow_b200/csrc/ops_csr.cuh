@@ -20,7 +20,10 @@ struct DevScalars {
 struct PhysParams {
     int nf, nt;
     double h, DL, DH, rho0, p0, c_f, mu, nu, g, inv_sigma0, transport_coeff;
-    double sigma;    // 10/(7 pi h^2)
+    double sigma;      // 10/(7 pi h^2)
+    double inv_h;      // 1/h
+    double sigma_h;    // sigma/h
+    double inv_rho0;   // 1/rho0
 };
 
 // SoA state in HBM.  2-vectors are double2 (one 128-bit load per particle), B is one 32-byte record.
@@ -28,10 +31,13 @@ struct StateView {
     double2 *pos, *vel, *vel_new, *wall_vel, *force, *force_prior;
     double *rho, *p, *drho_dt, *mass, *Vol;
     Mat2 *B;
+    double2 *rp_half;   // (rho, p) at the half step of the current substep (ph:857-862), written by k_time_step
     // neighbour structures (frozen geometry = positions at list-build time)
     const double2 *snap;
-    const int *row_ptr;
-    const unsigned *col;
+    const int *ell_cnt;       // neighbours of fluid particle i
+    const unsigned *ell_col;  // col[k * ell_stride + i]: j | kind << 28 | (m + 1) << 30
+    size_t ell_stride;
+    int ell_cap;
 };
 
 int csr_density(const PhysParams &P, const StateView &S, cudaStream_t st);                       // P1 pass 1
@@ -39,7 +45,8 @@ int csr_kgc(const PhysParams &P, const StateView &S, cudaStream_t st);          
 int csr_visc_transport(const PhysParams &P, const StateView &S, bool do_visc, bool add_gravity, bool do_transport,
                        cudaStream_t st);                                                         // P2 + P3
 // dt = min(acoustic, viscous, body, remain) from the device vmax (m:519-527); fixed_dt > 0 overrides
-int csr_time_step(const PhysParams &P, DevScalars *sc, double remain, double fixed_dt, cudaStream_t st);
+int csr_time_step(const PhysParams &P, const StateView &S, DevScalars *sc, double remain, double fixed_dt,
+                  cudaStream_t st);
 int csr_pressure(const PhysParams &P, const StateView &S, const DevScalars *sc, cudaStream_t st);    // P4 + kick
 int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool wrap, cudaStream_t st);  // P5 + finish
 int csr_advance_clock(DevScalars *sc, cudaStream_t st);                                          // t += dt, step++, vmax

@@ -5,6 +5,28 @@
 
 namespace sphb {
 
+// Reciprocal and reciprocal square root of a normal positive double: the SFU seed (MUFU.RCP64H /
+// MUFU.RSQ64H, ~2^-22) refined by two Newton steps on the FP64 pipe, ~1 ulp.  Used only by the physics
+// gathers (1e-11 gate); every decision about list membership uses IEEE sqrt and divide (neighbor.cu).
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x * y, y, 1.0);
+    y = fma(y * 0.5, e, y);
+    e = fma(-x * y, y, 1.0);
+    return fma(y * 0.5, e, y);
+}
+
 // KGC matrix from the accumulated A (ph:321-366): regularised pseudo-inverse blended with I.
 __device__ __forceinline__ void kgc_from_A(double a11, double a12, double a21, double a22, double &b11, double &b12, double &b21,
                            double &b22)
