@@ -67,6 +67,7 @@ def parse_args():
     ap.add_argument("--profile-steps", type=int, default=5)
     ap.add_argument("--cpu-baseline-steps", type=int, default=20, help="outer steps of the CPU sample (0 = skip)")
     ap.add_argument("--seed", type=int, default=12345)
+    ap.add_argument("--presort", action="store_true", help="experiment: apply the cell sort (m:529-568) once before timing")
     return ap.parse_args()
 
 
@@ -244,6 +245,8 @@ def b200_arm(args):
     pt = lp.channel_setup.developed(cfg, seed=args.seed + rank)     # one independent channel per rank
     nt, inner, K, W = pt.n_total, args.inner, args.steps, args.warmup
     ch = lp.channel_from_config(cfg, pt, device=local_rank)
+    if args.presort:
+        ch.sort_by_cell()
     ch.initialise()
     stream = torch.cuda.ExternalStream(ch.stream, device=torch.device("cuda", local_rank))
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")

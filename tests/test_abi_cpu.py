@@ -87,3 +87,37 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(sphb._Params) == 2 * 4 + 11 * 8 + 3 * 4 + 4   # ints, doubles, ints + tail pad
     assert ctypes.sizeof(sphb._Status) == 5 * 8 + 3 * 8 + 8
     assert ctypes.sizeof(sphb._Mat) == 24
+
+
+def test_mex_shims_load_and_keep_gateway_contract():
+    """The two MEX gateways (sph-poiseuille-flow_b200/mex/*.c) built against the stub MATLAB host:
+    symbols present, argument-count errors raised with the reference's identifiers (no GPU needed)."""
+    from oracle.mexhost import MexError, MexLibrary
+    path = os.path.join(ROOT, "sph-poiseuille-flow_b200", "libsphb_mex_stubhost.so")
+    if not os.path.exists(path):
+        import __graft_entry__ as ge
+        ge.build()
+    mex = MexLibrary(path)
+    assert mex.has("sphb_neighbor_mexFunction") and mex.has("sphb_physics_mexFunction")
+    pos = np.zeros((4, 2), order="F")
+    with pytest.raises(MexError) as e:
+        mex.call("sphb_neighbor_mexFunction", 7, pos, 2, 4, 0.1)
+    assert e.value.identifier == "SPH:Neighbor:nrhs"
+    with pytest.raises(MexError) as e:
+        mex.call("sphb_neighbor_mexFunction", 6, pos, 2, 4, 0.1, 1.0)
+    assert e.value.identifier == "SPH:Neighbor:nlhs"
+    with pytest.raises(MexError) as e:
+        mex.call("sphb_neighbor_mexFunction", 7, np.zeros((4, 3), order="F"), 2, 4, 0.1, 1.0)
+    assert e.value.identifier == "SPH:Neighbor:pos"
+    with pytest.raises(MexError) as e:
+        mex.call("sphb_neighbor_mexFunction", 7, pos, 2, 5, 0.1, 1.0)
+    assert e.value.identifier == "SPH:Neighbor:count"
+    with pytest.raises(MexError) as e:
+        mex.call("sphb_physics_mexFunction", 1, "no_such_mode")
+    assert e.value.identifier == "SPH:Physics:mode"
+    with pytest.raises(MexError) as e:
+        mex.call("sphb_physics_mexFunction", 3, "density_correction", 1.0)
+    assert e.value.identifier == "SPH:Physics:density:nrhs"
+    with pytest.raises(MexError) as e:
+        mex.call("sphb_physics_mexFunction", 2, "integration_verlet", *([1.0] * 21))
+    assert e.value.identifier == "SPH:Physics:verlet:nlhs"

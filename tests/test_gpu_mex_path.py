@@ -204,3 +204,73 @@ def test_reference_loop_through_gpu_mex(be, H, golden):
             for f in ("pos", "vel", "rho", "p", "drho_dt", "force", "force_prior", "Vol", "B"):
                 assert_close(getattr(st, f), g[f"s{k}_{f}"], f"step {k} {f}", tol=tol)
     assert_close(np.array([st.tau_bottom, st.tau_top]), g["tau"][119], "tau", tol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------
+# the compiled MEX shims, driven by the fake MATLAB host exactly like the reference's MEX files
+# ------------------------------------------------------------------------------------------------
+class _ShimBackend:
+    kind = "b200-mex-shim"
+
+    def __init__(self):
+        import os
+        from conftest import ROOT
+        from oracle.mexhost import MexLibrary
+        self.mex = MexLibrary(os.path.join(ROOT, "sph-poiseuille-flow_b200", "libsphb_mex_stubhost.so"))
+
+    def neighbor_search(self, pos, n_fluid, n_total, h, DL):
+        out = self.mex.call("sphb_neighbor_mexFunction", 7, pos, n_fluid, n_total, h, DL)
+        return tuple(o.ravel(order="F") for o in out)
+
+    def physics(self, mode, *args, nargout):
+        out = self.mex.call("sphb_physics_mexFunction", nargout, mode, *args)
+        return [o if o.shape[1] > 1 else o.ravel(order="F") for o in out]
+
+
+def test_mex_shims_all_modes_against_golden(be, H, golden):
+    """feval(mex, ...) as SPH_Poiseuille.m issues it -> MEX shim (C) -> C ABI -> sm_100a kernels."""
+    from oracle.gen_golden import ops_case
+    shim = _ShimBackend()
+    g = golden("ops_dp01_dev.npz")
+    prm = H.derive_params(dp=float(g["dp"]), c_f=float(g["c_f"]))
+    st = H.init_particles(prm)
+    st.pos = np.asfortranarray(g["in_pos"])
+    st.vel = np.asfortranarray(g["in_vel"])
+    st.drho_dt = g["in_drho_dt"].copy()
+    got = ops_case(shim, prm, st)
+    for k, v in got.items():
+        if k in PAIR_NAMES:
+            assert np.array_equal(v, g[k]), k
+        else:
+            assert_close(np.asarray(v), g[k], k)
+
+
+def test_mex_shims_error_identifiers_match_reference(be, H, oracle_be):
+    from oracle.mexhost import MexError
+    if oracle_be.kind != "reference":
+        pytest.skip("needs oracle/_ref")
+    shim = _ShimBackend()
+    prm = H.derive_params(dp=0.1)
+    st = H.init_particles(prm)
+    nf, nt = st.n_fluid, st.n_total
+    pi, pj, dx, dy, r, W, dW = oracle_be.neighbor_search(st.pos, nf, nt, prm.h, prm.DL)
+    cases = [
+        ("viscous_force", (pi, pj, dx, dy, r, dW, st.vel, st.Vol[:-1], st.B, prm.mu, prm.h, nf, nt, st.mass, st.wall_vel), 1),
+        ("viscous_force", (pi, pj, dx, dy, r, dW, st.vel, st.Vol, st.B[:, :3], prm.mu, prm.h, nf, nt, st.mass, st.wall_vel), 1),
+        ("transport_correction", (pi, pj, dx, dy, r, dW, st.Vol, st.B, st.pos[:-1], prm.h, nf, nt), 1),
+        ("integration_verlet", (pi, pj, dx, dy, r, dW, st.Vol, st.B, st.rho, st.mass, st.pos, st.vel, st.drho_dt[:-1],
+                                st.force_prior, 1e-3, nf, nt, prm.rho0, prm.p0, prm.c_f, st.wall_vel), 6),
+        ("integration_1st", (pi, pj, dx, dy, r, dW, st.Vol, st.B, st.rho, st.mass, st.pos, st.vel, st.drho_dt,
+                             st.force_prior[:-1], 1e-3, nf, nt, prm.rho0, prm.p0, prm.c_f, st.wall_vel), 5),
+        ("wall_shear_monitor", (pi, pj, dx, dy, r, dW, st.pos, st.vel[:-1], st.wall_vel, st.Vol, st.B, nf, prm.DL, prm.DH,
+                                prm.mu, prm.h), 2),
+        ("advance_shell_step", (pi, pj, dx, dy, r, W, dW, st.mass, st.pos, st.vel, st.wall_vel, st.rho[:-1], st.drho_dt,
+                                1e-3, nf, nt, prm.rho0, prm.p0, prm.c_f, prm.mu, prm.h, prm.inv_sigma0, prm.gravity_g), 9),
+        ("density_correction", (pi, pj, dx, dy, r, W, dW, st.mass, 0, nt, prm.rho0, prm.h, prm.inv_sigma0), 3),
+    ]
+    for mode, args, nout in cases:
+        with pytest.raises(MexError) as want:
+            oracle_be.physics(mode, *args, nargout=nout)
+        with pytest.raises(MexError) as got:
+            shim.physics(mode, *args, nargout=nout)
+        assert got.value.identifier == want.value.identifier, (mode, got.value.identifier, want.value.identifier)
