@@ -84,20 +84,21 @@ struct NeighborWork {
     double h = 0, DL = 0;
     int cell_cap = 0;            // allocated cells
     int ell_cap = 0;             // allocated ELL rows (longest storable neighbour row)
-    size_t ell_stride = 0;       // n_fluid rounded up to 32
+    size_t ell_stride = 0;       // entry capacity of the ELL rows (rows are indexed by ENTRY)
     bool half_only = false;      // the last build kept only the reference's half list
     DevBuf grid;                 // GridDesc
     DevBuf flags;                // int error flags
     DevBuf snap;                 // double2 [n_total]   wrapped x, y at build time
     DevBuf cell_of;              // int [n_total]       home cell of the real entry
+    DevBuf ent_of;               // int [n_total]       index of the real entry in the sorted entry array
     DevBuf cell_cnt;             // int [cell_cap+1]
     DevBuf cell_start;           // int [cell_cap+1]
     DevBuf cell_fill;            // int [cell_cap]
     DevBuf ent_key;              // int [3*n_total]     (particle << 3) | (multi << 2) | kind
     DevBuf ent_pos;              // double2 [3*n_total] entry coordinates (ghosts shifted by -+DL)
-    DevBuf ell_cnt;              // int [n_fluid]       neighbours of each fluid particle
-    DevBuf ell_col;              // uint [ell_cap * ell_stride], column-major: col[k * stride + i]
-                                 //   j (28 bits) | entry kind (2) | minimum-image shift + 1 (2)
+    DevBuf ell_cnt;              // int [ell_stride]    neighbours of the walker whose real entry is e
+    DevBuf ell_col;              // uint [ell_cap * ell_stride], column-major: col[k * stride + e]
+                                 //   accepted entry (28 bits) | min-image shift + 1 (2) | row offset + 1 (2)
     DevBuf half_cnt, half_ptr;   // int [n_fluid+1]     export only (reference half-pair list)
     DevBuf scan_tmp;             // scan workspace
     DevBuf totals;               // int[4]: n_half, n_full, longest row (device), read back on demand
@@ -152,6 +153,8 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
                    long long *launches, Prof *prof = nullptr);
 int neighbor_export_pairs(NeighborWork &w, size_t n_half, double *pair_i, double *pair_j, double *dx, double *dy,
                           double *r, double *W, double *dW, cudaStream_t st);   // device pointers
+
+int neighbor_export_csr(NeighborWork &w, int *row_ptr, int *col, cudaStream_t st);   // device pointers
 
 // scan.cu
 int exclusive_scan_i32(const int *in, int *out, size_t n, DevBuf &tmp, int *total_out_dev, cudaStream_t st,

@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "ops_csr.cuh"
 #include "sort.cuh"
+#include "tile.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -62,10 +63,18 @@ struct sphb_ctx {
         S.B = B.as<Mat2>();
         S.rp_half = rp_half.as<double2>();
         S.snap = nw.snap.as<double2>();
+        S.grid = nw.grid.as<GridDesc>();
+        S.cell_start = nw.cell_start.as<int>();
+        S.ent_key = nw.ent_key.as<int>();
+        S.ent_pos = nw.ent_pos.as<double2>();
+        S.ent_of = nw.ent_of.as<int>();
         S.ell_cnt = nw.ell_cnt.as<int>();
         S.ell_col = nw.ell_col.as<unsigned>();
         S.ell_stride = nw.ell_stride;
         S.ell_cap = nw.ell_cap;
+        S.ncx = (int)std::ceil(prm.DL / (2.0 * prm.h));   // nb:254
+        if (S.ncx < 1) S.ncx = 1;
+        S.n_tiles = (unsigned)((nw.cell_cap / S.ncx) * tiles_per_row(S.ncx));
         return S;
     }
     DevScalars *sc() const { return scalars.as<DevScalars>(); }
@@ -479,27 +488,24 @@ SPHB_API int sphb_ctx_neighbor_export_csr(sphb_ctx *c, int *row_ptr, int *col)
     clear_error();
     size_t nc = 0;
     SPHB_TRY(sphb_ctx_neighbor_count(c, nullptr, &nc));
-    const size_t nf = (size_t)c->prm.n_fluid, stride = c->nw.ell_stride;
-    const int cap = c->nw.ell_cap;
-    std::vector<int> cnt(nf);
-    std::vector<unsigned> ell((size_t)cap * stride);
-    SPHB_CUDA(cudaMemcpyAsync(cnt.data(), c->nw.ell_cnt.p, nf * sizeof(int), cudaMemcpyDeviceToHost, c->st));
-    SPHB_CUDA(cudaMemcpyAsync(ell.data(), c->nw.ell_col.p, ell.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
-    SPHB_CUDA(cudaStreamSynchronize(c->st));
-    // export path (not hot): ELL rows -> CSR with ascending j, image codes stripped
-    size_t o = 0;
-    std::vector<int> row;
-    for (size_t i = 0; i < nf; ++i) {
-        if (row_ptr) row_ptr[i] = (int)o;
-        const int n = cnt[i] < cap ? cnt[i] : cap;
-        row.resize((size_t)n);
-        for (int k = 0; k < n; ++k) row[(size_t)k] = (int)(ell[(size_t)k * stride + i] & 0x0fffffffu);
-        std::sort(row.begin(), row.end());
-        if (col)
-            for (int k = 0; k < n; ++k) col[o + (size_t)k] = row[(size_t)k];
-        o += (size_t)n;
-    }
-    if (row_ptr) row_ptr[nf] = (int)o;
+    const size_t nf = (size_t)c->prm.n_fluid;
+    DevBuf tmp;
+    SPHB_TRY(tmp.reserve((nf + 1 + nc) * sizeof(int)));
+    int *d_ptr = tmp.as<int>(), *d_col = d_ptr + nf + 1;
+    std::vector<int> h_ptr(nf + 1);
+    int rc = neighbor_export_csr(c->nw, d_ptr, col ? d_col : nullptr, c->st);
+    if (!rc && cudaMemcpyAsync(h_ptr.data(), d_ptr, (nf + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->st) != cudaSuccess)
+        rc = set_error("SPHB:cuda", "CSR export copy failed");
+    if (!rc && col && nc &&
+        cudaMemcpyAsync(col, d_col, nc * sizeof(int), cudaMemcpyDeviceToHost, c->st) != cudaSuccess)
+        rc = set_error("SPHB:cuda", "CSR export copy failed");
+    if (cudaStreamSynchronize(c->st) != cudaSuccess && !rc) rc = set_error("SPHB:cuda", "CSR export failed");
+    tmp.release();
+    if (rc) return rc;
+    // export path (not hot): rows come in the reference's walk order; the API promises ascending j
+    if (col)
+        for (size_t i = 0; i < nf; ++i) std::sort(col + h_ptr[i], col + h_ptr[i + 1]);
+    if (row_ptr) std::copy(h_ptr.begin(), h_ptr.end(), row_ptr);
     return 0;
 }
 

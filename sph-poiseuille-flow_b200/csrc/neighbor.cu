@@ -21,6 +21,7 @@
 //   k_half_count / scan / k_export_pairs   (MEX export only) the reference's half-pair COO list, same
 //                   order, same bits (nb:375-381)
 #include "common.cuh"
+#include "tile.cuh"
 
 #include <cmath>
 #include <climits>
@@ -29,7 +30,6 @@ namespace sphb {
 
 namespace {
 
-constexpr unsigned kIdMask = 0x0fffffffu;
 
 struct NbrParams {
     int n_fluid, n_total;
@@ -204,10 +204,12 @@ __global__ void __launch_bounds__(kBlock) k_scatter(const double2 *__restrict__ 
     }
 }
 
-// insertion sort of one cell's entries by DEcreasing key (= the order the reference's list is walked in)
+// insertion sort of one cell's entries by DEcreasing key (= the order the reference's list is walked in);
+// also records where each particle's REAL entry ended up (rows of the ELL are indexed by entry)
 __global__ void __launch_bounds__(kBlock) k_cell_canon(const GridDesc *__restrict__ g,
                                                       const int *__restrict__ cell_start,
-                                                      int *__restrict__ ent_key, double2 *__restrict__ ent_pos)
+                                                      int *__restrict__ ent_key, double2 *__restrict__ ent_pos,
+                                                      int *__restrict__ ent_of)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= g->ncells) return;
@@ -223,6 +225,10 @@ __global__ void __launch_bounds__(kBlock) k_cell_canon(const GridDesc *__restric
         }
         ent_key[b + 1] = key;
         ent_pos[b + 1] = p;
+    }
+    for (int a = s; a < e; ++a) {
+        const int key = ent_key[a];
+        if ((key & 3) == 0) ent_of[key >> 3] = a;
     }
 }
 
@@ -309,38 +315,65 @@ __device__ int replay_low_walk(double xl, double yl, int home_l, double xh, doub
     return 2;
 }
 
-// ELL entry: j (28 bits) | entry kind (2 bits) | minimum-image shift + 1 (2 bits).  The shift of x_j
-// as seen from the row's particle is  (m) + (kind == 1) - (kind == 2).
-__device__ __forceinline__ unsigned ell_pack(int j, int kind, int m)
-{
-    return (unsigned)j | ((unsigned)kind << 28) | ((unsigned)(m + 1) << 30);
-}
+constexpr int kWalkCap = 640;   // staged candidate entries per tile (3 x 18 cells x ~6.8 = 365 on the lattice)
 
-// One pass over the 3x3 stencil of fluid particle i (nb:312-392), the reference's walk order.
+// The 3x3 stencil walk of nb:312-392, one CTA per tile of cells, candidates staged in shared memory.
 //   HALF = true : the reference's own list (fluid-fluid pairs only from the lower index) -- MEX export
 //   HALF = false: the full gather list: every neighbour of i, fluid-fluid pairs decided by the lower
 //                 index exactly as the reference decides them (symmetric closure of its list)
-// Output: ELL, column-major: col[k * stride + i], k < cnt[i]; rows keep the walk order, so dropping the
-// (fluid j < i) entries of a full row gives the reference's emission order.  No atomics, no sort.
+// A thread owns one walker = the real entry of a fluid particle; lanes of a warp are consecutive
+// entries of the cell-sorted array, i.e. particles of the same or adjacent cells.  Output: ELL rows
+// indexed by the walker's ENTRY, column-major col[k * stride + e], in the reference's walk order
+// (dropping the fluid j < i entries of a full row gives the reference's emission order).
 template <bool HALF>
-__global__ void __launch_bounds__(kBlock) k_walk(NbrParams P, const GridDesc *__restrict__ g,
-                                                const double2 *__restrict__ snap, const int *__restrict__ cell_of,
-                                                const int *__restrict__ cell_start,
-                                                const int *__restrict__ ent_key,
-                                                const double2 *__restrict__ ent_pos, unsigned *col,
-                                                int *__restrict__ cnt, int *__restrict__ totals,
-                                                int *__restrict__ flags)
+__global__ void __launch_bounds__(kTileThreads) k_walk_tile(NbrParams P, const GridDesc *__restrict__ g,
+                                                           const double2 *__restrict__ snap,
+                                                           const int *__restrict__ cell_of,
+                                                           const int *__restrict__ ent_of,
+                                                           const int *__restrict__ cell_start,
+                                                           const int *__restrict__ ent_key,
+                                                           const double2 *__restrict__ ent_pos, unsigned *col,
+                                                           int *__restrict__ cnt, int *__restrict__ totals,
+                                                           int *__restrict__ flags)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int count = 0, n_half = 0;
-    if (i < P.n_fluid) {
-        const int ncx = P.ncx, ncy = g->ncy;
-        const double2 pi = snap[i];
+    __shared__ TileDesc T;
+    __shared__ int s_key[kWalkCap];
+    __shared__ double s_x[kWalkCap], s_y[kWalkCap];
+    const int ncx = P.ncx, ncy = g->ncy;
+    tile_setup(T, blockIdx.x, ncx, ncy, cell_start, kWalkCap);
+    if (!T.valid || T.own_b == T.own_e) return;
+    SPHB_TILE_FOR_STAGED(T, e, slot)
+    {
+        s_key[slot] = ent_key[e];
+        const double2 p = ent_pos[e];
+        s_x[slot] = p.x;
+        s_y[slot] = p.y;
+    }
+    __syncthreads();
+
+    const size_t stride = P.ell_stride;
+    const int cyi = T.cy;
+    int t_half = 0, t_full = 0, t_max = 0;
+    for (int e0 = T.own_b; e0 < T.own_e; e0 += kTileThreads) {
+        const int ew = e0 + (int)threadIdx.x;
+        if (ew >= T.own_e) break;
+        if ((size_t)ew >= stride) {   // more entries than ELL columns: reported, never written
+            atomicOr(flags, kErrCsrCap);
+            continue;
+        }
+        const int own_slot = tile_lookup(T, ew, 1);
+        const int key_i = own_slot >= 0 ? s_key[own_slot] : ent_key[ew];
+        const int i = key_i >> 3;
+        if ((key_i & 3) != 0 || i >= P.n_fluid) {   // ghost or wall entry: not a walker
+            cnt[ew] = 0;
+            continue;
+        }
+        const double2 pi = own_slot >= 0 ? make_double2(s_x[own_slot], s_y[own_slot]) : ent_pos[ew];
         const int home = cell_of[i];
-        const int cxi = home % ncx, cyi = home / ncx;
-        const size_t stride = P.ell_stride;
+        const int cxi = home % ncx;
         // does i itself own ghost entries?  (then a lower fluid index may have met one of them)
         const bool i_multi = (pi.x > P.DL - P.cutoff || pi.x < P.cutoff) && ncx > 1;
+        int count = 0, n_half = 0;
 
         for (int oy = -1; oy <= 1; ++oy) {
             const int cy = cyi + oy;
@@ -356,10 +389,14 @@ __global__ void __launch_bounds__(kBlock) k_walk(NbrParams P, const GridDesc *__
                 // rejected again by the same arithmetic (nb:342-372), so the revisit emits nothing.
                 if (cx == cx_prev[0] || cx == cx_prev[1]) continue;
                 cx_prev[ox == -1 ? 0 : 1] = cx;
-                const int cid = cy * ncx + cx;
-                const int e_end = cell_start[cid + 1];
-                for (int e = cell_start[cid]; e < e_end; ++e) {   // entries are stored last-inserted first
-                    const int key = ent_key[e];
+                int cb, ce;
+                tile_cell_range(T, oy + 1, cx, ncx, cb, ce);
+                if (cb == ce) continue;
+                int n_staged;
+                const int sb = tile_lookup_run(T, cb, ce, oy + 1, n_staged);
+                for (int e = cb; e < ce; ++e) {   // entries are stored last-inserted first
+                    const int s = (e - cb) < n_staged ? sb + (e - cb) : -1;   // -1: beyond the staged part
+                    const int key = s >= 0 ? s_key[s] : ent_key[e];
                     const int j = key >> 3;
                     if (j == i) continue;
                     const bool low_fluid = j < P.n_fluid && j < i;
@@ -368,61 +405,72 @@ __global__ void __launch_bounds__(kBlock) k_walk(NbrParams P, const GridDesc *__
                     if (seam) {   // seen_neighbor (nb:342): j may already be in the row through another entry
                         bool dup = false;
                         const int lim = count < P.ell_cap ? count : P.ell_cap;
-                        for (int q = 0; q < lim; ++q) dup |= ((int)(col[(size_t)q * stride + i] & kIdMask) == j);
+                        for (int q = 0; q < lim; ++q)
+                            dup |= ((ent_key[ell_entry(col[(size_t)q * stride + ew])] >> 3) == j);
                         if (dup) continue;
                     }
-                    int kind = key & 3, m;
+                    int m, acc = e, row_off = oy;
                     if (low_fluid && seam) {
                         const double2 pj = snap[j];
-                        const int sh = replay_low_walk(pj.x, pj.y, cell_of[j], pi.x, pi.y, home, ncy, P);
+                        const int home_j = cell_of[j];
+                        const int sh = replay_low_walk(pj.x, pj.y, home_j, pi.x, pi.y, home, ncy, P);
                         if (sh == 2) continue;
-                        kind = 0;
+                        acc = ent_of[j];   // the row names j's REAL entry; the image shift goes into m
                         m = -sh;
+                        row_off = home_j / ncx - cyi;
                     } else {
-                        const double2 pe = ent_pos[e];
-                        if (!accept_entry(pi.x, pi.y, pe.x, pe.y, P, m)) continue;
+                        const double ex = s >= 0 ? s_x[s] : ent_pos[e].x;
+                        const double ey = s >= 0 ? s_y[s] : ent_pos[e].y;
+                        if (!accept_entry(pi.x, pi.y, ex, ey, P, m)) continue;
                     }
-                    if (count < P.ell_cap) col[(size_t)count * stride + i] = ell_pack(j, kind, m);
+                    if (count < P.ell_cap) col[(size_t)count * stride + ew] = ell_pack(acc, m, row_off);
                     ++count;
                     n_half += low_fluid ? 0 : 1;
                 }
             }
         }
-        cnt[i] = count;
+        cnt[ew] = count;
+        t_half += n_half;
+        t_full += count;
+        t_max = max(t_max, count);
     }
     // totals: half pairs, full entries, longest row (capacity check)
-    int mx = count;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
-        n_half += __shfl_xor_sync(0xffffffffu, n_half, d);
-        count += __shfl_xor_sync(0xffffffffu, count, d);
-        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        t_half += __shfl_xor_sync(0xffffffffu, t_half, d);
+        t_full += __shfl_xor_sync(0xffffffffu, t_full, d);
+        t_max = max(t_max, __shfl_xor_sync(0xffffffffu, t_max, d));
     }
     if ((threadIdx.x & 31) == 0) {
-        if (n_half) atomicAdd(&totals[0], n_half);
-        if (count) atomicAdd(&totals[1], count);
-        if (mx) atomicMax(&totals[2], mx);
-        if (mx > P.ell_cap) atomicOr(flags, kErrCsrCap);
+        if (t_half) atomicAdd(&totals[0], t_half);
+        if (t_full) atomicAdd(&totals[1], t_full);
+        if (t_max) atomicMax(&totals[2], t_max);
+        if (t_max > P.ell_cap) atomicOr(flags, kErrCsrCap);
     }
 }
 
 // rows of the reference's half list inside a FULL row set: count of entries with j wall or j > i
-__global__ void __launch_bounds__(kBlock) k_half_count(NbrParams P, const unsigned *__restrict__ col,
+__global__ void __launch_bounds__(kBlock) k_half_count(NbrParams P, const int *__restrict__ ent_of,
+                                                      const int *__restrict__ ent_key,
+                                                      const unsigned *__restrict__ col,
                                                       const int *__restrict__ cnt, int *__restrict__ half_cnt)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_fluid) return;
-    const int n = min(cnt[i], P.ell_cap);
+    const int e = ent_of[i];
+    const int n = min(cnt[e], P.ell_cap);
     int c = 0;
     for (int k = 0; k < n; ++k) {
-        const int j = (int)(col[(size_t)k * P.ell_stride + i] & kIdMask);
+        const int j = ent_key[ell_entry(col[(size_t)k * P.ell_stride + e])] >> 3;
         c += (j >= P.n_fluid || j > i) ? 1 : 0;
     }
     half_cnt[i] = c;
 }
 
-// nb:357-381 re-evaluated for the stored (j, kind): identical operations, identical bits
-__global__ void __launch_bounds__(kBlock) k_export_pairs(NbrParams P, const double2 *__restrict__ snap,
+// nb:357-381 re-evaluated for the stored entry: identical operations, identical bits
+__global__ void __launch_bounds__(kBlock) k_export_pairs(NbrParams P, const int *__restrict__ ent_of,
+                                                        const int *__restrict__ ent_key,
+                                                        const double2 *__restrict__ ent_pos,
                                                         const unsigned *__restrict__ col,
                                                         const int *__restrict__ cnt,
                                                         const int *__restrict__ half_ptr,
@@ -433,20 +481,19 @@ __global__ void __launch_bounds__(kBlock) k_export_pairs(NbrParams P, const doub
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_fluid) return;
-    const double2 pi = snap[i];
-    const int n = min(cnt[i], P.ell_cap);
+    const int ew = ent_of[i];
+    const double2 pi = ent_pos[ew];
+    const int n = min(cnt[ew], P.ell_cap);
     size_t o = (size_t)half_ptr[i];
     for (int k = 0; k < n; ++k) {
-        const unsigned v = col[(size_t)k * P.ell_stride + i];
-        const int j = (int)(v & kIdMask);
+        const int ea = ell_entry(col[(size_t)k * P.ell_stride + ew]);
+        const int j = ent_key[ea] >> 3;
         if (j < P.n_fluid && j < i) continue;
-        const int kind = (int)((v >> 28) & 3u);
-        const double2 pj = snap[j];
-        const double ex = kind == 0 ? pj.x : (kind == 1 ? pj.x - P.DL : pj.x + P.DL);
-        double dx = pi.x - ex;
+        const double2 pe = ent_pos[ea];   // a ghost entry already holds x_j -+ DL (nb:284,291)
+        double dx = pi.x - pe.x;
         if (dx > P.half_DL) dx -= P.DL;
         else if (dx < -P.half_DL) dx += P.DL;
-        const double dy = pi.y - pj.y;
+        const double dy = pi.y - pe.y;
         const double r = sqrt(dx * dx + dy * dy);
         double W, dW;
         spline2d(r, P.h, P.sigma, W, dW);
@@ -459,6 +506,26 @@ __global__ void __launch_bounds__(kBlock) k_export_pairs(NbrParams P, const doub
         odW[o] = dW;
         ++o;
     }
+}
+
+// full rows by PARTICLE (export only): counts, then particle ids in walk order
+__global__ void __launch_bounds__(kBlock) k_row_count(NbrParams P, const int *__restrict__ ent_of,
+                                                     const int *__restrict__ cnt, int *__restrict__ row_cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.n_fluid) row_cnt[i] = min(cnt[ent_of[i]], P.ell_cap);
+}
+__global__ void __launch_bounds__(kBlock) k_row_fill(NbrParams P, const int *__restrict__ ent_of,
+                                                    const int *__restrict__ ent_key,
+                                                    const unsigned *__restrict__ col, const int *__restrict__ cnt,
+                                                    const int *__restrict__ row_ptr, int *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_fluid) return;
+    const int e = ent_of[i];
+    const int n = min(cnt[e], P.ell_cap);
+    const size_t o = (size_t)row_ptr[i];
+    for (int k = 0; k < n; ++k) out[o + (size_t)k] = ent_key[ell_entry(col[(size_t)k * P.ell_stride + e])] >> 3;
 }
 
 NbrParams make_params(const NeighborWork &w)
@@ -488,16 +555,24 @@ NbrParams make_params(const NeighborWork &w)
 
 void NeighborWork::release_all()
 {
-    DevBuf *all[] = {&grid, &flags, &snap, &cell_of, &cell_cnt, &cell_start, &cell_fill, &ent_key, &ent_pos,
+    DevBuf *all[] = {&grid, &flags, &snap, &cell_of, &ent_of, &cell_cnt, &cell_start, &cell_fill, &ent_key, &ent_pos,
                      &ell_cnt, &ell_col, &half_cnt, &half_ptr, &scan_tmp, &totals};
     for (DevBuf *b : all) b->release();
 }
 
+// ELL rows are indexed by ENTRY (real + ghost): the stride is the entry capacity the rows may use.
+// Ghost entries are a sliver of the total unless the box is only a few cells long, so large problems
+// get n_total * 1.25 columns, small ones the reference's own worst case 3 n_total (nb:265).
 int neighbor_reserve_ell(NeighborWork &w, int rows)
 {
-    if (rows <= w.ell_cap && w.ell_col.p) return 0;
-    w.ell_stride = ((size_t)w.n_fluid + 31) & ~(size_t)31;
-    SPHB_TRY(w.ell_col.reserve((size_t)rows * w.ell_stride * sizeof(unsigned)));
+    const size_t nt = (size_t)w.n_total;
+    size_t stride = nt < (1u << 20) ? 3 * nt : nt + nt / 4 + 4096;
+    stride = (stride + 31) & ~(size_t)31;
+    if (rows <= w.ell_cap && w.ell_col.p && stride == w.ell_stride) return 0;
+    if (rows < w.ell_cap) rows = w.ell_cap;
+    w.ell_stride = stride;
+    SPHB_TRY(w.ell_col.reserve((size_t)rows * stride * sizeof(unsigned)));
+    SPHB_TRY(w.ell_cnt.reserve(stride * sizeof(int)));
     w.ell_cap = rows;
     return 0;
 }
@@ -507,7 +582,7 @@ int neighbor_reserve_ell(NeighborWork &w, int rows)
 int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL, double y_min_hint,
                   double y_max_hint, int max_nbr_hint)
 {
-    const bool resized = n_fluid != w.n_fluid;
+    const bool resized = n_total != w.n_total;
     w.n_fluid = n_fluid;
     w.n_total = n_total;
     w.h = h;
@@ -518,10 +593,10 @@ int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL
     if (!(ncx_d >= 1.0) || !(ncy_d >= 1.0) || ncx_d * ncy_d > 1.0e9)
         return set_error("SPH:Neighbor:entryCapacity", "cell grid of %g x %g cells is not representable",
                          ncx_d, ncy_d);
-    if ((long long)n_total >= (1LL << 28))
-        return set_error("SPH:Neighbor:entryCapacity", "n_total exceeds the 2^28 particle limit of the entry key");
+    if (3LL * (long long)n_total >= (1LL << 28))
+        return set_error("SPH:Neighbor:entryCapacity", "3 n_total exceeds the 2^28 limit of the entry index");
     w.cell_cap = (int)(ncx_d * ncy_d);
-    const size_t nt = (size_t)n_total, nf = (size_t)n_fluid;
+    const size_t nt = (size_t)n_total;
     SPHB_TRY(w.grid.reserve(sizeof(GridDesc)));
     if (!w.flags.p) {
         SPHB_TRY(w.flags.reserve(sizeof(int)));
@@ -530,14 +605,14 @@ int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL
     SPHB_TRY(w.totals.reserve(4 * sizeof(int)));
     SPHB_TRY(w.snap.reserve(nt * sizeof(double2)));
     SPHB_TRY(w.cell_of.reserve(nt * sizeof(int)));
+    SPHB_TRY(w.ent_of.reserve(nt * sizeof(int)));
     SPHB_TRY(w.cell_cnt.reserve(((size_t)w.cell_cap + 1) * sizeof(int)));
     SPHB_TRY(w.cell_start.reserve(((size_t)w.cell_cap + 1) * sizeof(int)));
     SPHB_TRY(w.cell_fill.reserve(((size_t)w.cell_cap + 1) * sizeof(int)));
     SPHB_TRY(w.ent_key.reserve(3 * nt * sizeof(int)));
     SPHB_TRY(w.ent_pos.reserve(3 * nt * sizeof(double2)));
-    SPHB_TRY(w.ell_cnt.reserve((nf + 1) * sizeof(int)));
     if (resized) {
-        w.ell_cap = 0;   // the stride depends on n_fluid
+        w.ell_cap = 0;   // the stride depends on n_total
         w.ell_col.release();
     }
     SPHB_TRY(neighbor_reserve_ell(w, max_nbr_hint > 0 ? max_nbr_hint : kDefaultEllRows));
@@ -585,23 +660,25 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
     {
         ProfScope ps(prof, kPfNbrCanon, st);
         k_cell_canon<<<grid_for((size_t)w.cell_cap), kBlock, 0, st>>>(g, w.cell_start.as<int>(), w.ent_key.as<int>(),
-                                                                      w.ent_pos.as<double2>());
+                                                                      w.ent_pos.as<double2>(), w.ent_of.as<int>());
     }
     nl += 2;
 
     for (int attempt = 0; attempt < 2; ++attempt) {
         ProfScope ps(prof, kPfNbrWalk, st);
         SPHB_CUDA(cudaMemsetAsync(w.totals.p, 0, 4 * sizeof(int), st));
+        // one CTA per tile of kTileCells cells; rows beyond the device-side n_cell_y exit at once
+        const unsigned n_tiles = (unsigned)((w.cell_cap / P.ncx) * tiles_per_row(P.ncx));
         if (half_only)
-            k_walk<true><<<grid_for(nf), kBlock, 0, st>>>(P, g, w.snap.as<double2>(), w.cell_of.as<int>(),
-                                                          w.cell_start.as<int>(), w.ent_key.as<int>(),
-                                                          w.ent_pos.as<double2>(), w.ell_col.as<unsigned>(),
-                                                          w.ell_cnt.as<int>(), w.totals.as<int>(), flags);
+            k_walk_tile<true><<<n_tiles, kTileThreads, 0, st>>>(
+                P, g, w.snap.as<double2>(), w.cell_of.as<int>(), w.ent_of.as<int>(), w.cell_start.as<int>(),
+                w.ent_key.as<int>(), w.ent_pos.as<double2>(), w.ell_col.as<unsigned>(), w.ell_cnt.as<int>(),
+                w.totals.as<int>(), flags);
         else
-            k_walk<false><<<grid_for(nf), kBlock, 0, st>>>(P, g, w.snap.as<double2>(), w.cell_of.as<int>(),
-                                                           w.cell_start.as<int>(), w.ent_key.as<int>(),
-                                                           w.ent_pos.as<double2>(), w.ell_col.as<unsigned>(),
-                                                           w.ell_cnt.as<int>(), w.totals.as<int>(), flags);
+            k_walk_tile<false><<<n_tiles, kTileThreads, 0, st>>>(
+                P, g, w.snap.as<double2>(), w.cell_of.as<int>(), w.ent_of.as<int>(), w.cell_start.as<int>(),
+                w.ent_key.as<int>(), w.ent_pos.as<double2>(), w.ell_col.as<unsigned>(), w.ell_cnt.as<int>(),
+                w.totals.as<int>(), flags);
         nl += 1;
         if (!exact || attempt == 1) break;
         int host[4] = {0, 0, 0, 0};
@@ -633,12 +710,28 @@ int neighbor_export_pairs(NeighborWork &w, size_t n_half, double *pair_i, double
     const size_t nf = (size_t)w.n_fluid;
     SPHB_TRY(w.half_cnt.reserve((nf + 1) * sizeof(int)));
     SPHB_TRY(w.half_ptr.reserve((nf + 1) * sizeof(int)));
-    k_half_count<<<grid_for(nf), kBlock, 0, st>>>(P, w.ell_col.as<unsigned>(), w.ell_cnt.as<int>(),
-                                                  w.half_cnt.as<int>());
+    k_half_count<<<grid_for(nf), kBlock, 0, st>>>(P, w.ent_of.as<int>(), w.ent_key.as<int>(),
+                                                  w.ell_col.as<unsigned>(), w.ell_cnt.as<int>(), w.half_cnt.as<int>());
     SPHB_TRY(exclusive_scan_i32(w.half_cnt.as<int>(), w.half_ptr.as<int>(), nf, w.scan_tmp, nullptr, st, nullptr));
-    k_export_pairs<<<grid_for(nf), kBlock, 0, st>>>(P, w.snap.as<double2>(), w.ell_col.as<unsigned>(),
+    k_export_pairs<<<grid_for(nf), kBlock, 0, st>>>(P, w.ent_of.as<int>(), w.ent_key.as<int>(),
+                                                    w.ent_pos.as<double2>(), w.ell_col.as<unsigned>(),
                                                     w.ell_cnt.as<int>(), w.half_ptr.as<int>(), pair_i, pair_j, dx, dy,
                                                     r, W, dW);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// The full gather list as CSR by particle (device outputs: row_ptr[n_fluid+1], col[n_full] in walk order).
+int neighbor_export_csr(NeighborWork &w, int *row_ptr, int *col, cudaStream_t st)
+{
+    NbrParams P = make_params(w);
+    const size_t nf = (size_t)w.n_fluid;
+    SPHB_TRY(w.half_cnt.reserve((nf + 1) * sizeof(int)));
+    k_row_count<<<grid_for(nf), kBlock, 0, st>>>(P, w.ent_of.as<int>(), w.ell_cnt.as<int>(), w.half_cnt.as<int>());
+    SPHB_TRY(exclusive_scan_i32(w.half_cnt.as<int>(), row_ptr, nf, w.scan_tmp, nullptr, st, nullptr));
+    if (col)
+        k_row_fill<<<grid_for(nf), kBlock, 0, st>>>(P, w.ent_of.as<int>(), w.ent_key.as<int>(), w.ell_col.as<unsigned>(),
+                                                    w.ell_cnt.as<int>(), row_ptr, col);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -32,12 +32,19 @@ struct StateView {
     double *rho, *p, *drho_dt, *mass, *Vol;
     Mat2 *B;
     double2 *rp_half;   // (rho, p) at the half step of the current substep (ph:857-862), written by k_time_step
-    // neighbour structures (frozen geometry = positions at list-build time)
-    const double2 *snap;
-    const int *ell_cnt;       // neighbours of fluid particle i
-    const unsigned *ell_col;  // col[k * ell_stride + i]: j | kind << 28 | (m + 1) << 30
+    // neighbour structures (frozen geometry = entry positions at list-build time), see neighbor.cu / tile.cuh
+    const double2 *snap;      // wrapped position of particle i at build time
+    const GridDesc *grid;     // device-side grid (n_cell_y)
+    const int *cell_start;    // entry range of each cell
+    const int *ent_key;       // particle << 3 | multi << 2 | kind, cell-sorted
+    const double2 *ent_pos;   // entry position (ghost x already shifted)
+    const int *ent_of;        // real entry of particle i
+    const int *ell_cnt;       // neighbours of the walker whose real entry is e
+    const unsigned *ell_col;  // col[k * ell_stride + e]: accepted entry | shift | row offset
     size_t ell_stride;
     int ell_cap;
+    int ncx;
+    unsigned n_tiles;
 };
 
 int csr_density(const PhysParams &P, const StateView &S, cudaStream_t st);                       // P1 pass 1
