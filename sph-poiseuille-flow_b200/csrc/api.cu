@@ -149,7 +149,7 @@ SPHB_API int sphb_neighbor_search(sphb_mat pos, int n_fluid, int n_total, double
         lo = pos.p[n + i] < lo ? pos.p[n + i] : lo;
         hi = pos.p[n + i] > hi ? pos.p[n + i] : hi;
     }
-    SPHB_TRY(neighbor_plan(g.nw, n_fluid, n_total, h, DL, lo, hi, 0));
+    SPHB_TRY(neighbor_plan(g.nw, n_fluid, n_total, h, DL, lo, hi, 0, 0));
     SPHB_CUDA(cudaMemsetAsync(g.nw.flags.p, 0, sizeof(int), g.st));
     Bump b;
     SPHB_TRY(open_arena(g, pad4(2 * n), b));

@@ -63,7 +63,7 @@ constexpr int kBlock = 128;
 inline unsigned grid_for(size_t n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
 
 // device error flags (sphb_status.error_flags)
-enum : int { kErrCsrCap = 1, kErrCellCap = 2, kErrSeenCap = 4, kErrNonFinite = 8 };
+enum : int { kErrCsrCap = 1, kErrCellCap = 2, kErrSeenCap = 4, kErrNonFinite = 8, kErrTileCap = 16 };
 
 // ------------------------------------------------------------------------------------------------
 // cell grid descriptor, lives in device memory, written by the grid-setup kernel (nb:244-258)
@@ -79,29 +79,36 @@ struct GridDesc {
 // ------------------------------------------------------------------------------------------------
 // neighbour-list storage shared by the stateless search and the resident context
 // ------------------------------------------------------------------------------------------------
+struct TileDesc;
 struct NeighborWork {
     int n_fluid = 0, n_total = 0;
     double h = 0, DL = 0;
     int cell_cap = 0;            // allocated cells
-    int ell_cap = 0;             // allocated ELL rows (longest storable neighbour row)
-    size_t ell_stride = 0;       // entry capacity of the ELL rows (rows are indexed by ENTRY)
+    int ell_cap = 0;             // longest storable neighbour row (a multiple of 8)
+    size_t ell_stride = 0;       // entry capacity (rows of the list are indexed by ENTRY)
+    int tile_w = 0;              // cells per tile (one cell row)
+    int tile_cap = 0;            // staged entries a tile may hold (shared-memory slots)
+    int tile_cap_limit = 0;      // what the kernels of the caller can stage (set by the planner)
+    unsigned n_tiles = 0;
     bool half_only = false;      // the last build kept only the reference's half list
+    bool half_valid = false;     // totals[0] holds the half-pair count of the current list
+    bool tile_fitted = false;    // tile_cap has been fitted to the first build
     DevBuf grid;                 // GridDesc
     DevBuf flags;                // int error flags
     DevBuf snap;                 // double2 [n_total]   wrapped x, y at build time
     DevBuf cell_of;              // int [n_total]       home cell of the real entry
     DevBuf ent_of;               // int [n_total]       index of the real entry in the sorted entry array
-    DevBuf cell_cnt;             // int [cell_cap+1]
+    DevBuf cell_cnt;             // int [2*(cell_cap+1)] counts, then fill cursors
     DevBuf cell_start;           // int [cell_cap+1]
-    DevBuf cell_fill;            // int [cell_cap]
-    DevBuf ent_key;              // int [3*n_total]     (particle << 3) | (multi << 2) | kind
-    DevBuf ent_pos;              // double2 [3*n_total] entry coordinates (ghosts shifted by -+DL)
+    DevBuf tmp_key, tmp_pos, tmp_cell;   // entries as scattered (any order inside a cell)
+    DevBuf ent_key;              // int [ent_cap]       (particle << 3) | (multi << 2) | kind, canonical order
+    DevBuf ent_pos;              // double2 [ent_cap]   entry coordinates (ghosts shifted by -+DL)
+    DevBuf tiles;                // TileDesc [n_tiles]
     DevBuf ell_cnt;              // int [ell_stride]    neighbours of the walker whose real entry is e
-    DevBuf ell_col;              // uint [ell_cap * ell_stride], column-major: col[k * stride + e]
-                                 //   accepted entry (28 bits) | min-image shift + 1 (2) | row offset + 1 (2)
+    DevBuf ell_q;                // uint4 [ell_cap/8 * ell_stride]: eight 16-bit entries per word (tile.cuh)
     DevBuf half_cnt, half_ptr;   // int [n_fluid+1]     export only (reference half-pair list)
     DevBuf scan_tmp;             // scan workspace
-    DevBuf totals;               // int[4]: n_half, n_full, longest row (device), read back on demand
+    DevBuf totals;               // int[8]: n_half, n_full, longest row, most staged entries of a tile
     void release_all();
 };
 constexpr int kDefaultEllRows = 48;
@@ -147,7 +154,7 @@ struct ProfScope {
 
 // neighbor.cu (compiled with -fmad=false: bit-exact accept tests)
 int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL, double y_min_hint,
-                  double y_max_hint, int max_nbr_hint);
+                  double y_max_hint, int max_nbr_hint, int tile_cap_limit);
 int neighbor_reserve_ell(NeighborWork &w, int rows);
 int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exact, cudaStream_t st,
                    long long *launches, Prof *prof = nullptr);
@@ -155,6 +162,7 @@ int neighbor_export_pairs(NeighborWork &w, size_t n_half, double *pair_i, double
                           double *r, double *W, double *dW, cudaStream_t st);   // device pointers
 
 int neighbor_export_csr(NeighborWork &w, int *row_ptr, int *col, cudaStream_t st);   // device pointers
+int neighbor_half_total(NeighborWork &w, cudaStream_t st);   // makes totals[0] valid after a full build
 
 // scan.cu
 int exclusive_scan_i32(const int *in, int *out, size_t n, DevBuf &tmp, int *total_out_dev, cudaStream_t st,

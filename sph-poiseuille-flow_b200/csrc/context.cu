@@ -64,17 +64,16 @@ struct sphb_ctx {
         S.rp_half = rp_half.as<double2>();
         S.snap = nw.snap.as<double2>();
         S.grid = nw.grid.as<GridDesc>();
-        S.cell_start = nw.cell_start.as<int>();
         S.ent_key = nw.ent_key.as<int>();
         S.ent_pos = nw.ent_pos.as<double2>();
         S.ent_of = nw.ent_of.as<int>();
+        S.tiles = nw.tiles.as<TileDesc>();
         S.ell_cnt = nw.ell_cnt.as<int>();
-        S.ell_col = nw.ell_col.as<unsigned>();
+        S.ell_q = nw.ell_q.as<uint4>();
         S.ell_stride = nw.ell_stride;
         S.ell_cap = nw.ell_cap;
-        S.ncx = (int)std::ceil(prm.DL / (2.0 * prm.h));   // nb:254
-        if (S.ncx < 1) S.ncx = 1;
-        S.n_tiles = (unsigned)((nw.cell_cap / S.ncx) * tiles_per_row(S.ncx));
+        S.tile_cap = nw.tile_cap;
+        S.n_tiles = nw.n_tiles;
         return S;
     }
     DevScalars *sc() const { return scalars.as<DevScalars>(); }
@@ -138,7 +137,10 @@ void drop_graphs(sphb_ctx *c)
 int plan_lists(sphb_ctx *c, double y_lo, double y_hi)
 {
     const sphb_params &p = c->prm;
-    SPHB_TRY(neighbor_plan(c->nw, p.n_fluid, p.n_total, p.h, p.DL, y_lo, y_hi, p.max_neighbors_hint));
+    SPHB_TRY(neighbor_plan(c->nw, p.n_fluid, p.n_total, p.h, p.DL, y_lo, y_hi, p.max_neighbors_hint,
+                           csr_max_tile_slots()));
+    SPHB_TRY(csr_configure(c->nw.tile_cap));
+    SPHB_TRY(c->shear_partials.reserve(2 * (size_t)c->nw.n_tiles * sizeof(double)));
     SPHB_TRY(sort_plan(c->sw, p.n_fluid, p.DL, p.h, y_hi - y_lo));
     c->planned = true;
     c->y_lo = y_lo;
@@ -209,7 +211,9 @@ int do_neighbor(sphb_ctx *c)
     SPHB_TRY(neighbor_build(c->nw, c->pos.as<double2>(), false, exact, c->st, &c->launches, &c->kprof));
     if (exact) {
         c->list_sized = true;
-        drop_graphs(c);   // the ELL may have moved
+        drop_graphs(c);   // the list, the tiles or their slot count may have changed
+        SPHB_TRY(csr_configure(c->nw.tile_cap));
+        SPHB_TRY(c->shear_partials.reserve(2 * (size_t)c->nw.n_tiles * sizeof(double)));
     }
     c->have_list = true;
     return 0;
@@ -309,7 +313,6 @@ SPHB_API int sphb_ctx_create(const sphb_params *prm, sphb_ctx **out)
         SPHB_TRY(c->a_B.reserve(nt * sizeof(Mat2)));
         SPHB_TRY(c->scalars.reserve(sizeof(DevScalars)));
         SPHB_CUDA(cudaMemsetAsync(c->scalars.p, 0, sizeof(DevScalars), c->st));
-        SPHB_TRY(c->shear_partials.reserve(2 * (size_t)kShearPartialBlocks * sizeof(double)));
         SPHB_TRY(c->stage.reserve(4 * nt * sizeof(double)));
         k_fill<<<grid_for(nt), kBlock, 0, c->st>>>(c->rho.as<double>(), prm->rho0, (int)nt);
         k_fill_identity<<<grid_for(nt), kBlock, 0, c->st>>>(c->B.as<Mat2>(), (int)nt);
@@ -449,6 +452,7 @@ SPHB_API int sphb_ctx_neighbor_count(sphb_ctx *c, size_t *n_half, size_t *n_csr)
     if (!c) return set_error("SPHB:arg", "null context");
     SPHB_TRY(bind_device(c));
     if (!c->have_list) return set_error("SPHB:state", "no neighbour list");
+    SPHB_TRY(neighbor_half_total(c->nw, c->st));
     SPHB_CUDA(cudaMemcpyAsync(c->h_ints, c->nw.totals.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     SPHB_CUDA(cudaMemcpyAsync(c->h_ints + 2, c->nw.flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     SPHB_CUDA(cudaStreamSynchronize(c->st));
@@ -587,6 +591,7 @@ SPHB_API int sphb_ctx_status(sphb_ctx *c, sphb_status *out)
     SPHB_CUDA(cudaMemcpyAsync(c->h_scalars, c->sc(), sizeof(DevScalars), cudaMemcpyDeviceToHost, c->st));
     c->h_ints[0] = c->h_ints[1] = c->h_ints[2] = 0;
     if (c->planned) {
+        if (c->have_list) SPHB_TRY(neighbor_half_total(c->nw, c->st));
         SPHB_CUDA(cudaMemcpyAsync(c->h_ints, c->nw.totals.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
         SPHB_CUDA(cudaMemcpyAsync(c->h_ints + 2, c->nw.flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     }
@@ -702,6 +707,7 @@ SPHB_API int sphb_ctx_run_dual(sphb_ctx *c, int n_outer, int n_inner)
             c->launches = l0;
         }
         SPHB_CUDA(cudaGraphLaunch(c->graph[0], c->st));
+        c->nw.half_valid = false;   // the replayed build rewrote the list
         c->launches += c->graph_launches;
     }
     c->h_step += (long long)n_outer * n_inner;

@@ -12,11 +12,12 @@
 //   k_bin_count     wrap, bin, count real + ghost entries per cell (nb:270-296) + position snapshot
 //   scan            cell_start
 //   k_scatter       entry records into their cell ranges (atomic slot), then
-//   k_cell_canon    each cell's range sorted by DEcreasing insertion key: the reference's linked list
-//                   is walked "last inserted first", so a forward scan of the range is its walk order
-//   k_walk          ONE pass per fluid particle over its 3x3 stencil in the reference's order with its
-//                   skip rules and its real/ghost dedup (seen_neighbor, nb:342,383), writing the row
-//                   straight into an ELL (column-major, coalesced for the gather kernels): no count
+//   k_cell_canon    rank sort of each cell's range by DEcreasing insertion key: the reference's linked
+//                   list is walked "last inserted first", so a forward scan of the range is its walk order
+//   k_tile_setup    descriptors of the cell tiles (tile.cuh): staged entry ranges and their slots
+//   k_walk_tile     ONE pass per fluid particle over its 3x3 stencil out of shared memory, in the
+//                   reference's order with its skip rules and its real/ghost dedup (seen_neighbor,
+//                   nb:342,383); rows of 16-bit tile-local entries, eight to a 128-bit store: no count
 //                   pass, no scatter atomics, no row sort
 //   k_half_count / scan / k_export_pairs   (MEX export only) the reference's half-pair COO list, same
 //                   order, same bits (nb:375-381)
@@ -177,7 +178,8 @@ __global__ void __launch_bounds__(kBlock) k_bin_count(const double2 *__restrict_
 __global__ void __launch_bounds__(kBlock) k_scatter(const double2 *__restrict__ pos, NbrParams P,
                                                    const GridDesc *__restrict__ g,
                                                    const int *__restrict__ cell_start, int *__restrict__ cell_fill,
-                                                   int *__restrict__ ent_key, double2 *__restrict__ ent_pos)
+                                                   int *__restrict__ tmp_key, double2 *__restrict__ tmp_pos,
+                                                   int *__restrict__ tmp_cell)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_total) return;
@@ -187,53 +189,133 @@ __global__ void __launch_bounds__(kBlock) k_scatter(const double2 *__restrict__ 
     {
         const int c = row + b.cx;
         const int s = cell_start[c] + atomicAdd(&cell_fill[c], 1);
-        ent_key[s] = (i << 3) | multi | 0;
-        ent_pos[s] = make_double2(b.xw, b.y);
+        tmp_key[s] = (i << 3) | multi | 0;
+        tmp_pos[s] = make_double2(b.xw, b.y);
+        tmp_cell[s] = c;
     }
     if (b.gcx_lo >= 0) {
         const int c = row + b.gcx_lo;
         const int s = cell_start[c] + atomicAdd(&cell_fill[c], 1);
-        ent_key[s] = (i << 3) | multi | 1;
-        ent_pos[s] = make_double2(b.xw - P.DL, b.y);
+        tmp_key[s] = (i << 3) | multi | 1;
+        tmp_pos[s] = make_double2(b.xw - P.DL, b.y);
+        tmp_cell[s] = c;
     }
     if (b.gcx_hi >= 0) {
         const int c = row + b.gcx_hi;
         const int s = cell_start[c] + atomicAdd(&cell_fill[c], 1);
-        ent_key[s] = (i << 3) | multi | 2;
-        ent_pos[s] = make_double2(b.xw + P.DL, b.y);
+        tmp_key[s] = (i << 3) | multi | 2;
+        tmp_pos[s] = make_double2(b.xw + P.DL, b.y);
+        tmp_cell[s] = c;
     }
 }
 
-// insertion sort of one cell's entries by DEcreasing key (= the order the reference's list is walked in);
-// also records where each particle's REAL entry ended up (rows of the ELL are indexed by entry)
-__global__ void __launch_bounds__(kBlock) k_cell_canon(const GridDesc *__restrict__ g,
+// Canonical order inside a cell = DEcreasing insertion key (the reference's linked list is walked "last
+// inserted first", so a forward scan of the range is its walk order).  Rank sort, one thread per entry:
+// the rank of an entry is the number of larger keys in its cell (keys are distinct); every load is
+// independent.  Also records where each particle's REAL entry ends up (rows are indexed by entry).
+__global__ void __launch_bounds__(kBlock) k_cell_canon(const GridDesc *__restrict__ g, int ent_cap,
                                                       const int *__restrict__ cell_start,
-                                                      int *__restrict__ ent_key, double2 *__restrict__ ent_pos,
-                                                      int *__restrict__ ent_of)
+                                                      const int *__restrict__ tmp_key,
+                                                      const double2 *__restrict__ tmp_pos,
+                                                      const int *__restrict__ tmp_cell, int *__restrict__ ent_key,
+                                                      double2 *__restrict__ ent_pos, int *__restrict__ ent_of,
+                                                      int *__restrict__ flags)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g->ncells) return;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = g->n_entries;
+    if (a == 0 && n > ent_cap) atomicOr(flags, kErrCsrCap);
+    if (a >= n || a >= ent_cap) return;
+    const int c = tmp_cell[a];
     const int s = cell_start[c], e = cell_start[c + 1];
-    for (int a = s + 1; a < e; ++a) {
-        const int key = ent_key[a];
-        const double2 p = ent_pos[a];
-        int b = a - 1;
-        while (b >= s && ent_key[b] < key) {
-            ent_key[b + 1] = ent_key[b];
-            ent_pos[b + 1] = ent_pos[b];
-            --b;
+    const int key = tmp_key[a];
+    int rank = 0;
+    for (int b = s; b < e; ++b) rank += tmp_key[b] > key ? 1 : 0;
+    const int dst = s + rank;
+    if (dst >= ent_cap) return;
+    ent_key[dst] = key;
+    ent_pos[dst] = tmp_pos[a];
+    if ((key & 3) == 0) ent_of[key >> 3] = dst;
+}
+
+// One descriptor per tile (tile.cuh): entry ranges of the (kTileRows + 2) x (w + 2) cell neighbourhood and
+// their slots.
+__global__ void __launch_bounds__(kBlock) k_tile_setup(const GridDesc *__restrict__ g, int ncx, int w, unsigned n_tiles,
+                                                      int cap, int ent_cap, const int *__restrict__ cell_start,
+                                                      TileDesc *__restrict__ tiles, int *__restrict__ totals,
+                                                      int *__restrict__ flags)
+{
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const int ncy = g->ncy;
+    const int tpr = tiles_per_row(ncx, w);
+    const int cy0 = (int)(t / (unsigned)tpr) * kTileRows, cx0 = (int)(t % (unsigned)tpr) * w;
+    const int cx1 = min(cx0 + w, ncx);
+    const int a = max(cx0 - 1, 0), b = min(cx1 + 1, ncx);
+    const bool valid = cy0 < ncy;
+    TileDesc &T = tiles[t];
+    int used = 0;
+    bool fits = true;
+    for (int r = 0; r < kStageRows; ++r) {
+        const int row = cy0 + r - 1;
+        const bool row_ok = valid && row >= 0 && row < ncy;
+        int rb[3] = {0, 0, 0}, re[3] = {0, 0, 0};
+        const int *cs = cell_start + (size_t)(row_ok ? row : 0) * ncx;
+        for (int k = 0; k <= b - a; ++k) T.cs[r][k] = row_ok ? cs[a + k] : 0;
+        if (row_ok) {
+            rb[0] = cs[a];
+            re[0] = cs[b];
+            if (cx0 == 0 && b <= ncx - 1) {   // left halo column wraps to ncx-1
+                rb[1] = cs[ncx - 1];
+                re[1] = cs[ncx];
+            }
+            if (cx1 == ncx && a >= 1) {       // right halo column wraps to 0
+                rb[2] = cs[0];
+                re[2] = cs[1];
+            }
         }
-        ent_key[b + 1] = key;
-        ent_pos[b + 1] = p;
+        for (int k = 0; k < 3; ++k) {
+            T.seg[3 * r + k].b = rb[k];
+            T.seg[3 * r + k].e = re[k];
+            T.seg[3 * r + k].off = used;
+            used += re[k] - rb[k];
+            if (re[k] > ent_cap) fits = false;   // entry overflow (reported by k_cell_canon)
+        }
     }
-    for (int a = s; a < e; ++a) {
-        const int key = ent_key[a];
-        if ((key & 3) == 0) ent_of[key >> 3] = a;
+    T.n_staged = used;
+    for (int k = 0; k < kTileRows; ++k) {
+        const int r = k + 1;
+        const bool row_ok = valid && cy0 + k < ncy;
+        T.own_b[k] = row_ok ? T.cs[r][cx0 - a] : 0;
+        T.own_n[k] = row_ok ? T.cs[r][cx1 - a] - T.cs[r][cx0 - a] : 0;
+        T.own_off[k] = T.seg[3 * r].off + (T.own_b[k] - T.seg[3 * r].b);
     }
+    T.cy0 = cy0;
+    T.cx0 = cx0;
+    T.cx1 = cx1;
+    T.a = a;
+    T.b = b;
+    int f = valid && fits ? kTileValid : 0;
+    // walkers of columns 0, ncx-2 and ncx-1 can meet ghost entries, both entries of a particle that owns
+    // a ghost, or the periodic wrap: they take the general walk (ghosts live in column ncx-1 only and
+    // their owners in columns 0, ncx-2, ncx-1; nb:282-295)
+    if (cx0 < 1 || cx1 > ncx - 2 || ncx < 6) f |= kTileSeam;
+    if (used + 1 > cap) {   // cannot be staged (+ the dummy slot): reported, the tile is skipped by every kernel
+        atomicOr(flags, kErrTileCap);
+        f &= ~kTileValid;
+    }
+    T.flags = f;
+    if (valid) atomicMax(&totals[3], used + 1);
 }
 
 // nb:357-372 for "particle a (wrapped xa, ya) meets an entry at (ex, ey)": minimum image, cut-off and
 // kernel-support tests with the reference's arithmetic.  m = -1/0/+1 is the minimum-image shift.
+__device__ __forceinline__ bool support_exact(double r2, const NbrParams &P)
+{
+    const double r = sqrt(r2);
+    double W, dW;
+    spline2d(r, P.h, P.sigma, W, dW);
+    return W > 0.0 || fabs(dW) > 0.0;
+}
 __device__ __forceinline__ bool accept_entry(double xa, double ya, double ex, double ey, const NbrParams &P, int &m)
 {
     double dx = xa - ex;
@@ -251,10 +333,7 @@ __device__ __forceinline__ bool accept_entry(double xa, double ya, double ex, do
     // r2 < rc2 (1 - 1e-12) guarantees fl(fl(sqrt(r2)) / h) < 2, i.e. W > 0 (nb:116-133, 372); only the
     // last 1e-12 below the cut-off needs the reference's sqrt / divide / spline evaluated exactly
     if (r2 < P.rc2_safe) return true;
-    const double r = sqrt(r2);
-    double W, dW;
-    spline2d(r, P.h, P.sigma, W, dW);
-    return W > 0.0 || fabs(dW) > 0.0;
+    return support_exact(r2, P);
 }
 
 // Entries of one particle as the reference inserts them (nb:278-295), from its wrapped position and
@@ -286,17 +365,31 @@ __device__ __forceinline__ Entries entries_of(double xw, int home, const NbrPara
     return E;
 }
 
+// position of column cx in the stencil walk of a particle of column cxi (ox = -1, 0, 1, wrapped; a
+// revisited column counts at its first visit), or -1 when the stencil does not reach it
+__device__ __forceinline__ int stencil_rank(int cx, int cxi, int ncx)
+{
+    int c0 = cxi - 1, c2 = cxi + 1;
+    if (c0 < 0) c0 += ncx;
+    if (c2 >= ncx) c2 -= ncx;
+    if (cx == c0) return 0;
+    if (cx == cxi) return 1;
+    if (cx == c2) return 2;
+    return -1;
+}
+
 // The reference stores a fluid-fluid pair once, found by the LOWER index's walk (nb:353).  When ghost
 // entries are involved the two ends do not round dx identically, so the higher index replays the
 // lower one's walk restricted to its own entries: cells in (oy, ox) order, within a cell the
 // higher-kind entry first (list order = reverse insertion), first accepted entry wins.  Returns the
-// image shift of x_high as seen from the low particle, or 2 when the pair is not accepted.
+// image shift of x_high as seen from the low particle, or kNoPair when the pair is not accepted.
+constexpr int kNoPair = 99;
 __device__ int replay_low_walk(double xl, double yl, int home_l, double xh, double yh, int home_h, int ncy,
                                const NbrParams &P)
 {
     const Entries E = entries_of(xh, home_h, P);
     const int cxl = home_l % P.ncx, cyl = home_l / P.ncx;
-    if (E.cy < cyl - 1 || E.cy > cyl + 1 || E.cy < 0 || E.cy >= ncy) return 2;
+    if (E.cy < cyl - 1 || E.cy > cyl + 1 || E.cy < 0 || E.cy >= ncy) return kNoPair;
     int cx_prev[2] = {-1, -1};
     for (int ox = -1; ox <= 1; ++ox) {
         int cx = cxl + ox;
@@ -312,166 +405,338 @@ __device__ int replay_low_walk(double xl, double yl, int home_l, double xh, doub
             if (accept_entry(xl, yl, E.x[kind], yh, P, m)) return m + (kind == 1 ? 1 : (kind == 2 ? -1 : 0));
         }
     }
-    return 2;
+    return kNoPair;
 }
-
-constexpr int kWalkCap = 640;   // staged candidate entries per tile (3 x 18 cells x ~6.8 = 365 on the lattice)
 
 // The 3x3 stencil walk of nb:312-392, one CTA per tile of cells, candidates staged in shared memory.
 //   HALF = true : the reference's own list (fluid-fluid pairs only from the lower index) -- MEX export
 //   HALF = false: the full gather list: every neighbour of i, fluid-fluid pairs decided by the lower
 //                 index exactly as the reference decides them (symmetric closure of its list)
 // A thread owns one walker = the real entry of a fluid particle; lanes of a warp are consecutive
-// entries of the cell-sorted array, i.e. particles of the same or adjacent cells.  Output: ELL rows
-// indexed by the walker's ENTRY, column-major col[k * stride + e], in the reference's walk order
-// (dropping the fluid j < i entries of a full row gives the reference's emission order).
+// entries of the cell-sorted array, i.e. particles of the same or adjacent cells.  The row is emitted
+// in the reference's walk order (dropping the fluid j < i entries of a full row gives the reference's
+// emission order), eight 16-bit entries per 128-bit store.
+//
+// Interior walkers (columns 2 .. ncx-4) cannot meet a ghost entry, a particle that owns one, or the
+// periodic wrap: their three stencil cells of a row are ONE contiguous slot range and the accept test
+// is the reference's arithmetic with no image shift.  The others take the general walk, where the
+// reference's seen_neighbor dedup (nb:342,383) is decided from the walk positions of the (at most
+// three) entries of the other particle instead of from a per-particle table.
+struct RowWriter {
+    uint4 q;
+    int count;
+    uint4 *dst;        // ell_q + ew
+    size_t stride;
+    int qcap;          // words a row may use
+    __device__ __forceinline__ void init(uint4 *d, size_t s, int cap_words)
+    {
+        q = make_uint4(0u, 0u, 0u, 0u);
+        count = 0;
+        dst = d;
+        stride = s;
+        qcap = cap_words;
+    }
+    __device__ __forceinline__ void push(int slot, int m)
+    {
+        ell_push(q, ell_pack(slot, m));
+        ++count;
+        if ((count & 7) == 0) {
+            const int w = (count >> 3) - 1;
+            if (w < qcap) dst[(size_t)w * stride] = q;
+        }
+    }
+    // pads the last word with the dummy slot (tile.cuh) and stores it
+    __device__ __forceinline__ void finish(int dummy_slot)
+    {
+        const int c = count & 7;
+        if (c) {
+            for (int k = c; k < 8; ++k) ell_push(q, ell_pack(dummy_slot, 0));
+            const int w = count >> 3;
+            if (w < qcap) dst[(size_t)w * stride] = q;
+        }
+    }
+};
+
+// Seam tiles (first / last of a tile row) carry the expensive general walkers: they are dealt to the
+// first CTAs so that they do not form the tail of the launch.
+__device__ __forceinline__ unsigned walk_tile_of_block(unsigned b, int tpr, unsigned n_tiles)
+{
+    if (tpr < 3) return b;
+    const unsigned n_rows = n_tiles / (unsigned)tpr;
+    if (b < 2 * n_rows) return (b >> 1) * (unsigned)tpr + ((b & 1u) ? (unsigned)(tpr - 1) : 0u);
+    const unsigned r = b - 2 * n_rows;
+    return (r / (unsigned)(tpr - 2)) * (unsigned)tpr + 1u + r % (unsigned)(tpr - 2);
+}
+
 template <bool HALF>
 __global__ void __launch_bounds__(kTileThreads) k_walk_tile(NbrParams P, const GridDesc *__restrict__ g,
+                                                           const TileDesc *__restrict__ tiles, int tile_w,
                                                            const double2 *__restrict__ snap,
                                                            const int *__restrict__ cell_of,
-                                                           const int *__restrict__ ent_of,
-                                                           const int *__restrict__ cell_start,
                                                            const int *__restrict__ ent_key,
-                                                           const double2 *__restrict__ ent_pos, unsigned *col,
+                                                           const double2 *__restrict__ ent_pos, uint4 *ell_q,
                                                            int *__restrict__ cnt, int *__restrict__ totals,
-                                                           int *__restrict__ flags)
+                                                           int *__restrict__ flags, int cap)
 {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ TileDesc T;
-    __shared__ int s_key[kWalkCap];
-    __shared__ double s_x[kWalkCap], s_y[kWalkCap];
+    double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
+    int *s_key = reinterpret_cast<int *>(s_xy + cap);
     const int ncx = P.ncx, ncy = g->ncy;
-    tile_setup(T, blockIdx.x, ncx, ncy, cell_start, kWalkCap);
-    if (!T.valid || T.own_b == T.own_e) return;
+    tile_load(T, tiles, walk_tile_of_block(blockIdx.x, tiles_per_row(ncx, tile_w), gridDim.x));
+    __syncthreads();
+    if (!(T.flags & kTileValid)) return;
     SPHB_TILE_FOR_STAGED(T, e, slot)
     {
         s_key[slot] = ent_key[e];
-        const double2 p = ent_pos[e];
-        s_x[slot] = p.x;
-        s_y[slot] = p.y;
+        s_xy[slot] = ent_pos[e];
     }
     __syncthreads();
 
     const size_t stride = P.ell_stride;
-    const int cyi = T.cy;
-    int t_half = 0, t_full = 0, t_max = 0;
-    for (int e0 = T.own_b; e0 < T.own_e; e0 += kTileThreads) {
-        const int ew = e0 + (int)threadIdx.x;
-        if (ew >= T.own_e) break;
-        if ((size_t)ew >= stride) {   // more entries than ELL columns: reported, never written
+    const int qcap = P.ell_cap >> 3;
+    const bool seam_tile = (T.flags & kTileSeam) != 0;
+    const int dummy = T.n_staged;
+    int t_full = 0, t_max = 0;
+    SPHB_TILE_FOR_OWN(T, ew, slot_i, orow)
+    {
+        if ((size_t)ew >= stride) {   // more entries than list columns: reported, never written
             atomicOr(flags, kErrCsrCap);
             continue;
         }
-        const int own_slot = tile_lookup(T, ew, 1);
-        const int key_i = own_slot >= 0 ? s_key[own_slot] : ent_key[ew];
+        const int key_i = s_key[slot_i];
         const int i = key_i >> 3;
         if ((key_i & 3) != 0 || i >= P.n_fluid) {   // ghost or wall entry: not a walker
             cnt[ew] = 0;
             continue;
         }
-        const double2 pi = own_slot >= 0 ? make_double2(s_x[own_slot], s_y[own_slot]) : ent_pos[ew];
-        const int home = cell_of[i];
-        const int cxi = home % ncx;
-        // does i itself own ghost entries?  (then a lower fluid index may have met one of them)
-        const bool i_multi = (pi.x > P.DL - P.cutoff || pi.x < P.cutoff) && ncx > 1;
-        int count = 0, n_half = 0;
-
-        for (int oy = -1; oy <= 1; ++oy) {
-            const int cy = cyi + oy;
-            if (cy < 0 || cy >= ncy) continue;
-            int cx_prev[2] = {-1, -1};
-            for (int ox = -1; ox <= 1; ++ox) {
-                int cx = cxi + ox;
-                if (cx < 0) cx += ncx;
-                else if (cx >= ncx) cx -= ncx;
-                if (cx < 0 || cx >= ncx) continue;
-                // n_cell_x <= 2: the wrapped stencil revisits a column.  The reference re-walks it, but
-                // every entry it accepted is already in seen_neighbor and every entry it rejected is
-                // rejected again by the same arithmetic (nb:342-372), so the revisit emits nothing.
-                if (cx == cx_prev[0] || cx == cx_prev[1]) continue;
-                cx_prev[ox == -1 ? 0 : 1] = cx;
-                int cb, ce;
-                tile_cell_range(T, oy + 1, cx, ncx, cb, ce);
-                if (cb == ce) continue;
-                int n_staged;
-                const int sb = tile_lookup_run(T, cb, ce, oy + 1, n_staged);
-                for (int e = cb; e < ce; ++e) {   // entries are stored last-inserted first
-                    const int s = (e - cb) < n_staged ? sb + (e - cb) : -1;   // -1: beyond the staged part
-                    const int key = s >= 0 ? s_key[s] : ent_key[e];
-                    const int j = key >> 3;
-                    if (j == i) continue;
-                    const bool low_fluid = j < P.n_fluid && j < i;
-                    if (HALF && low_fluid) continue;                       // nb:353
-                    const bool seam = (key & 4) || (low_fluid && i_multi);
-                    if (seam) {   // seen_neighbor (nb:342): j may already be in the row through another entry
-                        bool dup = false;
-                        const int lim = count < P.ell_cap ? count : P.ell_cap;
-                        for (int q = 0; q < lim; ++q)
-                            dup |= ((ent_key[ell_entry(col[(size_t)q * stride + ew])] >> 3) == j);
-                        if (dup) continue;
+        const double2 pi = s_xy[slot_i];
+        const int cyi = T.cy0 + orow;
+        const int ri = orow + 1;   // staged row of the walker
+        RowWriter row;
+        row.init(ell_q + ew, stride, qcap);
+        // the walker's column: binary search of its entry in the staged cell starts of its row
+        int cxi;
+        {
+            int lo = T.cx0 - T.a, hi = T.cx1 - T.a;   // cs[ri][lo] <= ew < cs[ri][hi]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (T.cs[ri][mid] <= ew) lo = mid;
+                else hi = mid;
+            }
+            cxi = T.a + lo;
+        }
+        if (!seam_tile || (cxi >= 1 && cxi <= ncx - 3 && ncx >= 6)) {
+            // ---- interior walker: per stencil row one contiguous slot range; first a branch-free pass
+            // that records the accepted candidates as a bit mask, then the mask is unrolled into the row
+#pragma unroll 1
+            for (int r = ri - 1; r <= ri + 1; ++r) {
+                const int cy = cyi + (r - ri);
+                if (cy < 0 || cy >= ncy) continue;
+                const int k0 = cxi - 1 - T.a;
+                const int c0 = T.cs[r][k0];
+                const int sb = T.seg[3 * r].off + (c0 - T.seg[3 * r].b);
+                const int se = sb + (T.cs[r][k0 + 3] - c0);
+#pragma unroll 1
+                for (int s0 = sb; s0 < se; s0 += 32) {
+                    const int s1 = min(s0 + 32, se);
+                    unsigned mask = 0u, edge = 0u, bit = 1u;
+                    for (int s = s0; s < s1; ++s, bit <<= 1) {
+                        const double2 pj = s_xy[s];
+                        const double dx = pi.x - pj.x;
+                        const double dy = pi.y - pj.y;
+                        const double r2 = dx * dx + dy * dy;
+                        const bool in = r2 > 1e-24 && r2 < P.rc2;       // also rejects the walker itself
+                        mask |= in ? bit : 0u;
+                        edge |= (in && !(r2 < P.rc2_safe)) ? bit : 0u;
                     }
-                    int m, acc = e, row_off = oy;
-                    if (low_fluid && seam) {
-                        const double2 pj = snap[j];
-                        const int home_j = cell_of[j];
-                        const int sh = replay_low_walk(pj.x, pj.y, home_j, pi.x, pi.y, home, ncy, P);
-                        if (sh == 2) continue;
-                        acc = ent_of[j];   // the row names j's REAL entry; the image shift goes into m
-                        m = -sh;
-                        row_off = home_j / ncx - cyi;
-                    } else {
-                        const double ex = s >= 0 ? s_x[s] : ent_pos[e].x;
-                        const double ey = s >= 0 ? s_y[s] : ent_pos[e].y;
-                        if (!accept_entry(pi.x, pi.y, ex, ey, P, m)) continue;
+                    while (edge) {   // last 1e-12 below the cut-off: the reference's kernel-support test
+                        const int k = __ffs((int)edge) - 1;
+                        edge &= edge - 1;
+                        const double2 pj = s_xy[s0 + k];
+                        const double dx = pi.x - pj.x;
+                        const double dy = pi.y - pj.y;
+                        if (!support_exact(dx * dx + dy * dy, P)) mask &= ~(1u << k);
                     }
-                    if (count < P.ell_cap) col[(size_t)count * stride + ew] = ell_pack(acc, m, row_off);
-                    ++count;
-                    n_half += low_fluid ? 0 : 1;
+                    while (mask) {
+                        const int k = __ffs((int)mask) - 1;
+                        mask &= mask - 1;
+                        if (HALF) {
+                            const int j = s_key[s0 + k] >> 3;
+                            if (j < P.n_fluid && j < i) continue;   // nb:353
+                        }
+                        row.push(s0 + k, 0);
+                    }
+                }
+            }
+        } else {
+            // ---- general walker (periodic seam)
+            const int home = cyi * ncx + cxi;
+            // does i itself own ghost entries?  (then a lower fluid index may have met one of them)
+            const bool i_multi = (pi.x > P.DL - P.cutoff || pi.x < P.cutoff) && ncx > 1;
+            for (int oy = -1; oy <= 1; ++oy) {
+                const int cy = cyi + oy;
+                if (cy < 0 || cy >= ncy) continue;
+                int cx_prev[2] = {-1, -1};
+                for (int ox = -1; ox <= 1; ++ox) {
+                    int cx = cxi + ox;
+                    if (cx < 0) cx += ncx;
+                    else if (cx >= ncx) cx -= ncx;
+                    if (cx < 0 || cx >= ncx) continue;
+                    // n_cell_x <= 2: the wrapped stencil revisits a column.  The reference re-walks it, but
+                    // every entry it accepted is already in seen_neighbor and every entry it rejected is
+                    // rejected again by the same arithmetic (nb:342-372), so the revisit emits nothing.
+                    if (cx == cx_prev[0] || cx == cx_prev[1]) continue;
+                    cx_prev[ox == -1 ? 0 : 1] = cx;
+                    int sb, se;
+                    tile_cell_slots(T, ri + oy, cx, ncx, sb, se);
+                    const int rank_col = stencil_rank(cx, cxi, ncx);
+                    for (int s = sb; s < se; ++s) {   // entries are stored last-inserted first
+                        const int key = s_key[s];
+                        const int j = key >> 3;
+                        if (j == i) continue;
+                        const bool low_fluid = j < P.n_fluid && j < i;
+                        if (HALF && low_fluid) continue;                       // nb:353
+                        const bool seam = (key & 4) || (low_fluid && i_multi);
+                        const double2 pe = s_xy[s];
+                        int m;
+                        if (!seam) {
+                            if (!accept_entry(pi.x, pi.y, pe.x, pe.y, P, m)) continue;
+                        } else {
+                            // j has up to three entries; the ones the walk reaches BEFORE this one decide
+                            // whether j is already in the row (seen_neighbor, nb:342)
+                            // (a real entry is j's wrapped position in j's home cell: only ghosts look them up)
+                            const int kind = key & 3;
+                            const double2 pj = kind == 0 ? pe : snap[j];
+                            const int home_j = kind == 0 ? cy * ncx + cx : cell_of[j];
+                            const Entries E = entries_of(pj.x, home_j, P);
+                            const int rank_cur = rank_col * 3 + (2 - kind);
+                            if (low_fluid) {
+                                // the pair is decided by j's walk: the first entry of j the walk meets carries it
+                                bool first = true;
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) {
+                                    if (k == kind || E.cx[k] < 0) continue;
+                                    const int rk = stencil_rank(E.cx[k], cxi, ncx);
+                                    if (rk >= 0 && rk * 3 + (2 - k) < rank_cur) first = false;
+                                }
+                                if (!first) continue;
+                                const int sh = replay_low_walk(pj.x, pj.y, home_j, pi.x, pi.y, home, ncy, P);
+                                if (sh == kNoPair) continue;
+                                m = -sh + (kind == 1 ? -1 : (kind == 2 ? 1 : 0));   // relative to the entry met
+                            } else {
+                                if (!accept_entry(pi.x, pi.y, pe.x, pe.y, P, m)) continue;
+                                bool dup = false;
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) {
+                                    if (k == kind || E.cx[k] < 0) continue;
+                                    const int rk = stencil_rank(E.cx[k], cxi, ncx);
+                                    if (rk >= 0 && rk * 3 + (2 - k) < rank_cur) {
+                                        int m2;
+                                        dup |= accept_entry(pi.x, pi.y, E.x[k], pj.y, P, m2);
+                                    }
+                                }
+                                if (dup) continue;
+                            }
+                        }
+                        row.push(s, m);
+                    }
                 }
             }
         }
-        cnt[ew] = count;
-        t_half += n_half;
-        t_full += count;
-        t_max = max(t_max, count);
+        row.finish(dummy);
+        cnt[ew] = row.count;
+        t_full += row.count;
+        t_max = max(t_max, row.count);
     }
-    // totals: half pairs, full entries, longest row (capacity check)
+    // totals: entries, longest row (capacity check)
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
-        t_half += __shfl_xor_sync(0xffffffffu, t_half, d);
         t_full += __shfl_xor_sync(0xffffffffu, t_full, d);
         t_max = max(t_max, __shfl_xor_sync(0xffffffffu, t_max, d));
     }
     if ((threadIdx.x & 31) == 0) {
-        if (t_half) atomicAdd(&totals[0], t_half);
         if (t_full) atomicAdd(&totals[1], t_full);
+        if (HALF && t_full) atomicAdd(&totals[0], t_full);
         if (t_max) atomicMax(&totals[2], t_max);
         if (t_max > P.ell_cap) atomicOr(flags, kErrCsrCap);
     }
 }
 
+// Number of reference half pairs inside a FULL row set (status / export sizing only): entries whose
+// neighbour is a wall particle or a higher fluid index.
+__global__ void __launch_bounds__(kTileThreads) k_half_total(NbrParams P, const TileDesc *__restrict__ tiles,
+                                                            const int *__restrict__ ent_key,
+                                                            const uint4 *__restrict__ ell_q,
+                                                            const int *__restrict__ cnt, int *__restrict__ totals,
+                                                            int cap)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ TileDesc T;
+    int *s_key = reinterpret_cast<int *>(smem_raw);
+    tile_load(T, tiles, blockIdx.x);
+    __syncthreads();
+    if (!(T.flags & kTileValid)) return;
+    SPHB_TILE_FOR_STAGED(T, e, slot) s_key[slot] = ent_key[e];
+    __syncthreads();
+    int n_half = 0;
+    SPHB_TILE_FOR_OWN(T, ew, si, orow)
+    {
+        if ((size_t)ew >= P.ell_stride) continue;
+        const int i = s_key[si] >> 3;
+        const int n = min(cnt[ew], P.ell_cap);
+        for (int k = 0; k < n; ++k) {
+            const uint4 q = ell_q[(size_t)(k >> 3) * P.ell_stride + ew];
+            const int j = s_key[ell_slot(ell_extract(q, k & 7))] >> 3;
+            n_half += (j >= P.n_fluid || j > i) ? 1 : 0;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_half += __shfl_xor_sync(0xffffffffu, n_half, d);
+    if ((threadIdx.x & 31) == 0 && n_half) atomicAdd(&totals[0], n_half);
+}
+
+// ---- export paths (not hot): rows by particle out of the tile-local lists --------------------------------
+__device__ __forceinline__ const TileDesc &tile_of_cell(const TileDesc *tiles, int cell, int ncx, int w)
+{
+    return tiles[(size_t)((cell / ncx) / kTileRows) * tiles_per_row(ncx, w) + (cell % ncx) / w];
+}
+
+// k-th entry of the row of the walker at entry ew -> global entry index and particle
+__device__ __forceinline__ int row_entry(const NbrParams &P, const TileDesc &T, const uint4 *__restrict__ ell_q, int ew, int k)
+{
+    const uint4 q = ell_q[(size_t)(k >> 3) * P.ell_stride + ew];
+    return tile_slot_entry(T, ell_slot(ell_extract(q, k & 7)));
+}
+
 // rows of the reference's half list inside a FULL row set: count of entries with j wall or j > i
-__global__ void __launch_bounds__(kBlock) k_half_count(NbrParams P, const int *__restrict__ ent_of,
+__global__ void __launch_bounds__(kBlock) k_half_count(NbrParams P, int tile_w, const TileDesc *__restrict__ tiles,
+                                                      const int *__restrict__ cell_of,
+                                                      const int *__restrict__ ent_of,
                                                       const int *__restrict__ ent_key,
-                                                      const unsigned *__restrict__ col,
+                                                      const uint4 *__restrict__ ell_q,
                                                       const int *__restrict__ cnt, int *__restrict__ half_cnt)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_fluid) return;
     const int e = ent_of[i];
-    const int n = min(cnt[e], P.ell_cap);
+    const TileDesc &T = tile_of_cell(tiles, cell_of[i], P.ncx, tile_w);
+    const int n = (T.flags & kTileValid) ? min(cnt[e], P.ell_cap) : 0;
     int c = 0;
     for (int k = 0; k < n; ++k) {
-        const int j = ent_key[ell_entry(col[(size_t)k * P.ell_stride + e])] >> 3;
+        const int j = ent_key[row_entry(P, T, ell_q, e, k)] >> 3;
         c += (j >= P.n_fluid || j > i) ? 1 : 0;
     }
     half_cnt[i] = c;
 }
 
 // nb:357-381 re-evaluated for the stored entry: identical operations, identical bits
-__global__ void __launch_bounds__(kBlock) k_export_pairs(NbrParams P, const int *__restrict__ ent_of,
+__global__ void __launch_bounds__(kBlock) k_export_pairs(NbrParams P, int tile_w, const TileDesc *__restrict__ tiles,
+                                                        const int *__restrict__ cell_of,
+                                                        const int *__restrict__ ent_of,
                                                         const int *__restrict__ ent_key,
                                                         const double2 *__restrict__ ent_pos,
-                                                        const unsigned *__restrict__ col,
+                                                        const uint4 *__restrict__ ell_q,
                                                         const int *__restrict__ cnt,
                                                         const int *__restrict__ half_ptr,
                                                         double *__restrict__ pair_i, double *__restrict__ pair_j,
@@ -482,11 +747,12 @@ __global__ void __launch_bounds__(kBlock) k_export_pairs(NbrParams P, const int 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_fluid) return;
     const int ew = ent_of[i];
+    const TileDesc &T = tile_of_cell(tiles, cell_of[i], P.ncx, tile_w);
     const double2 pi = ent_pos[ew];
-    const int n = min(cnt[ew], P.ell_cap);
+    const int n = (T.flags & kTileValid) ? min(cnt[ew], P.ell_cap) : 0;
     size_t o = (size_t)half_ptr[i];
     for (int k = 0; k < n; ++k) {
-        const int ea = ell_entry(col[(size_t)k * P.ell_stride + ew]);
+        const int ea = row_entry(P, T, ell_q, ew, k);
         const int j = ent_key[ea] >> 3;
         if (j < P.n_fluid && j < i) continue;
         const double2 pe = ent_pos[ea];   // a ghost entry already holds x_j -+ DL (nb:284,291)
@@ -509,23 +775,30 @@ __global__ void __launch_bounds__(kBlock) k_export_pairs(NbrParams P, const int 
 }
 
 // full rows by PARTICLE (export only): counts, then particle ids in walk order
-__global__ void __launch_bounds__(kBlock) k_row_count(NbrParams P, const int *__restrict__ ent_of,
+__global__ void __launch_bounds__(kBlock) k_row_count(NbrParams P, int tile_w, const TileDesc *__restrict__ tiles,
+                                                     const int *__restrict__ cell_of,
+                                                     const int *__restrict__ ent_of,
                                                      const int *__restrict__ cnt, int *__restrict__ row_cnt)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P.n_fluid) row_cnt[i] = min(cnt[ent_of[i]], P.ell_cap);
+    if (i >= P.n_fluid) return;
+    const TileDesc &T = tile_of_cell(tiles, cell_of[i], P.ncx, tile_w);
+    row_cnt[i] = (T.flags & kTileValid) ? min(cnt[ent_of[i]], P.ell_cap) : 0;
 }
-__global__ void __launch_bounds__(kBlock) k_row_fill(NbrParams P, const int *__restrict__ ent_of,
+__global__ void __launch_bounds__(kBlock) k_row_fill(NbrParams P, int tile_w, const TileDesc *__restrict__ tiles,
+                                                    const int *__restrict__ cell_of,
+                                                    const int *__restrict__ ent_of,
                                                     const int *__restrict__ ent_key,
-                                                    const unsigned *__restrict__ col, const int *__restrict__ cnt,
+                                                    const uint4 *__restrict__ ell_q, const int *__restrict__ cnt,
                                                     const int *__restrict__ row_ptr, int *__restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_fluid) return;
     const int e = ent_of[i];
-    const int n = min(cnt[e], P.ell_cap);
+    const TileDesc &T = tile_of_cell(tiles, cell_of[i], P.ncx, tile_w);
+    const int n = (T.flags & kTileValid) ? min(cnt[e], P.ell_cap) : 0;
     const size_t o = (size_t)row_ptr[i];
-    for (int k = 0; k < n; ++k) out[o + (size_t)k] = ent_key[ell_entry(col[(size_t)k * P.ell_stride + e])] >> 3;
+    for (int k = 0; k < n; ++k) out[o + (size_t)k] = ent_key[row_entry(P, T, ell_q, e, k)] >> 3;
 }
 
 NbrParams make_params(const NeighborWork &w)
@@ -551,38 +824,72 @@ NbrParams make_params(const NeighborWork &w)
     return P;
 }
 
+constexpr size_t kWalkSlotBytes = sizeof(double2) + sizeof(int);
+
+int set_walk_smem(size_t bytes)
+{
+    static size_t granted[2] = {0, 0};
+    if (bytes <= 48 * 1024) return 0;
+    if (bytes > granted[0]) {
+        SPHB_CUDA(cudaFuncSetAttribute(k_walk_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        granted[0] = bytes;
+    }
+    if (bytes > granted[1]) {
+        SPHB_CUDA(cudaFuncSetAttribute(k_walk_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        granted[1] = bytes;
+    }
+    return 0;
+}
+
 }  // namespace
 
 void NeighborWork::release_all()
 {
-    DevBuf *all[] = {&grid, &flags, &snap, &cell_of, &ent_of, &cell_cnt, &cell_start, &cell_fill, &ent_key, &ent_pos,
-                     &ell_cnt, &ell_col, &half_cnt, &half_ptr, &scan_tmp, &totals};
+    DevBuf *all[] = {&grid, &flags, &snap, &cell_of, &ent_of, &cell_cnt, &cell_start, &tmp_key, &tmp_pos, &tmp_cell,
+                     &ent_key, &ent_pos, &tiles, &ell_cnt, &ell_q, &half_cnt, &half_ptr, &scan_tmp, &totals};
     for (DevBuf *b : all) b->release();
 }
 
-// ELL rows are indexed by ENTRY (real + ghost): the stride is the entry capacity the rows may use.
-// Ghost entries are a sliver of the total unless the box is only a few cells long, so large problems
-// get n_total * 1.25 columns, small ones the reference's own worst case 3 n_total (nb:265).
+// Rows are indexed by ENTRY (real + ghost): the stride is the entry capacity.  Ghost entries are a
+// sliver of the total unless the box is only a few cells long, so large problems get n_total * 1.25
+// columns, small ones the reference's own worst case 3 n_total (nb:265).
+static size_t entry_capacity(size_t nt)
+{
+    size_t cap = nt < (1u << 20) ? 3 * nt : nt + nt / 4 + 4096;
+    return (cap + 31) & ~(size_t)31;
+}
+
 int neighbor_reserve_ell(NeighborWork &w, int rows)
 {
-    const size_t nt = (size_t)w.n_total;
-    size_t stride = nt < (1u << 20) ? 3 * nt : nt + nt / 4 + 4096;
-    stride = (stride + 31) & ~(size_t)31;
-    if (rows <= w.ell_cap && w.ell_col.p && stride == w.ell_stride) return 0;
+    rows = (rows + 7) & ~7;
+    const size_t stride = entry_capacity((size_t)w.n_total);
+    if (rows <= w.ell_cap && w.ell_q.p && stride == w.ell_stride) return 0;
     if (rows < w.ell_cap) rows = w.ell_cap;
     w.ell_stride = stride;
-    SPHB_TRY(w.ell_col.reserve((size_t)rows * stride * sizeof(unsigned)));
+    SPHB_TRY(w.ell_q.reserve((size_t)(rows / 8) * stride * sizeof(uint4)));
     SPHB_TRY(w.ell_cnt.reserve(stride * sizeof(int)));
     w.ell_cap = rows;
+    return 0;
+}
+
+// Tile geometry: `w` cells per tile, descriptors for every cell row the grid may have.
+static int plan_tiles(NeighborWork &w, int tile_w)
+{
+    const int ncx = std::max(1, (int)std::ceil(w.DL / (2.0 * w.h)));
+    if (tile_w > kMaxTileW) tile_w = kMaxTileW;
+    if (tile_w < 1) tile_w = 1;
+    w.tile_w = tile_w;
+    w.n_tiles = (unsigned)(tile_rows(w.cell_cap / ncx) * tiles_per_row(ncx, tile_w));
+    SPHB_TRY(w.tiles.reserve((size_t)w.n_tiles * sizeof(TileDesc)));
     return 0;
 }
 
 // Size every buffer whose size is known a priori.  y hints bound the cell rows (a fluid particle
 // escaping beyond the hinted range raises the cell-capacity flag instead of writing out of bounds).
 int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL, double y_min_hint,
-                  double y_max_hint, int max_nbr_hint)
+                  double y_max_hint, int max_nbr_hint, int tile_cap_limit)
 {
-    const bool resized = n_total != w.n_total;
+    const bool resized = n_total != w.n_total || h != w.h || DL != w.DL;
     w.n_fluid = n_fluid;
     w.n_total = n_total;
     w.h = h;
@@ -595,41 +902,62 @@ int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL
                          ncx_d, ncy_d);
     if (3LL * (long long)n_total >= (1LL << 28))
         return set_error("SPH:Neighbor:entryCapacity", "3 n_total exceeds the 2^28 limit of the entry index");
-    w.cell_cap = (int)(ncx_d * ncy_d);
+    const int new_cell_cap = (int)(ncx_d * ncy_d);
+    const bool regrid = new_cell_cap != w.cell_cap;
+    w.cell_cap = new_cell_cap;
     const size_t nt = (size_t)n_total;
+    const size_t ecap = entry_capacity(nt);
     SPHB_TRY(w.grid.reserve(sizeof(GridDesc)));
     if (!w.flags.p) {
         SPHB_TRY(w.flags.reserve(sizeof(int)));
         SPHB_CUDA(cudaMemset(w.flags.p, 0, sizeof(int)));
     }
-    SPHB_TRY(w.totals.reserve(4 * sizeof(int)));
+    SPHB_TRY(w.totals.reserve(8 * sizeof(int)));
     SPHB_TRY(w.snap.reserve(nt * sizeof(double2)));
     SPHB_TRY(w.cell_of.reserve(nt * sizeof(int)));
     SPHB_TRY(w.ent_of.reserve(nt * sizeof(int)));
-    SPHB_TRY(w.cell_cnt.reserve(((size_t)w.cell_cap + 1) * sizeof(int)));
+    SPHB_TRY(w.cell_cnt.reserve(2 * ((size_t)w.cell_cap + 1) * sizeof(int)));
     SPHB_TRY(w.cell_start.reserve(((size_t)w.cell_cap + 1) * sizeof(int)));
-    SPHB_TRY(w.cell_fill.reserve(((size_t)w.cell_cap + 1) * sizeof(int)));
-    SPHB_TRY(w.ent_key.reserve(3 * nt * sizeof(int)));
-    SPHB_TRY(w.ent_pos.reserve(3 * nt * sizeof(double2)));
+    SPHB_TRY(w.tmp_key.reserve(3 * nt * sizeof(int)));
+    SPHB_TRY(w.tmp_pos.reserve(3 * nt * sizeof(double2)));
+    SPHB_TRY(w.tmp_cell.reserve(3 * nt * sizeof(int)));
+    SPHB_TRY(w.ent_key.reserve(ecap * sizeof(int)));
+    SPHB_TRY(w.ent_pos.reserve(ecap * sizeof(double2)));
     if (resized) {
         w.ell_cap = 0;   // the stride depends on n_total
-        w.ell_col.release();
+        w.ell_q.release();
     }
     SPHB_TRY(neighbor_reserve_ell(w, max_nbr_hint > 0 ? max_nbr_hint : kDefaultEllRows));
+    w.tile_cap_limit = tile_cap_limit > 0 && tile_cap_limit < kMaxSlots ? tile_cap_limit : kMaxSlots;
+    if (resized || regrid || w.tile_w == 0) {
+        w.tile_fitted = false;
+        // ~0.9 own entries per thread for a uniformly filled grid; the first exact build narrows the
+        // tiles if the densest neighbourhood does not fit the shared-memory slots
+        const double per_cell = (double)n_total / std::max(1.0, ncx_d * (ncy_d - 9.0));
+        int tw = (int)std::floor(0.955 * kTileThreads / std::max(per_cell * kTileRows, 1e-9));
+        SPHB_TRY(plan_tiles(w, std::max(1, std::min(tw, kMaxTileW))));
+        const double guess = (double)kStageRows * (w.tile_w + 2) * per_cell * 1.25 + 64.0;
+        w.tile_cap = (int)std::min((double)w.tile_cap_limit, guess);
+    } else {
+        SPHB_TRY(plan_tiles(w, w.tile_w));
+    }
     return 0;
 }
 
-// Builds the list from `pos` (device, double2[n_total]).  A row longer than the ELL raises the
-// capacity flag; with `exact` the build then synchronises, grows the ELL to the longest row and walks
-// again (stateless path and the first resident build); in steady state there is no host round trip.
+// Builds the list from `pos` (device, double2[n_total]).  A row longer than the list columns or a
+// neighbourhood larger than the tile slots raises a capacity flag; with `exact` the build then
+// synchronises, grows what was short (or narrows the tiles) and walks again (stateless path and the
+// first resident build); in steady state there is no host round trip.
 int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exact, cudaStream_t st,
                    long long *launches, Prof *prof)
 {
     NbrParams P = make_params(w);
     GridDesc *g = w.grid.as<GridDesc>();
     int *flags = w.flags.as<int>();
-    const int nt = w.n_total, nf = w.n_fluid;
+    const int nt = w.n_total;
     long long nl = 0;
+    int *cell_cnt = w.cell_cnt.as<int>();
+    int *cell_fill = cell_cnt + ((size_t)w.cell_cap + 1);
 
     {
         ProfScope ps(prof, kPfNbrGrid, st);
@@ -638,70 +966,119 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
         if (blocks > 148 * 8) blocks = 148 * 8;
         k_yrange<<<blocks, 256, 0, st>>>(pos, nt, g);
         k_grid_setup<<<1, 1, 0, st>>>(g, P, flags);
-        SPHB_CUDA(cudaMemsetAsync(w.cell_cnt.p, 0, ((size_t)w.cell_cap + 1) * sizeof(int), st));
-        SPHB_CUDA(cudaMemsetAsync(w.cell_fill.p, 0, ((size_t)w.cell_cap + 1) * sizeof(int), st));
+        SPHB_CUDA(cudaMemsetAsync(cell_cnt, 0, 2 * ((size_t)w.cell_cap + 1) * sizeof(int), st));
     }
     {
         ProfScope ps(prof, kPfNbrBin, st);
-        k_bin_count<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.snap.as<double2>(), w.cell_of.as<int>(),
-                                                     w.cell_cnt.as<int>());
+        k_bin_count<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.snap.as<double2>(), w.cell_of.as<int>(), cell_cnt);
     }
     nl += 4;
     {
         ProfScope ps(prof, kPfNbrScan, st);
-        SPHB_TRY(exclusive_scan_i32(w.cell_cnt.as<int>(), w.cell_start.as<int>(), (size_t)w.cell_cap, w.scan_tmp,
-                                    &g->n_entries, st, &nl));
+        SPHB_TRY(exclusive_scan_i32(cell_cnt, w.cell_start.as<int>(), (size_t)w.cell_cap, w.scan_tmp, &g->n_entries, st,
+                                    &nl));
     }
     {
         ProfScope ps(prof, kPfNbrScatter, st);
-        k_scatter<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.cell_start.as<int>(), w.cell_fill.as<int>(),
-                                                   w.ent_key.as<int>(), w.ent_pos.as<double2>());
+        k_scatter<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.cell_start.as<int>(), cell_fill, w.tmp_key.as<int>(),
+                                                   w.tmp_pos.as<double2>(), w.tmp_cell.as<int>());
     }
     {
         ProfScope ps(prof, kPfNbrCanon, st);
-        k_cell_canon<<<grid_for((size_t)w.cell_cap), kBlock, 0, st>>>(g, w.cell_start.as<int>(), w.ent_key.as<int>(),
-                                                                      w.ent_pos.as<double2>(), w.ent_of.as<int>());
+        k_cell_canon<<<grid_for(w.ell_stride), kBlock, 0, st>>>(g, (int)w.ell_stride, w.cell_start.as<int>(),
+                                                              w.tmp_key.as<int>(), w.tmp_pos.as<double2>(),
+                                                              w.tmp_cell.as<int>(), w.ent_key.as<int>(),
+                                                              w.ent_pos.as<double2>(), w.ent_of.as<int>(), flags);
     }
     nl += 2;
 
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int attempt = 0; attempt < 8; ++attempt) {
         ProfScope ps(prof, kPfNbrWalk, st);
-        SPHB_CUDA(cudaMemsetAsync(w.totals.p, 0, 4 * sizeof(int), st));
-        // one CTA per tile of kTileCells cells; rows beyond the device-side n_cell_y exit at once
-        const unsigned n_tiles = (unsigned)((w.cell_cap / P.ncx) * tiles_per_row(P.ncx));
+        SPHB_CUDA(cudaMemsetAsync(w.totals.p, 0, 8 * sizeof(int), st));
+        k_tile_setup<<<grid_for(w.n_tiles), kBlock, 0, st>>>(g, P.ncx, w.tile_w, w.n_tiles, w.tile_cap,
+                                                            (int)w.ell_stride, w.cell_start.as<int>(), w.tiles.as<TileDesc>(),
+                                                            w.totals.as<int>(), flags);
+        const size_t smem = (size_t)w.tile_cap * kWalkSlotBytes;
+        SPHB_TRY(set_walk_smem(smem));
+        // one CTA per tile; rows beyond the device-side n_cell_y exit at once
         if (half_only)
-            k_walk_tile<true><<<n_tiles, kTileThreads, 0, st>>>(
-                P, g, w.snap.as<double2>(), w.cell_of.as<int>(), w.ent_of.as<int>(), w.cell_start.as<int>(),
-                w.ent_key.as<int>(), w.ent_pos.as<double2>(), w.ell_col.as<unsigned>(), w.ell_cnt.as<int>(),
-                w.totals.as<int>(), flags);
+            k_walk_tile<true><<<w.n_tiles, kTileThreads, smem, st>>>(
+                P, g, w.tiles.as<TileDesc>(), w.tile_w, w.snap.as<double2>(), w.cell_of.as<int>(),
+                w.ent_key.as<int>(), w.ent_pos.as<double2>(), w.ell_q.as<uint4>(), w.ell_cnt.as<int>(),
+                w.totals.as<int>(), flags, w.tile_cap);
         else
-            k_walk_tile<false><<<n_tiles, kTileThreads, 0, st>>>(
-                P, g, w.snap.as<double2>(), w.cell_of.as<int>(), w.ent_of.as<int>(), w.cell_start.as<int>(),
-                w.ent_key.as<int>(), w.ent_pos.as<double2>(), w.ell_col.as<unsigned>(), w.ell_cnt.as<int>(),
-                w.totals.as<int>(), flags);
-        nl += 1;
-        if (!exact || attempt == 1) break;
+            k_walk_tile<false><<<w.n_tiles, kTileThreads, smem, st>>>(
+                P, g, w.tiles.as<TileDesc>(), w.tile_w, w.snap.as<double2>(), w.cell_of.as<int>(),
+                w.ent_key.as<int>(), w.ent_pos.as<double2>(), w.ell_q.as<uint4>(), w.ell_cnt.as<int>(),
+                w.totals.as<int>(), flags, w.tile_cap);
+        nl += 2;
+        if (!exact) break;
         int host[4] = {0, 0, 0, 0};
         SPHB_CUDA(cudaMemcpyAsync(host, w.totals.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         SPHB_CUDA(cudaStreamSynchronize(st));
-        if (host[2] <= w.ell_cap) break;
-        // grow to the longest row (+ head-room for later rebuilds) and walk again
-        SPHB_TRY(neighbor_reserve_ell(w, host[2] + host[2] / 4 + 4));
+        const bool rows_short = host[2] > w.ell_cap;
+        const bool tile_short = host[3] > w.tile_cap;
+        if (!rows_short && !tile_short) {
+            // fit the slot count to what the tiles hold (shared memory per CTA decides the occupancy of
+            // every gather kernel of the step); later rebuilds only raise the flag
+            if (attempt == 0 && !w.tile_fitted) {
+                w.tile_cap = std::min(w.tile_cap, host[3] + host[3] / 8 + 16);
+                w.tile_fitted = true;
+            }
+            break;
+        }
+        if (tile_short) {
+            // first give the tiles the slots they need (+ head-room for later rebuilds); if even the
+            // kernels' shared memory cannot hold the densest neighbourhood, halve the tile width
+            if (host[3] <= w.tile_cap_limit) {
+                w.tile_cap = std::min(w.tile_cap_limit, host[3] + host[3] / 8 + 16);
+            } else if (w.tile_w > 1) {
+                SPHB_TRY(plan_tiles(w, w.tile_w / 2));
+                w.tile_cap = w.tile_cap_limit;
+            } else {
+                return set_error("SPH:Neighbor:entryCapacity",
+                                 "%d entries in one 3x3 cell neighbourhood exceed the %d a tile can stage", host[3],
+                                 w.tile_cap_limit);
+            }
+        }
+        if (rows_short) SPHB_TRY(neighbor_reserve_ell(w, host[2] + host[2] / 4 + 4));
+        // clear the capacity flags of the failed attempt and walk again
         int f = 0;
         SPHB_CUDA(cudaMemcpyAsync(&f, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
         SPHB_CUDA(cudaStreamSynchronize(st));
-        f &= ~kErrCsrCap;
+        f &= ~(kErrCsrCap | kErrTileCap);
         SPHB_CUDA(cudaMemcpyAsync(flags, &f, sizeof(int), cudaMemcpyHostToDevice, st));
         SPHB_CUDA(cudaStreamSynchronize(st));
         P = make_params(w);
     }
     w.half_only = half_only;
+    w.half_valid = half_only;   // a full build counts its half pairs on demand (neighbor_half_total)
     SPHB_CUDA(cudaGetLastError());
     if (launches) *launches += nl;
     return 0;
 }
 
-// The reference's half-pair COO list from the ELL rows (device output pointers, n_half slots each).
+// totals[0] = number of reference half pairs of the current list (computed on demand after a full build)
+int neighbor_half_total(NeighborWork &w, cudaStream_t st)
+{
+    if (w.half_valid) return 0;
+    NbrParams P = make_params(w);
+    const size_t smem = (size_t)w.tile_cap * sizeof(int);
+    static size_t granted = 0;
+    if (smem > 48 * 1024 && smem > granted) {
+        SPHB_CUDA(cudaFuncSetAttribute(k_half_total, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        granted = smem;
+    }
+    SPHB_CUDA(cudaMemsetAsync(w.totals.p, 0, sizeof(int), st));
+    k_half_total<<<w.n_tiles, kTileThreads, smem, st>>>(P, w.tiles.as<TileDesc>(), w.ent_key.as<int>(),
+                                                        w.ell_q.as<uint4>(), w.ell_cnt.as<int>(), w.totals.as<int>(),
+                                                        w.tile_cap);
+    SPHB_CUDA(cudaGetLastError());
+    w.half_valid = true;
+    return 0;
+}
+
+// The reference's half-pair COO list from the rows (device output pointers, n_half slots each).
 int neighbor_export_pairs(NeighborWork &w, size_t n_half, double *pair_i, double *pair_j, double *dx, double *dy,
                           double *r, double *W, double *dW, cudaStream_t st)
 {
@@ -710,13 +1087,14 @@ int neighbor_export_pairs(NeighborWork &w, size_t n_half, double *pair_i, double
     const size_t nf = (size_t)w.n_fluid;
     SPHB_TRY(w.half_cnt.reserve((nf + 1) * sizeof(int)));
     SPHB_TRY(w.half_ptr.reserve((nf + 1) * sizeof(int)));
-    k_half_count<<<grid_for(nf), kBlock, 0, st>>>(P, w.ent_of.as<int>(), w.ent_key.as<int>(),
-                                                  w.ell_col.as<unsigned>(), w.ell_cnt.as<int>(), w.half_cnt.as<int>());
+    k_half_count<<<grid_for(nf), kBlock, 0, st>>>(P, w.tile_w, w.tiles.as<TileDesc>(), w.cell_of.as<int>(),
+                                                  w.ent_of.as<int>(), w.ent_key.as<int>(), w.ell_q.as<uint4>(),
+                                                  w.ell_cnt.as<int>(), w.half_cnt.as<int>());
     SPHB_TRY(exclusive_scan_i32(w.half_cnt.as<int>(), w.half_ptr.as<int>(), nf, w.scan_tmp, nullptr, st, nullptr));
-    k_export_pairs<<<grid_for(nf), kBlock, 0, st>>>(P, w.ent_of.as<int>(), w.ent_key.as<int>(),
-                                                    w.ent_pos.as<double2>(), w.ell_col.as<unsigned>(),
-                                                    w.ell_cnt.as<int>(), w.half_ptr.as<int>(), pair_i, pair_j, dx, dy,
-                                                    r, W, dW);
+    k_export_pairs<<<grid_for(nf), kBlock, 0, st>>>(P, w.tile_w, w.tiles.as<TileDesc>(), w.cell_of.as<int>(),
+                                                    w.ent_of.as<int>(), w.ent_key.as<int>(), w.ent_pos.as<double2>(),
+                                                    w.ell_q.as<uint4>(), w.ell_cnt.as<int>(), w.half_ptr.as<int>(),
+                                                    pair_i, pair_j, dx, dy, r, W, dW);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -727,10 +1105,12 @@ int neighbor_export_csr(NeighborWork &w, int *row_ptr, int *col, cudaStream_t st
     NbrParams P = make_params(w);
     const size_t nf = (size_t)w.n_fluid;
     SPHB_TRY(w.half_cnt.reserve((nf + 1) * sizeof(int)));
-    k_row_count<<<grid_for(nf), kBlock, 0, st>>>(P, w.ent_of.as<int>(), w.ell_cnt.as<int>(), w.half_cnt.as<int>());
+    k_row_count<<<grid_for(nf), kBlock, 0, st>>>(P, w.tile_w, w.tiles.as<TileDesc>(), w.cell_of.as<int>(),
+                                                 w.ent_of.as<int>(), w.ell_cnt.as<int>(), w.half_cnt.as<int>());
     SPHB_TRY(exclusive_scan_i32(w.half_cnt.as<int>(), row_ptr, nf, w.scan_tmp, nullptr, st, nullptr));
     if (col)
-        k_row_fill<<<grid_for(nf), kBlock, 0, st>>>(P, w.ent_of.as<int>(), w.ent_key.as<int>(), w.ell_col.as<unsigned>(),
+        k_row_fill<<<grid_for(nf), kBlock, 0, st>>>(P, w.tile_w, w.tiles.as<TileDesc>(), w.cell_of.as<int>(),
+                                                    w.ent_of.as<int>(), w.ent_key.as<int>(), w.ell_q.as<uint4>(),
                                                     w.ell_cnt.as<int>(), row_ptr, col);
     SPHB_CUDA(cudaGetLastError());
     return 0;

@@ -1,18 +1,20 @@
 // ops_csr.cu -- fp64 physics operators of the DEVICE-RESIDENT path as per-particle gathers over the
-// ELL neighbour list (column-major, so a warp's k-th neighbour indices are one coalesced load) (rows P1-P9 and the epilogues of S1 in SURVEY.md 8(a)).
+// tile-local neighbour lists (rows P1-P9 and the epilogues of S1 in SURVEY.md 8(a)).
 //
-// One thread owns one particle and walks its CSR row; every pair is therefore evaluated from both
-// ends, there are no atomics and the sums are deterministic.  All the reference's pair formulas are
-// symmetric under (i <-> j, e -> -e) (ph:262-291, 502-520, 667-685, 891-925, 1091-1099), so the
-// gather uses one formula per entry with e pointing from j to i.
+// One CTA owns one cell tile (tile.cuh): it stages what the operator needs of every entry of the tile's
+// 3 x (w + 2) cell neighbourhood into shared memory with coalesced loads, then one thread per own
+// particle walks its row -- 16-bit slots, eight per 128-bit load -- and reads its neighbours out of
+// shared memory.  Every pair is evaluated from both ends, there are no atomics and the sums are
+// deterministic.  All the reference's pair formulas are symmetric under (i <-> j, e -> -e) (ph:262-291,
+// 502-520, 667-685, 891-925, 1091-1099), so the gather uses one formula per entry with e from j to i.
 //
 // Geometry is FROZEN at list-build time, as in the reference, where every mode consumes the pair
-// cache computed by the neighbour search: dx = (x_i - x_j) + shift*DL from the
-// position snapshot `snap` and the image code stored in the top four bits of each list entry.
+// cache computed by the neighbour search: dx = (x_i - x_entry) + shift*DL from the
+// entry positions of the build and the image code stored with each list entry.
 //
-// Fusion: viscous + transport share one row walk (same inputs B_j, Vol_j); the pressure kernel
-// recomputes the neighbour's half-step density/pressure inline (ph:857-862) and its epilogue does the
-// velocity kick and the full position update (ph:1400-1404, 863-864, 1066-1069); the continuity
+// Fusion: viscous + transport share one row walk (same inputs B_j, Vol_j); the pressure kernel reads
+// the neighbours' half-step density/pressure staged by k_time_step (ph:857-862) and its epilogue does
+// the velocity kick and the full position update (ph:1400-1404, 863-864, 1066-1069); the continuity
 // kernel's epilogue finishes density/EOS (ph:1440-1446), wraps x (m:570-577) and feeds the grid-wide
 // max|v| reduction (warp shuffle + one atomicMax per warp) that the next dt is computed from on the
 // device (m:519-527).
@@ -24,20 +26,18 @@ namespace sphb {
 
 namespace {
 
-constexpr int kPhysCap = 512;   // staged entries per tile (3 x 18 cells x ~6.8 = 365 on the lattice)
-
 // Geometry of one list entry, recomputed from build-time entry positions (16 B staged per neighbour
 // instead of the reference's 40 B cached per pair): e points from j to i.
 struct Geo {
     double dx, dy, r, ex, ey;
 };
 
-__device__ __forceinline__ Geo pair_geometry(double2 pi, double xj, double yj, int m, const PhysParams &P)
+__device__ __forceinline__ Geo pair_geometry(double2 pi, double2 pj, int m, const PhysParams &P)
 {
     Geo g;
-    const double shift = m == 0 ? 0.0 : (m > 0 ? P.DL : -P.DL);   // minimum image (nb:359-363)
-    g.dx = (pi.x - xj) + shift;
-    g.dy = pi.y - yj;
+    g.dx = pi.x - pj.x;
+    if (m != 0) g.dx += (double)m * P.DL;   // minimum image (nb:359-363); only seam tiles ever shift
+    g.dy = pi.y - pj.y;
     const double r2 = g.dx * g.dx + g.dy * g.dy;
     const double inv_r = fast_rsqrt(r2);
     g.r = r2 * inv_r;
@@ -63,61 +63,96 @@ __device__ __forceinline__ double spline_dW(double r, const PhysParams &P)
 }
 
 // ---- the tile frame shared by every gather kernel --------------------------------------------------
-// TILE_BEGIN: descriptor + early exit.  TILE_WALKERS: one thread per REAL entry of the tile's own
-// cells (ew = entry, i = particle); ghost entries are skipped.  tile_for_row: the walker's ELL row; for
-// each neighbour `ea` = its entry, `sl` = its shared-memory slot (or -1: load from global), `m` = shift.
-#define SPHB_TILE_BEGIN()                                                                         \
-    __shared__ TileDesc T;                                                                        \
-    tile_setup(T, blockIdx.x, S.ncx, S.grid->ncy, S.cell_start, kPhysCap);                        \
-    if (!T.valid || T.own_b == T.own_e) return
+// SPHB_TILE_BEGIN: descriptor into shared memory + early exit.  SPHB_TILE_WALKERS: one thread per REAL
+// entry of the tile's own cells (ew = entry, si = its slot, i = particle); ghost entries are skipped.
+#define SPHB_TILE_BEGIN()                                                  \
+    extern __shared__ __align__(16) unsigned char smem_raw[];              \
+    __shared__ TileDesc T;                                                 \
+    tile_load(T, S.tiles, blockIdx.x);                                     \
+    __syncthreads();                                                       \
+    if (!(T.flags & kTileValid)) return;                                   \
+    const int cap = S.tile_cap;                                            \
+    (void)cap
 
-#define SPHB_TILE_WALKERS(ew, i)                                                                  \
-    for (int ew = T.own_b + (int)threadIdx.x; ew < T.own_e; ew += kTileThreads)                    \
-        if (const int key__ = S.ent_key[ew]; (key__ & 3) == 0)                                    \
-            if (const int i = key__ >> 3; true)
-
-// The walker's ELL row.  The column indices are fetched eight at a time (independent coalesced loads,
-// next chunk in flight while the current one is processed) so a row costs ~3 global latencies, not 20.
-template <class Body>
-__device__ __forceinline__ void tile_for_row(const StateView &S, const TileDesc &T, int ew, Body &&body)
+// What a thread needs of its (first) walker from global memory, fetched BEFORE the staging loads so that
+// both latencies overlap: entry key, row length, first row word.
+struct OwnPre {
+    int key, n;
+    uint4 q0;
+};
+__device__ __forceinline__ OwnPre tile_prefetch_own(const StateView &S, const TileDesc &T)
 {
-    constexpr int U = 8;
-    const int n = (size_t)ew < S.ell_stride ? min(S.ell_cnt[ew], S.ell_cap) : 0;
-    const unsigned *col = S.ell_col + ew;
-    unsigned cur[U], nxt[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) cur[u] = u < n ? col[(size_t)u * S.ell_stride] : 0u;
-    for (int k0 = 0; k0 < n; k0 += U) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) nxt[u] = (k0 + U + u) < n ? col[(size_t)(k0 + U + u) * S.ell_stride] : 0u;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (k0 + u < n) {
-                const unsigned c = cur[u];
-                const int ea = ell_entry(c);
-                body(ea, tile_lookup(T, ea, ell_row(c)), ell_shift(c));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+    OwnPre p;
+    p.key = 3;   // "not a real entry"
+    p.n = 0;
+    p.q0 = make_uint4(0u, 0u, 0u, 0u);
+    if ((int)threadIdx.x < tile_own_total(T)) {
+        int orow, ew, si;
+        tile_own_locate(T, (int)threadIdx.x, orow, ew, si);
+        p.key = S.ent_key[ew];
+        p.n = S.ell_cnt[ew];
+        p.q0 = S.ell_q[ew];
     }
+    return p;
 }
 
-// ---------------------------------------------------------------- P1 pass 1: sigma sums -> rho, Vol
-__global__ void __launch_bounds__(kTileThreads) k_density(PhysParams P, StateView S)
+#define SPHB_TILE_WALKERS(ew, si, i)                                                              \
+    SPHB_TILE_FOR_OWN(T, ew, si, orow__)                                                          \
+        if (const bool first__ = v__ == (int)threadIdx.x; true)                                   \
+            if (const int key__ = first__ ? pre.key : S.ent_key[ew]; (key__ & 3) == 0)            \
+                if (const int i = key__ >> 3; true)
+
+// The walker's row: 128-bit words of eight 16-bit entries (padded with the dummy slot), the next word
+// in flight while the current one is processed, four entries per unrolled group.  body(slot, image
+// shift); SHIFT = false skips the decode of the image shift (tiles away from the periodic seam never
+// shift).
+template <bool SHIFT, class Body>
+__device__ __forceinline__ void tile_for_row_impl(const StateView &S, int ew, int n, uint4 cur, Body &&body)
 {
-    __shared__ double s_x[kPhysCap], s_y[kPhysCap];
-    __shared__ int s_id[kPhysCap];
-    SPHB_TILE_BEGIN();
-    SPHB_TILE_FOR_STAGED(T, e, slot)
-    {
-        const double2 p = S.ent_pos[e];
-        s_x[slot] = p.x;
-        s_y[slot] = p.y;
-        s_id[slot] = S.ent_key[e] >> 3;
+    n = min(n, S.ell_cap);
+    const int nw = (n + 7) >> 3;
+    const uint4 *q = S.ell_q + ew;
+#pragma unroll 1
+    for (int w = 0; w < nw; ++w) {
+        const uint4 nxt = (w + 1 < nw) ? q[(size_t)(w + 1) * S.ell_stride] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned c = ell_extract(cur, u);
+            body(ell_slot(c), SHIFT ? ell_shift(c) : 0);
+        }
+        if (w * 8 + 4 < n) {
+#pragma unroll
+            for (int u = 4; u < 8; ++u) {
+                const unsigned c = ell_extract(cur, u);
+                body(ell_slot(c), SHIFT ? ell_shift(c) : 0);
+            }
+        }
+        cur = nxt;
     }
-    __syncthreads();
-    SPHB_TILE_WALKERS(ew, i)
+}
+// rows of the walker loop: the first pass uses the prefetched length and word
+#define SPHB_ROW(SHIFT, body_lambda)                                                               \
+    tile_for_row_impl<SHIFT>(S, ew, first__ ? pre.n : S.ell_cnt[ew], first__ ? pre.q0 : S.ell_q[ew], body_lambda)
+
+// A tile is PLAIN when its neighbourhood holds no wall entry and it is away from the periodic seam:
+// every neighbour is a fluid particle at its stored position, so the row loops are branch-free.
+#define SPHB_TILE_DISPATCH(walls_flag, call)                                          \
+    do {                                                                              \
+        const bool plain__ = !__syncthreads_or(walls_flag) && !(T.flags & kTileSeam); \
+        if (plain__) {                                                                \
+            call(true);                                                               \
+        } else {                                                                      \
+            call(false);                                                              \
+        }                                                                             \
+    } while (0)
+
+// ---------------------------------------------------------------- P1 pass 1: sigma sums -> rho, Vol
+// staged per slot: position, and for a wall entry m_j / rho0 (ph:205), for a fluid entry -1
+template <bool PLAIN>
+__device__ __forceinline__ void density_rows(const PhysParams &P, const StateView &S, const TileDesc &T, const OwnPre &pre,
+                                             const double2 *s_xy, const double *s_w)
+{
+    SPHB_TILE_WALKERS(ew, si, i)
     {
         const double m_i = S.mass[i];
         if (i >= P.nf) {   // wall rows: rho = rho0 (ph:214-216), Vol = m/rho0
@@ -125,27 +160,20 @@ __global__ void __launch_bounds__(kTileThreads) k_density(PhysParams P, StateVie
             S.Vol[i] = m_i / P.rho0;
             continue;
         }
-        const double2 pi = S.ent_pos[ew];
+        const double2 pi = s_xy[si];
         double s_in = P.sigma;   // W(0), ph:178-181
         double s_ct = 0.0;
-        tile_for_row(S, T, ew, [&](const int ea, const int sl, const int m) {
-            double xj, yj;
-            int j;
-            if (sl >= 0) {
-                xj = s_x[sl];
-                yj = s_y[sl];
-                j = s_id[sl];
-            } else {
-                const double2 p = S.ent_pos[ea];
-                xj = p.x;
-                yj = p.y;
-                j = S.ent_key[ea] >> 3;
-            }
-            const Geo g = pair_geometry(pi, xj, yj, m, P);
+        SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
+            const Geo g = pair_geometry(pi, s_xy[sl], m, P);
             const double W = spline_W(g.r, P);
-            if (j < P.nf) s_in += W;
-            else s_ct += W * (S.mass[j] * P.inv_rho0);
-        });
+            if (PLAIN) {
+                s_in += W;
+            } else {
+                const double wj = s_w[sl];
+                if (wj < 0.0) s_in += W;
+                else s_ct += W * wj;
+            }
+        }));
         double rho = s_in * P.rho0 * P.inv_sigma0;
         rho += s_ct * P.rho0 * P.rho0 * P.inv_sigma0 / m_i;
         if (rho <= 1e-12) rho = P.rho0;
@@ -154,20 +182,39 @@ __global__ void __launch_bounds__(kTileThreads) k_density(PhysParams P, StateVie
     }
 }
 
-// ---------------------------------------------------------------- P1 pass 2: A -> B (ph:239-366)
-__global__ void __launch_bounds__(kTileThreads) k_kgc(PhysParams P, StateView S)
+__global__ void __launch_bounds__(kTileThreads) k_density(PhysParams P, StateView S)
 {
-    __shared__ double s_x[kPhysCap], s_y[kPhysCap], s_V[kPhysCap];
     SPHB_TILE_BEGIN();
+    const OwnPre pre = tile_prefetch_own(S, T);
+    double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
+    double *s_w = reinterpret_cast<double *>(s_xy + cap);
+    int walls = 0;
     SPHB_TILE_FOR_STAGED(T, e, slot)
     {
-        const double2 p = S.ent_pos[e];
-        s_x[slot] = p.x;
-        s_y[slot] = p.y;
-        s_V[slot] = S.Vol[S.ent_key[e] >> 3];
+        const int j = S.ent_key[e] >> 3;
+        s_xy[slot] = S.ent_pos[e];
+        if (j < P.nf) {
+            s_w[slot] = -1.0;
+        } else {
+            s_w[slot] = S.mass[j] * P.inv_rho0;
+            walls = 1;
+        }
     }
-    __syncthreads();
-    SPHB_TILE_WALKERS(ew, i)
+    if (threadIdx.x == 0) {
+        s_xy[T.n_staged] = make_double2(kDummyCoord, kDummyCoord);
+        s_w[T.n_staged] = -1.0;
+    }
+#define SPHB_CALL(plain) density_rows<plain>(P, S, T, pre, s_xy, s_w)
+    SPHB_TILE_DISPATCH(walls, SPHB_CALL);
+#undef SPHB_CALL
+}
+
+// ---------------------------------------------------------------- P1 pass 2: A -> B (ph:239-366)
+template <bool PLAIN>
+__device__ __forceinline__ void kgc_rows(const PhysParams &P, const StateView &S, const TileDesc &T, const OwnPre &pre,
+                                         const double2 *s_xy, const double *s_V)
+{
+    SPHB_TILE_WALKERS(ew, si, i)
     {
         Mat2 B;
         B.b11 = 1.0;
@@ -175,129 +222,94 @@ __global__ void __launch_bounds__(kTileThreads) k_kgc(PhysParams P, StateView S)
         B.b21 = 0.0;
         B.b22 = 1.0;
         if (i < P.nf) {
-            const double2 pi = S.ent_pos[ew];
+            const double2 pi = s_xy[si];
             double a11 = 0.0, a12 = 0.0, a21 = 0.0, a22 = 0.0;
-            tile_for_row(S, T, ew, [&](const int ea, const int sl, const int m) {
-                double xj, yj, Vj;
-                if (sl >= 0) {
-                    xj = s_x[sl];
-                    yj = s_y[sl];
-                    Vj = s_V[sl];
-                } else {
-                    const double2 p = S.ent_pos[ea];
-                    xj = p.x;
-                    yj = p.y;
-                    Vj = S.Vol[S.ent_key[ea] >> 3];
-                }
-                const Geo g = pair_geometry(pi, xj, yj, m, P);
-                if (!(g.r > 1e-12)) return;
-                const double f = spline_dW(g.r, P) * Vj;
+            SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
+                const Geo g = pair_geometry(pi, s_xy[sl], m, P);
+                const double f = spline_dW(g.r, P) * s_V[sl];
                 const double fx = f * g.ex, fy = f * g.ey;
                 a11 -= g.dx * fx;
                 a12 -= g.dx * fy;
                 a21 -= g.dy * fx;
                 a22 -= g.dy * fy;
-            });
+            }));
             kgc_from_A(a11, a12, a21, a22, B.b11, B.b12, B.b21, B.b22);
         }
         S.B[i] = B;
     }
 }
 
-// ---------------------------------------------------------------- P2 + P3 fused (ph:469-545, 636-710)
-template <bool VISC, bool TRANSP>
-__global__ void __launch_bounds__(kTileThreads) k_visc_transport(PhysParams P, StateView S, int add_gravity)
+__global__ void __launch_bounds__(kTileThreads) k_kgc(PhysParams P, StateView S)
 {
-    __shared__ double s_x[kPhysCap], s_y[kPhysCap], s_V[kPhysCap], s_vx[kPhysCap], s_vy[kPhysCap];
-    __shared__ double s_b11[kPhysCap], s_b12[kPhysCap], s_b21[kPhysCap], s_b22[kPhysCap];
-    __shared__ int s_id[kPhysCap];
     SPHB_TILE_BEGIN();
+    const OwnPre pre = tile_prefetch_own(S, T);
+    double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
+    double *s_V = reinterpret_cast<double *>(s_xy + cap);
     SPHB_TILE_FOR_STAGED(T, e, slot)
     {
-        const int j = S.ent_key[e] >> 3;
-        const double2 p = S.ent_pos[e];
-        s_x[slot] = p.x;
-        s_y[slot] = p.y;
-        s_id[slot] = j;
-        s_V[slot] = S.Vol[j];
-        const double2 v = j < P.nf ? S.vel[j] : S.wall_vel[j];   // a wall neighbour contributes its wall velocity
-        s_vx[slot] = v.x;
-        s_vy[slot] = v.y;
-        const Mat2 B = S.B[j];
-        s_b11[slot] = B.b11;
-        s_b12[slot] = B.b12;
-        s_b21[slot] = B.b21;
-        s_b22[slot] = B.b22;
+        s_xy[slot] = S.ent_pos[e];
+        s_V[slot] = S.Vol[S.ent_key[e] >> 3];
     }
-    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_xy[T.n_staged] = make_double2(kDummyCoord, kDummyCoord);
+        s_V[T.n_staged] = 0.0;
+    }
+    // walls take the same formula here (ph:293-309): only the seam needs the image shift
+#define SPHB_CALL(plain) kgc_rows<plain>(P, S, T, pre, s_xy, s_V)
+    SPHB_TILE_DISPATCH(0, SPHB_CALL);
+#undef SPHB_CALL
+}
+
+// ---------------------------------------------------------------- P2 + P3 fused (ph:469-545, 636-710)
+// staged per slot: position, velocity (a wall entry: its wall velocity), B, and the volume with the
+// sign bit set for wall entries
+template <bool VISC, bool TRANSP, bool PLAIN>
+__device__ __forceinline__ void visc_transport_rows(const PhysParams &P, const StateView &S, const TileDesc &T, const OwnPre &pre,
+                                                    const double2 *s_xy, const double2 *s_v, const double2 *s_b1,
+                                                    const double2 *s_b2, const double *s_V, int add_gravity)
+{
     const double h001 = 0.01 * P.h;
-    SPHB_TILE_WALKERS(ew, i)
+    SPHB_TILE_WALKERS(ew, si, i)
     {
         if (i >= P.nf) {
             if (VISC) S.force_prior[i] = make_double2(0.0, 0.0);
             continue;
         }
-        const double2 pi = S.ent_pos[ew];
-        const double2 vi = S.vel[i];
-        const Mat2 Bi = S.B[i];
-        const double Vi = S.Vol[i];
+        const double2 pi = s_xy[si];
+        const double2 vi = VISC ? s_v[si] : make_double2(0.0, 0.0);
+        const double2 bi1 = s_b1[si], bi2 = s_b2[si];
+        const double Vi = s_V[si];
         double ax = 0.0, ay = 0.0, ix = 0.0, iy = 0.0;
-        tile_for_row(S, T, ew, [&](const int ea, const int sl, const int m) {
-            double xj, yj, Vj, vjx, vjy;
-            Mat2 Bj;
-            int j;
-            if (sl >= 0) {
-                xj = s_x[sl];
-                yj = s_y[sl];
-                Vj = s_V[sl];
-                vjx = s_vx[sl];
-                vjy = s_vy[sl];
-                Bj.b11 = s_b11[sl];
-                Bj.b12 = s_b12[sl];
-                Bj.b21 = s_b21[sl];
-                Bj.b22 = s_b22[sl];
-                j = s_id[sl];
-            } else {
-                j = S.ent_key[ea] >> 3;
-                const double2 p = S.ent_pos[ea];
-                xj = p.x;
-                yj = p.y;
-                Vj = S.Vol[j];
-                const double2 v = j < P.nf ? S.vel[j] : S.wall_vel[j];
-                vjx = v.x;
-                vjy = v.y;
-                Bj = S.B[j];
-            }
-            const Geo g = pair_geometry(pi, xj, yj, m, P);
-            if (!(g.r > 1e-12)) return;
+        SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
+            const Geo g = pair_geometry(pi, s_xy[sl], m, P);
             const double ex = g.ex, ey = g.ey;
-            const double gj = spline_dW(g.r, P) * Vj;
-            double tx, ty, wv, wt;
-            if (j < P.nf) {
-                const double s11 = Bi.b11 + Bj.b11, s12 = Bi.b12 + Bj.b12;
-                const double s21 = Bi.b21 + Bj.b21, s22 = Bi.b22 + Bj.b22;
-                tx = s11 * ex + s12 * ey;
-                ty = s21 * ex + s22 * ey;
-                wv = 1.0;
-                wt = 1.0;
+            const double Vs = s_V[sl];
+            const double gj = spline_dW(g.r, P) * (PLAIN ? Vs : fabs(Vs));
+            double tx, ty, wv = 1.0, wt = 1.0;
+            if (PLAIN || Vs >= 0.0) {
+                const double2 bj1 = s_b1[sl], bj2 = s_b2[sl];
+                tx = (bi1.x + bj1.x) * ex + (bi1.y + bj1.y) * ey;
+                ty = (bi2.x + bj2.x) * ex + (bi2.y + bj2.y) * ey;
             } else {
-                tx = Bi.b11 * ex + Bi.b12 * ey;
-                ty = Bi.b21 * ex + Bi.b22 * ey;
+                tx = bi1.x * ex + bi1.y * ey;
+                ty = bi2.x * ex + bi2.y * ey;
                 wv = 4.0;   // no-slip mirror, ph:526
                 wt = 2.0;   // ph:690
             }
             if (VISC) {
+                const double2 vj = s_v[sl];
                 const double eBe = ex * tx + ey * ty;
-                const double cf = wv * eBe * P.mu * gj * fast_rcp(g.r + h001);
-                ax += cf * (vi.x - vjx);
-                ay += cf * (vi.y - vjy);
+                double cf = eBe * P.mu * gj * fast_rcp(g.r + h001);
+                if (!PLAIN) cf *= wv;
+                ax += cf * (vi.x - vj.x);
+                ay += cf * (vi.y - vj.y);
             }
             if (TRANSP) {
-                const double ci = -wt * gj;
+                const double ci = PLAIN ? -gj : -wt * gj;
                 ix += ci * tx;
                 iy += ci * ty;
             }
-        });
+        }));
         if (VISC) {
             double fx = ax * Vi, fy = ay * Vi;
             if (add_gravity) fx += S.mass[i] * P.g;   // m:392
@@ -315,6 +327,48 @@ __global__ void __launch_bounds__(kTileThreads) k_visc_transport(PhysParams P, S
             S.pos[i] = x;
         }
     }
+}
+
+template <bool VISC, bool TRANSP>
+__global__ void __launch_bounds__(kTileThreads) k_visc_transport(PhysParams P, StateView S, int add_gravity)
+{
+    SPHB_TILE_BEGIN();
+    const OwnPre pre = tile_prefetch_own(S, T);
+    double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
+    double2 *s_v = s_xy + cap;
+    double2 *s_b1 = s_v + cap;
+    double2 *s_b2 = s_b1 + cap;
+    double *s_V = reinterpret_cast<double *>(s_b2 + cap);
+    int walls = 0;
+    SPHB_TILE_FOR_STAGED(T, e, slot)
+    {
+        const int j = S.ent_key[e] >> 3;
+        s_xy[slot] = S.ent_pos[e];
+        const double V = S.Vol[j];
+        if (j < P.nf) {
+            s_V[slot] = V;
+            if (VISC) s_v[slot] = S.vel[j];
+            const double4 B = *reinterpret_cast<const double4 *>(&S.B[j]);
+            s_b1[slot] = make_double2(B.x, B.y);
+            s_b2[slot] = make_double2(B.z, B.w);
+        } else {   // a wall neighbour contributes its wall velocity and no B (ph:522-533, 687-697)
+            s_V[slot] = -V;
+            if (VISC) s_v[slot] = S.wall_vel[j];
+            walls = 1;
+        }
+    }
+    if (threadIdx.x == 0) {
+        const int d = T.n_staged;
+        s_xy[d] = make_double2(kDummyCoord, kDummyCoord);
+        s_v[d] = make_double2(0.0, 0.0);
+        s_b1[d] = make_double2(0.0, 0.0);
+        s_b2[d] = make_double2(0.0, 0.0);
+        s_V[d] = 0.0;
+    }
+#define SPHB_CALL(plain) \
+    visc_transport_rows<VISC, TRANSP, plain>(P, S, T, pre, s_xy, s_v, s_b1, s_b2, s_V, add_gravity)
+    SPHB_TILE_DISPATCH(walls, SPHB_CALL);
+#undef SPHB_CALL
 }
 
 __device__ __forceinline__ double half_step_rho(double rho, double drho, double dt, double rho0)
@@ -360,110 +414,55 @@ __global__ void k_advance_clock(DevScalars *sc)
 }
 
 // ---------------------------------------------------------------- P4 + velocity kick + position update
-__global__ void __launch_bounds__(kTileThreads) k_pressure(PhysParams P, StateView S, const DevScalars *__restrict__ sc)
+// staged per slot: position, volume (sign bit = wall); for fluid entries also velocity, half-step
+// (rho, p) and B -- wall neighbours need only position and volume (ph:927-947)
+template <bool PLAIN>
+__device__ __forceinline__ void pressure_rows(const PhysParams &P, const StateView &S, const TileDesc &T, const OwnPre &pre,
+                                              const double2 *s_xy, const double2 *s_v, const double2 *s_rp,
+                                              const double2 *s_b1, const double2 *s_b2, const double *s_V, double dt)
 {
-    __shared__ double s_x[kPhysCap], s_y[kPhysCap], s_V[kPhysCap], s_vx[kPhysCap], s_vy[kPhysCap];
-    __shared__ double s_rho[kPhysCap], s_p[kPhysCap];
-    __shared__ double s_b11[kPhysCap], s_b12[kPhysCap], s_b21[kPhysCap], s_b22[kPhysCap];
-    __shared__ int s_id[kPhysCap];
-    SPHB_TILE_BEGIN();
-    SPHB_TILE_FOR_STAGED(T, e, slot)
-    {
-        const int j = S.ent_key[e] >> 3;
-        const double2 p = S.ent_pos[e];
-        s_x[slot] = p.x;
-        s_y[slot] = p.y;
-        s_id[slot] = j;
-        s_V[slot] = S.Vol[j];
-        if (j < P.nf) {   // wall neighbours need only position and volume (ph:927-947)
-            const double2 v = S.vel[j];
-            s_vx[slot] = v.x;
-            s_vy[slot] = v.y;
-            const double2 rp = S.rp_half[j];
-            s_rho[slot] = rp.x;
-            s_p[slot] = rp.y;
-            const Mat2 B = S.B[j];
-            s_b11[slot] = B.b11;
-            s_b12[slot] = B.b12;
-            s_b21[slot] = B.b21;
-            s_b22[slot] = B.b22;
-        }
-    }
-    __syncthreads();
-    const double dt = sc->dt;
-    SPHB_TILE_WALKERS(ew, i)
+    SPHB_TILE_WALKERS(ew, si, i)
     {
         if (i >= P.nf) {   // wall rows: force 0, velocity 0 (ph:958-962, 1405-1408)
             S.force[i] = make_double2(0.0, 0.0);
             S.vel_new[i] = make_double2(0.0, 0.0);
             continue;
         }
-        const double2 pi = S.ent_pos[ew];
-        const double2 vi = S.vel[i];
-        const Mat2 Bi = S.B[i];
-        const double Vi = S.Vol[i], m_i = S.mass[i];
+        const double2 pi = s_xy[si];
+        const double2 vi = s_v[si];
+        const double2 bi1 = s_b1[si], bi2 = s_b2[si];
+        const double Vi = s_V[si], m_i = S.mass[i];
         const double2 fp = S.force_prior[i];
-        const double2 rpi = S.rp_half[i];
+        const double2 rpi = s_rp[si];
         const double rho_i = rpi.x, p_i = rpi.y;
         const double inv_m = 1.0 / m_i;
         const double wax = fp.x * inv_m, way = fp.y * inv_m;   // a = F_prior / m, ph:929-930
         double fx = 0.0, fy = 0.0;
-        tile_for_row(S, T, ew, [&](const int ea, const int sl, const int m) {
-            double xj, yj, Vj;
-            int j;
-            if (sl >= 0) {
-                xj = s_x[sl];
-                yj = s_y[sl];
-                Vj = s_V[sl];
-                j = s_id[sl];
-            } else {
-                j = S.ent_key[ea] >> 3;
-                const double2 p = S.ent_pos[ea];
-                xj = p.x;
-                yj = p.y;
-                Vj = S.Vol[j];
-            }
-            const Geo g = pair_geometry(pi, xj, yj, m, P);
-            if (!(g.r > 1e-12)) return;
+        SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
+            const Geo g = pair_geometry(pi, s_xy[sl], m, P);
             const double ex = g.ex, ey = g.ey;
-            const double gj = spline_dW(g.r, P) * Vj;
-            if (j < P.nf) {
-                double vjx, vjy, rho_j, p_j;
-                Mat2 Bj;
-                if (sl >= 0) {
-                    vjx = s_vx[sl];
-                    vjy = s_vy[sl];
-                    rho_j = s_rho[sl];
-                    p_j = s_p[sl];
-                    Bj.b11 = s_b11[sl];
-                    Bj.b12 = s_b12[sl];
-                    Bj.b21 = s_b21[sl];
-                    Bj.b22 = s_b22[sl];
-                } else {
-                    const double2 v = S.vel[j];
-                    vjx = v.x;
-                    vjy = v.y;
-                    const double2 rp = S.rp_half[j];
-                    rho_j = rp.x;
-                    p_j = rp.y;
-                    Bj = S.B[j];
-                }
-                const double rho_bar = 0.5 * (rho_i + rho_j);
-                const double du = (vi.x - vjx) * ex + (vi.y - vjy) * ey;     // u_l - u_r
-                const double beta = fmin(3.0 * fmax(du, 0.0), P.c_f);        // ph:1121-1129
-                const double p_avg = 0.5 * (p_i + p_j);
+            const double Vs = s_V[sl];
+            const double gj = spline_dW(g.r, P) * (PLAIN ? Vs : fabs(Vs));
+            if (PLAIN || Vs >= 0.0) {
+                const double2 vj = s_v[sl];
+                const double2 rpj = s_rp[sl];
+                const double2 bj1 = s_b1[sl], bj2 = s_b2[sl];
+                const double rho_bar = 0.5 * (rho_i + rpj.x);
+                const double du = (vi.x - vj.x) * ex + (vi.y - vj.y) * ey;     // u_l - u_r
+                const double beta = fmin(3.0 * fmax(du, 0.0), P.c_f);          // ph:1121-1129
+                const double p_avg = 0.5 * (p_i + rpj.y);
                 const double p_star = p_avg + 0.5 * beta * rho_bar * du;
                 const double pg = 0.5 * (p_avg + p_star) * gj;
-                fx -= pg * ((Bi.b11 + Bj.b11) * ex + (Bi.b12 + Bj.b12) * ey);
-                fy -= pg * ((Bi.b21 + Bj.b21) * ex + (Bi.b22 + Bj.b22) * ey);
+                fx -= pg * ((bi1.x + bj1.x) * ex + (bi1.y + bj1.y) * ey);
+                fy -= pg * ((bi2.x + bj2.x) * ex + (bi2.y + bj2.y) * ey);
             } else {
                 const double ext = -(wax * ex + way * ey);
                 const double pw = p_i + rho_i * g.r * fmax(0.0, ext);   // virtual wall pressure, ph:934
                 const double pg = (p_i + pw) * gj;
-                fx -= pg * (Bi.b11 * ex + Bi.b12 * ey);
-                fy -= pg * (Bi.b21 * ex + Bi.b22 * ey);
+                fx -= pg * (bi1.x * ex + bi1.y * ey);
+                fy -= pg * (bi2.x * ex + bi2.y * ey);
             }
-        });
+        }));
         fx *= Vi;
         fy *= Vi;
         S.force[i] = make_double2(fx, fy);
@@ -480,6 +479,49 @@ __global__ void __launch_bounds__(kTileThreads) k_pressure(PhysParams P, StateVi
     }
 }
 
+__global__ void __launch_bounds__(kTileThreads) k_pressure(PhysParams P, StateView S, const DevScalars *__restrict__ sc)
+{
+    SPHB_TILE_BEGIN();
+    const OwnPre pre = tile_prefetch_own(S, T);
+    double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
+    double2 *s_v = s_xy + cap;
+    double2 *s_rp = s_v + cap;
+    double2 *s_b1 = s_rp + cap;
+    double2 *s_b2 = s_b1 + cap;
+    double *s_V = reinterpret_cast<double *>(s_b2 + cap);
+    int walls = 0;
+    SPHB_TILE_FOR_STAGED(T, e, slot)
+    {
+        const int j = S.ent_key[e] >> 3;
+        s_xy[slot] = S.ent_pos[e];
+        const double V = S.Vol[j];
+        if (j < P.nf) {
+            s_V[slot] = V;
+            s_v[slot] = S.vel[j];
+            s_rp[slot] = S.rp_half[j];
+            const double4 B = *reinterpret_cast<const double4 *>(&S.B[j]);
+            s_b1[slot] = make_double2(B.x, B.y);
+            s_b2[slot] = make_double2(B.z, B.w);
+        } else {
+            s_V[slot] = -V;
+            walls = 1;
+        }
+    }
+    if (threadIdx.x == 0) {
+        const int d = T.n_staged;
+        s_xy[d] = make_double2(kDummyCoord, kDummyCoord);
+        s_v[d] = make_double2(0.0, 0.0);
+        s_rp[d] = make_double2(0.0, 0.0);
+        s_b1[d] = make_double2(0.0, 0.0);
+        s_b2[d] = make_double2(0.0, 0.0);
+        s_V[d] = 0.0;
+    }
+    const double dt = sc->dt;
+#define SPHB_CALL(plain) pressure_rows<plain>(P, S, T, pre, s_xy, s_v, s_rp, s_b1, s_b2, s_V, dt)
+    SPHB_TILE_DISPATCH(walls, SPHB_CALL);
+#undef SPHB_CALL
+}
+
 __device__ __forceinline__ double wrap_x(double x, double DL)   // MATLAB mod(x, DL), m:573
 {
     if (x >= 0.0 && x < DL) return x;
@@ -489,27 +531,14 @@ __device__ __forceinline__ double wrap_x(double x, double DL)   // MATLAB mod(x,
 }
 
 // ---------------------------------------------------------------- P5 + density/EOS finish + wrap + max|v|
-__global__ void __launch_bounds__(kTileThreads) k_continuity(PhysParams P, StateView S, DevScalars *sc, int do_wrap)
+// staged per slot: position, new velocity (a wall entry: its wall velocity), volume (sign bit = wall)
+template <bool PLAIN>
+__device__ __forceinline__ double continuity_rows(const PhysParams &P, const StateView &S, const TileDesc &T, const OwnPre &pre,
+                                                  const double2 *s_xy, const double2 *s_v, const double *s_V,
+                                                  double dt, int do_wrap)
 {
-    __shared__ double s_x[kPhysCap], s_y[kPhysCap], s_V[kPhysCap], s_vx[kPhysCap], s_vy[kPhysCap];
-    __shared__ int s_id[kPhysCap];
-    SPHB_TILE_BEGIN();
-    SPHB_TILE_FOR_STAGED(T, e, slot)
-    {
-        const int j = S.ent_key[e] >> 3;
-        const double2 p = S.ent_pos[e];
-        s_x[slot] = p.x;
-        s_y[slot] = p.y;
-        s_id[slot] = j;
-        s_V[slot] = S.Vol[j];
-        const double2 v = j < P.nf ? S.vel_new[j] : S.wall_vel[j];
-        s_vx[slot] = v.x;
-        s_vy[slot] = v.y;
-    }
-    __syncthreads();
-    const double dt = sc->dt;
     double speed = 0.0;
-    SPHB_TILE_WALKERS(ew, i)
+    SPHB_TILE_WALKERS(ew, si, i)
     {
         if (i >= P.nf) {
             S.drho_dt[i] = 0.0;   // ph:1114-1116
@@ -517,42 +546,24 @@ __global__ void __launch_bounds__(kTileThreads) k_continuity(PhysParams P, State
             S.vel[i] = make_double2(0.0, 0.0);   // ph:1405-1408, m:270
             continue;
         }
-        const double2 pi = S.ent_pos[ew];
-        const double2 vi = S.vel_new[i];
+        const double2 pi = s_xy[si];
+        const double2 vi = s_v[si];
         double rate = 0.0;
-        tile_for_row(S, T, ew, [&](const int ea, const int sl, const int m) {
-            double xj, yj, Vj, vjx, vjy;
-            int j;
-            if (sl >= 0) {
-                xj = s_x[sl];
-                yj = s_y[sl];
-                Vj = s_V[sl];
-                vjx = s_vx[sl];
-                vjy = s_vy[sl];
-                j = s_id[sl];
-            } else {
-                j = S.ent_key[ea] >> 3;
-                const double2 p = S.ent_pos[ea];
-                xj = p.x;
-                yj = p.y;
-                Vj = S.Vol[j];
-                const double2 v = j < P.nf ? S.vel_new[j] : S.wall_vel[j];
-                vjx = v.x;
-                vjy = v.y;
-            }
-            const Geo g = pair_geometry(pi, xj, yj, m, P);
-            if (!(g.r > 1e-12)) return;
-            const double gj = spline_dW(g.r, P) * Vj;
+        SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
+            const Geo g = pair_geometry(pi, s_xy[sl], m, P);
+            const double Vs = s_V[sl];
+            const double gj = spline_dW(g.r, P) * (PLAIN ? Vs : fabs(Vs));
+            const double2 vj = s_v[sl];
             double ux, uy;
-            if (j < P.nf) {
-                ux = vi.x - vjx;
-                uy = vi.y - vjy;
+            if (PLAIN || Vs >= 0.0) {
+                ux = vi.x - vj.x;
+                uy = vi.y - vj.y;
             } else {
-                ux = vi.x - (2.0 * vjx - vi.x);   // mirrored velocity, ph:1101-1102
-                uy = vi.y - (2.0 * vjy - vi.y);
+                ux = vi.x - (2.0 * vj.x - vi.x);   // mirrored velocity, ph:1101-1102
+                uy = vi.y - (2.0 * vj.y - vi.y);
             }
             rate += (ux * g.ex + uy * g.ey) * gj;
-        });
+        }));
         const double rho_h = S.rp_half[i].x;
         const double drho = rate * rho_h;          // ph:1112
         double rho = rho_h + drho * (0.5 * dt);    // ph:1441
@@ -568,6 +579,42 @@ __global__ void __launch_bounds__(kTileThreads) k_continuity(PhysParams P, State
         S.vel[i] = vi;   // nobody reads `vel` in this kernel (neighbours read vel_new): commit in place
         speed = fmax(speed, sqrt(vi.x * vi.x + vi.y * vi.y));
     }
+    return speed;
+}
+
+__global__ void __launch_bounds__(kTileThreads) k_continuity(PhysParams P, StateView S, DevScalars *sc, int do_wrap)
+{
+    SPHB_TILE_BEGIN();
+    const OwnPre pre = tile_prefetch_own(S, T);
+    double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
+    double2 *s_v = s_xy + cap;
+    double *s_V = reinterpret_cast<double *>(s_v + cap);
+    int walls = 0;
+    SPHB_TILE_FOR_STAGED(T, e, slot)
+    {
+        const int j = S.ent_key[e] >> 3;
+        s_xy[slot] = S.ent_pos[e];
+        const double V = S.Vol[j];
+        if (j < P.nf) {
+            s_V[slot] = V;
+            s_v[slot] = S.vel_new[j];
+        } else {
+            s_V[slot] = -V;
+            s_v[slot] = S.wall_vel[j];
+            walls = 1;
+        }
+    }
+    if (threadIdx.x == 0) {
+        const int d = T.n_staged;
+        s_xy[d] = make_double2(kDummyCoord, kDummyCoord);
+        s_v[d] = make_double2(0.0, 0.0);
+        s_V[d] = 0.0;
+    }
+    const double dt = sc->dt;
+    double speed = 0.0;
+#define SPHB_CALL(plain) speed = continuity_rows<plain>(P, S, T, pre, s_xy, s_v, s_V, dt, do_wrap)
+    SPHB_TILE_DISPATCH(walls, SPHB_CALL);
+#undef SPHB_CALL
     // grid-wide max |v| over fluid rows: warp shuffle, then one atomicMax per warp
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) speed = fmax(speed, __shfl_xor_sync(0xffffffffu, speed, d));
@@ -600,41 +647,66 @@ __global__ void __launch_bounds__(kBlock) k_wrap(int nf, double DL, double2 *pos
 }
 
 // ---------------------------------------------------------------- P8 wall shear (ph:1713-1742)
-// Only wall particles at y <= 0 or y >= DH count (ph:1731-1736) and the pair distance is < 2h, so a
-// fluid particle with 2h <= y <= DH - 2h cannot contribute: those rows are skipped unread.
-__global__ void __launch_bounds__(256) k_wall_shear(PhysParams P, StateView S, double *partials)
+// Only wall particles at y <= 0 or y >= DH count (ph:1731-1736) and the pair distance is < 2h, so only
+// tiles whose neighbourhood holds wall entries do any work: the others exit after the staging vote.
+// One partial (bottom, top) per tile, summed in tile order by k_wall_shear_final: deterministic.
+__global__ void __launch_bounds__(kTileThreads) k_wall_shear(PhysParams P, StateView S, double *partials)
 {
+    __shared__ double shb[kTileThreads], sht[kTileThreads];
+    const unsigned nt = gridDim.x;
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = 0.0;
+        partials[nt + blockIdx.x] = 0.0;
+    }
+    SPHB_TILE_BEGIN();
+    const OwnPre pre = tile_prefetch_own(S, T);
+    double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
+    double *s_V = reinterpret_cast<double *>(s_xy + cap);
+    double *s_wvx = s_V + cap;
+    int walls = 0;
+    SPHB_TILE_FOR_STAGED(T, e, slot)
+    {
+        const int j = S.ent_key[e] >> 3;
+        s_xy[slot] = S.ent_pos[e];
+        if (j >= P.nf) {
+            s_V[slot] = -S.Vol[j];
+            s_wvx[slot] = S.wall_vel[j].x;
+            walls = 1;
+        } else {
+            s_V[slot] = 1.0;
+        }
+    }
+    if (threadIdx.x == 0) {
+        s_xy[T.n_staged] = make_double2(kDummyCoord, kDummyCoord);
+        s_V[T.n_staged] = 1.0;   // skipped like a fluid neighbour
+    }
+    if (!__syncthreads_or(walls)) return;
     double sb = 0.0, st = 0.0;
-    const double band = 2.0 * P.h;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.nf; i += gridDim.x * blockDim.x) {
-        const double2 pi = S.snap[i];
-        if (pi.y >= band && pi.y <= P.DH - band) continue;
-        const int ew = S.ent_of[i];
+    SPHB_TILE_WALKERS(ew, si, i)
+    {
+        if (i >= P.nf) continue;
+        const double2 pi = s_xy[si];
         const double vx = S.vel[i].x;
         const Mat2 Bi = S.B[i];
         const double Vi = S.Vol[i];
-        const int n = (size_t)ew < S.ell_stride ? min(S.ell_cnt[ew], S.ell_cap) : 0;
-        for (int k = 0; k < n; ++k) {
-            const unsigned c = S.ell_col[(size_t)k * S.ell_stride + ew];
-            const int ea = ell_entry(c);
-            const int j = S.ent_key[ea] >> 3;
-            if (j < P.nf) continue;
-            const double2 pj = S.ent_pos[ea];
-            const Geo g = pair_geometry(pi, pj.x, pj.y, ell_shift(c), P);
-            if (!(g.r > 1e-12)) continue;
+        SPHB_ROW(true, ([&](const int sl, const int m) {
+            const double Vs = s_V[sl];
+            if (Vs > 0.0) return;
+            const double2 pj = s_xy[sl];
+            const Geo g = pair_geometry(pi, pj, m, P);
+            if (!(g.r > 1e-12)) return;
             const double ex = g.ex, ey = g.ey;
             const double eBe = ex * (Bi.b11 * ex + Bi.b12 * ey) + ey * (Bi.b21 * ex + Bi.b22 * ey);
-            const double dvx = vx - S.wall_vel[j].x;
-            const double f = 4.0 * P.mu * eBe * spline_dW(g.r, P) * S.Vol[j] * dvx / (g.r + 0.01 * P.h) * Vi;
+            const double dvx = vx - s_wvx[sl];
+            const double f = 4.0 * P.mu * eBe * spline_dW(g.r, P) * (-Vs) * dvx / (g.r + 0.01 * P.h) * Vi;
             if (pj.y <= 0.0) sb += f;
             else if (pj.y >= P.DH) st += f;
-        }
+        }));
     }
-    __shared__ double shb[256], sht[256];
     shb[threadIdx.x] = sb;
     sht[threadIdx.x] = st;
     __syncthreads();
-    for (int d = 128; d > 0; d >>= 1) {
+    for (int d = kTileThreads / 2; d > 0; d >>= 1) {
         if (threadIdx.x < d) {
             shb[threadIdx.x] += shb[threadIdx.x + d];
             sht[threadIdx.x] += sht[threadIdx.x + d];
@@ -643,7 +715,7 @@ __global__ void __launch_bounds__(256) k_wall_shear(PhysParams P, StateView S, d
     }
     if (threadIdx.x == 0) {
         partials[blockIdx.x] = shb[0];
-        partials[gridDim.x + blockIdx.x] = sht[0];
+        partials[nt + blockIdx.x] = sht[0];
     }
 }
 
@@ -700,15 +772,46 @@ __global__ void __launch_bounds__(kBlock) k_profile(PhysParams P, StateView S, d
 }  // namespace
 
 // ================================================================================================
+// bytes of shared memory per staged slot
+constexpr size_t kDensitySlot = 24, kKgcSlot = 24, kViscSlot = 72, kPressureSlot = 88, kContinuitySlot = 40,
+                 kShearSlot = 32;
+
+int csr_max_tile_slots()
+{
+    return (int)((227 * 1024 - 4096) / kPressureSlot);
+}
+
+// dynamic shared memory above 48 KB must be granted per kernel
+int csr_configure(int tile_cap)
+{
+    static int granted = 0;
+    if (tile_cap <= granted) return 0;
+    const size_t c = (size_t)tile_cap;
+#define SPHB_GRANT(kern, bytes)                                                                              \
+    if ((bytes) > 48 * 1024)                                                                                 \
+    SPHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
+    SPHB_GRANT(k_density, c * kDensitySlot);
+    SPHB_GRANT(k_kgc, c * kKgcSlot);
+    SPHB_GRANT((k_visc_transport<true, true>), c * kViscSlot);
+    SPHB_GRANT((k_visc_transport<true, false>), c * kViscSlot);
+    SPHB_GRANT((k_visc_transport<false, true>), c * kViscSlot);
+    SPHB_GRANT(k_pressure, c * kPressureSlot);
+    SPHB_GRANT(k_continuity, c * kContinuitySlot);
+    SPHB_GRANT(k_wall_shear, c * kShearSlot);
+#undef SPHB_GRANT
+    granted = tile_cap;
+    return 0;
+}
+
 int csr_density(const PhysParams &P, const StateView &S, cudaStream_t st)
 {
-    k_density<<<S.n_tiles, kTileThreads, 0, st>>>(P, S);
+    k_density<<<S.n_tiles, kTileThreads, (size_t)S.tile_cap * kDensitySlot, st>>>(P, S);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
 int csr_kgc(const PhysParams &P, const StateView &S, cudaStream_t st)
 {
-    k_kgc<<<S.n_tiles, kTileThreads, 0, st>>>(P, S);
+    k_kgc<<<S.n_tiles, kTileThreads, (size_t)S.tile_cap * kKgcSlot, st>>>(P, S);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -716,9 +819,10 @@ int csr_visc_transport(const PhysParams &P, const StateView &S, bool do_visc, bo
                        cudaStream_t st)
 {
     const unsigned g = S.n_tiles;
-    if (do_visc && do_transport) k_visc_transport<true, true><<<g, kTileThreads, 0, st>>>(P, S, add_gravity ? 1 : 0);
-    else if (do_visc) k_visc_transport<true, false><<<g, kTileThreads, 0, st>>>(P, S, add_gravity ? 1 : 0);
-    else if (do_transport) k_visc_transport<false, true><<<g, kTileThreads, 0, st>>>(P, S, 0);
+    const size_t sm = (size_t)S.tile_cap * kViscSlot;
+    if (do_visc && do_transport) k_visc_transport<true, true><<<g, kTileThreads, sm, st>>>(P, S, add_gravity ? 1 : 0);
+    else if (do_visc) k_visc_transport<true, false><<<g, kTileThreads, sm, st>>>(P, S, add_gravity ? 1 : 0);
+    else if (do_transport) k_visc_transport<false, true><<<g, kTileThreads, sm, st>>>(P, S, 0);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -731,13 +835,13 @@ int csr_time_step(const PhysParams &P, const StateView &S, DevScalars *sc, doubl
 }
 int csr_pressure(const PhysParams &P, const StateView &S, const DevScalars *sc, cudaStream_t st)
 {
-    k_pressure<<<S.n_tiles, kTileThreads, 0, st>>>(P, S, sc);
+    k_pressure<<<S.n_tiles, kTileThreads, (size_t)S.tile_cap * kPressureSlot, st>>>(P, S, sc);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
 int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool wrap, cudaStream_t st)
 {
-    k_continuity<<<S.n_tiles, kTileThreads, 0, st>>>(P, S, sc, wrap ? 1 : 0);
+    k_continuity<<<S.n_tiles, kTileThreads, (size_t)S.tile_cap * kContinuitySlot, st>>>(P, S, sc, wrap ? 1 : 0);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -766,11 +870,8 @@ int csr_wrap(const PhysParams &P, double2 *pos, cudaStream_t st)
 }
 int csr_wall_shear(const PhysParams &P, const StateView &S, DevScalars *sc, double *partials, cudaStream_t st)
 {
-    int blocks = (P.nf + 255) / 256;
-    if (blocks > kShearPartialBlocks) blocks = kShearPartialBlocks;
-    if (blocks < 1) blocks = 1;
-    k_wall_shear<<<blocks, 256, 0, st>>>(P, S, partials);
-    k_wall_shear_final<<<1, 256, 0, st>>>(partials, blocks, P.DL, sc);
+    k_wall_shear<<<S.n_tiles, kTileThreads, (size_t)S.tile_cap * kShearSlot, st>>>(P, S, partials);
+    k_wall_shear_final<<<1, 256, 0, st>>>(partials, (int)S.n_tiles, P.DL, sc);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }

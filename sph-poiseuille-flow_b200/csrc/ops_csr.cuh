@@ -1,6 +1,7 @@
 // ops_csr.cuh -- device-resident state views and launchers of the CSR gather kernels (ops_csr.cu).
 #pragma once
 #include "common.cuh"
+#include "tile.cuh"
 
 namespace sphb {
 
@@ -35,15 +36,15 @@ struct StateView {
     // neighbour structures (frozen geometry = entry positions at list-build time), see neighbor.cu / tile.cuh
     const double2 *snap;      // wrapped position of particle i at build time
     const GridDesc *grid;     // device-side grid (n_cell_y)
-    const int *cell_start;    // entry range of each cell
     const int *ent_key;       // particle << 3 | multi << 2 | kind, cell-sorted
     const double2 *ent_pos;   // entry position (ghost x already shifted)
     const int *ent_of;        // real entry of particle i
+    const TileDesc *tiles;    // one descriptor per cell tile
     const int *ell_cnt;       // neighbours of the walker whose real entry is e
-    const unsigned *ell_col;  // col[k * ell_stride + e]: accepted entry | shift | row offset
+    const uint4 *ell_q;       // ell_q[(k / 8) * ell_stride + e]: eight 16-bit (slot | shift) entries
     size_t ell_stride;
     int ell_cap;
-    int ncx;
+    int tile_cap;             // shared-memory slots per tile
     unsigned n_tiles;
 };
 
@@ -62,6 +63,7 @@ int csr_wrap(const PhysParams &P, double2 *pos, cudaStream_t st);               
 int csr_wall_shear(const PhysParams &P, const StateView &S, DevScalars *sc, double *partials, cudaStream_t st);  // P8
 int csr_profile(const PhysParams &P, const StateView &S, double x0, double half_width, int n_bins,
                 const double *edges_dev, double *sum_dev, double *cnt_dev, cudaStream_t st);
-constexpr int kShearPartialBlocks = 148 * 8;
+int csr_configure(int tile_cap);     // grants the gather kernels the shared memory `tile_cap` slots need
+int csr_max_tile_slots();            // what the widest gather kernel (pressure) can stage
 
 }  // namespace sphb

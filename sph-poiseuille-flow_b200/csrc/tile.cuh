@@ -1,154 +1,146 @@
-// tile.cuh -- shared-memory staging of neighbour-cell tiles.
+// tile.cuh -- cell tiles: the unit of work of the neighbour walk and of every gather kernel.
 //
-// The cell-sorted ENTRY array of the neighbour build (real + periodic ghost entries, cells in
-// row-major order, nb:46-103) is cut into tiles of kTileCells consecutive cells of one cell row.  One
-// CTA owns one tile: it stages the entries of the tile's 3 x (kTileCells + 2) cell neighbourhood --
-// at most nine contiguous entry ranges, the periodic wrap columns included -- into shared memory with
-// coalesced loads, and its threads then walk their particles' neighbours out of shared memory.  A
-// neighbour is named by its ENTRY index, so a ghost entry carries its already shifted position and
-// the lookup below is three range compares.  Whatever does not fit (capacity) or lies outside the
-// staged ranges (a seam pair met through a ghost entry) falls back to global loads.
+// The cell-sorted ENTRY array of the neighbour build (real + periodic ghost entries, cells in row-major
+// order, nb:46-103) is cut into tiles of kTileRows cell rows x `tile_w` cell columns.  One CTA owns one
+// tile: it stages the entries of the tile's (kTileRows + 2) x (tile_w + 2) cell neighbourhood -- per cell
+// row one contiguous entry range plus, for the first / last tile of a row, the periodic wrap column --
+// into shared memory with coalesced loads; its threads (one per own entry) then work out of shared
+// memory only.
+//
+// A neighbour is named by its SLOT in the staged array, so a list entry is 16 bits:
+//     slot (13 bits) | minimum-image shift + 3 (3 bits)
+// and a walker's row is stored eight entries to a 128-bit word, column-major over walkers:
+//     ell_q[(k / 8) * stride + entry],   entry k in bits 16 * (7 - k % 8) of the 128-bit word.
+// Rows are padded to a multiple of eight with the tile's DUMMY slot (index n_staged): every gather
+// kernel stages a far-away, zero-volume particle there, so the padded entries contribute exact zeros
+// and the unrolled row loops need no per-entry bound check.
+// A ghost entry carries its already shifted position, so interior tiles never shift.
+//
+// The descriptors are written once per list build (k_tile_setup) and read by every kernel of the step.
 #pragma once
 #include "common.cuh"
 
 namespace sphb {
 
-constexpr int kTileCells = 16;     // cells of one cell row per CTA
-constexpr int kTileThreads = 128;  // threads per CTA
+constexpr int kTileThreads = 128;   // threads per CTA (one per own entry, strided when a tile holds more)
+constexpr int kTileRows = 2;        // own cell rows of a tile
+constexpr int kStageRows = kTileRows + 2;
+constexpr int kMaxTileW = 32;       // widest tile in cells
+constexpr int kSlotBits = 13;
+constexpr int kMaxSlots = (1 << kSlotBits) - 2;   // staged entries per tile at most (+ the dummy slot)
+constexpr unsigned kSlotMask = (1u << kSlotBits) - 1u;
+constexpr int kShiftBias = 3;       // stored shift = m + 3, m in [-3, 4]
+constexpr double kDummyCoord = 1.0e100;   // position of the dummy slot: finite r, q >> 2, W = dW = 0
+
+enum : int { kTileValid = 1, kTileSeam = 2 };
 
 struct TileSeg {
-    int b, e;   // entry range [b, e) (already truncated to the staged part)
-    int off;    // shared-memory slot of entry b
+    int b, e;   // entry range [b, e)
+    int off;    // slot of entry b
 };
 
-struct TileDesc {
-    TileSeg seg[9];    // [row 0..2 = cy-1, cy, cy+1][0 main, 1 wrap column ncx-1, 2 wrap column 0]
-    int full_e[9];     // untruncated end of each range (entries past seg.e are read from global)
-    int cstart[3][kTileCells + 3];   // cell_start of the main range's cells a .. b (b - a + 1 values)
-    int own_b, own_e;  // entries of the tile's own cells (row cy, columns cx0..cx1-1)
-    int cy, cx0, cx1;
-    int a, b;          // main range = columns [a, b)
-    int valid;
+struct __align__(16) TileDesc {
+    TileSeg seg[kStageRows * 3];   // [staged row r <-> cell row cy0-1+r][0 main columns a..b-1, 1 wrap column ncx-1, 2 wrap column 0]
+    int n_staged;                  // also the dummy slot
+    int own_b[kTileRows];          // entries of the tile's own cells, per own row (columns cx0..cx1-1)
+    int own_n[kTileRows];
+    int own_off[kTileRows];        // slot of entry own_b[k]
+    int cy0, cx0, cx1;             // first own cell row; own columns [cx0, cx1)
+    int a, b;                      // main range = columns [a, b)
+    int flags;
+    int cs[kStageRows][kMaxTileW + 3];   // cell_start of the main range's cells a .. b (b - a + 1 values) per staged row
+    int pad[(4 - (kStageRows * 9 + 1 + 3 * kTileRows + 6 + kStageRows * (kMaxTileW + 3)) % 4) % 4];
 };
+static_assert(sizeof(TileDesc) % 16 == 0, "TileDesc is copied as int4");
 
-// ELL entry: accepted ENTRY index (28 bits) | minimum-image shift + 1 (2 bits) | row offset + 1 (2 bits)
-constexpr unsigned kEllIdMask = 0x0fffffffu;
-__device__ __forceinline__ unsigned ell_pack(int entry, int m, int oy)
+__host__ __device__ inline int tiles_per_row(int ncx, int w) { return (ncx + w - 1) / w; }
+__host__ __device__ inline int tile_rows(int ncy) { return (ncy + kTileRows - 1) / kTileRows; }
+
+__device__ __forceinline__ unsigned ell_pack(int slot, int m) { return (unsigned)slot | ((unsigned)(m + kShiftBias) << kSlotBits); }
+__device__ __forceinline__ int ell_slot(unsigned c) { return (int)(c & kSlotMask); }
+__device__ __forceinline__ int ell_shift(unsigned c) { return (int)((c >> kSlotBits) & 7u) - kShiftBias; }
+
+// k-th (k = 0..7) 16-bit entry of a row word
+__device__ __forceinline__ unsigned ell_extract(const uint4 &q, int u)
 {
-    return (unsigned)entry | ((unsigned)(m + 1) << 28) | ((unsigned)(oy + 1) << 30);
-}
-__device__ __forceinline__ int ell_entry(unsigned c) { return (int)(c & kEllIdMask); }
-__device__ __forceinline__ int ell_shift(unsigned c) { return (int)((c >> 28) & 3u) - 1; }
-__device__ __forceinline__ int ell_row(unsigned c) { return (int)(c >> 30); }
-
-__host__ __device__ inline int tiles_per_row(int ncx) { return (ncx + kTileCells - 1) / kTileCells; }
-
-// Fills the descriptor (the cell starts of the three rows are fetched by 3 x (kTileCells + 3) threads
-// in parallel, then thread 0 lays the ranges out); everybody syncs.  `cap` = shared-memory slots.
-__device__ __forceinline__ void tile_setup(TileDesc &T, int tile, int ncx, int ncy, const int *__restrict__ cell_start,
-                                           int cap)
-{
-    const int tpr = tiles_per_row(ncx);
-    const int cy = tile / tpr, cx0 = (tile % tpr) * kTileCells;
-    const int cx1 = min(cx0 + kTileCells, ncx);
-    const int a = max(cx0 - 1, 0), b = min(cx1 + 1, ncx);
-    const bool valid = cy < ncy;
-    {
-        const int r = threadIdx.x / 32, k = threadIdx.x % 32;   // one warp per row
-        const int row = cy + r - 1;
-        if (r < 3 && valid && row >= 0 && row < ncy) {
-            if (k <= b - a) T.cstart[r][k] = cell_start[row * ncx + a + k];
-            if (k == 24) T.full_e[3 * r + 1] = cell_start[row * ncx + ncx - 1];   // wrap column ncx-1: begin
-            if (k == 25) T.full_e[3 * r + 2] = cell_start[row * ncx + 1];         // wrap column 0: end
-            if (k == 26) T.seg[3 * r + 1].b = cell_start[row * ncx + ncx];        // (scratch) end of the row
-            if (k == 27) T.seg[3 * r + 2].b = cell_start[row * ncx];              // (scratch) start of the row
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        T.cy = cy;
-        T.cx0 = cx0;
-        T.cx1 = cx1;
-        T.a = a;
-        T.b = b;
-        T.valid = valid;
-        int used = 0;
-        for (int r = 0; r < 3; ++r) {
-            const int row = cy + r - 1;
-            TileSeg *s = &T.seg[3 * r];
-            int rb[3] = {0, 0, 0}, re[3] = {0, 0, 0};
-            if (valid && row >= 0 && row < ncy) {
-                rb[0] = T.cstart[r][0];
-                re[0] = T.cstart[r][b - a];
-                if (cx0 == 0 && b <= ncx - 1) {   // left halo column wraps to ncx-1
-                    rb[1] = T.full_e[3 * r + 1];
-                    re[1] = s[1].b;
-                }
-                if (cx1 == ncx && a >= 1) {       // right halo column wraps to 0
-                    rb[2] = s[2].b;
-                    re[2] = T.full_e[3 * r + 2];
-                }
-            }
-            for (int k = 0; k < 3; ++k) {
-                int len = re[k] - rb[k];
-                if (len > cap - used) len = cap - used;
-                if (len < 0) len = 0;
-                s[k].b = rb[k];
-                s[k].e = rb[k] + len;
-                s[k].off = used;
-                T.full_e[3 * r + k] = re[k];
-                used += len;
-            }
-        }
-        T.own_b = valid ? T.cstart[1][cx0 - a] : 0;
-        T.own_e = valid ? T.cstart[1][cx1 - a] : 0;
-    }
-    __syncthreads();
+    const unsigned w = u < 2 ? q.w : (u < 4 ? q.z : (u < 6 ? q.y : q.x));
+    return (u & 1) ? (w & 0xffffu) : (w >> 16);
 }
 
-// entry range [cb, ce) of cell (row r = 0..2, column cx) out of the staged cell starts
-__device__ __forceinline__ void tile_cell_range(const TileDesc &T, int r, int cx, int ncx, int &cb, int &ce)
+// Appends one 16-bit entry to the row word under construction (a 128-bit shift register).
+__device__ __forceinline__ void ell_push(uint4 &q, unsigned v)
+{
+    q.w = __funnelshift_l(q.z, q.w, 16);
+    q.z = __funnelshift_l(q.y, q.z, 16);
+    q.y = __funnelshift_l(q.x, q.y, 16);
+    q.x = (q.x << 16) | v;
+}
+
+// CTA-wide copy of the tile's descriptor into shared memory (callers sync afterwards).
+__device__ __forceinline__ void tile_load(TileDesc &T, const TileDesc *__restrict__ tiles, unsigned tile)
+{
+    const int4 *src = reinterpret_cast<const int4 *>(tiles + tile);
+    int4 *dst = reinterpret_cast<int4 *>(&T);
+    for (int k = threadIdx.x; k < (int)(sizeof(TileDesc) / 16); k += blockDim.x) dst[k] = src[k];
+}
+
+// slot range [sb, se) of cell (staged row r, column cx) of the staged neighbourhood
+__device__ __forceinline__ void tile_cell_slots(const TileDesc &T, int r, int cx, int ncx, int &sb, int &se)
 {
     if (cx >= T.a && cx < T.b) {
-        cb = T.cstart[r][cx - T.a];
-        ce = T.cstart[r][cx - T.a + 1];
-    } else if (cx == ncx - 1) {
-        cb = T.seg[3 * r + 1].b;
-        ce = T.full_e[3 * r + 1];
+        const int c0 = T.cs[r][cx - T.a];
+        sb = T.seg[3 * r].off + (c0 - T.seg[3 * r].b);
+        se = sb + (T.cs[r][cx - T.a + 1] - c0);
     } else {
-        cb = T.seg[3 * r + 2].b;
-        ce = T.full_e[3 * r + 2];
+        const TileSeg &s = T.seg[3 * r + (cx == ncx - 1 ? 1 : 2)];
+        sb = s.off;
+        se = s.off + (s.e - s.b);
     }
 }
 
-// shared-memory slot of entry e met in row `row` (0..2), or -1 when it is not staged
-__device__ __forceinline__ int tile_lookup(const TileDesc &T, int e, int row)
+// entry behind a slot (export paths only)
+__device__ __forceinline__ int tile_slot_entry(const TileDesc &T, int slot)
 {
-    const TileSeg *s = &T.seg[3 * row];
-    if (e >= s[0].b && e < s[0].e) return s[0].off + (e - s[0].b);
-    if (e >= s[1].b && e < s[1].e) return s[1].off + (e - s[1].b);
-    if (e >= s[2].b && e < s[2].e) return s[2].off + (e - s[2].b);
-    return -1;
-}
-
-// run of entries [b, e_end) of ONE cell met in row `row`: slot of b (or -1) and how many are staged
-__device__ __forceinline__ int tile_lookup_run(const TileDesc &T, int b, int e_end, int row, int &n_staged)
-{
-    const TileSeg *s = &T.seg[3 * row];
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-        if (b >= s[k].b && b < s[k].e) {
-            n_staged = min(e_end, s[k].e) - b;
-            return s[k].off + (b - s[k].b);
-        }
-    n_staged = 0;
+    for (int k = 0; k < kStageRows * 3; ++k) {
+        const int n = T.seg[k].e - T.seg[k].b;
+        if (slot >= T.seg[k].off && slot < T.seg[k].off + n) return T.seg[k].b + (slot - T.seg[k].off);
+    }
     return -1;
 }
 
 // for (e, slot) over every staged entry, strided over the CTA's threads
-#define SPHB_TILE_FOR_STAGED(T, e, slot)                                               \
-    for (int sg__ = 0; sg__ < 9; ++sg__)                                               \
-        for (int e = (T).seg[sg__].b + (int)threadIdx.x, slot = (T).seg[sg__].off + (int)threadIdx.x; \
+#define SPHB_TILE_FOR_STAGED(T, e, slot)                                                                  \
+    for (int sg__ = 0; sg__ < kStageRows * 3; ++sg__)                                                     \
+        for (int e = (T).seg[sg__].b + (int)threadIdx.x, slot = (T).seg[sg__].off + (int)threadIdx.x;     \
              e < (T).seg[sg__].e; e += (int)blockDim.x, slot += (int)blockDim.x)
+
+// Own entries of a tile as one virtual index range: v in [0, own total) -> own row, entry, slot.
+__device__ __forceinline__ int tile_own_total(const TileDesc &T)
+{
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < kTileRows; ++k) n += T.own_n[k];
+    return n;
+}
+__device__ __forceinline__ void tile_own_locate(const TileDesc &T, int v, int &orow, int &ew, int &si)
+{
+    orow = 0;
+#pragma unroll
+    for (int k = 0; k + 1 < kTileRows; ++k) {
+        if (orow == k && v >= T.own_n[k]) {
+            v -= T.own_n[k];
+            orow = k + 1;
+        }
+    }
+    ew = T.own_b[orow] + v;
+    si = T.own_off[orow] + v;
+}
+
+// for (ew, si, orow) over the tile's own entries (ew = entry, si = its slot, orow = own row 0..kTileRows-1):
+// one per thread, all own rows in ONE pass (a tile holds <= blockDim own entries by construction of its
+// width; a denser tile takes more passes)
+#define SPHB_TILE_FOR_OWN(T, ew, si, orow)                                                                \
+    for (int v__ = (int)threadIdx.x, nown__ = tile_own_total(T), orow = 0, ew = 0, si = 0;                \
+         v__ < nown__ && (tile_own_locate(T, v__, orow, ew, si), true); v__ += (int)blockDim.x)
 
 }  // namespace sphb
