@@ -73,6 +73,8 @@ struct sphb_ctx {
         S.ell_stride = nw.ell_stride;
         S.ell_cap = nw.ell_cap;
         S.tile_cap = nw.tile_cap;
+        S.tile_w = nw.tile_w;
+        S.ncx = std::max(1, (int)std::ceil(prm.DL / (2.0 * prm.h)));   // nb:254
         S.n_tiles = nw.n_tiles;
         return S;
     }
@@ -240,13 +242,25 @@ int do_substep(sphb_ctx *c, double remain, double fixed_dt, bool wrap)
     }
     {
         ProfScope ps(&c->kprof, kPfContinuity, c->st);
-        SPHB_TRY(csr_continuity(c->P, S, c->sc(), wrap, c->st));
+        SPHB_TRY(csr_continuity(c->P, S, c->sc(), wrap, true, c->st));
+    }
+    c->launches += 3;
+    return 0;
+}
+
+// first substep of an outer step: viscous + transport + dt + pressure in one gather, then continuity
+int do_fused_first_substep(sphb_ctx *c, double remain, double fixed_dt, bool wrap)
+{
+    const StateView S = c->view();
+    {
+        ProfScope ps(&c->kprof, kPfPressure, c->st);
+        SPHB_TRY(csr_force_fused(c->P, S, c->sc(), remain, fixed_dt, true, c->st));
     }
     {
-        ProfScope ps(&c->kprof, kPfClock, c->st);
-        SPHB_TRY(csr_advance_clock(c->sc(), c->st));
+        ProfScope ps(&c->kprof, kPfContinuity, c->st);
+        SPHB_TRY(csr_continuity(c->P, S, c->sc(), wrap, true, c->st));
     }
-    c->launches += 4;
+    c->launches += 3;
     return 0;
 }
 
@@ -553,7 +567,7 @@ SPHB_API int sphb_ctx_integration_verlet(sphb_ctx *c, double dt)
     const StateView S = c->view();
     SPHB_TRY(csr_time_step(c->P, S, c->sc(), std::numeric_limits<double>::infinity(), dt, c->st));
     SPHB_TRY(csr_pressure(c->P, S, c->sc(), c->st));
-    SPHB_TRY(csr_continuity(c->P, S, c->sc(), false, c->st));
+    SPHB_TRY(csr_continuity(c->P, S, c->sc(), false, false, c->st));
     c->launches += 3;
     return 0;
 }
@@ -617,9 +631,8 @@ SPHB_API int sphb_ctx_step(sphb_ctx *c, double remain)
     tick(c, 0);
     SPHB_TRY(do_density(c));                                                          // m:254-255
     tick(c, 1);
-    SPHB_TRY(do_visc_transport(c, true, true, true));                                 // m:256-257
     tick(c, 2);
-    SPHB_TRY(do_substep(c, remain, 0.0, true));                                       // m:259-269
+    SPHB_TRY(do_fused_first_substep(c, remain, 0.0, true));                           // m:256-269
     tick(c, 3);
     const int si = c->prm.sort_interval;
     if (si > 0 && c->h_step % si == 0 && c->h_step != 1) SPHB_TRY(do_sort(c));        // m:272-278
@@ -656,8 +669,8 @@ int enqueue_outer(sphb_ctx *c, int n_inner, bool with_sort)
 {
     const double inf = std::numeric_limits<double>::infinity();
     SPHB_TRY(do_density(c));
-    SPHB_TRY(do_visc_transport(c, true, true, true));
-    for (int s = 0; s < n_inner; ++s) SPHB_TRY(do_substep(c, inf, 0.0, true));
+    SPHB_TRY(do_fused_first_substep(c, inf, 0.0, true));
+    for (int s = 1; s < n_inner; ++s) SPHB_TRY(do_substep(c, inf, 0.0, true));
     if (with_sort) SPHB_TRY(do_sort(c));
     SPHB_TRY(do_neighbor(c));
     SPHB_TRY(do_shear(c));

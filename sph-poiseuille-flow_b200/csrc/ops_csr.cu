@@ -522,6 +522,190 @@ __global__ void __launch_bounds__(kTileThreads) k_pressure(PhysParams P, StateVi
 #undef SPHB_CALL
 }
 
+// ---------------------------------------------------------------- P2 + P3 + dt + P4 + kick, one gather
+// The viscous/transport pass and the pressure pass read the same neighbour fields (position, velocity,
+// B, volume), and the pressure pass depends on the viscous one only through the walker's OWN F_prior
+// (virtual wall pressure ph:929-934 and the kick ph:1402-1403).  One row walk therefore serves all
+// three operators: 88 B gathered per neighbour once instead of 72 B + 88 B.  Walkers with wall
+// neighbours take a second, short walk over their wall entries once F_prior is complete.  The time
+// step (m:519-527) is derived by every CTA from the device vmax, and the neighbours' half-step (rho, p)
+// (ph:857-862) is evaluated while staging, so there is no separate dt / half-step launch.
+__device__ __forceinline__ double device_dt(const PhysParams &P, const DevScalars *sc, double remain, double fixed_dt)
+{
+    if (fixed_dt > 0.0) return fixed_dt;
+    const double vmax = sc->vmax;
+    const double dt_a = 0.25 * P.h / fmax(P.c_f + vmax, 1e-12);
+    const double dt_v = 0.125 * P.h * P.h / fmax(P.nu, 1e-12);
+    const double dt_b = 0.25 * sqrt(P.h / fmax(fabs(P.g), 1e-12));
+    return fmax(fmin(fmin(dt_a, dt_v), fmin(dt_b, remain)), 1e-12);
+}
+
+template <bool PLAIN>
+__device__ __forceinline__ void force_rows(const PhysParams &P, const StateView &S, const TileDesc &T, const OwnPre &pre,
+                                           const double2 *s_xy, const double2 *s_v, const double2 *s_rp,
+                                           const double2 *s_b1, const double2 *s_b2, const double *s_V, double dt,
+                                           int add_gravity)
+{
+    const double h001 = 0.01 * P.h;
+    SPHB_TILE_WALKERS(ew, si, i)
+    {
+        if (i >= P.nf) {   // wall rows: forces 0, velocity 0 (ph:958-962, 1405-1408)
+            S.force_prior[i] = make_double2(0.0, 0.0);
+            S.force[i] = make_double2(0.0, 0.0);
+            S.vel_new[i] = make_double2(0.0, 0.0);
+            continue;
+        }
+        const double2 pi = s_xy[si];
+        const double2 vi = s_v[si];
+        const double2 bi1 = s_b1[si], bi2 = s_b2[si];
+        const double Vi = s_V[si], m_i = S.mass[i];
+        const double2 rpi = s_rp[si];
+        const double rho_i = rpi.x, p_i = rpi.y;
+        double ax = 0.0, ay = 0.0, ix = 0.0, iy = 0.0, fx = 0.0, fy = 0.0;
+        bool has_wall = false;
+        SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
+            const Geo g = pair_geometry(pi, s_xy[sl], m, P);
+            const double ex = g.ex, ey = g.ey;
+            const double Vs = s_V[sl];
+            const double gj = spline_dW(g.r, P) * (PLAIN ? Vs : fabs(Vs));
+            const double2 vj = s_v[sl];
+            const double dvx = vi.x - vj.x, dvy = vi.y - vj.y;
+            const double rinv = fast_rcp(g.r + h001);
+            if (PLAIN || Vs >= 0.0) {
+                const double2 bj1 = s_b1[sl], bj2 = s_b2[sl];
+                const double tx = (bi1.x + bj1.x) * ex + (bi1.y + bj1.y) * ey;
+                const double ty = (bi2.x + bj2.x) * ex + (bi2.y + bj2.y) * ey;
+                // viscous (ph:502-520) and transport (ph:667-685)
+                const double cf = (ex * tx + ey * ty) * P.mu * gj * rinv;
+                ax += cf * dvx;
+                ay += cf * dvy;
+                ix -= gj * tx;
+                iy -= gj * ty;
+                // pressure with Riemann dissipation (ph:891-925)
+                const double2 rpj = s_rp[sl];
+                const double rho_bar = 0.5 * (rho_i + rpj.x);
+                const double du = dvx * ex + dvy * ey;                          // u_l - u_r
+                const double beta = fmin(3.0 * fmax(du, 0.0), P.c_f);           // ph:1121-1129
+                const double p_avg = 0.5 * (p_i + rpj.y);
+                const double p_star = p_avg + 0.5 * beta * rho_bar * du;
+                const double pg = 0.5 * (p_avg + p_star) * gj;
+                fx -= pg * tx;
+                fy -= pg * ty;
+            } else {
+                const double tx = bi1.x * ex + bi1.y * ey;
+                const double ty = bi2.x * ex + bi2.y * ey;
+                const double cf = 4.0 * (ex * tx + ey * ty) * P.mu * gj * rinv;   // no-slip mirror, ph:526
+                ax += cf * dvx;
+                ay += cf * dvy;
+                ix -= 2.0 * gj * tx;                                              // ph:690
+                iy -= 2.0 * gj * ty;
+                has_wall = true;
+            }
+        }));
+        double2 fp;
+        fp.x = ax * Vi;
+        fp.y = ay * Vi;
+        if (add_gravity) fp.x += m_i * P.g;   // m:392
+        S.force_prior[i] = fp;
+        if (!PLAIN && has_wall) {
+            // virtual wall pressure needs the complete F_prior of the walker (ph:929-947)
+            const double inv_m = 1.0 / m_i;
+            const double wax = fp.x * inv_m, way = fp.y * inv_m;
+            SPHB_ROW(true, ([&](const int sl, const int m) {
+                const double Vs = s_V[sl];
+                if (Vs >= 0.0) return;
+                const Geo g = pair_geometry(pi, s_xy[sl], m, P);
+                const double ex = g.ex, ey = g.ey;
+                const double gj = spline_dW(g.r, P) * fabs(Vs);
+                const double ext = -(wax * ex + way * ey);
+                const double pw = p_i + rho_i * g.r * fmax(0.0, ext);   // ph:934
+                const double pg = (p_i + pw) * gj;
+                fx -= pg * (bi1.x * ex + bi1.y * ey);
+                fy -= pg * (bi2.x * ex + bi2.y * ey);
+            }));
+        }
+        double2 x = S.pos[i];
+        {   // transport correction (ph:702-710)
+            const double n2 = ix * ix + iy * iy;
+            double lim = 100.0 * n2 / (P.h * P.h);
+            const double scale = P.transport_coeff * P.h * P.h;
+            if (lim > 1.0) lim = 1.0;
+            if (lim < 0.0) lim = 0.0;
+            x.x += scale * lim * ix;
+            x.y += scale * lim * iy;
+        }
+        fx *= Vi;
+        fy *= Vi;
+        S.force[i] = make_double2(fx, fy);
+        S.rp_half[i] = rpi;
+        double2 vn;
+        vn.x = vi.x + (fp.x + fx) / m_i * dt;   // ph:1402-1403
+        vn.y = vi.y + (fp.y + fy) / m_i * dt;
+        S.vel_new[i] = vn;
+        x.x += 0.5 * dt * vi.x;   // ph:863-864
+        x.y += 0.5 * dt * vi.y;
+        x.x += 0.5 * dt * vn.x;   // ph:1067-1068
+        x.y += 0.5 * dt * vn.y;
+        S.pos[i] = x;
+    }
+}
+
+__global__ void __launch_bounds__(kTileThreads) k_force_fused(PhysParams P, StateView S, DevScalars *sc, double remain,
+                                                             double fixed_dt, int add_gravity)
+{
+    (void)remain;
+    (void)fixed_dt;
+    const double dt = sc->dt;   // published by k_publish_dt on the same stream
+    SPHB_TILE_BEGIN();
+    const OwnPre pre = tile_prefetch_own(S, T);
+    double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
+    double2 *s_v = s_xy + cap;
+    double2 *s_rp = s_v + cap;
+    double2 *s_b1 = s_rp + cap;
+    double2 *s_b2 = s_b1 + cap;
+    double *s_V = reinterpret_cast<double *>(s_b2 + cap);
+    int walls = 0;
+    SPHB_TILE_FOR_STAGED(T, e, slot)
+    {
+        const int j = S.ent_key[e] >> 3;
+        s_xy[slot] = S.ent_pos[e];
+        const double V = S.Vol[j];
+        if (j < P.nf) {
+            s_V[slot] = V;
+            s_v[slot] = S.vel[j];
+            const double rho_h = half_step_rho(S.rho[j], S.drho_dt[j], dt, P.rho0);
+            s_rp[slot] = make_double2(rho_h, P.p0 * (rho_h / P.rho0 - 1.0));   // ph:862
+            const double4 B = *reinterpret_cast<const double4 *>(&S.B[j]);
+            s_b1[slot] = make_double2(B.x, B.y);
+            s_b2[slot] = make_double2(B.z, B.w);
+        } else {
+            s_V[slot] = -V;
+            s_v[slot] = S.wall_vel[j];
+            walls = 1;
+        }
+    }
+    if (threadIdx.x == 0) {
+        const int d = T.n_staged;
+        s_xy[d] = make_double2(kDummyCoord, kDummyCoord);
+        s_v[d] = make_double2(0.0, 0.0);
+        s_rp[d] = make_double2(0.0, 0.0);
+        s_b1[d] = make_double2(0.0, 0.0);
+        s_b2[d] = make_double2(0.0, 0.0);
+        s_V[d] = 0.0;
+    }
+#define SPHB_CALL(plain) force_rows<plain>(P, S, T, pre, s_xy, s_v, s_rp, s_b1, s_b2, s_V, dt, add_gravity)
+    SPHB_TILE_DISPATCH(walls, SPHB_CALL);
+#undef SPHB_CALL
+}
+
+// publishes the time step of the substep and re-arms the max|v| reduction (one thread; runs before the
+// fused force kernel on the same stream)
+__global__ void k_publish_dt(PhysParams P, DevScalars *sc, double remain, double fixed_dt)
+{
+    sc->dt = device_dt(P, sc, remain, fixed_dt);
+    sc->vmax_bits = 0ull;
+}
+
 __device__ __forceinline__ double wrap_x(double x, double DL)   // MATLAB mod(x, DL), m:573
 {
     if (x >= 0.0 && x < DL) return x;
@@ -582,44 +766,66 @@ __device__ __forceinline__ double continuity_rows(const PhysParams &P, const Sta
     return speed;
 }
 
-__global__ void __launch_bounds__(kTileThreads) k_continuity(PhysParams P, StateView S, DevScalars *sc, int do_wrap)
+__global__ void __launch_bounds__(kTileThreads) k_continuity(PhysParams P, StateView S, DevScalars *sc, int do_wrap,
+                                                            int advance_clock)
 {
-    SPHB_TILE_BEGIN();
-    const OwnPre pre = tile_prefetch_own(S, T);
-    double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
-    double2 *s_v = s_xy + cap;
-    double *s_V = reinterpret_cast<double *>(s_v + cap);
-    int walls = 0;
-    SPHB_TILE_FOR_STAGED(T, e, slot)
-    {
-        const int j = S.ent_key[e] >> 3;
-        s_xy[slot] = S.ent_pos[e];
-        const double V = S.Vol[j];
-        if (j < P.nf) {
-            s_V[slot] = V;
-            s_v[slot] = S.vel_new[j];
-        } else {
-            s_V[slot] = -V;
-            s_v[slot] = S.wall_vel[j];
-            walls = 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ TileDesc T;
+    tile_load(T, S.tiles, blockIdx.x);
+    __syncthreads();
+    if (T.flags & kTileValid) {
+        const int cap = S.tile_cap;
+        const OwnPre pre = tile_prefetch_own(S, T);
+        double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
+        double2 *s_v = s_xy + cap;
+        double *s_V = reinterpret_cast<double *>(s_v + cap);
+        int walls = 0;
+        SPHB_TILE_FOR_STAGED(T, e, slot)
+        {
+            const int j = S.ent_key[e] >> 3;
+            s_xy[slot] = S.ent_pos[e];
+            const double V = S.Vol[j];
+            if (j < P.nf) {
+                s_V[slot] = V;
+                s_v[slot] = S.vel_new[j];
+            } else {
+                s_V[slot] = -V;
+                s_v[slot] = S.wall_vel[j];
+                walls = 1;
+            }
+        }
+        if (threadIdx.x == 0) {
+            const int d = T.n_staged;
+            s_xy[d] = make_double2(kDummyCoord, kDummyCoord);
+            s_v[d] = make_double2(0.0, 0.0);
+            s_V[d] = 0.0;
+        }
+        const double dt = sc->dt;
+        double speed = 0.0;
+#define SPHB_CALL(plain) speed = continuity_rows<plain>(P, S, T, pre, s_xy, s_v, s_V, dt, do_wrap)
+        SPHB_TILE_DISPATCH(walls, SPHB_CALL);
+#undef SPHB_CALL
+        // grid-wide max |v| over fluid rows: warp shuffle, then one atomicMax per warp
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) speed = fmax(speed, __shfl_xor_sync(0xffffffffu, speed, d));
+        if ((threadIdx.x & 31) == 0 && speed > 0.0)
+            atomicMax(&sc->vmax_bits, (unsigned long long)__double_as_longlong(speed));
+    }
+    if (!advance_clock) return;
+    // the last CTA to finish advances the clock and publishes max|v| (what k_advance_clock does as a
+    // launch of its own): t += dt, step += 1, m:264-266
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned ticket = atomicAdd(&sc->ticket, 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            sc->t += sc->dt;
+            sc->step += 1;
+            sc->vmax = __longlong_as_double((long long)atomicAdd(&sc->vmax_bits, 0ull));
+            sc->ticket = 0u;
         }
     }
-    if (threadIdx.x == 0) {
-        const int d = T.n_staged;
-        s_xy[d] = make_double2(kDummyCoord, kDummyCoord);
-        s_v[d] = make_double2(0.0, 0.0);
-        s_V[d] = 0.0;
-    }
-    const double dt = sc->dt;
-    double speed = 0.0;
-#define SPHB_CALL(plain) speed = continuity_rows<plain>(P, S, T, pre, s_xy, s_v, s_V, dt, do_wrap)
-    SPHB_TILE_DISPATCH(walls, SPHB_CALL);
-#undef SPHB_CALL
-    // grid-wide max |v| over fluid rows: warp shuffle, then one atomicMax per warp
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) speed = fmax(speed, __shfl_xor_sync(0xffffffffu, speed, d));
-    if ((threadIdx.x & 31) == 0 && speed > 0.0)
-        atomicMax(&sc->vmax_bits, (unsigned long long)__double_as_longlong(speed));
 }
 
 __global__ void __launch_bounds__(256) k_vmax(int nf, const double2 *__restrict__ vel, DevScalars *sc)
@@ -657,6 +863,12 @@ __global__ void __launch_bounds__(kTileThreads) k_wall_shear(PhysParams P, State
     if (threadIdx.x == 0) {
         partials[blockIdx.x] = 0.0;
         partials[nt + blockIdx.x] = 0.0;
+    }
+    {   // tiles whose neighbourhood cannot reach a cell row holding y <= 0 or y >= DH exit unread
+        const GridDesc *g = S.grid;
+        const int cy0 = (int)(blockIdx.x / (unsigned)tiles_per_row(S.ncx, S.tile_w)) * kTileRows;
+        const int cyb = (int)floor((0.0 - g->y_min) / g->cell), cyt = (int)floor((P.DH - g->y_min) / g->cell);
+        if (cy0 - 1 > cyb && cy0 + kTileRows < cyt) return;
     }
     SPHB_TILE_BEGIN();
     const OwnPre pre = tile_prefetch_own(S, T);
@@ -796,6 +1008,7 @@ int csr_configure(int tile_cap)
     SPHB_GRANT((k_visc_transport<true, false>), c * kViscSlot);
     SPHB_GRANT((k_visc_transport<false, true>), c * kViscSlot);
     SPHB_GRANT(k_pressure, c * kPressureSlot);
+    SPHB_GRANT(k_force_fused, c * kPressureSlot);
     SPHB_GRANT(k_continuity, c * kContinuitySlot);
     SPHB_GRANT(k_wall_shear, c * kShearSlot);
 #undef SPHB_GRANT
@@ -839,9 +1052,21 @@ int csr_pressure(const PhysParams &P, const StateView &S, const DevScalars *sc, 
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
-int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool wrap, cudaStream_t st)
+int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool wrap, bool advance_clock,
+                   cudaStream_t st)
 {
-    k_continuity<<<S.n_tiles, kTileThreads, (size_t)S.tile_cap * kContinuitySlot, st>>>(P, S, sc, wrap ? 1 : 0);
+    k_continuity<<<S.n_tiles, kTileThreads, (size_t)S.tile_cap * kContinuitySlot, st>>>(P, S, sc, wrap ? 1 : 0,
+                                                                                        advance_clock ? 1 : 0);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+// viscous + transport + dt + pressure + kick in one gather (the first substep of an outer step)
+int csr_force_fused(const PhysParams &P, const StateView &S, DevScalars *sc, double remain, double fixed_dt,
+                    bool add_gravity, cudaStream_t st)
+{
+    k_publish_dt<<<1, 1, 0, st>>>(P, sc, remain, fixed_dt);
+    k_force_fused<<<S.n_tiles, kTileThreads, (size_t)S.tile_cap * kPressureSlot, st>>>(P, S, sc, remain, fixed_dt,
+                                                                                       add_gravity ? 1 : 0);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -15,7 +15,8 @@ struct DevScalars {
     long long step;
     double y0_fluid;                // min fluid y (cell sort key origin, m:565)
     long long y0_key;
-    long long pad;
+    unsigned int ticket;            // CTAs of the continuity kernel that have finished (clock advance)
+    unsigned int pad;
 };
 
 struct PhysParams {
@@ -45,6 +46,7 @@ struct StateView {
     size_t ell_stride;
     int ell_cap;
     int tile_cap;             // shared-memory slots per tile
+    int tile_w, ncx;          // tile width in cells, cell columns
     unsigned n_tiles;
 };
 
@@ -56,7 +58,10 @@ int csr_visc_transport(const PhysParams &P, const StateView &S, bool do_visc, bo
 int csr_time_step(const PhysParams &P, const StateView &S, DevScalars *sc, double remain, double fixed_dt,
                   cudaStream_t st);
 int csr_pressure(const PhysParams &P, const StateView &S, const DevScalars *sc, cudaStream_t st);    // P4 + kick
-int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool wrap, cudaStream_t st);  // P5 + finish
+int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool wrap, bool advance_clock,
+                   cudaStream_t st);                                                             // P5 + finish (+ clock)
+int csr_force_fused(const PhysParams &P, const StateView &S, DevScalars *sc, double remain, double fixed_dt,
+                    bool add_gravity, cudaStream_t st);                                          // P2 + P3 + dt + P4
 int csr_advance_clock(DevScalars *sc, cudaStream_t st);                                          // t += dt, step++, vmax
 int csr_vmax(const PhysParams &P, const double2 *vel, DevScalars *sc, cudaStream_t st);          // standalone reduction
 int csr_wrap(const PhysParams &P, double2 *pos, cudaStream_t st);                                // m:570-577
