@@ -245,6 +245,38 @@ SPHB_API int sphb_ctx_kernel_profile(sphb_ctx *ctx, int enable, int reset, sphb_
 SPHB_API void *sphb_ctx_stream(sphb_ctx *ctx);
 SPHB_API int sphb_ctx_sync(sphb_ctx *ctx);
 
+/* ================== 3. x-slab sharding of one long periodic channel ==================
+ * The reference has no domain decomposition; this is the multi-GPU form of its main loop (m:250-283),
+ * checked against the single-domain run.  One context per rank owns the fluid rows whose wrapped x lies in
+ * the cell columns [col_lo, col_hi) (cell = 2h, nb:253) plus `halo_cols` columns of copies on either
+ * side; halo_cols = 4 lets a rank compute a whole reference step without a mid-step exchange (list ->
+ * density -> KGC -> forces -> continuity each consume one column of validity).  Per step:
+ *     sphb_ctx_slab_step_begin   density + KGC, forces, continuity, wrap            (m:254-270)
+ *     sphb_ctx_slab_scalars_export -> caller all-reduces max|v| (MAX) and the shear partials (SUM)
+ *     sphb_ctx_slab_pack         migrants + edge copies into two device buffers of the caller
+ *     (caller: NCCL send/recv of the two buffers to the left / right neighbour rank)
+ *     sphb_ctx_slab_unpack       new owned rows, new halo copies (shifted by -+DL across the seam, nb:284,291)
+ *     sphb_ctx_slab_vmax_import  the all-reduced max|v| (time step of the next step, m:519-527)
+ *     sphb_ctx_slab_step_end     list rebuild + wall-shear partials                 (m:280-283)
+ * Buffers: 16 header doubles + rec_cap records of 16 doubles, DEVICE pointers owned by the caller.
+ * The context is created by sphb_ctx_create with n_fluid = fluid-row CAPACITY (owned + copies, with
+ * head-room) and n_total = capacity + n_wall; rows are [owned fluid | halo fluid | wall].
+ */
+SPHB_API int sphb_ctx_slab_init(sphb_ctx *ctx, int col_lo, int col_hi, int halo_cols, int n_owned, const double *pos,
+                                const double *vel, const double *rho, const double *drho_dt, const double *mass,
+                                const int *ids, int n_wall, const double *wall_pos, const double *wall_mass,
+                                const double *wall_wall_vel);
+/* global identity (the `ids` given at init, carried through migrations) of the fluid rows, owned first */
+SPHB_API int sphb_ctx_slab_ids(sphb_ctx *ctx, int *ids);
+SPHB_API int sphb_ctx_slab_pack(sphb_ctx *ctx, double *send_left_dev, double *send_right_dev, int rec_cap);
+SPHB_API int sphb_ctx_slab_unpack(sphb_ctx *ctx, const double *recv_left_dev, const double *recv_right_dev,
+                                  const double *sent_left_dev, const double *sent_right_dev, int rec_cap);
+SPHB_API int sphb_ctx_slab_step_begin(sphb_ctx *ctx, double remain);
+SPHB_API int sphb_ctx_slab_step_end(sphb_ctx *ctx);
+SPHB_API int sphb_ctx_slab_scalars_export(sphb_ctx *ctx, double *out_dev3);   /* vmax, tau_bottom, tau_top partials */
+SPHB_API int sphb_ctx_slab_vmax_import(sphb_ctx *ctx, const double *in_dev1);
+SPHB_API int sphb_ctx_slab_counts(sphb_ctx *ctx, int *n_owned, int *n_halo, int *n_wall);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,7 @@ UNITS = {
     "ops_pairs.cu": [],
     "ops_csr.cu": [],
     "context.cu": [],
+    "slab.cu": [],
     "api.cu": [],
 }
 HOST_CC = "/usr/bin/gcc"   # the image's $CC wrapper lacks libgomp.spec; shims/driver are plain C

@@ -63,7 +63,7 @@ constexpr int kBlock = 128;
 inline unsigned grid_for(size_t n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
 
 // device error flags (sphb_status.error_flags)
-enum : int { kErrCsrCap = 1, kErrCellCap = 2, kErrSeenCap = 4, kErrNonFinite = 8, kErrTileCap = 16 };
+enum : int { kErrCsrCap = 1, kErrCellCap = 2, kErrSeenCap = 4, kErrNonFinite = 8, kErrTileCap = 16, kErrSlabCap = 32 };
 
 // ------------------------------------------------------------------------------------------------
 // cell grid descriptor, lives in device memory, written by the grid-setup kernel (nb:244-258)
@@ -90,6 +90,9 @@ struct NeighborWork {
     int tile_cap = 0;            // staged entries a tile may hold (shared-memory slots)
     int tile_cap_limit = 0;      // what the kernels of the caller can stage (set by the planner)
     unsigned n_tiles = 0;
+    bool slab = false;           // x-slab of a sharded channel (no wrap, no ghosts; set before neighbor_plan)
+    int col0 = 0;                // global cell column of local column 0 (slab mode)
+    int ncx_local = 0;           // local cell columns (slab mode)
     bool half_only = false;      // the last build kept only the reference's half list
     bool half_valid = false;     // totals[0] holds the half-pair count of the current list
     bool tile_fitted = false;    // tile_cap has been fitted to the first build

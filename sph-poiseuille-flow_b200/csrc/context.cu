@@ -4,82 +4,9 @@
 // with verlet_time_step m:519-527, periodic_bounding m:570-577, sort_particles_by_cell m:529-568 and
 // the S5 initialisation m:165-173, as a fixed sequence of kernel launches on one stream; the time
 // step, max|v|, clock and monitors stay on the device (DevScalars), so a step needs no host round trip.
-#include "common.cuh"
-#include "ops_csr.cuh"
-#include "sort.cuh"
-#include "tile.cuh"
+#include "context.cuh"
 
-#include <algorithm>
-#include <cmath>
 #include <limits>
-
-using namespace sphb;
-
-struct sphb_ctx {
-    sphb_params prm{};
-    PhysParams P{};
-    int device = 0;
-    cudaStream_t st = nullptr;
-    // state (+ alternates for the cell-sort permutation)
-    DevBuf pos, vel, vel_new, wall_vel, force, force_prior, rho, p, drho_dt, mass, Vol, B;
-    DevBuf a_pos, a_vel, a_wall_vel, a_force, a_force_prior, a_rho, a_p, a_drho_dt, a_mass, a_Vol, a_B;
-    DevBuf scalars, shear_partials, stage, prof, rp_half;
-    NeighborWork nw;
-    SortWork sw;
-    bool have_list = false;
-    bool list_sized = false;     // the ELL has been grown to the longest row seen at the first build
-    bool planned = false;
-    double y_lo = 0, y_hi = 0;
-    long long h_step = 0;        // host mirror of the step counter (sort cadence, m:272)
-    long long launches = 0;
-    // pinned host mirror for status read-back
-    DevScalars *h_scalars = nullptr;
-    int *h_ints = nullptr;
-    // phase timing
-    bool timing = false;
-    cudaEvent_t ev[8]{};
-    sphb_timing last_timing{};
-    Prof kprof;                  // per-kernel event timing (sphb_ctx_kernel_profile)
-    // cached graphs for the dual-criteria schedule: [0] without, [1] with cell sort
-    cudaGraphExec_t graph[2]{nullptr, nullptr};
-    int graph_inner = -1;
-    long long graph_launches = 0;
-    long long outer_count = 0;
-
-    StateView view() const
-    {
-        StateView S;
-        S.pos = pos.as<double2>();
-        S.vel = vel.as<double2>();
-        S.vel_new = vel_new.as<double2>();
-        S.wall_vel = wall_vel.as<double2>();
-        S.force = force.as<double2>();
-        S.force_prior = force_prior.as<double2>();
-        S.rho = rho.as<double>();
-        S.p = p.as<double>();
-        S.drho_dt = drho_dt.as<double>();
-        S.mass = mass.as<double>();
-        S.Vol = Vol.as<double>();
-        S.B = B.as<Mat2>();
-        S.rp_half = rp_half.as<double2>();
-        S.snap = nw.snap.as<double2>();
-        S.grid = nw.grid.as<GridDesc>();
-        S.ent_key = nw.ent_key.as<int>();
-        S.ent_pos = nw.ent_pos.as<double2>();
-        S.ent_of = nw.ent_of.as<int>();
-        S.tiles = nw.tiles.as<TileDesc>();
-        S.ell_cnt = nw.ell_cnt.as<int>();
-        S.ell_q = nw.ell_q.as<uint4>();
-        S.ell_stride = nw.ell_stride;
-        S.ell_cap = nw.ell_cap;
-        S.tile_cap = nw.tile_cap;
-        S.tile_w = nw.tile_w;
-        S.ncx = std::max(1, (int)std::ceil(prm.DL / (2.0 * prm.h)));   // nb:254
-        S.n_tiles = nw.n_tiles;
-        return S;
-    }
-    DevScalars *sc() const { return scalars.as<DevScalars>(); }
-};
 
 namespace {
 
@@ -271,6 +198,27 @@ void tick(sphb_ctx *c, int k)
 
 }  // namespace
 
+int ctx_bind_device(sphb_ctx *c) { return bind_device(c); }
+int ctx_plan_lists(sphb_ctx *c, double y_lo, double y_hi) { return plan_lists(c, y_lo, y_hi); }
+void ctx_drop_graphs(sphb_ctx *c) { drop_graphs(c); }
+int ctx_do_neighbor(sphb_ctx *c) { return do_neighbor(c); }
+int ctx_do_shear(sphb_ctx *c) { return do_shear(c); }
+int ctx_volumes_from_mass(sphb_ctx *c)
+{
+    const int nt = c->prm.n_total;
+    k_vol_from_mass<<<grid_for((size_t)nt), kBlock, 0, c->st>>>(c->mass.as<double>(), c->rho.as<double>(),
+                                                                c->Vol.as<double>(), nt);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int ctx_step_physics(sphb_ctx *c, double remain)
+{
+    c->h_step += 1;
+    SPHB_TRY(do_density(c));                                  // m:254-255
+    SPHB_TRY(do_fused_first_substep(c, remain, 0.0, true));   // m:256-270
+    return 0;
+}
+
 extern "C" {
 
 SPHB_API int sphb_ctx_create(const sphb_params *prm, sphb_ctx **out)
@@ -293,6 +241,7 @@ SPHB_API int sphb_ctx_create(const sphb_params *prm, sphb_ctx **out)
         const size_t nt = (size_t)prm->n_total;
         PhysParams &P = c->P;
         P.nf = prm->n_fluid;
+        P.nfo = prm->n_fluid;
         P.nt = prm->n_total;
         P.h = prm->h;
         P.DL = prm->DL;
@@ -355,6 +304,10 @@ SPHB_API void sphb_ctx_destroy(sphb_ctx *c)
                      &c->a_force_prior, &c->a_rho, &c->a_p, &c->a_drho_dt, &c->a_mass, &c->a_Vol, &c->a_B,
                      &c->scalars, &c->shear_partials, &c->stage, &c->prof, &c->rp_half};
     for (DevBuf *b : all) b->release();
+    for (DevBuf *b : {&c->slab.w_pos, &c->slab.w_mass, &c->slab.w_wall_vel, &c->slab.counts, &c->slab.block_tot,
+                      &c->slab.pid, &c->slab.a_pid})
+        b->release();
+    if (c->slab.h_counts) cudaFreeHost(c->slab.h_counts);
     c->nw.release_all();
     c->sw.release_all();
     c->kprof.release();

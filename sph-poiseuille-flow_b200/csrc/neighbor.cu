@@ -45,6 +45,8 @@ struct NbrParams {
     double sigma;     // 10 / (7 pi h h)                 nb:119
     int ell_cap;      // rows of the ELL (longest storable neighbour row)
     size_t ell_stride;
+    int slab;         // x-slab of a sharded channel: no wrap, no ghost entries, columns counted from col0
+    int col0;         // global cell column of local column 0 (slab mode)
 };
 
 __device__ __forceinline__ long long ordered_key(double d)
@@ -138,8 +140,21 @@ struct Bins {
 __device__ __forceinline__ Bins bin_particle(double2 p, const NbrParams &P, double y_min, int ncy)
 {
     Bins b;
-    b.xw = p.x - floor(p.x / P.DL) * P.DL;
     b.y = p.y;
+    if (P.slab) {
+        // slab of a sharded channel: positions are kept unwrapped around the slab (halo particles from
+        // across the periodic seam arrive shifted by -+DL, exactly like the reference's ghost entries,
+        // nb:284,291), the column is the GLOBAL one counted from col0, and there are no ghost entries
+        b.xw = p.x;
+        int c = (int)floor(p.x / P.cell) - P.col0;
+        b.cx = c < 0 ? 0 : (c >= P.ncx ? P.ncx - 1 : c);
+        int cys = (int)floor((p.y - y_min) / P.cell);
+        b.cy = cys < 0 ? 0 : (cys >= ncy ? ncy - 1 : cys);
+        b.gcx_lo = -1;
+        b.gcx_hi = -1;
+        return b;
+    }
+    b.xw = p.x - floor(p.x / P.DL) * P.DL;
     b.cx = wrap_col((int)floor(b.xw / P.cell), P.ncx);
     int cy = (int)floor((p.y - y_min) / P.cell);
     if (cy < 0) cy = 0;
@@ -239,8 +254,9 @@ __global__ void __launch_bounds__(kBlock) k_cell_canon(const GridDesc *__restric
 
 // One descriptor per tile (tile.cuh): entry ranges of the (kTileRows + 2) x (w + 2) cell neighbourhood and
 // their slots.
-__global__ void __launch_bounds__(kBlock) k_tile_setup(const GridDesc *__restrict__ g, int ncx, int w, unsigned n_tiles,
-                                                      int cap, int ent_cap, const int *__restrict__ cell_start,
+__global__ void __launch_bounds__(kBlock) k_tile_setup(const GridDesc *__restrict__ g, int ncx, int slab, int w,
+                                                      unsigned n_tiles, int cap, int ent_cap,
+                                                      const int *__restrict__ cell_start,
                                                       TileDesc *__restrict__ tiles, int *__restrict__ totals,
                                                       int *__restrict__ flags)
 {
@@ -298,7 +314,8 @@ __global__ void __launch_bounds__(kBlock) k_tile_setup(const GridDesc *__restric
     // walkers of columns 0, ncx-2 and ncx-1 can meet ghost entries, both entries of a particle that owns
     // a ghost, or the periodic wrap: they take the general walk (ghosts live in column ncx-1 only and
     // their owners in columns 0, ncx-2, ncx-1; nb:282-295)
-    if (cx0 < 1 || cx1 > ncx - 2 || ncx < 6) f |= kTileSeam;
+    // (a slab of a sharded channel has neither: its outermost columns are empty margins)
+    if (!slab && (cx0 < 1 || cx1 > ncx - 2 || ncx < 6)) f |= kTileSeam;
     if (used + 1 > cap) {   // cannot be staged (+ the dummy slot): reported, the tile is skipped by every kernel
         atomicOr(flags, kErrTileCap);
         f &= ~kTileValid;
@@ -526,7 +543,12 @@ __global__ void __launch_bounds__(kTileThreads) k_walk_tile(NbrParams P, const G
             }
             cxi = T.a + lo;
         }
-        if (!seam_tile || (cxi >= 1 && cxi <= ncx - 3 && ncx >= 6)) {
+        const bool interior = cxi >= 1 && cxi <= ncx - 3 && ncx >= 6;
+        if (!seam_tile && !interior) {   // slab mode: a particle clamped into the empty margin columns
+            cnt[ew] = 0;
+            continue;
+        }
+        if (interior) {
             // ---- interior walker: per stencil row one contiguous slot range; first a branch-free pass
             // that records the accepted candidates as a bit mask, then the mask is unrolled into the row
 #pragma unroll 1
@@ -815,9 +837,11 @@ NbrParams make_params(const NeighborWork &w)
     P.rc2_safe = P.rc2 * (1.0 - 1e-12);
     P.half_DL = 0.5 * w.DL;
     P.sigma = 10.0 / (7.0 * pi * w.h * w.h);
-    int ncx = (int)std::ceil(w.DL / P.cell);   // nb:254
+    int ncx = w.slab ? w.ncx_local : (int)std::ceil(w.DL / P.cell);   // nb:254
     if (ncx < 1) ncx = 1;
     P.ncx = ncx;
+    P.slab = w.slab ? 1 : 0;
+    P.col0 = w.col0;
     P.cell_cap = w.cell_cap;
     P.ell_cap = w.ell_cap;
     P.ell_stride = w.ell_stride;
@@ -875,7 +899,7 @@ int neighbor_reserve_ell(NeighborWork &w, int rows)
 // Tile geometry: `w` cells per tile, descriptors for every cell row the grid may have.
 static int plan_tiles(NeighborWork &w, int tile_w)
 {
-    const int ncx = std::max(1, (int)std::ceil(w.DL / (2.0 * w.h)));
+    const int ncx = w.slab ? std::max(1, w.ncx_local) : std::max(1, (int)std::ceil(w.DL / (2.0 * w.h)));
     if (tile_w > kMaxTileW) tile_w = kMaxTileW;
     if (tile_w < 1) tile_w = 1;
     w.tile_w = tile_w;
@@ -895,7 +919,7 @@ int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL
     w.h = h;
     w.DL = DL;
     const double cell = 2.0 * h;
-    const double ncx_d = std::ceil(DL / cell);
+    const double ncx_d = w.slab ? (double)w.ncx_local : std::ceil(DL / cell);
     const double ncy_d = std::ceil((y_max_hint - y_min_hint + 1e-12) / cell) + 1.0 + 8.0;   // slack rows
     if (!(ncx_d >= 1.0) || !(ncy_d >= 1.0) || ncx_d * ncy_d > 1.0e9)
         return set_error("SPH:Neighbor:entryCapacity", "cell grid of %g x %g cells is not representable",
@@ -995,7 +1019,7 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
     for (int attempt = 0; attempt < 8; ++attempt) {
         ProfScope ps(prof, kPfNbrWalk, st);
         SPHB_CUDA(cudaMemsetAsync(w.totals.p, 0, 8 * sizeof(int), st));
-        k_tile_setup<<<grid_for(w.n_tiles), kBlock, 0, st>>>(g, P.ncx, w.tile_w, w.n_tiles, w.tile_cap,
+        k_tile_setup<<<grid_for(w.n_tiles), kBlock, 0, st>>>(g, P.ncx, P.slab, w.tile_w, w.n_tiles, w.tile_cap,
                                                             (int)w.ell_stride, w.cell_start.as<int>(), w.tiles.as<TileDesc>(),
                                                             w.totals.as<int>(), flags);
         const size_t smem = (size_t)w.tile_cap * kWalkSlotBytes;

@@ -761,7 +761,7 @@ __device__ __forceinline__ double continuity_rows(const PhysParams &P, const Sta
             S.pos[i] = x;
         }
         S.vel[i] = vi;   // nobody reads `vel` in this kernel (neighbours read vel_new): commit in place
-        speed = fmax(speed, sqrt(vi.x * vi.x + vi.y * vi.y));
+        if (i < P.nfo) speed = fmax(speed, sqrt(vi.x * vi.x + vi.y * vi.y));
     }
     return speed;
 }
@@ -896,7 +896,7 @@ __global__ void __launch_bounds__(kTileThreads) k_wall_shear(PhysParams P, State
     double sb = 0.0, st = 0.0;
     SPHB_TILE_WALKERS(ew, si, i)
     {
-        if (i >= P.nf) continue;
+        if (i >= P.nfo) continue;   // wall rows and halo copies of a slab
         const double2 pi = s_xy[si];
         const double vx = S.vel[i].x;
         const Mat2 Bi = S.B[i];
@@ -1082,7 +1082,7 @@ int csr_vmax(const PhysParams &P, const double2 *vel, DevScalars *sc, cudaStream
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     k_vmax_reset<<<1, 1, 0, st>>>(sc);
-    k_vmax<<<blocks, 256, 0, st>>>(P.nf, vel, sc);
+    k_vmax<<<blocks, 256, 0, st>>>(P.nfo, vel, sc);
     k_vmax_commit<<<1, 1, 0, st>>>(sc);
     SPHB_CUDA(cudaGetLastError());
     return 0;

@@ -21,6 +21,7 @@ struct DevScalars {
 
 struct PhysParams {
     int nf, nt;
+    int nfo;           // fluid rows OWNED by this context (= nf unless it is a slab with halo copies)
     double h, DL, DH, rho0, p0, c_f, mu, nu, g, inv_sigma0, transport_coeff;
     double sigma;      // 10/(7 pi h^2)
     double inv_h;      // 1/h

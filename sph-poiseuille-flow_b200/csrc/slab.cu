@@ -1,0 +1,563 @@
+// slab.cu -- x-slab sharding of one long periodic channel over several GPUs.
+//
+// The reference has no domain decomposition; this is new design, checked against the
+// single-domain run.  One context per rank owns the fluid particles whose wrapped x lies in the cell
+// columns [col_lo, col_hi) and keeps H halo columns of copies on either side.  Interaction radius = one
+// cell, and one reference step consumes four columns of halo validity (list -> density -> KGC ->
+// forces -> continuity), so with H = 4 a rank computes a whole step -- redundantly on its halo copies --
+// WITHOUT any mid-step exchange.  Once per step, before the list rebuild:
+//     pack    owned rows are classified by their new column: stay / migrate left / migrate right, and
+//             stayers within H columns of an edge are also copied for that neighbour (deterministic
+//             block-scan compaction, no atomics); records = x y vx vy rho drho_dt mass Vol B(4)
+//     (the caller moves the two buffers to the neighbours: NCCL send/recv over NVLink)
+//     unpack  new owned rows = stayers + immigrants; new halo rows = received copies + the rows that just
+//             left (their new owner sits next door); copies from across the periodic seam are shifted
+//             by -+DL exactly like the reference's ghost entries (nb:284,291); wall rows (static) follow
+// plus a MAX all-reduce of max|v| (time step, m:519-527) and a SUM of the wall-shear partials by the caller.
+// Positions stay in GLOBAL coordinates (the cell column is global, counted from col0), so the pair
+// arithmetic away from the seam is bit-identical to the single-domain run.
+#include "context.cuh"
+
+namespace {
+
+constexpr int kRec = 16;        // doubles per record
+constexpr int kHdr = 16;        // doubles of buffer header: [0] migrants, [1] halo copies
+constexpr int kSlabBlock = 256;
+enum { cStay = 0, cMigL, cHaloL, cMigR, cHaloR, cN };
+
+struct SlabGeom {
+    int col_lo, width, halo, ncx_g;
+    double cell, DL;
+    int nfo;
+};
+
+// class bits of an owned fluid row (nb:253,270 binning of the wrapped x)
+__device__ __forceinline__ unsigned slab_class(double x, const SlabGeom &G)
+{
+    const double xw = x - floor(x / G.DL) * G.DL;
+    int c = (int)floor(xw / G.cell);
+    if (c >= G.ncx_g) c = G.ncx_g - 1;
+    if (c < 0) c = 0;
+    int d = c - G.col_lo;
+    d %= G.ncx_g;
+    if (d < 0) d += G.ncx_g;
+    unsigned m = 0;
+    if (d < G.width) {
+        m |= 1u << cStay;
+        if (d < G.halo) m |= 1u << cHaloL;
+        if (d >= G.width - G.halo) m |= 1u << cHaloR;
+    } else if (d < G.width + (G.ncx_g - G.width + 1) / 2) {
+        m |= 1u << cMigR;
+    } else {
+        m |= 1u << cMigL;
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(kSlabBlock) k_slab_count(const double2 *__restrict__ pos, SlabGeom G,
+                                                          int *__restrict__ block_tot)
+{
+    __shared__ int tot[cN];
+    if (threadIdx.x < cN) tot[threadIdx.x] = 0;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned m = i < G.nfo ? slab_class(pos[i].x, G) : 0u;
+#pragma unroll
+    for (int k = 0; k < cN; ++k) {
+        const unsigned b = __ballot_sync(0xffffffffu, (m >> k) & 1u);
+        if ((threadIdx.x & 31) == 0 && b) atomicAdd(&tot[k], __popc(b));
+    }
+    __syncthreads();
+    if (threadIdx.x < cN) block_tot[threadIdx.x * gridDim.x + blockIdx.x] = tot[threadIdx.x];
+}
+
+// exclusive scan of the block totals of each class (one CTA; blocks <= a few thousand), totals -> counts
+__global__ void __launch_bounds__(1024) k_slab_offsets(int *__restrict__ block_tot, int blocks, int *__restrict__ counts)
+{
+    __shared__ int warp_sum[32];
+    __shared__ int chunk_total, carry;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int k = 0; k < cN; ++k) {
+        int *v = block_tot + (size_t)k * blocks;
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        for (int base = 0; base < blocks; base += 1024) {
+            const int idx = base + (int)threadIdx.x;
+            const int x = idx < blocks ? v[idx] : 0;
+            int inc = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            if (lane == 31) warp_sum[wid] = inc;
+            __syncthreads();
+            if (wid == 0) {
+                const int s = warp_sum[lane];
+                int si = s;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, si, d);
+                    if (lane >= d) si += t;
+                }
+                warp_sum[lane] = si - s;
+                if (lane == 31) chunk_total = si;
+            }
+            __syncthreads();
+            if (idx < blocks) v[idx] = inc - x + warp_sum[wid] + carry;
+            __syncthreads();
+            if (threadIdx.x == 0) carry += chunk_total;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) counts[k] = carry;
+        __syncthreads();
+    }
+}
+
+struct SlabArrays {
+    const double2 *pos, *vel;
+    const double *rho, *drho, *mass, *Vol;
+    const Mat2 *B;
+    double2 *n_pos, *n_vel;
+    double *n_rho, *n_drho, *n_mass, *n_Vol;
+    Mat2 *n_B;
+    const int *pid;   // global particle identity, carried through every migration
+    int *n_pid;
+};
+
+__device__ __forceinline__ void write_record(double *rec, double2 x, double2 v, double rho, double drho, double mass,
+                                             double Vol, const Mat2 &B, int pid)
+{
+    double4 *r = reinterpret_cast<double4 *>(rec);
+    r[0] = make_double4(x.x, x.y, v.x, v.y);
+    r[1] = make_double4(rho, drho, mass, Vol);
+    r[2] = make_double4(B.b11, B.b12, B.b21, B.b22);
+    r[3] = make_double4((double)pid, 0.0, 0.0, 0.0);
+}
+
+// stayers -> compacted new arrays; migrants and halo copies -> the two send buffers [migrants | copies]
+__global__ void __launch_bounds__(kSlabBlock) k_slab_scatter(SlabArrays A, SlabGeom G,
+                                                            const int *__restrict__ block_off,
+                                                            const int *__restrict__ counts, double *send_left,
+                                                            double *send_right, int rec_cap, int *flags)
+{
+    __shared__ int warp_off[cN][kSlabBlock / 32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned m = i < G.nfo ? slab_class(A.pos[i].x, G) : 0u;
+    int rank[cN];
+#pragma unroll
+    for (int k = 0; k < cN; ++k) {
+        const unsigned b = __ballot_sync(0xffffffffu, (m >> k) & 1u);
+        rank[k] = __popc(b & ((1u << lane) - 1u));
+        if (lane == 0) warp_off[k][wid] = __popc(b);
+    }
+    __syncthreads();
+    if (threadIdx.x < cN) {
+        int s = 0;
+        for (int w = 0; w < kSlabBlock / 32; ++w) {
+            const int t = warp_off[threadIdx.x][w];
+            warp_off[threadIdx.x][w] = s;
+            s += t;
+        }
+    }
+    __syncthreads();
+    if (i == 0) {
+        const int nl = counts[cMigL] + counts[cHaloL], nr = counts[cMigR] + counts[cHaloR];
+        send_left[0] = (double)counts[cMigL];
+        send_left[1] = (double)counts[cHaloL];
+        send_right[0] = (double)counts[cMigR];
+        send_right[1] = (double)counts[cHaloR];
+        if (nl > rec_cap || nr > rec_cap) atomicOr(flags, kErrSlabCap);
+    }
+    if (!m) return;
+    const double2 x = A.pos[i], v = A.vel[i];
+    const double rho = A.rho[i], drho = A.drho[i], mass = A.mass[i], Vol = A.Vol[i];
+    const Mat2 B = A.B[i];
+    const int pid = A.pid[i];
+#pragma unroll
+    for (int k = 0; k < cN; ++k) {
+        if (!((m >> k) & 1u)) continue;
+        const int d = block_off[(size_t)k * gridDim.x + blockIdx.x] + warp_off[k][wid] + rank[k];
+        if (k == cStay) {
+            A.n_pos[d] = x;
+            A.n_vel[d] = v;
+            A.n_rho[d] = rho;
+            A.n_drho[d] = drho;
+            A.n_mass[d] = mass;
+            A.n_Vol[d] = Vol;
+            A.n_B[d] = B;
+            A.n_pid[d] = pid;
+        } else {
+            const bool left = k == cMigL || k == cHaloL;
+            const int base = (k == cHaloL) ? counts[cMigL] : (k == cHaloR ? counts[cMigR] : 0);
+            const int slot = base + d;
+            if (slot < rec_cap) write_record((left ? send_left : send_right) + kHdr + (size_t)slot * kRec, x, v, rho, drho, mass, Vol, B, pid);
+        }
+    }
+}
+
+struct UnpackSrc {
+    const double *buf[4];   // received from left, received from right, sent to left, sent to right
+};
+
+// new owned rows = [stayers | migrants from the left | migrants from the right];
+// new halo rows  = [copies from the left | copies from the right | own rows that left to the left | ... right]
+__global__ void __launch_bounds__(kSlabBlock) k_slab_unpack(UnpackSrc U, SlabArrays A, SlabGeom G, int rec_cap,
+                                                           int nf_cap, double rho0, double p0, double *n_p,
+                                                           double2 *n_wall_vel, int *counts, int *flags)
+{
+    // segment sizes from the headers
+    const int n_stay = counts[cStay];
+    int seg_n[6], seg_src[6], seg_first[6];
+    const int nmL = min((int)U.buf[0][0], rec_cap), nhL = min((int)U.buf[0][1], rec_cap - nmL);
+    const int nmR = min((int)U.buf[1][0], rec_cap), nhR = min((int)U.buf[1][1], rec_cap - nmR);
+    const int smL = min((int)U.buf[2][0], rec_cap), smR = min((int)U.buf[3][0], rec_cap);
+    seg_n[0] = nmL; seg_src[0] = 0; seg_first[0] = 0;      // migrants from the left   -> owned
+    seg_n[1] = nmR; seg_src[1] = 1; seg_first[1] = 0;      // migrants from the right  -> owned
+    seg_n[2] = nhL; seg_src[2] = 0; seg_first[2] = nmL;    // copies from the left     -> halo
+    seg_n[3] = nhR; seg_src[3] = 1; seg_first[3] = nmR;    // copies from the right    -> halo
+    seg_n[4] = smL; seg_src[4] = 2; seg_first[4] = 0;      // rows that left leftwards -> halo
+    seg_n[5] = smR; seg_src[5] = 3; seg_first[5] = 0;      // rows that left rightwards-> halo
+    int total = 0;
+    for (int k = 0; k < 6; ++k) total += seg_n[k];
+    const int n_owned = n_stay + nmL + nmR;
+    const int n_fluid = n_stay + total;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        counts[8] = n_owned;
+        counts[9] = n_fluid - n_owned;
+        if (n_fluid > nf_cap) atomicOr(flags, kErrSlabCap);
+    }
+    const double x_lo = (double)G.col_lo * G.cell, x_hi = (double)(G.col_lo + G.width) * G.cell;
+    const double margin = (double)(G.halo + 2) * G.cell;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        int k = 0, off = t;
+        while (off >= seg_n[k]) {
+            off -= seg_n[k];
+            ++k;
+        }
+        const int d = n_stay + t;
+        if (d >= nf_cap) continue;
+        const double4 *r = reinterpret_cast<const double4 *>(U.buf[seg_src[k]] + kHdr + (size_t)(seg_first[k] + off) * kRec);
+        const double4 a = r[0], b = r[1], c = r[2];
+        A.n_pid[d] = (int)r[3].x;
+        double x = a.x;
+        if (k >= 2) {   // a halo copy sits next to the slab: across the periodic seam it is shifted by -+DL
+            if (x > x_hi + margin) x -= G.DL;
+            else if (x < x_lo - margin) x += G.DL;
+        }
+        A.n_pos[d] = make_double2(x, a.y);
+        A.n_vel[d] = make_double2(a.z, a.w);
+        A.n_rho[d] = b.x;
+        A.n_drho[d] = b.y;
+        A.n_mass[d] = b.z;
+        A.n_Vol[d] = b.w;
+        Mat2 B;
+        B.b11 = c.x;
+        B.b12 = c.y;
+        B.b21 = c.z;
+        B.b22 = c.w;
+        A.n_B[d] = B;
+    }
+    (void)rho0;
+    (void)p0;
+    (void)n_p;
+    (void)n_wall_vel;
+}
+
+// wall rows (static) after the fluid rows
+__global__ void __launch_bounds__(kSlabBlock) k_slab_walls(const int *__restrict__ counts, int nf_cap, int n_wall,
+                                                          const double2 *__restrict__ w_pos,
+                                                          const double *__restrict__ w_mass,
+                                                          const double2 *__restrict__ w_wall_vel, double rho0,
+                                                          double p0, SlabArrays A, double2 *n_wall_vel, double *n_p)
+{
+    const int nf = min(counts[8] + counts[9], nf_cap);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nf + n_wall; t += gridDim.x * blockDim.x) {
+        if (t < nf) {   // EOS of the new fluid rows (m:172); fluid rows carry no wall velocity
+            n_p[t] = p0 * (A.n_rho[t] / rho0 - 1.0);
+            n_wall_vel[t] = make_double2(0.0, 0.0);
+            continue;
+        }
+        const int w = t - nf;
+        A.n_pos[t] = w_pos[w];
+        A.n_vel[t] = make_double2(0.0, 0.0);
+        A.n_rho[t] = rho0;
+        A.n_drho[t] = 0.0;
+        A.n_mass[t] = w_mass[w];
+        A.n_Vol[t] = w_mass[w] / rho0;
+        Mat2 B;
+        B.b11 = 1.0;
+        B.b12 = 0.0;
+        B.b21 = 0.0;
+        B.b22 = 1.0;
+        A.n_B[t] = B;
+        n_wall_vel[t] = w_wall_vel[w];
+        n_p[t] = 0.0;
+    }
+}
+
+__global__ void k_slab_scalars_out(const DevScalars *sc, double *out)
+{
+    out[0] = sc->vmax;
+    out[1] = sc->tau_bottom;
+    out[2] = sc->tau_top;
+}
+__global__ void k_slab_vmax_in(DevScalars *sc, const double *in) { sc->vmax = in[0]; }
+
+SlabGeom geom_of(const sphb_ctx *c)
+{
+    SlabGeom G;
+    G.col_lo = c->slab.col_lo;
+    G.width = c->slab.col_hi - c->slab.col_lo;
+    G.halo = c->slab.halo;
+    G.ncx_g = c->slab.ncx_global;
+    G.cell = 2.0 * c->prm.h;
+    G.DL = c->prm.DL;
+    G.nfo = c->slab.n_owned;
+    return G;
+}
+
+SlabArrays arrays_of(sphb_ctx *c)
+{
+    SlabArrays A;
+    A.pos = c->pos.as<double2>();
+    A.vel = c->vel.as<double2>();
+    A.rho = c->rho.as<double>();
+    A.drho = c->drho_dt.as<double>();
+    A.mass = c->mass.as<double>();
+    A.Vol = c->Vol.as<double>();
+    A.B = c->B.as<Mat2>();
+    A.n_pos = c->a_pos.as<double2>();
+    A.n_vel = c->a_vel.as<double2>();
+    A.n_rho = c->a_rho.as<double>();
+    A.n_drho = c->a_drho_dt.as<double>();
+    A.n_mass = c->a_mass.as<double>();
+    A.n_Vol = c->a_Vol.as<double>();
+    A.n_B = c->a_B.as<Mat2>();
+    A.pid = c->slab.pid.as<int>();
+    A.n_pid = c->slab.a_pid.as<int>();
+    return A;
+}
+
+void apply_counts(sphb_ctx *c, int n_owned, int n_halo)
+{
+    c->slab.n_owned = n_owned;
+    c->slab.n_halo = n_halo;
+    const int nf = n_owned + n_halo, nt = nf + c->slab.n_wall;
+    c->prm.n_fluid = nf;
+    c->prm.n_total = nt;
+    c->P.nf = nf;
+    c->P.nfo = n_owned;
+    c->P.nt = nt;
+    c->nw.n_fluid = nf;
+    c->nw.n_total = nt;
+}
+
+}  // namespace
+
+extern "C" {
+
+#define SLAB_ENTER()                                                                     \
+    clear_error();                                                                       \
+    if (!c) return set_error("SPHB:arg", "null context");                                \
+    SPHB_TRY(ctx_bind_device(c));                                                        \
+    if (!c->slab.on) return set_error("SPHB:state", "the context is not a slab: call sphb_ctx_slab_init")
+
+// The context must have been created with n_fluid = fluid-row CAPACITY (owned + halo copies, with
+// head-room) and n_total = that capacity + n_wall.  Host arrays are column-major like sphb_ctx_upload's.
+SPHB_API int sphb_ctx_slab_init(sphb_ctx *c, int col_lo, int col_hi, int halo_cols, int n_owned, const double *pos,
+                                const double *vel, const double *rho, const double *drho_dt, const double *mass,
+                                const int *ids, int n_wall, const double *wall_pos, const double *wall_mass,
+                                const double *wall_wall_vel)
+{
+    clear_error();
+    if (!c) return set_error("SPHB:arg", "null context");
+    SPHB_TRY(ctx_bind_device(c));
+    const int nf_cap = c->prm.n_fluid;
+    const int ncx_g = std::max(1, (int)std::ceil(c->prm.DL / (2.0 * c->prm.h)));   // nb:254
+    if (col_lo < 0 || col_hi <= col_lo || col_hi > ncx_g || halo_cols < 1 || n_owned < 0 || n_owned > nf_cap ||
+        n_wall < 0 || nf_cap + n_wall != c->prm.n_total)
+        return set_error("SPHB:arg", "bad slab description");
+    if (col_hi - col_lo < halo_cols || ncx_g < (col_hi - col_lo) + 2 * halo_cols + 2)
+        return set_error("SPHB:arg", "slab of %d columns with %d halo columns does not fit a channel of %d columns",
+                         col_hi - col_lo, halo_cols, ncx_g);
+    SlabState &s = c->slab;
+    s.on = true;
+    s.col_lo = col_lo;
+    s.col_hi = col_hi;
+    s.halo = halo_cols;
+    s.ncx_global = ncx_g;
+    s.n_wall = n_wall;
+    s.nf_cap = nf_cap;
+    ctx_drop_graphs(c);
+    // static wall store
+    const size_t nw = (size_t)n_wall;
+    SPHB_TRY(s.w_pos.reserve((nw + 1) * sizeof(double2)));
+    SPHB_TRY(s.w_mass.reserve((nw + 1) * sizeof(double)));
+    SPHB_TRY(s.w_wall_vel.reserve((nw + 1) * sizeof(double2)));
+    SPHB_TRY(s.counts.reserve(16 * sizeof(int)));
+    SPHB_TRY(s.block_tot.reserve((size_t)cN * (grid_for((size_t)nf_cap, kSlabBlock) + 1) * sizeof(int)));
+    if (!s.h_counts) SPHB_CUDA(cudaMallocHost((void **)&s.h_counts, 16 * sizeof(int)));
+    SPHB_TRY(s.pid.reserve(((size_t)nf_cap + 1) * sizeof(int)));
+    SPHB_TRY(s.a_pid.reserve(((size_t)nf_cap + 1) * sizeof(int)));
+    if (ids && n_owned) SPHB_CUDA(cudaMemcpyAsync(s.pid.p, ids, (size_t)n_owned * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    double *stage = c->stage.as<double>();   // 4 * n_total doubles
+    auto up2 = [&](const double *src, size_t n, double2 *dst) -> int {
+        if (!n) return 0;
+        SPHB_CUDA(cudaMemcpyAsync(stage, src, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        launch_pack2(stage, dst, (int)n, c->st);
+        SPHB_CUDA(cudaStreamSynchronize(c->st));
+        return 0;
+    };
+    SPHB_TRY(up2(wall_pos, nw, s.w_pos.as<double2>()));
+    SPHB_TRY(up2(wall_wall_vel, nw, s.w_wall_vel.as<double2>()));
+    if (nw) SPHB_CUDA(cudaMemcpyAsync(s.w_mass.p, wall_mass, nw * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    // owned fluid rows; no halo copies yet (the first exchange brings them)
+    const size_t no = (size_t)n_owned;
+    SPHB_TRY(up2(pos, no, c->pos.as<double2>()));
+    SPHB_TRY(up2(vel, no, c->vel.as<double2>()));
+    if (no) {
+        SPHB_CUDA(cudaMemcpyAsync(c->rho.p, rho, no * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        SPHB_CUDA(cudaMemcpyAsync(c->drho_dt.p, drho_dt, no * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        SPHB_CUDA(cudaMemcpyAsync(c->mass.p, mass, no * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    }
+    apply_counts(c, n_owned, 0);
+    // Vol = m / rho (m:120), B = I already
+    SPHB_TRY(ctx_volumes_from_mass(c));
+    SPHB_TRY(csr_vmax(c->P, c->vel.as<double2>(), c->sc(), c->st));
+    // the cell grid of the slab: global columns [col_lo - H - 1, col_hi + H + 2): empty margins on both sides
+    c->nw.slab = true;
+    c->nw.col0 = col_lo - halo_cols - 1;
+    c->nw.ncx_local = (col_hi - col_lo) + 2 * halo_cols + 3;
+    double y_lo = 0.0, y_hi = c->prm.DH;
+    for (size_t i = 0; i < nw; ++i) {
+        y_lo = wall_pos[nw + i] < y_lo ? wall_pos[nw + i] : y_lo;
+        y_hi = wall_pos[nw + i] > y_hi ? wall_pos[nw + i] : y_hi;
+    }
+    for (size_t i = 0; i < no; ++i) {
+        y_lo = pos[no + i] < y_lo ? pos[no + i] : y_lo;
+        y_hi = pos[no + i] > y_hi ? pos[no + i] : y_hi;
+    }
+    // plan for the capacity, then run with the current row counts
+    apply_counts(c, nf_cap, 0);
+    SPHB_TRY(ctx_plan_lists(c, y_lo, y_hi));
+    apply_counts(c, n_owned, 0);
+    c->have_list = false;
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+SPHB_API int sphb_ctx_slab_pack(sphb_ctx *c, double *send_left_dev, double *send_right_dev, int rec_cap)
+{
+    SLAB_ENTER();
+    if (!send_left_dev || !send_right_dev || rec_cap < 1) return set_error("SPHB:arg", "bad send buffers");
+    SlabState &s = c->slab;
+    const SlabGeom G = geom_of(c);
+    const unsigned blocks = std::max(1u, grid_for((size_t)s.n_owned, kSlabBlock));
+    int *bt = s.block_tot.as<int>(), *cnt = s.counts.as<int>();
+    k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), G, bt);
+    k_slab_offsets<<<1, 1024, 0, c->st>>>(bt, (int)blocks, cnt);
+    k_slab_scatter<<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, bt, cnt, send_left_dev, send_right_dev, rec_cap,
+                                                     c->nw.flags.as<int>());
+    c->launches += 3;
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+SPHB_API int sphb_ctx_slab_unpack(sphb_ctx *c, const double *recv_left_dev, const double *recv_right_dev,
+                                  const double *sent_left_dev, const double *sent_right_dev, int rec_cap)
+{
+    SLAB_ENTER();
+    SlabState &s = c->slab;
+    const SlabGeom G = geom_of(c);
+    UnpackSrc U;
+    U.buf[0] = recv_left_dev;
+    U.buf[1] = recv_right_dev;
+    U.buf[2] = sent_left_dev;
+    U.buf[3] = sent_right_dev;
+    int *cnt = s.counts.as<int>();
+    const SlabArrays A = arrays_of(c);
+    k_slab_unpack<<<148 * 2, kSlabBlock, 0, c->st>>>(U, A, G, rec_cap, s.nf_cap, c->prm.rho0, c->prm.p0,
+                                                     c->a_p.as<double>(), c->a_wall_vel.as<double2>(), cnt,
+                                                     c->nw.flags.as<int>());
+    k_slab_walls<<<148 * 2, kSlabBlock, 0, c->st>>>(cnt, s.nf_cap, s.n_wall, s.w_pos.as<double2>(), s.w_mass.as<double>(),
+                                                    s.w_wall_vel.as<double2>(), c->prm.rho0, c->prm.p0, A,
+                                                    c->a_wall_vel.as<double2>(), c->a_p.as<double>());
+    c->launches += 2;
+    SPHB_CUDA(cudaMemcpyAsync(s.h_counts, cnt, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    SPHB_CUDA(cudaGetLastError());
+    const int n_owned = s.h_counts[8], n_halo = s.h_counts[9];
+    if (n_owned + n_halo > s.nf_cap)
+        return set_error("SPHB:capacity", "slab holds %d owned + %d halo fluid rows, capacity %d", n_owned, n_halo,
+                         s.nf_cap);
+    std::swap(c->pos, c->a_pos);
+    std::swap(c->vel, c->a_vel);
+    std::swap(c->rho, c->a_rho);
+    std::swap(c->drho_dt, c->a_drho_dt);
+    std::swap(c->mass, c->a_mass);
+    std::swap(c->Vol, c->a_Vol);
+    std::swap(c->B, c->a_B);
+    std::swap(c->wall_vel, c->a_wall_vel);
+    std::swap(c->p, c->a_p);
+    std::swap(s.pid, s.a_pid);
+    apply_counts(c, n_owned, n_halo);
+    c->have_list = false;
+    return 0;
+}
+
+// first half of a reference step on the slab: density + KGC, forces, continuity (m:254-270)
+SPHB_API int sphb_ctx_slab_step_begin(sphb_ctx *c, double remain)
+{
+    SLAB_ENTER();
+    if (!c->have_list) return set_error("SPHB:state", "no neighbour list: call sphb_ctx_slab_step_end first");
+    return ctx_step_physics(c, remain);
+}
+
+// second half, after the exchange: list rebuild and wall-shear partials (m:280-283)
+SPHB_API int sphb_ctx_slab_step_end(sphb_ctx *c)
+{
+    SLAB_ENTER();
+    SPHB_TRY(ctx_do_neighbor(c));
+    SPHB_TRY(ctx_do_shear(c));
+    return 0;
+}
+
+// [max|v| over owned rows, tau_bottom partial, tau_top partial] -> device buffer of the caller (3 doubles)
+SPHB_API int sphb_ctx_slab_scalars_export(sphb_ctx *c, double *out_dev)
+{
+    SLAB_ENTER();
+    k_slab_scalars_out<<<1, 1, 0, c->st>>>(c->sc(), out_dev);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+// the all-reduced max|v| back into the context (device buffer, 1 double)
+SPHB_API int sphb_ctx_slab_vmax_import(sphb_ctx *c, const double *in_dev)
+{
+    SLAB_ENTER();
+    k_slab_vmax_in<<<1, 1, 0, c->st>>>(c->sc(), in_dev);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// global identity of every fluid row (owned rows first), n_owned + n_halo ints
+SPHB_API int sphb_ctx_slab_ids(sphb_ctx *c, int *ids)
+{
+    SLAB_ENTER();
+    const size_t n = (size_t)(c->slab.n_owned + c->slab.n_halo);
+    if (n) SPHB_CUDA(cudaMemcpyAsync(ids, c->slab.pid.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+SPHB_API int sphb_ctx_slab_counts(sphb_ctx *c, int *n_owned, int *n_halo, int *n_wall)
+{
+    SLAB_ENTER();
+    if (n_owned) *n_owned = c->slab.n_owned;
+    if (n_halo) *n_halo = c->slab.n_halo;
+    if (n_wall) *n_wall = c->slab.n_wall;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,254 @@
+"""x-slab sharding of one long periodic channel over several GPUs: host side.
+
+The reference has no domain decomposition.  The periodic channel is cut on cell-column
+boundaries (cell = 2h, sph_neighbor_search_mex.c:253); each rank runs the device-resident step of
+libsph_b200 on its slab plus four halo columns, and once per step -- before the list rebuild -- moves
+the rows that changed slab and refreshes the halo copies.  Everything that touches particle data is a
+CUDA kernel of the library (sphb_ctx_slab_pack / _unpack, csrc/slab.cu); this module only
+  * cuts the initial condition into slabs (numpy bookkeeping, like channel_setup.py),
+  * owns the exchange buffers (torch CUDA tensors: device memory only) and
+  * moves them between ranks: NCCL send/recv + all-reduce through torch.distributed (`SlabChannel`),
+    or plain device copies between slabs living on ONE GPU (`SlabGroup`, used by the parity tests and
+    wherever there are fewer GPUs than slabs).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import Channel, ChannelParams, SphError, _check, _p, lib   # noqa: F401
+
+HALO_COLS = 4        # list -> density -> KGC -> forces -> continuity: one column of validity each
+REC = 16             # doubles per record
+HDR = 16             # doubles of header
+_IP = C.POINTER(C.c_int)
+
+
+def n_columns(cfg) -> int:
+    return max(1, int(math.ceil(cfg.DL / (2.0 * cfg.h))))     # nb:254
+
+
+def partition_columns(ncx: int, world: int):
+    """Balanced cut of the cell columns [0, ncx) into `world` contiguous slabs."""
+    base, extra = divmod(ncx, world)
+    cuts, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < extra else 0)
+        cuts.append((lo, hi))
+        lo = hi
+    return cuts
+
+
+def _columns(x, cfg, ncx):
+    cell = 2.0 * cfg.h
+    xw = x - np.floor(x / cfg.DL) * cfg.DL                     # nb:270
+    c = np.floor(xw / cell).astype(np.int64)
+    return np.clip(c, 0, ncx - 1)
+
+
+def cut_slab(cfg, pt, col_lo: int, col_hi: int, halo: int = HALO_COLS):
+    """Owned fluid rows of the slab and the (static) wall rows of the slab and its halo columns, the
+    latter unwrapped around the slab (x -+ DL across the periodic seam, as nb:284,291)."""
+    ncx = n_columns(cfg)
+    nf = pt.n_fluid
+    c = _columns(pt.pos[:, 0], cfg, ncx)
+    own = np.nonzero((c[:nf] >= col_lo) & (c[:nf] < col_hi))[0]
+    width = col_hi - col_lo
+    cw = c[nf:]
+    rel = np.mod(cw - col_lo + halo, ncx) - halo
+    keep = rel < width + halo
+    k = (col_lo + rel - cw) // ncx                             # -1, 0 or +1 periods
+    wx = pt.pos[nf:, 0] + k * cfg.DL
+    widx = np.nonzero(keep)[0]
+    wall_pos = np.asfortranarray(np.stack([wx[widx], pt.pos[nf:, 1][widx]], axis=1))
+    return dict(
+        ids=own.astype(np.int32),
+        pos=np.asfortranarray(pt.pos[own, :]), vel=np.asfortranarray(pt.vel[own, :]),
+        rho=np.ascontiguousarray(pt.rho[own]), drho_dt=np.ascontiguousarray(pt.drho_dt[own]),
+        mass=np.ascontiguousarray(pt.mass[own]),
+        wall_ids=(widx + nf).astype(np.int32), wall_pos=wall_pos,
+        wall_mass=np.ascontiguousarray(pt.mass[nf:][widx]),
+        wall_wall_vel=np.asfortranarray(pt.wall_vel[nf:, :][widx, :]))
+
+
+class Slab:
+    """One slab: a device-resident context in slab mode plus its four exchange buffers."""
+
+    def __init__(self, cfg, pt, col_lo, col_hi, device, halo=HALO_COLS, headroom=1.25, **overrides):
+        import torch
+        self.torch = torch
+        self.cfg, self.col_lo, self.col_hi, self.halo = cfg, col_lo, col_hi, halo
+        self.device = torch.device(device)
+        part = cut_slab(cfg, pt, col_lo, col_hi, halo)
+        n_owned, n_wall = part["pos"].shape[0], part["wall_pos"].shape[0]
+        width = col_hi - col_lo
+        per_col = max(1.0, pt.n_fluid / n_columns(cfg))
+        self.nf_cap = int((n_owned + 2 * (halo + 1) * per_col) * headroom) + 1024
+        self.rec_cap = int((halo + 2) * per_col * 1.5) + 256
+        kw = dict(n_fluid=self.nf_cap, n_total=self.nf_cap + n_wall, DL=cfg.DL, DH=cfg.DH, dp=cfg.dp, h=cfg.h,
+                  rho0=cfg.rho0, p0=cfg.p0, c_f=cfg.c_f, mu=cfg.mu, gravity_g=cfg.gravity_g,
+                  inv_sigma0=cfg.inv_sigma0, transport_coeff=cfg.transport_coeff, sort_interval=0,
+                  device=self.device.index if self.device.index is not None else -1)
+        kw.update(overrides)
+        self.ch = Channel(ChannelParams(**kw))
+        self._keep = part
+        ids = part["ids"]
+        _check(lib().sphb_ctx_slab_init(
+            self.ch._ctx, C.c_int(col_lo), C.c_int(col_hi), C.c_int(halo), C.c_int(n_owned), _p(part["pos"]),
+            _p(part["vel"]), _p(part["rho"]), _p(part["drho_dt"]), _p(part["mass"]), ids.ctypes.data_as(_IP),
+            C.c_int(n_wall), _p(part["wall_pos"]), _p(part["wall_mass"]), _p(part["wall_wall_vel"])))
+        n = HDR + self.rec_cap * REC
+        mk = lambda: torch.zeros(n, dtype=torch.float64, device=self.device)   # noqa: E731
+        self.send_left, self.send_right, self.recv_left, self.recv_right = mk(), mk(), mk(), mk()
+        self.scal = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self.width = width
+
+    # -- the two halves of a step and the device side of the exchange ---------------------------------
+    def step_begin(self, remain=float("inf")):
+        _check(lib().sphb_ctx_slab_step_begin(self.ch._ctx, C.c_double(remain)))
+
+    def step_end(self):
+        _check(lib().sphb_ctx_slab_step_end(self.ch._ctx))
+
+    def pack(self):
+        L = lib()
+        _check(L.sphb_ctx_slab_scalars_export(self.ch._ctx, C.c_void_p(self.scal.data_ptr())))
+        _check(L.sphb_ctx_slab_pack(self.ch._ctx, C.c_void_p(self.send_left.data_ptr()),
+                                    C.c_void_p(self.send_right.data_ptr()), C.c_int(self.rec_cap)))
+
+    def unpack(self):
+        L = lib()
+        _check(L.sphb_ctx_slab_unpack(self.ch._ctx, C.c_void_p(self.recv_left.data_ptr()),
+                                      C.c_void_p(self.recv_right.data_ptr()), C.c_void_p(self.send_left.data_ptr()),
+                                      C.c_void_p(self.send_right.data_ptr()), C.c_int(self.rec_cap)))
+        _check(L.sphb_ctx_slab_vmax_import(self.ch._ctx, C.c_void_p(self.scal.data_ptr())))
+
+    def counts(self):
+        a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        _check(lib().sphb_ctx_slab_counts(self.ch._ctx, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def owned(self, fields=("pos", "vel", "rho", "p", "drho_dt")):
+        """Owned fluid rows with their global ids: {"ids": ..., field: ...}."""
+        n_owned, n_halo, n_wall = self.counts()
+        self.ch.prm.n_total = n_owned + n_halo + n_wall
+        self.ch.prm.n_fluid = n_owned + n_halo
+        out = self.ch.download(fields)
+        ids = np.zeros(n_owned + n_halo, dtype=np.int32)
+        _check(lib().sphb_ctx_slab_ids(self.ch._ctx, ids.ctypes.data_as(_IP)))
+        res = {k: v[:n_owned] for k, v in out.items()}
+        res["ids"] = ids[:n_owned]
+        return res
+
+    def close(self):
+        self.ch.close()
+
+
+class SlabGroup:
+    """All slabs of a channel on ONE GPU, exchanged by device copies: the single-process form of the
+    sharded run (parity tests; fewer GPUs than slabs).  Same kernels, same buffers as the NCCL form."""
+
+    def __init__(self, cfg, pt, n_slabs: int, device="cuda:0", **kw):
+        cuts = partition_columns(n_columns(cfg), n_slabs)
+        self.slabs = [Slab(cfg, pt, lo, hi, device, **kw) for lo, hi in cuts]
+        self.n = n_slabs
+        self.tau = (0.0, 0.0)
+        self.exchange()
+        for s in self.slabs:
+            s.step_end()
+
+    def exchange(self):
+        import torch
+        S = self.slabs
+        for s in S:
+            s.pack()
+        for s in S:
+            s.ch.sync()
+        scal = torch.stack([s.scal for s in S])
+        vmax = scal[:, 0].max()
+        tau = scal[:, 1:3].sum(dim=0)
+        for r, s in enumerate(S):
+            left, right = S[(r - 1) % self.n], S[(r + 1) % self.n]
+            s.recv_left.copy_(left.send_right)     # what my left neighbour sent to ITS right
+            s.recv_right.copy_(right.send_left)
+            s.scal[0] = vmax
+        torch.cuda.synchronize()
+        for s in S:
+            s.unpack()
+        self.tau = tuple(float(v) for v in tau.tolist())
+
+    def step(self, remain=float("inf")):
+        for s in self.slabs:
+            s.step_begin(remain)
+        self.exchange()
+        for s in self.slabs:
+            s.step_end()
+
+    def gather(self, fields=("pos", "vel", "rho", "p", "drho_dt")):
+        """Owned rows of every slab, ordered by global particle id."""
+        parts = [s.owned(fields) for s in self.slabs]
+        ids = np.concatenate([p["ids"] for p in parts])
+        order = np.argsort(ids, kind="stable")
+        out = {k: np.concatenate([p[k] for p in parts], axis=0)[order] for k in fields}
+        out["ids"] = ids[order]
+        return out
+
+    def status(self):
+        st = [s.ch.status() for s in self.slabs]
+        return dict(t=st[0]["t"], dt=st[0]["dt"], step=st[0]["step"], vmax=max(x["vmax"] for x in st),
+                    error_flags=max(x["error_flags"] for x in st))
+
+    def close(self):
+        for s in self.slabs:
+            s.close()
+
+
+class SlabChannel:
+    """One rank of the sharded channel: its slab, and the exchange over torch.distributed
+    (backend "nccl": send/recv over NVLink; "gloo" works for the host-side logic with CPU staging)."""
+
+    def __init__(self, cfg, pt, rank: int, world: int, device, **kw):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = rank, world
+        lo, hi = partition_columns(n_columns(cfg), world)[rank]
+        self.slab = Slab(cfg, pt, lo, hi, device, **kw)
+        self.left, self.right = (rank - 1) % world, (rank + 1) % world
+        self.tau = (0.0, 0.0)
+        self.exchange()
+        self.slab.step_end()
+
+    def exchange(self):
+        torch, dist, s = self.torch, self.dist, self.slab
+        s.pack()
+        s.ch.sync()                      # the library launches on its own stream
+        if self.world == 1:
+            s.recv_left.copy_(s.send_right)
+            s.recv_right.copy_(s.send_left)
+        else:
+            # a rank's "to the right" arrives as its neighbour's "from the left"; with two ranks both
+            # messages travel between the same pair, matched in posting order
+            ops = [dist.P2POp(dist.isend, s.send_left, self.left), dist.P2POp(dist.isend, s.send_right, self.right),
+                   dist.P2POp(dist.irecv, s.recv_right, self.right), dist.P2POp(dist.irecv, s.recv_left, self.left)]
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            vmax = s.scal[0:1].clone()
+            tau = s.scal[1:3].clone()
+            dist.all_reduce(vmax, op=dist.ReduceOp.MAX)     # time step of the next step (m:519-527)
+            dist.all_reduce(tau, op=dist.ReduceOp.SUM)      # wall-shear partials (ph:1713-1742)
+            s.scal[0:1] = vmax
+            s.scal[1:3] = tau
+        torch.cuda.current_stream(s.device).synchronize()
+        self.tau = (float(s.scal[1]), float(s.scal[2])) if False else self.tau
+        s.unpack()
+
+    def step(self, remain=float("inf")):
+        self.slab.step_begin(remain)
+        self.exchange()
+        self.slab.step_end()
+
+    def close(self):
+        self.slab.close()
