@@ -15,9 +15,13 @@ degenerates to (freezing the viscous force over several substeps is unstable the
 particle-substep is one integration_verlet application to one particle; value = n_total * inner *
 steps * ranks / time, so all outer-step work (list rebuild included) is amortised into the number.
 
-Multi-GPU (launched by torchrun, one rank per GPU): independent channels, one per rank, no
-data-path collective ("scaling": "weak").  Timing: CUDA events on the library's stream, barrier +
-synchronize on both sides, max over ranks.
+Multi-GPU (launched by torchrun, one rank per GPU), "scaling": "weak" (fixed work per GPU):
+  --mode slab (default for N > 1): ONE periodic channel of length N * DL cut into x-slabs on cell-column
+      boundaries (BASELINE.json configs[4] in weak-scaling form): every rank steps its slab + 4 halo
+      columns, and once per step migrating rows and halo copies move to the neighbour ranks (NCCL
+      send/recv over NVLink) and max|v| / the shear partials are all-reduced;
+  --mode replicas: N independent channels, one per rank, no data-path collective (configs[3]-style).
+Timing: CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks.
 
 Lines printed: ONE JSON line on rank 0 (see the task contract: value, e2e, roofline, cpu_baseline,
 clocks, gpu_launches).  `--impl reference` times the reference's own OpenMP C code (oracle/_ref,
@@ -43,6 +47,7 @@ METRIC = "particle-substeps/s"
 ALG_BYTES_SUBSTEP = 184           # P6 contract, 112 B read + 72 B written per particle
 # per-particle algorithmic bytes of each kernel (inputs read once + outputs written once, fp64)
 ALG_BYTES_KERNEL = {
+    "force_fused": 112 + 80,       # P2+P3+dt+P4: pos vel rho drho Vol B mass wall_vel -> F_prior force v_new pos (rho,p)half
     "pressure": 112 + 48,          # pos vel rho drho F_prior Vol B mass -> force, v_new, pos
     "continuity": 56 + 56,         # v_new Vol rho drho pos -> rho p drho pos vel
     "density": 24 + 16,            # snapshot pos, mass -> rho, Vol
@@ -68,6 +73,10 @@ def parse_args():
     ap.add_argument("--cpu-baseline-steps", type=int, default=20, help="outer steps of the CPU sample (0 = skip)")
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--presort", action="store_true", help="experiment: apply the cell sort (m:529-568) once before timing")
+    ap.add_argument("--mode", default="auto", choices=("auto", "slab", "replicas"),
+                    help="N > 1: 'slab' = ONE periodic channel of length N*DL cut into x-slabs (halo exchange + "
+                         "migration over NCCL, weak scaling); 'replicas' = N independent channels (ensemble); "
+                         "auto = slab")
     return ap.parse_args()
 
 
@@ -241,6 +250,8 @@ def b200_arm(args):
         return float(t.item())
 
     lp = load_product()
+    if world > 1 and args.mode in ("auto", "slab"):
+        return b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks)
     cfg = lp.ChannelConfig(DL=args.DL, dp=args.dp).derive()
     pt = lp.channel_setup.developed(cfg, seed=args.seed + rank)     # one independent channel per rank
     nt, inner, K, W = pt.n_total, args.inner, args.steps, args.warmup
@@ -370,6 +381,139 @@ def b200_arm(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return 0
+
+
+
+# ------------------------------------------------------------------------------------------------
+# N > 1: one periodic channel of length N * DL, x-slab sharded
+# ------------------------------------------------------------------------------------------------
+def b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks):
+    import importlib
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    slabmod = importlib.import_module("sph_b200.slab")
+    cfg = lp.ChannelConfig(DL=args.DL * world, dp=args.dp, sort_interval=0).derive()
+    pt = lp.channel_setup.developed(cfg, seed=args.seed)              # the same global state on every rank
+    K, W = args.steps, max(args.warmup, 3)
+    dev = torch.device("cuda", local_rank)
+    sc = slabmod.SlabChannel(cfg, pt, rank, world, dev)
+    ch = sc.slab.ch
+    stream = sc.stream                           # the library's kernels, torch and NCCL share this stream in slab mode
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    for _ in range(W):
+        sc.step()
+    ch.sync()
+    l0 = ch.timing()["launches"]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    for k in range(K):
+        with torch.cuda.stream(stream):
+            if flush is not None:
+                flush.zero_()                     # > L2 (126 MB): the next step starts from HBM
+            ev[k][0].record(stream)
+        sc.step()                                 # physics | pack -> NCCL send/recv + all-gather -> unpack | list + shear
+        ev[k][1].record(stream)
+    ch.sync()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+    launches = ch.timing()["launches"] - l0
+    st = ch.status()
+    flags = max_over_ranks(float(st["error_flags"]))
+    if flags or not np.isfinite(st["vmax"]) or st["vmax"] > 10 * cfg.U_max:
+        raise SystemExit(f"bench.py: sharded run invalid (flags={flags}, vmax={st['vmax']})")
+    value = pt.n_total * K / (ms_total * 1e-3)
+    n_owned, n_halo, n_wall = sc.slab.counts()
+
+    # ---- end to end: host rows -> upload -> halo exchange -> list -> physics -> download, every step ----
+    Ke = max(1, min(args.e2e_steps, K))
+    fields = ("pos", "vel", "rho", "drho_dt")
+
+    def e2e_step():
+        o = sc.slab.owned(fields + ("p",))                       # D2H of the rank's rows
+        sc.slab.reload(o)                                        # H2D of the owned rows (+ the static walls)
+        sc.exchange()                                            # halo copies over NCCL
+        sc.slab.step_end()                                       # list
+        sc.slab.step_begin()                                     # density .. continuity
+        return o
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    torch.cuda.synchronize()
+    ch.sync()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = pt.n_total * Ke / e2e_s
+    nl = n_owned + n_halo + n_wall
+    h2d = int(sum_over_ranks(float(n_owned * (16 + 16 + 8 + 8 + 8 + 4) + n_wall * 40)))
+    d2h = int(sum_over_ranks(float(nl * (16 + 16 + 8 + 8 + 8) + (n_owned + n_halo) * 4)))
+    # bring the slab back to a consistent "after step" state for the profile pass
+    sc.exchange()
+    sc.slab.step_end()
+
+    roof, kernels = None, {}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    ch.kernel_profile(enable=1, reset=True)
+    for _ in range(max(1, args.profile_steps)):
+        sc.step()
+    prof = ch.kernel_profile(enable=0, reset=True)
+    if rank == 0:
+        total = sum(ms for ms, _ in prof.values()) or 1.0
+        for name, (ms, calls) in prof.items():
+            if calls:
+                kernels[name] = {"ms_per_call": ms / calls, "calls": calls, "share": ms / total}
+        top = max((n for n in kernels if n in ALG_BYTES_KERNEL), key=lambda n: kernels[n]["share"])
+        achieved = ALG_BYTES_KERNEL[top] * nl / (kernels[top]["ms_per_call"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_particle": ALG_BYTES_KERNEL[top], "ms_per_launch": kernels[top]["ms_per_call"],
+                "share_of_step": kernels[top]["share"], "rows_per_launch": nl,
+                "step_frac": (value / world) * ALG_BYTES_SUBSTEP / (hbm * 1e9),
+                "kernel_ms_per_step_rank0": total / max(1, args.profile_steps)}
+    total_launches = sum_over_ranks(float(launches))
+    sc.close()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "particle-substeps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, pt, 1) + f", x-slab sharded over {world} GPUs "
+                                   f"({args.DL:g} of length per GPU)", "inner_substeps": 1,
+                       "list_rebuild": "every step (device counting sort + tile-local lists)",
+                       "cell_sort_interval": 0,
+                       "l2": ("256 MiB memset between timed steps" if flush is not None else
+                              "no flush: consecutive steps of one simulation"),
+                       "parallelism": f"x-slabs on cell-column boundaries, {slabmod.HALO_COLS} halo columns, one "
+                                      f"exchange per step (migration + halo copies: NCCL send/recv; max|v|, shear: "
+                                      f"all-reduce)",
+                       "rows_rank0": {"owned": n_owned, "halo": n_halo, "wall": n_wall}},
+            "e2e": {"value": e2e_value, "unit": "particle-substeps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": Ke,
+                    "path": "per rank: download rows -> sphb_ctx_slab_init (H2D) -> exchange -> list -> physics"},
+            "gpu_launches": int(total_launches),
+            "roofline": roof, "kernels": kernels, "cpu_baseline": None, "clocks": clocks,
+            "final_state": {"vmax": st["vmax"], "t": st["t"], "step": st["step"]},
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
     return 0
 
 

@@ -243,6 +243,8 @@ typedef struct sphb_kprof {
 SPHB_API int sphb_ctx_kernel_profile(sphb_ctx *ctx, int enable, int reset, sphb_kprof *out);
 /* The CUDA stream the context launches on (as a void* cudaStream_t), for event timing by callers. */
 SPHB_API void *sphb_ctx_stream(sphb_ctx *ctx);
+/* Launch on a stream of the caller (cudaStream_t as void*); NULL = back to the context's own stream. */
+SPHB_API int sphb_ctx_set_stream(sphb_ctx *ctx, void *stream);
 SPHB_API int sphb_ctx_sync(sphb_ctx *ctx);
 
 /* ================== 3. x-slab sharding of one long periodic channel ==================

@@ -122,7 +122,7 @@ constexpr int kDefaultEllRows = 48;
 enum ProfId : int {
     kPfNbrGrid = 0, kPfNbrBin, kPfNbrScan, kPfNbrScatter, kPfNbrCanon, kPfNbrWalk,
     kPfDensity, kPfKgc, kPfViscTransp, kPfTimeStep, kPfPressure, kPfContinuity, kPfClock,
-    kPfShear, kPfSort, kPfCount
+    kPfShear, kPfSort, kPfForceFused, kPfSlab, kPfCount
 };
 const char *prof_name(int id);
 

@@ -180,7 +180,7 @@ int do_fused_first_substep(sphb_ctx *c, double remain, double fixed_dt, bool wra
 {
     const StateView S = c->view();
     {
-        ProfScope ps(&c->kprof, kPfPressure, c->st);
+        ProfScope ps(&c->kprof, kPfForceFused, c->st);
         SPHB_TRY(csr_force_fused(c->P, S, c->sc(), remain, fixed_dt, true, c->st));
     }
     {
@@ -299,6 +299,7 @@ SPHB_API void sphb_ctx_destroy(sphb_ctx *c)
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     drop_graphs(c);
+    if (c->own_st) c->st = c->own_st;   // never destroy a stream of the caller
     DevBuf *all[] = {&c->pos, &c->vel, &c->vel_new, &c->wall_vel, &c->force, &c->force_prior, &c->rho, &c->p,
                      &c->drho_dt, &c->mass, &c->Vol, &c->B, &c->a_pos, &c->a_vel, &c->a_wall_vel, &c->a_force,
                      &c->a_force_prior, &c->a_rho, &c->a_p, &c->a_drho_dt, &c->a_mass, &c->a_Vol, &c->a_B,
@@ -754,6 +755,19 @@ SPHB_API int sphb_ctx_kernel_profile(sphb_ctx *c, int enable, int reset, sphb_kp
 }
 
 SPHB_API void *sphb_ctx_stream(sphb_ctx *c) { return c ? (void *)c->st : nullptr; }
+
+// Launch on a stream of the caller (e.g. torch's current stream, so that NCCL collectives issued through
+// torch.distributed are ordered with the library's kernels without host synchronisation).  NULL restores
+// the context's own stream.  Cached graphs are dropped.
+SPHB_API int sphb_ctx_set_stream(sphb_ctx *c, void *stream)
+{
+    CTX_ENTER(false);
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    drop_graphs(c);
+    if (!c->own_st) c->own_st = c->st;
+    c->st = stream ? (cudaStream_t)stream : c->own_st;
+    return 0;
+}
 
 SPHB_API int sphb_ctx_sync(sphb_ctx *c)
 {

@@ -46,7 +46,7 @@ const char *prof_name(int id)
     static const char *names[kPfCount] = {"nbr_grid", "nbr_bin_count", "nbr_scan", "nbr_scatter", "nbr_cell_canon",
                                           "nbr_walk", "density", "kgc",
                                           "visc_transport", "time_step", "pressure", "continuity", "clock",
-                                          "wall_shear", "cell_sort"};
+                                          "wall_shear", "cell_sort", "force_fused", "slab_exchange"};
     return (id >= 0 && id < kPfCount) ? names[id] : "?";
 }
 

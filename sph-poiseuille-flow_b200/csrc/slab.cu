@@ -374,10 +374,11 @@ SPHB_API int sphb_ctx_slab_init(sphb_ctx *c, int col_lo, int col_hi, int halo_co
     clear_error();
     if (!c) return set_error("SPHB:arg", "null context");
     SPHB_TRY(ctx_bind_device(c));
-    const int nf_cap = c->prm.n_fluid;
+    const bool again = c->slab.on;   // re-initialisation keeps the capacity of the first one
+    const int nf_cap = again ? c->slab.nf_cap : c->prm.n_fluid;
     const int ncx_g = std::max(1, (int)std::ceil(c->prm.DL / (2.0 * c->prm.h)));   // nb:254
     if (col_lo < 0 || col_hi <= col_lo || col_hi > ncx_g || halo_cols < 1 || n_owned < 0 || n_owned > nf_cap ||
-        n_wall < 0 || nf_cap + n_wall != c->prm.n_total)
+        n_wall < 0 || (again ? n_wall != c->slab.n_wall : nf_cap + n_wall != c->prm.n_total))
         return set_error("SPHB:arg", "bad slab description");
     if (col_hi - col_lo < halo_cols || ncx_g < (col_hi - col_lo) + 2 * halo_cols + 2)
         return set_error("SPHB:arg", "slab of %d columns with %d halo columns does not fit a channel of %d columns",
@@ -456,6 +457,7 @@ SPHB_API int sphb_ctx_slab_pack(sphb_ctx *c, double *send_left_dev, double *send
     const SlabGeom G = geom_of(c);
     const unsigned blocks = std::max(1u, grid_for((size_t)s.n_owned, kSlabBlock));
     int *bt = s.block_tot.as<int>(), *cnt = s.counts.as<int>();
+    ProfScope ps(&c->kprof, kPfSlab, c->st);
     k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), G, bt);
     k_slab_offsets<<<1, 1024, 0, c->st>>>(bt, (int)blocks, cnt);
     k_slab_scatter<<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, bt, cnt, send_left_dev, send_right_dev, rec_cap,
@@ -478,12 +480,15 @@ SPHB_API int sphb_ctx_slab_unpack(sphb_ctx *c, const double *recv_left_dev, cons
     U.buf[3] = sent_right_dev;
     int *cnt = s.counts.as<int>();
     const SlabArrays A = arrays_of(c);
+    {
+    ProfScope ps(&c->kprof, kPfSlab, c->st);
     k_slab_unpack<<<148 * 2, kSlabBlock, 0, c->st>>>(U, A, G, rec_cap, s.nf_cap, c->prm.rho0, c->prm.p0,
                                                      c->a_p.as<double>(), c->a_wall_vel.as<double2>(), cnt,
                                                      c->nw.flags.as<int>());
     k_slab_walls<<<148 * 2, kSlabBlock, 0, c->st>>>(cnt, s.nf_cap, s.n_wall, s.w_pos.as<double2>(), s.w_mass.as<double>(),
                                                     s.w_wall_vel.as<double2>(), c->prm.rho0, c->prm.p0, A,
                                                     c->a_wall_vel.as<double2>(), c->a_p.as<double>());
+    }
     c->launches += 2;
     SPHB_CUDA(cudaMemcpyAsync(s.h_counts, cnt, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     SPHB_CUDA(cudaStreamSynchronize(c->st));

@@ -142,6 +142,24 @@ class Slab:
         res["ids"] = ids[:n_owned]
         return res
 
+    def reload(self, rows):
+        """Re-initialise the slab from host rows (as returned by owned()): the H2D leg of an end-to-end step."""
+        n_owned = rows["pos"].shape[0]
+        keep = dict(ids=np.ascontiguousarray(rows["ids"], dtype=np.int32),
+                    pos=np.asfortranarray(rows["pos"]), vel=np.asfortranarray(rows["vel"]),
+                    rho=np.ascontiguousarray(rows["rho"]), drho_dt=np.ascontiguousarray(rows["drho_dt"]))
+        mass = np.full(n_owned, self.cfg.rho0 * self.cfg.dp * self.cfg.dp) if "mass" not in rows else rows["mass"]
+        keep["mass"] = np.ascontiguousarray(mass)
+        part = self._keep
+        n_wall = part["wall_pos"].shape[0]
+        self.ch.prm.n_fluid, self.ch.prm.n_total = self.nf_cap, self.nf_cap + n_wall
+        self._rows = keep
+        _check(lib().sphb_ctx_slab_init(
+            self.ch._ctx, C.c_int(self.col_lo), C.c_int(self.col_hi), C.c_int(self.halo), C.c_int(n_owned),
+            _p(keep["pos"]), _p(keep["vel"]), _p(keep["rho"]), _p(keep["drho_dt"]), _p(keep["mass"]),
+            keep["ids"].ctypes.data_as(_IP), C.c_int(n_wall), _p(part["wall_pos"]), _p(part["wall_mass"]),
+            _p(part["wall_wall_vel"])))
+
     def close(self):
         self.ch.close()
 
@@ -206,8 +224,10 @@ class SlabGroup:
 
 
 class SlabChannel:
-    """One rank of the sharded channel: its slab, and the exchange over torch.distributed
-    (backend "nccl": send/recv over NVLink; "gloo" works for the host-side logic with CPU staging)."""
+    """One rank of the sharded channel: its slab, and the exchange over torch.distributed (backend "nccl":
+    send/recv over NVLink).  The library launches on torch's current stream, so its kernels and the NCCL
+    operations are stream-ordered; the only host synchronisation of a step is the read-back of the new
+    row counts in unpack."""
 
     def __init__(self, cfg, pt, rank: int, world: int, device, **kw):
         import torch
@@ -216,15 +236,26 @@ class SlabChannel:
         self.rank, self.world = rank, world
         lo, hi = partition_columns(n_columns(cfg), world)[rank]
         self.slab = Slab(cfg, pt, lo, hi, device, **kw)
+        s = self.slab
         self.left, self.right = (rank - 1) % world, (rank + 1) % world
-        self.tau = (0.0, 0.0)
+        self.stream = torch.cuda.Stream(device=s.device)     # shared by the library's kernels and torch / NCCL
+        _check(lib().sphb_ctx_set_stream(s.ch._ctx, C.c_void_p(self.stream.cuda_stream)))
+        self._gath = torch.zeros(world * 3, dtype=torch.float64, device=s.device)
+        self._tau = torch.zeros(2, dtype=torch.float64, device=s.device)
         self.exchange()
-        self.slab.step_end()
+        s.step_end()
+
+    @property
+    def tau(self):
+        return tuple(float(v) for v in self._tau.tolist())
 
     def exchange(self):
-        torch, dist, s = self.torch, self.dist, self.slab
+        with self.torch.cuda.stream(self.stream):
+            self._exchange()
+
+    def _exchange(self):
+        dist, s = self.dist, self.slab
         s.pack()
-        s.ch.sync()                      # the library launches on its own stream
         if self.world == 1:
             s.recv_left.copy_(s.send_right)
             s.recv_right.copy_(s.send_left)
@@ -233,22 +264,21 @@ class SlabChannel:
             # messages travel between the same pair, matched in posting order
             ops = [dist.P2POp(dist.isend, s.send_left, self.left), dist.P2POp(dist.isend, s.send_right, self.right),
                    dist.P2POp(dist.irecv, s.recv_right, self.right), dist.P2POp(dist.irecv, s.recv_left, self.left)]
-            for w in dist.batch_isend_irecv(ops):
+            works = dist.batch_isend_irecv(ops)
+            # max|v| -> time step of the next step (m:519-527); wall-shear partials (ph:1713-1742): one collective
+            dist.all_gather_into_tensor(self._gath, s.scal[0:3])
+            for w in works:
                 w.wait()
-            vmax = s.scal[0:1].clone()
-            tau = s.scal[1:3].clone()
-            dist.all_reduce(vmax, op=dist.ReduceOp.MAX)     # time step of the next step (m:519-527)
-            dist.all_reduce(tau, op=dist.ReduceOp.SUM)      # wall-shear partials (ph:1713-1742)
-            s.scal[0:1] = vmax
-            s.scal[1:3] = tau
-        torch.cuda.current_stream(s.device).synchronize()
-        self.tau = (float(s.scal[1]), float(s.scal[2])) if False else self.tau
+            g = self._gath.view(self.world, 3)
+            s.scal[0:1] = g[:, 0].max().reshape(1)
+            self._tau.copy_(g[:, 1:3].sum(dim=0))
         s.unpack()
 
     def step(self, remain=float("inf")):
-        self.slab.step_begin(remain)
-        self.exchange()
-        self.slab.step_end()
+        with self.torch.cuda.stream(self.stream):
+            self.slab.step_begin(remain)
+            self._exchange()
+            self.slab.step_end()
 
     def close(self):
         self.slab.close()
