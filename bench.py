@@ -290,22 +290,24 @@ def b200_arm(args):
 
     # ---- end to end through the C ABI with host buffers --------------------------------------------
     Ke = max(1, min(args.e2e_steps, K))
-    host = {k: torch.empty(shape, dtype=torch.float64).pin_memory().numpy()
-            for k, shape in (("pos", (2, nt)), ("vel", (2, nt)), ("rho", (nt,)), ("drho_dt", (nt,)))}
-    host = {k: (v.T if v.ndim == 2 else v) for k, v in host.items()}      # [nt, 2] column-major views
-    d = ch.download(("pos", "vel", "rho", "drho_dt"))
-    for k in host:
-        host[k][...] = d[k]
-    out_fields = ("pos", "vel", "rho", "p", "drho_dt", "force")
+
+    def pinned(cols):
+        t = torch.empty((cols, nt) if cols > 1 else (nt,), dtype=torch.float64).pin_memory().numpy()
+        return t.T if cols > 1 else t                                  # [nt, cols] column-major view
+    in_fields = (("pos", 2), ("vel", 2), ("rho", 1), ("drho_dt", 1))
+    out_fields = (("pos", 2), ("vel", 2), ("rho", 1), ("p", 1), ("drho_dt", 1), ("force", 2))
+    host = {k: pinned(c) for k, c in in_fields}                        # pinned inputs of a step
+    outs = {k: pinned(c) for k, c in out_fields}                       # pinned results of a step
+    ch.download_into(host)
 
     def e2e_step():
         ch.upload(pos=host["pos"], vel=host["vel"], rho=host["rho"], drho_dt=host["drho_dt"])
         ch.neighbor_build()
         ch.run_dual(1, inner)
-        o = ch.download(out_fields)
-        for k in host:
-            host[k][...] = o[k]
-        return o
+        ch.download_into(outs)
+        for k in host:                                                 # the results are the next step's inputs
+            host[k], outs[k] = outs[k], host[k]
+        return outs
 
     for _ in range(2):
         e2e_step()

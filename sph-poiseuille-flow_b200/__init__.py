@@ -343,6 +343,19 @@ class Channel:
         _check(lib().sphb_ctx_download(self._ctx, *[(_p(out[k]) if k in out else None) for k in order]))
         return out
 
+    def download_into(self, out: dict):
+        """Like download(), but into arrays of the caller (column-major float64 of the right shape, e.g.
+        pinned host memory): no allocation, no extra copy."""
+        order = ("pos", "vel", "rho", "p", "drho_dt", "force", "force_prior", "Vol", "B")
+        cols = dict(pos=2, vel=2, rho=1, p=1, drho_dt=1, force=2, force_prior=2, Vol=1, B=4)
+        nt = self.prm.n_total
+        for k, a in out.items():
+            want = (nt, cols[k]) if cols[k] > 1 else (nt,)
+            if a.dtype != np.float64 or a.shape != want or not (a.flags.f_contiguous or a.ndim == 1):
+                raise SphError("SPHB:arg", f"download_into: {k} must be a column-major float64 array of shape {want}")
+        _check(lib().sphb_ctx_download(self._ctx, *[(_p(out[k]) if k in out else None) for k in order]))
+        return out
+
     def set_time(self, t: float, step: int):
         _check(lib().sphb_ctx_set_time(self._ctx, C.c_double(t), C.c_longlong(step)))
 

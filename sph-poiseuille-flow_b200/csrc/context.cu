@@ -276,7 +276,7 @@ SPHB_API int sphb_ctx_create(const sphb_params *prm, sphb_ctx **out)
         SPHB_TRY(c->a_B.reserve(nt * sizeof(Mat2)));
         SPHB_TRY(c->scalars.reserve(sizeof(DevScalars)));
         SPHB_CUDA(cudaMemsetAsync(c->scalars.p, 0, sizeof(DevScalars), c->st));
-        SPHB_TRY(c->stage.reserve(4 * nt * sizeof(double)));
+        SPHB_TRY(c->stage.reserve(6 * nt * sizeof(double)));   // three 2-column (or one 4- + one 2-column) arrays in flight
         k_fill<<<grid_for(nt), kBlock, 0, c->st>>>(c->rho.as<double>(), prm->rho0, (int)nt);
         k_fill_identity<<<grid_for(nt), kBlock, 0, c->st>>>(c->B.as<Mat2>(), (int)nt);
         SPHB_CUDA(cudaMallocHost((void **)&c->h_scalars, sizeof(DevScalars)));
@@ -328,11 +328,13 @@ SPHB_API int sphb_ctx_upload(sphb_ctx *c, const double *pos, const double *vel, 
     SPHB_TRY(bind_device(c));
     const int nt = c->prm.n_total;
     const size_t n = (size_t)nt;
+    // every 2-column array has its own staging region: the copies and the pack kernels queue back to back
     double *stage = c->stage.as<double>();
+    int region = 0;
     auto up2 = [&](const double *src, DevBuf &dst) -> int {
-        SPHB_CUDA(cudaMemcpyAsync(stage, src, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->st));
-        launch_pack2(stage, dst.as<double2>(), nt, c->st);
-        SPHB_CUDA(cudaStreamSynchronize(c->st));   // `stage` is reused by the next array
+        double *st2 = stage + (size_t)(region++) * 2 * n;
+        SPHB_CUDA(cudaMemcpyAsync(st2, src, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        launch_pack2(st2, dst.as<double2>(), nt, c->st);
         return 0;
     };
     if (pos) {
@@ -370,10 +372,15 @@ SPHB_API int sphb_ctx_download(sphb_ctx *c, double *pos, double *vel, double *rh
     const int nt = c->prm.n_total;
     const size_t n = (size_t)nt;
     double *stage = c->stage.as<double>();
+    int region = 0;
     auto down2 = [&](const DevBuf &src, double *dst) -> int {
-        launch_unpack2(src.as<double2>(), stage, nt, c->st);
-        SPHB_CUDA(cudaMemcpyAsync(dst, stage, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-        SPHB_CUDA(cudaStreamSynchronize(c->st));
+        if (region >= 3) {   // the three staging regions are in flight: drain before reusing them
+            SPHB_CUDA(cudaStreamSynchronize(c->st));
+            region = 0;
+        }
+        double *st2 = stage + (size_t)(region++) * 2 * n;
+        launch_unpack2(src.as<double2>(), st2, nt, c->st);
+        SPHB_CUDA(cudaMemcpyAsync(dst, st2, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
         return 0;
     };
     if (pos) SPHB_TRY(down2(c->pos, pos));
@@ -381,9 +388,9 @@ SPHB_API int sphb_ctx_download(sphb_ctx *c, double *pos, double *vel, double *rh
     if (force) SPHB_TRY(down2(c->force, force));
     if (force_prior) SPHB_TRY(down2(c->force_prior, force_prior));
     if (B) {
+        SPHB_CUDA(cudaStreamSynchronize(c->st));
         launch_unpack4(c->B.as<Mat2>(), stage, nt, c->st);
         SPHB_CUDA(cudaMemcpyAsync(B, stage, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-        SPHB_CUDA(cudaStreamSynchronize(c->st));
     }
     if (rho) SPHB_CUDA(cudaMemcpyAsync(rho, c->rho.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     if (p) SPHB_CUDA(cudaMemcpyAsync(p, c->p.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));

@@ -401,10 +401,9 @@ __device__ __forceinline__ int stencil_rank(int cx, int cxi, int ncx)
 // higher-kind entry first (list order = reverse insertion), first accepted entry wins.  Returns the
 // image shift of x_high as seen from the low particle, or kNoPair when the pair is not accepted.
 constexpr int kNoPair = 99;
-__device__ int replay_low_walk(double xl, double yl, int home_l, double xh, double yh, int home_h, int ncy,
+__device__ int replay_low_walk(double xl, double yl, int home_l, const Entries &E, double yh, int ncy,
                                const NbrParams &P)
 {
-    const Entries E = entries_of(xh, home_h, P);
     const int cxl = home_l % P.ncx, cyl = home_l / P.ncx;
     if (E.cy < cyl - 1 || E.cy > cyl + 1 || E.cy < 0 || E.cy >= ncy) return kNoPair;
     int cx_prev[2] = {-1, -1};
@@ -485,8 +484,149 @@ __device__ __forceinline__ unsigned walk_tile_of_block(unsigned b, int tpr, unsi
     return (r / (unsigned)(tpr - 2)) * (unsigned)tpr + 1u + r % (unsigned)(tpr - 2);
 }
 
+// The general walk of ONE walker (columns 0, ncx-2, ncx-1: ghost entries, particles that own ghosts, the
+// periodic wrap), executed by a whole warp: the walker's candidates, enumerated in the reference's walk
+// order, are spread over the lanes; each lane decides its candidate on its own -- the seen_neighbor dedup
+// (nb:342,383) is a function of the walk positions of the (at most three) entries of the other particle,
+// not of a per-walker table -- and a ballot compacts the accepted entries, in walk order, into the row.
 template <bool HALF>
-__global__ void __launch_bounds__(kTileThreads) k_walk_tile(NbrParams P, const GridDesc *__restrict__ g,
+__device__ __forceinline__ int general_walk(const NbrParams &P, const TileDesc &T, const double2 *s_xy,
+                                            const int *s_key, const double2 *__restrict__ snap,
+                                            const int *__restrict__ cell_of, int ncy, int ew, int slot_i, int orow,
+                                            int cxi, unsigned short *row_sm, uint4 *ell_q, int *__restrict__ cnt,
+                                            int dummy)
+{
+    const int lane = threadIdx.x & 31;
+    const int ncx = P.ncx;
+    const int i = s_key[slot_i] >> 3;
+    const double2 pi = s_xy[slot_i];
+    const int cyi = T.cy0 + orow, ri = orow + 1;
+    const int home = cyi * ncx + cxi;
+    const Entries Ei = entries_of(pi.x, home, P);
+    // does i itself own ghost entries?  (then a lower fluid index may have met one of them)
+    const bool i_multi = (pi.x > P.DL - P.cutoff || pi.x < P.cutoff) && ncx > 1;
+    // the nine stencil cells in walk order (oy, ox), as slot ranges
+    int rb[9], rn[9], rcx[9];
+    int total = 0;
+#pragma unroll
+    for (int oy = -1; oy <= 1; ++oy) {
+        const int cy = cyi + oy;
+        int cx_prev[2] = {-1, -1};
+#pragma unroll
+        for (int ox = -1; ox <= 1; ++ox) {
+            const int k = (oy + 1) * 3 + (ox + 1);
+            int cx = cxi + ox;
+            if (cx < 0) cx += ncx;
+            else if (cx >= ncx) cx -= ncx;
+            rb[k] = 0;
+            rn[k] = 0;
+            rcx[k] = cx;
+            if (cy < 0 || cy >= ncy || cx < 0 || cx >= ncx) continue;
+            // n_cell_x <= 2: the wrapped stencil revisits a column.  The reference re-walks it, but every
+            // entry it accepted is already in seen_neighbor and every entry it rejected is rejected again
+            // by the same arithmetic (nb:342-372), so the revisit emits nothing.
+            if (cx == cx_prev[0] || cx == cx_prev[1]) continue;
+            cx_prev[ox == -1 ? 0 : 1] = cx;
+            int sb, se;
+            tile_cell_slots(T, ri + oy, cx, ncx, sb, se);
+            rb[k] = sb;
+            rn[k] = se - sb;
+            total += se - sb;
+        }
+    }
+    int count = 0;
+    for (int base = 0; base < total; base += 32) {
+        const int t = base + lane;
+        bool acc = false;
+        int s = 0, m = 0;
+        if (t < total) {
+            int cx = 0, cy = 0, pre = 0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                if (t >= pre && t < pre + rn[k]) {
+                    s = rb[k] + (t - pre);
+                    cx = rcx[k];
+                    cy = cyi + k / 3 - 1;
+                }
+                pre += rn[k];
+            }
+            const int rank_col = stencil_rank(cx, cxi, ncx);
+            const int key = s_key[s];   // entries are stored last-inserted first
+            const int j = key >> 3;
+            const bool low_fluid = j < P.n_fluid && j < i;
+            if (j != i && !(HALF && low_fluid)) {                                  // nb:353
+                const bool seam = (key & 4) || (low_fluid && i_multi);
+                const double2 pe = s_xy[s];
+                if (!seam) {
+                    acc = accept_entry(pi.x, pi.y, pe.x, pe.y, P, m);
+                } else {
+                    // j has up to three entries; the ones the walk reaches BEFORE this one decide whether
+                    // j is already in the row (seen_neighbor, nb:342).  A real entry is j's wrapped position
+                    // in j's home cell: only ghosts look them up.
+                    const int kind = key & 3;
+                    const double2 pj = kind == 0 ? pe : snap[j];
+                    const int home_j = kind == 0 ? cy * ncx + cx : cell_of[j];
+                    const Entries E = entries_of(pj.x, home_j, P);
+                    const int rank_cur = rank_col * 3 + (2 - kind);
+                    if (low_fluid) {
+                        // the pair is decided by j's walk: the first entry of j the walk meets carries it
+                        bool first = true;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            if (k == kind || E.cx[k] < 0) continue;
+                            const int rk = stencil_rank(E.cx[k], cxi, ncx);
+                            if (rk >= 0 && rk * 3 + (2 - k) < rank_cur) first = false;
+                        }
+                        if (first) {
+                            const int sh = replay_low_walk(pj.x, pj.y, home_j, Ei, pi.y, ncy, P);
+                            if (sh != kNoPair) {
+                                acc = true;
+                                m = -sh + (kind == 1 ? -1 : (kind == 2 ? 1 : 0));   // relative to the entry met
+                            }
+                        }
+                    } else if (accept_entry(pi.x, pi.y, pe.x, pe.y, P, m)) {
+                        bool dup = false;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            if (k == kind || E.cx[k] < 0) continue;
+                            const int rk = stencil_rank(E.cx[k], cxi, ncx);
+                            if (rk >= 0 && rk * 3 + (2 - k) < rank_cur) {
+                                int m2;
+                                dup |= accept_entry(pi.x, pi.y, E.x[k], pj.y, P, m2);
+                            }
+                        }
+                        acc = !dup;
+                    }
+                }
+            }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, acc);
+        if (acc) {
+            const int pos = count + __popc(mask & ((1u << lane) - 1u));
+            if (pos < P.ell_cap) row_sm[pos] = (unsigned short)ell_pack(s, m);
+        }
+        count += __popc(mask);
+    }
+    __syncwarp();
+    const int nw = min((count + 7) >> 3, P.ell_cap >> 3);
+    for (int w = lane; w < nw; w += 32) {
+        unsigned e[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = (8 * w + k < count) ? (unsigned)row_sm[8 * w + k] : ell_pack(dummy, 0);
+        uint4 q;
+        q.w = (e[0] << 16) | e[1];
+        q.z = (e[2] << 16) | e[3];
+        q.y = (e[4] << 16) | e[5];
+        q.x = (e[6] << 16) | e[7];
+        ell_q[(size_t)w * P.ell_stride + ew] = q;
+    }
+    if (lane == 0) cnt[ew] = count;
+    __syncwarp();
+    return count;
+}
+
+template <bool HALF>
+__global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, const GridDesc *__restrict__ g,
                                                            const TileDesc *__restrict__ tiles, int tile_w,
                                                            const double2 *__restrict__ snap,
                                                            const int *__restrict__ cell_of,
@@ -514,162 +654,123 @@ __global__ void __launch_bounds__(kTileThreads) k_walk_tile(NbrParams P, const G
     const int qcap = P.ell_cap >> 3;
     const bool seam_tile = (T.flags & kTileSeam) != 0;
     const int dummy = T.n_staged;
+    const int lane = threadIdx.x & 31;
+    __shared__ int gq[kTileThreads];   // own-entry indices of the queued general walkers
+    __shared__ int gq_n;
+    if (threadIdx.x == 0) gq_n = 0;
+    __syncthreads();
+    unsigned short *row_sm = reinterpret_cast<unsigned short *>(s_key + cap) + (size_t)(threadIdx.x >> 5) * P.ell_cap;
     int t_full = 0, t_max = 0;
-    SPHB_TILE_FOR_OWN(T, ew, slot_i, orow)
-    {
-        if ((size_t)ew >= stride) {   // more entries than list columns: reported, never written
-            atomicOr(flags, kErrCsrCap);
-            continue;
-        }
-        const int key_i = s_key[slot_i];
-        const int i = key_i >> 3;
-        if ((key_i & 3) != 0 || i >= P.n_fluid) {   // ghost or wall entry: not a walker
-            cnt[ew] = 0;
-            continue;
-        }
-        const double2 pi = s_xy[slot_i];
-        const int cyi = T.cy0 + orow;
-        const int ri = orow + 1;   // staged row of the walker
-        RowWriter row;
-        row.init(ell_q + ew, stride, qcap);
-        // the walker's column: binary search of its entry in the staged cell starts of its row
-        int cxi;
-        {
-            int lo = T.cx0 - T.a, hi = T.cx1 - T.a;   // cs[ri][lo] <= ew < cs[ri][hi]
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (T.cs[ri][mid] <= ew) lo = mid;
-                else hi = mid;
-            }
-            cxi = T.a + lo;
-        }
-        const bool interior = cxi >= 1 && cxi <= ncx - 3 && ncx >= 6;
-        if (!seam_tile && !interior) {   // slab mode: a particle clamped into the empty margin columns
-            cnt[ew] = 0;
-            continue;
-        }
-        if (interior) {
-            // ---- interior walker: per stencil row one contiguous slot range; first a branch-free pass
-            // that records the accepted candidates as a bit mask, then the mask is unrolled into the row
-#pragma unroll 1
-            for (int r = ri - 1; r <= ri + 1; ++r) {
-                const int cy = cyi + (r - ri);
-                if (cy < 0 || cy >= ncy) continue;
-                const int k0 = cxi - 1 - T.a;
-                const int c0 = T.cs[r][k0];
-                const int sb = T.seg[3 * r].off + (c0 - T.seg[3 * r].b);
-                const int se = sb + (T.cs[r][k0 + 3] - c0);
-#pragma unroll 1
-                for (int s0 = sb; s0 < se; s0 += 32) {
-                    const int s1 = min(s0 + 32, se);
-                    unsigned mask = 0u, edge = 0u, bit = 1u;
-                    for (int s = s0; s < s1; ++s, bit <<= 1) {
-                        const double2 pj = s_xy[s];
-                        const double dx = pi.x - pj.x;
-                        const double dy = pi.y - pj.y;
-                        const double r2 = dx * dx + dy * dy;
-                        const bool in = r2 > 1e-24 && r2 < P.rc2;       // also rejects the walker itself
-                        mask |= in ? bit : 0u;
-                        edge |= (in && !(r2 < P.rc2_safe)) ? bit : 0u;
+    const int n_own = tile_own_total(T);
+    for (int base = 0; base < n_own; base += kTileThreads) {   // warp-uniform trip count (collectives below)
+        const int v = base + (int)threadIdx.x;
+        bool general = false;   // this lane's walker takes the warp-cooperative general walk
+        int ew = 0, slot_i = 0, orow = 0, cxi = 0;
+        if (v < n_own) {
+            tile_own_locate(T, v, orow, ew, slot_i);
+            const int key_i = s_key[slot_i];
+            const int i = key_i >> 3;
+            if ((size_t)ew >= stride) {   // more entries than list columns: reported, never written
+                atomicOr(flags, kErrCsrCap);
+            } else if ((key_i & 3) != 0 || i >= P.n_fluid) {   // ghost or wall entry: not a walker
+                cnt[ew] = 0;
+            } else {
+                const int ri = orow + 1;   // staged row of the walker
+                {   // the walker's column: binary search of its entry in the staged cell starts of its row
+                    int lo = T.cx0 - T.a, hi = T.cx1 - T.a;   // cs[ri][lo] <= ew < cs[ri][hi]
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (T.cs[ri][mid] <= ew) lo = mid;
+                        else hi = mid;
                     }
-                    while (edge) {   // last 1e-12 below the cut-off: the reference's kernel-support test
-                        const int k = __ffs((int)edge) - 1;
-                        edge &= edge - 1;
-                        const double2 pj = s_xy[s0 + k];
-                        const double dx = pi.x - pj.x;
-                        const double dy = pi.y - pj.y;
-                        if (!support_exact(dx * dx + dy * dy, P)) mask &= ~(1u << k);
-                    }
-                    while (mask) {
-                        const int k = __ffs((int)mask) - 1;
-                        mask &= mask - 1;
-                        if (HALF) {
-                            const int j = s_key[s0 + k] >> 3;
-                            if (j < P.n_fluid && j < i) continue;   // nb:353
-                        }
-                        row.push(s0 + k, 0);
-                    }
+                    cxi = T.a + lo;
                 }
-            }
-        } else {
-            // ---- general walker (periodic seam)
-            const int home = cyi * ncx + cxi;
-            // does i itself own ghost entries?  (then a lower fluid index may have met one of them)
-            const bool i_multi = (pi.x > P.DL - P.cutoff || pi.x < P.cutoff) && ncx > 1;
-            for (int oy = -1; oy <= 1; ++oy) {
-                const int cy = cyi + oy;
-                if (cy < 0 || cy >= ncy) continue;
-                int cx_prev[2] = {-1, -1};
-                for (int ox = -1; ox <= 1; ++ox) {
-                    int cx = cxi + ox;
-                    if (cx < 0) cx += ncx;
-                    else if (cx >= ncx) cx -= ncx;
-                    if (cx < 0 || cx >= ncx) continue;
-                    // n_cell_x <= 2: the wrapped stencil revisits a column.  The reference re-walks it, but
-                    // every entry it accepted is already in seen_neighbor and every entry it rejected is
-                    // rejected again by the same arithmetic (nb:342-372), so the revisit emits nothing.
-                    if (cx == cx_prev[0] || cx == cx_prev[1]) continue;
-                    cx_prev[ox == -1 ? 0 : 1] = cx;
-                    int sb, se;
-                    tile_cell_slots(T, ri + oy, cx, ncx, sb, se);
-                    const int rank_col = stencil_rank(cx, cxi, ncx);
-                    for (int s = sb; s < se; ++s) {   // entries are stored last-inserted first
-                        const int key = s_key[s];
-                        const int j = key >> 3;
-                        if (j == i) continue;
-                        const bool low_fluid = j < P.n_fluid && j < i;
-                        if (HALF && low_fluid) continue;                       // nb:353
-                        const bool seam = (key & 4) || (low_fluid && i_multi);
-                        const double2 pe = s_xy[s];
-                        int m;
-                        if (!seam) {
-                            if (!accept_entry(pi.x, pi.y, pe.x, pe.y, P, m)) continue;
-                        } else {
-                            // j has up to three entries; the ones the walk reaches BEFORE this one decide
-                            // whether j is already in the row (seen_neighbor, nb:342)
-                            // (a real entry is j's wrapped position in j's home cell: only ghosts look them up)
-                            const int kind = key & 3;
-                            const double2 pj = kind == 0 ? pe : snap[j];
-                            const int home_j = kind == 0 ? cy * ncx + cx : cell_of[j];
-                            const Entries E = entries_of(pj.x, home_j, P);
-                            const int rank_cur = rank_col * 3 + (2 - kind);
-                            if (low_fluid) {
-                                // the pair is decided by j's walk: the first entry of j the walk meets carries it
-                                bool first = true;
-#pragma unroll
-                                for (int k = 0; k < 3; ++k) {
-                                    if (k == kind || E.cx[k] < 0) continue;
-                                    const int rk = stencil_rank(E.cx[k], cxi, ncx);
-                                    if (rk >= 0 && rk * 3 + (2 - k) < rank_cur) first = false;
+                const bool interior = cxi >= 1 && cxi <= ncx - 3 && ncx >= 6;
+                if (!seam_tile && !interior) {   // slab mode: a particle clamped into the empty margin columns
+                    cnt[ew] = 0;
+                } else if (!interior) {
+                    general = true;
+                } else {
+                    // ---- interior walker: per stencil row one contiguous slot range; first a branch-free
+                    // pass that records the accepted candidates as a bit mask, then the mask is unrolled
+                    // into the row
+                    const double2 pi = s_xy[slot_i];
+                    const int cyi = T.cy0 + orow;
+                    RowWriter row;
+                    row.init(ell_q + ew, stride, qcap);
+#pragma unroll 1
+                    for (int r = ri - 1; r <= ri + 1; ++r) {
+                        const int cy = cyi + (r - ri);
+                        if (cy < 0 || cy >= ncy) continue;
+                        const int k0 = cxi - 1 - T.a;
+                        const int c0 = T.cs[r][k0];
+                        const int sb = T.seg[3 * r].off + (c0 - T.seg[3 * r].b);
+                        const int se = sb + (T.cs[r][k0 + 3] - c0);
+#pragma unroll 1
+                        for (int s0 = sb; s0 < se; s0 += 32) {
+                            const int s1 = min(s0 + 32, se);
+                            unsigned mask = 0u, edge = 0u, bit = 1u;
+                            for (int s = s0; s < s1; ++s, bit <<= 1) {
+                                const double2 pj = s_xy[s];
+                                const double dx = pi.x - pj.x;
+                                const double dy = pi.y - pj.y;
+                                const double r2 = dx * dx + dy * dy;
+                                const bool in = r2 > 1e-24 && r2 < P.rc2;       // also rejects the walker itself
+                                mask |= in ? bit : 0u;
+                                edge |= (in && !(r2 < P.rc2_safe)) ? bit : 0u;
+                            }
+                            while (edge) {   // last 1e-12 below the cut-off: the reference's kernel-support test
+                                const int k = __ffs((int)edge) - 1;
+                                edge &= edge - 1;
+                                const double2 pj = s_xy[s0 + k];
+                                const double dx = pi.x - pj.x;
+                                const double dy = pi.y - pj.y;
+                                if (!support_exact(dx * dx + dy * dy, P)) mask &= ~(1u << k);
+                            }
+                            while (mask) {
+                                const int k = __ffs((int)mask) - 1;
+                                mask &= mask - 1;
+                                if (HALF) {
+                                    const int j = s_key[s0 + k] >> 3;
+                                    if (j < P.n_fluid && j < i) continue;   // nb:353
                                 }
-                                if (!first) continue;
-                                const int sh = replay_low_walk(pj.x, pj.y, home_j, pi.x, pi.y, home, ncy, P);
-                                if (sh == kNoPair) continue;
-                                m = -sh + (kind == 1 ? -1 : (kind == 2 ? 1 : 0));   // relative to the entry met
-                            } else {
-                                if (!accept_entry(pi.x, pi.y, pe.x, pe.y, P, m)) continue;
-                                bool dup = false;
-#pragma unroll
-                                for (int k = 0; k < 3; ++k) {
-                                    if (k == kind || E.cx[k] < 0) continue;
-                                    const int rk = stencil_rank(E.cx[k], cxi, ncx);
-                                    if (rk >= 0 && rk * 3 + (2 - k) < rank_cur) {
-                                        int m2;
-                                        dup |= accept_entry(pi.x, pi.y, E.x[k], pj.y, P, m2);
-                                    }
-                                }
-                                if (dup) continue;
+                                row.push(s0 + k, 0);
                             }
                         }
-                        row.push(s, m);
                     }
+                    row.finish(dummy);
+                    cnt[ew] = row.count;
+                    t_full += row.count;
+                    t_max = max(t_max, row.count);
                 }
             }
         }
-        row.finish(dummy);
-        cnt[ew] = row.count;
-        t_full += row.count;
-        t_max = max(t_max, row.count);
+        // ---- general walkers (periodic seam): queued for the whole CTA, so that the few warps that own
+        // them do not walk them alone
+        if (general) gq[atomicAdd(&gq_n, 1)] = v;
+        if (seam_tile) {
+            __syncthreads();
+            const int nq = gq_n;
+            for (int q = (int)(threadIdx.x >> 5); q < nq; q += kTileThreads / 32) {
+                int w_orow, w_ew, w_slot;
+                tile_own_locate(T, gq[q], w_orow, w_ew, w_slot);
+                int lo = T.cx0 - T.a, hi = T.cx1 - T.a;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (T.cs[w_orow + 1][mid] <= w_ew) lo = mid;
+                    else hi = mid;
+                }
+                const int n = general_walk<HALF>(P, T, s_xy, s_key, snap, cell_of, ncy, w_ew, w_slot, w_orow, T.a + lo,
+                                                 row_sm, ell_q, cnt, dummy);
+                if (lane == 0) {
+                    t_full += n;
+                    t_max = max(t_max, n);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) gq_n = 0;
+            __syncthreads();
+        }
     }
     // totals: entries, longest row (capacity check)
 #pragma unroll
@@ -1022,7 +1123,7 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
         k_tile_setup<<<grid_for(w.n_tiles), kBlock, 0, st>>>(g, P.ncx, P.slab, w.tile_w, w.n_tiles, w.tile_cap,
                                                             (int)w.ell_stride, w.cell_start.as<int>(), w.tiles.as<TileDesc>(),
                                                             w.totals.as<int>(), flags);
-        const size_t smem = (size_t)w.tile_cap * kWalkSlotBytes;
+        const size_t smem = (size_t)w.tile_cap * kWalkSlotBytes + (size_t)(kTileThreads / 32) * w.ell_cap * sizeof(unsigned short);
         SPHB_TRY(set_walk_smem(smem));
         // one CTA per tile; rows beyond the device-side n_cell_y exit at once
         if (half_only)

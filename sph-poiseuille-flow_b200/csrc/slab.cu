@@ -404,11 +404,13 @@ SPHB_API int sphb_ctx_slab_init(sphb_ctx *c, int col_lo, int col_hi, int halo_co
     SPHB_TRY(s.a_pid.reserve(((size_t)nf_cap + 1) * sizeof(int)));
     if (ids && n_owned) SPHB_CUDA(cudaMemcpyAsync(s.pid.p, ids, (size_t)n_owned * sizeof(int), cudaMemcpyHostToDevice, c->st));
     double *stage = c->stage.as<double>();   // 4 * n_total doubles
+    size_t used = 0;   // every array has its own staging region (6 * n_total doubles in all)
     auto up2 = [&](const double *src, size_t n, double2 *dst) -> int {
         if (!n) return 0;
-        SPHB_CUDA(cudaMemcpyAsync(stage, src, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->st));
-        launch_pack2(stage, dst, (int)n, c->st);
-        SPHB_CUDA(cudaStreamSynchronize(c->st));
+        double *st2 = stage + used;
+        used += 2 * n;
+        SPHB_CUDA(cudaMemcpyAsync(st2, src, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        launch_pack2(st2, dst, (int)n, c->st);
         return 0;
     };
     SPHB_TRY(up2(wall_pos, nw, s.w_pos.as<double2>()));
