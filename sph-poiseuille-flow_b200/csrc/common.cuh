@@ -74,6 +74,8 @@ struct GridDesc {
     int ncx, ncy, ncells;
     int n_entries;     // real + ghost entries
     long long ymin_key, ymax_key;   // ordered-integer images used by the atomic min/max reduction
+    unsigned int ticket;            // CTAs of the y-range reduction that have finished
+    unsigned int pad;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -94,6 +96,7 @@ struct NeighborWork {
     int col0 = 0;                // global cell column of local column 0 (slab mode)
     int ncx_local = 0;           // local cell columns (slab mode)
     bool half_only = false;      // the last build kept only the reference's half list
+    bool grid_armed = false;     // the GridDesc reduction keys have been initialised
     bool half_valid = false;     // totals[0] holds the half-pair count of the current list
     bool tile_fitted = false;    // tile_cap has been fitted to the first build
     DevBuf grid;                 // GridDesc

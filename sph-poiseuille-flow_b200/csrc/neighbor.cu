@@ -88,9 +88,13 @@ __global__ void k_grid_init(GridDesc *g)
     g->ymin_key = LLONG_MAX;
     g->ymax_key = LLONG_MIN;
     g->n_entries = 0;
+    g->ticket = 0u;
 }
 
-__global__ void __launch_bounds__(256) k_yrange(const double2 *__restrict__ pos, int n, GridDesc *g)
+// y range over ALL particles (nb:245-250); the last CTA to finish derives the grid (nb:253-258), re-arms
+// the reduction for the next build and zeroes the build's totals: one launch instead of three.
+__global__ void __launch_bounds__(256) k_yrange_grid(const double2 *__restrict__ pos, int n, GridDesc *g, NbrParams P,
+                                                    int *flags, int *totals)
 {
     long long kmin = LLONG_MAX, kmax = LLONG_MIN;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -109,12 +113,13 @@ __global__ void __launch_bounds__(256) k_yrange(const double2 *__restrict__ pos,
         atomicMin(&g->ymin_key, kmin);
         atomicMax(&g->ymax_key, kmax);
     }
-}
-
-__global__ void k_grid_setup(GridDesc *g, NbrParams P, int *flags)
-{
-    const double y_min = from_ordered_key(g->ymin_key);
-    const double y_max = from_ordered_key(g->ymax_key);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    __threadfence();
+    if (atomicAdd(&g->ticket, 1u) != gridDim.x - 1) return;
+    __threadfence();
+    const double y_min = from_ordered_key(atomicMin(&g->ymin_key, LLONG_MAX));
+    const double y_max = from_ordered_key(atomicMax(&g->ymax_key, LLONG_MIN));
     int ncy = (int)ceil((y_max - y_min + 1e-12) / P.cell) + 1;   // nb:256
     if (ncy < 1) ncy = 1;
     if ((long long)ncy * P.ncx > (long long)P.cell_cap) {
@@ -128,6 +133,10 @@ __global__ void k_grid_setup(GridDesc *g, NbrParams P, int *flags)
     g->ncx = P.ncx;
     g->ncy = ncy;
     g->ncells = ncy * P.ncx;
+    g->ymin_key = LLONG_MAX;   // re-armed for the next build
+    g->ymax_key = LLONG_MIN;
+    g->ticket = 0u;
+    for (int k = 0; k < 8; ++k) totals[k] = 0;
 }
 
 struct Bins {
@@ -276,7 +285,6 @@ __global__ void __launch_bounds__(kBlock) k_tile_setup(const GridDesc *__restric
         const bool row_ok = valid && row >= 0 && row < ncy;
         int rb[3] = {0, 0, 0}, re[3] = {0, 0, 0};
         const int *cs = cell_start + (size_t)(row_ok ? row : 0) * ncx;
-        for (int k = 0; k <= b - a; ++k) T.cs[r][k] = row_ok ? cs[a + k] : 0;
         if (row_ok) {
             rb[0] = cs[a];
             re[0] = cs[b];
@@ -301,8 +309,9 @@ __global__ void __launch_bounds__(kBlock) k_tile_setup(const GridDesc *__restric
     for (int k = 0; k < kTileRows; ++k) {
         const int r = k + 1;
         const bool row_ok = valid && cy0 + k < ncy;
-        T.own_b[k] = row_ok ? T.cs[r][cx0 - a] : 0;
-        T.own_n[k] = row_ok ? T.cs[r][cx1 - a] - T.cs[r][cx0 - a] : 0;
+        const int *cs = cell_start + (size_t)(row_ok ? cy0 + k : 0) * ncx;
+        T.own_b[k] = row_ok ? cs[cx0] : 0;
+        T.own_n[k] = row_ok ? cs[cx1] - cs[cx0] : 0;
         T.own_off[k] = T.seg[3 * r].off + (T.own_b[k] - T.seg[3 * r].b);
     }
     T.cy0 = cy0;
@@ -490,7 +499,8 @@ __device__ __forceinline__ unsigned walk_tile_of_block(unsigned b, int tpr, unsi
 // (nb:342,383) is a function of the walk positions of the (at most three) entries of the other particle,
 // not of a per-walker table -- and a ballot compacts the accepted entries, in walk order, into the row.
 template <bool HALF>
-__device__ __forceinline__ int general_walk(const NbrParams &P, const TileDesc &T, const double2 *s_xy,
+__device__ __forceinline__ int general_walk(const NbrParams &P, const TileDesc &T, const TileCellStarts &s_cs,
+                                            const double2 *s_xy,
                                             const int *s_key, const double2 *__restrict__ snap,
                                             const int *__restrict__ cell_of, int ncy, int ew, int slot_i, int orow,
                                             int cxi, unsigned short *row_sm, uint4 *ell_q, int *__restrict__ cnt,
@@ -528,7 +538,7 @@ __device__ __forceinline__ int general_walk(const NbrParams &P, const TileDesc &
             if (cx == cx_prev[0] || cx == cx_prev[1]) continue;
             cx_prev[ox == -1 ? 0 : 1] = cx;
             int sb, se;
-            tile_cell_slots(T, ri + oy, cx, ncx, sb, se);
+            tile_cell_slots(T, s_cs, ri + oy, cx, ncx, sb, se);
             rb[k] = sb;
             rn[k] = se - sb;
             total += se - sb;
@@ -628,6 +638,7 @@ __device__ __forceinline__ int general_walk(const NbrParams &P, const TileDesc &
 template <bool HALF>
 __global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, const GridDesc *__restrict__ g,
                                                            const TileDesc *__restrict__ tiles, int tile_w,
+                                                           const int *__restrict__ cell_start,
                                                            const double2 *__restrict__ snap,
                                                            const int *__restrict__ cell_of,
                                                            const int *__restrict__ ent_key,
@@ -640,9 +651,15 @@ __global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, cons
     double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
     int *s_key = reinterpret_cast<int *>(s_xy + cap);
     const int ncx = P.ncx, ncy = g->ncy;
+    __shared__ TileCellStarts s_cs;
     tile_load(T, tiles, walk_tile_of_block(blockIdx.x, tiles_per_row(ncx, tile_w), gridDim.x));
     __syncthreads();
     if (!(T.flags & kTileValid)) return;
+    for (int k = threadIdx.x; k < kStageRows * (kMaxTileW + 3); k += kTileThreads) {
+        const int r = k / (kMaxTileW + 3), c = k % (kMaxTileW + 3);
+        const int row = T.cy0 + r - 1;
+        s_cs[r][c] = (row >= 0 && row < ncy && c <= T.b - T.a) ? cell_start[(size_t)row * ncx + T.a + c] : 0;
+    }
     SPHB_TILE_FOR_STAGED(T, e, slot)
     {
         s_key[slot] = ent_key[e];
@@ -680,7 +697,7 @@ __global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, cons
                     int lo = T.cx0 - T.a, hi = T.cx1 - T.a;   // cs[ri][lo] <= ew < cs[ri][hi]
                     while (hi - lo > 1) {
                         const int mid = (lo + hi) >> 1;
-                        if (T.cs[ri][mid] <= ew) lo = mid;
+                        if (s_cs[ri][mid] <= ew) lo = mid;
                         else hi = mid;
                     }
                     cxi = T.a + lo;
@@ -703,9 +720,9 @@ __global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, cons
                         const int cy = cyi + (r - ri);
                         if (cy < 0 || cy >= ncy) continue;
                         const int k0 = cxi - 1 - T.a;
-                        const int c0 = T.cs[r][k0];
+                        const int c0 = s_cs[r][k0];
                         const int sb = T.seg[3 * r].off + (c0 - T.seg[3 * r].b);
-                        const int se = sb + (T.cs[r][k0 + 3] - c0);
+                        const int se = sb + (s_cs[r][k0 + 3] - c0);
 #pragma unroll 1
                         for (int s0 = sb; s0 < se; s0 += 32) {
                             const int s1 = min(s0 + 32, se);
@@ -757,10 +774,10 @@ __global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, cons
                 int lo = T.cx0 - T.a, hi = T.cx1 - T.a;
                 while (hi - lo > 1) {
                     const int mid = (lo + hi) >> 1;
-                    if (T.cs[w_orow + 1][mid] <= w_ew) lo = mid;
+                    if (s_cs[w_orow + 1][mid] <= w_ew) lo = mid;
                     else hi = mid;
                 }
-                const int n = general_walk<HALF>(P, T, s_xy, s_key, snap, cell_of, ncy, w_ew, w_slot, w_orow, T.a + lo,
+                const int n = general_walk<HALF>(P, T, s_cs, s_xy, s_key, snap, cell_of, ncy, w_ew, w_slot, w_orow, T.a + lo,
                                                  row_sm, ell_q, cnt, dummy);
                 if (lane == 0) {
                     t_full += n;
@@ -1032,6 +1049,7 @@ int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL
     w.cell_cap = new_cell_cap;
     const size_t nt = (size_t)n_total;
     const size_t ecap = entry_capacity(nt);
+    if (!w.grid.p) w.grid_armed = false;
     SPHB_TRY(w.grid.reserve(sizeof(GridDesc)));
     if (!w.flags.p) {
         SPHB_TRY(w.flags.reserve(sizeof(int)));
@@ -1086,18 +1104,20 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
 
     {
         ProfScope ps(prof, kPfNbrGrid, st);
-        k_grid_init<<<1, 1, 0, st>>>(g);
+        if (!w.grid_armed) {   // once per plan; afterwards every build re-arms the reduction itself
+            k_grid_init<<<1, 1, 0, st>>>(g);
+            w.grid_armed = true;
+        }
         int blocks = (nt + 255) / 256;
-        if (blocks > 148 * 8) blocks = 148 * 8;
-        k_yrange<<<blocks, 256, 0, st>>>(pos, nt, g);
-        k_grid_setup<<<1, 1, 0, st>>>(g, P, flags);
+        if (blocks > 148 * 4) blocks = 148 * 4;
+        k_yrange_grid<<<blocks, 256, 0, st>>>(pos, nt, g, P, flags, w.totals.as<int>());
         SPHB_CUDA(cudaMemsetAsync(cell_cnt, 0, 2 * ((size_t)w.cell_cap + 1) * sizeof(int), st));
     }
     {
         ProfScope ps(prof, kPfNbrBin, st);
         k_bin_count<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.snap.as<double2>(), w.cell_of.as<int>(), cell_cnt);
     }
-    nl += 4;
+    nl += 2;
     {
         ProfScope ps(prof, kPfNbrScan, st);
         SPHB_TRY(exclusive_scan_i32(cell_cnt, w.cell_start.as<int>(), (size_t)w.cell_cap, w.scan_tmp, &g->n_entries, st,
@@ -1119,7 +1139,7 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
 
     for (int attempt = 0; attempt < 8; ++attempt) {
         ProfScope ps(prof, kPfNbrWalk, st);
-        SPHB_CUDA(cudaMemsetAsync(w.totals.p, 0, 8 * sizeof(int), st));
+        if (attempt > 0) SPHB_CUDA(cudaMemsetAsync(w.totals.p, 0, 8 * sizeof(int), st));
         k_tile_setup<<<grid_for(w.n_tiles), kBlock, 0, st>>>(g, P.ncx, P.slab, w.tile_w, w.n_tiles, w.tile_cap,
                                                             (int)w.ell_stride, w.cell_start.as<int>(), w.tiles.as<TileDesc>(),
                                                             w.totals.as<int>(), flags);
@@ -1128,12 +1148,14 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
         // one CTA per tile; rows beyond the device-side n_cell_y exit at once
         if (half_only)
             k_walk_tile<true><<<w.n_tiles, kTileThreads, smem, st>>>(
-                P, g, w.tiles.as<TileDesc>(), w.tile_w, w.snap.as<double2>(), w.cell_of.as<int>(),
+                P, g, w.tiles.as<TileDesc>(), w.tile_w, w.cell_start.as<int>(), w.snap.as<double2>(),
+                w.cell_of.as<int>(),
                 w.ent_key.as<int>(), w.ent_pos.as<double2>(), w.ell_q.as<uint4>(), w.ell_cnt.as<int>(),
                 w.totals.as<int>(), flags, w.tile_cap);
         else
             k_walk_tile<false><<<w.n_tiles, kTileThreads, smem, st>>>(
-                P, g, w.tiles.as<TileDesc>(), w.tile_w, w.snap.as<double2>(), w.cell_of.as<int>(),
+                P, g, w.tiles.as<TileDesc>(), w.tile_w, w.cell_start.as<int>(), w.snap.as<double2>(),
+                w.cell_of.as<int>(),
                 w.ent_key.as<int>(), w.ent_pos.as<double2>(), w.ell_q.as<uint4>(), w.ell_cnt.as<int>(),
                 w.totals.as<int>(), flags, w.tile_cap);
         nl += 2;

@@ -1,8 +1,8 @@
 // scan.cu -- hand-written exclusive prefix sum over int32 (no CUB/Thrust on the hot path).
 //
 // out[i] = sum_{k<i} in[k] for i = 0..n (out has n+1 elements, out[n] = grand total).
-// Three launches: (A) per-tile scan, 4096 elements per 1024-thread block, tile totals to tmp;
-// (B) one block scans the tile totals with a running carry; (C) tiles add their offset.
+// Two launches: (A) per-tile scan, 4096 elements per 1024-thread block, tile totals to tmp;
+// (B) every tile sums the totals before it and adds that offset (one launch when a single tile suffices).
 // Used for cell starts (N1), half-pair and CSR row pointers (N6) and the cell sort of particles (S1).
 #include "common.cuh"
 
@@ -45,7 +45,8 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *block_total)
 }
 
 __global__ void __launch_bounds__(kScanThreads) scan_tiles(const int *__restrict__ in, int *__restrict__ out,
-                                                          int *__restrict__ tile_totals, size_t n)
+                                                          int *__restrict__ tile_totals, size_t n,
+                                                          int *__restrict__ total_out)
 {
     __shared__ int total_sh;
     const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
@@ -63,40 +64,45 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles(const int *__restrict
         pre += v[k];
     }
     __syncthreads();
-    if (threadIdx.x == 0) tile_totals[blockIdx.x] = total_sh;
-}
-
-__global__ void __launch_bounds__(kScanThreads) scan_totals(int *__restrict__ tile_totals, size_t n_tiles,
-                                                           int *__restrict__ out_end, int *__restrict__ total_out)
-{
-    __shared__ int total_sh;
-    __shared__ int carry_sh;
-    if (threadIdx.x == 0) carry_sh = 0;
-    __syncthreads();
-    for (size_t start = 0; start < n_tiles; start += kScanThreads) {
-        size_t i = start + threadIdx.x;
-        int v = (i < n_tiles) ? tile_totals[i] : 0;
-        int pre = block_exclusive_scan(v, &total_sh);
-        int carry = carry_sh;
-        if (i < n_tiles) tile_totals[i] = pre + carry;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_sh = carry + total_sh;
-        __syncthreads();
-    }
     if (threadIdx.x == 0) {
-        *out_end = carry_sh;
-        if (total_out) *total_out = carry_sh;
+        tile_totals[blockIdx.x] = total_sh;
+        if (gridDim.x == 1) {   // a single tile is the whole scan
+            out[n] = total_sh;
+            if (total_out) *total_out = total_sh;
+        }
     }
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_add_offsets(int *__restrict__ out,
-                                                                const int *__restrict__ tile_totals, size_t n)
+// Every tile sums the totals of the tiles before it (a few hundred values at most) and adds the offset
+// to its elements; the last tile also writes the grand total.  No separate "scan of the totals" launch.
+__global__ void __launch_bounds__(kScanThreads) scan_finish(int *__restrict__ out, const int *__restrict__ tile_totals,
+                                                           size_t n, int *__restrict__ total_out)
 {
-    const int off = tile_totals[blockIdx.x];
+    __shared__ int warp_part[32];
+    __shared__ int off_sh;
+    int part = 0;
+    for (unsigned i = threadIdx.x; i < blockIdx.x; i += kScanThreads) part += tile_totals[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int s = warp_part[threadIdx.x];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (threadIdx.x == 0) off_sh = s;
+    }
+    __syncthreads();
+    const int off = off_sh;
     const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
 #pragma unroll
     for (int k = 0; k < kItems; ++k)
         if (base + k < n) out[base + k] += off;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        const int total = off + tile_totals[blockIdx.x];
+        out[n] = total;
+        if (total_out) *total_out = total;
+    }
 }
 
 }  // namespace
@@ -112,10 +118,9 @@ int exclusive_scan_i32(const int *in, int *out, size_t n, DevBuf &tmp, int *tota
     const size_t n_tiles = (n + kTile - 1) / kTile;
     SPHB_TRY(tmp.reserve(n_tiles * sizeof(int)));
     int *totals = tmp.as<int>();
-    scan_tiles<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(in, out, totals, n);
-    scan_totals<<<1, kScanThreads, 0, st>>>(totals, n_tiles, out + n, total_out_dev);
-    if (n_tiles > 1) scan_add_offsets<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(out, totals, n);
-    if (launches) *launches += (n_tiles > 1) ? 3 : 2;
+    scan_tiles<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(in, out, totals, n, total_out_dev);
+    if (n_tiles > 1) scan_finish<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(out, totals, n, total_out_dev);
+    if (launches) *launches += (n_tiles > 1) ? 2 : 1;
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -48,9 +48,11 @@ struct __align__(16) TileDesc {
     int cy0, cx0, cx1;             // first own cell row; own columns [cx0, cx1)
     int a, b;                      // main range = columns [a, b)
     int flags;
-    int cs[kStageRows][kMaxTileW + 3];   // cell_start of the main range's cells a .. b (b - a + 1 values) per staged row
-    int pad[(4 - (kStageRows * 9 + 1 + 3 * kTileRows + 6 + kStageRows * (kMaxTileW + 3)) % 4) % 4];
+    int pad[(4 - (kStageRows * 9 + 1 + 3 * kTileRows + 6) % 4) % 4 + 4];
 };
+// cell_start of the main range's cells a .. b (b - a + 1 values) per staged row: only the neighbour walk
+// needs it, and loads it from the cell starts itself
+typedef int TileCellStarts[kStageRows][kMaxTileW + 3];
 static_assert(sizeof(TileDesc) % 16 == 0, "TileDesc is copied as int4");
 
 __host__ __device__ inline int tiles_per_row(int ncx, int w) { return (ncx + w - 1) / w; }
@@ -85,12 +87,13 @@ __device__ __forceinline__ void tile_load(TileDesc &T, const TileDesc *__restric
 }
 
 // slot range [sb, se) of cell (staged row r, column cx) of the staged neighbourhood
-__device__ __forceinline__ void tile_cell_slots(const TileDesc &T, int r, int cx, int ncx, int &sb, int &se)
+__device__ __forceinline__ void tile_cell_slots(const TileDesc &T, const TileCellStarts &cs, int r, int cx, int ncx,
+                                                int &sb, int &se)
 {
     if (cx >= T.a && cx < T.b) {
-        const int c0 = T.cs[r][cx - T.a];
+        const int c0 = cs[r][cx - T.a];
         sb = T.seg[3 * r].off + (c0 - T.seg[3 * r].b);
-        se = sb + (T.cs[r][cx - T.a + 1] - c0);
+        se = sb + (cs[r][cx - T.a + 1] - c0);
     } else {
         const TileSeg &s = T.seg[3 * r + (cx == ncx - 1 ? 1 : 2)];
         sb = s.off;
