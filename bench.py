@@ -72,7 +72,9 @@ def parse_args():
     ap.add_argument("--profile-steps", type=int, default=5)
     ap.add_argument("--cpu-baseline-steps", type=int, default=20, help="outer steps of the CPU sample (0 = skip)")
     ap.add_argument("--seed", type=int, default=12345)
-    ap.add_argument("--presort", action="store_true", help="experiment: apply the cell sort (m:529-568) once before timing")
+    ap.add_argument("--no-presort", action="store_true",
+                    help="time from the raw lattice order instead of the order after the reference's first cell "
+                         "sort (m:272, 529-568)")
     ap.add_argument("--mode", default="auto", choices=("auto", "slab", "replicas"),
                     help="N > 1: 'slab' = ONE periodic channel of length N*DL cut into x-slabs (halo exchange + "
                          "migration over NCCL, weak scaling); 'replicas' = N independent channels (ensemble); "
@@ -90,6 +92,22 @@ def host_threads() -> int:
         return len(os.sched_getaffinity(0))
     except AttributeError:
         return os.cpu_count() or 1
+
+
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the newest committed ncu summary (profiles/*_ncu_summary.json,
+    written by tools/ncu_to_profile.py from an `ncu --set full` capture of this same command)."""
+    import glob
+    names = {"force_fused": "k_force_fused", "pressure": "k_pressure", "continuity": "k_continuity",
+             "density": "k_density", "kgc": "k_kgc", "visc_transport": "k_visc_transport", "nbr_walk": "k_walk_tile"}
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")))
+    if not files or kernel not in names:
+        return None, None
+    try:
+        rec = json.load(open(files[-1])).get(names[kernel])
+        return (rec[0]["dram_bytes"], os.path.relpath(files[-1], ROOT)) if rec else (None, None)
+    except (OSError, ValueError, KeyError, IndexError):
+        return None, None
 
 
 def workload_name(cfg, pt, inner):
@@ -193,6 +211,8 @@ def reference_arm(args):
         DL *= 0.5
     cfg_s = lp.ChannelConfig(DL=DL, dp=args.dp).derive()
     pt = lp.channel_setup.developed(cfg_s, seed=args.seed)
+    if not args.no_presort:
+        pt = lp.channel_setup.cell_sorted(cfg_s, pt)
     value, kind, threads, secs = cpu_run(cfg_s, pt, args.inner, args.steps, args.warmup)
     sample = (f"{args.steps} outer steps x {args.inner} substeps of the dp={cfg_s.dp:g} channel "
               f"{'at full length' if DL == cfg.DL else f'shortened to DL={cfg_s.DL:g}'} ({pt.n_total} particles)")
@@ -254,10 +274,10 @@ def b200_arm(args):
         return b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks)
     cfg = lp.ChannelConfig(DL=args.DL, dp=args.dp).derive()
     pt = lp.channel_setup.developed(cfg, seed=args.seed + rank)     # one independent channel per rank
+    if not args.no_presort:
+        pt = lp.channel_setup.cell_sorted(cfg, pt)   # the row order of a run past its first sort point (m:272)
     nt, inner, K, W = pt.n_total, args.inner, args.steps, args.warmup
     ch = lp.channel_from_config(cfg, pt, device=local_rank)
-    if args.presort:
-        ch.sort_by_cell()
     ch.initialise()
     stream = torch.cuda.ExternalStream(ch.stream, device=torch.device("cuda", local_rank))
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -343,13 +363,18 @@ def b200_arm(args):
         top = max((n for n in kernels if n in ALG_BYTES_KERNEL), key=lambda n: kernels[n]["share"])
         per_launch_bytes = ALG_BYTES_KERNEL[top] * nt
         achieved = per_launch_bytes / (kernels[top]["ms_per_call"] * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(top)
         roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "alg_bytes_per_launch": per_launch_bytes,
                 "alg_bytes_per_particle": ALG_BYTES_KERNEL[top], "ms_per_launch": kernels[top]["ms_per_call"],
                 "share_of_step": kernels[top]["share"],
-                "step_frac": (value / world) * ALG_BYTES_SUBSTEP / (hbm * 1e9)}
-        # the Verlet substep alone (time_step + pressure + continuity + clock), outer-step work excluded
-        sub_ms = sum(kernels[n]["ms_per_call"] for n in ("time_step", "pressure", "continuity", "clock") if n in kernels)
+                "step_frac": (value / world) * ALG_BYTES_SUBSTEP / (hbm * 1e9),
+                "fp64_note": "fp64 gather over ~41 neighbours per particle: the FP64 pipe and the shared-memory "
+                             "data pipe bound these kernels, not HBM (profiles/README.md)"}
+        # the kernels of the acoustic substep alone (forces + continuity), list rebuild and KGC excluded
+        sub_ms = sum(kernels[n]["ms_per_call"] for n in ("force_fused", "time_step", "pressure", "continuity", "clock")
+                     if n in kernels)
         roof["substep_kernels_only"] = {"ms": sub_ms, "value": nt / (sub_ms * 1e-3),
                                         "frac": nt / (sub_ms * 1e-3) * ALG_BYTES_SUBSTEP / (hbm * 1e9)}
 
@@ -368,8 +393,10 @@ def b200_arm(args):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(cfg, pt, inner), "inner_substeps": inner,
-                       "list_rebuild": "every outer step (device counting sort + CSR)",
+                       "list_rebuild": "every outer step (device counting sort + tile-local 16-bit lists)",
                        "cell_sort_interval": cfg.sort_interval,
+                       "row_order": ("raw lattice" if args.no_presort else
+                                     "after the reference's cell sort (m:529-568), as in a run past its first sort point"),
                        "l2": ("256 MiB memset between timed steps" if flush is not None else
                               "no flush: consecutive steps of one simulation"),
                        "parallelism": f"{world} independent channel(s), one per GPU"},
@@ -400,6 +427,8 @@ def b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, su
     slabmod = importlib.import_module("sph_b200.slab")
     cfg = lp.ChannelConfig(DL=args.DL * world, dp=args.dp, sort_interval=0).derive()
     pt = lp.channel_setup.developed(cfg, seed=args.seed)              # the same global state on every rank
+    if not args.no_presort:
+        pt = lp.channel_setup.cell_sorted(cfg, pt)                    # row order after the reference's cell sort
     K, W = args.steps, max(args.warmup, 3)
     dev = torch.device("cuda", local_rank)
     sc = slabmod.SlabChannel(cfg, pt, rank, world, dev)
@@ -484,8 +513,9 @@ def b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, su
                 kernels[name] = {"ms_per_call": ms / calls, "calls": calls, "share": ms / total}
         top = max((n for n in kernels if n in ALG_BYTES_KERNEL), key=lambda n: kernels[n]["share"])
         achieved = ALG_BYTES_KERNEL[top] * nl / (kernels[top]["ms_per_call"] * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(top)
         roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "alg_bytes_per_particle": ALG_BYTES_KERNEL[top], "ms_per_launch": kernels[top]["ms_per_call"],
                 "share_of_step": kernels[top]["share"], "rows_per_launch": nl,
                 "step_frac": (value / world) * ALG_BYTES_SUBSTEP / (hbm * 1e9),

@@ -95,6 +95,21 @@ def developed(cfg: ChannelConfig, seed: int = 12345, jitter: float = 0.1, noise:
     return pt
 
 
+def cell_sorted(cfg: ChannelConfig, pt: Particles) -> Particles:
+    """The fluid rows in the order the reference's periodic cell sort gives them (sort_particles_by_cell,
+    SPH_Poiseuille.m:529-568: key (cy, cx), cell = 2h, cy from min(fluid y), stable; walls stay last) -- the
+    order a running simulation is in after its first sort point (m:272)."""
+    nf = pt.n_fluid
+    cell = 2.0 * cfg.h
+    x = np.mod(pt.pos[:nf, 0], cfg.DL)
+    cx = np.floor(x / cell).astype(np.int64)
+    cy = np.floor((pt.pos[:nf, 1] - pt.pos[:nf, 1].min()) / cell).astype(np.int64)
+    perm = np.concatenate([np.lexsort((cx, cy)), np.arange(nf, pt.n_total)])     # stable, like sortrows
+    take2 = lambda a: np.asfortranarray(a[perm, :])   # noqa: E731
+    return Particles(pos=take2(pt.pos), vel=take2(pt.vel), rho=pt.rho[perm].copy(), drho_dt=pt.drho_dt[perm].copy(),
+                     mass=pt.mass[perm].copy(), wall_vel=take2(pt.wall_vel), n_fluid=nf, n_total=pt.n_total)
+
+
 def analytic_profile(cfg: ChannelConfig, y):
     """u(y) = g / (2 nu) y (DH - y)  (SPH_Poiseuille_postprocess.m:36-38)."""
     y = np.asarray(y, dtype=np.float64)

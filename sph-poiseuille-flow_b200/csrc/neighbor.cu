@@ -1076,7 +1076,8 @@ int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL
         w.tile_fitted = false;
         // ~0.9 own entries per thread for a uniformly filled grid; the first exact build narrows the
         // tiles if the densest neighbourhood does not fit the shared-memory slots
-        const double per_cell = (double)n_total / std::max(1.0, ncx_d * (ncy_d - 9.0));
+        const double per_cell = w.per_cell_hint > 0.0 ? w.per_cell_hint
+                                                      : (double)n_total / std::max(1.0, ncx_d * (ncy_d - 9.0));
         int tw = (int)std::floor(0.955 * kTileThreads / std::max(per_cell * kTileRows, 1e-9));
         SPHB_TRY(plan_tiles(w, std::max(1, std::min(tw, kMaxTileW))));
         const double guess = (double)kStageRows * (w.tile_w + 2) * per_cell * 1.25 + 64.0;

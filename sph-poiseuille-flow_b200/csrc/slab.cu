@@ -442,7 +442,13 @@ SPHB_API int sphb_ctx_slab_init(sphb_ctx *c, int col_lo, int col_hi, int halo_co
         y_lo = pos[no + i] < y_lo ? pos[no + i] : y_lo;
         y_hi = pos[no + i] > y_hi ? pos[no + i] : y_hi;
     }
-    // plan for the capacity, then run with the current row counts
+    // plan for the capacity (buffers) and for the actual row density (tile width), then run with the
+    // current row counts
+    {
+        const double rows = std::ceil((y_hi - y_lo + 1e-12) / (2.0 * c->prm.h)) + 1.0;
+        const double width = (double)(col_hi - col_lo);
+        c->nw.per_cell_hint = ((double)n_owned / width + (double)n_wall / (width + 2.0 * halo_cols)) / rows;
+    }
     apply_counts(c, nf_cap, 0);
     SPHB_TRY(ctx_plan_lists(c, y_lo, y_hi));
     apply_counts(c, n_owned, 0);

@@ -33,7 +33,7 @@ def bytes_of(r, key):
 out = {}
 for r in rows[2:]:
     name = r[col["Kernel Name"]]
-    short = name.split("::")[-1].split("(")[0]
+    short = name.split("(")[0].split("::")[-1].split("<")[0].strip()
     stalls = {h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""): num(r, h)
               for h in hdr if "issue_stalled" in h and h.endswith("_per_issue_active.ratio") and "not_issued" not in h}
     top = dict(sorted(((k, round(v, 3)) for k, v in stalls.items() if v), key=lambda kv: -kv[1])[:5])
