@@ -257,6 +257,7 @@ SPHB_API int sphb_ctx_sync(sphb_ctx *ctx);
  *     sphb_ctx_slab_scalars_export -> caller all-reduces max|v| (MAX) and the shear partials (SUM)
  *     sphb_ctx_slab_pack         migrants + edge copies into two device buffers of the caller
  *     (caller: NCCL send/recv of the two buffers to the left / right neighbour rank)
+ *     sphb_ctx_slab_compact      the rows that stay, compacted (runs while the buffers are on the wire)
  *     sphb_ctx_slab_unpack       new owned rows, new halo copies (shifted by -+DL across the seam, nb:284,291)
  *     sphb_ctx_slab_vmax_import  the all-reduced max|v| (time step of the next step, m:519-527)
  *     sphb_ctx_slab_step_end     list rebuild + wall-shear partials                 (m:280-283)
@@ -271,12 +272,17 @@ SPHB_API int sphb_ctx_slab_init(sphb_ctx *ctx, int col_lo, int col_hi, int halo_
 /* global identity (the `ids` given at init, carried through migrations) of the fluid rows, owned first */
 SPHB_API int sphb_ctx_slab_ids(sphb_ctx *ctx, int *ids);
 SPHB_API int sphb_ctx_slab_pack(sphb_ctx *ctx, double *send_left_dev, double *send_right_dev, int rec_cap);
+/* second half of the pack: the stayers are compacted (overlaps the transfer when called after the send) */
+SPHB_API int sphb_ctx_slab_compact(sphb_ctx *ctx);
 SPHB_API int sphb_ctx_slab_unpack(sphb_ctx *ctx, const double *recv_left_dev, const double *recv_right_dev,
                                   const double *sent_left_dev, const double *sent_right_dev, int rec_cap);
 SPHB_API int sphb_ctx_slab_step_begin(sphb_ctx *ctx, double remain);
 SPHB_API int sphb_ctx_slab_step_end(sphb_ctx *ctx);
 SPHB_API int sphb_ctx_slab_scalars_export(sphb_ctx *ctx, double *out_dev3);   /* vmax, tau_bottom, tau_top partials */
 SPHB_API int sphb_ctx_slab_vmax_import(sphb_ctx *ctx, const double *in_dev1);
+/* the scalars of all ranks after an all-gather ([world][3], device): max|v| (MAX) into the context; the
+ * reduced (max|v|, sum tau_bottom, sum tau_top) to out_dev3 (may be NULL) */
+SPHB_API int sphb_ctx_slab_scalars_reduce(sphb_ctx *ctx, const double *gathered_dev, int world, double *out_dev3);
 SPHB_API int sphb_ctx_slab_counts(sphb_ctx *ctx, int *n_owned, int *n_halo, int *n_wall);
 
 #ifdef __cplusplus

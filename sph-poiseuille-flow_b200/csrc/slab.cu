@@ -135,7 +135,10 @@ __device__ __forceinline__ void write_record(double *rec, double2 x, double2 v, 
     r[3] = make_double4((double)pid, 0.0, 0.0, 0.0);
 }
 
-// stayers -> compacted new arrays; migrants and halo copies -> the two send buffers [migrants | copies]
+// SEND: migrants and halo copies -> the two send buffers [migrants | copies]; !SEND: stayers -> compacted new
+// arrays.  Two launches so that the caller can put the buffers on the wire before the (much larger) stayer
+// copy runs: the NCCL transfer overlaps it.
+template <bool SEND>
 __global__ void __launch_bounds__(kSlabBlock) k_slab_scatter(SlabArrays A, SlabGeom G,
                                                             const int *__restrict__ block_off,
                                                             const int *__restrict__ counts, double *send_left,
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_scatter(SlabArrays A, SlabG
     __shared__ int warp_off[cN][kSlabBlock / 32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned m = i < G.nfo ? slab_class(A.pos[i].x, G) : 0u;
+    unsigned m = i < G.nfo ? slab_class(A.pos[i].x, G) : 0u;
     int rank[cN];
 #pragma unroll
     for (int k = 0; k < cN; ++k) {
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_scatter(SlabArrays A, SlabG
         }
     }
     __syncthreads();
-    if (i == 0) {
+    if (SEND && i == 0) {
         const int nl = counts[cMigL] + counts[cHaloL], nr = counts[cMigR] + counts[cHaloR];
         send_left[0] = (double)counts[cMigL];
         send_left[1] = (double)counts[cHaloL];
@@ -170,6 +173,7 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_scatter(SlabArrays A, SlabG
         send_right[1] = (double)counts[cHaloR];
         if (nl > rec_cap || nr > rec_cap) atomicOr(flags, kErrSlabCap);
     }
+    m &= SEND ? ~(1u << cStay) : (1u << cStay);
     if (!m) return;
     const double2 x = A.pos[i], v = A.vel[i];
     const double rho = A.rho[i], drho = A.drho[i], mass = A.mass[i], Vol = A.Vol[i];
@@ -304,6 +308,22 @@ __global__ void k_slab_scalars_out(const DevScalars *sc, double *out)
     out[2] = sc->tau_top;
 }
 __global__ void k_slab_vmax_in(DevScalars *sc, const double *in) { sc->vmax = in[0]; }
+// all-gathered [world][3] scalars -> max|v| (MAX) and the wall-shear sums (SUM, in rank order: deterministic)
+__global__ void k_slab_scalars_reduce(DevScalars *sc, const double *g, int world, double *out3)
+{
+    double vmax = 0.0, tb = 0.0, tt = 0.0;
+    for (int r = 0; r < world; ++r) {
+        vmax = fmax(vmax, g[3 * r]);
+        tb += g[3 * r + 1];
+        tt += g[3 * r + 2];
+    }
+    sc->vmax = vmax;
+    if (out3) {
+        out3[0] = vmax;
+        out3[1] = tb;
+        out3[2] = tt;
+    }
+}
 
 SlabGeom geom_of(const sphb_ctx *c)
 {
@@ -468,9 +488,25 @@ SPHB_API int sphb_ctx_slab_pack(sphb_ctx *c, double *send_left_dev, double *send
     ProfScope ps(&c->kprof, kPfSlab, c->st);
     k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), G, bt);
     k_slab_offsets<<<1, 1024, 0, c->st>>>(bt, (int)blocks, cnt);
-    k_slab_scatter<<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, bt, cnt, send_left_dev, send_right_dev, rec_cap,
-                                                     c->nw.flags.as<int>());
+    k_slab_scatter<true><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, bt, cnt, send_left_dev, send_right_dev,
+                                                           rec_cap, c->nw.flags.as<int>());
     c->launches += 3;
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// second half of the pack: the rows that stay are compacted into the alternate arrays (call it after the send
+// buffers have been handed to NCCL, before sphb_ctx_slab_unpack)
+SPHB_API int sphb_ctx_slab_compact(sphb_ctx *c)
+{
+    SLAB_ENTER();
+    SlabState &s = c->slab;
+    const SlabGeom G = geom_of(c);
+    const unsigned blocks = std::max(1u, grid_for((size_t)s.n_owned, kSlabBlock));
+    ProfScope ps(&c->kprof, kPfSlab, c->st);
+    k_slab_scatter<false><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, s.block_tot.as<int>(), s.counts.as<int>(),
+                                                            nullptr, nullptr, 0, c->nw.flags.as<int>());
+    c->launches += 1;
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -561,6 +597,15 @@ SPHB_API int sphb_ctx_slab_ids(sphb_ctx *c, int *ids)
     const size_t n = (size_t)(c->slab.n_owned + c->slab.n_halo);
     if (n) SPHB_CUDA(cudaMemcpyAsync(ids, c->slab.pid.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     SPHB_CUDA(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+// the all-gathered scalars of every rank ([world][3], device) -> max|v| into the context, reduced triple out
+SPHB_API int sphb_ctx_slab_scalars_reduce(sphb_ctx *c, const double *gathered_dev, int world, double *out_dev3)
+{
+    SLAB_ENTER();
+    k_slab_scalars_reduce<<<1, 1, 0, c->st>>>(c->sc(), gathered_dev, world, out_dev3);
+    SPHB_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -118,12 +118,16 @@ class Slab:
         _check(L.sphb_ctx_slab_pack(self.ch._ctx, C.c_void_p(self.send_left.data_ptr()),
                                     C.c_void_p(self.send_right.data_ptr()), C.c_int(self.rec_cap)))
 
-    def unpack(self):
+    def compact(self):
+        _check(lib().sphb_ctx_slab_compact(self.ch._ctx))
+
+    def unpack(self, import_vmax=True):
         L = lib()
         _check(L.sphb_ctx_slab_unpack(self.ch._ctx, C.c_void_p(self.recv_left.data_ptr()),
                                       C.c_void_p(self.recv_right.data_ptr()), C.c_void_p(self.send_left.data_ptr()),
                                       C.c_void_p(self.send_right.data_ptr()), C.c_int(self.rec_cap)))
-        _check(L.sphb_ctx_slab_vmax_import(self.ch._ctx, C.c_void_p(self.scal.data_ptr())))
+        if import_vmax:
+            _check(L.sphb_ctx_slab_vmax_import(self.ch._ctx, C.c_void_p(self.scal.data_ptr())))
 
     def counts(self):
         a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
@@ -182,6 +186,7 @@ class SlabGroup:
         S = self.slabs
         for s in S:
             s.pack()
+            s.compact()
         for s in S:
             s.ch.sync()
         scal = torch.stack([s.scal for s in S])
@@ -241,13 +246,13 @@ class SlabChannel:
         self.stream = torch.cuda.Stream(device=s.device)     # shared by the library's kernels and torch / NCCL
         _check(lib().sphb_ctx_set_stream(s.ch._ctx, C.c_void_p(self.stream.cuda_stream)))
         self._gath = torch.zeros(world * 3, dtype=torch.float64, device=s.device)
-        self._tau = torch.zeros(2, dtype=torch.float64, device=s.device)
+        self._red = torch.zeros(3, dtype=torch.float64, device=s.device)   # max|v|, sum tau_bottom, sum tau_top
         self.exchange()
         s.step_end()
 
     @property
     def tau(self):
-        return tuple(float(v) for v in self._tau.tolist())
+        return tuple(float(v) for v in self._red[1:3].tolist())
 
     def exchange(self):
         with self.torch.cuda.stream(self.stream):
@@ -257,6 +262,7 @@ class SlabChannel:
         dist, s = self.dist, self.slab
         s.pack()
         if self.world == 1:
+            s.compact()
             s.recv_left.copy_(s.send_right)
             s.recv_right.copy_(s.send_left)
         else:
@@ -267,12 +273,12 @@ class SlabChannel:
             works = dist.batch_isend_irecv(ops)
             # max|v| -> time step of the next step (m:519-527); wall-shear partials (ph:1713-1742): one collective
             dist.all_gather_into_tensor(self._gath, s.scal[0:3])
+            s.compact()                       # the stayer copy runs while the buffers are on the wire
             for w in works:
                 w.wait()
-            g = self._gath.view(self.world, 3)
-            s.scal[0:1] = g[:, 0].max().reshape(1)
-            self._tau.copy_(g[:, 1:3].sum(dim=0))
-        s.unpack()
+            _check(lib().sphb_ctx_slab_scalars_reduce(s.ch._ctx, C.c_void_p(self._gath.data_ptr()), C.c_int(self.world),
+                                                      C.c_void_p(self._red.data_ptr())))
+        s.unpack(import_vmax=self.world == 1)
 
     def step(self, remain=float("inf")):
         with self.torch.cuda.stream(self.stream):
