@@ -52,6 +52,28 @@ def check_csr(ch, pairs, n_fluid):
 
 
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("DL,dp", [(0.6, 0.05), (0.9, 0.05), (1.3, 0.04)])
+def test_step_in_short_periodic_channels(sphb, H, oracle_be, DL, dp):
+    """Channels a few cell columns long (every tile is a seam tile: image shifts, ghost entries, replayed
+    pairs in every gather): three full steps against the oracle."""
+    prm = H.derive_params(dp=dp, DL=DL, c_f=10.0)
+    st = H.developed_state(prm, seed=7, jitter=0.25)
+    ref = st.copy()
+    H.initialise(oracle_be, ref, prm)
+    ch = make_channel(sphb, prm, st)
+    ch.initialise()
+    check_pairs(ch, ref.pairs)                       # same positions: bit-exact list, all seven columns
+    for _ in range(3):
+        H.reference_step(oracle_be, ref, prm)
+        ch.step()
+    got = ch.export_pairs()                          # positions now differ in the last bits: same index sets
+    assert np.array_equal(got[0], ref.pairs[0]) and np.array_equal(got[1], ref.pairs[1])
+    d = ch.download()
+    for f in FIELDS:
+        assert_close(d[f], getattr(ref, f), f)
+    ch.close()
+
+
 @pytest.mark.parametrize("dp,seed,jitter", [(0.1, 1, 0.1), (0.05, 2, 0.3), (0.02, 3, 0.2)])
 def test_neighbor_build_bit_exact(sphb, H, oracle_be, dp, seed, jitter):
     prm = H.derive_params(dp=dp, c_f=10.0)

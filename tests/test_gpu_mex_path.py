@@ -83,6 +83,45 @@ def test_neighbor_single_column_matches_oracle(be, oracle_be):
             assert np.array_equal(got[k], want[k]), f"DL={DL}: {name}"
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_neighbor_clustered_clouds_match_oracle(be, oracle_be, seed):
+    """Dense clusters (hundreds of particles per cell, rows of several hundred neighbours), empty regions,
+    particles outside [0, DL) and on both sides of the periodic seam: the tile width is narrowed and the
+    list grown on the fly; the result is still the reference's list, bit for bit."""
+    rng = np.random.default_rng(seed)
+    h, DL = 0.05, 2.0
+    parts = [rng.random((300, 2)) * np.array([DL, 1.0])]                                # background
+    for cx, cy, n, s in ((0.02, 0.5, 400, 0.03), (1.98, 0.52, 300, 0.04), (1.0, 0.2, 500, 0.02), (0.6, 0.9, 250, 0.05)):
+        parts.append(np.array([cx, cy]) + rng.normal(size=(n, 2)) * s)                  # clusters (two at the seam)
+    pos = np.concatenate(parts)
+    pos[::7, 0] += DL * rng.integers(-2, 3, size=pos[::7, 0].shape)                     # unwrapped x
+    rng.shuffle(pos)
+    pos = np.asfortranarray(pos)
+    nt = pos.shape[0]
+    nf = int(0.8 * nt)
+    want = oracle_be.neighbor_search(pos, nf, nt, h, DL)
+    got = be.neighbor_search(pos, nf, nt, h, DL)
+    assert got[0].size == want[0].size and want[0].size > 50000
+    for k, name in enumerate(PAIR_NAMES):
+        assert np.array_equal(got[k], want[k]), name
+
+
+@pytest.mark.parametrize("ncols", [4, 5, 6, 7, 9, 12])
+def test_neighbor_short_periodic_boxes_match_oracle(be, oracle_be, ncols):
+    """Boxes only a few cell columns long: every walker is near the seam (ghost entries, both entries of a
+    particle inside one stencil, minimum-image shifts), the general walk does all the work."""
+    rng = np.random.default_rng(100 + ncols)
+    h = 0.05
+    DL = (ncols - 0.37) * 2.0 * h            # a sliver last column
+    n = 90 * ncols
+    pos = np.asfortranarray(rng.random((n, 2)) * np.array([DL, 0.9]))
+    nf = int(0.85 * n)
+    want = oracle_be.neighbor_search(pos, nf, n, h, DL)
+    got = be.neighbor_search(pos, nf, n, h, DL)
+    for k, name in enumerate(PAIR_NAMES):
+        assert np.array_equal(got[k], want[k]), f"{ncols} columns: {name}"
+
+
 def test_neighbor_error_identifiers(be, sphb):
     pos = np.zeros((4, 2), order="F")
     for args, ident in (((pos, 2, 5, 0.1, 1.0), "SPH:Neighbor:count"), ((pos, 5, 4, 0.1, 1.0), "SPH:Neighbor:count"),
