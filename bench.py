@@ -462,7 +462,7 @@ def b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, su
     if flags or not np.isfinite(st["vmax"]) or st["vmax"] > 10 * cfg.U_max:
         raise SystemExit(f"bench.py: sharded run invalid (flags={flags}, vmax={st['vmax']})")
     value = pt.n_total * K / (ms_total * 1e-3)
-    n_owned, n_halo, n_wall = sc.slab.counts()
+    n_owned, n_halo, n_wall = sc.slab.counts()      # owned region (incl. rows awaiting compaction), halo, walls
 
     # ---- end to end: host rows -> upload -> halo exchange -> list -> physics -> download, every step ----
     Ke = max(1, min(args.e2e_steps, K))

@@ -19,6 +19,7 @@ struct SlabState {
     int n_owned = 0, n_halo = 0;  // fluid rows: owned first, halo copies after
     int n_wall = 0;               // wall rows of the slab and its halo (static)
     int nf_cap = 0;               // fluid rows the buffers can hold
+    bool squeezed = false;        // a compaction ran since the last pack: unpack appends after its stayers
     DevBuf w_pos, w_mass, w_wall_vel;   // the static wall store
     DevBuf pid, a_pid;            // int[nf_cap] global identity of each fluid row
     DevBuf counts;                // int[16]: block-scan totals / new row counts (device)

@@ -47,7 +47,13 @@ struct NbrParams {
     size_t ell_stride;
     int slab;         // x-slab of a sharded channel: no wrap, no ghost entries, columns counted from col0
     int col0;         // global cell column of local column 0 (slab mode)
+    const int *alive; // slab mode: fluid row i takes part only if alive[i] >= 0 (rows that migrated away stay
+                      // in place, marked dead, until the next compaction); NULL = every row
 };
+__device__ __forceinline__ bool row_dead(const NbrParams &P, int i)
+{
+    return P.alive != nullptr && i < P.n_fluid && P.alive[i] < 0;
+}
 
 __device__ __forceinline__ long long ordered_key(double d)
 {
@@ -98,6 +104,7 @@ __global__ void __launch_bounds__(256) k_yrange_grid(const double2 *__restrict__
 {
     long long kmin = LLONG_MAX, kmax = LLONG_MIN;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (row_dead(P, i)) continue;
         long long k = ordered_key(pos[i].y);
         kmin = k < kmin ? k : kmin;
         kmax = k > kmax ? k : kmax;
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(kBlock) k_bin_count(const double2 *__restrict_
                                                      int *__restrict__ cell_of, int *__restrict__ cell_cnt)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_total) return;
+    if (i >= P.n_total || row_dead(P, i)) return;
     const Bins b = bin_particle(pos[i], P, g->y_min, g->ncy);
     snap[i] = make_double2(b.xw, b.y);
     const int row = b.cy * P.ncx;
@@ -206,7 +213,7 @@ __global__ void __launch_bounds__(kBlock) k_scatter(const double2 *__restrict__ 
                                                    int *__restrict__ tmp_cell)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_total) return;
+    if (i >= P.n_total || row_dead(P, i)) return;
     const Bins b = bin_particle(pos[i], P, g->y_min, g->ncy);
     const int row = b.cy * P.ncx;
     const int multi = (b.gcx_lo >= 0 || b.gcx_hi >= 0) ? 4 : 0;
@@ -859,6 +866,10 @@ __global__ void __launch_bounds__(kBlock) k_half_count(NbrParams P, int tile_w, 
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_fluid) return;
+    if (row_dead(P, i)) {
+        half_cnt[i] = 0;
+        return;
+    }
     const int e = ent_of[i];
     const TileDesc &T = tile_of_cell(tiles, cell_of[i], P.ncx, tile_w);
     const int n = (T.flags & kTileValid) ? min(cnt[e], P.ell_cap) : 0;
@@ -885,7 +896,7 @@ __global__ void __launch_bounds__(kBlock) k_export_pairs(NbrParams P, int tile_w
                                                         double *__restrict__ odW)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_fluid) return;
+    if (i >= P.n_fluid || row_dead(P, i)) return;
     const int ew = ent_of[i];
     const TileDesc &T = tile_of_cell(tiles, cell_of[i], P.ncx, tile_w);
     const double2 pi = ent_pos[ew];
@@ -922,6 +933,10 @@ __global__ void __launch_bounds__(kBlock) k_row_count(NbrParams P, int tile_w, c
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_fluid) return;
+    if (row_dead(P, i)) {
+        row_cnt[i] = 0;
+        return;
+    }
     const TileDesc &T = tile_of_cell(tiles, cell_of[i], P.ncx, tile_w);
     row_cnt[i] = (T.flags & kTileValid) ? min(cnt[ent_of[i]], P.ell_cap) : 0;
 }
@@ -933,7 +948,7 @@ __global__ void __launch_bounds__(kBlock) k_row_fill(NbrParams P, int tile_w, co
                                                     const int *__restrict__ row_ptr, int *__restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_fluid) return;
+    if (i >= P.n_fluid || row_dead(P, i)) return;
     const int e = ent_of[i];
     const TileDesc &T = tile_of_cell(tiles, cell_of[i], P.ncx, tile_w);
     const int n = (T.flags & kTileValid) ? min(cnt[e], P.ell_cap) : 0;
@@ -960,6 +975,7 @@ NbrParams make_params(const NeighborWork &w)
     P.ncx = ncx;
     P.slab = w.slab ? 1 : 0;
     P.col0 = w.col0;
+    P.alive = w.slab ? w.alive : nullptr;
     P.cell_cap = w.cell_cap;
     P.ell_cap = w.ell_cap;
     P.ell_stride = w.ell_stride;

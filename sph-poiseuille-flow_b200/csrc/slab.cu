@@ -54,14 +54,15 @@ __device__ __forceinline__ unsigned slab_class(double x, const SlabGeom &G)
     return m;
 }
 
-__global__ void __launch_bounds__(kSlabBlock) k_slab_count(const double2 *__restrict__ pos, SlabGeom G,
+__global__ void __launch_bounds__(kSlabBlock) k_slab_count(const double2 *__restrict__ pos,
+                                                          const int *__restrict__ pid, SlabGeom G,
                                                           int *__restrict__ block_tot)
 {
     __shared__ int tot[cN];
     if (threadIdx.x < cN) tot[threadIdx.x] = 0;
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned m = i < G.nfo ? slab_class(pos[i].x, G) : 0u;
+    const unsigned m = (i < G.nfo && pid[i] >= 0) ? slab_class(pos[i].x, G) : 0u;   // pid < 0: a row that has left
 #pragma unroll
     for (int k = 0; k < cN; ++k) {
         const unsigned b = __ballot_sync(0xffffffffu, (m >> k) & 1u);
@@ -121,7 +122,7 @@ struct SlabArrays {
     double2 *n_pos, *n_vel;
     double *n_rho, *n_drho, *n_mass, *n_Vol;
     Mat2 *n_B;
-    const int *pid;   // global particle identity, carried through every migration
+    int *pid;         // global particle identity, carried through every migration; -1 = the row has left
     int *n_pid;
 };
 
@@ -135,9 +136,8 @@ __device__ __forceinline__ void write_record(double *rec, double2 x, double2 v, 
     r[3] = make_double4((double)pid, 0.0, 0.0, 0.0);
 }
 
-// SEND: migrants and halo copies -> the two send buffers [migrants | copies]; !SEND: stayers -> compacted new
-// arrays.  Two launches so that the caller can put the buffers on the wire before the (much larger) stayer
-// copy runs: the NCCL transfer overlaps it.
+// SEND: migrants and halo copies -> the two send buffers [migrants | copies], migrants marked dead in place;
+// !SEND (now and then, sphb_ctx_slab_compact): the rows that stay -> compacted alternate arrays.
 template <bool SEND>
 __global__ void __launch_bounds__(kSlabBlock) k_slab_scatter(SlabArrays A, SlabGeom G,
                                                             const int *__restrict__ block_off,
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_scatter(SlabArrays A, SlabG
     __shared__ int warp_off[cN][kSlabBlock / 32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned m = i < G.nfo ? slab_class(A.pos[i].x, G) : 0u;
+    unsigned m = (i < G.nfo && A.pid[i] >= 0) ? slab_class(A.pos[i].x, G) : 0u;
     int rank[cN];
 #pragma unroll
     for (int k = 0; k < cN; ++k) {
@@ -199,6 +199,9 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_scatter(SlabArrays A, SlabG
             if (slot < rec_cap) write_record((left ? send_left : send_right) + kHdr + (size_t)slot * kRec, x, v, rho, drho, mass, Vol, B, pid);
         }
     }
+    // a row that migrates stays where it is, marked dead: the neighbour build skips it, so no kernel of the
+    // step ever visits it; sphb_ctx_slab_compact squeezes the dead rows out now and then
+    if (SEND && (m & ((1u << cMigL) | (1u << cMigR)))) A.pid[i] = -1;
 }
 
 struct UnpackSrc {
@@ -207,12 +210,14 @@ struct UnpackSrc {
 
 // new owned rows = [stayers | migrants from the left | migrants from the right];
 // new halo rows  = [copies from the left | copies from the right | own rows that left to the left | ... right]
+// The incoming rows are APPENDED to the owned region [0, base): stayers do not move (base = the high-water
+// mark of the owned rows, or the number of stayers right after a compaction).
 __global__ void __launch_bounds__(kSlabBlock) k_slab_unpack(UnpackSrc U, SlabArrays A, SlabGeom G, int rec_cap,
-                                                           int nf_cap, double rho0, double p0, double *n_p,
-                                                           double2 *n_wall_vel, int *counts, int *flags)
+                                                           int nf_cap, int base_host, int base_is_stay_count,
+                                                           int *counts, int *flags)
 {
     // segment sizes from the headers
-    const int n_stay = counts[cStay];
+    const int n_stay = base_is_stay_count ? counts[cStay] : base_host;
     int seg_n[6], seg_src[6], seg_first[6];
     const int nmL = min((int)U.buf[0][0], rec_cap), nhL = min((int)U.buf[0][1], rec_cap - nmL);
     const int nmR = min((int)U.buf[1][0], rec_cap), nhR = min((int)U.buf[1][1], rec_cap - nmR);
@@ -244,63 +249,68 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_unpack(UnpackSrc U, SlabArr
         if (d >= nf_cap) continue;
         const double4 *r = reinterpret_cast<const double4 *>(U.buf[seg_src[k]] + kHdr + (size_t)(seg_first[k] + off) * kRec);
         const double4 a = r[0], b = r[1], c = r[2];
-        A.n_pid[d] = (int)r[3].x;
+        A.pid[d] = (int)r[3].x;
         double x = a.x;
         if (k >= 2) {   // a halo copy sits next to the slab: across the periodic seam it is shifted by -+DL
             if (x > x_hi + margin) x -= G.DL;
             else if (x < x_lo - margin) x += G.DL;
         }
-        A.n_pos[d] = make_double2(x, a.y);
-        A.n_vel[d] = make_double2(a.z, a.w);
-        A.n_rho[d] = b.x;
-        A.n_drho[d] = b.y;
-        A.n_mass[d] = b.z;
-        A.n_Vol[d] = b.w;
+        const_cast<double2 *>(A.pos)[d] = make_double2(x, a.y);
+        const_cast<double2 *>(A.vel)[d] = make_double2(a.z, a.w);
+        const_cast<double *>(A.rho)[d] = b.x;
+        const_cast<double *>(A.drho)[d] = b.y;
+        const_cast<double *>(A.mass)[d] = b.z;
+        const_cast<double *>(A.Vol)[d] = b.w;
         Mat2 B;
         B.b11 = c.x;
         B.b12 = c.y;
         B.b21 = c.z;
         B.b22 = c.w;
-        A.n_B[d] = B;
+        const_cast<Mat2 *>(A.B)[d] = B;
     }
-    (void)rho0;
-    (void)p0;
-    (void)n_p;
-    (void)n_wall_vel;
 }
-
 // wall rows (static) after the fluid rows
 __global__ void __launch_bounds__(kSlabBlock) k_slab_walls(const int *__restrict__ counts, int nf_cap, int n_wall,
                                                           const double2 *__restrict__ w_pos,
                                                           const double *__restrict__ w_mass,
                                                           const double2 *__restrict__ w_wall_vel, double rho0,
-                                                          double p0, SlabArrays A, double2 *n_wall_vel, double *n_p)
+                                                          double p0, int first_new, SlabArrays A, double2 *wall_vel,
+                                                          double *p)
 {
     const int nf = min(counts[8] + counts[9], nf_cap);
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nf + n_wall; t += gridDim.x * blockDim.x) {
-        if (t < nf) {   // EOS of the new fluid rows (m:172); fluid rows carry no wall velocity
-            n_p[t] = p0 * (A.n_rho[t] / rho0 - 1.0);
-            n_wall_vel[t] = make_double2(0.0, 0.0);
+    double2 *pos = const_cast<double2 *>(A.pos), *vel = const_cast<double2 *>(A.vel);
+    double *rho = const_cast<double *>(A.rho), *drho = const_cast<double *>(A.drho);
+    double *mass = const_cast<double *>(A.mass), *Vol = const_cast<double *>(A.Vol);
+    Mat2 *Bm = const_cast<Mat2 *>(A.B);
+    for (int t = first_new + blockIdx.x * blockDim.x + threadIdx.x; t < nf + n_wall; t += gridDim.x * blockDim.x) {
+        if (t < nf) {   // EOS of the appended fluid rows (m:172); fluid rows carry no wall velocity
+            p[t] = p0 * (rho[t] / rho0 - 1.0);
+            wall_vel[t] = make_double2(0.0, 0.0);
             continue;
         }
         const int w = t - nf;
-        A.n_pos[t] = w_pos[w];
-        A.n_vel[t] = make_double2(0.0, 0.0);
-        A.n_rho[t] = rho0;
-        A.n_drho[t] = 0.0;
-        A.n_mass[t] = w_mass[w];
-        A.n_Vol[t] = w_mass[w] / rho0;
+        pos[t] = w_pos[w];
+        vel[t] = make_double2(0.0, 0.0);
+        rho[t] = rho0;
+        drho[t] = 0.0;
+        mass[t] = w_mass[w];
+        Vol[t] = w_mass[w] / rho0;
         Mat2 B;
         B.b11 = 1.0;
         B.b12 = 0.0;
         B.b21 = 0.0;
         B.b22 = 1.0;
-        A.n_B[t] = B;
-        n_wall_vel[t] = w_wall_vel[w];
-        n_p[t] = 0.0;
+        Bm[t] = B;
+        wall_vel[t] = w_wall_vel[w];
+        p[t] = 0.0;
     }
 }
 
+__global__ void k_slab_iota(int *p, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
 __global__ void k_slab_scalars_out(const DevScalars *sc, double *out)
 {
     out[0] = sc->vmax;
@@ -422,7 +432,11 @@ SPHB_API int sphb_ctx_slab_init(sphb_ctx *c, int col_lo, int col_hi, int halo_co
     if (!s.h_counts) SPHB_CUDA(cudaMallocHost((void **)&s.h_counts, 16 * sizeof(int)));
     SPHB_TRY(s.pid.reserve(((size_t)nf_cap + 1) * sizeof(int)));
     SPHB_TRY(s.a_pid.reserve(((size_t)nf_cap + 1) * sizeof(int)));
-    if (ids && n_owned) SPHB_CUDA(cudaMemcpyAsync(s.pid.p, ids, (size_t)n_owned * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    s.squeezed = false;
+    if (ids && n_owned)
+        SPHB_CUDA(cudaMemcpyAsync(s.pid.p, ids, (size_t)n_owned * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    else if (n_owned)
+        k_slab_iota<<<grid_for((size_t)n_owned), kBlock, 0, c->st>>>(s.pid.as<int>(), n_owned);
     double *stage = c->stage.as<double>();   // 4 * n_total doubles
     size_t used = 0;   // every array has its own staging region (6 * n_total doubles in all)
     auto up2 = [&](const double *src, size_t n, double2 *dst) -> int {
@@ -469,8 +483,10 @@ SPHB_API int sphb_ctx_slab_init(sphb_ctx *c, int col_lo, int col_hi, int halo_co
         const double width = (double)(col_hi - col_lo);
         c->nw.per_cell_hint = ((double)n_owned / width + (double)n_wall / (width + 2.0 * halo_cols)) / rows;
     }
-    apply_counts(c, nf_cap, 0);
-    SPHB_TRY(ctx_plan_lists(c, y_lo, y_hi));
+    if (!again || y_lo < c->y_lo || y_hi > c->y_hi) {   // a re-initialisation keeps the planned buffers
+        apply_counts(c, nf_cap, 0);
+        SPHB_TRY(ctx_plan_lists(c, y_lo, y_hi));
+    }
     apply_counts(c, n_owned, 0);
     c->have_list = false;
     SPHB_CUDA(cudaStreamSynchronize(c->st));
@@ -486,7 +502,7 @@ SPHB_API int sphb_ctx_slab_pack(sphb_ctx *c, double *send_left_dev, double *send
     const unsigned blocks = std::max(1u, grid_for((size_t)s.n_owned, kSlabBlock));
     int *bt = s.block_tot.as<int>(), *cnt = s.counts.as<int>();
     ProfScope ps(&c->kprof, kPfSlab, c->st);
-    k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), G, bt);
+    k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), s.pid.as<int>(), G, bt);
     k_slab_offsets<<<1, 1024, 0, c->st>>>(bt, (int)blocks, cnt);
     k_slab_scatter<true><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, bt, cnt, send_left_dev, send_right_dev,
                                                            rec_cap, c->nw.flags.as<int>());
@@ -495,19 +511,32 @@ SPHB_API int sphb_ctx_slab_pack(sphb_ctx *c, double *send_left_dev, double *send
     return 0;
 }
 
-// second half of the pack: the rows that stay are compacted into the alternate arrays (call it after the send
-// buffers have been handed to NCCL, before sphb_ctx_slab_unpack)
+// Squeeze the dead rows out of the owned region (now and then; between sphb_ctx_slab_pack, whose block scan
+// it reuses, and sphb_ctx_slab_unpack): the rows that stay are compacted into the alternate arrays, which
+// become the current ones.
 SPHB_API int sphb_ctx_slab_compact(sphb_ctx *c)
 {
     SLAB_ENTER();
     SlabState &s = c->slab;
     const SlabGeom G = geom_of(c);
     const unsigned blocks = std::max(1u, grid_for((size_t)s.n_owned, kSlabBlock));
-    ProfScope ps(&c->kprof, kPfSlab, c->st);
-    k_slab_scatter<false><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, s.block_tot.as<int>(), s.counts.as<int>(),
-                                                            nullptr, nullptr, 0, c->nw.flags.as<int>());
+    {
+        ProfScope ps(&c->kprof, kPfSlab, c->st);
+        k_slab_scatter<false><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, s.block_tot.as<int>(),
+                                                                s.counts.as<int>(), nullptr, nullptr, 0,
+                                                                c->nw.flags.as<int>());
+    }
     c->launches += 1;
     SPHB_CUDA(cudaGetLastError());
+    std::swap(c->pos, c->a_pos);
+    std::swap(c->vel, c->a_vel);
+    std::swap(c->rho, c->a_rho);
+    std::swap(c->drho_dt, c->a_drho_dt);
+    std::swap(c->mass, c->a_mass);
+    std::swap(c->Vol, c->a_Vol);
+    std::swap(c->B, c->a_B);
+    std::swap(s.pid, s.a_pid);
+    s.squeezed = true;   // the next unpack appends after the stayers counted by the pack
     return 0;
 }
 
@@ -525,32 +554,24 @@ SPHB_API int sphb_ctx_slab_unpack(sphb_ctx *c, const double *recv_left_dev, cons
     int *cnt = s.counts.as<int>();
     const SlabArrays A = arrays_of(c);
     {
-    ProfScope ps(&c->kprof, kPfSlab, c->st);
-    k_slab_unpack<<<148 * 2, kSlabBlock, 0, c->st>>>(U, A, G, rec_cap, s.nf_cap, c->prm.rho0, c->prm.p0,
-                                                     c->a_p.as<double>(), c->a_wall_vel.as<double2>(), cnt,
-                                                     c->nw.flags.as<int>());
-    k_slab_walls<<<148 * 2, kSlabBlock, 0, c->st>>>(cnt, s.nf_cap, s.n_wall, s.w_pos.as<double2>(), s.w_mass.as<double>(),
-                                                    s.w_wall_vel.as<double2>(), c->prm.rho0, c->prm.p0, A,
-                                                    c->a_wall_vel.as<double2>(), c->a_p.as<double>());
+        ProfScope ps(&c->kprof, kPfSlab, c->st);
+        k_slab_unpack<<<148 * 2, kSlabBlock, 0, c->st>>>(U, A, G, rec_cap, s.nf_cap, s.n_owned, s.squeezed ? 1 : 0, cnt,
+                                                         c->nw.flags.as<int>());
+        // appended rows start at the (possibly squeezed) end of the owned region; the walls follow the halo
+        k_slab_walls<<<148 * 2, kSlabBlock, 0, c->st>>>(cnt, s.nf_cap, s.n_wall, s.w_pos.as<double2>(),
+                                                        s.w_mass.as<double>(), s.w_wall_vel.as<double2>(), c->prm.rho0,
+                                                        c->prm.p0, s.squeezed ? 0 : s.n_owned, A, c->wall_vel.as<double2>(),
+                                                        c->p.as<double>());
     }
     c->launches += 2;
     SPHB_CUDA(cudaMemcpyAsync(s.h_counts, cnt, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     SPHB_CUDA(cudaStreamSynchronize(c->st));
     SPHB_CUDA(cudaGetLastError());
+    s.squeezed = false;
     const int n_owned = s.h_counts[8], n_halo = s.h_counts[9];
     if (n_owned + n_halo > s.nf_cap)
         return set_error("SPHB:capacity", "slab holds %d owned + %d halo fluid rows, capacity %d", n_owned, n_halo,
                          s.nf_cap);
-    std::swap(c->pos, c->a_pos);
-    std::swap(c->vel, c->a_vel);
-    std::swap(c->rho, c->a_rho);
-    std::swap(c->drho_dt, c->a_drho_dt);
-    std::swap(c->mass, c->a_mass);
-    std::swap(c->Vol, c->a_Vol);
-    std::swap(c->B, c->a_B);
-    std::swap(c->wall_vel, c->a_wall_vel);
-    std::swap(c->p, c->a_p);
-    std::swap(s.pid, s.a_pid);
     apply_counts(c, n_owned, n_halo);
     c->have_list = false;
     return 0;
@@ -568,6 +589,7 @@ SPHB_API int sphb_ctx_slab_step_begin(sphb_ctx *c, double remain)
 SPHB_API int sphb_ctx_slab_step_end(sphb_ctx *c)
 {
     SLAB_ENTER();
+    c->nw.alive = c->slab.pid.as<int>();   // rows that migrated away are skipped by the build
     SPHB_TRY(ctx_do_neighbor(c));
     SPHB_TRY(ctx_do_shear(c));
     return 0;

@@ -130,6 +130,7 @@ class Slab:
             _check(L.sphb_ctx_slab_vmax_import(self.ch._ctx, C.c_void_p(self.scal.data_ptr())))
 
     def counts(self):
+        """(owned region incl. rows that have left and await compaction, halo copies, wall rows)."""
         a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
         _check(lib().sphb_ctx_slab_counts(self.ch._ctx, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
@@ -142,8 +143,9 @@ class Slab:
         out = self.ch.download(fields)
         ids = np.zeros(n_owned + n_halo, dtype=np.int32)
         _check(lib().sphb_ctx_slab_ids(self.ch._ctx, ids.ctypes.data_as(_IP)))
-        res = {k: v[:n_owned] for k, v in out.items()}
-        res["ids"] = ids[:n_owned]
+        alive = ids[:n_owned] >= 0                    # rows that migrated away stay in place, marked -1
+        res = {k: v[:n_owned][alive] for k, v in out.items()}
+        res["ids"] = ids[:n_owned][alive]
         return res
 
     def reload(self, rows):
@@ -172,10 +174,11 @@ class SlabGroup:
     """All slabs of a channel on ONE GPU, exchanged by device copies: the single-process form of the
     sharded run (parity tests; fewer GPUs than slabs).  Same kernels, same buffers as the NCCL form."""
 
-    def __init__(self, cfg, pt, n_slabs: int, device="cuda:0", **kw):
+    def __init__(self, cfg, pt, n_slabs: int, device="cuda:0", compact_every: int = 64, **kw):
         cuts = partition_columns(n_columns(cfg), n_slabs)
         self.slabs = [Slab(cfg, pt, lo, hi, device, **kw) for lo, hi in cuts]
         self.n = n_slabs
+        self.compact_every, self._k = compact_every, 0
         self.tau = (0.0, 0.0)
         self.exchange()
         for s in self.slabs:
@@ -184,9 +187,11 @@ class SlabGroup:
     def exchange(self):
         import torch
         S = self.slabs
+        self._k += 1
         for s in S:
             s.pack()
-            s.compact()
+            if self.compact_every and self._k % self.compact_every == 0:
+                s.compact()                # squeeze out the rows that have left since the last compaction
         for s in S:
             s.ch.sync()
         scal = torch.stack([s.scal for s in S])
@@ -234,11 +239,12 @@ class SlabChannel:
     operations are stream-ordered; the only host synchronisation of a step is the read-back of the new
     row counts in unpack."""
 
-    def __init__(self, cfg, pt, rank: int, world: int, device, **kw):
+    def __init__(self, cfg, pt, rank: int, world: int, device, compact_every: int = 256, **kw):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.rank, self.world = rank, world
+        self.compact_every, self._k = compact_every, 0
         lo, hi = partition_columns(n_columns(cfg), world)[rank]
         self.slab = Slab(cfg, pt, lo, hi, device, **kw)
         s = self.slab
@@ -260,9 +266,12 @@ class SlabChannel:
 
     def _exchange(self):
         dist, s = self.dist, self.slab
+        self._k += 1
+        squeeze = self.compact_every and self._k % self.compact_every == 0
         s.pack()
         if self.world == 1:
-            s.compact()
+            if squeeze:
+                s.compact()
             s.recv_left.copy_(s.send_right)
             s.recv_right.copy_(s.send_left)
         else:
@@ -273,7 +282,8 @@ class SlabChannel:
             works = dist.batch_isend_irecv(ops)
             # max|v| -> time step of the next step (m:519-527); wall-shear partials (ph:1713-1742): one collective
             dist.all_gather_into_tensor(self._gath, s.scal[0:3])
-            s.compact()                       # the stayer copy runs while the buffers are on the wire
+            if squeeze:
+                s.compact()                   # now and then: squeeze out the rows that have left (overlaps the transfer)
             for w in works:
                 w.wait()
             _check(lib().sphb_ctx_slab_scalars_reduce(s.ch._ctx, C.c_void_p(self._gath.data_ptr()), C.c_int(self.world),
