@@ -216,6 +216,14 @@ SPHB_API int sphb_ctx_run_until(sphb_ctx *ctx, double t_target, double t_end, lo
  */
 SPHB_API int sphb_ctx_run_dual(sphb_ctx *ctx, int n_outer, int n_inner);
 
+/*
+ * Ensembles of independent channels (swept mu / g, ...): one context per channel, each with its own stream and
+ * cached graph; `n_outer` outer steps of every channel are enqueued round-robin from one host loop so that the
+ * small kernels of many channels overlap on the device.  Pure data parallelism: no communication.
+ */
+SPHB_API int sphb_ensemble_run_dual(sphb_ctx **ctxs, int n_ctx, int n_outer, int n_inner);
+SPHB_API int sphb_ensemble_sync(sphb_ctx **ctxs, int n_ctx);
+
 /* x-/bin-averaged u(y) of the fluid rows (m:579-605).  x0 < 0: all fluid rows (full-length profile). */
 SPHB_API int sphb_ctx_profile(sphb_ctx *ctx, double x0, double half_width, int n_bins, double *u_mean,
                               double *count);

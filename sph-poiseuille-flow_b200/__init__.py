@@ -460,6 +460,25 @@ class Channel:
         return int(lib().sphb_ctx_stream(self._ctx) or 0)
 
 
+class Ensemble:
+    """Independent channels stepped together (BASELINE.json configs[3]): one device-resident context per
+    channel, enqueued round-robin by sphb_ensemble_run_dual so their kernels overlap on the device."""
+
+    def __init__(self, channels):
+        self.channels = list(channels)
+        self._arr = (C.c_void_p * len(self.channels))(*[ch._ctx for ch in self.channels])
+
+    def run_dual(self, n_outer: int, n_inner: int = 1):
+        _check(lib().sphb_ensemble_run_dual(self._arr, C.c_int(len(self.channels)), C.c_int(n_outer), C.c_int(n_inner)))
+
+    def sync(self):
+        _check(lib().sphb_ensemble_sync(self._arr, C.c_int(len(self.channels))))
+
+    def close(self):
+        for ch in self.channels:
+            ch.close()
+
+
 def channel_from_config(cfg, particles, **overrides) -> Channel:
     """Channel for a channel_setup.ChannelConfig (after .derive()) and its Particles, state uploaded."""
     kw = dict(n_fluid=particles.n_fluid, n_total=particles.n_total, DL=cfg.DL, DH=cfg.DH, dp=cfg.dp, h=cfg.h,

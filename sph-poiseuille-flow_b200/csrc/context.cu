@@ -688,6 +688,27 @@ SPHB_API int sphb_ctx_run_dual(sphb_ctx *c, int n_outer, int n_inner)
     return 0;
 }
 
+// Ensembles of independent channels (BASELINE.json configs[3]; SURVEY.md 8(e) "replicas only"): every
+// channel is a context of its own with its own stream and its own cached graph; this call enqueues
+// `n_outer` outer steps of each of them round-robin from one host loop, so the small kernels of many
+// channels overlap on the device.  No data-path communication between channels.
+SPHB_API int sphb_ensemble_run_dual(sphb_ctx **ctxs, int n_ctx, int n_outer, int n_inner)
+{
+    clear_error();
+    if (!ctxs || n_ctx < 0) return set_error("SPHB:arg", "bad ensemble");
+    for (int o = 0; o < n_outer; ++o)
+        for (int k = 0; k < n_ctx; ++k) SPHB_TRY(sphb_ctx_run_dual(ctxs[k], 1, n_inner));
+    return 0;
+}
+
+SPHB_API int sphb_ensemble_sync(sphb_ctx **ctxs, int n_ctx)
+{
+    clear_error();
+    if (!ctxs || n_ctx < 0) return set_error("SPHB:arg", "bad ensemble");
+    for (int k = 0; k < n_ctx; ++k) SPHB_TRY(sphb_ctx_sync(ctxs[k]));
+    return 0;
+}
+
 SPHB_API int sphb_ctx_profile(sphb_ctx *c, double x0, double half_width, int n_bins, double *u_mean, double *count)
 {
     CTX_ENTER(false);

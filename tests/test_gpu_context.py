@@ -362,3 +362,36 @@ def test_full_size_one_step_against_oracle(sphb, H, oracle_be):
         assert_close(d[f], getattr(ref, f), f)
     assert_close(np.array([s["tau_bottom"], s["tau_top"]]), np.array([ref.tau_bottom, ref.tau_top]), "tau")
     ch.close()
+
+
+def test_ensemble_equals_separate_runs(sphb, H):
+    """Channels stepped together as an ensemble (round-robin graph launches on their own streams) give the
+    bits of the same channels stepped one after the other."""
+    import importlib
+    cs = importlib.import_module("sph_b200.channel_setup")
+    cfgs = [cs.ChannelConfig(DL=1.0, dp=0.04, mu=mu, U_bulk=ub, c_f=10.0).derive()
+            for mu, ub in ((0.05, 0.4), (0.1, 0.666667), (0.2, 1.0), (0.08, 0.5))]
+    pts = [cs.developed(c, seed=30 + k) for k, c in enumerate(cfgs)]
+
+    def make():
+        out = []
+        for c, p in zip(cfgs, pts):
+            ch = sphb.channel_from_config(c, p, sort_interval=0)
+            ch.initialise()
+            out.append(ch)
+        return out
+
+    a, b = make(), make()
+    ens = sphb.Ensemble(a)
+    ens.run_dual(7, 1)
+    ens.sync()
+    for ch in b:
+        ch.run_dual(7, 1)
+    for x, y in zip(a, b):
+        dx, dy = x.download(), y.download()
+        for f in FIELDS:
+            assert np.array_equal(dx[f], dy[f]), f
+        assert x.status()["t"] == y.status()["t"] and x.status()["error_flags"] == 0
+    ens.close()
+    for ch in b:
+        ch.close()
