@@ -96,6 +96,9 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
+NCU_EXTRA = {}      # pipe utilisation of the kernel ncu_traffic() was last asked about (same capture)
+
+
 def ncu_traffic(kernel: str):
     """DRAM bytes per launch of `kernel` from the newest committed ncu summary (profiles/*_ncu_summary.json,
     written by tools/ncu_to_profile.py from an `ncu --set full` capture of this same command)."""
@@ -107,7 +110,12 @@ def ncu_traffic(kernel: str):
         return None, None
     try:
         rec = json.load(open(files[-1])).get(names[kernel])
-        return (rec[0]["dram_bytes"], os.path.relpath(files[-1], ROOT)) if rec else (None, None)
+        if not rec:
+            return None, None
+        NCU_EXTRA.clear()
+        NCU_EXTRA.update({k: rec[0].get(k) for k in ("duration_us", "fp64_pipe_pct", "lsu_wavefronts_pct",
+                                                     "issue_active_pct", "warps_active_pct", "dram_throughput_pct")})
+        return rec[0]["dram_bytes"], os.path.relpath(files[-1], ROOT)
     except (OSError, ValueError, KeyError, IndexError):
         return None, None
 
@@ -204,7 +212,8 @@ def reference_arm(args):
     if rank != 0:
         return 0
     lp = load_product()
-    cfg = lp.ChannelConfig(DL=args.DL, dp=args.dp).derive()
+    sharded = args.gpus > 1 and args.mode in ("auto", "slab")      # the B200 arm then runs ONE channel of length N * DL
+    cfg = lp.ChannelConfig(DL=args.DL * (args.gpus if sharded else 1), dp=args.dp).derive()
     # bounded sample: shrink the channel length (same dp, same physics, per-particle cost unchanged)
     # until (steps + warmup) outer steps fit in ~150 s at ~1.2e-6 s per particle-substep-equivalent
     DL = cfg.DL
@@ -370,7 +379,7 @@ def b200_arm(args):
         traffic, traffic_src = ncu_traffic(top)
         roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                 "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "alg_bytes_per_launch": per_launch_bytes,
+                "alg_bytes_per_launch": per_launch_bytes, "ncu": dict(NCU_EXTRA),
                 "alg_bytes_per_particle": ALG_BYTES_KERNEL[top], "ms_per_launch": kernels[top]["ms_per_call"],
                 "share_of_step": kernels[top]["share"],
                 "step_frac": (value / world) * ALG_BYTES_SUBSTEP / (hbm * 1e9),
@@ -521,7 +530,7 @@ def b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, su
         roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                 "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "alg_bytes_per_particle": ALG_BYTES_KERNEL[top], "ms_per_launch": kernels[top]["ms_per_call"],
-                "share_of_step": kernels[top]["share"], "rows_per_launch": nl,
+                "share_of_step": kernels[top]["share"], "rows_per_launch": nl, "ncu": dict(NCU_EXTRA),
                 "step_frac": (value / world) * ALG_BYTES_SUBSTEP / (hbm * 1e9),
                 "kernel_ms_per_step_rank0": total / max(1, args.profile_steps)}
     total_launches = sum_over_ranks(float(launches))
