@@ -605,18 +605,56 @@ SPHB_API int sphb_ctx_step(sphb_ctx *c, double remain)
     return 0;
 }
 
+namespace {
+
+// clock, dt and flags only (one small D2H, no kernel): the per-step read-back of sphb_ctx_run_until
+int status_light(sphb_ctx *c, sphb_status *out)
+{
+    SPHB_CUDA(cudaMemcpyAsync(c->h_scalars, c->sc(), sizeof(DevScalars), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaMemcpyAsync(c->h_ints + 2, c->nw.flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    out->t = c->h_scalars->t;
+    out->dt = c->h_scalars->dt;
+    out->vmax = c->h_scalars->vmax;
+    out->step = c->h_scalars->step;
+    out->error_flags = c->h_ints[2];
+    return 0;
+}
+
+// A list that outgrew its row or tile capacity during a run (the state itself is intact: the build only
+// reads it): clear the flags, rebuild with the exact, growing build and redo the monitor of the step.
+int recover_list_capacity(sphb_ctx *c)
+{
+    int f = 0;
+    SPHB_CUDA(cudaMemcpyAsync(&f, c->nw.flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    f &= ~(kErrCsrCap | kErrTileCap);
+    SPHB_CUDA(cudaMemcpyAsync(c->nw.flags.p, &f, sizeof(int), cudaMemcpyHostToDevice, c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    c->list_sized = false;
+    SPHB_TRY(do_neighbor(c));
+    SPHB_TRY(do_shear(c));
+    return 0;
+}
+
+}  // namespace
+
 SPHB_API int sphb_ctx_run_until(sphb_ctx *c, double t_target, double t_end, long long max_steps,
                                 long long *steps_done)
 {
     CTX_ENTER(true);
     long long n = 0;
-    sphb_status s;
-    SPHB_TRY(sphb_ctx_status(c, &s));
+    sphb_status s{};
+    SPHB_TRY(status_light(c, &s));
     while (s.t < t_target - 1e-12 && (max_steps <= 0 || n < max_steps)) {   // m:250
         const double remain = fmin(t_target - s.t, t_end - s.t);           // m:252
         SPHB_TRY(sphb_ctx_step(c, remain));
-        SPHB_TRY(sphb_ctx_status(c, &s));
+        SPHB_TRY(status_light(c, &s));
         ++n;
+        if ((s.error_flags & (kErrCsrCap | kErrTileCap)) && !(s.error_flags & ~(kErrCsrCap | kErrTileCap))) {
+            SPHB_TRY(recover_list_capacity(c));
+            SPHB_TRY(status_light(c, &s));
+        }
         if (s.error_flags) return set_error("SPHB:capacity", "device error flags %d at step %lld", s.error_flags, s.step);
         if (s.dt < 1e-14) return set_error("SPHB:diverged", "time step collapsed (dt=%g) at t=%g step=%lld", s.dt, s.t, s.step);   // m:260-263
     }

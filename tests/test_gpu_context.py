@@ -395,3 +395,29 @@ def test_ensemble_equals_separate_runs(sphb, H):
     ens.close()
     for ch in b:
         ch.close()
+
+
+def test_run_until_recovers_from_list_capacity(sphb, H):
+    """A list that outgrows the row / tile capacity fitted at the first build (here: the particles are squeezed
+    to twice the density between two uploads) raises device flags; sphb_ctx_run_until rebuilds the list with
+    the growing build and carries on instead of failing."""
+    prm = H.derive_params(dp=0.05, c_f=10.0)
+    st = H.developed_state(prm, seed=9, jitter=0.1)
+    ch = make_channel(sphb, prm, st)
+    ch.initialise()                                   # capacities fitted to this state
+    _, n_before = ch.neighbor_count()
+    pos = st.pos.copy(order="F")
+    nf = st.n_fluid
+    pos[:nf, 0] = 0.5 * pos[:nf, 0] + 0.25 * prm.DL   # fluid squeezed into the middle half of the channel
+    ch.upload(pos=pos)
+    ch.neighbor_build()                               # steady-state build: overflows, raises flags
+    assert ch.status()["error_flags"] != 0
+    n = ch.run_until(ch.status()["t"] + 2e-4, 1.0, max_steps=2)
+    assert n >= 1
+    s = ch.status()
+    assert s["error_flags"] == 0
+    _, n_after = ch.neighbor_count()
+    assert n_after > 1.5 * n_before
+    d = ch.download(("pos", "vel", "rho"))
+    assert all(np.all(np.isfinite(d[k])) for k in d)
+    ch.close()
