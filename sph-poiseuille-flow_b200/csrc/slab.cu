@@ -27,19 +27,21 @@ enum { cStay = 0, cMigL, cHaloL, cMigR, cHaloR, cN };
 
 struct SlabGeom {
     int col_lo, width, halo, ncx_g;
-    double cell, DL;
+    double cell, inv_cell, DL;
     int nfo;
 };
 
-// class bits of an owned fluid row (nb:253,270 binning of the wrapped x)
+// class bits of an owned fluid row.  Owned rows are kept wrapped by the continuity kernel, so the wrap
+// (nb:270) is a rare branch, and the column is taken with a multiply: a row within rounding of a column
+// boundary may be classed one column off the list build's exact binning (nb:253), which only moves it
+// between "owned near the edge" and "first halo column" -- both are valid places for it.
 __device__ __forceinline__ unsigned slab_class(double x, const SlabGeom &G)
 {
-    const double xw = x - floor(x / G.DL) * G.DL;
-    int c = (int)floor(xw / G.cell);
+    if (!(x >= 0.0 && x < G.DL)) x -= floor(x / G.DL) * G.DL;
+    int c = (int)(x * G.inv_cell);
     if (c >= G.ncx_g) c = G.ncx_g - 1;
     if (c < 0) c = 0;
     int d = c - G.col_lo;
-    d %= G.ncx_g;
     if (d < 0) d += G.ncx_g;
     unsigned m = 0;
     if (d < G.width) {
@@ -72,13 +74,14 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_count(const double2 *__rest
     if (threadIdx.x < cN) block_tot[threadIdx.x * gridDim.x + blockIdx.x] = tot[threadIdx.x];
 }
 
-// exclusive scan of the block totals of each class (one CTA; blocks <= a few thousand), totals -> counts
+// exclusive scan of the block totals of each class (one CTA per class; blocks <= a few thousand), totals -> counts
 __global__ void __launch_bounds__(1024) k_slab_offsets(int *__restrict__ block_tot, int blocks, int *__restrict__ counts)
 {
     __shared__ int warp_sum[32];
     __shared__ int chunk_total, carry;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int k = 0; k < cN; ++k) {
+    {
+        const int k = blockIdx.x;
         int *v = block_tot + (size_t)k * blocks;
         if (threadIdx.x == 0) carry = 0;
         __syncthreads();
@@ -343,6 +346,7 @@ SlabGeom geom_of(const sphb_ctx *c)
     G.halo = c->slab.halo;
     G.ncx_g = c->slab.ncx_global;
     G.cell = 2.0 * c->prm.h;
+    G.inv_cell = 1.0 / G.cell;
     G.DL = c->prm.DL;
     G.nfo = c->slab.n_owned;
     return G;
@@ -503,7 +507,7 @@ SPHB_API int sphb_ctx_slab_pack(sphb_ctx *c, double *send_left_dev, double *send
     int *bt = s.block_tot.as<int>(), *cnt = s.counts.as<int>();
     ProfScope ps(&c->kprof, kPfSlab, c->st);
     k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), s.pid.as<int>(), G, bt);
-    k_slab_offsets<<<1, 1024, 0, c->st>>>(bt, (int)blocks, cnt);
+    k_slab_offsets<<<cN, 1024, 0, c->st>>>(bt, (int)blocks, cnt);
     k_slab_scatter<true><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, bt, cnt, send_left_dev, send_right_dev,
                                                            rec_cap, c->nw.flags.as<int>());
     c->launches += 3;
