@@ -291,6 +291,9 @@ SPHB_API int sphb_ctx_slab_vmax_import(sphb_ctx *ctx, const double *in_dev1);
 /* the scalars of all ranks after an all-gather ([world][3], device): max|v| (MAX) into the context; the
  * reduced (max|v|, sum tau_bottom, sum tau_top) to out_dev3 (may be NULL) */
 SPHB_API int sphb_ctx_slab_scalars_reduce(sphb_ctx *ctx, const double *gathered_dev, int world, double *out_dev3);
+/* same with the triple of rank r at gathered_dev + offsets_dev[r] (in doubles; device array of `world` int64) */
+SPHB_API int sphb_ctx_slab_scalars_reduce_at(sphb_ctx *ctx, const double *gathered_dev, const long long *offsets_dev,
+                                             int world, double *out_dev3);
 SPHB_API int sphb_ctx_slab_counts(sphb_ctx *ctx, int *n_owned, int *n_halo, int *n_wall);
 
 #ifdef __cplusplus

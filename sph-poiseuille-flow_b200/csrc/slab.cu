@@ -321,14 +321,16 @@ __global__ void k_slab_scalars_out(const DevScalars *sc, double *out)
     out[2] = sc->tau_top;
 }
 __global__ void k_slab_vmax_in(DevScalars *sc, const double *in) { sc->vmax = in[0]; }
-// all-gathered [world][3] scalars -> max|v| (MAX) and the wall-shear sums (SUM, in rank order: deterministic)
-__global__ void k_slab_scalars_reduce(DevScalars *sc, const double *g, int world, double *out3)
+// the scalars of every rank (triple r at g + off[r], or at g + 3 r when off is NULL) -> max|v| (MAX) and the
+// wall-shear sums (SUM, in rank order: deterministic)
+__global__ void k_slab_scalars_reduce(DevScalars *sc, const double *g, const long long *off, int world, double *out3)
 {
     double vmax = 0.0, tb = 0.0, tt = 0.0;
     for (int r = 0; r < world; ++r) {
-        vmax = fmax(vmax, g[3 * r]);
-        tb += g[3 * r + 1];
-        tt += g[3 * r + 2];
+        const double *t = g + (off ? off[r] : 3LL * r);
+        vmax = fmax(vmax, t[0]);
+        tb += t[1];
+        tt += t[2];
     }
     sc->vmax = vmax;
     if (out3) {
@@ -630,7 +632,18 @@ SPHB_API int sphb_ctx_slab_ids(sphb_ctx *c, int *ids)
 SPHB_API int sphb_ctx_slab_scalars_reduce(sphb_ctx *c, const double *gathered_dev, int world, double *out_dev3)
 {
     SLAB_ENTER();
-    k_slab_scalars_reduce<<<1, 1, 0, c->st>>>(c->sc(), gathered_dev, world, out_dev3);
+    k_slab_scalars_reduce<<<1, 1, 0, c->st>>>(c->sc(), gathered_dev, nullptr, world, out_dev3);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// same, the triple of rank r at gathered_dev + offsets_dev[r] (doubles): for callers that move the scalars
+// inside the same all-to-all as the record buffers
+SPHB_API int sphb_ctx_slab_scalars_reduce_at(sphb_ctx *c, const double *gathered_dev, const long long *offsets_dev,
+                                             int world, double *out_dev3)
+{
+    SLAB_ENTER();
+    k_slab_scalars_reduce<<<1, 1, 0, c->st>>>(c->sc(), gathered_dev, offsets_dev, world, out_dev3);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }

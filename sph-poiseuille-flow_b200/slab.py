@@ -234,10 +234,11 @@ class SlabGroup:
 
 
 class SlabChannel:
-    """One rank of the sharded channel: its slab, and the exchange over torch.distributed (backend "nccl":
-    send/recv over NVLink).  The library launches on torch's current stream, so its kernels and the NCCL
-    operations are stream-ordered; the only host synchronisation of a step is the read-back of the new
-    row counts in unpack."""
+    """One rank of the sharded channel: its slab, and the exchange over torch.distributed (backend "nccl").
+    The two record buffers and the rank's scalars travel in ONE uneven all-to-all per step (NCCL send/recv
+    over NVLink underneath): the left / right neighbour gets a record buffer + the scalars, every other rank
+    the scalars only.  The library launches on the stream torch uses, so its kernels and the collective are
+    stream-ordered; the only host synchronisation of a step is the read-back of the new row counts."""
 
     def __init__(self, cfg, pt, rank: int, world: int, device, compact_every: int = 256, **kw):
         import torch
@@ -251,8 +252,31 @@ class SlabChannel:
         self.left, self.right = (rank - 1) % world, (rank + 1) % world
         self.stream = torch.cuda.Stream(device=s.device)     # shared by the library's kernels and torch / NCCL
         _check(lib().sphb_ctx_set_stream(s.ch._ctx, C.c_void_p(self.stream.cuda_stream)))
-        self._gath = torch.zeros(world * 3, dtype=torch.float64, device=s.device)
         self._red = torch.zeros(3, dtype=torch.float64, device=s.device)   # max|v|, sum tau_bottom, sum tau_top
+        # all-to-all layout: the chunk for / from rank d = [4 scalars][record buffer(s) if d is a neighbour]
+        nbuf, S = s.send_left.numel(), 4
+        def chunk(d):
+            return S + (nbuf if d == self.left else 0) + (nbuf if d == self.right else 0)
+        self._split = [chunk(d) for d in range(world)]                 # symmetric: what I send d = what d sends me
+        offs = np.concatenate([[0], np.cumsum(self._split)]).astype(np.int64)
+        total = int(offs[-1])
+        self._xin = torch.zeros(total, dtype=torch.float64, device=s.device)
+        self._xout = torch.zeros(total, dtype=torch.float64, device=s.device)
+        self._scal_off = torch.tensor(offs[:-1], dtype=torch.int64, device=s.device)
+        self._head_idx = torch.tensor(np.concatenate([o + np.arange(3) for o in offs[:-1]]), dtype=torch.int64,
+                                      device=s.device)
+
+        def part(t, d, which):      # record buffer inside the chunk of rank d (which = 0 first, 1 second)
+            o = int(offs[d]) + S + which * nbuf
+            return t[o:o + nbuf]
+        if world > 1:
+            if self.left == self.right:      # two ranks: both buffers go to / come from the same peer
+                s.send_left, s.send_right = part(self._xin, self.left, 0), part(self._xin, self.left, 1)
+                # the peer's "to its left" is for me as its left neighbour = what I receive from my right
+                s.recv_right, s.recv_left = part(self._xout, self.left, 0), part(self._xout, self.left, 1)
+            else:
+                s.send_left, s.send_right = part(self._xin, self.left, 0), part(self._xin, self.right, 0)
+                s.recv_left, s.recv_right = part(self._xout, self.left, 0), part(self._xout, self.right, 0)
         self.exchange()
         s.step_end()
 
@@ -274,21 +298,18 @@ class SlabChannel:
                 s.compact()
             s.recv_left.copy_(s.send_right)
             s.recv_right.copy_(s.send_left)
-        else:
-            # a rank's "to the right" arrives as its neighbour's "from the left"; with two ranks both
-            # messages travel between the same pair, matched in posting order
-            ops = [dist.P2POp(dist.isend, s.send_left, self.left), dist.P2POp(dist.isend, s.send_right, self.right),
-                   dist.P2POp(dist.irecv, s.recv_right, self.right), dist.P2POp(dist.irecv, s.recv_left, self.left)]
-            works = dist.batch_isend_irecv(ops)
-            # max|v| -> time step of the next step (m:519-527); wall-shear partials (ph:1713-1742): one collective
-            dist.all_gather_into_tensor(self._gath, s.scal[0:3])
-            if squeeze:
-                s.compact()                   # now and then: squeeze out the rows that have left (overlaps the transfer)
-            for w in works:
-                w.wait()
-            _check(lib().sphb_ctx_slab_scalars_reduce(s.ch._ctx, C.c_void_p(self._gath.data_ptr()), C.c_int(self.world),
-                                                      C.c_void_p(self._red.data_ptr())))
-        s.unpack(import_vmax=self.world == 1)
+            s.unpack(import_vmax=True)
+            return
+        self._xin.index_copy_(0, self._head_idx, s.scal[0:3].repeat(self.world))     # my scalars head every chunk
+        work = dist.all_to_all_single(self._xout, self._xin, self._split, self._split, async_op=True)
+        if squeeze:
+            s.compact()                   # now and then: squeeze out the rows that have left (overlaps the transfer)
+        work.wait()
+        # max|v| -> time step of the next step (m:519-527); wall-shear partials (ph:1713-1742)
+        _check(lib().sphb_ctx_slab_scalars_reduce_at(s.ch._ctx, C.c_void_p(self._xout.data_ptr()),
+                                                     C.c_void_p(self._scal_off.data_ptr()), C.c_int(self.world),
+                                                     C.c_void_p(self._red.data_ptr())))
+        s.unpack(import_vmax=False)
 
     def step(self, remain=float("inf")):
         with self.torch.cuda.stream(self.stream):
