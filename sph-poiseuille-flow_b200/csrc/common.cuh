@@ -95,6 +95,7 @@ struct NeighborWork {
     bool slab = false;           // x-slab of a sharded channel (no wrap, no ghosts; set before neighbor_plan)
     int col0 = 0;                // global cell column of local column 0 (slab mode)
     int ncx_local = 0;           // local cell columns (slab mode)
+    const int *dev_counts = nullptr;   // slab mode: {n_fluid, owned, n_total} in device memory (see slab.cu)
     const int *alive = nullptr;  // slab mode: rows with alive[i] < 0 have migrated away and are skipped
     double per_cell_hint = 0.0;  // entries per cell the tile width is planned for (0 = n_total / cells)
     bool half_only = false;      // the last build kept only the reference's half list

@@ -47,9 +47,17 @@ struct NbrParams {
     size_t ell_stride;
     int slab;         // x-slab of a sharded channel: no wrap, no ghost entries, columns counted from col0
     int col0;         // global cell column of local column 0 (slab mode)
+    const int *dev_counts;   // slab mode: {n_fluid, owned, n_total} live in device memory; NULL = the values above
     const int *alive; // slab mode: fluid row i takes part only if alive[i] >= 0 (rows that migrated away stay
                       // in place, marked dead, until the next compaction); NULL = every row
 };
+__device__ __forceinline__ void load_counts(NbrParams &P)
+{
+    if (P.dev_counts) {
+        P.n_fluid = P.dev_counts[0];
+        P.n_total = P.dev_counts[2];
+    }
+}
 __device__ __forceinline__ bool row_dead(const NbrParams &P, int i)
 {
     return P.alive != nullptr && i < P.n_fluid && P.alive[i] < 0;
@@ -102,6 +110,8 @@ __global__ void k_grid_init(GridDesc *g)
 __global__ void __launch_bounds__(256) k_yrange_grid(const double2 *__restrict__ pos, int n, GridDesc *g, NbrParams P,
                                                     int *flags, int *totals)
 {
+    load_counts(P);
+    if (P.dev_counts) n = P.n_total;
     long long kmin = LLONG_MAX, kmax = LLONG_MIN;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (row_dead(P, i)) continue;
@@ -195,6 +205,7 @@ __global__ void __launch_bounds__(kBlock) k_bin_count(const double2 *__restrict_
                                                      const GridDesc *__restrict__ g, double2 *__restrict__ snap,
                                                      int *__restrict__ cell_of, int *__restrict__ cell_cnt)
 {
+    load_counts(P);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_total || row_dead(P, i)) return;
     const Bins b = bin_particle(pos[i], P, g->y_min, g->ncy);
@@ -212,6 +223,7 @@ __global__ void __launch_bounds__(kBlock) k_scatter(const double2 *__restrict__ 
                                                    int *__restrict__ tmp_key, double2 *__restrict__ tmp_pos,
                                                    int *__restrict__ tmp_cell)
 {
+    load_counts(P);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_total || row_dead(P, i)) return;
     const Bins b = bin_particle(pos[i], P, g->y_min, g->ncy);
@@ -653,6 +665,7 @@ __global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, cons
                                                            int *__restrict__ cnt, int *__restrict__ totals,
                                                            int *__restrict__ flags, int cap)
 {
+    load_counts(P);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ TileDesc T;
     double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
@@ -818,6 +831,7 @@ __global__ void __launch_bounds__(kTileThreads) k_half_total(NbrParams P, const 
                                                             const int *__restrict__ cnt, int *__restrict__ totals,
                                                             int cap)
 {
+    load_counts(P);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ TileDesc T;
     int *s_key = reinterpret_cast<int *>(smem_raw);
@@ -864,9 +878,11 @@ __global__ void __launch_bounds__(kBlock) k_half_count(NbrParams P, int tile_w, 
                                                       const uint4 *__restrict__ ell_q,
                                                       const int *__restrict__ cnt, int *__restrict__ half_cnt)
 {
+    const int n_launch = P.n_fluid;   // slab mode: the capacity; rows beyond the live count get empty rows
+    load_counts(P);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_fluid) return;
-    if (row_dead(P, i)) {
+    if (i >= n_launch) return;
+    if (i >= P.n_fluid || row_dead(P, i)) {
         half_cnt[i] = 0;
         return;
     }
@@ -895,6 +911,7 @@ __global__ void __launch_bounds__(kBlock) k_export_pairs(NbrParams P, int tile_w
                                                         double *__restrict__ orr, double *__restrict__ oW,
                                                         double *__restrict__ odW)
 {
+    load_counts(P);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_fluid || row_dead(P, i)) return;
     const int ew = ent_of[i];
@@ -931,9 +948,11 @@ __global__ void __launch_bounds__(kBlock) k_row_count(NbrParams P, int tile_w, c
                                                      const int *__restrict__ ent_of,
                                                      const int *__restrict__ cnt, int *__restrict__ row_cnt)
 {
+    const int n_launch = P.n_fluid;   // slab mode: the capacity; rows beyond the live count get empty rows
+    load_counts(P);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_fluid) return;
-    if (row_dead(P, i)) {
+    if (i >= n_launch) return;
+    if (i >= P.n_fluid || row_dead(P, i)) {
         row_cnt[i] = 0;
         return;
     }
@@ -947,6 +966,7 @@ __global__ void __launch_bounds__(kBlock) k_row_fill(NbrParams P, int tile_w, co
                                                     const uint4 *__restrict__ ell_q, const int *__restrict__ cnt,
                                                     const int *__restrict__ row_ptr, int *__restrict__ out)
 {
+    load_counts(P);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_fluid || row_dead(P, i)) return;
     const int e = ent_of[i];
@@ -976,6 +996,7 @@ NbrParams make_params(const NeighborWork &w)
     P.slab = w.slab ? 1 : 0;
     P.col0 = w.col0;
     P.alive = w.slab ? w.alive : nullptr;
+    P.dev_counts = w.slab ? w.dev_counts : nullptr;
     P.cell_cap = w.cell_cap;
     P.ell_cap = w.ell_cap;
     P.ell_stride = w.ell_stride;

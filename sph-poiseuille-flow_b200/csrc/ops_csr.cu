@@ -184,6 +184,7 @@ __device__ __forceinline__ void density_rows(const PhysParams &P, const StateVie
 
 __global__ void __launch_bounds__(kTileThreads) k_density(PhysParams P, StateView S)
 {
+    load_counts(P);
     SPHB_TILE_BEGIN();
     const OwnPre pre = tile_prefetch_own(S, T);
     double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
@@ -241,6 +242,7 @@ __device__ __forceinline__ void kgc_rows(const PhysParams &P, const StateView &S
 
 __global__ void __launch_bounds__(kTileThreads) k_kgc(PhysParams P, StateView S)
 {
+    load_counts(P);
     SPHB_TILE_BEGIN();
     const OwnPre pre = tile_prefetch_own(S, T);
     double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
@@ -332,6 +334,7 @@ __device__ __forceinline__ void visc_transport_rows(const PhysParams &P, const S
 template <bool VISC, bool TRANSP>
 __global__ void __launch_bounds__(kTileThreads) k_visc_transport(PhysParams P, StateView S, int add_gravity)
 {
+    load_counts(P);
     SPHB_TILE_BEGIN();
     const OwnPre pre = tile_prefetch_own(S, T);
     double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
@@ -384,6 +387,7 @@ __device__ __forceinline__ double half_step_rho(double rho, double drho, double 
 __global__ void __launch_bounds__(kBlock) k_time_step(PhysParams P, StateView S, DevScalars *sc, double remain,
                                                      double fixed_dt)
 {
+    load_counts(P);
     double dt;
     if (fixed_dt > 0.0) {
         dt = fixed_dt;
@@ -406,12 +410,6 @@ __global__ void __launch_bounds__(kBlock) k_time_step(PhysParams P, StateView S,
     }
 }
 
-__global__ void k_advance_clock(DevScalars *sc)
-{
-    sc->t += sc->dt;
-    sc->step += 1;
-    sc->vmax = __longlong_as_double((long long)sc->vmax_bits);
-}
 
 // ---------------------------------------------------------------- P4 + velocity kick + position update
 // staged per slot: position, volume (sign bit = wall); for fluid entries also velocity, half-step
@@ -481,6 +479,7 @@ __device__ __forceinline__ void pressure_rows(const PhysParams &P, const StateVi
 
 __global__ void __launch_bounds__(kTileThreads) k_pressure(PhysParams P, StateView S, const DevScalars *__restrict__ sc)
 {
+    load_counts(P);
     SPHB_TILE_BEGIN();
     const OwnPre pre = tile_prefetch_own(S, T);
     double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
@@ -653,6 +652,7 @@ __device__ __forceinline__ void force_rows(const PhysParams &P, const StateView 
 __global__ void __launch_bounds__(kTileThreads) k_force_fused(PhysParams P, StateView S, DevScalars *sc, double remain,
                                                              double fixed_dt, int add_gravity)
 {
+    load_counts(P);
     (void)remain;
     (void)fixed_dt;
     const double dt = sc->dt;   // published by k_publish_dt on the same stream
@@ -769,6 +769,7 @@ __device__ __forceinline__ double continuity_rows(const PhysParams &P, const Sta
 __global__ void __launch_bounds__(kTileThreads) k_continuity(PhysParams P, StateView S, DevScalars *sc, int do_wrap,
                                                             int advance_clock)
 {
+    load_counts(P);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ TileDesc T;
     tile_load(T, S.tiles, blockIdx.x);
@@ -858,6 +859,7 @@ __global__ void __launch_bounds__(kBlock) k_wrap(int nf, double DL, double2 *pos
 // One partial (bottom, top) per tile, summed in tile order by k_wall_shear_final: deterministic.
 __global__ void __launch_bounds__(kTileThreads) k_wall_shear(PhysParams P, StateView S, double *partials)
 {
+    load_counts(P);
     __shared__ double shb[kTileThreads], sht[kTileThreads];
     const unsigned nt = gridDim.x;
     if (threadIdx.x == 0) {
@@ -961,6 +963,7 @@ __global__ void __launch_bounds__(kBlock) k_profile(PhysParams P, StateView S, d
                                                    int n_bins, const double *__restrict__ edges, double *sum,
                                                    double *cnt)
 {
+    load_counts(P);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.nf) return;
     const double2 x = S.pos[i];
@@ -1067,12 +1070,6 @@ int csr_force_fused(const PhysParams &P, const StateView &S, DevScalars *sc, dou
     k_publish_dt<<<1, 1, 0, st>>>(P, sc, remain, fixed_dt);
     k_force_fused<<<S.n_tiles, kTileThreads, (size_t)S.tile_cap * kPressureSlot, st>>>(P, S, sc, remain, fixed_dt,
                                                                                        add_gravity ? 1 : 0);
-    SPHB_CUDA(cudaGetLastError());
-    return 0;
-}
-int csr_advance_clock(DevScalars *sc, cudaStream_t st)
-{
-    k_advance_clock<<<1, 1, 0, st>>>(sc);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }

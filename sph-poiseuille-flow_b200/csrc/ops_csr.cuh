@@ -27,7 +27,19 @@ struct PhysParams {
     double inv_h;      // 1/h
     double sigma_h;    // sigma/h
     double inv_rho0;   // 1/rho0
+    const int *dev_counts;   // slab mode: {nf, nfo, nt} live in device memory (they change every step and the
+                             // host never waits for them); NULL = the values above
 };
+#ifdef __CUDACC__
+__device__ __forceinline__ void load_counts(PhysParams &P)
+{
+    if (P.dev_counts) {
+        P.nf = P.dev_counts[0];
+        P.nfo = P.dev_counts[1];
+        P.nt = P.dev_counts[2];
+    }
+}
+#endif
 
 // SoA state in HBM.  2-vectors are double2 (one 128-bit load per particle), B is one 32-byte record.
 struct StateView {
@@ -63,7 +75,6 @@ int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool
                    cudaStream_t st);                                                             // P5 + finish (+ clock)
 int csr_force_fused(const PhysParams &P, const StateView &S, DevScalars *sc, double remain, double fixed_dt,
                     bool add_gravity, cudaStream_t st);                                          // P2 + P3 + dt + P4
-int csr_advance_clock(DevScalars *sc, cudaStream_t st);                                          // t += dt, step++, vmax
 int csr_vmax(const PhysParams &P, const double2 *vel, DevScalars *sc, cudaStream_t st);          // standalone reduction
 int csr_wrap(const PhysParams &P, double2 *pos, cudaStream_t st);                                // m:570-577
 int csr_wall_shear(const PhysParams &P, const StateView &S, DevScalars *sc, double *partials, cudaStream_t st);  // P8

@@ -28,7 +28,7 @@ enum { cStay = 0, cMigL, cHaloL, cMigR, cHaloR, cN };
 struct SlabGeom {
     int col_lo, width, halo, ncx_g;
     double cell, inv_cell, DL;
-    int nfo;
+    const int *cur;   // device {nf, nfo, nt} of the current rows (counts + 12)
 };
 
 // class bits of an owned fluid row.  Owned rows are kept wrapped by the continuity kernel, so the wrap
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_count(const double2 *__rest
     if (threadIdx.x < cN) tot[threadIdx.x] = 0;
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned m = (i < G.nfo && pid[i] >= 0) ? slab_class(pos[i].x, G) : 0u;   // pid < 0: a row that has left
+    const unsigned m = (i < G.cur[1] && pid[i] >= 0) ? slab_class(pos[i].x, G) : 0u;   // pid < 0: a row that has left
 #pragma unroll
     for (int k = 0; k < cN; ++k) {
         const unsigned b = __ballot_sync(0xffffffffu, (m >> k) & 1u);
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_scatter(SlabArrays A, SlabG
     __shared__ int warp_off[cN][kSlabBlock / 32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned m = (i < G.nfo && A.pid[i] >= 0) ? slab_class(A.pos[i].x, G) : 0u;
+    unsigned m = (i < G.cur[1] && A.pid[i] >= 0) ? slab_class(A.pos[i].x, G) : 0u;
     int rank[cN];
 #pragma unroll
     for (int k = 0; k < cN; ++k) {
@@ -216,11 +216,11 @@ struct UnpackSrc {
 // The incoming rows are APPENDED to the owned region [0, base): stayers do not move (base = the high-water
 // mark of the owned rows, or the number of stayers right after a compaction).
 __global__ void __launch_bounds__(kSlabBlock) k_slab_unpack(UnpackSrc U, SlabArrays A, SlabGeom G, int rec_cap,
-                                                           int nf_cap, int base_host, int base_is_stay_count,
-                                                           int *counts, int *flags)
+                                                           int nf_cap, int base_is_stay_count, int *counts,
+                                                           int *flags)
 {
     // segment sizes from the headers
-    const int n_stay = base_is_stay_count ? counts[cStay] : base_host;
+    const int n_stay = base_is_stay_count ? counts[cStay] : counts[13];
     int seg_n[6], seg_src[6], seg_first[6];
     const int nmL = min((int)U.buf[0][0], rec_cap), nhL = min((int)U.buf[0][1], rec_cap - nmL);
     const int nmR = min((int)U.buf[1][0], rec_cap), nhR = min((int)U.buf[1][1], rec_cap - nmR);
@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_unpack(UnpackSrc U, SlabArr
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         counts[8] = n_owned;
         counts[9] = n_fluid - n_owned;
+        counts[10] = n_stay;   // first appended row
         if (n_fluid > nf_cap) atomicOr(flags, kErrSlabCap);
     }
     const double x_lo = (double)G.col_lo * G.cell, x_hi = (double)(G.col_lo + G.width) * G.cell;
@@ -277,10 +278,11 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_walls(const int *__restrict
                                                           const double2 *__restrict__ w_pos,
                                                           const double *__restrict__ w_mass,
                                                           const double2 *__restrict__ w_wall_vel, double rho0,
-                                                          double p0, int first_new, SlabArrays A, double2 *wall_vel,
+                                                          double p0, int all_rows, SlabArrays A, double2 *wall_vel,
                                                           double *p)
 {
     const int nf = min(counts[8] + counts[9], nf_cap);
+    const int first_new = all_rows ? 0 : counts[10];
     double2 *pos = const_cast<double2 *>(A.pos), *vel = const_cast<double2 *>(A.vel);
     double *rho = const_cast<double *>(A.rho), *drho = const_cast<double *>(A.drho);
     double *mass = const_cast<double *>(A.mass), *Vol = const_cast<double *>(A.Vol);
@@ -309,6 +311,20 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_walls(const int *__restrict
     }
 }
 
+// the new row counts become current: {nf, nfo, nt} read by every kernel of the next step
+__global__ void k_slab_commit_counts(int *counts, int nf_cap, int n_wall)
+{
+    const int n_owned = min(counts[8], nf_cap), nf = min(counts[8] + counts[9], nf_cap);
+    counts[12] = nf;
+    counts[13] = n_owned;
+    counts[14] = nf + n_wall;
+}
+__global__ void k_slab_set_counts(int *counts, int nf, int nfo, int nt)
+{
+    counts[12] = nf;
+    counts[13] = nfo;
+    counts[14] = nt;
+}
 __global__ void k_slab_iota(int *p, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -350,7 +366,7 @@ SlabGeom geom_of(const sphb_ctx *c)
     G.cell = 2.0 * c->prm.h;
     G.inv_cell = 1.0 / G.cell;
     G.DL = c->prm.DL;
-    G.nfo = c->slab.n_owned;
+    G.cur = c->slab.counts.as<int>() + 12;
     return G;
 }
 
@@ -376,10 +392,11 @@ SlabArrays arrays_of(sphb_ctx *c)
     return A;
 }
 
+// Host-side values used for launch sizes and by-value kernel parameters.  In steady state they stay at the
+// CAPACITY (the rows of a slab change every step and the host never waits for the new counts: the kernels
+// read {nf, nfo, nt} from device memory, PhysParams::dev_counts).
 void apply_counts(sphb_ctx *c, int n_owned, int n_halo)
 {
-    c->slab.n_owned = n_owned;
-    c->slab.n_halo = n_halo;
     const int nf = n_owned + n_halo, nt = nf + c->slab.n_wall;
     c->prm.n_fluid = nf;
     c->prm.n_total = nt;
@@ -388,6 +405,17 @@ void apply_counts(sphb_ctx *c, int n_owned, int n_halo)
     c->P.nt = nt;
     c->nw.n_fluid = nf;
     c->nw.n_total = nt;
+}
+
+// the current row counts, read back from the device (the one place the host waits for them)
+int refresh_counts(sphb_ctx *c)
+{
+    SlabState &s = c->slab;
+    SPHB_CUDA(cudaMemcpyAsync(s.h_counts, s.counts.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    s.n_owned = s.h_counts[13];
+    s.n_halo = s.h_counts[12] - s.h_counts[13];
+    return 0;
 }
 
 }  // namespace
@@ -466,6 +494,10 @@ SPHB_API int sphb_ctx_slab_init(sphb_ctx *c, int col_lo, int col_hi, int halo_co
         SPHB_CUDA(cudaMemcpyAsync(c->mass.p, mass, no * sizeof(double), cudaMemcpyHostToDevice, c->st));
     }
     apply_counts(c, n_owned, 0);
+    s.n_owned = n_owned;
+    s.n_halo = 0;
+    k_slab_set_counts<<<1, 1, 0, c->st>>>(s.counts.as<int>(), n_owned, n_owned, n_owned + n_wall);
+    c->P.dev_counts = nullptr;   // the set-up kernels below run with the exact host values
     // Vol = m / rho (m:120), B = I already
     SPHB_TRY(ctx_volumes_from_mass(c));
     SPHB_TRY(csr_vmax(c->P, c->vel.as<double2>(), c->sc(), c->st));
@@ -493,7 +525,11 @@ SPHB_API int sphb_ctx_slab_init(sphb_ctx *c, int col_lo, int col_hi, int halo_co
         apply_counts(c, nf_cap, 0);
         SPHB_TRY(ctx_plan_lists(c, y_lo, y_hi));
     }
-    apply_counts(c, n_owned, 0);
+    // from here on: launch sizes = capacity, actual counts on the device
+    apply_counts(c, nf_cap, 0);
+    c->P.nfo = nf_cap;
+    c->P.dev_counts = s.counts.as<int>() + 12;
+    c->nw.dev_counts = c->P.dev_counts;
     c->have_list = false;
     SPHB_CUDA(cudaStreamSynchronize(c->st));
     return 0;
@@ -505,7 +541,7 @@ SPHB_API int sphb_ctx_slab_pack(sphb_ctx *c, double *send_left_dev, double *send
     if (!send_left_dev || !send_right_dev || rec_cap < 1) return set_error("SPHB:arg", "bad send buffers");
     SlabState &s = c->slab;
     const SlabGeom G = geom_of(c);
-    const unsigned blocks = std::max(1u, grid_for((size_t)s.n_owned, kSlabBlock));
+    const unsigned blocks = std::max(1u, grid_for((size_t)s.nf_cap, kSlabBlock));
     int *bt = s.block_tot.as<int>(), *cnt = s.counts.as<int>();
     ProfScope ps(&c->kprof, kPfSlab, c->st);
     k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), s.pid.as<int>(), G, bt);
@@ -525,7 +561,7 @@ SPHB_API int sphb_ctx_slab_compact(sphb_ctx *c)
     SLAB_ENTER();
     SlabState &s = c->slab;
     const SlabGeom G = geom_of(c);
-    const unsigned blocks = std::max(1u, grid_for((size_t)s.n_owned, kSlabBlock));
+    const unsigned blocks = std::max(1u, grid_for((size_t)s.nf_cap, kSlabBlock));
     {
         ProfScope ps(&c->kprof, kPfSlab, c->st);
         k_slab_scatter<false><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, s.block_tot.as<int>(),
@@ -561,26 +597,20 @@ SPHB_API int sphb_ctx_slab_unpack(sphb_ctx *c, const double *recv_left_dev, cons
     const SlabArrays A = arrays_of(c);
     {
         ProfScope ps(&c->kprof, kPfSlab, c->st);
-        k_slab_unpack<<<148 * 2, kSlabBlock, 0, c->st>>>(U, A, G, rec_cap, s.nf_cap, s.n_owned, s.squeezed ? 1 : 0, cnt,
+        k_slab_unpack<<<148 * 2, kSlabBlock, 0, c->st>>>(U, A, G, rec_cap, s.nf_cap, s.squeezed ? 1 : 0, cnt,
                                                          c->nw.flags.as<int>());
         // appended rows start at the (possibly squeezed) end of the owned region; the walls follow the halo
         k_slab_walls<<<148 * 2, kSlabBlock, 0, c->st>>>(cnt, s.nf_cap, s.n_wall, s.w_pos.as<double2>(),
                                                         s.w_mass.as<double>(), s.w_wall_vel.as<double2>(), c->prm.rho0,
-                                                        c->prm.p0, s.squeezed ? 0 : s.n_owned, A, c->wall_vel.as<double2>(),
+                                                        c->prm.p0, s.squeezed ? 1 : 0, A, c->wall_vel.as<double2>(),
                                                         c->p.as<double>());
+        k_slab_commit_counts<<<1, 1, 0, c->st>>>(cnt, s.nf_cap, s.n_wall);
     }
-    c->launches += 2;
-    SPHB_CUDA(cudaMemcpyAsync(s.h_counts, cnt, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
-    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    c->launches += 3;
     SPHB_CUDA(cudaGetLastError());
     s.squeezed = false;
-    const int n_owned = s.h_counts[8], n_halo = s.h_counts[9];
-    if (n_owned + n_halo > s.nf_cap)
-        return set_error("SPHB:capacity", "slab holds %d owned + %d halo fluid rows, capacity %d", n_owned, n_halo,
-                         s.nf_cap);
-    apply_counts(c, n_owned, n_halo);
     c->have_list = false;
-    return 0;
+    return 0;   // asynchronous: a capacity overflow raises the device flag (sphb_status.error_flags)
 }
 
 // first half of a reference step on the slab: density + KGC, forces, continuity (m:254-270)
@@ -622,6 +652,7 @@ SPHB_API int sphb_ctx_slab_vmax_import(sphb_ctx *c, const double *in_dev)
 SPHB_API int sphb_ctx_slab_ids(sphb_ctx *c, int *ids)
 {
     SLAB_ENTER();
+    SPHB_TRY(refresh_counts(c));
     const size_t n = (size_t)(c->slab.n_owned + c->slab.n_halo);
     if (n) SPHB_CUDA(cudaMemcpyAsync(ids, c->slab.pid.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     SPHB_CUDA(cudaStreamSynchronize(c->st));
@@ -651,6 +682,10 @@ SPHB_API int sphb_ctx_slab_scalars_reduce_at(sphb_ctx *c, const double *gathered
 SPHB_API int sphb_ctx_slab_counts(sphb_ctx *c, int *n_owned, int *n_halo, int *n_wall)
 {
     SLAB_ENTER();
+    SPHB_TRY(refresh_counts(c));
+    if (c->slab.n_owned + c->slab.n_halo > c->slab.nf_cap)
+        return set_error("SPHB:capacity", "slab holds %d owned + %d halo fluid rows, capacity %d", c->slab.n_owned,
+                         c->slab.n_halo, c->slab.nf_cap);
     if (n_owned) *n_owned = c->slab.n_owned;
     if (n_halo) *n_halo = c->slab.n_halo;
     if (n_wall) *n_wall = c->slab.n_wall;

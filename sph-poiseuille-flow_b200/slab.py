@@ -138,9 +138,7 @@ class Slab:
     def owned(self, fields=("pos", "vel", "rho", "p", "drho_dt")):
         """Owned fluid rows with their global ids: {"ids": ..., field: ...}."""
         n_owned, n_halo, n_wall = self.counts()
-        self.ch.prm.n_total = n_owned + n_halo + n_wall
-        self.ch.prm.n_fluid = n_owned + n_halo
-        out = self.ch.download(fields)
+        out = self.ch.download(fields)              # capacity-sized arrays (the context is sized for its capacity)
         ids = np.zeros(n_owned + n_halo, dtype=np.int32)
         _check(lib().sphb_ctx_slab_ids(self.ch._ctx, ids.ctypes.data_as(_IP)))
         alive = ids[:n_owned] >= 0                    # rows that migrated away stay in place, marked -1

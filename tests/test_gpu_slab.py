@@ -38,12 +38,11 @@ def _single(sphb, cfg, pt):
 def _global_rows(s, sl):
     """Neighbour sets of the owned rows of one slab as {global id: sorted global neighbour ids}."""
     n_owned, n_halo, n_wall = sl.counts()
-    sl.ch.prm.n_fluid, sl.ch.prm.n_total = n_owned + n_halo, n_owned + n_halo + n_wall
-    row_ptr, col = sl.ch.export_csr()
+    row_ptr, col = sl.ch.export_csr()                # rows of the whole capacity; those beyond the live rows are empty
     ids = np.zeros(n_owned + n_halo, dtype=np.int32)
     from ctypes import POINTER, c_int
     s._check(s.lib().sphb_ctx_slab_ids(sl.ch._ctx, ids.ctypes.data_as(POINTER(c_int))))
-    gid = np.concatenate([ids.astype(np.int64), sl._keep["wall_ids"].astype(np.int64)])
+    gid = np.concatenate([ids.astype(np.int64), sl._keep["wall_ids"].astype(np.int64)])   # local row -> global id
     out = {}
     for r in range(n_owned):
         if ids[r] >= 0:                      # a row that migrated away (awaiting compaction) is nobody's
