@@ -75,6 +75,7 @@ def parse_args():
     ap.add_argument("--no-presort", action="store_true",
                     help="time from the raw lattice order instead of the order after the reference's first cell "
                          "sort (m:272, 529-568)")
+    ap.add_argument("--no-graph", action="store_true", help="sharded mode: eager launches instead of one CUDA graph per step")
     ap.add_argument("--channels", type=int, default=512,
                     help="--mode ensemble: independent channels PER GPU (BASELINE configs[3]: 4096 in all at 8 GPUs)")
     ap.add_argument("--mode", default="auto", choices=("auto", "slab", "replicas", "ensemble"),
@@ -444,7 +445,7 @@ def b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, su
         pt = lp.channel_setup.cell_sorted(cfg, pt)                    # row order after the reference's cell sort
     K, W = args.steps, max(args.warmup, 3)
     dev = torch.device("cuda", local_rank)
-    sc = slabmod.SlabChannel(cfg, pt, rank, world, dev)
+    sc = slabmod.SlabChannel(cfg, pt, rank, world, dev, use_graph=not args.no_graph)
     ch = sc.slab.ch
     stream = sc.stream                           # the library's kernels, torch and NCCL share this stream in slab mode
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -477,6 +478,7 @@ def b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, su
     value = pt.n_total * K / (ms_total * 1e-3)
     n_owned, n_halo, n_wall = sc.slab.counts()      # owned region (incl. rows awaiting compaction), halo, walls
 
+    graph_used = bool(sc.use_graph and sc._graph_ok and sc._graph is not None)
     # ---- end to end: host rows -> upload -> halo exchange -> list -> physics -> download, every step ----
     Ke = max(1, min(args.e2e_steps, K))
     fields = ("pos", "vel", "rho", "drho_dt")
@@ -515,6 +517,7 @@ def b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, su
         pass
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    sc.use_graph = False                       # per-kernel events need eager launches
     ch.kernel_profile(enable=1, reset=True)
     for _ in range(max(1, args.profile_steps)):
         sc.step()
@@ -549,6 +552,7 @@ def b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, su
                        "parallelism": f"x-slabs on cell-column boundaries, {slabmod.HALO_COLS} halo columns, one "
                                       f"exchange per step (migration + halo copies: NCCL send/recv; max|v|, shear: "
                                       f"all-reduce)",
+                       "step_launch": "one CUDA graph per step (kernels + NCCL all-to-all)" if graph_used else "eager",
                        "rows_rank0": {"owned": n_owned, "halo": n_halo, "wall": n_wall}},
             "e2e": {"value": e2e_value, "unit": "particle-substeps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke,

@@ -238,12 +238,14 @@ class SlabChannel:
     the scalars only.  The library launches on the stream torch uses, so its kernels and the collective are
     stream-ordered; the only host synchronisation of a step is the read-back of the new row counts."""
 
-    def __init__(self, cfg, pt, rank: int, world: int, device, compact_every: int = 256, **kw):
+    def __init__(self, cfg, pt, rank: int, world: int, device, compact_every: int = 256, use_graph: bool = False,
+                 **kw):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.rank, self.world = rank, world
         self.compact_every, self._k = compact_every, 0
+        self.use_graph, self._graph, self._graph_ok = use_graph, None, True
         lo, hi = partition_columns(n_columns(cfg), world)[rank]
         self.slab = Slab(cfg, pt, lo, hi, device, **kw)
         s = self.slab
@@ -309,11 +311,47 @@ class SlabChannel:
                                                      C.c_void_p(self._red.data_ptr())))
         s.unpack(import_vmax=False)
 
+    def _body(self, remain):
+        self.slab.step_begin(remain)
+        self._exchange()
+        self.slab.step_end()
+
     def step(self, remain=float("inf")):
-        with self.torch.cuda.stream(self.stream):
-            self.slab.step_begin(remain)
-            self._exchange()
-            self.slab.step_end()
+        """One reference step of the sharded channel.  With use_graph the whole step -- the library's kernels and
+        the NCCL all-to-all, all on one stream, row counts on the device -- is captured once as a CUDA graph
+        and replayed (remain = inf only); the now-and-then compaction step runs eagerly and the graph is
+        captured again afterwards (the compaction swaps the state buffers)."""
+        torch = self.torch
+        squeeze_next = self.compact_every and (self._k + 1) % self.compact_every == 0
+        if not (self.use_graph and self._graph_ok and remain == float("inf") and self.world > 1) or squeeze_next:
+            with torch.cuda.stream(self.stream):
+                self._body(remain)
+            if squeeze_next:
+                self._graph = None
+            return
+        if self._graph is None:
+            k0 = self._k
+            try:
+                self.stream.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    self._body(remain)
+                self._graph = g
+                self._k = k0 + 1          # the capture enqueued nothing: replay it as this step
+            except Exception:             # capture not possible here: stay eager
+                self._graph_ok, self._graph, self._k = False, None, k0
+                with torch.cuda.stream(self.stream):
+                    self._body(remain)
+                return
+        else:
+            self._k += 1
+        with torch.cuda.stream(self.stream):
+            self._graph.replay()
 
     def close(self):
+        """Drop the captured graph (it holds NCCL work: do this BEFORE destroying the process group) and the slab."""
+        self._graph = None
         self.slab.close()
+
+    def __del__(self):
+        self._graph = None
