@@ -8,12 +8,17 @@
 // WITHOUT any mid-step exchange.  Once per step, before the list rebuild:
 //     pack    owned rows are classified by their new column: stay / migrate left / migrate right, and
 //             stayers within H columns of an edge are also copied for that neighbour (deterministic
-//             block-scan compaction, no atomics); records = x y vx vy rho drho_dt mass Vol B(4)
-//     (the caller moves the two buffers to the neighbours: NCCL send/recv over NVLink)
-//     unpack  new owned rows = stayers + immigrants; new halo rows = received copies + the rows that just
-//             left (their new owner sits next door); copies from across the periodic seam are shifted
-//             by -+DL exactly like the reference's ghost entries (nb:284,291); wall rows (static) follow
-// plus a MAX all-reduce of max|v| (time step, m:519-527) and a SUM of the wall-shear partials by the caller.
+//             block-scan ranks, no atomics); records = x y vx vy rho drho_dt mass Vol B(4) id.  A row that
+//             migrates is marked dead IN PLACE (the list build skips it, so no kernel visits it again)
+//     (the caller moves the two buffers to the neighbours and the scalars to everybody: one NCCL all-to-all)
+//     unpack  incoming rows are APPENDED: owned += immigrants; halo = received copies + the rows that just
+//             left (their new owner sits next door); copies from across the periodic seam are shifted by
+//             -+DL exactly like the reference's ghost entries (nb:284,291); wall rows (static) follow
+//     compact (now and then) squeezes the dead rows out of the owned region
+// plus max|v| (MAX: time step, m:519-527) and the wall-shear partials (SUM) reduced over the ranks.
+// The row counts {nf, owned, nt} live in DEVICE memory and every kernel reads them there
+// (PhysParams::dev_counts); launch sizes are the capacity.  A step therefore has no host synchronisation
+// and can be captured -- kernels and collective -- as one CUDA graph (slab.py).
 // Positions stay in GLOBAL coordinates (the cell column is global, counted from col0), so the pair
 // arithmetic away from the seam is bit-identical to the single-domain run.
 #include "context.cuh"
@@ -119,9 +124,9 @@ __global__ void __launch_bounds__(1024) k_slab_offsets(int *__restrict__ block_t
 }
 
 struct SlabArrays {
-    const double2 *pos, *vel;
-    const double *rho, *drho, *mass, *Vol;
-    const Mat2 *B;
+    double2 *pos, *vel;     // current rows (appended to in place by the unpack)
+    double *rho, *drho, *mass, *Vol;
+    Mat2 *B;
     double2 *n_pos, *n_vel;
     double *n_rho, *n_drho, *n_mass, *n_Vol;
     Mat2 *n_B;
@@ -259,18 +264,18 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_unpack(UnpackSrc U, SlabArr
             if (x > x_hi + margin) x -= G.DL;
             else if (x < x_lo - margin) x += G.DL;
         }
-        const_cast<double2 *>(A.pos)[d] = make_double2(x, a.y);
-        const_cast<double2 *>(A.vel)[d] = make_double2(a.z, a.w);
-        const_cast<double *>(A.rho)[d] = b.x;
-        const_cast<double *>(A.drho)[d] = b.y;
-        const_cast<double *>(A.mass)[d] = b.z;
-        const_cast<double *>(A.Vol)[d] = b.w;
+        A.pos[d] = make_double2(x, a.y);
+        A.vel[d] = make_double2(a.z, a.w);
+        A.rho[d] = b.x;
+        A.drho[d] = b.y;
+        A.mass[d] = b.z;
+        A.Vol[d] = b.w;
         Mat2 B;
         B.b11 = c.x;
         B.b12 = c.y;
         B.b21 = c.z;
         B.b22 = c.w;
-        const_cast<Mat2 *>(A.B)[d] = B;
+        A.B[d] = B;
     }
 }
 // wall rows (static) after the fluid rows
@@ -283,10 +288,9 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_walls(const int *__restrict
 {
     const int nf = min(counts[8] + counts[9], nf_cap);
     const int first_new = all_rows ? 0 : counts[10];
-    double2 *pos = const_cast<double2 *>(A.pos), *vel = const_cast<double2 *>(A.vel);
-    double *rho = const_cast<double *>(A.rho), *drho = const_cast<double *>(A.drho);
-    double *mass = const_cast<double *>(A.mass), *Vol = const_cast<double *>(A.Vol);
-    Mat2 *Bm = const_cast<Mat2 *>(A.B);
+    double2 *pos = A.pos, *vel = A.vel;
+    double *rho = A.rho, *drho = A.drho, *mass = A.mass, *Vol = A.Vol;
+    Mat2 *Bm = A.B;
     for (int t = first_new + blockIdx.x * blockDim.x + threadIdx.x; t < nf + n_wall; t += gridDim.x * blockDim.x) {
         if (t < nf) {   // EOS of the appended fluid rows (m:172); fluid rows carry no wall velocity
             p[t] = p0 * (rho[t] / rho0 - 1.0);
