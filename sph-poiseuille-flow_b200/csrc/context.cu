@@ -306,7 +306,7 @@ SPHB_API void sphb_ctx_destroy(sphb_ctx *c)
                      &c->scalars, &c->shear_partials, &c->stage, &c->prof, &c->rp_half};
     for (DevBuf *b : all) b->release();
     for (DevBuf *b : {&c->slab.w_pos, &c->slab.w_mass, &c->slab.w_wall_vel, &c->slab.counts, &c->slab.block_tot,
-                      &c->slab.pid, &c->slab.a_pid})
+                      &c->slab.pid, &c->slab.a_pid, &c->slab.sort_flag, &c->slab.sort_ptr})
         b->release();
     if (c->slab.h_counts) cudaFreeHost(c->slab.h_counts);
     c->nw.release_all();

@@ -22,6 +22,7 @@ struct SlabState {
     bool squeezed = false;        // a compaction ran since the last pack: unpack appends after its stayers
     DevBuf w_pos, w_mass, w_wall_vel;   // the static wall store
     DevBuf pid, a_pid;            // int[nf_cap] global identity of each fluid row
+    DevBuf sort_flag, sort_ptr;   // int[entry capacity + 1] scratch of the cell-ordered compaction
     DevBuf counts;                // int[16]: block-scan totals / new row counts (device)
     DevBuf block_tot;             // int[5 * blocks]
     int *h_counts = nullptr;      // pinned mirror

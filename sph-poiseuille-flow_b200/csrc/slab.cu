@@ -212,6 +212,40 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_scatter(SlabArrays A, SlabG
     if (SEND && (m & ((1u << cMigL) | (1u << cMigR)))) A.pid[i] = -1;
 }
 
+// Compaction in CELL order (the slab form of the reference's periodic cell sort, m:529-568): the rows that
+// stay are visited through the cell-sorted entry array of the last list build, so the compacted rows come
+// out sorted by (cell row, cell column) and the staging loads of the gather kernels stay coalesced.
+__global__ void __launch_bounds__(kSlabBlock) k_slab_sort_flags(const int *__restrict__ ent_key,
+                                                               const GridDesc *__restrict__ g, int ent_cap,
+                                                               SlabArrays A, SlabGeom G, int *__restrict__ flag)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ent_cap) return;
+    int f = 0;
+    if (e < g->n_entries) {
+        const int key = ent_key[e];
+        const int i = key >> 3;
+        if ((key & 3) == 0 && i < G.cur[1] && A.pid[i] >= 0) f = (slab_class(A.pos[i].x, G) >> cStay) & 1u;
+    }
+    flag[e] = f;
+}
+__global__ void __launch_bounds__(kSlabBlock) k_slab_sort_move(const int *__restrict__ ent_key,
+                                                              const int *__restrict__ flag,
+                                                              const int *__restrict__ ptr, int ent_cap, SlabArrays A)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ent_cap || !flag[e]) return;
+    const int i = ent_key[e] >> 3, d = ptr[e];
+    A.n_pos[d] = A.pos[i];
+    A.n_vel[d] = A.vel[i];
+    A.n_rho[d] = A.rho[i];
+    A.n_drho[d] = A.drho[i];
+    A.n_mass[d] = A.mass[i];
+    A.n_Vol[d] = A.Vol[i];
+    A.n_B[d] = A.B[i];
+    A.n_pid[d] = A.pid[i];
+}
+
 struct UnpackSrc {
     const double *buf[4];   // received from left, received from right, sent to left, sent to right
 };
@@ -557,16 +591,29 @@ SPHB_API int sphb_ctx_slab_pack(sphb_ctx *c, double *send_left_dev, double *send
     return 0;
 }
 
-// Squeeze the dead rows out of the owned region (now and then; between sphb_ctx_slab_pack, whose block scan
-// it reuses, and sphb_ctx_slab_unpack): the rows that stay are compacted into the alternate arrays, which
-// become the current ones.
+// Squeeze the dead rows out of the owned region (now and then; between sphb_ctx_slab_pack and
+// sphb_ctx_slab_unpack): the rows that stay are compacted -- in cell order, m:529-568 -- into the alternate
+// arrays, which become the current ones.
 SPHB_API int sphb_ctx_slab_compact(sphb_ctx *c)
 {
     SLAB_ENTER();
     SlabState &s = c->slab;
     const SlabGeom G = geom_of(c);
-    const unsigned blocks = std::max(1u, grid_for((size_t)s.nf_cap, kSlabBlock));
-    {
+    if (c->have_list) {
+        // in cell order, through the entry array of the last build (every live owned row has a real entry)
+        const int ent_cap = (int)c->nw.ell_stride;
+        SPHB_TRY(s.sort_flag.reserve(((size_t)ent_cap + 1) * sizeof(int)));
+        SPHB_TRY(s.sort_ptr.reserve(((size_t)ent_cap + 1) * sizeof(int)));
+        ProfScope ps(&c->kprof, kPfSlab, c->st);
+        const SlabArrays A = arrays_of(c);
+        k_slab_sort_flags<<<grid_for((size_t)ent_cap, kSlabBlock), kSlabBlock, 0, c->st>>>(
+            c->nw.ent_key.as<int>(), c->nw.grid.as<GridDesc>(), ent_cap, A, G, s.sort_flag.as<int>());
+        SPHB_TRY(exclusive_scan_i32(s.sort_flag.as<int>(), s.sort_ptr.as<int>(), (size_t)ent_cap, c->nw.scan_tmp, nullptr,
+                                    c->st, &c->launches));
+        k_slab_sort_move<<<grid_for((size_t)ent_cap, kSlabBlock), kSlabBlock, 0, c->st>>>(
+            c->nw.ent_key.as<int>(), s.sort_flag.as<int>(), s.sort_ptr.as<int>(), ent_cap, A);
+    } else {
+        const unsigned blocks = std::max(1u, grid_for((size_t)s.nf_cap, kSlabBlock));
         ProfScope ps(&c->kprof, kPfSlab, c->st);
         k_slab_scatter<false><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, s.block_tot.as<int>(),
                                                                 s.counts.as<int>(), nullptr, nullptr, 0,
