@@ -541,11 +541,11 @@ __device__ __forceinline__ double device_dt(const PhysParams &P, const DevScalar
 
 template <bool PLAIN>
 __device__ __forceinline__ void force_rows(const PhysParams &P, const StateView &S, const TileDesc &T, const OwnPre &pre,
-                                           const double2 *s_xy, const double2 *s_v, const double2 *s_rp,
-                                           const double2 *s_b1, const double2 *s_b2, const double *s_V, double dt,
-                                           int add_gravity)
+                                           const double2 *s_xy, const double2 *s_v, const double2 *s_pV,
+                                           const double2 *s_b1, const double2 *s_b2, double dt, int add_gravity)
 {
     const double h001 = 0.01 * P.h;
+    const double rho_per_p = P.rho0 / P.p0;
     SPHB_TILE_WALKERS(ew, si, i)
     {
         if (i >= P.nf) {   // wall rows: forces 0, velocity 0 (ph:958-962, 1405-1408)
@@ -557,15 +557,17 @@ __device__ __forceinline__ void force_rows(const PhysParams &P, const StateView 
         const double2 pi = s_xy[si];
         const double2 vi = s_v[si];
         const double2 bi1 = s_b1[si], bi2 = s_b2[si];
-        const double Vi = s_V[si], m_i = S.mass[i];
-        const double2 rpi = s_rp[si];
-        const double rho_i = rpi.x, p_i = rpi.y;
+        const double2 pVi = s_pV[si];                      // (half-step p, volume)
+        const double Vi = pVi.y, m_i = S.mass[i];
+        const double p_i = pVi.x;
+        const double rho_i = half_step_rho(S.rho[i], S.drho_dt[i], dt, P.rho0);   // ph:857-861 (own row: exact)
         double ax = 0.0, ay = 0.0, ix = 0.0, iy = 0.0, fx = 0.0, fy = 0.0;
         bool has_wall = false;
         SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
             const Geo g = pair_geometry(pi, s_xy[sl], m, P);
             const double ex = g.ex, ey = g.ey;
-            const double Vs = s_V[sl];
+            const double2 pVj = s_pV[sl];
+            const double Vs = pVj.y;
             const double gj = spline_dW(g.r, P) * (PLAIN ? Vs : fabs(Vs));
             const double2 vj = s_v[sl];
             const double dvx = vi.x - vj.x, dvy = vi.y - vj.y;
@@ -581,11 +583,12 @@ __device__ __forceinline__ void force_rows(const PhysParams &P, const StateView 
                 ix -= gj * tx;
                 iy -= gj * ty;
                 // pressure with Riemann dissipation (ph:891-925)
-                const double2 rpj = s_rp[sl];
-                const double rho_bar = 0.5 * (rho_i + rpj.x);
+                // neighbour's half-step density from its staged pressure: rho = rho0 (1 + p / p0), the EOS
+                // (ph:862) inverted -- 8 B less to gather per neighbour, ~1 ulp from the stored value
+                const double rho_bar = 0.5 * (rho_i + fma(pVj.x, rho_per_p, P.rho0));
                 const double du = dvx * ex + dvy * ey;                          // u_l - u_r
                 const double beta = fmin(3.0 * fmax(du, 0.0), P.c_f);           // ph:1121-1129
-                const double p_avg = 0.5 * (p_i + rpj.y);
+                const double p_avg = 0.5 * (p_i + pVj.x);
                 const double p_star = p_avg + 0.5 * beta * rho_bar * du;
                 const double pg = 0.5 * (p_avg + p_star) * gj;
                 fx -= pg * tx;
@@ -611,7 +614,7 @@ __device__ __forceinline__ void force_rows(const PhysParams &P, const StateView 
             const double inv_m = 1.0 / m_i;
             const double wax = fp.x * inv_m, way = fp.y * inv_m;
             SPHB_ROW(true, ([&](const int sl, const int m) {
-                const double Vs = s_V[sl];
+                const double Vs = s_pV[sl].y;
                 if (Vs >= 0.0) return;
                 const Geo g = pair_geometry(pi, s_xy[sl], m, P);
                 const double ex = g.ex, ey = g.ey;
@@ -636,7 +639,7 @@ __device__ __forceinline__ void force_rows(const PhysParams &P, const StateView 
         fx *= Vi;
         fy *= Vi;
         S.force[i] = make_double2(fx, fy);
-        S.rp_half[i] = rpi;
+        S.rp_half[i] = make_double2(rho_i, p_i);
         double2 vn;
         vn.x = vi.x + (fp.x + fx) / m_i * dt;   // ph:1402-1403
         vn.y = vi.y + (fp.y + fy) / m_i * dt;
@@ -660,10 +663,9 @@ __global__ void __launch_bounds__(kTileThreads) k_force_fused(PhysParams P, Stat
     const OwnPre pre = tile_prefetch_own(S, T);
     double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
     double2 *s_v = s_xy + cap;
-    double2 *s_rp = s_v + cap;
-    double2 *s_b1 = s_rp + cap;
+    double2 *s_pV = s_v + cap;    // (half-step pressure, volume; volume negative = wall entry)
+    double2 *s_b1 = s_pV + cap;
     double2 *s_b2 = s_b1 + cap;
-    double *s_V = reinterpret_cast<double *>(s_b2 + cap);
     int walls = 0;
     SPHB_TILE_FOR_STAGED(T, e, slot)
     {
@@ -671,15 +673,14 @@ __global__ void __launch_bounds__(kTileThreads) k_force_fused(PhysParams P, Stat
         s_xy[slot] = S.ent_pos[e];
         const double V = S.Vol[j];
         if (j < P.nf) {
-            s_V[slot] = V;
             s_v[slot] = S.vel[j];
             const double rho_h = half_step_rho(S.rho[j], S.drho_dt[j], dt, P.rho0);
-            s_rp[slot] = make_double2(rho_h, P.p0 * (rho_h / P.rho0 - 1.0));   // ph:862
+            s_pV[slot] = make_double2(P.p0 * (rho_h / P.rho0 - 1.0), V);   // ph:862
             const double4 B = *reinterpret_cast<const double4 *>(&S.B[j]);
             s_b1[slot] = make_double2(B.x, B.y);
             s_b2[slot] = make_double2(B.z, B.w);
         } else {
-            s_V[slot] = -V;
+            s_pV[slot] = make_double2(0.0, -V);
             s_v[slot] = S.wall_vel[j];
             walls = 1;
         }
@@ -688,12 +689,11 @@ __global__ void __launch_bounds__(kTileThreads) k_force_fused(PhysParams P, Stat
         const int d = T.n_staged;
         s_xy[d] = make_double2(kDummyCoord, kDummyCoord);
         s_v[d] = make_double2(0.0, 0.0);
-        s_rp[d] = make_double2(0.0, 0.0);
+        s_pV[d] = make_double2(0.0, 0.0);
         s_b1[d] = make_double2(0.0, 0.0);
         s_b2[d] = make_double2(0.0, 0.0);
-        s_V[d] = 0.0;
     }
-#define SPHB_CALL(plain) force_rows<plain>(P, S, T, pre, s_xy, s_v, s_rp, s_b1, s_b2, s_V, dt, add_gravity)
+#define SPHB_CALL(plain) force_rows<plain>(P, S, T, pre, s_xy, s_v, s_pV, s_b1, s_b2, dt, add_gravity)
     SPHB_TILE_DISPATCH(walls, SPHB_CALL);
 #undef SPHB_CALL
 }
@@ -988,7 +988,7 @@ __global__ void __launch_bounds__(kBlock) k_profile(PhysParams P, StateView S, d
 
 // ================================================================================================
 // bytes of shared memory per staged slot
-constexpr size_t kDensitySlot = 24, kKgcSlot = 24, kViscSlot = 72, kPressureSlot = 88, kContinuitySlot = 40,
+constexpr size_t kDensitySlot = 24, kKgcSlot = 24, kViscSlot = 72, kPressureSlot = 88, kForceSlot = 80, kContinuitySlot = 40,
                  kShearSlot = 32;
 
 int csr_max_tile_slots()
@@ -1011,7 +1011,7 @@ int csr_configure(int tile_cap)
     SPHB_GRANT((k_visc_transport<true, false>), c * kViscSlot);
     SPHB_GRANT((k_visc_transport<false, true>), c * kViscSlot);
     SPHB_GRANT(k_pressure, c * kPressureSlot);
-    SPHB_GRANT(k_force_fused, c * kPressureSlot);
+    SPHB_GRANT(k_force_fused, c * kForceSlot);
     SPHB_GRANT(k_continuity, c * kContinuitySlot);
     SPHB_GRANT(k_wall_shear, c * kShearSlot);
 #undef SPHB_GRANT
@@ -1068,7 +1068,7 @@ int csr_force_fused(const PhysParams &P, const StateView &S, DevScalars *sc, dou
                     bool add_gravity, cudaStream_t st)
 {
     k_publish_dt<<<1, 1, 0, st>>>(P, sc, remain, fixed_dt);
-    k_force_fused<<<S.n_tiles, kTileThreads, (size_t)S.tile_cap * kPressureSlot, st>>>(P, S, sc, remain, fixed_dt,
+    k_force_fused<<<S.n_tiles, kTileThreads, (size_t)S.tile_cap * kForceSlot, st>>>(P, S, sc, remain, fixed_dt,
                                                                                        add_gravity ? 1 : 0);
     SPHB_CUDA(cudaGetLastError());
     return 0;
