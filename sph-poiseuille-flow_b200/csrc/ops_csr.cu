@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(kTileThreads) k_pressure(PhysParams P, StateVi
 // The viscous/transport pass and the pressure pass read the same neighbour fields (position, velocity,
 // B, volume), and the pressure pass depends on the viscous one only through the walker's OWN F_prior
 // (virtual wall pressure ph:929-934 and the kick ph:1402-1403).  One row walk therefore serves all
-// three operators: 88 B gathered per neighbour once instead of 72 B + 88 B.  Walkers with wall
+// three operators: 80 B gathered per neighbour once instead of 72 B + 88 B.  Walkers with wall
 // neighbours take a second, short walk over their wall entries once F_prior is complete.  The time
 // step (m:519-527) is derived by every CTA from the device vmax, and the neighbours' half-step (rho, p)
 // (ph:857-862) is evaluated while staging, so there is no separate dt / half-step launch.
