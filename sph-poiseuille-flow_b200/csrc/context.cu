@@ -7,6 +7,9 @@
 #include "context.cuh"
 
 #include <limits>
+#include <string>
+#include <thread>
+#include <vector>
 
 namespace {
 
@@ -734,8 +737,31 @@ SPHB_API int sphb_ensemble_run_dual(sphb_ctx **ctxs, int n_ctx, int n_outer, int
 {
     clear_error();
     if (!ctxs || n_ctx < 0) return set_error("SPHB:arg", "bad ensemble");
-    for (int o = 0; o < n_outer; ++o)
-        for (int k = 0; k < n_ctx; ++k) SPHB_TRY(sphb_ctx_run_dual(ctxs[k], 1, n_inner));
+    // A graph launch costs the host ~10 us, a small channel's step the device about as much once several
+    // are in flight: the launches are spread over a few host threads (one slice of the channels each; a
+    // context is only ever touched by its own thread, error state is thread-local).
+    const int n_thr = std::max(1, std::min({8, n_ctx / 16, (int)std::thread::hardware_concurrency() / 2}));
+    if (n_thr == 1) {
+        for (int o = 0; o < n_outer; ++o)
+            for (int k = 0; k < n_ctx; ++k) SPHB_TRY(sphb_ctx_run_dual(ctxs[k], 1, n_inner));
+        return 0;
+    }
+    std::vector<int> rc((size_t)n_thr, 0);
+    std::vector<std::string> ids((size_t)n_thr), msgs((size_t)n_thr);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_thr; ++t)
+        pool.emplace_back([&, t]() {
+            const int k0 = (int)((long long)n_ctx * t / n_thr), k1 = (int)((long long)n_ctx * (t + 1) / n_thr);
+            for (int o = 0; o < n_outer && !rc[t]; ++o)
+                for (int k = k0; k < k1 && !rc[t]; ++k) rc[t] = sphb_ctx_run_dual(ctxs[k], 1, n_inner);
+            if (rc[t]) {
+                ids[t] = last_error_id();
+                msgs[t] = last_error_msg();
+            }
+        });
+    for (auto &th : pool) th.join();
+    for (int t = 0; t < n_thr; ++t)
+        if (rc[t]) return set_error(ids[t].c_str(), "%s", msgs[t].c_str());
     return 0;
 }
 

@@ -369,8 +369,9 @@ def test_ensemble_equals_separate_runs(sphb, H):
     bits of the same channels stepped one after the other."""
     import importlib
     cs = importlib.import_module("sph_b200.channel_setup")
-    cfgs = [cs.ChannelConfig(DL=1.0, dp=0.04, mu=mu, U_bulk=ub, c_f=10.0).derive()
-            for mu, ub in ((0.05, 0.4), (0.1, 0.666667), (0.2, 1.0), (0.08, 0.5))]
+    # 36 channels: enough for sphb_ensemble_run_dual to spread the graph launches over two host threads
+    cfgs = [cs.ChannelConfig(DL=1.0, dp=0.05, mu=0.05 + 0.004 * k, U_bulk=0.4 + 0.015 * k, c_f=10.0).derive()
+            for k in range(36)]
     pts = [cs.developed(c, seed=30 + k) for k, c in enumerate(cfgs)]
 
     def make():
