@@ -126,12 +126,20 @@ __global__ void __launch_bounds__(256) k_yrange_grid(const double2 *__restrict__
         kmin = a < kmin ? a : kmin;
         kmax = b > kmax ? b : kmax;
     }
+    // one atomic pair per CTA, not per warp: thousands of 64-bit atomics on one address serialise
+    __shared__ long long s_min[8], s_max[8];
     if ((threadIdx.x & 31) == 0) {
-        atomicMin(&g->ymin_key, kmin);
-        atomicMax(&g->ymax_key, kmax);
+        s_min[threadIdx.x >> 5] = kmin;
+        s_max[threadIdx.x >> 5] = kmax;
     }
     __syncthreads();
     if (threadIdx.x != 0) return;
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+        kmin = s_min[w] < kmin ? s_min[w] : kmin;
+        kmax = s_max[w] > kmax ? s_max[w] : kmax;
+    }
+    atomicMin(&g->ymin_key, kmin);
+    atomicMax(&g->ymax_key, kmax);
     __threadfence();
     if (atomicAdd(&g->ticket, 1u) != gridDim.x - 1) return;
     __threadfence();
