@@ -289,14 +289,16 @@ __global__ void __launch_bounds__(kBlock) k_cell_canon(const GridDesc *__restric
 }
 
 // One descriptor per tile (tile.cuh): entry ranges of the (kTileRows + 2) x (w + 2) cell neighbourhood and
-// their slots.
+// their slots.  One warp per tile: lane (3 r + k) fetches range k of staged row r, the slot offsets are a
+// warp prefix sum, lane 0 writes the rest.
 __global__ void __launch_bounds__(kBlock) k_tile_setup(const GridDesc *__restrict__ g, int ncx, int slab, int w,
                                                       unsigned n_tiles, int cap, int ent_cap,
                                                       const int *__restrict__ cell_start,
                                                       TileDesc *__restrict__ tiles, int *__restrict__ totals,
                                                       int *__restrict__ flags)
 {
-    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (t >= n_tiles) return;
     const int ncy = g->ncy;
     const int tpr = tiles_per_row(ncx, w);
@@ -305,59 +307,71 @@ __global__ void __launch_bounds__(kBlock) k_tile_setup(const GridDesc *__restric
     const int a = max(cx0 - 1, 0), b = min(cx1 + 1, ncx);
     const bool valid = cy0 < ncy;
     TileDesc &T = tiles[t];
-    int used = 0;
-    bool fits = true;
-    for (int r = 0; r < kStageRows; ++r) {
+    // lane -> (staged row r, range k): 0 main columns a..b-1, 1 wrap column ncx-1, 2 wrap column 0
+    int rb = 0, re = 0;
+    if (lane < kStageRows * 3) {
+        const int r = lane / 3, k = lane % 3;
         const int row = cy0 + r - 1;
-        const bool row_ok = valid && row >= 0 && row < ncy;
-        int rb[3] = {0, 0, 0}, re[3] = {0, 0, 0};
-        const int *cs = cell_start + (size_t)(row_ok ? row : 0) * ncx;
-        if (row_ok) {
-            rb[0] = cs[a];
-            re[0] = cs[b];
-            if (cx0 == 0 && b <= ncx - 1) {   // left halo column wraps to ncx-1
-                rb[1] = cs[ncx - 1];
-                re[1] = cs[ncx];
-            }
-            if (cx1 == ncx && a >= 1) {       // right halo column wraps to 0
-                rb[2] = cs[0];
-                re[2] = cs[1];
+        if (valid && row >= 0 && row < ncy) {
+            const int *cs = cell_start + (size_t)row * ncx;
+            if (k == 0) {
+                rb = cs[a];
+                re = cs[b];
+            } else if (k == 1 && cx0 == 0 && b <= ncx - 1) {   // left halo column wraps to ncx-1
+                rb = cs[ncx - 1];
+                re = cs[ncx];
+            } else if (k == 2 && cx1 == ncx && a >= 1) {       // right halo column wraps to 0
+                rb = cs[0];
+                re = cs[1];
             }
         }
-        for (int k = 0; k < 3; ++k) {
-            T.seg[3 * r + k].b = rb[k];
-            T.seg[3 * r + k].e = re[k];
-            T.seg[3 * r + k].off = used;
-            used += re[k] - rb[k];
-            if (re[k] > ent_cap) fits = false;   // entry overflow (reported by k_cell_canon)
+    }
+    const int len = re - rb;
+    int inc = len;   // inclusive prefix over the lanes = slot offsets
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += v;
+    }
+    const int used = __shfl_sync(0xffffffffu, inc, kStageRows * 3 - 1);
+    const bool fits = __all_sync(0xffffffffu, re <= ent_cap);   // entry overflow is reported by k_cell_canon
+    if (lane < kStageRows * 3) {
+        T.seg[lane].b = rb;
+        T.seg[lane].e = re;
+        T.seg[lane].off = inc - len;
+    }
+    // own rows: lane k < kTileRows fetches its own range; it is inside the main range of staged row k + 1
+    const int main_lane = 3 * (min(lane, kTileRows - 1) + 1);   // (all lanes take part in the shuffles)
+    const int main_b = __shfl_sync(0xffffffffu, rb, main_lane);
+    const int main_off = __shfl_sync(0xffffffffu, inc - len, main_lane);
+    if (lane < kTileRows) {
+        const bool row_ok = valid && cy0 + lane < ncy;
+        const int *cs = cell_start + (size_t)(row_ok ? cy0 + lane : 0) * ncx;
+        const int ob = row_ok ? cs[cx0] : 0, on = row_ok ? cs[cx1] - cs[cx0] : 0;
+        T.own_b[lane] = ob;
+        T.own_n[lane] = on;
+        T.own_off[lane] = main_off + (ob - main_b);
+    }
+    if (lane == 0) {
+        T.n_staged = used;
+        T.cy0 = cy0;
+        T.cx0 = cx0;
+        T.cx1 = cx1;
+        T.a = a;
+        T.b = b;
+        int f = valid && fits ? kTileValid : 0;
+        // walkers of columns 0, ncx-2 and ncx-1 can meet ghost entries, both entries of a particle that owns
+        // a ghost, or the periodic wrap: they take the general walk (ghosts live in column ncx-1 only and
+        // their owners in columns 0, ncx-2, ncx-1; nb:282-295)
+        // (a slab of a sharded channel has neither: its outermost columns are empty margins)
+        if (!slab && (cx0 < 1 || cx1 > ncx - 2 || ncx < 6)) f |= kTileSeam;
+        if (used + 1 > cap) {   // cannot be staged (+ the dummy slot): reported, the tile is skipped by every kernel
+            atomicOr(flags, kErrTileCap);
+            f &= ~kTileValid;
         }
+        T.flags = f;
+        if (valid) atomicMax(&totals[3], used + 1);
     }
-    T.n_staged = used;
-    for (int k = 0; k < kTileRows; ++k) {
-        const int r = k + 1;
-        const bool row_ok = valid && cy0 + k < ncy;
-        const int *cs = cell_start + (size_t)(row_ok ? cy0 + k : 0) * ncx;
-        T.own_b[k] = row_ok ? cs[cx0] : 0;
-        T.own_n[k] = row_ok ? cs[cx1] - cs[cx0] : 0;
-        T.own_off[k] = T.seg[3 * r].off + (T.own_b[k] - T.seg[3 * r].b);
-    }
-    T.cy0 = cy0;
-    T.cx0 = cx0;
-    T.cx1 = cx1;
-    T.a = a;
-    T.b = b;
-    int f = valid && fits ? kTileValid : 0;
-    // walkers of columns 0, ncx-2 and ncx-1 can meet ghost entries, both entries of a particle that owns
-    // a ghost, or the periodic wrap: they take the general walk (ghosts live in column ncx-1 only and
-    // their owners in columns 0, ncx-2, ncx-1; nb:282-295)
-    // (a slab of a sharded channel has neither: its outermost columns are empty margins)
-    if (!slab && (cx0 < 1 || cx1 > ncx - 2 || ncx < 6)) f |= kTileSeam;
-    if (used + 1 > cap) {   // cannot be staged (+ the dummy slot): reported, the tile is skipped by every kernel
-        atomicOr(flags, kErrTileCap);
-        f &= ~kTileValid;
-    }
-    T.flags = f;
-    if (valid) atomicMax(&totals[3], used + 1);
 }
 
 // nb:357-372 for "particle a (wrapped xa, ya) meets an entry at (ex, ey)": minimum image, cut-off and
@@ -1186,7 +1200,7 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
     for (int attempt = 0; attempt < 8; ++attempt) {
         ProfScope ps(prof, kPfNbrWalk, st);
         if (attempt > 0) SPHB_CUDA(cudaMemsetAsync(w.totals.p, 0, 8 * sizeof(int), st));
-        k_tile_setup<<<grid_for(w.n_tiles), kBlock, 0, st>>>(g, P.ncx, P.slab, w.tile_w, w.n_tiles, w.tile_cap,
+        k_tile_setup<<<grid_for((size_t)w.n_tiles * 32), kBlock, 0, st>>>(g, P.ncx, P.slab, w.tile_w, w.n_tiles, w.tile_cap,
                                                             (int)w.ell_stride, w.cell_start.as<int>(), w.tiles.as<TileDesc>(),
                                                             w.totals.as<int>(), flags);
         const size_t smem = (size_t)w.tile_cap * kWalkSlotBytes + (size_t)(kTileThreads / 32) * w.ell_cap * sizeof(unsigned short);
