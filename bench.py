@@ -18,9 +18,13 @@ steps * ranks / time, so all outer-step work (list rebuild included) is amortise
 Multi-GPU (launched by torchrun, one rank per GPU), "scaling": "weak" (fixed work per GPU):
   --mode slab (default for N > 1): ONE periodic channel of length N * DL cut into x-slabs on cell-column
       boundaries (BASELINE.json configs[4] in weak-scaling form): every rank steps its slab + 4 halo
-      columns, and once per step migrating rows and halo copies move to the neighbour ranks (NCCL
-      send/recv over NVLink) and max|v| / the shear partials are all-reduced;
-  --mode replicas: N independent channels, one per rank, no data-path collective (configs[3]-style).
+      columns, and once per step ONE uneven NCCL all-to-all moves the migrating rows and halo copies to the
+      two neighbour ranks and max|v| / the shear partials to everybody; the whole step (library kernels +
+      the collective) is replayed as one CUDA graph (--no-graph for eager launches);
+  --mode replicas: N independent channels, one per rank, no data-path collective;
+  --mode ensemble [--channels C]: C independent dp = 0.02 channels PER GPU with mu and g swept on a grid
+      (BASELINE.json configs[3]; 4096 in all at 8 GPUs with C = 512), stepped together by
+      sphb_ensemble_run_dual; no communication.
 Timing: CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks.
 
 Lines printed: ONE JSON line on rank 0 (see the task contract: value, e2e, roofline, cpu_baseline,
