@@ -231,12 +231,38 @@ class SlabGroup:
             s.close()
 
 
+def exchange_layout(rank: int, world: int, nbuf: int, n_scal: int = 4):
+    """Layout of the one uneven all-to-all of a sharded step.  The chunk rank `rank` sends to / receives from
+    rank d is [n_scal scalars][its "to the left" record buffer if d is its left neighbour][its "to the right"
+    buffer if d is its right neighbour] (symmetric sizes).  Returns the split sizes, the chunk offsets, and where
+    -- (offset, length) in the flat send / receive tensors -- the four record buffers live.  With two ranks
+    the left and the right neighbour are the same peer and both buffers travel in its chunk: the peer's "to
+    its left" buffer comes first and is what this rank receives FROM ITS RIGHT."""
+    left, right = (rank - 1) % world, (rank + 1) % world
+    split = [n_scal + (nbuf if d == left else 0) + (nbuf if d == right else 0) for d in range(world)]
+    offs = [0]
+    for n in split:
+        offs.append(offs[-1] + n)
+
+    def part(d, which):
+        return offs[d] + n_scal + which * nbuf, nbuf
+    if world == 1:
+        lay = dict(send_left=None, send_right=None, recv_left=None, recv_right=None)
+    elif left == right:
+        lay = dict(send_left=part(left, 0), send_right=part(left, 1), recv_right=part(left, 0), recv_left=part(left, 1))
+    else:
+        lay = dict(send_left=part(left, 0), send_right=part(right, 0), recv_left=part(left, 0), recv_right=part(right, 0))
+    lay.update(split=split, offs=offs[:-1], total=offs[-1], left=left, right=right)
+    return lay
+
+
 class SlabChannel:
     """One rank of the sharded channel: its slab, and the exchange over torch.distributed (backend "nccl").
     The two record buffers and the rank's scalars travel in ONE uneven all-to-all per step (NCCL send/recv
     over NVLink underneath): the left / right neighbour gets a record buffer + the scalars, every other rank
     the scalars only.  The library launches on the stream torch uses, so its kernels and the collective are
-    stream-ordered; the only host synchronisation of a step is the read-back of the new row counts."""
+    stream-ordered, and the row counts stay on the device: a step has no host synchronisation and can be
+    replayed as one CUDA graph (use_graph)."""
 
     def __init__(self, cfg, pt, rank: int, world: int, device, compact_every: int = 256, use_graph: bool = False,
                  **kw):
@@ -253,30 +279,18 @@ class SlabChannel:
         self.stream = torch.cuda.Stream(device=s.device)     # shared by the library's kernels and torch / NCCL
         _check(lib().sphb_ctx_set_stream(s.ch._ctx, C.c_void_p(self.stream.cuda_stream)))
         self._red = torch.zeros(3, dtype=torch.float64, device=s.device)   # max|v|, sum tau_bottom, sum tau_top
-        # all-to-all layout: the chunk for / from rank d = [4 scalars][record buffer(s) if d is a neighbour]
-        nbuf, S = s.send_left.numel(), 4
-        def chunk(d):
-            return S + (nbuf if d == self.left else 0) + (nbuf if d == self.right else 0)
-        self._split = [chunk(d) for d in range(world)]                 # symmetric: what I send d = what d sends me
-        offs = np.concatenate([[0], np.cumsum(self._split)]).astype(np.int64)
-        total = int(offs[-1])
-        self._xin = torch.zeros(total, dtype=torch.float64, device=s.device)
-        self._xout = torch.zeros(total, dtype=torch.float64, device=s.device)
-        self._scal_off = torch.tensor(offs[:-1], dtype=torch.int64, device=s.device)
-        self._head_idx = torch.tensor(np.concatenate([o + np.arange(3) for o in offs[:-1]]), dtype=torch.int64,
+        lay = exchange_layout(rank, world, s.send_left.numel())
+        self._split = lay["split"]
+        offs = np.asarray(lay["offs"], dtype=np.int64)
+        self._xin = torch.zeros(lay["total"], dtype=torch.float64, device=s.device)
+        self._xout = torch.zeros(lay["total"], dtype=torch.float64, device=s.device)
+        self._scal_off = torch.tensor(offs, dtype=torch.int64, device=s.device)
+        self._head_idx = torch.tensor(np.concatenate([o + np.arange(3) for o in offs]), dtype=torch.int64,
                                       device=s.device)
-
-        def part(t, d, which):      # record buffer inside the chunk of rank d (which = 0 first, 1 second)
-            o = int(offs[d]) + S + which * nbuf
-            return t[o:o + nbuf]
         if world > 1:
-            if self.left == self.right:      # two ranks: both buffers go to / come from the same peer
-                s.send_left, s.send_right = part(self._xin, self.left, 0), part(self._xin, self.left, 1)
-                # the peer's "to its left" is for me as its left neighbour = what I receive from my right
-                s.recv_right, s.recv_left = part(self._xout, self.left, 0), part(self._xout, self.left, 1)
-            else:
-                s.send_left, s.send_right = part(self._xin, self.left, 0), part(self._xin, self.right, 0)
-                s.recv_left, s.recv_right = part(self._xout, self.left, 0), part(self._xout, self.right, 0)
+            view = lambda t, ol: t[ol[0]:ol[0] + ol[1]]   # noqa: E731
+            s.send_left, s.send_right = view(self._xin, lay["send_left"]), view(self._xin, lay["send_right"])
+            s.recv_left, s.recv_right = view(self._xout, lay["recv_left"]), view(self._xout, lay["recv_right"])
         self.exchange()
         s.step_end()
 

@@ -47,6 +47,35 @@ def test_cut_covers_every_particle_once_and_unwraps_the_wall_halo(mods):
     assert np.array_equal(ids, np.arange(pt.n_fluid))
 
 
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_all_to_all_layout_delivers_each_buffer_to_the_right_neighbour(mods, world):
+    """The one uneven all-to-all of a sharded step, simulated: every rank's "to the left" buffer must arrive as
+    its left neighbour's "from the right" and vice versa (two ranks: both buffers share one chunk)."""
+    _, slab = mods
+    nbuf = 5
+    lays = [slab.exchange_layout(r, world, nbuf) for r in range(world)]
+    xin = []
+    for r, lay in enumerate(lays):
+        x = np.full(lay["total"], -1.0)
+        for d in range(world):
+            x[lay["offs"][d]:lay["offs"][d] + 3] = 100 * r + np.arange(3)            # scalars head every chunk
+        o, n = lay["send_left"]
+        x[o:o + n] = 1000 * r + 1                                                    # tag: r's buffer for its left
+        o, n = lay["send_right"]
+        x[o:o + n] = 1000 * r + 2                                                    # tag: r's buffer for its right
+        xin.append(x)
+    for r, lay in enumerate(lays):
+        # all_to_all_single: chunk d of the output of r = chunk r of the input of d
+        out = np.concatenate([xin[d][lays[d]["offs"][r]:lays[d]["offs"][r] + lays[d]["split"][r]] for d in range(world)])
+        assert out.size == lay["total"] and [lays[d]["split"][r] for d in range(world)] == lay["split"]
+        o, n = lay["recv_left"]
+        assert np.all(out[o:o + n] == 1000 * lay["left"] + 2)                        # my left neighbour's "to the right"
+        o, n = lay["recv_right"]
+        assert np.all(out[o:o + n] == 1000 * lay["right"] + 1)                       # my right neighbour's "to the left"
+        for d in range(world):
+            assert np.array_equal(out[lay["offs"][d]:lay["offs"][d] + 3], 100 * d + np.arange(3))
+
+
 def _gloo_worker(rank, world, port, root, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, root)
