@@ -131,3 +131,16 @@ def test_two_ranks_agree_on_ownership_and_halo_over_gloo(tmp_path):
     port = 29600 + os.getpid() % 300
     mp.spawn(_gloo_worker, args=(2, port, root, out), nprocs=2, join=True)
     assert open(out).read() == "ok"
+
+
+def test_cell_sorted_matches_the_reference_sort(mods, H):
+    """channel_setup.cell_sorted (the row order the benchmark starts from) is the reference's
+    sort_particles_by_cell (SPH_Poiseuille.m:529-568) as restated by the oracle host."""
+    cs, _ = mods
+    cfg = cs.ChannelConfig(DL=3.0, DH=1.0, dp=0.05, c_f=10.0).derive()
+    pt = cs.developed(cfg, seed=17, jitter=0.3)
+    got = cs.cell_sorted(cfg, pt)
+    perm = H.sort_permutation(pt.pos, pt.n_fluid, pt.n_total, cfg.DL, cfg.h)
+    assert np.array_equal(got.pos, pt.pos[perm]) and np.array_equal(got.vel, pt.vel[perm])
+    assert np.array_equal(got.rho, pt.rho[perm]) and np.array_equal(got.drho_dt, pt.drho_dt[perm])
+    assert got.n_fluid == pt.n_fluid and np.array_equal(got.pos[pt.n_fluid:], pt.pos[pt.n_fluid:])
