@@ -454,7 +454,14 @@ def b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, su
     stream = sc.stream                           # the library's kernels, torch and NCCL share this stream in slab mode
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    for _ in range(W):
+    # the first warm-up step runs eagerly and counts the kernels of one step (a replayed graph launches the
+    # same kernels but does not pass through the library's launch counter)
+    want_graph, sc.use_graph = sc.use_graph, False
+    l_eager = ch.timing()["launches"]
+    sc.step()
+    launches_per_step = ch.timing()["launches"] - l_eager
+    sc.use_graph = want_graph
+    for _ in range(W - 1):
         sc.step()
     ch.sync()
     l0 = ch.timing()["launches"]
@@ -483,6 +490,8 @@ def b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, su
     n_owned, n_halo, n_wall = sc.slab.counts()      # owned region (incl. rows awaiting compaction), halo, walls
 
     graph_used = bool(sc.use_graph and sc._graph_ok and sc._graph is not None)
+    if graph_used:
+        launches = launches_per_step * K      # every replay launches the kernels of one (captured) step
     # ---- end to end: host rows -> upload -> halo exchange -> list -> physics -> download, every step ----
     Ke = max(1, min(args.e2e_steps, K))
     fields = ("pos", "vel", "rho", "drho_dt")
