@@ -24,7 +24,8 @@ Multi-GPU (launched by torchrun, one rank per GPU), "scaling": "weak" (fixed wor
   --mode replicas: N independent channels, one per rank, no data-path collective;
   --mode ensemble [--channels C]: C independent dp = 0.02 channels PER GPU with mu and g swept on a grid
       (BASELINE.json configs[3]; 4096 in all at 8 GPUs with C = 512), stepped together by
-      sphb_ensemble_run_dual; no communication.
+      sphb_ensemble_run_dual; no communication.  With --batched the channels are stepped by batched
+      launches instead (sphb_batch_run_dual: every kernel launched once for all channels).
 Timing: CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks.
 
 Lines printed: ONE JSON line on rank 0 (see the task contract: value, e2e, roofline, cpu_baseline,
@@ -82,6 +83,9 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="sharded mode: eager launches instead of one CUDA graph per step")
     ap.add_argument("--channels", type=int, default=512,
                     help="--mode ensemble: independent channels PER GPU (BASELINE configs[3]: 4096 in all at 8 GPUs)")
+    ap.add_argument("--batched", action="store_true",
+                    help="--mode ensemble: step the channels with batched launches (sphb_batch_*: every kernel "
+                         "launched once for all channels) instead of one CUDA graph per channel")
     ap.add_argument("--mode", default="auto", choices=("auto", "slab", "replicas", "ensemble"),
                     help="N > 1: 'slab' = ONE periodic channel of length N*DL cut into x-slabs (halo exchange + "
                          "migration over NCCL, weak scaling); 'replicas' = N independent channels (ensemble); "
@@ -602,10 +606,10 @@ def b200_ensemble_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks
         ch.initialise()
         chans.append(ch)
         n_part += pt.n_total
-    ens = lp.Ensemble(chans)
+    ens = lp.Batch(chans) if args.batched else lp.Ensemble(chans)
     ens.run_dual(W, 1)
     ens.sync()
-    l0 = sum(ch.timing()["launches"] for ch in chans)
+    l0 = ens.launches if args.batched else sum(ch.timing()["launches"] for ch in chans)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -616,12 +620,15 @@ def b200_ensemble_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks
     secs = max_over_ranks(time.perf_counter() - t0)      # many streams: wall clock around a synchronised region
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    launches = sum(ch.timing()["launches"] for ch in chans) - l0
+    launches = (ens.launches if args.batched else sum(ch.timing()["launches"] for ch in chans)) - l0
     bad = sum(1 for ch in chans if ch.status()["error_flags"])
     n_all = int(sum_over_ranks(float(n_part)))
     value = n_all * K / secs
     total_launches = sum_over_ranks(float(launches))
-    ens.close()
+    if args.batched:
+        ens.close(channels=True)
+    else:
+        ens.close()
     if bad:
         raise SystemExit(f"bench.py: {bad} channels of the ensemble raised device flags")
     if rank == 0:
@@ -631,7 +638,9 @@ def b200_ensemble_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"ensemble of {total} independent dp={dp:g} DL={args.DL:g} channels "
                                    f"({n_all} particles), mu and g swept on a {side} x {side} grid", "inner_substeps": 1,
-                       "parallelism": f"{n_ch} channels per GPU, one context + stream + CUDA graph each, no communication",
+                       "parallelism": (f"{n_ch} channels per GPU, batched launches (grid = tiles x channels, one CUDA "
+                                       f"graph per step for all of them), no communication" if args.batched else
+                                       f"{n_ch} channels per GPU, one context + stream + CUDA graph each, no communication"),
                        "l2": "working set of the ensemble exceeds L2; no flush", "timing": "host clock around a "
                        "device-synchronised region (one stream per channel)"},
             "e2e": None, "gpu_launches": int(total_launches), "roofline": None, "cpu_baseline": None, "clocks": clocks}),

@@ -224,6 +224,29 @@ SPHB_API int sphb_ctx_run_dual(sphb_ctx *ctx, int n_outer, int n_inner);
 SPHB_API int sphb_ensemble_run_dual(sphb_ctx **ctxs, int n_ctx, int n_outer, int n_inner);
 SPHB_API int sphb_ensemble_sync(sphb_ctx **ctxs, int n_ctx);
 
+/*
+ * The same ensembles stepped by BATCHED launches: every kernel of the step (m:251-283) is launched once for
+ * all channels (grid = the channel's own grid x channels; the per-channel pointers, mu / g / ... and device
+ * scalars come from records in device memory), so the cost of a step no longer grows with the number of kernel
+ * launches per channel.  Every channel advances with its own dt; results are those of sphb_ctx_run_dual on each
+ * channel (same kernel bodies, same per-channel data).  Requirements, checked at creation (SPHB:batch
+ * otherwise): one device; equal n_fluid, n_total, h, DL, sort_interval and cell / tile geometry; every channel
+ * initialised (first neighbour build done) and at the same step count.  While a context is a member of a batch
+ * it launches on the batch's stream: upload / download / status / profile keep working; after anything that moves
+ * its buffers or changes its list capacity (position upload, sphb_ctx_sort_by_cell, sphb_ctx_run_until) call
+ * sphb_batch_refresh.  Destroy the batch before its member contexts.
+ */
+typedef struct sphb_batch sphb_batch;
+SPHB_API int sphb_batch_create(sphb_ctx **ctxs, int n_ctx, sphb_batch **out);
+SPHB_API void sphb_batch_destroy(sphb_batch *batch);
+SPHB_API int sphb_batch_refresh(sphb_batch *batch);
+SPHB_API int sphb_batch_run_dual(sphb_batch *batch, int n_outer, int n_inner);
+SPHB_API int sphb_batch_sync(sphb_batch *batch);
+/* kernels launched by the batch so far (graph replays counted by their captured kernels) */
+SPHB_API long long sphb_batch_launches(const sphb_batch *batch);
+/* OR of the members' sphb_status.error_flags (synchronises) */
+SPHB_API int sphb_batch_error_flags(sphb_batch *batch, int *flags_or);
+
 /* x-/bin-averaged u(y) of the fluid rows (m:579-605).  x0 < 0: all fluid rows (full-length profile). */
 SPHB_API int sphb_ctx_profile(sphb_ctx *ctx, double x0, double half_width, int n_bins, double *u_mean,
                               double *count);

@@ -90,6 +90,10 @@ def lib():
         L.sphb_ctx_destroy.argtypes = [C.c_void_p]
         L.sphb_neighbor_release.restype = None
         L.sphb_neighbor_release.argtypes = [C.c_void_p]
+        L.sphb_batch_destroy.restype = None
+        L.sphb_batch_destroy.argtypes = [C.c_void_p]
+        L.sphb_batch_launches.restype = C.c_longlong
+        L.sphb_batch_launches.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -477,6 +481,55 @@ class Ensemble:
     def close(self):
         for ch in self.channels:
             ch.close()
+
+
+class Batch:
+    """The channels of an ensemble stepped by BATCHED launches (sphb_batch_*): every kernel of the step is
+    launched once for all channels (grid = the channel's own grid x channels), each channel with its own
+    parameters, dt and clock.  Same kernel bodies and per-channel data as Channel.run_dual.  The channels must be
+    initialised (first list build done), share n_fluid / n_total / h / DL / sort_interval and their cell grid,
+    and live on one device; while the batch exists they launch on its stream."""
+
+    def __init__(self, channels):
+        self.channels = list(channels)
+        self._arr = (C.c_void_p * len(self.channels))(*[ch._ctx for ch in self.channels])
+        self._b = C.c_void_p()
+        _check(lib().sphb_batch_create(self._arr, C.c_int(len(self.channels)), C.byref(self._b)))
+
+    def run_dual(self, n_outer: int, n_inner: int = 1):
+        _check(lib().sphb_batch_run_dual(self._b, C.c_int(n_outer), C.c_int(n_inner)))
+
+    def refresh(self):
+        """After a member's buffers or list capacity changed outside the batch (position upload, sort_by_cell,
+        run_until)."""
+        _check(lib().sphb_batch_refresh(self._b))
+
+    def sync(self):
+        _check(lib().sphb_batch_sync(self._b))
+
+    @property
+    def launches(self) -> int:
+        return int(lib().sphb_batch_launches(self._b))
+
+    def error_flags(self) -> int:
+        f = C.c_int(0)
+        _check(lib().sphb_batch_error_flags(self._b, C.byref(f)))
+        return f.value
+
+    def close(self, channels: bool = False):
+        """Destroys the batch (its members get their own streams back); with channels=True the members too."""
+        if self._b:
+            lib().sphb_batch_destroy(self._b)
+            self._b = C.c_void_p()
+        if channels:
+            for ch in self.channels:
+                ch.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def channel_from_config(cfg, particles, **overrides) -> Channel:

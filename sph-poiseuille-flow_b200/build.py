@@ -35,6 +35,7 @@ UNITS = {
     "ops_csr.cu": [],
     "context.cu": [],
     "slab.cu": [],
+    "batch.cu": [],
     "api.cu": [],
 }
 HOST_CC = "/usr/bin/gcc"   # the image's $CC wrapper lacks libgomp.spec; shims/driver are plain C

@@ -176,6 +176,31 @@ int neighbor_half_total(NeighborWork &w, cudaStream_t st);   // makes totals[0] 
 // scan.cu
 int exclusive_scan_i32(const int *in, int *out, size_t n, DevBuf &tmp, int *total_out_dev, cudaStream_t st,
                        long long *launches);
+// the same scan for many independent arrays of one length in one grid (blockIdx.y = array); records in device memory
+struct ScanChan {
+    const int *in;
+    int *out;
+    int *tile_totals;   // scan_workspace_ints(n) ints
+    int *total_out;     // may be NULL
+};
+size_t scan_workspace_ints(size_t n);
+int exclusive_scan_i32_batch(const ScanChan *chan_dev, int n_chan, size_t n, cudaStream_t st, long long *launches);
+
+// batched list build over an ensemble of channels (neighbor.cu; used by batch.cu)
+struct NbrBatchLaunch {
+    const void *chan;       // device array of per-channel records (neighbor_batch_record_bytes() each)
+    const ScanChan *scan;   // device array [n_chan]: cell counts -> cell starts
+    int n_chan;
+    int n_total;            // rows of every channel
+    int cell_cap;           // cells of every channel
+    size_t ell_stride;      // entry capacity of every channel
+    unsigned n_tiles;       // tiles of every channel
+    int tile_cap, ell_cap;  // largest over the channels (size the walk's dynamic shared memory)
+    cudaStream_t st;
+};
+size_t neighbor_batch_record_bytes();
+int neighbor_batch_fill(NeighborWork &w, const double2 *pos, void *host_record, ScanChan *host_scan);
+int neighbor_batch_build(const NbrBatchLaunch &L, long long *launches);
 
 // pack/unpack helpers (misc.cu)
 void launch_pack2(const double *col_major, double2 *out, int n, cudaStream_t st);     // [n x 2] -> double2[n]

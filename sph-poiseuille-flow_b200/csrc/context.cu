@@ -206,6 +206,7 @@ int ctx_plan_lists(sphb_ctx *c, double y_lo, double y_hi) { return plan_lists(c,
 void ctx_drop_graphs(sphb_ctx *c) { drop_graphs(c); }
 int ctx_do_neighbor(sphb_ctx *c) { return do_neighbor(c); }
 int ctx_do_shear(sphb_ctx *c) { return do_shear(c); }
+int ctx_do_sort(sphb_ctx *c) { return do_sort(c); }
 int ctx_volumes_from_mass(sphb_ctx *c)
 {
     const int nt = c->prm.n_total;

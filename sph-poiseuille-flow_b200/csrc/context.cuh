@@ -102,5 +102,6 @@ int ctx_plan_lists(sphb_ctx *c, double y_lo, double y_hi);
 void ctx_drop_graphs(sphb_ctx *c);
 int ctx_do_neighbor(sphb_ctx *c);
 int ctx_do_shear(sphb_ctx *c);
+int ctx_do_sort(sphb_ctx *c);                       // m:272-278 (swaps the state buffers with their alternates)
 int ctx_volumes_from_mass(sphb_ctx *c);             // Vol = m / rho for every row (m:120)
 int ctx_step_physics(sphb_ctx *c, double remain);   // m:254-270: density + KGC, forces, continuity

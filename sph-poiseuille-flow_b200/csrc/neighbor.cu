@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "tile.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <climits>
 
@@ -97,6 +98,29 @@ __device__ __forceinline__ void spline2d(double r, double h, double sigma, doubl
     }
 }
 
+// Per-channel arguments of a BATCHED list build (ensembles of independent channels, batch.cu): the same
+// kernel bodies run for every channel in one grid, blockIdx.y = channel.
+struct NbrChan {
+    NbrParams P;
+    const double2 *pos;
+    GridDesc *g;
+    int *flags, *totals;
+    int *cell_cnt;      // counts, then (at + cell_cap + 1) the fill cursors
+    int *cell_start;
+    double2 *snap;
+    int *cell_of, *ent_of;
+    int *tmp_key;
+    double2 *tmp_pos;
+    int *tmp_cell;
+    int *ent_key;
+    double2 *ent_pos;
+    TileDesc *tiles;
+    uint4 *ell_q;
+    int *ell_cnt;
+    int tile_w, tile_cap;
+    unsigned n_tiles;
+};
+
 __global__ void k_grid_init(GridDesc *g)
 {
     g->ymin_key = LLONG_MAX;
@@ -107,8 +131,8 @@ __global__ void k_grid_init(GridDesc *g)
 
 // y range over ALL particles (nb:245-250); the last CTA to finish derives the grid (nb:253-258), re-arms
 // the reduction for the next build and zeroes the build's totals: one launch instead of three.
-__global__ void __launch_bounds__(256) k_yrange_grid(const double2 *__restrict__ pos, int n, GridDesc *g, NbrParams P,
-                                                    int *flags, int *totals)
+__device__ __forceinline__ void yrange_grid_body(const double2 *__restrict__ pos, int n, GridDesc *g, NbrParams P, int *flags,
+                                                 int *totals)
 {
     load_counts(P);
     if (P.dev_counts) n = P.n_total;
@@ -163,6 +187,22 @@ __global__ void __launch_bounds__(256) k_yrange_grid(const double2 *__restrict__
     g->ticket = 0u;
     for (int k = 0; k < 8; ++k) totals[k] = 0;
 }
+__global__ void __launch_bounds__(256) k_yrange_grid(const double2 *__restrict__ pos, int n, GridDesc *g, NbrParams P,
+                                                    int *flags, int *totals)
+{
+    yrange_grid_body(pos, n, g, P, flags, totals);
+}
+__global__ void __launch_bounds__(256) k_yrange_grid_batch(const NbrChan *__restrict__ chan)
+{
+    const NbrChan &c = chan[blockIdx.y];
+    yrange_grid_body(c.pos, c.P.n_total, c.g, c.P, c.flags, c.totals);
+}
+// zeroes the cell counters and fill cursors of every channel (the cudaMemsetAsync of the single build)
+__global__ void __launch_bounds__(kBlock) k_zero_cells_batch(const NbrChan *__restrict__ chan, int n_ints)
+{
+    int *dst = chan[blockIdx.y].cell_cnt;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_ints; k += gridDim.x * blockDim.x) dst[k] = 0;
+}
 
 struct Bins {
     double xw, y;
@@ -209,9 +249,9 @@ __device__ __forceinline__ Bins bin_particle(double2 p, const NbrParams &P, doub
     return b;
 }
 
-__global__ void __launch_bounds__(kBlock) k_bin_count(const double2 *__restrict__ pos, NbrParams P,
-                                                     const GridDesc *__restrict__ g, double2 *__restrict__ snap,
-                                                     int *__restrict__ cell_of, int *__restrict__ cell_cnt)
+__device__ __forceinline__ void bin_count_body(const double2 *__restrict__ pos, NbrParams P, const GridDesc *__restrict__ g,
+                                               double2 *__restrict__ snap, int *__restrict__ cell_of,
+                                               int *__restrict__ cell_cnt)
 {
     load_counts(P);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -224,12 +264,22 @@ __global__ void __launch_bounds__(kBlock) k_bin_count(const double2 *__restrict_
     if (b.gcx_lo >= 0) atomicAdd(&cell_cnt[row + b.gcx_lo], 1);
     if (b.gcx_hi >= 0) atomicAdd(&cell_cnt[row + b.gcx_hi], 1);
 }
+__global__ void __launch_bounds__(kBlock) k_bin_count(const double2 *__restrict__ pos, NbrParams P,
+                                                     const GridDesc *__restrict__ g, double2 *__restrict__ snap,
+                                                     int *__restrict__ cell_of, int *__restrict__ cell_cnt)
+{
+    bin_count_body(pos, P, g, snap, cell_of, cell_cnt);
+}
+__global__ void __launch_bounds__(kBlock) k_bin_count_batch(const NbrChan *__restrict__ chan)
+{
+    const NbrChan &c = chan[blockIdx.y];
+    bin_count_body(c.pos, c.P, c.g, c.snap, c.cell_of, c.cell_cnt);
+}
 
-__global__ void __launch_bounds__(kBlock) k_scatter(const double2 *__restrict__ pos, NbrParams P,
-                                                   const GridDesc *__restrict__ g,
-                                                   const int *__restrict__ cell_start, int *__restrict__ cell_fill,
-                                                   int *__restrict__ tmp_key, double2 *__restrict__ tmp_pos,
-                                                   int *__restrict__ tmp_cell)
+__device__ __forceinline__ void scatter_body(const double2 *__restrict__ pos, NbrParams P, const GridDesc *__restrict__ g,
+                                             const int *__restrict__ cell_start, int *__restrict__ cell_fill,
+                                             int *__restrict__ tmp_key, double2 *__restrict__ tmp_pos,
+                                             int *__restrict__ tmp_cell)
 {
     load_counts(P);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -259,18 +309,29 @@ __global__ void __launch_bounds__(kBlock) k_scatter(const double2 *__restrict__ 
         tmp_cell[s] = c;
     }
 }
+__global__ void __launch_bounds__(kBlock) k_scatter(const double2 *__restrict__ pos, NbrParams P,
+                                                   const GridDesc *__restrict__ g,
+                                                   const int *__restrict__ cell_start, int *__restrict__ cell_fill,
+                                                   int *__restrict__ tmp_key, double2 *__restrict__ tmp_pos,
+                                                   int *__restrict__ tmp_cell)
+{
+    scatter_body(pos, P, g, cell_start, cell_fill, tmp_key, tmp_pos, tmp_cell);
+}
+__global__ void __launch_bounds__(kBlock) k_scatter_batch(const NbrChan *__restrict__ chan)
+{
+    const NbrChan &c = chan[blockIdx.y];
+    scatter_body(c.pos, c.P, c.g, c.cell_start, c.cell_cnt + ((size_t)c.P.cell_cap + 1), c.tmp_key, c.tmp_pos, c.tmp_cell);
+}
 
 // Canonical order inside a cell = DEcreasing insertion key (the reference's linked list is walked "last
 // inserted first", so a forward scan of the range is its walk order).  Rank sort, one thread per entry:
 // the rank of an entry is the number of larger keys in its cell (keys are distinct); every load is
 // independent.  Also records where each particle's REAL entry ends up (rows are indexed by entry).
-__global__ void __launch_bounds__(kBlock) k_cell_canon(const GridDesc *__restrict__ g, int ent_cap,
-                                                      const int *__restrict__ cell_start,
-                                                      const int *__restrict__ tmp_key,
-                                                      const double2 *__restrict__ tmp_pos,
-                                                      const int *__restrict__ tmp_cell, int *__restrict__ ent_key,
-                                                      double2 *__restrict__ ent_pos, int *__restrict__ ent_of,
-                                                      int *__restrict__ flags)
+__device__ __forceinline__ void cell_canon_body(const GridDesc *__restrict__ g, int ent_cap,
+                                                const int *__restrict__ cell_start, const int *__restrict__ tmp_key,
+                                                const double2 *__restrict__ tmp_pos, const int *__restrict__ tmp_cell,
+                                                int *__restrict__ ent_key, double2 *__restrict__ ent_pos,
+                                                int *__restrict__ ent_of, int *__restrict__ flags)
 {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = g->n_entries;
@@ -287,15 +348,30 @@ __global__ void __launch_bounds__(kBlock) k_cell_canon(const GridDesc *__restric
     ent_pos[dst] = tmp_pos[a];
     if ((key & 3) == 0) ent_of[key >> 3] = dst;
 }
+__global__ void __launch_bounds__(kBlock) k_cell_canon(const GridDesc *__restrict__ g, int ent_cap,
+                                                      const int *__restrict__ cell_start,
+                                                      const int *__restrict__ tmp_key,
+                                                      const double2 *__restrict__ tmp_pos,
+                                                      const int *__restrict__ tmp_cell, int *__restrict__ ent_key,
+                                                      double2 *__restrict__ ent_pos, int *__restrict__ ent_of,
+                                                      int *__restrict__ flags)
+{
+    cell_canon_body(g, ent_cap, cell_start, tmp_key, tmp_pos, tmp_cell, ent_key, ent_pos, ent_of, flags);
+}
+__global__ void __launch_bounds__(kBlock) k_cell_canon_batch(const NbrChan *__restrict__ chan)
+{
+    const NbrChan &c = chan[blockIdx.y];
+    cell_canon_body(c.g, (int)c.P.ell_stride, c.cell_start, c.tmp_key, c.tmp_pos, c.tmp_cell, c.ent_key, c.ent_pos, c.ent_of,
+                    c.flags);
+}
 
 // One descriptor per tile (tile.cuh): entry ranges of the (kTileRows + 2) x (w + 2) cell neighbourhood and
 // their slots.  One warp per tile: lane (3 r + k) fetches range k of staged row r, the slot offsets are a
 // warp prefix sum, lane 0 writes the rest.
-__global__ void __launch_bounds__(kBlock) k_tile_setup(const GridDesc *__restrict__ g, int ncx, int slab, int w,
-                                                      unsigned n_tiles, int cap, int ent_cap,
-                                                      const int *__restrict__ cell_start,
-                                                      TileDesc *__restrict__ tiles, int *__restrict__ totals,
-                                                      int *__restrict__ flags)
+__device__ __forceinline__ void tile_setup_body(const GridDesc *__restrict__ g, int ncx, int slab, int w, unsigned n_tiles,
+                                                int cap, int ent_cap, const int *__restrict__ cell_start,
+                                                TileDesc *__restrict__ tiles, int *__restrict__ totals,
+                                                int *__restrict__ flags)
 {
     const unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -372,6 +448,20 @@ __global__ void __launch_bounds__(kBlock) k_tile_setup(const GridDesc *__restric
         T.flags = f;
         if (valid) atomicMax(&totals[3], used + 1);
     }
+}
+__global__ void __launch_bounds__(kBlock) k_tile_setup(const GridDesc *__restrict__ g, int ncx, int slab, int w,
+                                                      unsigned n_tiles, int cap, int ent_cap,
+                                                      const int *__restrict__ cell_start,
+                                                      TileDesc *__restrict__ tiles, int *__restrict__ totals,
+                                                      int *__restrict__ flags)
+{
+    tile_setup_body(g, ncx, slab, w, n_tiles, cap, ent_cap, cell_start, tiles, totals, flags);
+}
+__global__ void __launch_bounds__(kBlock) k_tile_setup_batch(const NbrChan *__restrict__ chan)
+{
+    const NbrChan &c = chan[blockIdx.y];
+    tile_setup_body(c.g, c.P.ncx, c.P.slab, c.tile_w, c.n_tiles, c.tile_cap, (int)c.P.ell_stride, c.cell_start, c.tiles,
+                    c.totals, c.flags);
 }
 
 // nb:357-372 for "particle a (wrapped xa, ya) meets an entry at (ex, ey)": minimum image, cut-off and
@@ -677,15 +767,12 @@ __device__ __forceinline__ int general_walk(const NbrParams &P, const TileDesc &
 }
 
 template <bool HALF>
-__global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, const GridDesc *__restrict__ g,
-                                                           const TileDesc *__restrict__ tiles, int tile_w,
-                                                           const int *__restrict__ cell_start,
-                                                           const double2 *__restrict__ snap,
-                                                           const int *__restrict__ cell_of,
-                                                           const int *__restrict__ ent_key,
-                                                           const double2 *__restrict__ ent_pos, uint4 *ell_q,
-                                                           int *__restrict__ cnt, int *__restrict__ totals,
-                                                           int *__restrict__ flags, int cap)
+__device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__restrict__ g, const TileDesc *__restrict__ tiles,
+                                               int tile_w, const int *__restrict__ cell_start,
+                                               const double2 *__restrict__ snap, const int *__restrict__ cell_of,
+                                               const int *__restrict__ ent_key, const double2 *__restrict__ ent_pos,
+                                               uint4 *ell_q, int *__restrict__ cnt, int *__restrict__ totals,
+                                               int *__restrict__ flags, int cap)
 {
     load_counts(P);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -843,6 +930,26 @@ __global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, cons
         if (t_max) atomicMax(&totals[2], t_max);
         if (t_max > P.ell_cap) atomicOr(flags, kErrCsrCap);
     }
+}
+template <bool HALF>
+__global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, const GridDesc *__restrict__ g,
+                                                           const TileDesc *__restrict__ tiles, int tile_w,
+                                                           const int *__restrict__ cell_start,
+                                                           const double2 *__restrict__ snap,
+                                                           const int *__restrict__ cell_of,
+                                                           const int *__restrict__ ent_key,
+                                                           const double2 *__restrict__ ent_pos, uint4 *ell_q,
+                                                           int *__restrict__ cnt, int *__restrict__ totals,
+                                                           int *__restrict__ flags, int cap)
+{
+    walk_tile_body<HALF>(P, g, tiles, tile_w, cell_start, snap, cell_of, ent_key, ent_pos, ell_q, cnt, totals, flags, cap);
+}
+// full lists only (the half list is the stateless MEX export)
+__global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile_batch(const NbrChan *__restrict__ chan)
+{
+    const NbrChan &c = chan[blockIdx.y];
+    walk_tile_body<false>(c.P, c.g, c.tiles, c.tile_w, c.cell_start, c.snap, c.cell_of, c.ent_key, c.ent_pos, c.ell_q,
+                          c.ell_cnt, c.totals, c.flags, c.tile_cap);
 }
 
 // Number of reference half pairs inside a FULL row set (status / export sizing only): entries whose
@@ -1260,6 +1367,78 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
     }
     w.half_only = half_only;
     w.half_valid = half_only;   // a full build counts its half pairs on demand (neighbor_half_total)
+    SPHB_CUDA(cudaGetLastError());
+    if (launches) *launches += nl;
+    return 0;
+}
+
+// ---- batched build over an ensemble of channels (common.cuh: NbrBatchLaunch) --------------------------------
+size_t neighbor_batch_record_bytes() { return sizeof(NbrChan); }
+
+// Writes the channel's record (host memory, neighbor_batch_record_bytes() bytes) and its scan record.
+int neighbor_batch_fill(NeighborWork &w, const double2 *pos, void *host_record, ScanChan *host_scan)
+{
+    if (w.slab) return set_error("SPHB:batch", "slabs of a sharded channel cannot be batched");
+    if (!w.grid_armed || !w.ell_q.p || !w.tiles.p)
+        return set_error("SPHB:batch", "every channel needs its first (exact) list build before it joins a batch");
+    SPHB_TRY(w.scan_tmp.reserve(scan_workspace_ints((size_t)w.cell_cap) * sizeof(int)));
+    NbrChan c;
+    c.P = make_params(w);
+    c.pos = pos;
+    c.g = w.grid.as<GridDesc>();
+    c.flags = w.flags.as<int>();
+    c.totals = w.totals.as<int>();
+    c.cell_cnt = w.cell_cnt.as<int>();
+    c.cell_start = w.cell_start.as<int>();
+    c.snap = w.snap.as<double2>();
+    c.cell_of = w.cell_of.as<int>();
+    c.ent_of = w.ent_of.as<int>();
+    c.tmp_key = w.tmp_key.as<int>();
+    c.tmp_pos = w.tmp_pos.as<double2>();
+    c.tmp_cell = w.tmp_cell.as<int>();
+    c.ent_key = w.ent_key.as<int>();
+    c.ent_pos = w.ent_pos.as<double2>();
+    c.tiles = w.tiles.as<TileDesc>();
+    c.ell_q = w.ell_q.as<uint4>();
+    c.ell_cnt = w.ell_cnt.as<int>();
+    c.tile_w = w.tile_w;
+    c.tile_cap = w.tile_cap;
+    c.n_tiles = w.n_tiles;
+    std::memcpy(host_record, &c, sizeof(NbrChan));
+    host_scan->in = c.cell_cnt;
+    host_scan->out = c.cell_start;
+    host_scan->tile_totals = w.scan_tmp.as<int>();
+    host_scan->total_out = &c.g->n_entries;
+    return 0;
+}
+
+// The steady-state (non-exact, full-list) build of neighbor_build for every channel of the batch: the same
+// kernel bodies, one launch each.  Capacity overflows only raise the channels' own device flags.
+int neighbor_batch_build(const NbrBatchLaunch &L, long long *launches)
+{
+    const NbrChan *chan = static_cast<const NbrChan *>(L.chan);
+    const unsigned ny = (unsigned)L.n_chan;
+    const int nt = L.n_total;
+    long long nl = 0;
+    int blocks = (nt + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    k_yrange_grid_batch<<<dim3((unsigned)blocks, ny), 256, 0, L.st>>>(chan);
+    const int n_ints = 2 * (L.cell_cap + 1);
+    k_zero_cells_batch<<<dim3(std::max(1u, std::min(grid_for((size_t)n_ints), 64u)), ny), kBlock, 0, L.st>>>(chan, n_ints);
+    k_bin_count_batch<<<dim3(grid_for((size_t)nt), ny), kBlock, 0, L.st>>>(chan);
+    nl += 3;
+    SPHB_TRY(exclusive_scan_i32_batch(L.scan, L.n_chan, (size_t)L.cell_cap, L.st, &nl));
+    k_scatter_batch<<<dim3(grid_for((size_t)nt), ny), kBlock, 0, L.st>>>(chan);
+    k_cell_canon_batch<<<dim3(grid_for(L.ell_stride), ny), kBlock, 0, L.st>>>(chan);
+    k_tile_setup_batch<<<dim3(grid_for((size_t)L.n_tiles * 32), ny), kBlock, 0, L.st>>>(chan);
+    const size_t smem = (size_t)L.tile_cap * kWalkSlotBytes + (size_t)(kTileThreads / 32) * L.ell_cap * sizeof(unsigned short);
+    static size_t granted = 0;
+    if (smem > 48 * 1024 && smem > granted) {
+        SPHB_CUDA(cudaFuncSetAttribute(k_walk_tile_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        granted = smem;
+    }
+    k_walk_tile_batch<<<dim3(L.n_tiles, ny), kTileThreads, smem, L.st>>>(chan);
+    nl += 4;
     SPHB_CUDA(cudaGetLastError());
     if (launches) *launches += nl;
     return 0;

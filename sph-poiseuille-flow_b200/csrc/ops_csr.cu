@@ -182,7 +182,7 @@ __device__ __forceinline__ void density_rows(const PhysParams &P, const StateVie
     }
 }
 
-__global__ void __launch_bounds__(kTileThreads) k_density(PhysParams P, StateView S)
+__device__ __forceinline__ void density_tile(PhysParams P, StateView S)
 {
     load_counts(P);
     SPHB_TILE_BEGIN();
@@ -208,6 +208,12 @@ __global__ void __launch_bounds__(kTileThreads) k_density(PhysParams P, StateVie
 #define SPHB_CALL(plain) density_rows<plain>(P, S, T, pre, s_xy, s_w)
     SPHB_TILE_DISPATCH(walls, SPHB_CALL);
 #undef SPHB_CALL
+}
+__global__ void __launch_bounds__(kTileThreads) k_density(PhysParams P, StateView S) { density_tile(P, S); }
+__global__ void __launch_bounds__(kTileThreads) k_density_batch(const BatchChan *__restrict__ chan)
+{
+    const BatchChan &c = chan[blockIdx.y];
+    density_tile(c.P, c.S);
 }
 
 // ---------------------------------------------------------------- P1 pass 2: A -> B (ph:239-366)
@@ -240,7 +246,7 @@ __device__ __forceinline__ void kgc_rows(const PhysParams &P, const StateView &S
     }
 }
 
-__global__ void __launch_bounds__(kTileThreads) k_kgc(PhysParams P, StateView S)
+__device__ __forceinline__ void kgc_tile(PhysParams P, StateView S)
 {
     load_counts(P);
     SPHB_TILE_BEGIN();
@@ -260,6 +266,12 @@ __global__ void __launch_bounds__(kTileThreads) k_kgc(PhysParams P, StateView S)
 #define SPHB_CALL(plain) kgc_rows<plain>(P, S, T, pre, s_xy, s_V)
     SPHB_TILE_DISPATCH(0, SPHB_CALL);
 #undef SPHB_CALL
+}
+__global__ void __launch_bounds__(kTileThreads) k_kgc(PhysParams P, StateView S) { kgc_tile(P, S); }
+__global__ void __launch_bounds__(kTileThreads) k_kgc_batch(const BatchChan *__restrict__ chan)
+{
+    const BatchChan &c = chan[blockIdx.y];
+    kgc_tile(c.P, c.S);
 }
 
 // ---------------------------------------------------------------- P2 + P3 fused (ph:469-545, 636-710)
@@ -384,8 +396,7 @@ __device__ __forceinline__ double half_step_rho(double rho, double drho, double 
 // ---------------------------------------------------------------- dt on the device (m:519-527) and the
 // half-step density / pressure of every particle (ph:857-862), which the pressure gather reads per
 // neighbour.  Every thread derives the same dt from the device vmax; thread 0 publishes it.
-__global__ void __launch_bounds__(kBlock) k_time_step(PhysParams P, StateView S, DevScalars *sc, double remain,
-                                                     double fixed_dt)
+__device__ __forceinline__ void time_step_rows(PhysParams P, StateView S, DevScalars *sc, double remain, double fixed_dt)
 {
     load_counts(P);
     double dt;
@@ -408,6 +419,17 @@ __global__ void __launch_bounds__(kBlock) k_time_step(PhysParams P, StateView S,
         const double rho_h = half_step_rho(S.rho[i], S.drho_dt[i], dt, P.rho0);
         S.rp_half[i] = make_double2(rho_h, P.p0 * (rho_h / P.rho0 - 1.0));   // ph:862
     }
+}
+__global__ void __launch_bounds__(kBlock) k_time_step(PhysParams P, StateView S, DevScalars *sc, double remain,
+                                                     double fixed_dt)
+{
+    time_step_rows(P, S, sc, remain, fixed_dt);
+}
+__global__ void __launch_bounds__(kBlock) k_time_step_batch(const BatchChan *__restrict__ chan, double remain,
+                                                           double fixed_dt)
+{
+    const BatchChan &c = chan[blockIdx.y];
+    time_step_rows(c.P, c.S, c.sc, remain, fixed_dt);
 }
 
 
@@ -477,7 +499,7 @@ __device__ __forceinline__ void pressure_rows(const PhysParams &P, const StateVi
     }
 }
 
-__global__ void __launch_bounds__(kTileThreads) k_pressure(PhysParams P, StateView S, const DevScalars *__restrict__ sc)
+__device__ __forceinline__ void pressure_tile(PhysParams P, StateView S, const DevScalars *__restrict__ sc)
 {
     load_counts(P);
     SPHB_TILE_BEGIN();
@@ -519,6 +541,15 @@ __global__ void __launch_bounds__(kTileThreads) k_pressure(PhysParams P, StateVi
 #define SPHB_CALL(plain) pressure_rows<plain>(P, S, T, pre, s_xy, s_v, s_rp, s_b1, s_b2, s_V, dt)
     SPHB_TILE_DISPATCH(walls, SPHB_CALL);
 #undef SPHB_CALL
+}
+__global__ void __launch_bounds__(kTileThreads) k_pressure(PhysParams P, StateView S, const DevScalars *__restrict__ sc)
+{
+    pressure_tile(P, S, sc);
+}
+__global__ void __launch_bounds__(kTileThreads) k_pressure_batch(const BatchChan *__restrict__ chan)
+{
+    const BatchChan &c = chan[blockIdx.y];
+    pressure_tile(c.P, c.S, c.sc);
 }
 
 // ---------------------------------------------------------------- P2 + P3 + dt + P4 + kick, one gather
@@ -652,8 +683,8 @@ __device__ __forceinline__ void force_rows(const PhysParams &P, const StateView 
     }
 }
 
-__global__ void __launch_bounds__(kTileThreads) k_force_fused(PhysParams P, StateView S, DevScalars *sc, double remain,
-                                                             double fixed_dt, int add_gravity)
+__device__ __forceinline__ void force_fused_tile(PhysParams P, StateView S, DevScalars *sc, double remain, double fixed_dt,
+                                                 int add_gravity)
 {
     load_counts(P);
     (void)remain;
@@ -697,12 +728,32 @@ __global__ void __launch_bounds__(kTileThreads) k_force_fused(PhysParams P, Stat
     SPHB_TILE_DISPATCH(walls, SPHB_CALL);
 #undef SPHB_CALL
 }
+__global__ void __launch_bounds__(kTileThreads) k_force_fused(PhysParams P, StateView S, DevScalars *sc, double remain,
+                                                             double fixed_dt, int add_gravity)
+{
+    force_fused_tile(P, S, sc, remain, fixed_dt, add_gravity);
+}
+__global__ void __launch_bounds__(kTileThreads) k_force_fused_batch(const BatchChan *__restrict__ chan, int add_gravity)
+{
+    const BatchChan &c = chan[blockIdx.y];
+    force_fused_tile(c.P, c.S, c.sc, 0.0, 0.0, add_gravity);
+}
 
 // publishes the time step of the substep and re-arms the max|v| reduction (one thread; runs before the
 // fused force kernel on the same stream)
 __global__ void k_publish_dt(PhysParams P, DevScalars *sc, double remain, double fixed_dt)
 {
     sc->dt = device_dt(P, sc, remain, fixed_dt);
+    sc->vmax_bits = 0ull;
+}
+// one thread per channel
+__global__ void __launch_bounds__(kBlock) k_publish_dt_batch(const BatchChan *__restrict__ chan, int n_chan, double remain,
+                                                            double fixed_dt)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_chan) return;
+    DevScalars *sc = chan[k].sc;
+    sc->dt = device_dt(chan[k].P, sc, remain, fixed_dt);
     sc->vmax_bits = 0ull;
 }
 
@@ -766,8 +817,7 @@ __device__ __forceinline__ double continuity_rows(const PhysParams &P, const Sta
     return speed;
 }
 
-__global__ void __launch_bounds__(kTileThreads) k_continuity(PhysParams P, StateView S, DevScalars *sc, int do_wrap,
-                                                            int advance_clock)
+__device__ __forceinline__ void continuity_tile(PhysParams P, StateView S, DevScalars *sc, int do_wrap, int advance_clock)
 {
     load_counts(P);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -828,6 +878,17 @@ __global__ void __launch_bounds__(kTileThreads) k_continuity(PhysParams P, State
         }
     }
 }
+__global__ void __launch_bounds__(kTileThreads) k_continuity(PhysParams P, StateView S, DevScalars *sc, int do_wrap,
+                                                            int advance_clock)
+{
+    continuity_tile(P, S, sc, do_wrap, advance_clock);
+}
+__global__ void __launch_bounds__(kTileThreads) k_continuity_batch(const BatchChan *__restrict__ chan, int do_wrap,
+                                                                  int advance_clock)
+{
+    const BatchChan &c = chan[blockIdx.y];
+    continuity_tile(c.P, c.S, c.sc, do_wrap, advance_clock);
+}
 
 __global__ void __launch_bounds__(256) k_vmax(int nf, const double2 *__restrict__ vel, DevScalars *sc)
 {
@@ -857,7 +918,7 @@ __global__ void __launch_bounds__(kBlock) k_wrap(int nf, double DL, double2 *pos
 // Only wall particles at y <= 0 or y >= DH count (ph:1731-1736) and the pair distance is < 2h, so only
 // tiles whose neighbourhood holds wall entries do any work: the others exit after the staging vote.
 // One partial (bottom, top) per tile, summed in tile order by k_wall_shear_final: deterministic.
-__global__ void __launch_bounds__(kTileThreads) k_wall_shear(PhysParams P, StateView S, double *partials)
+__device__ __forceinline__ void wall_shear_tile(PhysParams P, StateView S, double *partials)
 {
     load_counts(P);
     __shared__ double shb[kTileThreads], sht[kTileThreads];
@@ -932,9 +993,17 @@ __global__ void __launch_bounds__(kTileThreads) k_wall_shear(PhysParams P, State
         partials[nt + blockIdx.x] = sht[0];
     }
 }
+__global__ void __launch_bounds__(kTileThreads) k_wall_shear(PhysParams P, StateView S, double *partials)
+{
+    wall_shear_tile(P, S, partials);
+}
+__global__ void __launch_bounds__(kTileThreads) k_wall_shear_batch(const BatchChan *__restrict__ chan)
+{
+    const BatchChan &c = chan[blockIdx.y];
+    wall_shear_tile(c.P, c.S, c.shear_partials);
+}
 
-__global__ void __launch_bounds__(256) k_wall_shear_final(const double *partials, int nblocks, double DL,
-                                                         DevScalars *sc)
+__device__ __forceinline__ void wall_shear_sum(const double *partials, int nblocks, double DL, DevScalars *sc)
 {
     __shared__ double shb[256], sht[256];
     double sb = 0.0, st = 0.0;
@@ -956,6 +1025,16 @@ __global__ void __launch_bounds__(256) k_wall_shear_final(const double *partials
         sc->tau_bottom = -shb[0] / DL;
         sc->tau_top = -sht[0] / DL;
     }
+}
+__global__ void __launch_bounds__(256) k_wall_shear_final(const double *partials, int nblocks, double DL,
+                                                         DevScalars *sc)
+{
+    wall_shear_sum(partials, nblocks, DL, sc);
+}
+__global__ void __launch_bounds__(256) k_wall_shear_final_batch(const BatchChan *__restrict__ chan, int nblocks)
+{
+    const BatchChan &c = chan[blockIdx.y];
+    wall_shear_sum(c.shear_partials, nblocks, c.P.DL, c.sc);
 }
 
 // ---------------------------------------------------------------- binned u(y) monitor (m:579-605)
@@ -1097,6 +1176,74 @@ int csr_wall_shear(const PhysParams &P, const StateView &S, DevScalars *sc, doub
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
+// ---- batched launches (ops_csr.cuh): grid = (the channel's own grid, channels) ----------------------------
+int csr_batch_configure(int tile_cap)
+{
+    static int granted = 0;
+    if (tile_cap <= granted) return 0;
+    const size_t c = (size_t)tile_cap;
+#define SPHB_GRANT(kern, bytes)                                                                              \
+    if ((bytes) > 48 * 1024)                                                                                 \
+    SPHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
+    SPHB_GRANT(k_density_batch, c * kDensitySlot);
+    SPHB_GRANT(k_kgc_batch, c * kKgcSlot);
+    SPHB_GRANT(k_pressure_batch, c * kPressureSlot);
+    SPHB_GRANT(k_force_fused_batch, c * kForceSlot);
+    SPHB_GRANT(k_continuity_batch, c * kContinuitySlot);
+    SPHB_GRANT(k_wall_shear_batch, c * kShearSlot);
+#undef SPHB_GRANT
+    granted = tile_cap;
+    return 0;
+}
+static inline dim3 batch_grid(const BatchLaunch &L, unsigned gx) { return dim3(gx, (unsigned)L.n_chan, 1u); }
+
+int csr_batch_density(const BatchLaunch &L)
+{
+    k_density_batch<<<batch_grid(L, L.n_tiles), kTileThreads, (size_t)L.tile_cap * kDensitySlot, L.st>>>(L.chan);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_batch_kgc(const BatchLaunch &L)
+{
+    k_kgc_batch<<<batch_grid(L, L.n_tiles), kTileThreads, (size_t)L.tile_cap * kKgcSlot, L.st>>>(L.chan);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_batch_force_fused(const BatchLaunch &L, double remain, double fixed_dt, bool add_gravity)
+{
+    k_publish_dt_batch<<<grid_for((size_t)L.n_chan), kBlock, 0, L.st>>>(L.chan, L.n_chan, remain, fixed_dt);
+    k_force_fused_batch<<<batch_grid(L, L.n_tiles), kTileThreads, (size_t)L.tile_cap * kForceSlot, L.st>>>(
+        L.chan, add_gravity ? 1 : 0);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_batch_time_step(const BatchLaunch &L, double remain, double fixed_dt)
+{
+    k_time_step_batch<<<batch_grid(L, grid_for((size_t)L.n_fluid)), kBlock, 0, L.st>>>(L.chan, remain, fixed_dt);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_batch_pressure(const BatchLaunch &L)
+{
+    k_pressure_batch<<<batch_grid(L, L.n_tiles), kTileThreads, (size_t)L.tile_cap * kPressureSlot, L.st>>>(L.chan);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_batch_continuity(const BatchLaunch &L, bool wrap, bool advance_clock)
+{
+    k_continuity_batch<<<batch_grid(L, L.n_tiles), kTileThreads, (size_t)L.tile_cap * kContinuitySlot, L.st>>>(
+        L.chan, wrap ? 1 : 0, advance_clock ? 1 : 0);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_batch_wall_shear(const BatchLaunch &L)
+{
+    k_wall_shear_batch<<<batch_grid(L, L.n_tiles), kTileThreads, (size_t)L.tile_cap * kShearSlot, L.st>>>(L.chan);
+    k_wall_shear_final_batch<<<batch_grid(L, 1u), 256, 0, L.st>>>(L.chan, (int)L.n_tiles);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int csr_profile(const PhysParams &P, const StateView &S, double x0, double half_width, int n_bins,
                 const double *edges_dev, double *sum_dev, double *cnt_dev, cudaStream_t st)
 {

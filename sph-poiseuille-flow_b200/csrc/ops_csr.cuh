@@ -83,4 +83,32 @@ int csr_profile(const PhysParams &P, const StateView &S, double x0, double half_
 int csr_configure(int tile_cap);     // grants the gather kernels the shared memory `tile_cap` slots need
 int csr_max_tile_slots();            // what the widest gather kernel (pressure) can stage
 
+// ---- batched launches over an ensemble of independent channels (batch.cu; BASELINE configs[3]) ----------
+// Every channel keeps its own state, list and scalars; a batched launch runs the SAME kernel body for all of
+// them in one grid: blockIdx.x = the channel's own block index (tile), blockIdx.y = channel.  The per-channel
+// arguments live in a device array of BatchChan records (stable across steps; refreshed after a cell sort
+// has swapped buffers).  Launch geometry (n_tiles, rows, shared memory) must be uniform over the channels.
+struct BatchChan {
+    PhysParams P;
+    StateView S;
+    DevScalars *sc;
+    double *shear_partials;
+};
+struct BatchLaunch {
+    const BatchChan *chan;   // device array [n_chan]
+    int n_chan;
+    unsigned n_tiles;        // tiles of every channel
+    int n_fluid;             // fluid rows of every channel
+    int tile_cap;            // largest slot count over the channels (sizes the dynamic shared memory)
+    cudaStream_t st;
+};
+int csr_batch_configure(int tile_cap);
+int csr_batch_density(const BatchLaunch &L);
+int csr_batch_kgc(const BatchLaunch &L);
+int csr_batch_force_fused(const BatchLaunch &L, double remain, double fixed_dt, bool add_gravity);
+int csr_batch_time_step(const BatchLaunch &L, double remain, double fixed_dt);
+int csr_batch_pressure(const BatchLaunch &L);
+int csr_batch_continuity(const BatchLaunch &L, bool wrap, bool advance_clock);
+int csr_batch_wall_shear(const BatchLaunch &L);
+
 }  // namespace sphb

@@ -44,9 +44,8 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *block_total)
     return res;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_tiles(const int *__restrict__ in, int *__restrict__ out,
-                                                          int *__restrict__ tile_totals, size_t n,
-                                                          int *__restrict__ total_out)
+__device__ __forceinline__ void scan_tiles_body(const int *__restrict__ in, int *__restrict__ out,
+                                                int *__restrict__ tile_totals, size_t n, int *__restrict__ total_out)
 {
     __shared__ int total_sh;
     const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
@@ -72,11 +71,22 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles(const int *__restrict
         }
     }
 }
+__global__ void __launch_bounds__(kScanThreads) scan_tiles(const int *__restrict__ in, int *__restrict__ out,
+                                                          int *__restrict__ tile_totals, size_t n,
+                                                          int *__restrict__ total_out)
+{
+    scan_tiles_body(in, out, tile_totals, n, total_out);
+}
+__global__ void __launch_bounds__(kScanThreads) scan_tiles_batch(const ScanChan *__restrict__ chan, size_t n)
+{
+    const ScanChan c = chan[blockIdx.y];
+    scan_tiles_body(c.in, c.out, c.tile_totals, n, c.total_out);
+}
 
 // Every tile sums the totals of the tiles before it (a few hundred values at most) and adds the offset
 // to its elements; the last tile also writes the grand total.  No separate "scan of the totals" launch.
-__global__ void __launch_bounds__(kScanThreads) scan_finish(int *__restrict__ out, const int *__restrict__ tile_totals,
-                                                           size_t n, int *__restrict__ total_out)
+__device__ __forceinline__ void scan_finish_body(int *__restrict__ out, const int *__restrict__ tile_totals, size_t n,
+                                                 int *__restrict__ total_out)
 {
     __shared__ int warp_part[32];
     __shared__ int off_sh;
@@ -104,6 +114,16 @@ __global__ void __launch_bounds__(kScanThreads) scan_finish(int *__restrict__ ou
         if (total_out) *total_out = total;
     }
 }
+__global__ void __launch_bounds__(kScanThreads) scan_finish(int *__restrict__ out, const int *__restrict__ tile_totals,
+                                                           size_t n, int *__restrict__ total_out)
+{
+    scan_finish_body(out, tile_totals, n, total_out);
+}
+__global__ void __launch_bounds__(kScanThreads) scan_finish_batch(const ScanChan *__restrict__ chan, size_t n)
+{
+    const ScanChan c = chan[blockIdx.y];
+    scan_finish_body(c.out, c.tile_totals, n, c.total_out);
+}
 
 }  // namespace
 
@@ -120,6 +140,20 @@ int exclusive_scan_i32(const int *in, int *out, size_t n, DevBuf &tmp, int *tota
     int *totals = tmp.as<int>();
     scan_tiles<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(in, out, totals, n, total_out_dev);
     if (n_tiles > 1) scan_finish<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(out, totals, n, total_out_dev);
+    if (launches) *launches += (n_tiles > 1) ? 2 : 1;
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+size_t scan_workspace_ints(size_t n) { return n == 0 ? 1 : (n + kTile - 1) / kTile; }
+
+int exclusive_scan_i32_batch(const ScanChan *chan_dev, int n_chan, size_t n, cudaStream_t st, long long *launches)
+{
+    if (n == 0 || n_chan <= 0) return set_error("SPHB:arg", "empty batched scan");
+    const size_t n_tiles = (n + kTile - 1) / kTile;
+    const dim3 grid((unsigned)n_tiles, (unsigned)n_chan);
+    scan_tiles_batch<<<grid, kScanThreads, 0, st>>>(chan_dev, n);
+    if (n_tiles > 1) scan_finish_batch<<<grid, kScanThreads, 0, st>>>(chan_dev, n);
     if (launches) *launches += (n_tiles > 1) ? 2 : 1;
     SPHB_CUDA(cudaGetLastError());
     return 0;

@@ -121,3 +121,26 @@ def test_mex_shims_load_and_keep_gateway_contract():
     with pytest.raises(MexError) as e:
         mex.call("sphb_physics_mexFunction", 2, "integration_verlet", *([1.0] * 21))
     assert e.value.identifier == "SPH:Physics:verlet:nlhs"
+
+
+def test_batch_entry_points_validate_arguments_without_device():
+    """sphb_batch_* (batched ensemble launches): argument checks fire before any CUDA call, NULL handles are
+    tolerated by the accessors and by destroy."""
+    sphb = load_product()
+    L = sphb.lib()
+    out = ctypes.c_void_p()
+    assert L.sphb_batch_create(None, ctypes.c_int(0), ctypes.byref(out)) != 0
+    assert L.sphb_last_error_id() == b"SPHB:arg"
+    arr = (ctypes.c_void_p * 1)(None)
+    assert L.sphb_batch_create(arr, ctypes.c_int(1), ctypes.byref(out)) != 0      # null member
+    assert L.sphb_last_error_id() == b"SPHB:arg" and not out.value
+    assert L.sphb_batch_create(arr, ctypes.c_int(70000), ctypes.byref(out)) != 0   # more than grid.y allows
+    assert L.sphb_last_error_id() == b"SPHB:batch"
+    for fn in ("sphb_batch_refresh", "sphb_batch_sync"):
+        f = getattr(L, fn)
+        f.argtypes = [ctypes.c_void_p]
+        assert f(None) != 0 and L.sphb_last_error_id() == b"SPHB:arg"
+    L.sphb_batch_run_dual.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    assert L.sphb_batch_run_dual(None, 1, 1) != 0 and L.sphb_last_error_id() == b"SPHB:arg"
+    assert L.sphb_batch_launches(None) == 0
+    L.sphb_batch_destroy(None)
