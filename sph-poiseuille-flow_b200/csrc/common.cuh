@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
@@ -58,6 +59,25 @@ struct DevBuf {
 struct __align__(32) Mat2 {
     double b11, b12, b21, b22;
 };
+
+// Dynamic shared memory above 48 KB must be granted per kernel -- and per DEVICE (the attribute lives in the
+// device's context).  One SmemGrant per kernel remembers what each device of the process has been granted.
+struct SmemGrant {
+    static constexpr int kMaxDev = 64;
+    std::atomic<size_t> bytes[kMaxDev];
+};
+template <class Kern>
+inline int grant_smem(SmemGrant &g, Kern *kern, size_t bytes)
+{
+    if (bytes <= 48 * 1024) return 0;
+    int dev = 0;
+    SPHB_CUDA(cudaGetDevice(&dev));
+    const bool cached = dev >= 0 && dev < SmemGrant::kMaxDev;
+    if (cached && bytes <= g.bytes[dev].load(std::memory_order_relaxed)) return 0;
+    SPHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (cached) g.bytes[dev].store(bytes, std::memory_order_relaxed);
+    return 0;
+}
 
 constexpr int kBlock = 128;
 inline unsigned grid_for(size_t n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }

@@ -1136,16 +1136,9 @@ constexpr size_t kWalkSlotBytes = sizeof(double2) + sizeof(int);
 
 int set_walk_smem(size_t bytes)
 {
-    static size_t granted[2] = {0, 0};
-    if (bytes <= 48 * 1024) return 0;
-    if (bytes > granted[0]) {
-        SPHB_CUDA(cudaFuncSetAttribute(k_walk_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        granted[0] = bytes;
-    }
-    if (bytes > granted[1]) {
-        SPHB_CUDA(cudaFuncSetAttribute(k_walk_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        granted[1] = bytes;
-    }
+    static SmemGrant g[2];
+    SPHB_TRY(grant_smem(g[0], k_walk_tile<true>, bytes));
+    SPHB_TRY(grant_smem(g[1], k_walk_tile<false>, bytes));
     return 0;
 }
 
@@ -1432,11 +1425,8 @@ int neighbor_batch_build(const NbrBatchLaunch &L, long long *launches)
     k_cell_canon_batch<<<dim3(grid_for(L.ell_stride), ny), kBlock, 0, L.st>>>(chan);
     k_tile_setup_batch<<<dim3(grid_for((size_t)L.n_tiles * 32), ny), kBlock, 0, L.st>>>(chan);
     const size_t smem = (size_t)L.tile_cap * kWalkSlotBytes + (size_t)(kTileThreads / 32) * L.ell_cap * sizeof(unsigned short);
-    static size_t granted = 0;
-    if (smem > 48 * 1024 && smem > granted) {
-        SPHB_CUDA(cudaFuncSetAttribute(k_walk_tile_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        granted = smem;
-    }
+    static SmemGrant grant;
+    SPHB_TRY(grant_smem(grant, k_walk_tile_batch, smem));
     k_walk_tile_batch<<<dim3(L.n_tiles, ny), kTileThreads, smem, L.st>>>(chan);
     nl += 4;
     SPHB_CUDA(cudaGetLastError());
@@ -1450,11 +1440,8 @@ int neighbor_half_total(NeighborWork &w, cudaStream_t st)
     if (w.half_valid) return 0;
     NbrParams P = make_params(w);
     const size_t smem = (size_t)w.tile_cap * sizeof(int);
-    static size_t granted = 0;
-    if (smem > 48 * 1024 && smem > granted) {
-        SPHB_CUDA(cudaFuncSetAttribute(k_half_total, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        granted = smem;
-    }
+    static SmemGrant grant;
+    SPHB_TRY(grant_smem(grant, k_half_total, smem));
     SPHB_CUDA(cudaMemsetAsync(w.totals.p, 0, sizeof(int), st));
     k_half_total<<<w.n_tiles, kTileThreads, smem, st>>>(P, w.tiles.as<TileDesc>(), w.ent_key.as<int>(),
                                                         w.ell_q.as<uint4>(), w.ell_cnt.as<int>(), w.totals.as<int>(),

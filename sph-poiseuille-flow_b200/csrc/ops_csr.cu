@@ -1075,26 +1075,20 @@ int csr_max_tile_slots()
     return (int)((227 * 1024 - 4096) / kPressureSlot);
 }
 
-// dynamic shared memory above 48 KB must be granted per kernel
+// dynamic shared memory above 48 KB must be granted per kernel (and per device: SmemGrant)
 int csr_configure(int tile_cap)
 {
-    static int granted = 0;
-    if (tile_cap <= granted) return 0;
+    static SmemGrant g[9];
     const size_t c = (size_t)tile_cap;
-#define SPHB_GRANT(kern, bytes)                                                                              \
-    if ((bytes) > 48 * 1024)                                                                                 \
-    SPHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
-    SPHB_GRANT(k_density, c * kDensitySlot);
-    SPHB_GRANT(k_kgc, c * kKgcSlot);
-    SPHB_GRANT((k_visc_transport<true, true>), c * kViscSlot);
-    SPHB_GRANT((k_visc_transport<true, false>), c * kViscSlot);
-    SPHB_GRANT((k_visc_transport<false, true>), c * kViscSlot);
-    SPHB_GRANT(k_pressure, c * kPressureSlot);
-    SPHB_GRANT(k_force_fused, c * kForceSlot);
-    SPHB_GRANT(k_continuity, c * kContinuitySlot);
-    SPHB_GRANT(k_wall_shear, c * kShearSlot);
-#undef SPHB_GRANT
-    granted = tile_cap;
+    SPHB_TRY(grant_smem(g[0], k_density, c * kDensitySlot));
+    SPHB_TRY(grant_smem(g[1], k_kgc, c * kKgcSlot));
+    SPHB_TRY(grant_smem(g[2], k_visc_transport<true, true>, c * kViscSlot));
+    SPHB_TRY(grant_smem(g[3], k_visc_transport<true, false>, c * kViscSlot));
+    SPHB_TRY(grant_smem(g[4], k_visc_transport<false, true>, c * kViscSlot));
+    SPHB_TRY(grant_smem(g[5], k_pressure, c * kPressureSlot));
+    SPHB_TRY(grant_smem(g[6], k_force_fused, c * kForceSlot));
+    SPHB_TRY(grant_smem(g[7], k_continuity, c * kContinuitySlot));
+    SPHB_TRY(grant_smem(g[8], k_wall_shear, c * kShearSlot));
     return 0;
 }
 
@@ -1179,20 +1173,14 @@ int csr_wall_shear(const PhysParams &P, const StateView &S, DevScalars *sc, doub
 // ---- batched launches (ops_csr.cuh): grid = (the channel's own grid, channels) ----------------------------
 int csr_batch_configure(int tile_cap)
 {
-    static int granted = 0;
-    if (tile_cap <= granted) return 0;
+    static SmemGrant g[6];
     const size_t c = (size_t)tile_cap;
-#define SPHB_GRANT(kern, bytes)                                                                              \
-    if ((bytes) > 48 * 1024)                                                                                 \
-    SPHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
-    SPHB_GRANT(k_density_batch, c * kDensitySlot);
-    SPHB_GRANT(k_kgc_batch, c * kKgcSlot);
-    SPHB_GRANT(k_pressure_batch, c * kPressureSlot);
-    SPHB_GRANT(k_force_fused_batch, c * kForceSlot);
-    SPHB_GRANT(k_continuity_batch, c * kContinuitySlot);
-    SPHB_GRANT(k_wall_shear_batch, c * kShearSlot);
-#undef SPHB_GRANT
-    granted = tile_cap;
+    SPHB_TRY(grant_smem(g[0], k_density_batch, c * kDensitySlot));
+    SPHB_TRY(grant_smem(g[1], k_kgc_batch, c * kKgcSlot));
+    SPHB_TRY(grant_smem(g[2], k_pressure_batch, c * kPressureSlot));
+    SPHB_TRY(grant_smem(g[3], k_force_fused_batch, c * kForceSlot));
+    SPHB_TRY(grant_smem(g[4], k_continuity_batch, c * kContinuitySlot));
+    SPHB_TRY(grant_smem(g[5], k_wall_shear_batch, c * kShearSlot));
     return 0;
 }
 static inline dim3 batch_grid(const BatchLaunch &L, unsigned gx) { return dim3(gx, (unsigned)L.n_chan, 1u); }
