@@ -26,6 +26,10 @@ DRIVER = os.path.join(HERE, "sph_poiseuille_b200")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function",
           "-Xptxas", "-v" if os.environ.get("SPHB_PTXAS_V") else "-O3"]
+# experimental code paths, off unless asked for (each documented where it is defined)
+for _flag in ("SPHB_FLAT_STAGING",):
+    if os.environ.get(_flag):
+        COMMON.append(f"-D{_flag}={os.environ[_flag]}")
 UNITS = {
     "misc.cu": [],
     "scan.cu": [],
@@ -70,6 +74,11 @@ def _run(cmd, verbose):
 def build_library(force=False, verbose=False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
+    # objects built with other flags (an experimental -D switch toggled) are stale
+    stamp, flags = os.path.join(OBJ, "flags.txt"), " ".join(ARCH + COMMON)
+    if not os.path.exists(stamp) or open(stamp).read() != flags:
+        force = force or any(f.endswith(".o") for f in os.listdir(OBJ))
+        open(stamp, "w").write(flags)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "sph_b200.h"))
     objs = []

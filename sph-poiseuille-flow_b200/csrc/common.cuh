@@ -13,6 +13,10 @@
 
 #include "../../include/sph_b200.h"
 
+#ifndef SPHB_FLAT_STAGING
+#define SPHB_FLAT_STAGING 0   // 1: staging loops of the hot tile kernels as flat, load/store-split passes (tile.cuh)
+#endif
+
 namespace sphb {
 
 // ------------------------------------------------------------------------------------------------

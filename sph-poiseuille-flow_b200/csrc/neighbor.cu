@@ -789,11 +789,30 @@ __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__re
         const int row = T.cy0 + r - 1;
         s_cs[r][c] = (row >= 0 && row < ncy && c <= T.b - T.a) ? cell_start[(size_t)row * ncx + T.a + c] : 0;
     }
+#if SPHB_FLAT_STAGING
+    struct StageRec {
+        double2 xy;
+        int key;
+    };
+    tile_stage_flat(
+        T,
+        [&](int e) {
+            StageRec r;
+            r.key = ent_key[e];
+            r.xy = ent_pos[e];
+            return r;
+        },
+        [&](int slot, const StageRec &r) {
+            s_key[slot] = r.key;
+            s_xy[slot] = r.xy;
+        });
+#else
     SPHB_TILE_FOR_STAGED(T, e, slot)
     {
         s_key[slot] = ent_key[e];
         s_xy[slot] = ent_pos[e];
     }
+#endif
     __syncthreads();
 
     const size_t stride = P.ell_stride;

@@ -190,6 +190,31 @@ __device__ __forceinline__ void density_tile(PhysParams P, StateView S)
     double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
     double *s_w = reinterpret_cast<double *>(s_xy + cap);
     int walls = 0;
+#if SPHB_FLAT_STAGING
+    struct Rec {
+        double2 xy;
+        double m;
+        int j;
+    };
+    tile_stage_flat(
+        T,
+        [&](int e) {
+            Rec r;
+            r.j = S.ent_key[e] >> 3;
+            r.xy = S.ent_pos[e];
+            r.m = S.mass[r.j];
+            return r;
+        },
+        [&](int slot, const Rec &r) {
+            s_xy[slot] = r.xy;
+            if (r.j < P.nf) {
+                s_w[slot] = -1.0;
+            } else {
+                s_w[slot] = r.m * P.inv_rho0;
+                walls = 1;
+            }
+        });
+#else
     SPHB_TILE_FOR_STAGED(T, e, slot)
     {
         const int j = S.ent_key[e] >> 3;
@@ -201,6 +226,7 @@ __device__ __forceinline__ void density_tile(PhysParams P, StateView S)
             walls = 1;
         }
     }
+#endif
     if (threadIdx.x == 0) {
         s_xy[T.n_staged] = make_double2(kDummyCoord, kDummyCoord);
         s_w[T.n_staged] = -1.0;
@@ -253,11 +279,30 @@ __device__ __forceinline__ void kgc_tile(PhysParams P, StateView S)
     const OwnPre pre = tile_prefetch_own(S, T);
     double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
     double *s_V = reinterpret_cast<double *>(s_xy + cap);
+#if SPHB_FLAT_STAGING
+    struct Rec {
+        double2 xy;
+        double V;
+    };
+    tile_stage_flat(
+        T,
+        [&](int e) {
+            Rec r;
+            r.xy = S.ent_pos[e];
+            r.V = S.Vol[S.ent_key[e] >> 3];
+            return r;
+        },
+        [&](int slot, const Rec &r) {
+            s_xy[slot] = r.xy;
+            s_V[slot] = r.V;
+        });
+#else
     SPHB_TILE_FOR_STAGED(T, e, slot)
     {
         s_xy[slot] = S.ent_pos[e];
         s_V[slot] = S.Vol[S.ent_key[e] >> 3];
     }
+#endif
     if (threadIdx.x == 0) {
         s_xy[T.n_staged] = make_double2(kDummyCoord, kDummyCoord);
         s_V[T.n_staged] = 0.0;
@@ -698,6 +743,40 @@ __device__ __forceinline__ void force_fused_tile(PhysParams P, StateView S, DevS
     double2 *s_b1 = s_pV + cap;
     double2 *s_b2 = s_b1 + cap;
     int walls = 0;
+#if SPHB_FLAT_STAGING
+    struct Rec {
+        double2 xy, v;
+        double4 B;
+        double V, rho, drho;
+        int j;
+    };
+    tile_stage_flat(
+        T,
+        [&](int e) {
+            Rec r;
+            r.j = S.ent_key[e] >> 3;
+            r.xy = S.ent_pos[e];
+            r.V = S.Vol[r.j];
+            r.v = (r.j < P.nf ? S.vel : S.wall_vel)[r.j];   // a wall entry stages its wall velocity
+            r.rho = S.rho[r.j];                             // (wall rows hold valid values too; unused)
+            r.drho = S.drho_dt[r.j];
+            r.B = *reinterpret_cast<const double4 *>(&S.B[r.j]);
+            return r;
+        },
+        [&](int slot, const Rec &r) {
+            s_xy[slot] = r.xy;
+            s_v[slot] = r.v;
+            if (r.j < P.nf) {
+                const double rho_h = half_step_rho(r.rho, r.drho, dt, P.rho0);
+                s_pV[slot] = make_double2(P.p0 * (rho_h / P.rho0 - 1.0), r.V);   // ph:862
+                s_b1[slot] = make_double2(r.B.x, r.B.y);
+                s_b2[slot] = make_double2(r.B.z, r.B.w);
+            } else {
+                s_pV[slot] = make_double2(0.0, -r.V);
+                walls = 1;
+            }
+        });
+#else
     SPHB_TILE_FOR_STAGED(T, e, slot)
     {
         const int j = S.ent_key[e] >> 3;
@@ -716,6 +795,7 @@ __device__ __forceinline__ void force_fused_tile(PhysParams P, StateView S, DevS
             walls = 1;
         }
     }
+#endif
     if (threadIdx.x == 0) {
         const int d = T.n_staged;
         s_xy[d] = make_double2(kDummyCoord, kDummyCoord);
@@ -831,6 +911,33 @@ __device__ __forceinline__ void continuity_tile(PhysParams P, StateView S, DevSc
         double2 *s_v = s_xy + cap;
         double *s_V = reinterpret_cast<double *>(s_v + cap);
         int walls = 0;
+#if SPHB_FLAT_STAGING
+        struct Rec {
+            double2 xy, v;
+            double V;
+            int j;
+        };
+        tile_stage_flat(
+            T,
+            [&](int e) {
+                Rec r;
+                r.j = S.ent_key[e] >> 3;
+                r.xy = S.ent_pos[e];
+                r.V = S.Vol[r.j];
+                r.v = (r.j < P.nf ? S.vel_new : S.wall_vel)[r.j];
+                return r;
+            },
+            [&](int slot, const Rec &r) {
+                s_xy[slot] = r.xy;
+                s_v[slot] = r.v;
+                if (r.j < P.nf) {
+                    s_V[slot] = r.V;
+                } else {
+                    s_V[slot] = -r.V;
+                    walls = 1;
+                }
+            });
+#else
         SPHB_TILE_FOR_STAGED(T, e, slot)
         {
             const int j = S.ent_key[e] >> 3;
@@ -845,6 +952,7 @@ __device__ __forceinline__ void continuity_tile(PhysParams P, StateView S, DevSc
                 walls = 1;
             }
         }
+#endif
         if (threadIdx.x == 0) {
             const int d = T.n_staged;
             s_xy[d] = make_double2(kDummyCoord, kDummyCoord);

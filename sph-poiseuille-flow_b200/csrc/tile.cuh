@@ -117,6 +117,46 @@ __device__ __forceinline__ int tile_slot_entry(const TileDesc &T, int slot)
         for (int e = (T).seg[sg__].b + (int)threadIdx.x, slot = (T).seg[sg__].off + (int)threadIdx.x;     \
              e < (T).seg[sg__].e; e += (int)blockDim.x, slot += (int)blockDim.x)
 
+#if SPHB_FLAT_STAGING
+// ---- flat staging (opt-in: build with SPHB_FLAT_STAGING=1; profiles/r1_v8_source_hotspots.md, item 1) --------
+// The segment-by-segment loop above makes a CTA wait for one global-memory round trip per non-empty segment
+// and dependent load level (ent_key -> S.<field>[j]) before its row loop can start.  Here the staged slots
+// [0, n_staged) form ONE index range, kStageUnroll slots per thread and pass, and a pass is split into
+//   load(e)  -> a record of registers: every load of it is unconditional (clamped slot), so the loads of all
+//               the thread's slots are in flight together, level by level;
+//   store(slot, record) -> shared memory, predicated on slot < n_staged.
+constexpr int kStageUnroll = 3;   // 3 x 128 slots cover a lattice tile (4 x 11 cells x 6.8 entries ~ 300) in one pass
+
+// entry behind a slot: the segment offsets are non-decreasing (an empty segment shares the offset of its
+// successor), so the segment of `slot` is the LAST one whose offset is <= slot
+__device__ __forceinline__ int tile_entry_of_slot(const TileDesc &T, int slot)
+{
+    int k = 0;
+#pragma unroll
+    for (int j = 1; j < kStageRows * 3; ++j) k += (T.seg[j].off <= slot) ? 1 : 0;
+    return T.seg[k].b + (slot - T.seg[k].off);
+}
+
+template <class Load, class Store>
+__device__ __forceinline__ void tile_stage_flat(const TileDesc &T, Load &&load, Store &&store)
+{
+    const int n = T.n_staged;
+    if (n <= 0) return;
+    for (int base = 0; base < n; base += kStageUnroll * (int)blockDim.x) {
+        int slot[kStageUnroll];
+        decltype(load(0)) rec[kStageUnroll];
+#pragma unroll
+        for (int u = 0; u < kStageUnroll; ++u) {
+            slot[u] = base + u * (int)blockDim.x + (int)threadIdx.x;
+            rec[u] = load(tile_entry_of_slot(T, min(slot[u], n - 1)));
+        }
+#pragma unroll
+        for (int u = 0; u < kStageUnroll; ++u)
+            if (slot[u] < n) store(slot[u], rec[u]);
+    }
+}
+#endif
+
 // Own entries of a tile as one virtual index range: v in [0, own total) -> own row, entry, slot.
 __device__ __forceinline__ int tile_own_total(const TileDesc &T)
 {
