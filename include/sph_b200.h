@@ -205,6 +205,13 @@ SPHB_API int sphb_ctx_status(sphb_ctx *ctx, sphb_status *out);
  * asynchronous: call sphb_ctx_status()/download to synchronise.
  */
 SPHB_API int sphb_ctx_step(sphb_ctx *ctx, double remain);
+/*
+ * One reference step for a caller that keeps the state on the host between steps (sphb_ctx_upload -> this ->
+ * sphb_ctx_download; what the MEX drop-in does per pass of m:251-283): list build for the uploaded positions
+ * (skipped when the context still holds a valid list), wall-shear monitor, then the physics m:254-270.  The list is
+ * not rebuilt for the new positions (the next upload would discard it); asynchronous like sphb_ctx_step.
+ */
+SPHB_API int sphb_ctx_step_uploaded(sphb_ctx *ctx, double remain);
 /* Reference schedule until t >= t_target - 1e-12 (m:250) or max_steps; returns steps done. */
 SPHB_API int sphb_ctx_run_until(sphb_ctx *ctx, double t_target, double t_end, long long max_steps,
                                 long long *steps_done);

@@ -423,6 +423,11 @@ class Channel:
     def step(self, remain: float = float("inf")):
         _check(lib().sphb_ctx_step(self._ctx, C.c_double(remain)))
 
+    def step_uploaded(self, remain: float = float("inf")):
+        """One reference step on freshly uploaded state: list (if stale) + shear monitor + physics; no trailing
+        list rebuild (sphb_ctx_step_uploaded)."""
+        _check(lib().sphb_ctx_step_uploaded(self._ctx, C.c_double(remain)))
+
     def run_until(self, t_target: float, t_end: float, max_steps: int = 0) -> int:
         n = C.c_longlong(0)
         _check(lib().sphb_ctx_run_until(self._ctx, C.c_double(t_target), C.c_double(t_end), C.c_longlong(max_steps),

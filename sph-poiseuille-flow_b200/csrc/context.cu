@@ -609,6 +609,19 @@ SPHB_API int sphb_ctx_step(sphb_ctx *c, double remain)
     return 0;
 }
 
+// One reference step for a caller that keeps the state on the HOST between steps (upload -> this -> download, the
+// calling pattern of the MEX drop-in): the list for the uploaded positions (m:280, the search that closed the
+// caller's previous step), the wall-shear monitor on it (m:281-283), then the physics m:254-270.  Unlike
+// sphb_ctx_step it does not rebuild the list for the NEW positions: the next upload would discard it.
+SPHB_API int sphb_ctx_step_uploaded(sphb_ctx *c, double remain)
+{
+    CTX_ENTER(false);
+    if (!c->planned) return set_error("SPHB:state", "upload positions first");
+    if (!c->have_list) SPHB_TRY(do_neighbor(c));
+    SPHB_TRY(do_shear(c));
+    return ctx_step_physics(c, remain);
+}
+
 namespace {
 
 // clock, dt and flags only (one small D2H, no kernel): the per-step read-back of sphb_ctx_run_until

@@ -1,0 +1,72 @@
+"""sphb_ctx_step_uploaded (one reference step for a caller whose state lives on the host: list for the uploaded
+positions + shear monitor + physics, no trailing list rebuild) against the oracle and against sphb_ctx_step.
+
+Written after the GPU budget of round 1 was spent (the entry point composes calls the other GPU tests cover);
+the file sorts late so that a surprise here cannot mask the rest of the `-m gpu` run.
+"""
+import numpy as np
+import pytest
+
+from parity_util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("pos", "vel", "rho", "p", "drho_dt", "force", "force_prior", "Vol", "B")
+
+
+def _channel(sphb, prm, st):
+    ch = sphb.channel_from_oracle_params(prm, st.n_fluid, st.n_total, sort_interval=0)
+    ch.upload(pos=st.pos, vel=st.vel, rho=st.rho, drho_dt=st.drho_dt, mass=st.mass, wall_vel=st.wall_vel)
+    return ch
+
+
+def test_step_uploaded_is_the_physics_of_a_step(sphb, H, oracle_be):
+    """Three passes of upload -> step_uploaded -> download (state through host arrays every time) give the fields
+    of three sphb_ctx_step calls on a resident context to the bit; the first pass is also held against the oracle."""
+    prm = H.derive_params(dp=0.05, c_f=15.0)
+    st = H.developed_state(prm, seed=77)
+    ref = st.copy()
+    H.initialise(oracle_be, ref, prm)
+
+    a = _channel(sphb, prm, st)          # resident: reference steps on the device
+    a.initialise()
+    b = _channel(sphb, prm, st)          # host-state chain
+    b.initialise()
+    for k in range(3):
+        a.step()
+        d = b.download(("pos", "vel", "rho", "drho_dt"))
+        b.upload(pos=d["pos"], vel=d["vel"], rho=d["rho"], drho_dt=d["drho_dt"])
+        b.step_uploaded()
+        if k == 0:                       # one step against the oracle, at the one-step tolerance
+            H.reference_step(oracle_be, ref, prm)
+            d1 = b.download()
+            for f in FIELDS:
+                assert_close(d1[f], getattr(ref, f), f)
+    da, db = a.download(), b.download()
+    for f in FIELDS:
+        assert np.array_equal(da[f], db[f]), f
+    sa, sb = a.status(), b.status()
+    assert sa["t"] == sb["t"] and sa["dt"] == sb["dt"] and sb["error_flags"] == 0
+    a.close()
+    b.close()
+
+
+def test_step_uploaded_keeps_a_valid_list(sphb, H):
+    """With a list already built for the resident positions the call does not build another one (same launch
+    count as shear + physics), and it refuses to run before any upload."""
+    prm = H.derive_params(dp=0.05, c_f=15.0)
+    st = H.developed_state(prm, seed=78)
+    ch = _channel(sphb, prm, st)
+    ch.initialise()
+    l0 = ch.timing()["launches"]
+    ch.step_uploaded()
+    ch.sync()
+    with_list = ch.timing()["launches"] - l0
+    d = ch.download(("pos",))
+    ch.upload(pos=d["pos"])               # invalidates the list
+    l1 = ch.timing()["launches"]
+    ch.step_uploaded()
+    ch.sync()
+    assert ch.timing()["launches"] - l1 > with_list
+    assert ch.status()["error_flags"] == 0
+    ch.close()
