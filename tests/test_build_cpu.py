@@ -1,0 +1,67 @@
+"""CPU-only checks of the built device code (cuobjdump on libsph_b200.so; nothing is executed): the library holds
+sm_100a code only, every kernel of the step exists in its single-channel and its batched form, and the register /
+stack budgets the occupancy reasoning of DESIGN.md 3 relies on still hold (a regression here is a silent
+slow-down on the GPU, which this container cannot measure)."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+LIB = os.path.join(ROOT, "sph-poiseuille-flow_b200", "libsph_b200.so")
+
+
+def _res_usage():
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    if not os.path.exists(LIB):
+        import __graft_entry__ as ge
+        ge.build()
+    out = subprocess.run([exe, "-res-usage", LIB], capture_output=True, text=True, check=True).stdout
+    archs = set(re.findall(r"arch = (\S+)", out))
+    kernels = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", out):
+        name = m.group(1)
+        short = re.search(r"\d+((?:k_|scan_)\w+?)(?:I[A-Za-z0-9_]*?E{1,3}v|E)(?=N|P|i|d|m|v)", name)
+        key = short.group(1) if short else name
+        rec = dict(reg=int(m.group(2)), stack=int(m.group(3)), shared=int(m.group(4)), local=int(m.group(5)))
+        kernels.setdefault(key, []).append(rec)
+    return archs, kernels
+
+
+def test_library_is_sm_100a_only_and_holds_every_step_kernel():
+    archs, k = _res_usage()
+    assert archs == {"sm_100a"}, archs
+    step = ["k_yrange_grid", "k_bin_count", "scan_tiles", "scan_finish", "k_scatter", "k_cell_canon", "k_tile_setup",
+            "k_walk_tile", "k_density", "k_kgc", "k_force_fused", "k_publish_dt", "k_continuity", "k_time_step",
+            "k_pressure", "k_wall_shear", "k_wall_shear_final"]
+    for name in step:
+        assert name in k, f"{name} missing from libsph_b200.so"
+        assert name + "_batch" in k, f"{name}_batch missing from libsph_b200.so"
+    assert "k_zero_cells_batch" in k
+    # MEX-path (pair list) operators and the slab kernels
+    for name in ("k_dens_sigma", "k_visc_pairs", "k_transp_pairs", "k_int1_pairs", "k_int2_pairs", "k_shear_pairs",
+                 "k_export_pairs", "k_slab_scatter", "k_slab_unpack"):
+        assert name in k, name
+
+
+def test_gather_kernels_keep_their_register_budget_and_do_not_spill():
+    """128 threads per CTA: <= 128 registers keeps 4 CTAs of the fused force kernel resident per SM, <= 80 keeps 6
+    of the continuity / KGC / density kernels; none of them may use local memory."""
+    _, k = _res_usage()
+    budget = {"k_force_fused": 128, "k_continuity": 80, "k_kgc": 80, "k_density": 80, "k_wall_shear": 96,
+              "k_pressure": 128}
+    for name, regs in budget.items():
+        for rec in k[name]:
+            assert rec["reg"] <= regs, (name, rec)
+            assert rec["stack"] == 0 and rec["local"] == 0, (name, rec)
+    for rec in k["k_force_fused_batch"] + k["k_continuity_batch"] + k["k_kgc_batch"] + k["k_density_batch"]:
+        assert rec["stack"] == 0 and rec["local"] == 0, rec
+    # the walk is capped at 80 registers for 6 resident CTAs (__launch_bounds__(128, 6)); a few spilled words are
+    # the known price, more than that is a regression
+    for rec in k["k_walk_tile"] + k["k_walk_tile_batch"]:
+        assert rec["reg"] <= 80 and rec["stack"] <= 64, rec
