@@ -129,7 +129,7 @@ constexpr int kStageUnroll = 3;   // 3 x 128 slots cover a lattice tile (4 x 11 
 
 // entry behind a slot: the segment offsets are non-decreasing (an empty segment shares the offset of its
 // successor), so the segment of `slot` is the LAST one whose offset is <= slot
-__device__ __forceinline__ int tile_entry_of_slot(const TileDesc &T, int slot)
+__host__ __device__ __forceinline__ int tile_entry_of_slot(const TileDesc &T, int slot)
 {
     int k = 0;
 #pragma unroll
