@@ -70,6 +70,11 @@ def load_product():
     mod = importlib.util.module_from_spec(spec)
     sys.modules[name] = mod
     spec.loader.exec_module(mod)
+    # Test infrastructure only: SPHB_CPUSIM_LIB points the ctypes mirror at the CPU functional simulator build of
+    # the same sources (tests/cpusim, driven by tests/test_cpusim.py).  The product itself knows no such switch.
+    sim = os.environ.get("SPHB_CPUSIM_LIB")
+    if sim:
+        mod.LIB_PATH = sim
     return mod
 
 
