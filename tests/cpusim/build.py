@@ -111,7 +111,7 @@ def build(force: bool = False, defines=()) -> str:
     os.makedirs(src_out, exist_ok=True)
     os.makedirs(inc_out, exist_ok=True)
     stamp = os.path.join(OUT, "flags.txt")
-    flags = " ".join(defines)
+    flags = " ".join(list(defines) + (["asan"] if os.environ.get("CPUSIM_ASAN") else []))
     if not os.path.exists(stamp) or open(stamp).read() != flags:
         force = True
     newest = 0.0
@@ -129,9 +129,10 @@ def build(force: bool = False, defines=()) -> str:
     open(os.path.join(inc_out, "sph_b200.h"), "w").write(open(hdr).read())
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
         return LIB
+    san = ["-fsanitize=address", "-fno-omit-frame-pointer"] if os.environ.get("CPUSIM_ASAN") else []
     common = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-fvisibility=hidden", "-fno-ipa-reference", "-fno-ipa-pure-const",
               "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-attributes", "-x", "c++",
-              f"-I{os.path.join(HERE, 'include')}"] + list(defines)
+              f"-I{os.path.join(HERE, 'include')}"] + san + list(defines)
     objs, procs = [], []
     for unit, extra in UNITS.items():
         obj = os.path.join(OUT, unit.replace(".cu", ".o"))
@@ -149,7 +150,7 @@ def build(force: bool = False, defines=()) -> str:
             sys.stderr.write(f"--- {name}\n{log[:6000]}\n")
     if failed:
         raise RuntimeError("cpusim build failed")
-    subprocess.run(["g++", "-shared", "-o", LIB] + objs + [rt, "-lm"], check=True)
+    subprocess.run(["g++", "-shared", "-o", LIB] + san + objs + [rt, "-lm"], check=True)
     open(stamp, "w").write(flags)
     return LIB
 

@@ -1,0 +1,50 @@
+"""Runs the GPU test files against the CPU FUNCTIONAL SIMULATOR build of the same CUDA sources (tests/cpusim).
+
+Test infrastructure, not parity evidence: the simulator executes the kernel bodies and the host logic of
+libsph_b200 on the CPU (one ucontext fiber per CUDA thread, barriers at __syncthreads / *_sync, graphs as recorded
+closures), which catches logic errors, bad indexing and broken host orchestration in code written without a GPU at
+hand -- e.g. the batched ensemble launches and the flat staging build -- before GPU minutes are spent on them.  It
+cannot see races, memory-model or alignment problems, and it measures nothing.  Parity is claimed from
+`pytest -m gpu` on a B200 only.  The product never loads this library (SPHB_CPUSIM_LIB is read by tests/conftest.py).
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+FAST = ("not full_size and not ensemble_equals and not reference_loop and not golden_trajectory and not mex_shims")
+
+
+def _run(lib, files, k=None, env_extra=None, timeout=1500):
+    env = dict(os.environ, SPHB_CPUSIM_LIB=lib, OMP_NUM_THREADS="1", **(env_extra or {}))
+    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + files
+    if k:
+        cmd += ["-k", k]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
+    assert r.returncode == 0, tail
+    return tail
+
+
+@pytest.fixture(scope="module")
+def simlib():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "cpusim"))
+    import build as simbuild
+    return simbuild.build()
+
+
+def test_new_entry_points_on_the_simulator(simlib):
+    """Batched ensemble launches (bit identity with the single-channel schedule, across cell sorts, n_inner 1 and 3)
+    and sphb_ctx_step_uploaded."""
+    out = _run(simlib, ["tests/test_gpu_zz_batch.py", "tests/test_gpu_zy_step_uploaded.py"])
+    assert " passed" in out and "skipped" not in out.splitlines()[-1], out
+
+
+def test_parity_suite_subset_on_the_simulator(simlib):
+    """The quick part of the device-resident and MEX-path parity tests (bit-exact neighbour lists, 1e-11 fields):
+    guards the simulator itself and, with it, every later kernel change made without a GPU."""
+    out = _run(simlib, ["tests/test_gpu_context.py", "tests/test_gpu_mex_path.py"], k=FAST)
+    assert " passed" in out, out

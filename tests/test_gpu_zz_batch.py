@@ -1,23 +1,19 @@
 """Batched ensemble launches (sphb_batch_*, csrc/batch.cu) against the same channels stepped one by one.
 
-STATUS: written and compiled for sm_100a after the GPU budget of round 1 was spent -- NOT YET RUN ON A GPU.
-The tests are therefore opt-in (SPHB_TEST_BATCH=1) so that an unverified path cannot fail or hang the round-end
-`pytest -m gpu` run; the first GPU call of the next round is
-    SPHB_TEST_BATCH=1 timeout 300 python -m pytest tests/test_gpu_zz_batch.py -x -q -m gpu
-and the switch is removed once they are green.  The file sorts last on purpose.
+STATUS: written after the GPU budget of round 1 was spent.  The tests pass on the CPU functional simulator build of
+the same sources (tests/cpusim, run by tests/test_cpusim.py; also under AddressSanitizer) -- kernel bodies, record
+plumbing and host schedule are exercised there -- but have NOT yet run on a GPU, and no performance number is
+claimed for the batched path.  The file sorts last so that a surprise on the hardware cannot mask the other tests.
 
 The batch kernels call the very __device__ bodies of the single-channel kernels with per-channel arguments read
 from device records, so the expected result is BIT identity with Channel.run_dual, channel by channel.
 """
 import importlib
-import os
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SPHB_TEST_BATCH") != "1",
-                                 reason="batched ensemble path not yet verified on a GPU (set SPHB_TEST_BATCH=1)")]
+pytestmark = [pytest.mark.gpu]
 
 FIELDS = ("pos", "vel", "rho", "p", "drho_dt", "force", "force_prior", "Vol", "B")
 

@@ -6,7 +6,7 @@
 # Everything lands in gpurun_out/r2_first/ (one log / JSON line per step); a failing step does not stop the rest,
 # and every step runs under its own `timeout` so that an unverified path cannot hang the box.
 #   1. the default build: GPU parity tests + the N = 1 bench line (baseline of the round)
-#   2. batched ensemble launches (csrc/batch.cu): opt-in parity tests, then per-channel graphs vs --batched
+#   2. batched ensemble launches (csrc/batch.cu): parity tests, then per-channel graphs vs --batched
 #   3. flat staging (SPHB_FLAT_STAGING=1 build): GPU parity tests + bench line, then the default build is restored
 set -u
 cd "$(dirname "$0")/.."
@@ -24,7 +24,7 @@ step() {   # step <name> <seconds> <command...>
 step 1_tests_default 900 python -m pytest tests -x -q -m gpu
 step 1_bench_default 600 python bench.py --steps 20 --warmup 3
 
-step 2_batch_tests 600 env SPHB_TEST_BATCH=1 python -m pytest tests/test_gpu_zz_batch.py -x -q -m gpu
+step 2_batch_tests 600 python -m pytest tests/test_gpu_zz_batch.py -x -q -m gpu
 if grep -q " passed" "$OUT/2_batch_tests.out" && ! grep -q "failed\|error" "$OUT/2_batch_tests.out"; then
     step 2_ens256_graphs 600 python bench.py --mode ensemble --channels 256 --steps 20 --warmup 3
     step 2_ens256_batched 600 python bench.py --mode ensemble --channels 256 --steps 20 --warmup 3 --batched
