@@ -132,7 +132,9 @@ constexpr int kStageUnroll = 3;   // 3 x 128 slots cover a lattice tile (4 x 11 
 __host__ __device__ __forceinline__ int tile_entry_of_slot(const TileDesc &T, int slot)
 {
     int k = 0;
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for (int j = 1; j < kStageRows * 3; ++j) k += (T.seg[j].off <= slot) ? 1 : 0;
     return T.seg[k].b + (slot - T.seg[k].off);
 }
