@@ -22,6 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "sph-poiseuille-flow_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libsph_b200_cpusim.so")
+DRIVER = os.path.join(OUT, "sph_poiseuille_cpusim")
 UNITS = {"misc.cu": [], "scan.cu": [], "neighbor.cu": ["-ffp-contract=off"], "sort.cu": ["-ffp-contract=off"],
          "ops_pairs.cu": [], "ops_csr.cu": [], "context.cu": [], "batch.cu": [], "api.cu": []}
 
@@ -151,6 +152,10 @@ def build(force: bool = False, defines=()) -> str:
     if failed:
         raise RuntimeError("cpusim build failed")
     subprocess.run(["g++", "-shared", "-o", LIB] + san + objs + [rt, "-lm"], check=True)
+    # the standalone C driver against the simulator library (tests/test_driver.py through SPHB_CPUSIM_DRIVER)
+    drv = os.path.join(ROOT, "sph-poiseuille-flow_b200", "driver", "sph_poiseuille_main.c")
+    subprocess.run(["gcc", "-O2", f"-I{os.path.join(ROOT, 'include')}", drv, "-o", DRIVER, f"-L{OUT}",
+                    "-lsph_b200_cpusim", "-Wl,-rpath,$ORIGIN", "-lm"] + san, check=True)
     open(stamp, "w").write(flags)
     return LIB
 

@@ -19,7 +19,8 @@ FAST = ("not full_size and not ensemble_equals and not reference_loop and not go
 
 
 def _run(lib, files, k=None, env_extra=None, timeout=1500):
-    env = dict(os.environ, SPHB_CPUSIM_LIB=lib, OMP_NUM_THREADS="1", **(env_extra or {}))
+    env = dict(os.environ, SPHB_CPUSIM_LIB=lib, OMP_NUM_THREADS="1",
+               SPHB_CPUSIM_DRIVER=os.path.join(os.path.dirname(lib), "sph_poiseuille_cpusim"), **(env_extra or {}))
     cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + files
     if k:
         cmd += ["-k", k]
@@ -41,6 +42,13 @@ def test_new_entry_points_on_the_simulator(simlib):
     and sphb_ctx_step_uploaded."""
     out = _run(simlib, ["tests/test_gpu_zz_batch.py", "tests/test_gpu_zy_step_uploaded.py"])
     assert " passed" in out and "skipped" not in out.splitlines()[-1], out
+
+
+def test_standalone_driver_on_the_simulator(simlib):
+    """config.ini -> 120 main-loop steps -> log lines, profile CSV, restart round trip (tests/test_driver.py) with the
+    C driver linked against the simulator library."""
+    out = _run(simlib, ["tests/test_driver.py"])
+    assert " passed" in out, out
 
 
 def test_parity_suite_subset_on_the_simulator(simlib):

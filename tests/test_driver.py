@@ -32,6 +32,9 @@ restart_from_file = {restart}
 
 
 def _driver():
+    sim = os.environ.get("SPHB_CPUSIM_DRIVER")   # test infrastructure: the driver linked against tests/cpusim
+    if sim:
+        return sim
     if not os.path.exists(DRIVER):
         import __graft_entry__ as ge
         ge.build()
