@@ -125,9 +125,26 @@ void run_cta(const std::function<void()> &body, int n_threads)
         f.ctx.uc_link = nullptr;
         makecontext(&f.ctx, trampoline, 0);
     }
+    // Scheduling order of the fibers: CPUSIM_SCHEDULE = forward (default) | reverse | random.  Correct CUDA code
+    // gives the same results under every order; code that leans on an implicit order between barriers does not.
+    static const int mode = []() {
+        const char *m = std::getenv("CPUSIM_SCHEDULE");
+        return !m ? 0 : (m[0] == 'r' && m[1] == 'e') ? 1 : (m[0] == 'r' && m[1] == 'a') ? 2 : 0;
+    }();
+    static int order[kMaxThreads];
+    static unsigned long long rng = 0x2545F4914F6CDD1Dull;
+    for (int t = 0; t < n_threads; ++t) order[t] = mode == 1 ? n_threads - 1 - t : t;
     while (E.live > 0) {
         E.progress = false;
-        for (int t = 0; t < n_threads; ++t) {
+        if (mode == 2)
+            for (int t = n_threads - 1; t > 0; --t) {   // a fresh shuffle every round
+                rng ^= rng << 13;
+                rng ^= rng >> 7;
+                rng ^= rng << 17;
+                std::swap(order[t], order[rng % (unsigned)(t + 1)]);
+            }
+        for (int k = 0; k < n_threads; ++k) {
+            const int t = order[k];
             Fiber &f = E.fib[t];
             if (f.done) continue;
             if (f.waiting_cta && f.cta_gen == E.gen) continue;

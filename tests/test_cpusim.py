@@ -53,6 +53,9 @@ def test_standalone_driver_on_the_simulator(simlib):
 
 def test_parity_suite_subset_on_the_simulator(simlib):
     """The quick part of the device-resident and MEX-path parity tests (bit-exact neighbour lists, 1e-11 fields):
-    guards the simulator itself and, with it, every later kernel change made without a GPU."""
-    out = _run(simlib, ["tests/test_gpu_context.py", "tests/test_gpu_mex_path.py"], k=FAST)
+    guards the simulator itself and, with it, every later kernel change made without a GPU.  The fibers of a CTA are
+    scheduled in a freshly shuffled order every round (CPUSIM_SCHEDULE=random): code that leans on an implicit
+    order of threads between barriers would lose the bit-exact list parity here."""
+    out = _run(simlib, ["tests/test_gpu_context.py", "tests/test_gpu_mex_path.py"], k=FAST,
+               env_extra={"CPUSIM_SCHEDULE": "random"})
     assert " passed" in out, out
