@@ -236,7 +236,7 @@ __device__ __forceinline__ void density_tile(PhysParams P, StateView S)
 #undef SPHB_CALL
 }
 __global__ void __launch_bounds__(kTileThreads) k_density(PhysParams P, StateView S) { density_tile(P, S); }
-__global__ void __launch_bounds__(kTileThreads) k_density_batch(const BatchChan *__restrict__ chan)
+__global__ void __launch_bounds__(kTileThreads, 9) k_density_batch(const BatchChan *__restrict__ chan)
 {
     const BatchChan &c = chan[blockIdx.y];
     density_tile(c.P, c.S);
@@ -313,7 +313,7 @@ __device__ __forceinline__ void kgc_tile(PhysParams P, StateView S)
 #undef SPHB_CALL
 }
 __global__ void __launch_bounds__(kTileThreads) k_kgc(PhysParams P, StateView S) { kgc_tile(P, S); }
-__global__ void __launch_bounds__(kTileThreads) k_kgc_batch(const BatchChan *__restrict__ chan)
+__global__ void __launch_bounds__(kTileThreads, 8) k_kgc_batch(const BatchChan *__restrict__ chan)
 {
     const BatchChan &c = chan[blockIdx.y];
     kgc_tile(c.P, c.S);
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(kTileThreads) k_pressure(PhysParams P, StateVi
 {
     pressure_tile(P, S, sc);
 }
-__global__ void __launch_bounds__(kTileThreads) k_pressure_batch(const BatchChan *__restrict__ chan)
+__global__ void __launch_bounds__(kTileThreads, 5) k_pressure_batch(const BatchChan *__restrict__ chan)
 {
     const BatchChan &c = chan[blockIdx.y];
     pressure_tile(c.P, c.S, c.sc);
@@ -991,7 +991,7 @@ __global__ void __launch_bounds__(kTileThreads) k_continuity(PhysParams P, State
 {
     continuity_tile(P, S, sc, do_wrap, advance_clock);
 }
-__global__ void __launch_bounds__(kTileThreads) k_continuity_batch(const BatchChan *__restrict__ chan, int do_wrap,
+__global__ void __launch_bounds__(kTileThreads, 7) k_continuity_batch(const BatchChan *__restrict__ chan, int do_wrap,
                                                                   int advance_clock)
 {
     const BatchChan &c = chan[blockIdx.y];
@@ -1105,7 +1105,7 @@ __global__ void __launch_bounds__(kTileThreads) k_wall_shear(PhysParams P, State
 {
     wall_shear_tile(P, S, partials);
 }
-__global__ void __launch_bounds__(kTileThreads) k_wall_shear_batch(const BatchChan *__restrict__ chan)
+__global__ void __launch_bounds__(kTileThreads, 6) k_wall_shear_batch(const BatchChan *__restrict__ chan)
 {
     const BatchChan &c = chan[blockIdx.y];
     wall_shear_tile(c.P, c.S, c.shear_partials);

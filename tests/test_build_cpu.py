@@ -59,8 +59,12 @@ def test_gather_kernels_keep_their_register_budget_and_do_not_spill():
         for rec in k[name]:
             assert rec["reg"] <= regs, (name, rec)
             assert rec["stack"] == 0 and rec["local"] == 0, (name, rec)
-    for rec in k["k_force_fused_batch"] + k["k_continuity_batch"] + k["k_kgc_batch"] + k["k_density_batch"]:
-        assert rec["stack"] == 0 and rec["local"] == 0, rec
+    # the batched forms read their arguments from a device record instead of the constant bank: __launch_bounds__
+    # holds them at the single-channel register counts (same occupancy) at the price of a few spilled words
+    for name, regs in {"k_force_fused_batch": 128, "k_continuity_batch": 72, "k_kgc_batch": 64, "k_density_batch": 56,
+                       "k_pressure_batch": 96, "k_wall_shear_batch": 80}.items():
+        for rec in k[name]:
+            assert rec["reg"] <= regs and rec["stack"] <= 32 and rec["local"] == 0, (name, rec)
     # the walk is capped at 80 registers for 6 resident CTAs (__launch_bounds__(128, 6)); a few spilled words are
     # the known price, more than that is a regression
     for rec in k["k_walk_tile"] + k["k_walk_tile_batch"]:
