@@ -75,6 +75,17 @@ def load_product():
     sim = os.environ.get("SPHB_CPUSIM_LIB")
     if sim:
         mod.LIB_PATH = sim
+        # "device" memory of the simulator is host memory: the single-process slab group keeps its exchange
+        # buffers in CPU tensors there
+        import torch
+        slab = importlib.import_module(name + ".slab")
+        group_init = slab.SlabGroup.__init__
+
+        def init_on_cpu(self, cfg, pt, n_slabs, device="cpu", **kw):
+            group_init(self, cfg, pt, n_slabs, device="cpu", **kw)
+
+        slab.SlabGroup.__init__ = init_on_cpu
+        torch.cuda.synchronize = lambda *a, **k: None
     return mod
 
 

@@ -24,7 +24,7 @@ OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libsph_b200_cpusim.so")
 DRIVER = os.path.join(OUT, "sph_poiseuille_cpusim")
 UNITS = {"misc.cu": [], "scan.cu": [], "neighbor.cu": ["-ffp-contract=off"], "sort.cu": ["-ffp-contract=off"],
-         "ops_pairs.cu": [], "ops_csr.cu": [], "context.cu": [], "batch.cu": [], "api.cu": []}
+         "ops_pairs.cu": [], "ops_csr.cu": [], "context.cu": [], "slab.cu": [], "batch.cu": [], "api.cu": []}
 
 
 def _matching(text: str, start: int, open_ch: str, close_ch: str) -> int:
