@@ -51,6 +51,14 @@ def test_standalone_driver_on_the_simulator(simlib):
     assert " passed" in out, out
 
 
+def test_slab_group_on_the_simulator(simlib):
+    """Two x-slabs of one channel (pack / exchange / unpack / migration kernels of csrc/slab.cu, exchange buffers in
+    CPU tensors) against the single-domain run: identical neighbour sets, fields within 1e-11.  The three-slab and
+    the seam-migration cases of tests/test_gpu_slab.py pass too but take minutes on the simulator."""
+    out = _run(simlib, ["tests/test_gpu_slab.py"], k="2-0.02")
+    assert " passed" in out, out
+
+
 def test_parity_suite_subset_on_the_simulator(simlib):
     """The quick part of the device-resident and MEX-path parity tests (bit-exact neighbour lists, 1e-11 fields):
     guards the simulator itself and, with it, every later kernel change made without a GPU.  The fibers of a CTA are
