@@ -99,7 +99,11 @@ struct GridDesc {
     int n_entries;     // real + ghost entries
     long long ymin_key, ymax_key;   // ordered-integer images used by the atomic min/max reduction
     unsigned int ticket;            // CTAs of the y-range reduction that have finished
-    unsigned int pad;
+    // Set by the binning of a build when a periodic ghost entry or its owner lies outside the columns the fast
+    // walk takes for granted (ghosts in column ncx-1, owners in columns 0, ncx-2, ncx-1): exact multiples of the
+    // cell size can round floor((x_w +- DL) / cell) one column further (nb:284-294).  Every tile of such a build
+    // is a seam tile and every walker takes the general walk.
+    unsigned int ghost_anomaly;
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -127,6 +127,7 @@ __global__ void k_grid_init(GridDesc *g)
     g->ymax_key = LLONG_MIN;
     g->n_entries = 0;
     g->ticket = 0u;
+    g->ghost_anomaly = 0u;
 }
 
 // y range over ALL particles (nb:245-250); the last CTA to finish derives the grid (nb:253-258), re-arms
@@ -185,6 +186,7 @@ __device__ __forceinline__ void yrange_grid_body(const double2 *__restrict__ pos
     g->ymin_key = LLONG_MAX;   // re-armed for the next build
     g->ymax_key = LLONG_MIN;
     g->ticket = 0u;
+    g->ghost_anomaly = 0u;     // raised again by this build's binning if need be
     for (int k = 0; k < 8; ++k) totals[k] = 0;
 }
 __global__ void __launch_bounds__(256) k_yrange_grid(const double2 *__restrict__ pos, int n, GridDesc *g, NbrParams P,
@@ -251,12 +253,18 @@ __device__ __forceinline__ Bins bin_particle(double2 p, const NbrParams &P, doub
 
 __device__ __forceinline__ void bin_count_body(const double2 *__restrict__ pos, NbrParams P, const GridDesc *__restrict__ g,
                                                double2 *__restrict__ snap, int *__restrict__ cell_of,
-                                               int *__restrict__ cell_cnt)
+                                               int *__restrict__ cell_cnt, unsigned int *ghost_anomaly)
 {
     load_counts(P);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_total || row_dead(P, i)) return;
     const Bins b = bin_particle(pos[i], P, g->y_min, g->ncy);
+    if (b.gcx_lo >= 0 || b.gcx_hi >= 0) {   // see GridDesc::ghost_anomaly
+        const int last = P.ncx - 1;
+        const bool ghosts_ok = (b.gcx_lo < 0 || b.gcx_lo == last) && (b.gcx_hi < 0 || b.gcx_hi == last);
+        const bool owner_ok = b.cx == 0 || b.cx >= P.ncx - 2;
+        if (!(ghosts_ok && owner_ok)) *ghost_anomaly = 1u;
+    }
     snap[i] = make_double2(b.xw, b.y);
     const int row = b.cy * P.ncx;
     cell_of[i] = row + b.cx;
@@ -266,14 +274,15 @@ __device__ __forceinline__ void bin_count_body(const double2 *__restrict__ pos, 
 }
 __global__ void __launch_bounds__(kBlock) k_bin_count(const double2 *__restrict__ pos, NbrParams P,
                                                      const GridDesc *__restrict__ g, double2 *__restrict__ snap,
-                                                     int *__restrict__ cell_of, int *__restrict__ cell_cnt)
+                                                     int *__restrict__ cell_of, int *__restrict__ cell_cnt,
+                                                     unsigned int *ghost_anomaly)
 {
-    bin_count_body(pos, P, g, snap, cell_of, cell_cnt);
+    bin_count_body(pos, P, g, snap, cell_of, cell_cnt, ghost_anomaly);
 }
 __global__ void __launch_bounds__(kBlock) k_bin_count_batch(const NbrChan *__restrict__ chan)
 {
     const NbrChan &c = chan[blockIdx.y];
-    bin_count_body(c.pos, c.P, c.g, c.snap, c.cell_of, c.cell_cnt);
+    bin_count_body(c.pos, c.P, c.g, c.snap, c.cell_of, c.cell_cnt, &c.g->ghost_anomaly);
 }
 
 __device__ __forceinline__ void scatter_body(const double2 *__restrict__ pos, NbrParams P, const GridDesc *__restrict__ g,
@@ -440,7 +449,7 @@ __device__ __forceinline__ void tile_setup_body(const GridDesc *__restrict__ g, 
         // a ghost, or the periodic wrap: they take the general walk (ghosts live in column ncx-1 only and
         // their owners in columns 0, ncx-2, ncx-1; nb:282-295)
         // (a slab of a sharded channel has neither: its outermost columns are empty margins)
-        if (!slab && (cx0 < 1 || cx1 > ncx - 2 || ncx < 6)) f |= kTileSeam;
+        if (!slab && (cx0 < 1 || cx1 > ncx - 2 || ncx < 6 || g->ghost_anomaly != 0u)) f |= kTileSeam;
         if (used + 1 > cap) {   // cannot be staged (+ the dummy slot): reported, the tile is skipped by every kernel
             atomicOr(flags, kErrTileCap);
             f &= ~kTileValid;
@@ -818,6 +827,7 @@ __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__re
     const size_t stride = P.ell_stride;
     const int qcap = P.ell_cap >> 3;
     const bool seam_tile = (T.flags & kTileSeam) != 0;
+    const bool ghost_anomaly = g->ghost_anomaly != 0u;   // a ghost entry outside the usual columns: no fast walk
     const int dummy = T.n_staged;
     const int lane = threadIdx.x & 31;
     __shared__ int gq[kTileThreads];   // own-entry indices of the queued general walkers
@@ -850,7 +860,7 @@ __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__re
                     }
                     cxi = T.a + lo;
                 }
-                const bool interior = cxi >= 1 && cxi <= ncx - 3 && ncx >= 6;
+                const bool interior = cxi >= 1 && cxi <= ncx - 3 && ncx >= 6 && !ghost_anomaly;
                 if (!seam_tile && !interior) {   // slab mode: a particle clamped into the empty margin columns
                     cnt[ew] = 0;
                 } else if (!interior) {
@@ -1294,7 +1304,8 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
     }
     {
         ProfScope ps(prof, kPfNbrBin, st);
-        k_bin_count<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.snap.as<double2>(), w.cell_of.as<int>(), cell_cnt);
+        k_bin_count<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.snap.as<double2>(), w.cell_of.as<int>(), cell_cnt,
+                                                     &g->ghost_anomaly);
     }
     nl += 2;
     {
