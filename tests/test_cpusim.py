@@ -42,7 +42,7 @@ def test_new_entry_points_on_the_simulator(simlib):
     sphb_ctx_step_uploaded, and the seeded fuzz of the neighbour search (which found, on the simulator, the ghost
     entry that exact multiples of the cell size round one column further: GridDesc::ghost_anomaly)."""
     out = _run(simlib, ["tests/test_gpu_zz_batch.py", "tests/test_gpu_zy_step_uploaded.py",
-                        "tests/test_gpu_zx_neighbor_fuzz.py"])
+                        "tests/test_gpu_zx_neighbor_fuzz.py", "tests/test_gpu_zw_step_fuzz.py"])
     assert " passed" in out and "skipped" not in out.splitlines()[-1], out
 
 

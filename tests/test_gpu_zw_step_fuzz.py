@@ -1,0 +1,79 @@
+"""Seeded fuzz of the device-resident step and of the device cell sort against the oracle: small channels with
+random length (down to four cell columns, where every tile is a seam tile), height, resolution, viscosity, jitter
+and cell-sort cadence.  Pair counts and time steps must be the reference's, fields within the one-step tolerance
+after every one of four steps; the sorted row order must be MATLAB's sortrows order (m:529-568) also for
+coordinates on exact multiples of the cell size, on x = 0 / DL and just outside them.
+
+Also run against the CPU functional simulator by tests/test_cpusim.py (written after round 1's GPU budget was spent).
+"""
+import numpy as np
+import pytest
+
+from parity_util import TOL
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("pos", "vel", "rho", "p", "drho_dt", "force", "force_prior", "Vol", "B")
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    s = np.max(np.abs(b))
+    return float(np.max(np.abs(a.reshape(b.shape) - b)) / (s if s > 0 else 1.0))
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_step_fuzz_against_oracle(sphb, H, oracle_be, block):
+    rng = np.random.default_rng(4100 + block)
+    for case in range(5):
+        dp = float(rng.choice([0.1, 0.08, 0.0625, 0.05, 0.04]))
+        DL = float(rng.choice([0.4, 0.52, 0.7, 1.0, 1.3, 2.0, 3.0]))
+        prm = H.derive_params(DL=DL, DH=float(rng.choice([0.5, 1.0])), dp=dp, mu=float(rng.choice([0.05, 0.1, 0.2])),
+                              c_f=float(rng.choice([10.0, 15.0])), sort_interval=int(rng.choice([2, 3, 100])))
+        st = H.developed_state(prm, seed=int(rng.integers(1, 10 ** 6)), jitter=float(rng.choice([0.05, 0.2, 0.35])))
+        ref = st.copy()
+        H.initialise(oracle_be, ref, prm)
+        ch = sphb.channel_from_oracle_params(prm, st.n_fluid, st.n_total)
+        ch.upload(pos=st.pos, vel=st.vel, rho=st.rho, drho_dt=st.drho_dt, mass=st.mass, wall_vel=st.wall_vel)
+        ch.initialise()
+        what = f"block {block} case {case}: dp={dp} DL={DL} n={st.n_total}"
+        for k in range(4):
+            dt = H.reference_step(oracle_be, ref, prm)
+            ch.step()
+            s, d = ch.status(), ch.download()
+            assert s["error_flags"] == 0 and s["n_half_pairs"] == ref.pairs[0].size, (what, k)
+            assert abs(s["dt"] - dt) <= 1e-13 * dt, (what, k)
+            # the tolerance is per step; round-off carried over from earlier steps grows with the flow's own
+            # sensitivity, so later steps get the head-room the multi-step tests use
+            for f in FIELDS:
+                assert _rel(d[f], getattr(ref, f)) <= TOL * (1 if k == 0 else 10), (what, k, f)
+        ch.close()
+
+
+def test_cell_sort_fuzz_against_sortrows(sphb, H):
+    rng = np.random.default_rng(77)
+    for case in range(24):
+        dp, DL = float(rng.choice([0.1, 0.05, 0.04])), float(rng.choice([0.4, 0.52, 1.0, 1.3, 3.0]))
+        prm = H.derive_params(DL=DL, dp=dp)
+        st = H.developed_state(prm, seed=int(rng.integers(1, 10 ** 6)), jitter=float(rng.choice([0.0, 0.2, 0.4])))
+        nf, cell = st.n_fluid, 2.0 * prm.h
+        pos = st.pos.copy(order="F")
+        mode = case % 4
+        if mode == 1:      # x on multiples of the cell size
+            k = rng.random(nf) < 0.3
+            pos[:nf, 0][k] = np.round(pos[:nf, 0][k] / cell) * cell
+        elif mode == 2:    # x on and just outside the periodic seam
+            k = rng.random(nf) < 0.2
+            pos[:nf, 0][k] = rng.choice([0.0, DL, -1e-17, DL * (1 - 1e-16)], int(k.sum()))
+        elif mode == 3:    # y on multiples of the cell size above the lowest fluid particle
+            k = rng.random(nf) < 0.3
+            y0 = pos[:nf, 1].min()
+            pos[:nf, 1][k] = y0 + np.round((pos[:nf, 1][k] - y0) / cell) * cell
+        perm = H.sort_permutation(pos, nf, st.n_total, prm.DL, prm.h)
+        ch = sphb.channel_from_oracle_params(prm, nf, st.n_total)
+        ch.upload(pos=pos, vel=st.vel, rho=st.rho, drho_dt=st.drho_dt, mass=st.mass, wall_vel=st.wall_vel)
+        ch.sort_by_cell()
+        d = ch.download(("pos", "vel", "rho"))
+        ch.close()
+        assert np.array_equal(d["pos"], pos[perm]) and np.array_equal(d["vel"], st.vel[perm]), (case, mode, dp, DL)
+        assert np.array_equal(d["rho"], st.rho[perm]), (case, mode, dp, DL)
