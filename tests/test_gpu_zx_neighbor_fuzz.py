@@ -51,10 +51,10 @@ def _cloud(rng, kind, n, DL, height, h):
 KINDS = ("uniform", "clusters", "lattice", "boundaries", "seam", "threshold")
 
 
-@pytest.mark.parametrize("block", range(6))
-def test_neighbor_fuzz_bit_exact(sphb, oracle_be, block):
+def cases(block, n_cases=30):
+    """(label, pos, n_fluid, n_total, h, DL) of the seeded cases of one block."""
     rng = np.random.default_rng(9000 + block)
-    for case in range(30):
+    for case in range(n_cases):
         kind = KINDS[(block + case) % len(KINDS)]
         h = float(rng.choice([0.02, 0.05, 0.13, 0.2]))
         ncols = int(rng.integers(1, 15))
@@ -63,8 +63,13 @@ def test_neighbor_fuzz_bit_exact(sphb, oracle_be, block):
         n = int(rng.integers(2, 400))
         nf = int(rng.integers(1, n + 1))
         pos = _cloud(rng, kind, n, DL, height, h)
+        yield f"block {block} case {case} ({kind}, n={n}, nf={nf}, h={h}, DL={DL})", pos, nf, n, h, DL
+
+
+@pytest.mark.parametrize("block", range(6))
+def test_neighbor_fuzz_bit_exact(sphb, oracle_be, block):
+    for label, pos, nf, n, h, DL in cases(block):
         want = oracle_be.neighbor_search(pos, nf, n, h, DL)
         got = sphb.sph_neighbor_search_mex(pos, nf, n, h, DL)
         for k, name in enumerate(PAIR_NAMES):
-            assert np.array_equal(got[k], want[k]), (f"block {block} case {case} ({kind}, n={n}, nf={nf}, h={h}, DL={DL}, "
-                                                     f"{want[0].size} pairs): {name}")
+            assert np.array_equal(got[k], want[k]), f"{label}, {want[0].size} pairs: {name}"

@@ -118,3 +118,14 @@ def test_profile_helpers(H):
     assert H.l2_error(prm, st.pos[:nf], u) < 1e-12   # lattice rows sit on bin centres
     ym, um = H.mid_channel_profile(st.pos[:nf], u, prm.DL, prm.DH, 0.5 * prm.DL, max(prm.dp, prm.h), 20)
     assert ym.shape == (20,) and not np.isnan(um).any()
+
+
+def test_port_matches_reference_on_fuzz_clouds(port, ref):
+    """The clouds of tests/test_gpu_zx_neighbor_fuzz.py (few-column boxes, points on cell boundaries and on the seam,
+    coincident points, pairs at exactly the cut-off, unwrapped x): the plain-C port reproduces the reference build's
+    seven pair columns bit for bit, so either may serve as the checker of that GPU test."""
+    import test_gpu_zx_neighbor_fuzz as F
+    for block in range(6):
+        for label, pos, nf, n, h, DL in F.cases(block):
+            a, b = ref.neighbor_search(pos, nf, n, h, DL), port.neighbor_search(pos, nf, n, h, DL)
+            assert all(np.array_equal(x, y) for x, y in zip(a, b)), label
