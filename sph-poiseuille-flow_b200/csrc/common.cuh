@@ -101,8 +101,9 @@ struct GridDesc {
     unsigned int ticket;            // CTAs of the y-range reduction that have finished
     // Set by the binning of a build when a periodic ghost entry or its owner lies outside the columns the fast
     // walk takes for granted (ghosts in column ncx-1, owners in columns 0, ncx-2, ncx-1): exact multiples of the
-    // cell size can round floor((x_w +- DL) / cell) one column further (nb:284-294).  Every tile of such a build
-    // is a seam tile and every walker takes the general walk.
+    // cell size can round floor((x_w +- DL) / cell) one column further (nb:284-294) -- or when a wrapped x falls
+    // outside [0, DL) (nb:270-272 returns DL itself for a tiny negative x).  Every tile of such a build is a seam
+    // tile and every walker takes the general walk.
     unsigned int ghost_anomaly;
 };
 

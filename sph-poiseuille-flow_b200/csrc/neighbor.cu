@@ -259,11 +259,17 @@ __device__ __forceinline__ void bin_count_body(const double2 *__restrict__ pos, 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_total || row_dead(P, i)) return;
     const Bins b = bin_particle(pos[i], P, g->y_min, g->ncy);
-    if (b.gcx_lo >= 0 || b.gcx_hi >= 0) {   // see GridDesc::ghost_anomaly
-        const int last = P.ncx - 1;
-        const bool ghosts_ok = (b.gcx_lo < 0 || b.gcx_lo == last) && (b.gcx_hi < 0 || b.gcx_hi == last);
-        const bool owner_ok = b.cx == 0 || b.cx >= P.ncx - 2;
-        if (!(ghosts_ok && owner_ok)) *ghost_anomaly = 1u;
+    if (!P.slab) {   // see GridDesc::ghost_anomaly
+        // the reference's wrap x - floor(x / DL) DL returns DL itself for a tiny negative x (and can return a
+        // negative sliver): a real entry that needs the minimum image wherever it is met
+        bool odd = !(b.xw >= 0.0 && b.xw < P.DL);
+        if (b.gcx_lo >= 0 || b.gcx_hi >= 0) {
+            const int last = P.ncx - 1;
+            const bool ghosts_ok = (b.gcx_lo < 0 || b.gcx_lo == last) && (b.gcx_hi < 0 || b.gcx_hi == last);
+            const bool owner_ok = b.cx == 0 || b.cx >= P.ncx - 2;
+            odd = odd || !(ghosts_ok && owner_ok);
+        }
+        if (odd) *ghost_anomaly = 1u;
     }
     snap[i] = make_double2(b.xw, b.y);
     const int row = b.cy * P.ncx;

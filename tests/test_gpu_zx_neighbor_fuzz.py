@@ -73,3 +73,51 @@ def test_neighbor_fuzz_bit_exact(sphb, oracle_be, block):
         got = sphb.sph_neighbor_search_mex(pos, nf, n, h, DL)
         for k, name in enumerate(PAIR_NAMES):
             assert np.array_equal(got[k], want[k]), f"{label}, {want[0].size} pairs: {name}"
+
+
+def _ulps(x, k):
+    x = np.float64(x)
+    for _ in range(abs(k)):
+        x = np.nextafter(x, np.inf if k > 0 else -np.inf)
+    return float(x)
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_neighbor_fuzz_ulps_around_thresholds(sphb, oracle_be, seed):
+    """Coordinates within three ulps of the values where the reference's arithmetic changes branch (0, the cell
+    size and its multiples, DL - 2h, DL, DL + 2h, -2h), box lengths within three ulps of a whole number of cells."""
+    rng = np.random.default_rng(seed)
+    for case in range(150):
+        h = float(rng.choice([0.05, 0.1, 0.13, 0.0325, 0.065]))
+        cell = 2.0 * h
+        ncols = int(rng.integers(3, 12))
+        DL = _ulps(ncols * cell, int(rng.integers(-3, 4)))
+        n = int(rng.integers(20, 200))
+        nf = int(rng.integers(1, n + 1))
+        crit = [0.0, cell, DL - cell, DL, 2 * cell, DL - 2 * cell, (ncols - 1) * cell, (ncols - 2) * cell, 3 * cell,
+                DL + cell, -cell, DL / 2]
+        x = np.array([_ulps(rng.choice(crit), int(rng.integers(-3, 4))) for _ in range(n)])
+        k = rng.random(n) < 0.3
+        x[k] = rng.random(int(k.sum())) * DL
+        y = np.array([_ulps(rng.choice([0.0, cell, 2 * cell, h, 0.5 * h]), int(rng.integers(-2, 3))) for _ in range(n)])
+        k = rng.random(n) < 0.3
+        y[k] = rng.random(int(k.sum())) * int(rng.integers(1, 5)) * cell
+        pos = np.asfortranarray(np.column_stack([x, y]))
+        want = oracle_be.neighbor_search(pos, nf, n, h, DL)
+        got = sphb.sph_neighbor_search_mex(pos, nf, n, h, DL)
+        for kk, name in enumerate(PAIR_NAMES):
+            assert np.array_equal(got[kk], want[kk]), f"seed {seed} case {case} (h={h}, {ncols} columns, DL={DL!r}): {name}"
+
+
+def test_neighbor_wrapped_x_equal_to_DL(sphb, oracle_be):
+    """nb:270-272 wraps a tiny negative x to DL itself (x - floor(x / DL) DL rounds to DL), which files the particle
+    in column 0 with x_w = DL: its neighbours in column 1 find it through the minimum image.  (Found by the fuzz.)"""
+    h, DL = 0.1, 1.4000000000000001
+    pos = np.asfortranarray(np.array([[0.20000000000000004, 0.4], [-1.5e-323, 0.4], [0.7, 0.4], [-1e-17, 0.45],
+                                      [0.1, 0.5], [1.3, 0.45]]))
+    for nf in (6, 4, 2):
+        want = oracle_be.neighbor_search(pos, nf, 6, h, DL)
+        got = sphb.sph_neighbor_search_mex(pos, nf, 6, h, DL)
+        assert want[0].size >= 2
+        for k, name in enumerate(PAIR_NAMES):
+            assert np.array_equal(got[k], want[k]), (nf, name)
