@@ -132,7 +132,7 @@ def build(force: bool = False, defines=()) -> str:
         return LIB
     san = ["-fsanitize=address", "-fno-omit-frame-pointer"] if os.environ.get("CPUSIM_ASAN") else []
     common = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-fvisibility=hidden", "-fno-ipa-reference", "-fno-ipa-pure-const",
-              "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-attributes", "-x", "c++",
+              "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-attributes", "-U_FORTIFY_SOURCE", "-x", "c++",
               f"-I{os.path.join(HERE, 'include')}"] + san + list(defines)
     objs, procs = [], []
     for unit, extra in UNITS.items():

@@ -7,8 +7,18 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <csetjmp>
 #include <mutex>
 #include <ucontext.h>
+
+// Fibers are created with makecontext; afterwards they are switched with _setjmp / _longjmp, which (unlike
+// swapcontext) do not save and restore the signal mask with a system call on every switch.  AddressSanitizer
+// tracks stacks through swapcontext only, so sanitized builds keep it.
+#if defined(__SANITIZE_ADDRESS__)
+#define CPUSIM_FAST_SWITCH 0
+#else
+#define CPUSIM_FAST_SWITCH 1
+#endif
 
 #include <sys/mman.h>
 
@@ -24,6 +34,8 @@ constexpr size_t kDynSmemBytes = 232 * 1024;
 
 struct Fiber {
     ucontext_t ctx;
+    jmp_buf jb;
+    bool started = false;
     bool done = true;
     bool waiting_cta = false;
     bool waiting_warp = false;
@@ -40,6 +52,7 @@ struct WarpState {
 
 struct Engine {
     ucontext_t sched;
+    jmp_buf sched_jb;
     Fiber fib[kMaxThreads];
     unsigned char *stacks = nullptr;
     alignas(16) unsigned char smem[kDynSmemBytes];
@@ -58,7 +71,29 @@ void fail(const char *msg)
     std::abort();
 }
 
-void yield_to_scheduler() { swapcontext(&E.fib[E.cur].ctx, &E.sched); }
+void yield_to_scheduler()
+{
+#if CPUSIM_FAST_SWITCH
+    if (!_setjmp(E.fib[E.cur].jb)) _longjmp(E.sched_jb, 1);
+#else
+    swapcontext(&E.fib[E.cur].ctx, &E.sched);
+#endif
+}
+
+// scheduler -> fiber t
+void resume_fiber(int t)
+{
+    Fiber &f = E.fib[t];
+#if CPUSIM_FAST_SWITCH
+    if (!_setjmp(E.sched_jb)) {
+        if (f.started) _longjmp(f.jb, 1);
+        f.started = true;
+        setcontext(&f.ctx);   // first entry: onto the fiber's own stack
+    }
+#else
+    swapcontext(&E.sched, &f.ctx);
+#endif
+}
 
 void release_cta_barrier()
 {
@@ -93,7 +128,11 @@ void trampoline()
 {
     (*E.body)();
     fiber_exit_bookkeeping(E.cur);
+#if CPUSIM_FAST_SWITCH
+    _longjmp(E.sched_jb, 1);
+#else
     swapcontext(&E.fib[E.cur].ctx, &E.sched);
+#endif
     fail("resumed a finished fiber");
 }
 
@@ -118,6 +157,7 @@ void run_cta(const std::function<void()> &body, int n_threads)
     for (int t = 0; t < n_threads; ++t) {
         Fiber &f = E.fib[t];
         f.done = false;
+        f.started = false;
         f.waiting_cta = f.waiting_warp = false;
         getcontext(&f.ctx);
         f.ctx.uc_stack.ss_sp = E.stacks + kStackBytes * (size_t)t;
@@ -155,7 +195,7 @@ void run_cta(const std::function<void()> &body, int n_threads)
             threadIdx.y = ((unsigned)t / blockDim.x) % blockDim.y;
             threadIdx.z = (unsigned)t / (blockDim.x * blockDim.y);
             E.progress = true;
-            swapcontext(&E.sched, &f.ctx);
+            resume_fiber(t);
         }
         if (!E.progress) fail("deadlock: every live thread of the CTA waits at a barrier that cannot complete");
     }
