@@ -53,6 +53,11 @@ __device__ __forceinline__ unsigned slab_class(double x, const SlabGeom &G)
         m |= 1u << cStay;
         if (d < G.halo) m |= 1u << cHaloL;
         if (d >= G.width - G.halo) m |= 1u << cHaloR;
+        // Towards the periodic seam the copies must cover `halo` CELLS of x, not `halo` columns: the last column
+        // of the channel is a sliver unless DL is a whole number of cells (nb:254), and a step consumes four full
+        // cells of validity.  (Found by the slab fuzz on the simulator: with a 0.08-cell sliver the rows within a
+        // cell of x = 0 were off by 1e-6 in drho/dt.)
+        else if (G.col_lo + G.width == G.ncx_g && x >= G.DL - (double)G.halo * G.cell) m |= 1u << cHaloR;
     } else if (d < G.width + (G.ncx_g - G.width + 1) / 2) {
         m |= 1u << cMigR;
     } else {

@@ -50,7 +50,9 @@ def _global_rows(s, sl):
     return out
 
 
-@pytest.mark.parametrize("n_slabs,dp,DL", [(2, 0.02, 3.0), (3, 0.01, 2.0)])
+# (2, 0.05, 3.0): 23.08 cell columns, i.e. a last column only 0.08 cells wide -- the halo towards the periodic seam
+# must still cover four full cells (slab_class)
+@pytest.mark.parametrize("n_slabs,dp,DL", [(2, 0.02, 3.0), (3, 0.01, 2.0), (2, 0.05, 3.0)])
 def test_slab_group_matches_single_domain(sphb, n_slabs, dp, DL):
     cs, slab, cfg, pt = _setup(sphb, dp, DL, seed=11)
     # a fast, seam-crossing flow so that rows migrate within a few steps
@@ -120,5 +122,28 @@ def test_slab_rows_migrate_across_the_seam(sphb):
     for f in ("pos", "vel", "rho"):
         assert_close(got[f], want[f][:nf], f, 1e-9)
     assert grp.status()["error_flags"] == 0
+    ch.close()
+    grp.close()
+
+
+def test_halo_towards_the_seam_covers_four_cells_with_a_sliver_last_column(sphb):
+    """dp = 0.05, DL = 3: 23.08 cell columns.  Counted in columns, the copies the slab of column 0 receives from
+    across the periodic seam would span 3.08 cells; a step consumes four, and rows that a fast drift carries over
+    x = 0 came out 1e-6 off in drho/dt (1e-8 in rho after 6 steps).  With four full cells of copies the slabs
+    stay on the single-domain run."""
+    cs, slab, cfg, pt = _setup(sphb, 0.05, 3.0, seed=493)
+    pt.vel[:pt.n_fluid, 0] -= 8.0
+    ch = _single(sphb, cfg, pt)
+    grp = slab.SlabGroup(cfg, pt, 2)
+    for _ in range(8):
+        ch.step()
+        grp.step()
+    assert grp.status()["error_flags"] == 0
+    want = ch.download(("pos", "vel", "rho", "p", "drho_dt"))
+    got = grp.gather(("pos", "vel", "rho", "p", "drho_dt"))
+    nf = pt.n_fluid
+    assert np.array_equal(got["ids"], np.arange(nf))
+    for f in ("pos", "vel", "rho", "p", "drho_dt"):
+        assert_close(got[f], want[f][:nf], f, 10 * TOL)
     ch.close()
     grp.close()
