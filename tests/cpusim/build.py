@@ -23,6 +23,7 @@ CSRC = os.path.join(ROOT, "sph-poiseuille-flow_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libsph_b200_cpusim.so")
 DRIVER = os.path.join(OUT, "sph_poiseuille_cpusim")
+MEXHOST = os.path.join(OUT, "libsphb_mex_stubhost_cpusim.so")
 UNITS = {"misc.cu": [], "scan.cu": [], "neighbor.cu": ["-ffp-contract=off"], "sort.cu": ["-ffp-contract=off"],
          "ops_pairs.cu": [], "ops_csr.cu": [], "context.cu": [], "slab.cu": [], "batch.cu": [], "api.cu": []}
 
@@ -156,6 +157,20 @@ def build(force: bool = False, defines=()) -> str:
     drv = os.path.join(ROOT, "sph-poiseuille-flow_b200", "driver", "sph_poiseuille_main.c")
     subprocess.run(["gcc", "-O2", f"-I{os.path.join(ROOT, 'include')}", drv, "-o", DRIVER, f"-L{OUT}",
                     "-lsph_b200_cpusim", "-Wl,-rpath,$ORIGIN", "-lm"] + san, check=True)
+    # the two MEX shims + the stub MATLAB host (oracle/stub) against the simulator library
+    stub, mexdir = os.path.join(ROOT, "oracle", "stub"), os.path.join(ROOT, "sph-poiseuille-flow_b200", "mex")
+    mobjs = []
+    for src, sym in (("sph_neighbor_search_mex.c", "sphb_neighbor_mexFunction"),
+                     ("sph_physics_shell_mex.c", "sphb_physics_mexFunction")):
+        obj = os.path.join(OUT, src.replace(".c", ".o"))
+        subprocess.run(["gcc", "-O2", "-fPIC", f"-I{stub}", f"-I{os.path.join(ROOT, 'include')}", f"-DmexFunction={sym}",
+                        "-c", os.path.join(mexdir, src), "-o", obj] + san, check=True)
+        mobjs.append(obj)
+    hobj = os.path.join(OUT, "mexhost.o")
+    subprocess.run(["gcc", "-O2", "-fPIC", "-Wno-use-after-free", f"-I{stub}", "-c", os.path.join(stub, "mexhost.c"),
+                    "-o", hobj] + san, check=True)
+    subprocess.run(["gcc", "-shared", "-o", MEXHOST] + san + mobjs + [hobj, f"-L{OUT}", "-lsph_b200_cpusim",
+                                                                    "-Wl,-rpath,$ORIGIN", "-lm"], check=True)
     open(stamp, "w").write(flags)
     return LIB
 

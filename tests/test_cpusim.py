@@ -15,12 +15,14 @@ import pytest
 
 from conftest import ROOT
 
-FAST = ("not full_size and not ensemble_equals and not reference_loop and not golden_trajectory and not mex_shims")
+FAST = "not full_size and not ensemble_equals and not reference_loop and not golden_trajectory"
 
 
 def _run(lib, files, k=None, env_extra=None, timeout=1500):
     env = dict(os.environ, SPHB_CPUSIM_LIB=lib, OMP_NUM_THREADS="1",
-               SPHB_CPUSIM_DRIVER=os.path.join(os.path.dirname(lib), "sph_poiseuille_cpusim"), **(env_extra or {}))
+               SPHB_CPUSIM_DRIVER=os.path.join(os.path.dirname(lib), "sph_poiseuille_cpusim"),
+               SPHB_CPUSIM_MEXHOST=os.path.join(os.path.dirname(lib), "libsphb_mex_stubhost_cpusim.so"),
+               **(env_extra or {}))
     cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + files
     if k:
         cmd += ["-k", k]

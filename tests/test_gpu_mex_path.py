@@ -255,7 +255,9 @@ class _ShimBackend:
         import os
         from conftest import ROOT
         from oracle.mexhost import MexLibrary
-        self.mex = MexLibrary(os.path.join(ROOT, "sph-poiseuille-flow_b200", "libsphb_mex_stubhost.so"))
+        # (SPHB_CPUSIM_MEXHOST: test infrastructure, the shims linked against the simulator build of the library)
+        self.mex = MexLibrary(os.environ.get("SPHB_CPUSIM_MEXHOST") or
+                              os.path.join(ROOT, "sph-poiseuille-flow_b200", "libsphb_mex_stubhost.so"))
 
     def neighbor_search(self, pos, n_fluid, n_total, h, DL):
         out = self.mex.call("sphb_neighbor_mexFunction", 7, pos, n_fluid, n_total, h, DL)
