@@ -193,7 +193,8 @@ typedef struct sphb_status {
     long long step;
     long long n_half_pairs;
     long long n_csr_entries;
-    int error_flags;      /* device-side flags: 1 CSR capacity, 2 cell capacity, 4 dedup capacity, 8 non-finite */
+    int error_flags;      /* device-side flags: 1 list rows, 2 cell capacity, 4 dedup capacity, 8 non-finite, 16 tile slots,
+                             32 slab rows */
 } sphb_status;
 SPHB_API int sphb_ctx_status(sphb_ctx *ctx, sphb_status *out);
 

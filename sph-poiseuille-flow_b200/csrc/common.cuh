@@ -103,7 +103,12 @@ struct GridDesc {
     // walk takes for granted (ghosts in column ncx-1, owners in columns 0, ncx-2, ncx-1): exact multiples of the
     // cell size can round floor((x_w +- DL) / cell) one column further (nb:284-294) -- or when a wrapped x falls
     // outside [0, DL) (nb:270-272 returns DL itself for a tiny negative x).  Every tile of such a build is a seam
-    // tile and every walker takes the general walk.
+    // tile and every walker takes the general walk.  Bit 0: wrapped x out of range; bit 1: ghost / owner column.
+    // The reference's HALF list (stateless search, MEX export) is exact either way.  In the FULL gather list of
+    // the resident path a pair that one end finds only through such a rounding accident (a ghost in an unusual
+    // column, or a ghost that exists for one end because x_w sits exactly on the insertion threshold nb:282,289)
+    // can be missing from the other end's row: in exact arithmetic both ends see each other, so these pairs lie
+    // within rounding of r = 2h, where W ~ (2 - q)^3 and dW ~ (2 - q)^2 vanish -- no effect on any sum.
     unsigned int ghost_anomaly;
 };
 

@@ -262,14 +262,14 @@ __device__ __forceinline__ void bin_count_body(const double2 *__restrict__ pos, 
     if (!P.slab) {   // see GridDesc::ghost_anomaly
         // the reference's wrap x - floor(x / DL) DL returns DL itself for a tiny negative x (and can return a
         // negative sliver): a real entry that needs the minimum image wherever it is met
-        bool odd = !(b.xw >= 0.0 && b.xw < P.DL);
+        unsigned odd = (b.xw >= 0.0 && b.xw < P.DL) ? 0u : 1u;
         if (b.gcx_lo >= 0 || b.gcx_hi >= 0) {
             const int last = P.ncx - 1;
             const bool ghosts_ok = (b.gcx_lo < 0 || b.gcx_lo == last) && (b.gcx_hi < 0 || b.gcx_hi == last);
             const bool owner_ok = b.cx == 0 || b.cx >= P.ncx - 2;
-            odd = odd || !(ghosts_ok && owner_ok);
+            if (!(ghosts_ok && owner_ok)) odd |= 2u;
         }
-        if (odd) *ghost_anomaly = 1u;
+        if (odd) atomicOr(ghost_anomaly, odd);
     }
     snap[i] = make_double2(b.xw, b.y);
     const int row = b.cy * P.ncx;
