@@ -59,6 +59,13 @@ def cut_slab(cfg, pt, col_lo: int, col_hi: int, halo: int = HALO_COLS):
     cw = c[nf:]
     rel = np.mod(cw - col_lo + halo, ncx) - halo
     keep = rel < width + halo
+    if col_lo == 0:
+        # towards the periodic seam the halo is `halo` CELLS of x, not columns: the channel's last column is a
+        # sliver unless DL is a whole number of cells (same rule as slab_class in csrc/slab.cu for the fluid copies)
+        xw = pt.pos[nf:, 0] - np.floor(pt.pos[nf:, 0] / cfg.DL) * cfg.DL
+        deeper = ~keep & (xw >= cfg.DL - halo * 2.0 * cfg.h)
+        rel = np.where(deeper, cw - ncx, rel)
+        keep = keep | deeper
     k = (col_lo + rel - cw) // ncx                             # -1, 0 or +1 periods
     wx = pt.pos[nf:, 0] + k * cfg.DL
     widx = np.nonzero(keep)[0]
