@@ -6,6 +6,16 @@ closures), which catches logic errors, bad indexing and broken host orchestratio
 hand -- e.g. the batched ensemble launches and the flat staging build -- before GPU minutes are spent on them.  It
 cannot see races, memory-model or alignment problems, and it measures nothing.  Parity is claimed from
 `pytest -m gpu` on a B200 only.  The product never loads this library (SPHB_CPUSIM_LIB is read by tests/conftest.py).
+
+The tests below run the quick part of the GPU suite.  The whole of it (everything but the two-rank NCCL test; about six
+minutes) runs with
+
+    B=tests/cpusim/_build; python tests/cpusim/build.py [-DSPHB_FLAT_STAGING=1]
+    SPHB_CPUSIM_LIB=$PWD/$B/libsph_b200_cpusim.so SPHB_CPUSIM_DRIVER=$PWD/$B/sph_poiseuille_cpusim \
+    SPHB_CPUSIM_MEXHOST=$PWD/$B/libsphb_mex_stubhost_cpusim.so python -m pytest tests -q -m gpu -k "not nccl"
+
+Options: CPUSIM_SCHEDULE=reverse|random (order in which the threads of a CTA run between barriers), CPUSIM_ASAN=1 at
+build time (AddressSanitizer; run with LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0).
 """
 import os
 import subprocess
