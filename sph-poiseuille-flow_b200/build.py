@@ -27,7 +27,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function",
           "-Xptxas", "-v" if os.environ.get("SPHB_PTXAS_V") else "-O3"]
 # experimental code paths, off unless asked for (each documented where it is defined)
-for _flag in ("SPHB_FLAT_STAGING",):
+for _flag in ("SPHB_FLAT_STAGING", "SPHB_STAGE_UNROLL"):
     if os.environ.get(_flag):
         COMMON.append(f"-D{_flag}={os.environ[_flag]}")
 UNITS = {

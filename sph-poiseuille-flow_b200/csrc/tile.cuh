@@ -125,7 +125,10 @@ __device__ __forceinline__ int tile_slot_entry(const TileDesc &T, int slot)
 //   load(e)  -> a record of registers: every load of it is unconditional (clamped slot), so the loads of all
 //               the thread's slots are in flight together, level by level;
 //   store(slot, record) -> shared memory, predicated on slot < n_staged.
-constexpr int kStageUnroll = 3;   // 3 x 128 slots cover a lattice tile (4 x 11 cells x 6.8 entries ~ 300) in one pass
+#ifndef SPHB_STAGE_UNROLL
+#define SPHB_STAGE_UNROLL 3       // 3 x 128 slots cover a lattice tile (4 x 11 cells x 6.8 entries ~ 300) in one pass
+#endif
+constexpr int kStageUnroll = SPHB_STAGE_UNROLL;
 
 // entry behind a slot: the segment offsets are non-decreasing (an empty segment shares the offset of its
 // successor), so the segment of `slot` is the LAST one whose offset is <= slot
