@@ -42,7 +42,7 @@ def test_step_fuzz_against_oracle(sphb, H, oracle_be, block):
             ch.step()
             s, d = ch.status(), ch.download()
             assert s["error_flags"] == 0 and s["n_half_pairs"] == ref.pairs[0].size, (what, k)
-            assert abs(s["dt"] - dt) <= 1e-13 * dt, (what, k)
+            assert abs(s["dt"] - dt) <= 1e-11 * dt, (what, k)
             # the tolerance is per step; round-off carried over from earlier steps grows with the flow's own
             # sensitivity, so later steps get the head-room the multi-step tests use
             for f in FIELDS:

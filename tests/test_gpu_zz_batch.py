@@ -6,12 +6,14 @@ plumbing and host schedule are exercised there -- but have NOT yet run on a GPU,
 claimed for the batched path.  The file sorts last so that a surprise on the hardware cannot mask the other tests.
 
 The batch kernels call the very __device__ bodies of the single-channel kernels with per-channel arguments read
-from device records, so the expected result is BIT identity with Channel.run_dual, channel by channel.
+from device records, so the expected result is Channel.run_dual's, channel by channel (bit for bit on the simulator).
 """
 import importlib
 
 import numpy as np
 import pytest
+
+from parity_util import TOL, assert_close
 
 pytestmark = [pytest.mark.gpu]
 
@@ -36,20 +38,26 @@ def _channels(sphb, n, sort_interval, DL=1.0, dp=0.05):
 
 
 def _assert_same(a, b):
+    """Batched launches run the same __device__ bodies as the single-channel kernels, but they are separate kernels
+    to the compiler (arguments from a device record, other register budget), so the last bit of a sum may differ
+    on the GPU (FMA contraction is decided per kernel); on the CPU simulator the two are bit-identical.  Fields are
+    held to the one-step tolerance times a small factor for the steps taken, integers and flags exactly."""
     for k, (x, y) in enumerate(zip(a, b)):
         dx, dy = x.download(), y.download()
         for f in FIELDS:
-            assert np.array_equal(dx[f], dy[f]), (k, f)
+            assert_close(dx[f], dy[f], f"channel {k} {f}", 20 * TOL)
         sx, sy = x.status(), y.status()
-        for key in ("t", "dt", "vmax", "tau_bottom", "tau_top", "step", "n_half_pairs", "n_csr_entries"):
+        for key in ("step", "n_half_pairs", "n_csr_entries"):
             assert sx[key] == sy[key], (k, key, sx[key], sy[key])
+        for key in ("t", "dt", "vmax", "tau_bottom", "tau_top"):
+            assert abs(sx[key] - sy[key]) <= 1e-10 * max(abs(sy[key]), 1e-300), (k, key, sx[key], sy[key])
         assert sx["error_flags"] == 0
 
 
 @pytest.mark.parametrize("n_inner", [1, 3])
 def test_batch_equals_separate_runs(sphb, n_inner):
-    """12 channels with different mu and g, 7 outer steps: batched launches == one channel after the other, to the
-    bit, including each channel's own clock, dt, max|v|, wall shear and pair counts."""
+    """12 channels with different mu and g, 7 outer steps: batched launches == one channel after the other,
+    including each channel's own clock, dt, max|v|, wall shear and pair counts."""
     make = _channels(sphb, 12, sort_interval=0)
     a, b = make(), make()
     batch = sphb.Batch(a)
@@ -67,7 +75,7 @@ def test_batch_equals_separate_runs(sphb, n_inner):
 
 def test_batch_across_cell_sorts(sphb):
     """sort_interval = 3: the per-channel cell sort swaps buffers in the middle of the batched schedule and the
-    records are refreshed; 10 outer steps stay bit-identical to the single-channel schedule."""
+    records are refreshed; 10 outer steps stay on the single-channel schedule."""
     make = _channels(sphb, 5, sort_interval=3)
     a, b = make(), make()
     batch = sphb.Batch(a)
