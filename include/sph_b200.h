@@ -157,7 +157,8 @@ typedef struct sphb_params {
 SPHB_API int sphb_ctx_create(const sphb_params *prm, sphb_ctx **ctx);
 SPHB_API void sphb_ctx_destroy(sphb_ctx *ctx);
 
-/* Host (pageable or pinned) column-major arrays; any pointer may be NULL = leave untouched. */
+/* Host (pageable or pinned) column-major arrays; any pointer may be NULL = leave untouched.  Uploading `mass` sets
+ * Vol = mass / rho (the initial condition, m:120); without it the volumes of the last density pass are kept. */
 SPHB_API int sphb_ctx_upload(sphb_ctx *ctx, const double *pos, const double *vel, const double *rho,
                              const double *drho_dt, const double *mass, const double *wall_vel);
 SPHB_API int sphb_ctx_download(sphb_ctx *ctx, double *pos, double *vel, double *rho, double *p, double *drho_dt,

@@ -359,7 +359,10 @@ SPHB_API int sphb_ctx_upload(sphb_ctx *c, const double *pos, const double *vel, 
     if (rho) SPHB_CUDA(cudaMemcpyAsync(c->rho.p, rho, n * sizeof(double), cudaMemcpyHostToDevice, c->st));
     if (drho_dt) SPHB_CUDA(cudaMemcpyAsync(c->drho_dt.p, drho_dt, n * sizeof(double), cudaMemcpyHostToDevice, c->st));
     if (mass) SPHB_CUDA(cudaMemcpyAsync(c->mass.p, mass, n * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    if (mass || rho)
+    // Vol = m / rho is the initial condition (m:120) and comes with the masses.  A caller that feeds the state of
+    // the last step back (rho without mass) keeps the volumes of that step's density pass, like B: they are what
+    // the reference hands to the wall-shear monitor (m:281-283), and every step recomputes them first thing.
+    if (mass)
         k_vol_from_mass<<<grid_for(n), kBlock, 0, c->st>>>(c->mass.as<double>(), c->rho.as<double>(),
                                                            c->Vol.as<double>(), nt);
     if (vel) SPHB_TRY(csr_vmax(c->P, c->vel.as<double2>(), c->sc(), c->st));

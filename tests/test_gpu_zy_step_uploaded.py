@@ -47,6 +47,13 @@ def test_step_uploaded_is_the_physics_of_a_step(sphb, H, oracle_be):
         assert np.array_equal(da[f], db[f]), f
     sa, sb = a.status(), b.status()
     assert sa["t"] == sb["t"] and sa["dt"] == sb["dt"] and sb["error_flags"] == 0
+    # the monitor of the chain runs at the start of the next pass, on the list of the uploaded positions and with
+    # the volumes and B of the last step: the shear the resident run reported at the end of its step
+    d = b.download(("pos", "vel", "rho", "drho_dt"))
+    b.upload(pos=d["pos"], vel=d["vel"], rho=d["rho"], drho_dt=d["drho_dt"])
+    b.step_uploaded()
+    sb = b.status()
+    assert sb["tau_bottom"] == sa["tau_bottom"] and sb["tau_top"] == sa["tau_top"]
     a.close()
     b.close()
 
