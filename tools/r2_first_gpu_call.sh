@@ -7,7 +7,8 @@
 # and every step runs under its own `timeout` so that an unverified path cannot hang the box.
 #   1. the default build: GPU parity tests + the N = 1 bench line (baseline of the round)
 #   2. batched ensemble launches (csrc/batch.cu): parity tests, then per-channel graphs vs --batched
-#   3. flat staging (SPHB_FLAT_STAGING=1 build): GPU parity tests + bench line, then the default build is restored
+#   3. flat staging (SPHB_FLAT_STAGING=1 build): GPU parity tests + bench line, 2 and 4 slots per pass, then the
+#      default build is restored
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out/r2_first
@@ -38,6 +39,10 @@ if [ -f sph-poiseuille-flow_b200/libsph_b200.so ]; then
     step 3_tests_flat 900 python -m pytest tests -x -q -m gpu
     step 3_bench_flat 600 python bench.py --steps 20 --warmup 3
 fi
+for u in 2 4; do   # slots per thread and staging pass (default 3)
+    step 3_build_flat_u$u 900 env SPHB_FLAT_STAGING=1 SPHB_STAGE_UNROLL=$u python sph-poiseuille-flow_b200/build.py
+    step 3_bench_flat_u$u 600 python bench.py --steps 20 --warmup 3 --e2e-steps 2 --cpu-baseline-steps 0
+done
 step 3_build_default 900 python sph-poiseuille-flow_b200/build.py
 step 3_tests_default_again 900 python -m pytest tests -x -q -m gpu
 cat "$OUT/summary.txt"
