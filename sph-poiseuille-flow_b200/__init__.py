@@ -29,7 +29,10 @@ from . import channel_setup  # noqa: F401  (host-side set-up mirror of SPH_Poise
 from .channel_setup import ChannelConfig  # noqa: F401
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsph_b200.so")
+# SPHB_LIB_VARIANT=<tag> loads libsph_b200_<tag>.so, an A/B build of the same sources with experimental -D
+# switches (build.py, SPHB_BUILD_TAG); a missing variant fails loudly like a missing default build.
+_VARIANT = os.environ.get("SPHB_LIB_VARIANT", "")
+LIB_PATH = os.path.join(HERE, f"libsph_b200_{_VARIANT}.so" if _VARIANT else "libsph_b200.so")
 
 _DP = C.POINTER(C.c_double)
 

@@ -18,8 +18,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libsph_b200.so")
+# A/B experiments: SPHB_BUILD_TAG=<tag> builds the library with the experimental -D switches below into
+# libsph_b200_<tag>.so (objects in build_<tag>/) beside the default build; SPHB_LIB_VARIANT=<tag> makes the
+# Python mirror load it.  Tagged builds skip the MEX shims and the driver.
+TAG = os.environ.get("SPHB_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build_" + TAG if TAG else "build")
+LIB = os.path.join(HERE, f"libsph_b200_{TAG}.so" if TAG else "libsph_b200.so")
 MEXHOST_LIB = os.path.join(HERE, "libsphb_mex_stubhost.so")
 DRIVER = os.path.join(HERE, "sph_poiseuille_b200")
 
@@ -30,6 +34,8 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hi
 for _flag in ("SPHB_FLAT_STAGING", "SPHB_STAGE_UNROLL"):
     if os.environ.get(_flag):
         COMMON.append(f"-D{_flag}={os.environ[_flag]}")
+for _d in os.environ.get("SPHB_DEFINES", "").split():   # e.g. SPHB_DEFINES="SPHB_X=1 SPHB_Y=2"
+    COMMON.append("-D" + _d)
 UNITS = {
     "misc.cu": [],
     "scan.cu": [],
@@ -133,6 +139,8 @@ def build_driver(force=False, verbose=False) -> str:
 
 def build_all(force=False, verbose=False):
     out = [build_library(force, verbose)]
+    if TAG:
+        return out
     out.append(build_mex_stubhost(force, verbose))
     out.append(build_driver(force, verbose))
     return [o for o in out if o]

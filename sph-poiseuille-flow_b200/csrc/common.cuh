@@ -14,7 +14,7 @@
 #include "../../include/sph_b200.h"
 
 #ifndef SPHB_FLAT_STAGING
-#define SPHB_FLAT_STAGING 0   // 1: staging loops of the hot tile kernels as flat, load/store-split passes (tile.cuh)
+#define SPHB_FLAT_STAGING 1   // staging loops of the hot tile kernels as flat, load/store-split passes (tile.cuh); 0 = segment by segment (round 1)
 #endif
 
 namespace sphb {

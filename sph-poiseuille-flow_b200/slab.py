@@ -219,6 +219,24 @@ class SlabGroup:
         for s in self.slabs:
             s.step_end()
 
+    def monitors(self):
+        """(max|v|, tau_bottom, tau_top) of the whole channel NOW: every slab's scalars, reduced on the device by the
+        kernel the NCCL form uses on its gathered chunks (sphb_ctx_slab_scalars_reduce_at).  `self.tau` is what the
+        last exchange carried, i.e. the shear of the list the step started from."""
+        import torch
+        S = self.slabs
+        for s in S:
+            _check(lib().sphb_ctx_slab_scalars_export(s.ch._ctx, C.c_void_p(s.scal.data_ptr())))
+            s.ch.sync()
+        gathered = torch.cat([s.scal for s in S])
+        offs = torch.arange(0, 4 * self.n, 4, dtype=torch.int64, device=gathered.device)
+        red = torch.zeros(3, dtype=torch.float64, device=gathered.device)
+        _check(lib().sphb_ctx_slab_scalars_reduce_at(S[0].ch._ctx, C.c_void_p(gathered.data_ptr()),
+                                                     C.c_void_p(offs.data_ptr()), C.c_int(self.n),
+                                                     C.c_void_p(red.data_ptr())))
+        S[0].ch.sync()
+        return tuple(float(v) for v in red.tolist())   # (the kernel also stores max|v| in slab 0, which holds it already)
+
     def gather(self, fields=("pos", "vel", "rho", "p", "drho_dt")):
         """Owned rows of every slab, ordered by global particle id."""
         parts = [s.owned(fields) for s in self.slabs]

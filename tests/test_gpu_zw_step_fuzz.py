@@ -9,7 +9,7 @@ Also run against the CPU functional simulator by tests/test_cpusim.py (written a
 import numpy as np
 import pytest
 
-from parity_util import TOL
+from parity_util import TOL, log_observed
 
 pytestmark = pytest.mark.gpu
 
@@ -42,10 +42,12 @@ def test_step_fuzz_against_oracle(sphb, H, oracle_be, block):
             ch.step()
             s, d = ch.status(), ch.download()
             assert s["error_flags"] == 0 and s["n_half_pairs"] == ref.pairs[0].size, (what, k)
+            log_observed(f"{what} step {k} dt", abs(s["dt"] - dt) / dt, 1e-11)
             assert abs(s["dt"] - dt) <= 1e-11 * dt, (what, k)
             # the tolerance is per step; round-off carried over from earlier steps grows with the flow's own
             # sensitivity, so later steps get the head-room the multi-step tests use
             for f in FIELDS:
+                log_observed(f"{what} step {k} {f}", _rel(d[f], getattr(ref, f)), TOL * (1 if k == 0 else 10))
                 assert _rel(d[f], getattr(ref, f)) <= TOL * (1 if k == 0 else 10), (what, k, f)
         ch.close()
 

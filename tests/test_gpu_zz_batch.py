@@ -13,7 +13,7 @@ import importlib
 import numpy as np
 import pytest
 
-from parity_util import TOL, assert_close
+from parity_util import TOL, assert_close, log_observed
 
 pytestmark = [pytest.mark.gpu]
 
@@ -50,6 +50,7 @@ def _assert_same(a, b):
         for key in ("step", "n_half_pairs", "n_csr_entries"):
             assert sx[key] == sy[key], (k, key, sx[key], sy[key])
         for key in ("t", "dt", "vmax", "tau_bottom", "tau_top"):
+            log_observed(f"channel {k} {key}", abs(sx[key] - sy[key]) / max(abs(sy[key]), 1e-300), 1e-10)
             assert abs(sx[key] - sy[key]) <= 1e-10 * max(abs(sy[key]), 1e-300), (k, key, sx[key], sy[key])
         assert sx["error_flags"] == 0
 
