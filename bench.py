@@ -83,9 +83,11 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="sharded mode: eager launches instead of one CUDA graph per step")
     ap.add_argument("--channels", type=int, default=512,
                     help="--mode ensemble: independent channels PER GPU (BASELINE configs[3]: 4096 in all at 8 GPUs)")
-    ap.add_argument("--batched", action="store_true",
+    ap.add_argument("--batched", action="store_true", default=True,
                     help="--mode ensemble: step the channels with batched launches (sphb_batch_*: every kernel "
-                         "launched once for all channels) instead of one CUDA graph per channel")
+                         "launched once for all channels; the default, measured 8.8e8 vs 7.2e8 particle-substeps/s)")
+    ap.add_argument("--per-channel-graphs", dest="batched", action="store_false",
+                    help="--mode ensemble: one context + stream + CUDA graph per channel instead of batched launches")
     ap.add_argument("--mode", default="auto", choices=("auto", "slab", "replicas", "ensemble"),
                     help="N > 1: 'slab' = ONE periodic channel of length N*DL cut into x-slabs (halo exchange + "
                          "migration over NCCL, weak scaling); 'replicas' = N independent channels (ensemble); "
@@ -123,7 +125,9 @@ def ncu_traffic(kernel: str):
             return None, None
         NCU_EXTRA.clear()
         NCU_EXTRA.update({k: rec[0].get(k) for k in ("duration_us", "fp64_pipe_pct", "lsu_wavefronts_pct",
-                                                     "issue_active_pct", "warps_active_pct", "dram_throughput_pct")})
+                                                     "issue_active_pct", "warps_active_pct", "dram_throughput_pct",
+                                                     "fp64_thread_instructions")})
+        NCU_EXTRA["capture"] = os.path.relpath(files[-1], ROOT)
         return rec[0]["dram_bytes"], os.path.relpath(files[-1], ROOT)
     except (OSError, ValueError, KeyError, IndexError):
         return None, None
@@ -409,6 +413,24 @@ def b200_arm(args):
                 "fp64_note": "fp64 gather over ~41 neighbours per particle: the FP64 pipe and the shared-memory "
                              "data pipe bound these kernels, not HBM (profiles/README.md)"}
         # the kernels of the acoustic substep alone (forces + continuity), list rebuild and KGC excluded
+        # FP64 roofline of the same kernel: FP64-pipe thread instructions per launch (counted once per profile by
+        # ncu, smsp__thread_inst_executed_pipe_fp64 of the committed capture named in roofline.ncu.capture) over the
+        # live launch time, against the DFMA rate measured on this device just now (sphb_fp64_peak)
+        try:
+            peak_tf = lp.fp64_peak()
+        except Exception as err:   # noqa: BLE001
+            peak_tf = None
+            print(f"bench.py: fp64 peak not measured ({err})", file=sys.stderr)
+        n_inst = NCU_EXTRA.get("fp64_thread_instructions")
+        if peak_tf:
+            fp64 = {"peak_tflops": peak_tf, "peak_source": "sphb_fp64_peak: DFMA chains, this device, this run",
+                    "peak_ginst_s": peak_tf * 1e3 / 2.0}
+            if n_inst:
+                ginst = n_inst / (kernels[top]["ms_per_call"] * 1e-3) / 1e9
+                fp64.update({"achieved_ginst_s": ginst, "achieved_tflops_dfma_equiv": 2.0 * ginst / 1e3,
+                             "frac": ginst / (peak_tf * 1e3 / 2.0), "inst_per_particle": n_inst / nt,
+                             "inst_source": NCU_EXTRA.get("capture")})
+            roof["fp64"] = fp64
         sub_ms = sum(kernels[n]["ms_per_call"] for n in ("force_fused", "time_step", "pressure", "continuity", "clock")
                      if n in kernels)
         roof["substep_kernels_only"] = {"ms": sub_ms, "value": nt / (sub_ms * 1e-3),

@@ -65,6 +65,10 @@ SPHB_API const char *sphb_last_error_msg(void);
 SPHB_API int sphb_version(void);
 /* 0 when a CUDA device is usable, else non-zero (and the last error says why). */
 SPHB_API int sphb_device_check(void);
+/* Measured DFMA throughput of the current device in TFLOP/s (2 flops per DFMA; eight independent chains per thread,
+ * 8 warps per SM sub-partition), best of `reps` launches of iters x 32 DFMAs per thread, CUDA events.  The fp64
+ * roofline denominator of bench.py; the reference has no counterpart. */
+SPHB_API int sphb_fp64_peak(int iters, int reps, double *tflops);
 
 /* ============================== 1. stateless MEX-path entry points ============================== */
 

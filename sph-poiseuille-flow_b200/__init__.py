@@ -112,6 +112,13 @@ def device_available() -> bool:
     return lib().sphb_device_check() == 0
 
 
+def fp64_peak(iters: int = 4096, reps: int = 5) -> float:
+    """Measured DFMA throughput of the current device in TFLOP/s (sphb_fp64_peak)."""
+    out = C.c_double(0.0)
+    _check(lib().sphb_fp64_peak(C.c_int(iters), C.c_int(reps), C.byref(out)))
+    return out.value
+
+
 # ------------------------------------------------------------------------------------------------
 # marshalling: MATLAB values -> sphb_mat
 # ------------------------------------------------------------------------------------------------

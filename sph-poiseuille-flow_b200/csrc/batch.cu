@@ -61,6 +61,8 @@ BatchLaunch phys_launch(const sphb_batch *b)
     L.n_tiles = b->n_tiles;
     L.n_fluid = b->n_fluid;
     L.tile_cap = b->tile_cap;
+    L.ncx = b->ctx[0]->view().ncx;
+    L.tile_w = b->ctx[0]->nw.tile_w;
     L.st = b->st;
     return L;
 }
@@ -133,9 +135,10 @@ int enqueue_physics(sphb_batch *b, int n_inner)
 {
     const double inf = std::numeric_limits<double>::infinity();
     const BatchLaunch L = phys_launch(b);
+    SPHB_TRY(csr_batch_publish_dt(L, inf, 0.0));
     SPHB_TRY(csr_batch_density(L));
     SPHB_TRY(csr_batch_kgc(L));
-    SPHB_TRY(csr_batch_force_fused(L, inf, 0.0, true));
+    SPHB_TRY(csr_batch_force_fused(L, true));
     SPHB_TRY(csr_batch_continuity(L, true, true));
     b->launches += 5;
     for (int s = 1; s < n_inner; ++s) {
@@ -152,7 +155,7 @@ int enqueue_list_and_shear(sphb_batch *b)
 {
     SPHB_TRY(neighbor_batch_build(nbr_launch(b), &b->launches));
     SPHB_TRY(csr_batch_wall_shear(phys_launch(b)));
-    b->launches += 2;
+    b->launches += 1;
     return 0;
 }
 
@@ -261,8 +264,10 @@ SPHB_API int sphb_batch_run_dual(sphb_batch *b, int n_outer, int n_inner)
     if (!b) return set_error("SPHB:arg", "null batch");
     if (n_inner < 1 || n_outer < 0) return set_error("SPHB:arg", "n_inner >= 1 and n_outer >= 0 required");
     SPHB_CUDA(cudaSetDevice(b->device));
-    for (sphb_ctx *c : b->ctx)
+    for (sphb_ctx *c : b->ctx) {
         if (!c->have_list) return set_error("SPHB:state", "a channel of the batch has no neighbour list");
+        SPHB_TRY(ctx_fresh_mirrors(c, false));   // rows uploaded behind a standing list (eager, on the batch's stream)
+    }
     if (b->graph_inner != n_inner) batch_drop_graph(b);
     const int si = b->sort_interval;
     for (int o = 0; o < n_outer; ++o) {

@@ -17,6 +17,10 @@
 #define SPHB_FLAT_STAGING 1   // staging loops of the hot tile kernels as flat, load/store-split passes (tile.cuh); 0 = segment by segment (round 1)
 #endif
 
+#ifndef SPHB_ROW_FULLWORD
+#define SPHB_ROW_FULLWORD 0
+#endif
+
 namespace sphb {
 
 // ------------------------------------------------------------------------------------------------
@@ -116,6 +120,16 @@ struct GridDesc {
 // neighbour-list storage shared by the stateless search and the resident context
 // ------------------------------------------------------------------------------------------------
 struct TileDesc;
+// Entry-ordered mirrors written by the list build for the gather kernels of the resident path (ops_csr.cu): the
+// walker of every real entry copies its row's velocity (a wall row: its wall velocity) and wall weight to the
+// entry's index, so that a tile's neighbourhood is a few contiguous ranges.  All NULL = not wanted (stateless search).
+struct BuildMirrors {
+    const double2 *vel = nullptr, *wall_vel = nullptr;
+    const double *mass = nullptr;
+    double inv_rho0 = 0.0;
+    double2 *e_vel = nullptr;   // velocity at build time
+    double2 *e_w = nullptr;     // (m / rho0, 0) for a wall entry, (-1, 0) for a fluid entry (ph:205)
+};
 struct NeighborWork {
     int n_fluid = 0, n_total = 0;
     double h = 0, DL = 0;
@@ -136,6 +150,7 @@ struct NeighborWork {
     bool grid_armed = false;     // the GridDesc reduction keys have been initialised
     bool half_valid = false;     // totals[0] holds the half-pair count of the current list
     bool tile_fitted = false;    // tile_cap has been fitted to the first build
+    BuildMirrors mirrors;        // set by the resident context before every build
     DevBuf grid;                 // GridDesc
     DevBuf flags;                // int error flags
     DevBuf snap;                 // double2 [n_total]   wrapped x, y at build time

@@ -73,6 +73,11 @@ int plan_lists(sphb_ctx *c, double y_lo, double y_hi)
                            csr_max_tile_slots()));
     SPHB_TRY(csr_configure(c->nw.tile_cap));
     SPHB_TRY(c->shear_partials.reserve(2 * (size_t)c->nw.n_tiles * sizeof(double)));
+    for (DevBuf *b : {&c->e_vel, &c->e_w, &c->e_pV, &c->e_b1, &c->e_b2, &c->e_vn})   // entry-ordered mirrors
+        if (b->bytes < c->nw.ell_stride * sizeof(double2)) {
+            SPHB_TRY(b->reserve(c->nw.ell_stride * sizeof(double2)));
+            SPHB_CUDA(cudaMemsetAsync(b->p, 0, c->nw.ell_stride * sizeof(double2), c->st));
+        }
     SPHB_TRY(sort_plan(c->sw, p.n_fluid, p.DL, p.h, y_hi - y_lo));
     c->planned = true;
     c->y_lo = y_lo;
@@ -81,18 +86,30 @@ int plan_lists(sphb_ctx *c, double y_lo, double y_hi)
 }
 
 // ---- pieces of one step ------------------------------------------------------------------------
+int fresh_mirrors(sphb_ctx *c, bool need_pv)
+{
+    if (!c->have_list || !(c->mirrors_stale || (need_pv && !c->pv_valid))) return 0;
+    SPHB_TRY(csr_refresh_mirrors(c->P, c->view(), c->st));
+    c->launches += 1;
+    c->mirrors_stale = false;
+    c->pv_valid = true;
+    return 0;
+}
+
 int do_density(sphb_ctx *c)
 {
+    SPHB_TRY(fresh_mirrors(c, false));
     const StateView S = c->view();
     {
         ProfScope ps(&c->kprof, kPfDensity, c->st);
-        SPHB_TRY(csr_density(c->P, S, c->st));
+        SPHB_TRY(csr_density(c->P, S, c->sc(), c->st));
     }
     {
         ProfScope ps(&c->kprof, kPfKgc, c->st);
         SPHB_TRY(csr_kgc(c->P, S, c->st));
     }
     c->launches += 2;
+    c->pv_valid = true;
     return 0;
 }
 
@@ -140,6 +157,13 @@ int do_neighbor(sphb_ctx *c)
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     (void)cudaStreamIsCapturing(c->st, &cap);
     const bool exact = !c->list_sized && cap == cudaStreamCaptureStatusNone;
+    // entry-ordered mirrors the build writes for the gather kernels (the state buffers swap at a cell sort: set anew)
+    c->nw.mirrors.vel = c->vel.as<double2>();
+    c->nw.mirrors.wall_vel = c->wall_vel.as<double2>();
+    c->nw.mirrors.mass = c->mass.as<double>();
+    c->nw.mirrors.inv_rho0 = c->P.inv_rho0;
+    c->nw.mirrors.e_vel = c->e_vel.as<double2>();
+    c->nw.mirrors.e_w = c->e_w.as<double2>();
     SPHB_TRY(neighbor_build(c->nw, c->pos.as<double2>(), false, exact, c->st, &c->launches, &c->kprof));
     if (exact) {
         c->list_sized = true;
@@ -148,6 +172,8 @@ int do_neighbor(sphb_ctx *c)
         SPHB_TRY(c->shear_partials.reserve(2 * (size_t)c->nw.n_tiles * sizeof(double)));
     }
     c->have_list = true;
+    c->mirrors_stale = false;   // the build wrote e_vel / e_w for the new entry order
+    c->pv_valid = false;        // (p, V) and B mirrors belong to the old one until the next density pass
     return 0;
 }
 
@@ -155,7 +181,7 @@ int do_shear(sphb_ctx *c)
 {
     ProfScope ps(&c->kprof, kPfShear, c->st);
     SPHB_TRY(csr_wall_shear(c->P, c->view(), c->sc(), c->shear_partials.as<double>(), c->st));
-    c->launches += 2;
+    c->launches += 1;
     return 0;
 }
 
@@ -178,19 +204,30 @@ int do_substep(sphb_ctx *c, double remain, double fixed_dt, bool wrap)
     return 0;
 }
 
-// first substep of an outer step: viscous + transport + dt + pressure in one gather, then continuity
-int do_fused_first_substep(sphb_ctx *c, double remain, double fixed_dt, bool wrap)
+// the time step of the outer step's first substep (m:259): published before the density pass, which evaluates the
+// half-step pressures of every row with it
+int do_publish_dt(sphb_ctx *c, double remain, double fixed_dt)
+{
+    ProfScope ps(&c->kprof, kPfTimeStep, c->st);
+    SPHB_TRY(csr_publish_dt(c->P, c->sc(), remain, fixed_dt, c->st));
+    c->launches += 1;
+    return 0;
+}
+
+// first substep of an outer step (after do_publish_dt and do_density): viscous + transport + pressure in one
+// gather, then continuity
+int do_fused_first_substep(sphb_ctx *c, bool wrap)
 {
     const StateView S = c->view();
     {
         ProfScope ps(&c->kprof, kPfForceFused, c->st);
-        SPHB_TRY(csr_force_fused(c->P, S, c->sc(), remain, fixed_dt, true, c->st));
+        SPHB_TRY(csr_force_fused(c->P, S, c->sc(), true, c->st));
     }
     {
         ProfScope ps(&c->kprof, kPfContinuity, c->st);
         SPHB_TRY(csr_continuity(c->P, S, c->sc(), wrap, true, c->st));
     }
-    c->launches += 3;
+    c->launches += 2;
     return 0;
 }
 
@@ -205,6 +242,7 @@ int ctx_bind_device(sphb_ctx *c) { return bind_device(c); }
 int ctx_plan_lists(sphb_ctx *c, double y_lo, double y_hi) { return plan_lists(c, y_lo, y_hi); }
 void ctx_drop_graphs(sphb_ctx *c) { drop_graphs(c); }
 int ctx_do_neighbor(sphb_ctx *c) { return do_neighbor(c); }
+int ctx_fresh_mirrors(sphb_ctx *c, bool need_pv) { return fresh_mirrors(c, need_pv); }
 int ctx_do_shear(sphb_ctx *c) { return do_shear(c); }
 int ctx_do_sort(sphb_ctx *c) { return do_sort(c); }
 int ctx_volumes_from_mass(sphb_ctx *c)
@@ -218,8 +256,9 @@ int ctx_volumes_from_mass(sphb_ctx *c)
 int ctx_step_physics(sphb_ctx *c, double remain)
 {
     c->h_step += 1;
+    SPHB_TRY(do_publish_dt(c, remain, 0.0));                  // m:259
     SPHB_TRY(do_density(c));                                  // m:254-255
-    SPHB_TRY(do_fused_first_substep(c, remain, 0.0, true));   // m:256-270
+    SPHB_TRY(do_fused_first_substep(c, true));                // m:256-270
     return 0;
 }
 
@@ -307,7 +346,8 @@ SPHB_API void sphb_ctx_destroy(sphb_ctx *c)
     DevBuf *all[] = {&c->pos, &c->vel, &c->vel_new, &c->wall_vel, &c->force, &c->force_prior, &c->rho, &c->p,
                      &c->drho_dt, &c->mass, &c->Vol, &c->B, &c->a_pos, &c->a_vel, &c->a_wall_vel, &c->a_force,
                      &c->a_force_prior, &c->a_rho, &c->a_p, &c->a_drho_dt, &c->a_mass, &c->a_Vol, &c->a_B,
-                     &c->scalars, &c->shear_partials, &c->stage, &c->prof, &c->rp_half};
+                     &c->scalars, &c->shear_partials, &c->stage, &c->prof, &c->rp_half,
+                     &c->e_vel, &c->e_w, &c->e_pV, &c->e_b1, &c->e_b2, &c->e_vn};
     for (DevBuf *b : all) b->release();
     for (DevBuf *b : {&c->slab.w_pos, &c->slab.w_mass, &c->slab.w_wall_vel, &c->slab.counts, &c->slab.block_tot,
                       &c->slab.pid, &c->slab.a_pid, &c->slab.sort_flag, &c->slab.sort_ptr})
@@ -366,6 +406,7 @@ SPHB_API int sphb_ctx_upload(sphb_ctx *c, const double *pos, const double *vel, 
         k_vol_from_mass<<<grid_for(n), kBlock, 0, c->st>>>(c->mass.as<double>(), c->rho.as<double>(),
                                                            c->Vol.as<double>(), nt);
     if (vel) SPHB_TRY(csr_vmax(c->P, c->vel.as<double2>(), c->sc(), c->st));
+    if (vel || wall_vel || mass || rho) c->mirrors_stale = true;   // (a standing list keeps its entry order)
     SPHB_CUDA(cudaStreamSynchronize(c->st));
     return 0;
 }
@@ -532,6 +573,7 @@ SPHB_API int sphb_ctx_transport_correction(sphb_ctx *c)
 SPHB_API int sphb_ctx_integration_verlet(sphb_ctx *c, double dt)
 {
     CTX_ENTER(true);
+    SPHB_TRY(fresh_mirrors(c, true));
     const StateView S = c->view();
     SPHB_TRY(csr_time_step(c->P, S, c->sc(), std::numeric_limits<double>::infinity(), dt, c->st));
     SPHB_TRY(csr_pressure(c->P, S, c->sc(), c->st));
@@ -597,10 +639,11 @@ SPHB_API int sphb_ctx_step(sphb_ctx *c, double remain)
     CTX_ENTER(true);
     c->h_step += 1;
     tick(c, 0);
+    SPHB_TRY(do_publish_dt(c, remain, 0.0));                                          // m:259
     SPHB_TRY(do_density(c));                                                          // m:254-255
     tick(c, 1);
     tick(c, 2);
-    SPHB_TRY(do_fused_first_substep(c, remain, 0.0, true));                           // m:256-269
+    SPHB_TRY(do_fused_first_substep(c, true));                                        // m:256-269
     tick(c, 3);
     const int si = c->prm.sort_interval;
     if (si > 0 && c->h_step % si == 0 && c->h_step != 1) SPHB_TRY(do_sort(c));        // m:272-278
@@ -687,8 +730,9 @@ namespace {
 int enqueue_outer(sphb_ctx *c, int n_inner, bool with_sort)
 {
     const double inf = std::numeric_limits<double>::infinity();
+    SPHB_TRY(do_publish_dt(c, inf, 0.0));
     SPHB_TRY(do_density(c));
-    SPHB_TRY(do_fused_first_substep(c, inf, 0.0, true));
+    SPHB_TRY(do_fused_first_substep(c, true));
     for (int s = 1; s < n_inner; ++s) SPHB_TRY(do_substep(c, inf, 0.0, true));
     if (with_sort) SPHB_TRY(do_sort(c));
     SPHB_TRY(do_neighbor(c));

@@ -38,12 +38,15 @@ struct sphb_ctx {
     DevBuf pos, vel, vel_new, wall_vel, force, force_prior, rho, p, drho_dt, mass, Vol, B;
     DevBuf a_pos, a_vel, a_wall_vel, a_force, a_force_prior, a_rho, a_p, a_drho_dt, a_mass, a_Vol, a_B;
     DevBuf scalars, shear_partials, stage, prof, rp_half;
+    DevBuf e_vel, e_w, e_pV, e_b1, e_b2, e_vn;   // entry-ordered mirrors (StateView), nw.ell_stride double2 each
     NeighborWork nw;
     SlabState slab;
     SortWork sw;
     bool have_list = false;
     bool list_sized = false;     // the ELL has been grown to the longest row seen at the first build
     bool planned = false;
+    bool mirrors_stale = false;  // rows were changed behind a standing list (upload without positions): StateView::e_* lag
+    bool pv_valid = false;       // a density pass has written the (p, V) mirror for the current list
     double y_lo = 0, y_hi = 0;
     long long h_step = 0;        // host mirror of the step counter (sort cadence, m:272)
     long long launches = 0;
@@ -85,6 +88,12 @@ struct sphb_ctx {
         S.tiles = nw.tiles.as<TileDesc>();
         S.ell_cnt = nw.ell_cnt.as<int>();
         S.ell_q = nw.ell_q.as<uint4>();
+        S.e_vel = e_vel.as<double2>();
+        S.e_w = e_w.as<double2>();
+        S.e_pV = e_pV.as<double2>();
+        S.e_b1 = e_b1.as<double2>();
+        S.e_b2 = e_b2.as<double2>();
+        S.e_vn = e_vn.as<double2>();
         S.ell_stride = nw.ell_stride;
         S.ell_cap = nw.ell_cap;
         S.tile_cap = nw.tile_cap;
@@ -101,6 +110,7 @@ int ctx_bind_device(sphb_ctx *c);
 int ctx_plan_lists(sphb_ctx *c, double y_lo, double y_hi);
 void ctx_drop_graphs(sphb_ctx *c);
 int ctx_do_neighbor(sphb_ctx *c);
+int ctx_fresh_mirrors(sphb_ctx *c, bool need_pv);   // makes StateView::e_* current (no-op inside a step)
 int ctx_do_shear(sphb_ctx *c);
 int ctx_do_sort(sphb_ctx *c);                       // m:272-278 (swaps the state buffers with their alternates)
 int ctx_volumes_from_mass(sphb_ctx *c);             // Vol = m / rho for every row (m:120)

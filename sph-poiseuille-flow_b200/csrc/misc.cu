@@ -185,9 +185,70 @@ void launch_unpack4(const Mat2 *in, double *cm, int n, cudaStream_t st)
     if (n > 0) k_unpack4<<<grid_for(n), kBlock, 0, st>>>(in, cm, n);
 }
 
+// ---- measured FP64 peak (the roofline denominator bench.py quotes for the fp64 gathers) ----------------------
+// Eight independent DFMA chains per thread, 8 warps per SM sub-partition: nothing but the FP64 pipe limits it.
+namespace {
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0,
+           x7 = x0 + 7.0;
+#pragma unroll 1
+    for (int k = 0; k < iters; ++k) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            x0 = fma(x0, a, b);
+            x1 = fma(x1, a, b);
+            x2 = fma(x2, a, b);
+            x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b);
+            x5 = fma(x5, a, b);
+            x6 = fma(x6, a, b);
+            x7 = fma(x7, a, b);
+        }
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[0] = s;   // never true: keeps the chains alive
+}
+}  // namespace
+
 }  // namespace sphb
 
 extern "C" {
+// DFMA throughput of the current device in TFLOP/s (2 flops per DFMA), best of `reps` launches of ~`iters` x 32
+// DFMAs per thread, timed with CUDA events.
+SPHB_API int sphb_fp64_peak(int iters, int reps, double *tflops)
+{
+    using namespace sphb;
+    clear_error();
+    if (!tflops || iters < 1 || reps < 1) return set_error("SPHB:arg", "bad fp64 peak arguments");
+    SPHB_TRY(ensure_device());
+    int dev = 0, sms = 0;
+    SPHB_CUDA(cudaGetDevice(&dev));
+    SPHB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double *d = nullptr;
+    SPHB_CUDA(cudaMalloc((void **)&d, sizeof(double)));
+    cudaEvent_t e0, e1;
+    SPHB_CUDA(cudaEventCreate(&e0));
+    SPHB_CUDA(cudaEventCreate(&e1));
+    const int blocks = sms * 8, threads = 256;
+    double best = 0.0;
+    for (int r = 0; r < reps + 1; ++r) {   // the first launch warms up
+        cudaEventRecord(e0, 0);
+        k_dfma_peak<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1, 0);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 32.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (r > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    SPHB_CUDA(cudaGetLastError());
+    *tflops = best;
+    return 0;
+}
 SPHB_API const char *sphb_last_error_id(void) { return sphb::last_error_id(); }
 SPHB_API const char *sphb_last_error_msg(void) { return sphb::last_error_msg(); }
 SPHB_API int sphb_version(void) { return SPHB_VERSION; }

@@ -119,6 +119,7 @@ struct NbrChan {
     int *ell_cnt;
     int tile_w, tile_cap;
     unsigned n_tiles;
+    BuildMirrors M;
 };
 
 __global__ void k_grid_init(GridDesc *g)
@@ -782,7 +783,7 @@ __device__ __forceinline__ int general_walk(const NbrParams &P, const TileDesc &
 }
 
 template <bool HALF>
-__device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__restrict__ g, const TileDesc *__restrict__ tiles,
+__device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__restrict__ g, TileDesc *tiles, BuildMirrors M,
                                                int tile_w, const int *__restrict__ cell_start,
                                                const double2 *__restrict__ snap, const int *__restrict__ cell_of,
                                                const int *__restrict__ ent_key, const double2 *__restrict__ ent_pos,
@@ -796,9 +797,11 @@ __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__re
     int *s_key = reinterpret_cast<int *>(s_xy + cap);
     const int ncx = P.ncx, ncy = g->ncy;
     __shared__ TileCellStarts s_cs;
-    tile_load(T, tiles, walk_tile_of_block(blockIdx.x, tiles_per_row(ncx, tile_w), gridDim.x));
+    const unsigned tile_id = walk_tile_of_block(blockIdx.x, tiles_per_row(ncx, tile_w), gridDim.x);
+    tile_load(T, tiles, tile_id);
     __syncthreads();
     if (!(T.flags & kTileValid)) return;
+    int walls = 0;   // does the staged neighbourhood hold a wall entry?  (kTileHasWall, read by the gather kernels)
     for (int k = threadIdx.x; k < kStageRows * (kMaxTileW + 3); k += kTileThreads) {
         const int r = k / (kMaxTileW + 3), c = k % (kMaxTileW + 3);
         const int row = T.cy0 + r - 1;
@@ -820,15 +823,19 @@ __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__re
         [&](int slot, const StageRec &r) {
             s_key[slot] = r.key;
             s_xy[slot] = r.xy;
+            walls |= (r.key >> 3) >= P.n_fluid ? 1 : 0;
         });
 #else
     SPHB_TILE_FOR_STAGED(T, e, slot)
     {
-        s_key[slot] = ent_key[e];
+        const int key = ent_key[e];
+        s_key[slot] = key;
         s_xy[slot] = ent_pos[e];
+        walls |= (key >> 3) >= P.n_fluid ? 1 : 0;
     }
 #endif
-    __syncthreads();
+    walls = __syncthreads_or(walls);
+    if (walls && threadIdx.x == 0) tiles[tile_id].flags = T.flags | kTileHasWall;
 
     const size_t stride = P.ell_stride;
     const int qcap = P.ell_cap >> 3;
@@ -851,6 +858,16 @@ __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__re
             tile_own_locate(T, v, orow, ew, slot_i);
             const int key_i = s_key[slot_i];
             const int i = key_i >> 3;
+            // entry-ordered mirrors of the row's velocity and wall weight (BuildMirrors): loaded here, stored
+            // after the walk so that the latency hides behind it
+            const bool mirror = M.e_vel != nullptr && (key_i & 3) == 0 && (size_t)ew < stride;
+            double2 mv = make_double2(0.0, 0.0);
+            double mw = -1.0;
+            if (mirror) {
+                const bool fluid = i < P.n_fluid;
+                mv = (fluid ? M.vel : M.wall_vel)[i];
+                if (!fluid) mw = M.mass[i] * M.inv_rho0;
+            }
             if ((size_t)ew >= stride) {   // more entries than list columns: reported, never written
                 atomicOr(flags, kErrCsrCap);
             } else if ((key_i & 3) != 0 || i >= P.n_fluid) {   // ghost or wall entry: not a walker
@@ -925,6 +942,10 @@ __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__re
                     t_max = max(t_max, row.count);
                 }
             }
+            if (mirror) {
+                M.e_vel[ew] = mv;
+                M.e_w[ew] = make_double2(mw, 0.0);
+            }
         }
         // ---- general walkers (periodic seam): queued for the whole CTA, so that the few warps that own
         // them do not walk them alone
@@ -968,7 +989,7 @@ __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__re
 }
 template <bool HALF>
 __global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, const GridDesc *__restrict__ g,
-                                                           const TileDesc *__restrict__ tiles, int tile_w,
+                                                           TileDesc *tiles, BuildMirrors M, int tile_w,
                                                            const int *__restrict__ cell_start,
                                                            const double2 *__restrict__ snap,
                                                            const int *__restrict__ cell_of,
@@ -977,13 +998,13 @@ __global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, cons
                                                            int *__restrict__ cnt, int *__restrict__ totals,
                                                            int *__restrict__ flags, int cap)
 {
-    walk_tile_body<HALF>(P, g, tiles, tile_w, cell_start, snap, cell_of, ent_key, ent_pos, ell_q, cnt, totals, flags, cap);
+    walk_tile_body<HALF>(P, g, tiles, M, tile_w, cell_start, snap, cell_of, ent_key, ent_pos, ell_q, cnt, totals, flags, cap);
 }
 // full lists only (the half list is the stateless MEX export)
 __global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile_batch(const NbrChan *__restrict__ chan)
 {
     const NbrChan &c = chan[blockIdx.y];
-    walk_tile_body<false>(c.P, c.g, c.tiles, c.tile_w, c.cell_start, c.snap, c.cell_of, c.ent_key, c.ent_pos, c.ell_q,
+    walk_tile_body<false>(c.P, c.g, c.tiles, c.M, c.tile_w, c.cell_start, c.snap, c.cell_of, c.ent_key, c.ent_pos, c.ell_q,
                           c.ell_cnt, c.totals, c.flags, c.tile_cap);
 }
 
@@ -1344,13 +1365,13 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
         // one CTA per tile; rows beyond the device-side n_cell_y exit at once
         if (half_only)
             k_walk_tile<true><<<w.n_tiles, kTileThreads, smem, st>>>(
-                P, g, w.tiles.as<TileDesc>(), w.tile_w, w.cell_start.as<int>(), w.snap.as<double2>(),
+                P, g, w.tiles.as<TileDesc>(), BuildMirrors(), w.tile_w, w.cell_start.as<int>(), w.snap.as<double2>(),
                 w.cell_of.as<int>(),
                 w.ent_key.as<int>(), w.ent_pos.as<double2>(), w.ell_q.as<uint4>(), w.ell_cnt.as<int>(),
                 w.totals.as<int>(), flags, w.tile_cap);
         else
             k_walk_tile<false><<<w.n_tiles, kTileThreads, smem, st>>>(
-                P, g, w.tiles.as<TileDesc>(), w.tile_w, w.cell_start.as<int>(), w.snap.as<double2>(),
+                P, g, w.tiles.as<TileDesc>(), w.mirrors, w.tile_w, w.cell_start.as<int>(), w.snap.as<double2>(),
                 w.cell_of.as<int>(),
                 w.ent_key.as<int>(), w.ent_pos.as<double2>(), w.ell_q.as<uint4>(), w.ell_cnt.as<int>(),
                 w.totals.as<int>(), flags, w.tile_cap);
@@ -1433,6 +1454,7 @@ int neighbor_batch_fill(NeighborWork &w, const double2 *pos, void *host_record, 
     c.tile_w = w.tile_w;
     c.tile_cap = w.tile_cap;
     c.n_tiles = w.n_tiles;
+    c.M = w.mirrors;
     std::memcpy(host_record, &c, sizeof(NbrChan));
     host_scan->in = c.cell_cnt;
     host_scan->out = c.cell_start;

@@ -19,6 +19,7 @@
 // max|v| reduction (warp shuffle + one atomicMax per warp) that the next dt is computed from on the
 // device (m:519-527).
 #include "ops_csr.cuh"
+#include "async_copy.cuh"
 #include "physmath.cuh"
 #include "tile.cuh"
 
@@ -146,177 +147,334 @@ __device__ __forceinline__ void tile_for_row_impl(const StateView &S, int ew, in
         }                                                                             \
     } while (0)
 
-// ---------------------------------------------------------------- P1 pass 1: sigma sums -> rho, Vol
-// staged per slot: position, and for a wall entry m_j / rho0 (ph:205), for a fluid entry -1
-template <bool PLAIN>
-__device__ __forceinline__ void density_rows(const PhysParams &P, const StateView &S, const TileDesc &T, const OwnPre &pre,
-                                             const double2 *s_xy, const double *s_w)
+__device__ __forceinline__ double half_step_rho(double rho, double drho, double dt, double rho0)
 {
-    SPHB_TILE_WALKERS(ew, si, i)
-    {
-        const double m_i = S.mass[i];
-        if (i >= P.nf) {   // wall rows: rho = rho0 (ph:214-216), Vol = m/rho0
-            S.rho[i] = P.rho0;
-            S.Vol[i] = m_i / P.rho0;
-            continue;
-        }
-        const double2 pi = s_xy[si];
-        double s_in = P.sigma;   // W(0), ph:178-181
-        double s_ct = 0.0;
-        SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
-            const Geo g = pair_geometry(pi, s_xy[sl], m, P);
-            const double W = spline_W(g.r, P);
-            if (PLAIN) {
-                s_in += W;
-            } else {
-                const double wj = s_w[sl];
-                if (wj < 0.0) s_in += W;
-                else s_ct += W * wj;
-            }
-        }));
-        double rho = s_in * P.rho0 * P.inv_sigma0;
-        rho += s_ct * P.rho0 * P.rho0 * P.inv_sigma0 / m_i;
-        if (rho <= 1e-12) rho = P.rho0;
-        S.rho[i] = rho;
-        S.Vol[i] = m_i / rho;
+    double r = rho + 0.5 * dt * drho;   // ph:858
+    if (r < 1e-10) r = rho0;            // ph:859-861
+    return r;
+}
+
+// ================================================================================================
+// The persistent tile pipeline of the four hot gather kernels (density, KGC, fused forces, continuity).
+//
+// A CTA takes tiles cta, cta + n_ctas, ... and keeps TWO staging buffers: while its threads walk the rows of
+// one tile out of one buffer, the copy engine fills the other with the next tile's neighbourhood.  That is
+// possible because everything a tile stages lives in ENTRY order (StateView::e_*, written by the kernel that
+// produces the field, at the walker's own entry index): per staged cell row one contiguous range per field, moved by
+// cp.async.bulk and signalled on an mbarrier (async_copy.cuh) -- no thread gathers through ent_key, and the
+// dependent-load chain that used to open every tile (descriptor -> ent_key -> field -> STS -> barrier) is gone.
+// The next tile's descriptor travels one tile further ahead in registers, the walkers' row heads one tile ahead.
+// Tiles on the periodic seam hold ghost entries, which have no mirror values: they are staged through ent_key as
+// before (stage_sync; first and last tile of a tile row).
+//
+// A kernel K provides: kFields (16-byte fields per slot), bulk_fields(T), src(S, f), dummy(buf, cap, slot),
+// stage_sync(S, T, buf, cap) -> "holds wall entries", rows<PLAIN>(S, T, pre, buf, cap).
+// ================================================================================================
+// The seam-tile staging and the row loops of tiles with wall entries run for a few percent of the tiles.  A/B switch:
+// SPHB_COLD_INLINE=0 keeps them out of line (off the plain path's register allocation, at the price of a stack frame).
+#ifndef SPHB_COLD_INLINE
+#define SPHB_COLD_INLINE 1   // measured (r2 call 4): out of line costs a 0.5 KB stack frame for the kernel object, +20 % per kernel
+#endif
+#if SPHB_COLD_INLINE
+#define SPHB_COLD __forceinline__
+#else
+#define SPHB_COLD __noinline__
+#endif
+
+template <class K>
+__device__ __forceinline__ void stage_bulk(const K &k, const StateView &S, const TileDesc &T, unsigned char *buf, int cap,
+                                           mbar_t *bar)
+{
+    if ((T.flags & (kTileValid | kTileSeam)) != kTileValid) return;
+    if (threadIdx.x >= 32) return;
+    const int lane = (int)threadIdx.x;
+    const int nf = k.bulk_fields(T);
+    if (lane == 0) {
+        int entries = 0;
+#pragma unroll
+        for (int r = 0; r < kStageRows; ++r) entries += T.seg[3 * r].e - T.seg[3 * r].b;
+        mbar_arrive_expect_tx(bar, (unsigned)(entries * nf) * (unsigned)sizeof(double2));
+        k.dummy(buf, cap, T.n_staged);
+    }
+    __syncwarp();
+    for (int c = lane; c < kStageRows * nf; c += 32) {
+        const int r = c / nf, f = c - r * nf;
+        const TileSeg sg = T.seg[3 * r];
+        const int n = sg.e - sg.b;
+        if (n > 0)
+            bulk_copy_g2s(buf + ((size_t)f * cap + sg.off) * sizeof(double2), k.src(S, f) + sg.b,
+                          (unsigned)n * (unsigned)sizeof(double2), bar);
     }
 }
 
-__device__ __forceinline__ void density_tile(PhysParams P, StateView S)
+template <class K>
+__device__ __forceinline__ void run_tiles(K &k, const StateView &S, unsigned cta, unsigned n_ctas)
 {
-    load_counts(P);
-    SPHB_TILE_BEGIN();
-    const OwnPre pre = tile_prefetch_own(S, T);
-    double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
-    double *s_w = reinterpret_cast<double *>(s_xy + cap);
-    int walls = 0;
-#if SPHB_FLAT_STAGING
-    struct Rec {
-        double2 xy;
-        double m;
-        int j;
-    };
-    tile_stage_flat(
-        T,
-        [&](int e) {
-            Rec r;
-            r.j = S.ent_key[e] >> 3;
-            r.xy = S.ent_pos[e];
-            r.m = S.mass[r.j];
-            return r;
-        },
-        [&](int slot, const Rec &r) {
-            s_xy[slot] = r.xy;
-            if (r.j < P.nf) {
-                s_w[slot] = -1.0;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // three descriptor slots: the one of tile k + 1 is written at the top of iteration k, while slower threads may
+    // still be reading tile k - 1's in their row loops (no barrier in between)
+    __shared__ TileDesc Ts[3];
+    __shared__ __align__(8) mbar_t bars[2];
+    constexpr int kDescWords = (int)(sizeof(TileDesc) / 16);
+    const int cap = S.tile_cap;
+    const size_t buf_bytes = (size_t)cap * K::kFields * sizeof(double2);
+    const unsigned n_tiles = S.n_tiles;
+    if (cta >= n_tiles) return;
+    const int tid = (int)threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1u);
+        mbar_init(&bars[1], 1u);
+        mbar_init_fence();
+    }
+    int4 dnext = make_int4(0, 0, 0, 0);   // descriptor of the tile after the next one (threads 0 .. kDescWords-1)
+    if (tid < kDescWords) {
+        reinterpret_cast<int4 *>(&Ts[0])[tid] = reinterpret_cast<const int4 *>(S.tiles + cta)[tid];
+        if (cta + n_ctas < n_tiles) dnext = reinterpret_cast<const int4 *>(S.tiles + cta + n_ctas)[tid];
+    }
+    __syncthreads();
+    stage_bulk(k, S, Ts[0], smem_raw, cap, &bars[0]);
+    OwnPre pre = tile_prefetch_own(S, Ts[0]);
+    unsigned parity = 0u;   // bit b = phase of bars[b] to wait for next
+    int cur = 0, dcur = 0;
+    for (unsigned t = cta; t < n_tiles; t += n_ctas, cur ^= 1, dcur = dcur == 2 ? 0 : dcur + 1) {
+        const TileDesc &T = Ts[dcur];
+        TileDesc &Tn = Ts[dcur == 2 ? 0 : dcur + 1];
+        unsigned char *buf = smem_raw + (size_t)cur * buf_bytes;
+        unsigned char *bufn = smem_raw + (size_t)(cur ^ 1) * buf_bytes;
+        const unsigned tn = t + n_ctas;
+        const bool has_next = tn < n_tiles;
+        if (tid < kDescWords) {
+            if (has_next) reinterpret_cast<int4 *>(&Tn)[tid] = dnext;
+            if (tn + n_ctas < n_tiles) dnext = reinterpret_cast<const int4 *>(S.tiles + tn + n_ctas)[tid];
+        }
+        async_proxy_fence();   // this thread's stores into the other buffer (a seam tile staged by hand) before the copies below
+        __syncthreads();       // Tn is visible; every thread has left the rows of the previous tile: the other buffer is free
+        OwnPre pre_next;
+        pre_next.key = 3;
+        pre_next.n = 0;
+        pre_next.q0 = make_uint4(0u, 0u, 0u, 0u);
+        if (has_next) {
+            stage_bulk(k, S, Tn, bufn, cap, &bars[cur ^ 1]);
+            pre_next = tile_prefetch_own(S, Tn);
+        }
+        if (T.flags & kTileValid) {
+            if (!(T.flags & kTileSeam)) {
+                mbar_wait(&bars[cur], (parity >> cur) & 1u);
+                parity ^= 1u << cur;
+                if (T.flags & kTileHasWall) k.rows_cold(S, T, pre, buf, cap);
+                else k.template rows<true>(S, T, pre, buf, cap);
             } else {
-                s_w[slot] = r.m * P.inv_rho0;
-                walls = 1;
+                (void)k.stage_sync(S, T, buf, cap);
+                __syncthreads();
+                k.rows_cold(S, T, pre, buf, cap);
             }
-        });
-#else
-    SPHB_TILE_FOR_STAGED(T, e, slot)
+        }
+        pre = pre_next;
+    }
+}
+
+// fields of a staging buffer: field f of slot s at buf + (f * cap + s) * 16
+__device__ __forceinline__ double2 *field(unsigned char *buf, int cap, int f)
+{
+    return reinterpret_cast<double2 *>(buf) + (size_t)f * cap;
+}
+
+// ---------------------------------------------------------------- P1 pass 1: sigma sums -> rho, Vol
+// staged per slot: position; tiles with wall entries also (m_j / rho0, 0) for a wall entry (ph:205), (-1, 0) for a
+// fluid entry.  Also writes the entry-ordered (half-step pressure, volume) pair the later kernels stage.
+struct DensityK {
+    static constexpr int kFields = 2;
+    PhysParams P;
+    double dt;
+    __device__ __forceinline__ int bulk_fields(const TileDesc &T) const { return (T.flags & kTileHasWall) ? 2 : 1; }
+    __device__ __forceinline__ const double2 *src(const StateView &S, int f) const { return f == 0 ? S.ent_pos : S.e_w; }
+    __device__ __forceinline__ void dummy(unsigned char *buf, int cap, int slot) const
     {
-        const int j = S.ent_key[e] >> 3;
-        s_xy[slot] = S.ent_pos[e];
-        if (j < P.nf) {
-            s_w[slot] = -1.0;
-        } else {
-            s_w[slot] = S.mass[j] * P.inv_rho0;
-            walls = 1;
+        field(buf, cap, 0)[slot] = make_double2(kDummyCoord, kDummyCoord);
+        field(buf, cap, 1)[slot] = make_double2(-1.0, 0.0);
+    }
+    __device__ SPHB_COLD int stage_sync(const StateView &S, const TileDesc &T, unsigned char *buf, int cap) const
+    {
+        double2 *s_xy = field(buf, cap, 0), *s_w = field(buf, cap, 1);
+        struct Rec {
+            double2 xy;
+            double m;
+            int j;
+        };
+        const PhysParams &Pr = P;
+        tile_stage_flat(
+            T,
+            [&](int e) {
+                Rec r;
+                r.j = S.ent_key[e] >> 3;
+                r.xy = S.ent_pos[e];
+                r.m = S.mass[r.j];
+                return r;
+            },
+            [&](int slot, const Rec &r) {
+                s_xy[slot] = r.xy;
+                s_w[slot] = make_double2(r.j < Pr.nf ? -1.0 : r.m * Pr.inv_rho0, 0.0);
+            });
+        if (threadIdx.x == 0) dummy(buf, cap, T.n_staged);
+        return 1;
+    }
+    template <bool PLAIN>
+    __device__ __forceinline__ void rows(const StateView &S, const TileDesc &T, const OwnPre &pre, unsigned char *buf, int cap)
+    {
+        const double2 *s_xy = field(buf, cap, 0), *s_w = field(buf, cap, 1);
+        SPHB_TILE_WALKERS(ew, si, i)
+        {
+            const double m_i = S.mass[i];
+            if (i >= P.nf) {   // wall rows: rho = rho0 (ph:214-216), Vol = m/rho0
+                const double V = m_i / P.rho0;
+                S.rho[i] = P.rho0;
+                S.Vol[i] = V;
+                S.e_pV[ew] = make_double2(0.0, -V);
+                continue;
+            }
+            const double drho_i = S.drho_dt[i];
+            const double2 pi = s_xy[si];
+            double s_in = P.sigma;   // W(0), ph:178-181
+            double s_ct = 0.0;
+            SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
+                const Geo g = pair_geometry(pi, s_xy[sl], m, P);
+                const double W = spline_W(g.r, P);
+                if (PLAIN) {
+                    s_in += W;
+                } else {
+                    const double wj = s_w[sl].x;
+                    if (wj < 0.0) s_in += W;
+                    else s_ct += W * wj;
+                }
+            }));
+            double rho = s_in * P.rho0 * P.inv_sigma0;
+            rho += s_ct * P.rho0 * P.rho0 * P.inv_sigma0 / m_i;
+            if (rho <= 1e-12) rho = P.rho0;
+            const double V = m_i / rho;
+            S.rho[i] = rho;
+            S.Vol[i] = V;
+            // half-step pressure of this row for the force kernel's neighbours (ph:857-862)
+            const double rho_h = half_step_rho(rho, drho_i, dt, P.rho0);
+            S.e_pV[ew] = make_double2(P.p0 * (rho_h / P.rho0 - 1.0), V);
         }
     }
-#endif
-    if (threadIdx.x == 0) {
-        s_xy[T.n_staged] = make_double2(kDummyCoord, kDummyCoord);
-        s_w[T.n_staged] = -1.0;
+    __device__ SPHB_COLD void rows_cold(const StateView &S, const TileDesc &T, const OwnPre &pre, unsigned char *buf, int cap)
+    {
+        rows<false>(S, T, pre, buf, cap);
     }
-#define SPHB_CALL(plain) density_rows<plain>(P, S, T, pre, s_xy, s_w)
-    SPHB_TILE_DISPATCH(walls, SPHB_CALL);
-#undef SPHB_CALL
+};
+
+__device__ __forceinline__ void density_tiles(PhysParams P, const StateView &S, const DevScalars *sc, unsigned cta, unsigned n_ctas)
+{
+    load_counts(P);
+    DensityK k;
+    k.P = P;
+    k.dt = sc->dt;
+    run_tiles(k, S, cta, n_ctas);
 }
-__global__ void __launch_bounds__(kTileThreads) k_density(PhysParams P, StateView S) { density_tile(P, S); }
-__global__ void __launch_bounds__(kTileThreads, 9) k_density_batch(const BatchChan *__restrict__ chan)
+#ifndef SPHB_DENS_MINCTAS
+#define SPHB_DENS_MINCTAS 6   // (r2 calls 3-4: 8 -> 150 B of spills, 53 us; 6 -> 43 us; 5 -> 44 us)
+#endif
+__global__ void __launch_bounds__(kTileThreads, SPHB_DENS_MINCTAS) k_density(PhysParams P, StateView S, const DevScalars *sc)
+{
+    density_tiles(P, S, sc, blockIdx.x, gridDim.x);
+}
+__global__ void __launch_bounds__(kTileThreads, SPHB_DENS_MINCTAS) k_density_batch(const BatchChan *__restrict__ chan)
 {
     const BatchChan &c = chan[blockIdx.y];
-    density_tile(c.P, c.S);
+    density_tiles(c.P, c.S, c.sc, blockIdx.x, gridDim.x);
 }
 
 // ---------------------------------------------------------------- P1 pass 2: A -> B (ph:239-366)
-template <bool PLAIN>
-__device__ __forceinline__ void kgc_rows(const PhysParams &P, const StateView &S, const TileDesc &T, const OwnPre &pre,
-                                         const double2 *s_xy, const double *s_V)
-{
-    SPHB_TILE_WALKERS(ew, si, i)
+// staged per slot: position, (-, volume).  Also writes the entry-ordered rows of B.
+struct KgcK {
+    static constexpr int kFields = 2;
+    PhysParams P;
+    __device__ __forceinline__ int bulk_fields(const TileDesc &) const { return 2; }
+    __device__ __forceinline__ const double2 *src(const StateView &S, int f) const { return f == 0 ? S.ent_pos : S.e_pV; }
+    __device__ __forceinline__ void dummy(unsigned char *buf, int cap, int slot) const
     {
-        Mat2 B;
-        B.b11 = 1.0;
-        B.b12 = 0.0;
-        B.b21 = 0.0;
-        B.b22 = 1.0;
-        if (i < P.nf) {
-            const double2 pi = s_xy[si];
-            double a11 = 0.0, a12 = 0.0, a21 = 0.0, a22 = 0.0;
-            SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
-                const Geo g = pair_geometry(pi, s_xy[sl], m, P);
-                const double f = spline_dW(g.r, P) * s_V[sl];
-                const double fx = f * g.ex, fy = f * g.ey;
-                a11 -= g.dx * fx;
-                a12 -= g.dx * fy;
-                a21 -= g.dy * fx;
-                a22 -= g.dy * fy;
-            }));
-            kgc_from_A(a11, a12, a21, a22, B.b11, B.b12, B.b21, B.b22);
-        }
-        S.B[i] = B;
+        field(buf, cap, 0)[slot] = make_double2(kDummyCoord, kDummyCoord);
+        field(buf, cap, 1)[slot] = make_double2(0.0, 0.0);
     }
-}
+    __device__ SPHB_COLD int stage_sync(const StateView &S, const TileDesc &T, unsigned char *buf, int cap) const
+    {
+        double2 *s_xy = field(buf, cap, 0), *s_pV = field(buf, cap, 1);
+        struct Rec {
+            double2 xy;
+            double V;
+        };
+        tile_stage_flat(
+            T,
+            [&](int e) {
+                Rec r;
+                r.xy = S.ent_pos[e];
+                r.V = S.Vol[S.ent_key[e] >> 3];
+                return r;
+            },
+            [&](int slot, const Rec &r) {
+                s_xy[slot] = r.xy;
+                s_pV[slot] = make_double2(0.0, r.V);
+            });
+        if (threadIdx.x == 0) dummy(buf, cap, T.n_staged);
+        return 1;
+    }
+    template <bool PLAIN>
+    __device__ __forceinline__ void rows(const StateView &S, const TileDesc &T, const OwnPre &pre, unsigned char *buf, int cap)
+    {
+        const double2 *s_xy = field(buf, cap, 0), *s_pV = field(buf, cap, 1);
+        SPHB_TILE_WALKERS(ew, si, i)
+        {
+            Mat2 B;
+            B.b11 = 1.0;
+            B.b12 = 0.0;
+            B.b21 = 0.0;
+            B.b22 = 1.0;
+            if (i < P.nf) {
+                const double2 pi = s_xy[si];
+                double a11 = 0.0, a12 = 0.0, a21 = 0.0, a22 = 0.0;
+                SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
+                    const Geo g = pair_geometry(pi, s_xy[sl], m, P);
+                    // walls take the same formula (ph:293-309); their staged volume carries the wall sign
+                    const double Vs = s_pV[sl].y;
+                    const double f = spline_dW(g.r, P) * (PLAIN ? Vs : fabs(Vs));
+                    const double fx = f * g.ex, fy = f * g.ey;
+                    a11 -= g.dx * fx;
+                    a12 -= g.dx * fy;
+                    a21 -= g.dy * fx;
+                    a22 -= g.dy * fy;
+                }));
+                kgc_from_A(a11, a12, a21, a22, B.b11, B.b12, B.b21, B.b22);
+                S.e_b1[ew] = make_double2(B.b11, B.b12);
+                S.e_b2[ew] = make_double2(B.b21, B.b22);
+            }
+            S.B[i] = B;
+        }
+    }
+    __device__ SPHB_COLD void rows_cold(const StateView &S, const TileDesc &T, const OwnPre &pre, unsigned char *buf, int cap)
+    {
+        rows<false>(S, T, pre, buf, cap);
+    }
+};
 
-__device__ __forceinline__ void kgc_tile(PhysParams P, StateView S)
+__device__ __forceinline__ void kgc_tiles(PhysParams P, const StateView &S, unsigned cta, unsigned n_ctas)
 {
     load_counts(P);
-    SPHB_TILE_BEGIN();
-    const OwnPre pre = tile_prefetch_own(S, T);
-    double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
-    double *s_V = reinterpret_cast<double *>(s_xy + cap);
-#if SPHB_FLAT_STAGING
-    struct Rec {
-        double2 xy;
-        double V;
-    };
-    tile_stage_flat(
-        T,
-        [&](int e) {
-            Rec r;
-            r.xy = S.ent_pos[e];
-            r.V = S.Vol[S.ent_key[e] >> 3];
-            return r;
-        },
-        [&](int slot, const Rec &r) {
-            s_xy[slot] = r.xy;
-            s_V[slot] = r.V;
-        });
-#else
-    SPHB_TILE_FOR_STAGED(T, e, slot)
-    {
-        s_xy[slot] = S.ent_pos[e];
-        s_V[slot] = S.Vol[S.ent_key[e] >> 3];
-    }
-#endif
-    if (threadIdx.x == 0) {
-        s_xy[T.n_staged] = make_double2(kDummyCoord, kDummyCoord);
-        s_V[T.n_staged] = 0.0;
-    }
-    // walls take the same formula here (ph:293-309): only the seam needs the image shift
-#define SPHB_CALL(plain) kgc_rows<plain>(P, S, T, pre, s_xy, s_V)
-    SPHB_TILE_DISPATCH(0, SPHB_CALL);
-#undef SPHB_CALL
+    KgcK k;
+    k.P = P;
+    run_tiles(k, S, cta, n_ctas);
 }
-__global__ void __launch_bounds__(kTileThreads) k_kgc(PhysParams P, StateView S) { kgc_tile(P, S); }
-__global__ void __launch_bounds__(kTileThreads, 8) k_kgc_batch(const BatchChan *__restrict__ chan)
+#ifndef SPHB_KGC_MINCTAS
+#define SPHB_KGC_MINCTAS 6    // (8 -> spills, 57 us; 6 -> 51.5 us)
+#endif
+__global__ void __launch_bounds__(kTileThreads, SPHB_KGC_MINCTAS) k_kgc(PhysParams P, StateView S)
+{
+    kgc_tiles(P, S, blockIdx.x, gridDim.x);
+}
+__global__ void __launch_bounds__(kTileThreads, SPHB_KGC_MINCTAS) k_kgc_batch(const BatchChan *__restrict__ chan)
 {
     const BatchChan &c = chan[blockIdx.y];
-    kgc_tile(c.P, c.S);
+    kgc_tiles(c.P, c.S, blockIdx.x, gridDim.x);
 }
 
 // ---------------------------------------------------------------- P2 + P3 fused (ph:469-545, 636-710)
@@ -431,13 +589,6 @@ __global__ void __launch_bounds__(kTileThreads) k_visc_transport(PhysParams P, S
 #undef SPHB_CALL
 }
 
-__device__ __forceinline__ double half_step_rho(double rho, double drho, double dt, double rho0)
-{
-    double r = rho + 0.5 * dt * drho;   // ph:858
-    if (r < 1e-10) r = rho0;            // ph:859-861
-    return r;
-}
-
 // ---------------------------------------------------------------- dt on the device (m:519-527) and the
 // half-step density / pressure of every particle (ph:857-862), which the pressure gather reads per
 // neighbour.  Every thread derives the same dt from the device vmax; thread 0 publishes it.
@@ -491,6 +642,7 @@ __device__ __forceinline__ void pressure_rows(const PhysParams &P, const StateVi
         if (i >= P.nf) {   // wall rows: force 0, velocity 0 (ph:958-962, 1405-1408)
             S.force[i] = make_double2(0.0, 0.0);
             S.vel_new[i] = make_double2(0.0, 0.0);
+            S.e_vn[ew] = S.wall_vel[i];   // what the continuity pass stages of a wall neighbour
             continue;
         }
         const double2 pi = s_xy[si];
@@ -535,6 +687,7 @@ __device__ __forceinline__ void pressure_rows(const PhysParams &P, const StateVi
         vn.x = vi.x + (fp.x + fx) / m_i * dt;   // ph:1402-1403
         vn.y = vi.y + (fp.y + fy) / m_i * dt;
         S.vel_new[i] = vn;
+        S.e_vn[ew] = vn;
         double2 x = S.pos[i];
         x.x += 0.5 * dt * vi.x;   // ph:863-864
         x.y += 0.5 * dt * vi.y;
@@ -603,8 +756,10 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_pressure_batch(const BatchC
 // (virtual wall pressure ph:929-934 and the kick ph:1402-1403).  One row walk therefore serves all
 // three operators: 80 B gathered per neighbour once instead of 72 B + 88 B.  Walkers with wall
 // neighbours take a second, short walk over their wall entries once F_prior is complete.  The time
-// step (m:519-527) is derived by every CTA from the device vmax, and the neighbours' half-step (rho, p)
-// (ph:857-862) is evaluated while staging, so there is no separate dt / half-step launch.
+// step (m:519-527) is published by k_publish_dt before the density pass, which evaluates every row's
+// half-step pressure (ph:857-862) into the entry-ordered (p, V) pairs this kernel stages.
+// staged per slot: position, velocity (wall entry: wall velocity), (half-step pressure, volume; volume < 0 = wall
+// entry), the two rows of B.
 __device__ __forceinline__ double device_dt(const PhysParams &P, const DevScalars *sc, double remain, double fixed_dt)
 {
     if (fixed_dt > 0.0) return fixed_dt;
@@ -615,208 +770,207 @@ __device__ __forceinline__ double device_dt(const PhysParams &P, const DevScalar
     return fmax(fmin(fmin(dt_a, dt_v), fmin(dt_b, remain)), 1e-12);
 }
 
-template <bool PLAIN>
-__device__ __forceinline__ void force_rows(const PhysParams &P, const StateView &S, const TileDesc &T, const OwnPre &pre,
-                                           const double2 *s_xy, const double2 *s_v, const double2 *s_pV,
-                                           const double2 *s_b1, const double2 *s_b2, double dt, int add_gravity)
-{
-    const double h001 = 0.01 * P.h;
-    const double rho_per_p = P.rho0 / P.p0;
-    SPHB_TILE_WALKERS(ew, si, i)
+struct ForceK {
+    static constexpr int kFields = 5;
+    PhysParams P;
+    double dt;
+    int add_gravity;
+    __device__ __forceinline__ int bulk_fields(const TileDesc &) const { return 5; }
+    __device__ __forceinline__ const double2 *src(const StateView &S, int f) const
     {
-        if (i >= P.nf) {   // wall rows: forces 0, velocity 0 (ph:958-962, 1405-1408)
-            S.force_prior[i] = make_double2(0.0, 0.0);
-            S.force[i] = make_double2(0.0, 0.0);
-            S.vel_new[i] = make_double2(0.0, 0.0);
-            continue;
-        }
-        const double2 pi = s_xy[si];
-        const double2 vi = s_v[si];
-        const double2 bi1 = s_b1[si], bi2 = s_b2[si];
-        const double2 pVi = s_pV[si];                      // (half-step p, volume)
-        const double Vi = pVi.y, m_i = S.mass[i];
-        const double p_i = pVi.x;
-        const double rho_i = half_step_rho(S.rho[i], S.drho_dt[i], dt, P.rho0);   // ph:857-861 (own row: exact)
-        double ax = 0.0, ay = 0.0, ix = 0.0, iy = 0.0, fx = 0.0, fy = 0.0;
-        bool has_wall = false;
-        SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
-            const Geo g = pair_geometry(pi, s_xy[sl], m, P);
-            const double ex = g.ex, ey = g.ey;
-            const double2 pVj = s_pV[sl];
-            const double Vs = pVj.y;
-            const double gj = spline_dW(g.r, P) * (PLAIN ? Vs : fabs(Vs));
-            const double2 vj = s_v[sl];
-            const double dvx = vi.x - vj.x, dvy = vi.y - vj.y;
-            const double rinv = fast_rcp(g.r + h001);
-            if (PLAIN || Vs >= 0.0) {
-                const double2 bj1 = s_b1[sl], bj2 = s_b2[sl];
-                const double tx = (bi1.x + bj1.x) * ex + (bi1.y + bj1.y) * ey;
-                const double ty = (bi2.x + bj2.x) * ex + (bi2.y + bj2.y) * ey;
-                // viscous (ph:502-520) and transport (ph:667-685)
-                const double cf = (ex * tx + ey * ty) * P.mu * gj * rinv;
-                ax += cf * dvx;
-                ay += cf * dvy;
-                ix -= gj * tx;
-                iy -= gj * ty;
-                // pressure with Riemann dissipation (ph:891-925)
-                // neighbour's half-step density from its staged pressure: rho = rho0 (1 + p / p0), the EOS
-                // (ph:862) inverted -- 8 B less to gather per neighbour, ~1 ulp from the stored value
-                const double rho_bar = 0.5 * (rho_i + fma(pVj.x, rho_per_p, P.rho0));
-                const double du = dvx * ex + dvy * ey;                          // u_l - u_r
-                const double beta = fmin(3.0 * fmax(du, 0.0), P.c_f);           // ph:1121-1129
-                const double p_avg = 0.5 * (p_i + pVj.x);
-                const double p_star = p_avg + 0.5 * beta * rho_bar * du;
-                const double pg = 0.5 * (p_avg + p_star) * gj;
-                fx -= pg * tx;
-                fy -= pg * ty;
-            } else {
-                const double tx = bi1.x * ex + bi1.y * ey;
-                const double ty = bi2.x * ex + bi2.y * ey;
-                const double cf = 4.0 * (ex * tx + ey * ty) * P.mu * gj * rinv;   // no-slip mirror, ph:526
-                ax += cf * dvx;
-                ay += cf * dvy;
-                ix -= 2.0 * gj * tx;                                              // ph:690
-                iy -= 2.0 * gj * ty;
-                has_wall = true;
+        return f == 0 ? S.ent_pos : (f == 1 ? S.e_vel : (f == 2 ? S.e_pV : (f == 3 ? S.e_b1 : S.e_b2)));
+    }
+    __device__ __forceinline__ void dummy(unsigned char *buf, int cap, int slot) const
+    {
+        field(buf, cap, 0)[slot] = make_double2(kDummyCoord, kDummyCoord);
+#pragma unroll
+        for (int f = 1; f < 5; ++f) field(buf, cap, f)[slot] = make_double2(0.0, 0.0);
+    }
+    __device__ SPHB_COLD int stage_sync(const StateView &S, const TileDesc &T, unsigned char *buf, int cap) const
+    {
+        double2 *s_xy = field(buf, cap, 0), *s_v = field(buf, cap, 1), *s_pV = field(buf, cap, 2), *s_b1 = field(buf, cap, 3),
+                *s_b2 = field(buf, cap, 4);
+        struct Rec {
+            double2 xy, v;
+            double4 B;
+            double V, rho, drho;
+            int j;
+        };
+        const PhysParams &Pr = P;
+        const double dt_ = dt;
+        tile_stage_flat(
+            T,
+            [&](int e) {
+                Rec r;
+                r.j = S.ent_key[e] >> 3;
+                r.xy = S.ent_pos[e];
+                r.V = S.Vol[r.j];
+                r.v = (r.j < Pr.nf ? S.vel : S.wall_vel)[r.j];   // a wall entry stages its wall velocity
+                r.rho = S.rho[r.j];                              // (wall rows hold valid values too; unused)
+                r.drho = S.drho_dt[r.j];
+                r.B = *reinterpret_cast<const double4 *>(&S.B[r.j]);
+                return r;
+            },
+            [&](int slot, const Rec &r) {
+                s_xy[slot] = r.xy;
+                s_v[slot] = r.v;
+                if (r.j < Pr.nf) {
+                    const double rho_h = half_step_rho(r.rho, r.drho, dt_, Pr.rho0);
+                    s_pV[slot] = make_double2(Pr.p0 * (rho_h / Pr.rho0 - 1.0), r.V);   // ph:862
+                    s_b1[slot] = make_double2(r.B.x, r.B.y);
+                    s_b2[slot] = make_double2(r.B.z, r.B.w);
+                } else {
+                    s_pV[slot] = make_double2(0.0, -r.V);
+                }
+            });
+        if (threadIdx.x == 0) dummy(buf, cap, T.n_staged);
+        return 1;
+    }
+    template <bool PLAIN>
+    __device__ __forceinline__ void rows(const StateView &S, const TileDesc &T, const OwnPre &pre, unsigned char *buf, int cap)
+    {
+        const double2 *s_xy = field(buf, cap, 0), *s_v = field(buf, cap, 1), *s_pV = field(buf, cap, 2),
+                      *s_b1 = field(buf, cap, 3), *s_b2 = field(buf, cap, 4);
+        const double h001 = 0.01 * P.h;
+        const double rho_per_p = P.rho0 / P.p0;
+        SPHB_TILE_WALKERS(ew, si, i)
+        {
+            if (i >= P.nf) {   // wall rows: forces 0, velocity 0 (ph:958-962, 1405-1408)
+                S.force_prior[i] = make_double2(0.0, 0.0);
+                S.force[i] = make_double2(0.0, 0.0);
+                S.vel_new[i] = make_double2(0.0, 0.0);
+                S.e_vn[ew] = S.wall_vel[i];   // what the continuity pass reads of a wall neighbour (ph:1101-1102)
+                continue;
             }
-        }));
-        double2 fp;
-        fp.x = ax * Vi;
-        fp.y = ay * Vi;
-        if (add_gravity) fp.x += m_i * P.g;   // m:392
-        S.force_prior[i] = fp;
-        if (!PLAIN && has_wall) {
-            // virtual wall pressure needs the complete F_prior of the walker (ph:929-947)
-            const double inv_m = 1.0 / m_i;
-            const double wax = fp.x * inv_m, way = fp.y * inv_m;
-            SPHB_ROW(true, ([&](const int sl, const int m) {
-                const double Vs = s_pV[sl].y;
-                if (Vs >= 0.0) return;
+            const double2 pi = s_xy[si];
+            const double2 vi = s_v[si];
+            const double2 bi1 = s_b1[si], bi2 = s_b2[si];
+            const double2 pVi = s_pV[si];                      // (half-step p, volume)
+            const double Vi = pVi.y, m_i = S.mass[i];
+            const double p_i = pVi.x;
+            const double rho_i = half_step_rho(S.rho[i], S.drho_dt[i], dt, P.rho0);   // ph:857-861 (own row: exact)
+            double ax = 0.0, ay = 0.0, ix = 0.0, iy = 0.0, fx = 0.0, fy = 0.0;
+            bool has_wall = false;
+            SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
                 const Geo g = pair_geometry(pi, s_xy[sl], m, P);
                 const double ex = g.ex, ey = g.ey;
-                const double gj = spline_dW(g.r, P) * fabs(Vs);
-                const double ext = -(wax * ex + way * ey);
-                const double pw = p_i + rho_i * g.r * fmax(0.0, ext);   // ph:934
-                const double pg = (p_i + pw) * gj;
-                fx -= pg * (bi1.x * ex + bi1.y * ey);
-                fy -= pg * (bi2.x * ex + bi2.y * ey);
+                const double2 pVj = s_pV[sl];
+                const double Vs = pVj.y;
+                const double gj = spline_dW(g.r, P) * (PLAIN ? Vs : fabs(Vs));
+                const double2 vj = s_v[sl];
+                const double dvx = vi.x - vj.x, dvy = vi.y - vj.y;
+                const double rinv = fast_rcp(g.r + h001);
+                if (PLAIN || Vs >= 0.0) {
+                    const double2 bj1 = s_b1[sl], bj2 = s_b2[sl];
+                    const double tx = (bi1.x + bj1.x) * ex + (bi1.y + bj1.y) * ey;
+                    const double ty = (bi2.x + bj2.x) * ex + (bi2.y + bj2.y) * ey;
+                    // viscous (ph:502-520) and transport (ph:667-685)
+                    const double cf = (ex * tx + ey * ty) * P.mu * gj * rinv;
+                    ax += cf * dvx;
+                    ay += cf * dvy;
+                    ix -= gj * tx;
+                    iy -= gj * ty;
+                    // pressure with Riemann dissipation (ph:891-925)
+                    // neighbour's half-step density from its staged pressure: rho = rho0 (1 + p / p0), the EOS
+                    // (ph:862) inverted -- 8 B less to gather per neighbour, ~1 ulp from the stored value
+                    const double rho_bar = 0.5 * (rho_i + fma(pVj.x, rho_per_p, P.rho0));
+                    const double du = dvx * ex + dvy * ey;                          // u_l - u_r
+                    const double beta = fmin(3.0 * fmax(du, 0.0), P.c_f);           // ph:1121-1129
+                    const double p_avg = 0.5 * (p_i + pVj.x);
+                    const double p_star = p_avg + 0.5 * beta * rho_bar * du;
+                    const double pg = 0.5 * (p_avg + p_star) * gj;
+                    fx -= pg * tx;
+                    fy -= pg * ty;
+                } else {
+                    const double tx = bi1.x * ex + bi1.y * ey;
+                    const double ty = bi2.x * ex + bi2.y * ey;
+                    const double cf = 4.0 * (ex * tx + ey * ty) * P.mu * gj * rinv;   // no-slip mirror, ph:526
+                    ax += cf * dvx;
+                    ay += cf * dvy;
+                    ix -= 2.0 * gj * tx;                                              // ph:690
+                    iy -= 2.0 * gj * ty;
+                    has_wall = true;
+                }
             }));
+            double2 fp;
+            fp.x = ax * Vi;
+            fp.y = ay * Vi;
+            if (add_gravity) fp.x += m_i * P.g;   // m:392
+            S.force_prior[i] = fp;
+            if (!PLAIN && has_wall) {
+                // virtual wall pressure needs the complete F_prior of the walker (ph:929-947)
+                const double inv_m = 1.0 / m_i;
+                const double wax = fp.x * inv_m, way = fp.y * inv_m;
+                SPHB_ROW(true, ([&](const int sl, const int m) {
+                    const double Vs = s_pV[sl].y;
+                    if (Vs >= 0.0) return;
+                    const Geo g = pair_geometry(pi, s_xy[sl], m, P);
+                    const double ex = g.ex, ey = g.ey;
+                    const double gj = spline_dW(g.r, P) * fabs(Vs);
+                    const double ext = -(wax * ex + way * ey);
+                    const double pw = p_i + rho_i * g.r * fmax(0.0, ext);   // ph:934
+                    const double pg = (p_i + pw) * gj;
+                    fx -= pg * (bi1.x * ex + bi1.y * ey);
+                    fy -= pg * (bi2.x * ex + bi2.y * ey);
+                }));
+            }
+            double2 x = S.pos[i];
+            {   // transport correction (ph:702-710)
+                const double n2 = ix * ix + iy * iy;
+                double lim = 100.0 * n2 / (P.h * P.h);
+                const double scale = P.transport_coeff * P.h * P.h;
+                if (lim > 1.0) lim = 1.0;
+                if (lim < 0.0) lim = 0.0;
+                x.x += scale * lim * ix;
+                x.y += scale * lim * iy;
+            }
+            fx *= Vi;
+            fy *= Vi;
+            S.force[i] = make_double2(fx, fy);
+            S.rp_half[i] = make_double2(rho_i, p_i);
+            double2 vn;
+            vn.x = vi.x + (fp.x + fx) / m_i * dt;   // ph:1402-1403
+            vn.y = vi.y + (fp.y + fy) / m_i * dt;
+            S.vel_new[i] = vn;
+            S.e_vn[ew] = vn;
+            x.x += 0.5 * dt * vi.x;   // ph:863-864
+            x.y += 0.5 * dt * vi.y;
+            x.x += 0.5 * dt * vn.x;   // ph:1067-1068
+            x.y += 0.5 * dt * vn.y;
+            S.pos[i] = x;
         }
-        double2 x = S.pos[i];
-        {   // transport correction (ph:702-710)
-            const double n2 = ix * ix + iy * iy;
-            double lim = 100.0 * n2 / (P.h * P.h);
-            const double scale = P.transport_coeff * P.h * P.h;
-            if (lim > 1.0) lim = 1.0;
-            if (lim < 0.0) lim = 0.0;
-            x.x += scale * lim * ix;
-            x.y += scale * lim * iy;
-        }
-        fx *= Vi;
-        fy *= Vi;
-        S.force[i] = make_double2(fx, fy);
-        S.rp_half[i] = make_double2(rho_i, p_i);
-        double2 vn;
-        vn.x = vi.x + (fp.x + fx) / m_i * dt;   // ph:1402-1403
-        vn.y = vi.y + (fp.y + fy) / m_i * dt;
-        S.vel_new[i] = vn;
-        x.x += 0.5 * dt * vi.x;   // ph:863-864
-        x.y += 0.5 * dt * vi.y;
-        x.x += 0.5 * dt * vn.x;   // ph:1067-1068
-        x.y += 0.5 * dt * vn.y;
-        S.pos[i] = x;
     }
-}
+    __device__ SPHB_COLD void rows_cold(const StateView &S, const TileDesc &T, const OwnPre &pre, unsigned char *buf, int cap)
+    {
+        rows<false>(S, T, pre, buf, cap);
+    }
+};
 
-__device__ __forceinline__ void force_fused_tile(PhysParams P, StateView S, DevScalars *sc, double remain, double fixed_dt,
-                                                 int add_gravity)
+__device__ __forceinline__ void force_fused_tiles(PhysParams P, const StateView &S, const DevScalars *sc, int add_gravity,
+                                                  unsigned cta, unsigned n_ctas)
 {
     load_counts(P);
-    (void)remain;
-    (void)fixed_dt;
-    const double dt = sc->dt;   // published by k_publish_dt on the same stream
-    SPHB_TILE_BEGIN();
-    const OwnPre pre = tile_prefetch_own(S, T);
-    double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
-    double2 *s_v = s_xy + cap;
-    double2 *s_pV = s_v + cap;    // (half-step pressure, volume; volume negative = wall entry)
-    double2 *s_b1 = s_pV + cap;
-    double2 *s_b2 = s_b1 + cap;
-    int walls = 0;
-#if SPHB_FLAT_STAGING
-    struct Rec {
-        double2 xy, v;
-        double4 B;
-        double V, rho, drho;
-        int j;
-    };
-    tile_stage_flat(
-        T,
-        [&](int e) {
-            Rec r;
-            r.j = S.ent_key[e] >> 3;
-            r.xy = S.ent_pos[e];
-            r.V = S.Vol[r.j];
-            r.v = (r.j < P.nf ? S.vel : S.wall_vel)[r.j];   // a wall entry stages its wall velocity
-            r.rho = S.rho[r.j];                             // (wall rows hold valid values too; unused)
-            r.drho = S.drho_dt[r.j];
-            r.B = *reinterpret_cast<const double4 *>(&S.B[r.j]);
-            return r;
-        },
-        [&](int slot, const Rec &r) {
-            s_xy[slot] = r.xy;
-            s_v[slot] = r.v;
-            if (r.j < P.nf) {
-                const double rho_h = half_step_rho(r.rho, r.drho, dt, P.rho0);
-                s_pV[slot] = make_double2(P.p0 * (rho_h / P.rho0 - 1.0), r.V);   // ph:862
-                s_b1[slot] = make_double2(r.B.x, r.B.y);
-                s_b2[slot] = make_double2(r.B.z, r.B.w);
-            } else {
-                s_pV[slot] = make_double2(0.0, -r.V);
-                walls = 1;
-            }
-        });
-#else
-    SPHB_TILE_FOR_STAGED(T, e, slot)
-    {
-        const int j = S.ent_key[e] >> 3;
-        s_xy[slot] = S.ent_pos[e];
-        const double V = S.Vol[j];
-        if (j < P.nf) {
-            s_v[slot] = S.vel[j];
-            const double rho_h = half_step_rho(S.rho[j], S.drho_dt[j], dt, P.rho0);
-            s_pV[slot] = make_double2(P.p0 * (rho_h / P.rho0 - 1.0), V);   // ph:862
-            const double4 B = *reinterpret_cast<const double4 *>(&S.B[j]);
-            s_b1[slot] = make_double2(B.x, B.y);
-            s_b2[slot] = make_double2(B.z, B.w);
-        } else {
-            s_pV[slot] = make_double2(0.0, -V);
-            s_v[slot] = S.wall_vel[j];
-            walls = 1;
-        }
-    }
+    ForceK k;
+    k.P = P;
+    k.dt = sc->dt;   // published by k_publish_dt on the same stream
+    k.add_gravity = add_gravity;
+    run_tiles(k, S, cta, n_ctas);
+}
+#ifndef SPHB_FORCE_MINCTAS
+// two staging buffers of 80 B per slot: three CTAs per SM fit with two-row tiles (~390 slots), four with three-row
+// tiles (~320 slots)
+#define SPHB_FORCE_MINCTAS (SPHB_TILE_ROWS >= 3 ? 4 : 3)
 #endif
-    if (threadIdx.x == 0) {
-        const int d = T.n_staged;
-        s_xy[d] = make_double2(kDummyCoord, kDummyCoord);
-        s_v[d] = make_double2(0.0, 0.0);
-        s_pV[d] = make_double2(0.0, 0.0);
-        s_b1[d] = make_double2(0.0, 0.0);
-        s_b2[d] = make_double2(0.0, 0.0);
-    }
-#define SPHB_CALL(plain) force_rows<plain>(P, S, T, pre, s_xy, s_v, s_pV, s_b1, s_b2, dt, add_gravity)
-    SPHB_TILE_DISPATCH(walls, SPHB_CALL);
-#undef SPHB_CALL
-}
-__global__ void __launch_bounds__(kTileThreads) k_force_fused(PhysParams P, StateView S, DevScalars *sc, double remain,
-                                                             double fixed_dt, int add_gravity)
+__global__ void __launch_bounds__(kTileThreads, SPHB_FORCE_MINCTAS) k_force_fused(PhysParams P, StateView S,
+                                                                                 const DevScalars *sc, int add_gravity)
 {
-    force_fused_tile(P, S, sc, remain, fixed_dt, add_gravity);
+    force_fused_tiles(P, S, sc, add_gravity, blockIdx.x, gridDim.x);
 }
-__global__ void __launch_bounds__(kTileThreads) k_force_fused_batch(const BatchChan *__restrict__ chan, int add_gravity)
+__global__ void __launch_bounds__(kTileThreads, SPHB_FORCE_MINCTAS) k_force_fused_batch(const BatchChan *__restrict__ chan,
+                                                                                       int add_gravity)
 {
     const BatchChan &c = chan[blockIdx.y];
-    force_fused_tile(c.P, c.S, c.sc, 0.0, 0.0, add_gravity);
+    force_fused_tiles(c.P, c.S, c.sc, add_gravity, blockIdx.x, gridDim.x);
 }
 
 // publishes the time step of the substep and re-arms the max|v| reduction (one thread; runs before the
@@ -846,77 +1000,33 @@ __device__ __forceinline__ double wrap_x(double x, double DL)   // MATLAB mod(x,
 }
 
 // ---------------------------------------------------------------- P5 + density/EOS finish + wrap + max|v|
-// staged per slot: position, new velocity (a wall entry: its wall velocity), volume (sign bit = wall)
-template <bool PLAIN>
-__device__ __forceinline__ double continuity_rows(const PhysParams &P, const StateView &S, const TileDesc &T, const OwnPre &pre,
-                                                  const double2 *s_xy, const double2 *s_v, const double *s_V,
-                                                  double dt, int do_wrap)
-{
-    double speed = 0.0;
-    SPHB_TILE_WALKERS(ew, si, i)
+// staged per slot: position, new velocity (a wall entry: its wall velocity), (-, volume; volume < 0 = wall entry)
+struct ContinuityK {
+    static constexpr int kFields = 3;
+    PhysParams P;
+    double dt;
+    int do_wrap;
+    double speed;
+    __device__ __forceinline__ int bulk_fields(const TileDesc &) const { return 3; }
+    __device__ __forceinline__ const double2 *src(const StateView &S, int f) const
     {
-        if (i >= P.nf) {
-            S.drho_dt[i] = 0.0;   // ph:1114-1116
-            S.p[i] = 0.0;         // ph:1449
-            S.vel[i] = make_double2(0.0, 0.0);   // ph:1405-1408, m:270
-            continue;
-        }
-        const double2 pi = s_xy[si];
-        const double2 vi = s_v[si];
-        double rate = 0.0;
-        SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
-            const Geo g = pair_geometry(pi, s_xy[sl], m, P);
-            const double Vs = s_V[sl];
-            const double gj = spline_dW(g.r, P) * (PLAIN ? Vs : fabs(Vs));
-            const double2 vj = s_v[sl];
-            double ux, uy;
-            if (PLAIN || Vs >= 0.0) {
-                ux = vi.x - vj.x;
-                uy = vi.y - vj.y;
-            } else {
-                ux = vi.x - (2.0 * vj.x - vi.x);   // mirrored velocity, ph:1101-1102
-                uy = vi.y - (2.0 * vj.y - vi.y);
-            }
-            rate += (ux * g.ex + uy * g.ey) * gj;
-        }));
-        const double rho_h = S.rp_half[i].x;
-        const double drho = rate * rho_h;          // ph:1112
-        double rho = rho_h + drho * (0.5 * dt);    // ph:1441
-        if (rho < 1e-10) rho = P.rho0;
-        S.drho_dt[i] = drho;
-        S.rho[i] = rho;
-        S.p[i] = P.p0 * (rho / P.rho0 - 1.0);
-        if (do_wrap) {
-            double2 x = S.pos[i];
-            x.x = wrap_x(x.x, P.DL);
-            S.pos[i] = x;
-        }
-        S.vel[i] = vi;   // nobody reads `vel` in this kernel (neighbours read vel_new): commit in place
-        if (i < P.nfo) speed = fmax(speed, sqrt(vi.x * vi.x + vi.y * vi.y));
+        return f == 0 ? S.ent_pos : (f == 1 ? S.e_vn : S.e_pV);
     }
-    return speed;
-}
-
-__device__ __forceinline__ void continuity_tile(PhysParams P, StateView S, DevScalars *sc, int do_wrap, int advance_clock)
-{
-    load_counts(P);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ TileDesc T;
-    tile_load(T, S.tiles, blockIdx.x);
-    __syncthreads();
-    if (T.flags & kTileValid) {
-        const int cap = S.tile_cap;
-        const OwnPre pre = tile_prefetch_own(S, T);
-        double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
-        double2 *s_v = s_xy + cap;
-        double *s_V = reinterpret_cast<double *>(s_v + cap);
-        int walls = 0;
-#if SPHB_FLAT_STAGING
+    __device__ __forceinline__ void dummy(unsigned char *buf, int cap, int slot) const
+    {
+        field(buf, cap, 0)[slot] = make_double2(kDummyCoord, kDummyCoord);
+        field(buf, cap, 1)[slot] = make_double2(0.0, 0.0);
+        field(buf, cap, 2)[slot] = make_double2(0.0, 0.0);
+    }
+    __device__ SPHB_COLD int stage_sync(const StateView &S, const TileDesc &T, unsigned char *buf, int cap) const
+    {
+        double2 *s_xy = field(buf, cap, 0), *s_v = field(buf, cap, 1), *s_pV = field(buf, cap, 2);
         struct Rec {
             double2 xy, v;
             double V;
             int j;
         };
+        const PhysParams &Pr = P;
         tile_stage_flat(
             T,
             [&](int e) {
@@ -924,52 +1034,85 @@ __device__ __forceinline__ void continuity_tile(PhysParams P, StateView S, DevSc
                 r.j = S.ent_key[e] >> 3;
                 r.xy = S.ent_pos[e];
                 r.V = S.Vol[r.j];
-                r.v = (r.j < P.nf ? S.vel_new : S.wall_vel)[r.j];
+                r.v = (r.j < Pr.nf ? S.vel_new : S.wall_vel)[r.j];
                 return r;
             },
             [&](int slot, const Rec &r) {
                 s_xy[slot] = r.xy;
                 s_v[slot] = r.v;
-                if (r.j < P.nf) {
-                    s_V[slot] = r.V;
-                } else {
-                    s_V[slot] = -r.V;
-                    walls = 1;
-                }
+                s_pV[slot] = make_double2(0.0, r.j < Pr.nf ? r.V : -r.V);
             });
-#else
-        SPHB_TILE_FOR_STAGED(T, e, slot)
-        {
-            const int j = S.ent_key[e] >> 3;
-            s_xy[slot] = S.ent_pos[e];
-            const double V = S.Vol[j];
-            if (j < P.nf) {
-                s_V[slot] = V;
-                s_v[slot] = S.vel_new[j];
-            } else {
-                s_V[slot] = -V;
-                s_v[slot] = S.wall_vel[j];
-                walls = 1;
-            }
-        }
-#endif
-        if (threadIdx.x == 0) {
-            const int d = T.n_staged;
-            s_xy[d] = make_double2(kDummyCoord, kDummyCoord);
-            s_v[d] = make_double2(0.0, 0.0);
-            s_V[d] = 0.0;
-        }
-        const double dt = sc->dt;
-        double speed = 0.0;
-#define SPHB_CALL(plain) speed = continuity_rows<plain>(P, S, T, pre, s_xy, s_v, s_V, dt, do_wrap)
-        SPHB_TILE_DISPATCH(walls, SPHB_CALL);
-#undef SPHB_CALL
-        // grid-wide max |v| over fluid rows: warp shuffle, then one atomicMax per warp
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) speed = fmax(speed, __shfl_xor_sync(0xffffffffu, speed, d));
-        if ((threadIdx.x & 31) == 0 && speed > 0.0)
-            atomicMax(&sc->vmax_bits, (unsigned long long)__double_as_longlong(speed));
+        if (threadIdx.x == 0) dummy(buf, cap, T.n_staged);
+        return 1;
     }
+    template <bool PLAIN>
+    __device__ __forceinline__ void rows(const StateView &S, const TileDesc &T, const OwnPre &pre, unsigned char *buf, int cap)
+    {
+        const double2 *s_xy = field(buf, cap, 0), *s_v = field(buf, cap, 1), *s_pV = field(buf, cap, 2);
+        SPHB_TILE_WALKERS(ew, si, i)
+        {
+            if (i >= P.nf) {
+                S.drho_dt[i] = 0.0;   // ph:1114-1116
+                S.p[i] = 0.0;         // ph:1449
+                S.vel[i] = make_double2(0.0, 0.0);   // ph:1405-1408, m:270
+                continue;
+            }
+            const double2 pi = s_xy[si];
+            const double2 vi = s_v[si];
+            double rate = 0.0;
+            SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
+                const Geo g = pair_geometry(pi, s_xy[sl], m, P);
+                const double Vs = s_pV[sl].y;
+                const double gj = spline_dW(g.r, P) * (PLAIN ? Vs : fabs(Vs));
+                const double2 vj = s_v[sl];
+                double ux, uy;
+                if (PLAIN || Vs >= 0.0) {
+                    ux = vi.x - vj.x;
+                    uy = vi.y - vj.y;
+                } else {
+                    ux = vi.x - (2.0 * vj.x - vi.x);   // mirrored velocity, ph:1101-1102
+                    uy = vi.y - (2.0 * vj.y - vi.y);
+                }
+                rate += (ux * g.ex + uy * g.ey) * gj;
+            }));
+            const double rho_h = S.rp_half[i].x;
+            const double drho = rate * rho_h;          // ph:1112
+            double rho = rho_h + drho * (0.5 * dt);    // ph:1441
+            if (rho < 1e-10) rho = P.rho0;
+            S.drho_dt[i] = drho;
+            S.rho[i] = rho;
+            S.p[i] = P.p0 * (rho / P.rho0 - 1.0);
+            if (do_wrap) {
+                double2 x = S.pos[i];
+                x.x = wrap_x(x.x, P.DL);
+                S.pos[i] = x;
+            }
+            S.vel[i] = vi;   // nobody reads `vel` in this kernel (neighbours read the staged new velocity): commit in place
+            if (i < P.nfo) speed = fmax(speed, sqrt(vi.x * vi.x + vi.y * vi.y));
+        }
+    }
+    __device__ SPHB_COLD void rows_cold(const StateView &S, const TileDesc &T, const OwnPre &pre, unsigned char *buf, int cap)
+    {
+        rows<false>(S, T, pre, buf, cap);
+    }
+};
+
+__device__ __forceinline__ void continuity_tiles(PhysParams P, const StateView &S, DevScalars *sc, int do_wrap, int advance_clock,
+                                                 unsigned cta, unsigned n_ctas)
+{
+    load_counts(P);
+    ContinuityK k;
+    k.P = P;
+    k.dt = sc->dt;
+    k.do_wrap = do_wrap;
+    k.speed = 0.0;
+    run_tiles(k, S, cta, n_ctas);
+    // grid-wide max |v| over fluid rows: warp shuffle, then one atomicMax per warp and CTA
+    double speed = k.speed;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) speed = fmax(speed, __shfl_xor_sync(0xffffffffu, speed, d));
+    if ((threadIdx.x & 31) == 0 && speed > 0.0)
+        atomicMax(&sc->vmax_bits, (unsigned long long)__double_as_longlong(speed));
     if (!advance_clock) return;
     // the last CTA to finish advances the clock and publishes max|v| (what k_advance_clock does as a
     // launch of its own): t += dt, step += 1, m:264-266
@@ -977,7 +1120,7 @@ __device__ __forceinline__ void continuity_tile(PhysParams P, StateView S, DevSc
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned ticket = atomicAdd(&sc->ticket, 1u);
-        if (ticket == gridDim.x - 1) {
+        if (ticket == n_ctas - 1) {
             __threadfence();
             sc->t += sc->dt;
             sc->step += 1;
@@ -986,16 +1129,19 @@ __device__ __forceinline__ void continuity_tile(PhysParams P, StateView S, DevSc
         }
     }
 }
-__global__ void __launch_bounds__(kTileThreads) k_continuity(PhysParams P, StateView S, DevScalars *sc, int do_wrap,
-                                                            int advance_clock)
+#ifndef SPHB_CONT_MINCTAS
+#define SPHB_CONT_MINCTAS 5   // (6 -> 170 B of spills, 77 us; 5 -> 57.8 us; 4 -> 58.2 us)
+#endif
+__global__ void __launch_bounds__(kTileThreads, SPHB_CONT_MINCTAS) k_continuity(PhysParams P, StateView S, DevScalars *sc,
+                                                                               int do_wrap, int advance_clock)
 {
-    continuity_tile(P, S, sc, do_wrap, advance_clock);
+    continuity_tiles(P, S, sc, do_wrap, advance_clock, blockIdx.x, gridDim.x);
 }
-__global__ void __launch_bounds__(kTileThreads, 7) k_continuity_batch(const BatchChan *__restrict__ chan, int do_wrap,
+__global__ void __launch_bounds__(kTileThreads, SPHB_CONT_MINCTAS) k_continuity_batch(const BatchChan *__restrict__ chan, int do_wrap,
                                                                   int advance_clock)
 {
     const BatchChan &c = chan[blockIdx.y];
-    continuity_tile(c.P, c.S, c.sc, do_wrap, advance_clock);
+    continuity_tiles(c.P, c.S, c.sc, do_wrap, advance_clock, blockIdx.x, gridDim.x);
 }
 
 __global__ void __launch_bounds__(256) k_vmax(int nf, const double2 *__restrict__ vel, DevScalars *sc)
@@ -1023,68 +1169,79 @@ __global__ void __launch_bounds__(kBlock) k_wrap(int nf, double DL, double2 *pos
 }
 
 // ---------------------------------------------------------------- P8 wall shear (ph:1713-1742)
-// Only wall particles at y <= 0 or y >= DH count (ph:1731-1736) and the pair distance is < 2h, so only
-// tiles whose neighbourhood holds wall entries do any work: the others exit after the staging vote.
-// One partial (bottom, top) per tile, summed in tile order by k_wall_shear_final: deterministic.
-__device__ __forceinline__ void wall_shear_tile(PhysParams P, StateView S, double *partials)
+// Only wall particles at y <= 0 or y >= DH count (ph:1731-1736) and the pair distance is < 2h, so only the tile
+// rows whose neighbourhood reaches the cell rows of y <= 0 or y >= DH can contribute: the CTAs deal exactly those
+// tiles among themselves (a few hundred instead of every tile of the channel).  One partial (bottom, top) per CTA;
+// the last CTA to finish sums them in CTA order -- deterministic -- and publishes tau (no second launch).
+__device__ __forceinline__ void wall_shear_tiles(PhysParams P, const StateView &S, double *partials, DevScalars *sc,
+                                                 unsigned cta, unsigned n_ctas)
 {
     load_counts(P);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ TileDesc T;
     __shared__ double shb[kTileThreads], sht[kTileThreads];
-    const unsigned nt = gridDim.x;
-    if (threadIdx.x == 0) {
-        partials[blockIdx.x] = 0.0;
-        partials[nt + blockIdx.x] = 0.0;
-    }
-    {   // tiles whose neighbourhood cannot reach a cell row holding y <= 0 or y >= DH exit unread
-        const GridDesc *g = S.grid;
-        const int cy0 = (int)(blockIdx.x / (unsigned)tiles_per_row(S.ncx, S.tile_w)) * kTileRows;
-        const int cyb = (int)floor((0.0 - g->y_min) / g->cell), cyt = (int)floor((P.DH - g->y_min) / g->cell);
-        if (cy0 - 1 > cyb && cy0 + kTileRows < cyt) return;
-    }
-    SPHB_TILE_BEGIN();
-    const OwnPre pre = tile_prefetch_own(S, T);
+    __shared__ int s_last;
+    const int cap = S.tile_cap;
     double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
     double *s_V = reinterpret_cast<double *>(s_xy + cap);
     double *s_wvx = s_V + cap;
-    int walls = 0;
-    SPHB_TILE_FOR_STAGED(T, e, slot)
-    {
-        const int j = S.ent_key[e] >> 3;
-        s_xy[slot] = S.ent_pos[e];
-        if (j >= P.nf) {
-            s_V[slot] = -S.Vol[j];
-            s_wvx[slot] = S.wall_vel[j].x;
-            walls = 1;
-        } else {
-            s_V[slot] = 1.0;
-        }
-    }
-    if (threadIdx.x == 0) {
-        s_xy[T.n_staged] = make_double2(kDummyCoord, kDummyCoord);
-        s_V[T.n_staged] = 1.0;   // skipped like a fluid neighbour
-    }
-    if (!__syncthreads_or(walls)) return;
+    // candidate tile rows: cy0 - 1 <= cyb (bottom) or cy0 + kTileRows >= cyt (top)
+    const GridDesc *g = S.grid;
+    const int tpr = tiles_per_row(S.ncx, S.tile_w);
+    const int n_trows = (int)(S.n_tiles / (unsigned)tpr);
+    const int cyb = (int)floor((0.0 - g->y_min) / g->cell), cyt = (int)floor((P.DH - g->y_min) / g->cell);
+    const int nb = cyb + 1 < 0 ? 0 : min(n_trows, (cyb + 1) / kTileRows + 1);
+    const int t0 = max(nb, cyt - kTileRows <= 0 ? 0 : (cyt - 1) / kTileRows);
+    const int ncand = (nb + max(0, n_trows - t0)) * tpr;
     double sb = 0.0, st = 0.0;
-    SPHB_TILE_WALKERS(ew, si, i)
-    {
-        if (i >= P.nfo) continue;   // wall rows and halo copies of a slab
-        const double2 pi = s_xy[si];
-        const double vx = S.vel[i].x;
-        const Mat2 Bi = S.B[i];
-        const double Vi = S.Vol[i];
-        SPHB_ROW(true, ([&](const int sl, const int m) {
-            const double Vs = s_V[sl];
-            if (Vs > 0.0) return;
-            const double2 pj = s_xy[sl];
-            const Geo g = pair_geometry(pi, pj, m, P);
-            if (!(g.r > 1e-12)) return;
-            const double ex = g.ex, ey = g.ey;
-            const double eBe = ex * (Bi.b11 * ex + Bi.b12 * ey) + ey * (Bi.b21 * ex + Bi.b22 * ey);
-            const double dvx = vx - s_wvx[sl];
-            const double f = 4.0 * P.mu * eBe * spline_dW(g.r, P) * (-Vs) * dvx / (g.r + 0.01 * P.h) * Vi;
-            if (pj.y <= 0.0) sb += f;
-            else if (pj.y >= P.DH) st += f;
-        }));
+    for (int q = (int)cta; q < ncand; q += (int)n_ctas) {
+        int tr = q / tpr;
+        const int tc = q - tr * tpr;
+        if (tr >= nb) tr = t0 + (tr - nb);
+        __syncthreads();   // the previous tile's readers are done with T and the staging arrays
+        tile_load(T, S.tiles, (unsigned)(tr * tpr + tc));
+        __syncthreads();
+        if (!(T.flags & kTileValid)) continue;
+        const OwnPre pre = tile_prefetch_own(S, T);
+        int walls = 0;
+        SPHB_TILE_FOR_STAGED(T, e, slot)
+        {
+            const int j = S.ent_key[e] >> 3;
+            s_xy[slot] = S.ent_pos[e];
+            if (j >= P.nf) {
+                s_V[slot] = -S.Vol[j];
+                s_wvx[slot] = S.wall_vel[j].x;
+                walls = 1;
+            } else {
+                s_V[slot] = 1.0;
+            }
+        }
+        if (threadIdx.x == 0) {
+            s_xy[T.n_staged] = make_double2(kDummyCoord, kDummyCoord);
+            s_V[T.n_staged] = 1.0;   // skipped like a fluid neighbour
+        }
+        if (!__syncthreads_or(walls)) continue;
+        SPHB_TILE_WALKERS(ew, si, i)
+        {
+            if (i >= P.nfo) continue;   // wall rows and halo copies of a slab
+            const double2 pi = s_xy[si];
+            const double vx = S.vel[i].x;
+            const Mat2 Bi = S.B[i];
+            const double Vi = S.Vol[i];
+            SPHB_ROW(true, ([&](const int sl, const int m) {
+                const double Vs = s_V[sl];
+                if (Vs > 0.0) return;
+                const double2 pj = s_xy[sl];
+                const Geo g2 = pair_geometry(pi, pj, m, P);
+                if (!(g2.r > 1e-12)) return;
+                const double ex = g2.ex, ey = g2.ey;
+                const double eBe = ex * (Bi.b11 * ex + Bi.b12 * ey) + ey * (Bi.b21 * ex + Bi.b22 * ey);
+                const double dvx = vx - s_wvx[sl];
+                const double f = 4.0 * P.mu * eBe * spline_dW(g2.r, P) * (-Vs) * dvx / (g2.r + 0.01 * P.h) * Vi;
+                if (pj.y <= 0.0) sb += f;
+                else if (pj.y >= P.DH) st += f;
+            }));
+        }
     }
     shb[threadIdx.x] = sb;
     sht[threadIdx.x] = st;
@@ -1097,32 +1254,25 @@ __device__ __forceinline__ void wall_shear_tile(PhysParams P, StateView S, doubl
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        partials[blockIdx.x] = shb[0];
-        partials[nt + blockIdx.x] = sht[0];
+        partials[cta] = shb[0];
+        partials[n_ctas + cta] = sht[0];
+        __threadfence();
+        s_last = atomicAdd(&sc->shear_ticket, 1u) == n_ctas - 1 ? 1 : 0;
     }
-}
-__global__ void __launch_bounds__(kTileThreads) k_wall_shear(PhysParams P, StateView S, double *partials)
-{
-    wall_shear_tile(P, S, partials);
-}
-__global__ void __launch_bounds__(kTileThreads, 6) k_wall_shear_batch(const BatchChan *__restrict__ chan)
-{
-    const BatchChan &c = chan[blockIdx.y];
-    wall_shear_tile(c.P, c.S, c.shear_partials);
-}
-
-__device__ __forceinline__ void wall_shear_sum(const double *partials, int nblocks, double DL, DevScalars *sc)
-{
-    __shared__ double shb[256], sht[256];
-    double sb = 0.0, st = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += 256) {
+    __syncthreads();
+    if (!s_last) return;
+    // the last CTA: every partial is visible (fence + ticket); sum in CTA order
+    __threadfence();
+    sb = 0.0;
+    st = 0.0;
+    for (unsigned b = threadIdx.x; b < n_ctas; b += kTileThreads) {
         sb += partials[b];
-        st += partials[nblocks + b];
+        st += partials[n_ctas + b];
     }
     shb[threadIdx.x] = sb;
     sht[threadIdx.x] = st;
     __syncthreads();
-    for (int d = 128; d > 0; d >>= 1) {
+    for (int d = kTileThreads / 2; d > 0; d >>= 1) {
         if (threadIdx.x < d) {
             shb[threadIdx.x] += shb[threadIdx.x + d];
             sht[threadIdx.x] += sht[threadIdx.x + d];
@@ -1130,19 +1280,41 @@ __device__ __forceinline__ void wall_shear_sum(const double *partials, int nbloc
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        sc->tau_bottom = -shb[0] / DL;
-        sc->tau_top = -sht[0] / DL;
+        sc->tau_bottom = -shb[0] / P.DL;
+        sc->tau_top = -sht[0] / P.DL;
+        sc->shear_ticket = 0u;
     }
 }
-__global__ void __launch_bounds__(256) k_wall_shear_final(const double *partials, int nblocks, double DL,
-                                                         DevScalars *sc)
+__global__ void __launch_bounds__(kTileThreads) k_wall_shear(PhysParams P, StateView S, double *partials, DevScalars *sc)
 {
-    wall_shear_sum(partials, nblocks, DL, sc);
+    wall_shear_tiles(P, S, partials, sc, blockIdx.x, gridDim.x);
 }
-__global__ void __launch_bounds__(256) k_wall_shear_final_batch(const BatchChan *__restrict__ chan, int nblocks)
+__global__ void __launch_bounds__(kTileThreads, 6) k_wall_shear_batch(const BatchChan *__restrict__ chan)
 {
     const BatchChan &c = chan[blockIdx.y];
-    wall_shear_sum(c.shear_partials, nblocks, c.P.DL, c.sc);
+    wall_shear_tiles(c.P, c.S, c.shear_partials, c.sc, blockIdx.x, gridDim.x);
+}
+
+// ---------------------------------------------------------------- entry-ordered mirrors rebuilt from the rows
+// The producing kernels keep the mirrors current inside a step.  A caller that changes rows behind a standing list
+// (sphb_ctx_upload without positions) or runs the Verlet operator without a density pass since the last build gets
+// them from here: one thread per entry.
+__global__ void __launch_bounds__(kBlock) k_refresh_mirrors(PhysParams P, StateView S)
+{
+    load_counts(P);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.grid->n_entries || (size_t)e >= S.ell_stride) return;
+    const int j = S.ent_key[e] >> 3;
+    if (j < 0 || j >= P.nt) return;
+    const bool fluid = j < P.nf;
+    const double V = S.Vol[j];
+    S.e_vel[e] = (fluid ? S.vel : S.wall_vel)[j];
+    S.e_w[e] = make_double2(fluid ? -1.0 : S.mass[j] * P.inv_rho0, 0.0);
+    S.e_pV[e] = make_double2(fluid ? S.rp_half[j].y : 0.0, fluid ? V : -V);
+    const Mat2 B = S.B[j];
+    S.e_b1[e] = make_double2(B.b11, B.b12);
+    S.e_b2[e] = make_double2(B.b21, B.b22);
+    S.e_vn[e] = (fluid ? S.vel_new : S.wall_vel)[j];
 }
 
 // ---------------------------------------------------------------- binned u(y) monitor (m:579-605)
@@ -1175,12 +1347,34 @@ __global__ void __launch_bounds__(kBlock) k_profile(PhysParams P, StateView S, d
 
 // ================================================================================================
 // bytes of shared memory per staged slot
-constexpr size_t kDensitySlot = 24, kKgcSlot = 24, kViscSlot = 72, kPressureSlot = 88, kForceSlot = 80, kContinuitySlot = 40,
-                 kShearSlot = 32;
+// bytes of shared memory per staged slot.  The four pipelined kernels hold TWO buffers of kFields 16-byte fields.
+constexpr size_t kDensitySlot = 2 * DensityK::kFields * 16, kKgcSlot = 2 * KgcK::kFields * 16, kViscSlot = 72, kPressureSlot = 88,
+                 kForceSlot = 2 * ForceK::kFields * 16, kContinuitySlot = 2 * ContinuityK::kFields * 16, kShearSlot = 32;
 
 int csr_max_tile_slots()
 {
-    return (int)((227 * 1024 - 4096) / kPressureSlot);
+    return (int)((227 * 1024 - 4096) / kForceSlot);
+}
+
+// Persistent launches: one CTA per resident slot of the device (SMs x CTAs per SM at the kernel's register and
+// shared-memory footprint), never more than there are tiles.
+template <class Kern>
+static unsigned persistent_ctas(Kern *kern, size_t smem, unsigned n_tiles)
+{
+    int dev = 0, sms = 148, per_sm = 1;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    static int sm_count[SmemGrant::kMaxDev] = {};
+    if (dev >= 0 && dev < SmemGrant::kMaxDev) {
+        if (sm_count[dev] == 0 && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            sm_count[dev] = sms;
+        if (sm_count[dev] > 0) sms = sm_count[dev];
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem) != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
+        per_sm = 1;
+    }
+    const unsigned g = (unsigned)sms * (unsigned)per_sm;
+    return n_tiles < g ? (n_tiles ? n_tiles : 1u) : g;
 }
 
 // dynamic shared memory above 48 KB must be granted per kernel (and per device: SmemGrant)
@@ -1200,15 +1394,17 @@ int csr_configure(int tile_cap)
     return 0;
 }
 
-int csr_density(const PhysParams &P, const StateView &S, cudaStream_t st)
+int csr_density(const PhysParams &P, const StateView &S, const DevScalars *sc, cudaStream_t st)
 {
-    k_density<<<S.n_tiles, kTileThreads, (size_t)S.tile_cap * kDensitySlot, st>>>(P, S);
+    const size_t sm = (size_t)S.tile_cap * kDensitySlot;
+    k_density<<<persistent_ctas(k_density, sm, S.n_tiles), kTileThreads, sm, st>>>(P, S, sc);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
 int csr_kgc(const PhysParams &P, const StateView &S, cudaStream_t st)
 {
-    k_kgc<<<S.n_tiles, kTileThreads, (size_t)S.tile_cap * kKgcSlot, st>>>(P, S);
+    const size_t sm = (size_t)S.tile_cap * kKgcSlot;
+    k_kgc<<<persistent_ctas(k_kgc, sm, S.n_tiles), kTileThreads, sm, st>>>(P, S);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1239,18 +1435,26 @@ int csr_pressure(const PhysParams &P, const StateView &S, const DevScalars *sc, 
 int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool wrap, bool advance_clock,
                    cudaStream_t st)
 {
-    k_continuity<<<S.n_tiles, kTileThreads, (size_t)S.tile_cap * kContinuitySlot, st>>>(P, S, sc, wrap ? 1 : 0,
-                                                                                        advance_clock ? 1 : 0);
+    const size_t sm = (size_t)S.tile_cap * kContinuitySlot;
+    k_continuity<<<persistent_ctas(k_continuity, sm, S.n_tiles), kTileThreads, sm, st>>>(P, S, sc, wrap ? 1 : 0,
+                                                                                         advance_clock ? 1 : 0);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
-// viscous + transport + dt + pressure + kick in one gather (the first substep of an outer step)
-int csr_force_fused(const PhysParams &P, const StateView &S, DevScalars *sc, double remain, double fixed_dt,
-                    bool add_gravity, cudaStream_t st)
+// the time step of the coming substep (m:519-527) and the re-armed max|v| reduction: before the density pass of an
+// outer step, which evaluates the half-step pressures with it
+int csr_publish_dt(const PhysParams &P, DevScalars *sc, double remain, double fixed_dt, cudaStream_t st)
 {
     k_publish_dt<<<1, 1, 0, st>>>(P, sc, remain, fixed_dt);
-    k_force_fused<<<S.n_tiles, kTileThreads, (size_t)S.tile_cap * kForceSlot, st>>>(P, S, sc, remain, fixed_dt,
-                                                                                       add_gravity ? 1 : 0);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+// viscous + transport + pressure + kick in one gather (the first substep of an outer step; after csr_publish_dt
+// and csr_density of the same outer step)
+int csr_force_fused(const PhysParams &P, const StateView &S, const DevScalars *sc, bool add_gravity, cudaStream_t st)
+{
+    const size_t sm = (size_t)S.tile_cap * kForceSlot;
+    k_force_fused<<<persistent_ctas(k_force_fused, sm, S.n_tiles), kTileThreads, sm, st>>>(P, S, sc, add_gravity ? 1 : 0);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1271,10 +1475,17 @@ int csr_wrap(const PhysParams &P, double2 *pos, cudaStream_t st)
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
+// CTAs of the wall-shear kernel: the tiles of six tile rows (bottom + top wall neighbourhoods of a channel whose
+// walls are BW = 4 dp thick; more candidate rows are dealt round-robin), never more than there are tiles.  The
+// partials buffer holds 2 x n_tiles doubles.
+static unsigned shear_ctas(unsigned n_tiles, int ncx, int tile_w)
+{
+    const unsigned g = 6u * (unsigned)tiles_per_row(ncx, tile_w);
+    return n_tiles < g ? (n_tiles ? n_tiles : 1u) : g;
+}
 int csr_wall_shear(const PhysParams &P, const StateView &S, DevScalars *sc, double *partials, cudaStream_t st)
 {
-    k_wall_shear<<<S.n_tiles, kTileThreads, (size_t)S.tile_cap * kShearSlot, st>>>(P, S, partials);
-    k_wall_shear_final<<<1, 256, 0, st>>>(partials, (int)S.n_tiles, P.DL, sc);
+    k_wall_shear<<<shear_ctas(S.n_tiles, S.ncx, S.tile_w), kTileThreads, (size_t)S.tile_cap * kShearSlot, st>>>(P, S, partials, sc);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1292,23 +1503,30 @@ int csr_batch_configure(int tile_cap)
     return 0;
 }
 static inline dim3 batch_grid(const BatchLaunch &L, unsigned gx) { return dim3(gx, (unsigned)L.n_chan, 1u); }
+// pipelined kernels: a few tiles per CTA, so that the copies of one tile overlap the rows of the one before
+static inline dim3 batch_tile_grid(const BatchLaunch &L) { return dim3((L.n_tiles + 2u) / 3u, (unsigned)L.n_chan, 1u); }
 
 int csr_batch_density(const BatchLaunch &L)
 {
-    k_density_batch<<<batch_grid(L, L.n_tiles), kTileThreads, (size_t)L.tile_cap * kDensitySlot, L.st>>>(L.chan);
+    k_density_batch<<<batch_tile_grid(L), kTileThreads, (size_t)L.tile_cap * kDensitySlot, L.st>>>(L.chan);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
 int csr_batch_kgc(const BatchLaunch &L)
 {
-    k_kgc_batch<<<batch_grid(L, L.n_tiles), kTileThreads, (size_t)L.tile_cap * kKgcSlot, L.st>>>(L.chan);
+    k_kgc_batch<<<batch_tile_grid(L), kTileThreads, (size_t)L.tile_cap * kKgcSlot, L.st>>>(L.chan);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
-int csr_batch_force_fused(const BatchLaunch &L, double remain, double fixed_dt, bool add_gravity)
+int csr_batch_publish_dt(const BatchLaunch &L, double remain, double fixed_dt)
 {
     k_publish_dt_batch<<<grid_for((size_t)L.n_chan), kBlock, 0, L.st>>>(L.chan, L.n_chan, remain, fixed_dt);
-    k_force_fused_batch<<<batch_grid(L, L.n_tiles), kTileThreads, (size_t)L.tile_cap * kForceSlot, L.st>>>(
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_batch_force_fused(const BatchLaunch &L, bool add_gravity)
+{
+    k_force_fused_batch<<<batch_tile_grid(L), kTileThreads, (size_t)L.tile_cap * kForceSlot, L.st>>>(
         L.chan, add_gravity ? 1 : 0);
     SPHB_CUDA(cudaGetLastError());
     return 0;
@@ -1327,15 +1545,22 @@ int csr_batch_pressure(const BatchLaunch &L)
 }
 int csr_batch_continuity(const BatchLaunch &L, bool wrap, bool advance_clock)
 {
-    k_continuity_batch<<<batch_grid(L, L.n_tiles), kTileThreads, (size_t)L.tile_cap * kContinuitySlot, L.st>>>(
+    k_continuity_batch<<<batch_tile_grid(L), kTileThreads, (size_t)L.tile_cap * kContinuitySlot, L.st>>>(
         L.chan, wrap ? 1 : 0, advance_clock ? 1 : 0);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
 int csr_batch_wall_shear(const BatchLaunch &L)
 {
-    k_wall_shear_batch<<<batch_grid(L, L.n_tiles), kTileThreads, (size_t)L.tile_cap * kShearSlot, L.st>>>(L.chan);
-    k_wall_shear_final_batch<<<batch_grid(L, 1u), 256, 0, L.st>>>(L.chan, (int)L.n_tiles);
+    k_wall_shear_batch<<<batch_grid(L, shear_ctas(L.n_tiles, L.ncx, L.tile_w)), kTileThreads, (size_t)L.tile_cap * kShearSlot,
+                         L.st>>>(L.chan);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int csr_refresh_mirrors(const PhysParams &P, const StateView &S, cudaStream_t st)
+{
+    k_refresh_mirrors<<<grid_for(S.ell_stride), kBlock, 0, st>>>(P, S);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }

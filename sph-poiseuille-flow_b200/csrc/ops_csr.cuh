@@ -16,7 +16,7 @@ struct DevScalars {
     double y0_fluid;                // min fluid y (cell sort key origin, m:565)
     long long y0_key;
     unsigned int ticket;            // CTAs of the continuity kernel that have finished (clock advance)
-    unsigned int pad;
+    unsigned int shear_ticket;      // CTAs of the wall-shear kernel that have finished (final sum by the last one)
 };
 
 struct PhysParams {
@@ -56,6 +56,13 @@ struct StateView {
     const TileDesc *tiles;    // one descriptor per cell tile
     const int *ell_cnt;       // neighbours of the walker whose real entry is e
     const uint4 *ell_q;       // ell_q[(k / 8) * ell_stride + e]: eight 16-bit (slot | shift) entries
+    // entry-ordered mirrors (index = entry, valid for real entries): what the gather kernels stage with bulk
+    // asynchronous copies instead of gathering it through ent_key (async_copy.cuh, ops_csr.cu)
+    double2 *e_vel;           // velocity at list-build time (wall entry: wall velocity)      written by the list build
+    double2 *e_w;             // (wall weight m / rho0 or -1 for fluid, 0)                     written by the list build
+    double2 *e_pV;            // (half-step pressure, volume; volume < 0 marks a wall entry)  written by k_density
+    double2 *e_b1, *e_b2;     // rows of B                                                     written by k_kgc
+    double2 *e_vn;            // new velocity (wall entry: wall velocity)                      written by the force kernels
     size_t ell_stride;
     int ell_cap;
     int tile_cap;             // shared-memory slots per tile
@@ -63,7 +70,7 @@ struct StateView {
     unsigned n_tiles;
 };
 
-int csr_density(const PhysParams &P, const StateView &S, cudaStream_t st);                       // P1 pass 1
+int csr_density(const PhysParams &P, const StateView &S, const DevScalars *sc, cudaStream_t st);   // P1 pass 1 (+ half-step p)
 int csr_kgc(const PhysParams &P, const StateView &S, cudaStream_t st);                           // P1 pass 2
 int csr_visc_transport(const PhysParams &P, const StateView &S, bool do_visc, bool add_gravity, bool do_transport,
                        cudaStream_t st);                                                         // P2 + P3
@@ -73,13 +80,17 @@ int csr_time_step(const PhysParams &P, const StateView &S, DevScalars *sc, doubl
 int csr_pressure(const PhysParams &P, const StateView &S, const DevScalars *sc, cudaStream_t st);    // P4 + kick
 int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool wrap, bool advance_clock,
                    cudaStream_t st);                                                             // P5 + finish (+ clock)
-int csr_force_fused(const PhysParams &P, const StateView &S, DevScalars *sc, double remain, double fixed_dt,
-                    bool add_gravity, cudaStream_t st);                                          // P2 + P3 + dt + P4
+// dt of the coming substep = min(acoustic, viscous, body, remain) from the device vmax (m:519-527), published BEFORE
+// the density pass of an outer step (which evaluates the half-step pressures with it); fixed_dt > 0 overrides
+int csr_publish_dt(const PhysParams &P, DevScalars *sc, double remain, double fixed_dt, cudaStream_t st);
+int csr_force_fused(const PhysParams &P, const StateView &S, const DevScalars *sc, bool add_gravity,
+                    cudaStream_t st);                                                            // P2 + P3 + P4 + kick
 int csr_vmax(const PhysParams &P, const double2 *vel, DevScalars *sc, cudaStream_t st);          // standalone reduction
 int csr_wrap(const PhysParams &P, double2 *pos, cudaStream_t st);                                // m:570-577
 int csr_wall_shear(const PhysParams &P, const StateView &S, DevScalars *sc, double *partials, cudaStream_t st);  // P8
 int csr_profile(const PhysParams &P, const StateView &S, double x0, double half_width, int n_bins,
                 const double *edges_dev, double *sum_dev, double *cnt_dev, cudaStream_t st);
+int csr_refresh_mirrors(const PhysParams &P, const StateView &S, cudaStream_t st);   // StateView::e_* from the rows
 int csr_configure(int tile_cap);     // grants the gather kernels the shared memory `tile_cap` slots need
 int csr_max_tile_slots();            // what the widest gather kernel (pressure) can stage
 
@@ -100,12 +111,14 @@ struct BatchLaunch {
     unsigned n_tiles;        // tiles of every channel
     int n_fluid;             // fluid rows of every channel
     int tile_cap;            // largest slot count over the channels (sizes the dynamic shared memory)
+    int ncx, tile_w;         // cell columns and tile width of every channel
     cudaStream_t st;
 };
 int csr_batch_configure(int tile_cap);
 int csr_batch_density(const BatchLaunch &L);
 int csr_batch_kgc(const BatchLaunch &L);
-int csr_batch_force_fused(const BatchLaunch &L, double remain, double fixed_dt, bool add_gravity);
+int csr_batch_publish_dt(const BatchLaunch &L, double remain, double fixed_dt);
+int csr_batch_force_fused(const BatchLaunch &L, bool add_gravity);
 int csr_batch_time_step(const BatchLaunch &L, double remain, double fixed_dt);
 int csr_batch_pressure(const BatchLaunch &L);
 int csr_batch_continuity(const BatchLaunch &L, bool wrap, bool advance_clock);

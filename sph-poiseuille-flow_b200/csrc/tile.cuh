@@ -23,7 +23,10 @@
 namespace sphb {
 
 constexpr int kTileThreads = 128;   // threads per CTA (one per own entry, strided when a tile holds more)
-constexpr int kTileRows = 2;        // own cell rows of a tile
+#ifndef SPHB_TILE_ROWS
+#define SPHB_TILE_ROWS 2
+#endif
+constexpr int kTileRows = SPHB_TILE_ROWS;   // own cell rows of a tile
 constexpr int kStageRows = kTileRows + 2;
 constexpr int kMaxTileW = 32;       // widest tile in cells
 constexpr int kSlotBits = 13;
@@ -32,7 +35,7 @@ constexpr unsigned kSlotMask = (1u << kSlotBits) - 1u;
 constexpr int kShiftBias = 3;       // stored shift = m + 3, m in [-3, 4]
 constexpr double kDummyCoord = 1.0e100;   // position of the dummy slot: finite r, q >> 2, W = dW = 0
 
-enum : int { kTileValid = 1, kTileSeam = 2 };
+enum : int { kTileValid = 1, kTileSeam = 2, kTileHasWall = 4 };   // kTileHasWall is set by the walk (it sees the keys)
 
 struct TileSeg {
     int b, e;   // entry range [b, e)

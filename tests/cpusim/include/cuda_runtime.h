@@ -129,6 +129,20 @@ inline cudaError_t cudaFuncSetAttribute(K *, cudaFuncAttribute, int)
 {
     return cudaSuccess;
 }
+// persistent launches size their grid from these: the simulator pretends to be a 3-SM device with 2 CTAs per SM, so
+// that every CTA takes several tiles (the pipelined path) on the small test channels
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int)
+{
+    *v = 3;
+    return cudaSuccess;
+}
+template <class K>
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K *, int, size_t)
+{
+    *n = 2;
+    return cudaSuccess;
+}
 
 // kernel<<<grid, block, smem, stream>>>(args...) is rewritten to this by tests/cpusim/build.py
 namespace cpusim {

@@ -38,11 +38,11 @@ def test_library_is_sm_100a_only_and_holds_every_step_kernel():
     assert archs == {"sm_100a"}, archs
     step = ["k_yrange_grid", "k_bin_count", "scan_tiles", "scan_finish", "k_scatter", "k_cell_canon", "k_tile_setup",
             "k_walk_tile", "k_density", "k_kgc", "k_force_fused", "k_publish_dt", "k_continuity", "k_time_step",
-            "k_pressure", "k_wall_shear", "k_wall_shear_final"]
+            "k_pressure", "k_wall_shear"]
     for name in step:
         assert name in k, f"{name} missing from libsph_b200.so"
         assert name + "_batch" in k, f"{name}_batch missing from libsph_b200.so"
-    assert "k_zero_cells_batch" in k
+    assert "k_zero_cells_batch" in k and "k_refresh_mirrors" in k
     # MEX-path (pair list) operators and the slab kernels
     for name in ("k_dens_sigma", "k_visc_pairs", "k_transp_pairs", "k_int1_pairs", "k_int2_pairs", "k_shear_pairs",
                  "k_export_pairs", "k_slab_scatter", "k_slab_unpack"):
@@ -50,21 +50,22 @@ def test_library_is_sm_100a_only_and_holds_every_step_kernel():
 
 
 def test_gather_kernels_keep_their_register_budget_and_do_not_spill():
-    """128 threads per CTA: <= 128 registers keeps 4 CTAs of the fused force kernel resident per SM, <= 80 keeps 6
-    of the continuity / KGC / density kernels; none of them may use local memory."""
+    """128 threads per CTA, two staging buffers per CTA (ops_csr.cu run_tiles): the fused force kernel is held to
+    three CTAs per SM by its shared memory (<= 170 registers), continuity to five (<= 102), KGC / density to six
+    (<= 85); a few spilled words at most (measured: every further CTA bought with spills costs time)."""
     _, k = _res_usage()
-    budget = {"k_force_fused": 128, "k_continuity": 80, "k_kgc": 80, "k_density": 80, "k_wall_shear": 96,
+    budget = {"k_force_fused": 170, "k_continuity": 102, "k_kgc": 85, "k_density": 85, "k_wall_shear": 96,
               "k_pressure": 128}
     for name, regs in budget.items():
         for rec in k[name]:
             assert rec["reg"] <= regs, (name, rec)
-            assert rec["stack"] == 0 and rec["local"] == 0, (name, rec)
-    # the batched forms read their arguments from a device record instead of the constant bank: __launch_bounds__
-    # holds them at the single-channel register counts (same occupancy) at the price of a few spilled words
-    for name, regs in {"k_force_fused_batch": 128, "k_continuity_batch": 72, "k_kgc_batch": 64, "k_density_batch": 56,
-                       "k_pressure_batch": 96, "k_wall_shear_batch": 80}.items():
+            assert rec["stack"] <= 16 and rec["local"] == 0, (name, rec)
+    # the batched forms read their arguments from a device record instead of the constant bank: same bounds, a few
+    # more spilled words
+    for name, regs in {"k_force_fused_batch": 170, "k_continuity_batch": 102, "k_kgc_batch": 85, "k_density_batch": 85,
+                       "k_pressure_batch": 96, "k_wall_shear_batch": 96}.items():
         for rec in k[name]:
-            assert rec["reg"] <= regs and rec["stack"] <= 32 and rec["local"] == 0, (name, rec)
+            assert rec["reg"] <= regs and rec["stack"] <= 48 and rec["local"] == 0, (name, rec)
     # the walk is capped at 80 registers for 6 resident CTAs (__launch_bounds__(128, 6)); a few spilled words are
     # the known price, more than that is a regression
     for rec in k["k_walk_tile"] + k["k_walk_tile_batch"]:

@@ -174,6 +174,46 @@ def test_moving_walls_and_nonuniform_mass(sphb, H, oracle_be):
     ch.close()
 
 
+def test_rows_uploaded_behind_a_standing_list(sphb, H, oracle_be):
+    """A caller may change velocities, densities or masses and keep the neighbour list (no positions uploaded):
+    the entry-ordered mirrors the gather kernels stage must follow.  Also the Verlet operator called without a
+    density pass since the last list build."""
+    prm = H.derive_params(dp=0.05, c_f=10.0)
+    st = H.developed_state(prm, seed=31)
+    ref = st.copy()
+    H.initialise(oracle_be, ref, prm)
+    ch = make_channel(sphb, prm, st)
+    ch.initialise()
+    rng = np.random.default_rng(8)
+    nf = st.n_fluid
+    vel2 = ref.vel.copy(order="F")
+    vel2[:nf] *= 1.0 + 0.1 * rng.standard_normal((nf, 2))
+    rho2 = ref.rho.copy()
+    mass2 = ref.mass * (1.0 + 0.02 * rng.standard_normal(ref.mass.size))
+    ref.vel, ref.mass = vel2.copy(order="F"), mass2.copy()
+    ref.Vol = ref.mass / ref.rho                      # what sphb_ctx_upload derives with the masses (m:120)
+    ch.upload(vel=vel2, rho=rho2, mass=mass2)         # the list of initialise() stands
+    dt = H.reference_step(oracle_be, ref, prm)
+    ch.step()
+    s = ch.status()
+    assert abs(s["dt"] - dt) <= 1e-14 * dt
+    d = ch.download()
+    for f in FIELDS:
+        assert_close(d[f], getattr(ref, f), f)
+    # operator level: list -> Verlet substep with no density pass in between (volumes and B of the last step)
+    ch.neighbor_build()
+    pairs = oracle_be.neighbor_search(d["pos"], st.n_fluid, st.n_total, prm.h, prm.DL)
+    dt2 = 0.5 * dt
+    want = oracle_be.physics("integration_verlet", *pairs[:5], pairs[6], ref.Vol, ref.B, ref.rho, ref.mass, ref.pos, ref.vel,
+                             ref.drho_dt, ref.force_prior, dt2, st.n_fluid, st.n_total, prm.rho0, prm.p0, prm.c_f,
+                             ref.wall_vel, nargout=6)
+    ch.integration_verlet(dt2)
+    d2 = ch.download(("rho", "p", "pos", "vel", "drho_dt", "force"))
+    for f, w in zip(("rho", "p", "pos", "vel", "drho_dt", "force"), want):
+        assert_close(d2[f], np.asarray(w).reshape(d2[f].shape), "verlet " + f)
+    ch.close()
+
+
 def test_steps_against_golden_trajectory(sphb, H, golden):
     """The fused device step replays the reference's 120-step trajectory from the dp=0.05 lattice
     (sort at step 100): dt, pair count and wall shear every step, full state at steps 10 and 120."""

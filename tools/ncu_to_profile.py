@@ -49,6 +49,13 @@ for r in rows[2:]:
         "registers": num(r, "launch__registers_per_thread"), "grid": num(r, "launch__grid_size"),
         "dyn_smem_kb": num(r, "launch__shared_mem_per_block_dynamic"),
         "warp_instructions": num(r, "smsp__inst_executed.sum"),
+        # DADD + DMUL + DFMA thread instructions of the launch (per-cycle sums x elapsed SMSP cycles): numerator of
+        # the fp64 roofline in bench.py (peak = 64 per cycle and SM = sm__sass_thread_inst_executed_op_dfma_pred_on
+        # .sum.peak_sustained / 148)
+        "fp64_thread_instructions": (lambda c, ops: c * sum(ops) if c and all(o is not None for o in ops) else None)(
+            num(r, "smsp__cycles_elapsed.avg"),
+            [num(r, f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed") for op in ("dadd", "dmul", "dfma")]),
+        "fp64_peak_thread_inst_per_cycle": num(r, "sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained"),
         "threads_per_instruction": num(r, "smsp__thread_inst_executed_per_inst_executed.ratio"),
         "l1_hit_pct": num(r, "l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": num(r, "lts__t_sector_hit_rate.pct"),
         "stalls_per_issue": top,
