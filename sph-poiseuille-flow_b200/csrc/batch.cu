@@ -79,6 +79,7 @@ NbrBatchLaunch nbr_launch(const sphb_batch *b)
     L.n_tiles = b->n_tiles;
     L.tile_cap = b->tile_cap;
     L.ell_cap = b->ell_cap;
+    L.grid_ready = true;   // enqueue_physics always precedes the build and fuses the grid set-up
     L.st = b->st;
     return L;
 }
@@ -120,6 +121,7 @@ int batch_refresh(sphb_batch *b)
         r.S = c->view();
         r.sc = c->sc();
         r.shear_partials = c->shear_partials.as<double>();
+        r.F = neighbor_grid_fuse(c->nw);
         SPHB_TRY(neighbor_batch_fill(c->nw, c->pos.as<double2>(), b->h_nbr + k * b->nbr_rec, &b->h_scan[k]));
     }
     SPHB_TRY(csr_configure(b->tile_cap));
@@ -139,12 +141,14 @@ int enqueue_physics(sphb_batch *b, int n_inner)
     SPHB_TRY(csr_batch_density(L));
     SPHB_TRY(csr_batch_kgc(L));
     SPHB_TRY(csr_batch_force_fused(L, true));
-    SPHB_TRY(csr_batch_continuity(L, true, true));
+    // the step's last continuity pass also reduces the y range, derives the grid and zeroes the cell counters of the
+    // list build that follows (GridFuse)
+    SPHB_TRY(csr_batch_continuity(L, true, true, n_inner == 1));
     b->launches += 5;
     for (int s = 1; s < n_inner; ++s) {
         SPHB_TRY(csr_batch_time_step(L, inf, 0.0));
         SPHB_TRY(csr_batch_pressure(L));
-        SPHB_TRY(csr_batch_continuity(L, true, true));
+        SPHB_TRY(csr_batch_continuity(L, true, true, s == n_inner - 1));
         b->launches += 3;
     }
     return 0;

@@ -7,6 +7,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
+#include <climits>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -116,6 +117,56 @@ struct GridDesc {
     unsigned int ghost_anomaly;
 };
 
+#ifdef __CUDACC__
+// order-preserving integer image of a double (atomic min / max of y over all particles, nb:245-250)
+__device__ __forceinline__ long long ordered_key(double d)
+{
+    long long b = __double_as_longlong(d);
+    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double from_ordered_key(long long k)
+{
+    return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffLL));
+}
+// The grid of a build from the reduced y range (nb:253-258); re-arms the reduction and zeroes the build's totals.
+// Executed by ONE thread once every contribution to ymin_key / ymax_key is visible.
+__device__ __forceinline__ void grid_derive(GridDesc *g, double cell, int ncx, int cell_cap, int *flags, int *totals)
+{
+    const double y_min = from_ordered_key(atomicMin(&g->ymin_key, LLONG_MAX));
+    const double y_max = from_ordered_key(atomicMax(&g->ymax_key, LLONG_MIN));
+    int ncy = (int)ceil((y_max - y_min + 1e-12) / cell) + 1;   // nb:256
+    if (ncy < 1) ncy = 1;
+    if ((long long)ncy * ncx > (long long)cell_cap) {
+        atomicOr(flags, kErrCellCap);
+        ncy = cell_cap / ncx;
+        if (ncy < 1) ncy = 1;
+    }
+    g->y_min = y_min;
+    g->y_max = y_max;
+    g->cell = cell;
+    g->ncx = ncx;
+    g->ncy = ncy;
+    g->ncells = ncy * ncx;
+    g->ymin_key = LLONG_MAX;   // re-armed for the next build
+    g->ymax_key = LLONG_MIN;
+    g->ticket = 0u;
+    g->ghost_anomaly = 0u;     // raised again by the build's binning if need be
+    for (int k = 0; k < 8; ++k) totals[k] = 0;
+}
+#endif
+
+// What the continuity kernel prepares for the list build that follows it in a step of the unsharded resident
+// channel (so that the build starts at the binning): the y range of ALL rows (nb:245-250), the grid derived by the
+// last CTA (nb:253-258), the cell counters zeroed.  g = NULL: off.
+struct GridFuse {
+    GridDesc *g = nullptr;
+    int *flags = nullptr, *totals = nullptr;
+    int *cell_cnt = nullptr;
+    int n_cell_ints = 0;
+    double cell = 0.0;
+    int ncx = 0, cell_cap = 0;
+};
+
 // ------------------------------------------------------------------------------------------------
 // neighbour-list storage shared by the stateless search and the resident context
 // ------------------------------------------------------------------------------------------------
@@ -151,6 +202,8 @@ struct NeighborWork {
     bool half_valid = false;     // totals[0] holds the half-pair count of the current list
     bool tile_fitted = false;    // tile_cap has been fitted to the first build
     BuildMirrors mirrors;        // set by the resident context before every build
+    bool grid_ready = false;     // the caller's continuity kernel has derived the grid and zeroed the cell counters
+                                 // for THIS build (GridFuse): it starts at the binning
     DevBuf grid;                 // GridDesc
     DevBuf flags;                // int error flags
     DevBuf snap;                 // double2 [n_total]   wrapped x, y at build time
@@ -158,7 +211,7 @@ struct NeighborWork {
     DevBuf ent_of;               // int [n_total]       index of the real entry in the sorted entry array
     DevBuf cell_cnt;             // int [2*(cell_cap+1)] counts, then fill cursors
     DevBuf cell_start;           // int [cell_cap+1]
-    DevBuf tmp_key, tmp_pos, tmp_cell;   // entries as scattered (any order inside a cell)
+    DevBuf tmp_key, tmp_pos;     // entries as scattered (any order inside a cell)
     DevBuf ent_key;              // int [ent_cap]       (particle << 3) | (multi << 2) | kind, canonical order
     DevBuf ent_pos;              // double2 [ent_cap]   entry coordinates (ghosts shifted by -+DL)
     DevBuf tiles;                // TileDesc [n_tiles]
@@ -214,6 +267,8 @@ struct ProfScope {
 int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL, double y_min_hint,
                   double y_max_hint, int max_nbr_hint, int tile_cap_limit);
 int neighbor_reserve_ell(NeighborWork &w, int rows);
+// GridFuse record of the NEXT build (off unless the y-range reduction is armed and the context is not a slab)
+GridFuse neighbor_grid_fuse(const NeighborWork &w);
 int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exact, cudaStream_t st,
                    long long *launches, Prof *prof = nullptr);
 int neighbor_export_pairs(NeighborWork &w, size_t n_half, double *pair_i, double *pair_j, double *dx, double *dy,
@@ -245,6 +300,7 @@ struct NbrBatchLaunch {
     size_t ell_stride;      // entry capacity of every channel
     unsigned n_tiles;       // tiles of every channel
     int tile_cap, ell_cap;  // largest over the channels (size the walk's dynamic shared memory)
+    bool grid_ready;        // the step's last continuity pass has derived the grids and zeroed the cell counters
     cudaStream_t st;
 };
 size_t neighbor_batch_record_bytes();

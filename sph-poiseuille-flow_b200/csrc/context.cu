@@ -185,7 +185,16 @@ int do_shear(sphb_ctx *c)
     return 0;
 }
 
-int do_substep(sphb_ctx *c, double remain, double fixed_dt, bool wrap)
+// GridFuse record when the list build follows this continuity pass at once (sphb_ctx_step, run_dual)
+GridFuse fuse_for_next_build(sphb_ctx *c, bool build_follows)
+{
+    if (!build_follows) return GridFuse();
+    const GridFuse F = neighbor_grid_fuse(c->nw);
+    if (F.g) c->nw.grid_ready = true;   // consumed by the next neighbor_build
+    return F;
+}
+
+int do_substep(sphb_ctx *c, double remain, double fixed_dt, bool wrap, bool build_follows = false)
 {
     const StateView S = c->view();
     {
@@ -198,7 +207,7 @@ int do_substep(sphb_ctx *c, double remain, double fixed_dt, bool wrap)
     }
     {
         ProfScope ps(&c->kprof, kPfContinuity, c->st);
-        SPHB_TRY(csr_continuity(c->P, S, c->sc(), wrap, true, c->st));
+        SPHB_TRY(csr_continuity(c->P, S, c->sc(), wrap, true, fuse_for_next_build(c, build_follows), c->st));
     }
     c->launches += 3;
     return 0;
@@ -216,7 +225,7 @@ int do_publish_dt(sphb_ctx *c, double remain, double fixed_dt)
 
 // first substep of an outer step (after do_publish_dt and do_density): viscous + transport + pressure in one
 // gather, then continuity
-int do_fused_first_substep(sphb_ctx *c, bool wrap)
+int do_fused_first_substep(sphb_ctx *c, bool wrap, bool build_follows = false)
 {
     const StateView S = c->view();
     {
@@ -225,7 +234,7 @@ int do_fused_first_substep(sphb_ctx *c, bool wrap)
     }
     {
         ProfScope ps(&c->kprof, kPfContinuity, c->st);
-        SPHB_TRY(csr_continuity(c->P, S, c->sc(), wrap, true, c->st));
+        SPHB_TRY(csr_continuity(c->P, S, c->sc(), wrap, true, fuse_for_next_build(c, build_follows), c->st));
     }
     c->launches += 2;
     return 0;
@@ -393,6 +402,7 @@ SPHB_API int sphb_ctx_upload(sphb_ctx *c, const double *pos, const double *vel, 
             SPHB_TRY(plan_lists(c, lo, hi));
         }
         c->have_list = false;
+        c->nw.grid_ready = false;
     }
     if (vel) SPHB_TRY(up2(vel, c->vel));
     if (wall_vel) SPHB_TRY(up2(wall_vel, c->wall_vel));
@@ -577,7 +587,7 @@ SPHB_API int sphb_ctx_integration_verlet(sphb_ctx *c, double dt)
     const StateView S = c->view();
     SPHB_TRY(csr_time_step(c->P, S, c->sc(), std::numeric_limits<double>::infinity(), dt, c->st));
     SPHB_TRY(csr_pressure(c->P, S, c->sc(), c->st));
-    SPHB_TRY(csr_continuity(c->P, S, c->sc(), false, false, c->st));
+    SPHB_TRY(csr_continuity(c->P, S, c->sc(), false, false, GridFuse(), c->st));
     c->launches += 3;
     return 0;
 }
@@ -643,7 +653,7 @@ SPHB_API int sphb_ctx_step(sphb_ctx *c, double remain)
     SPHB_TRY(do_density(c));                                                          // m:254-255
     tick(c, 1);
     tick(c, 2);
-    SPHB_TRY(do_fused_first_substep(c, true));                                        // m:256-269
+    SPHB_TRY(do_fused_first_substep(c, true, true));                                  // m:256-269
     tick(c, 3);
     const int si = c->prm.sort_interval;
     if (si > 0 && c->h_step % si == 0 && c->h_step != 1) SPHB_TRY(do_sort(c));        // m:272-278
@@ -732,8 +742,8 @@ int enqueue_outer(sphb_ctx *c, int n_inner, bool with_sort)
     const double inf = std::numeric_limits<double>::infinity();
     SPHB_TRY(do_publish_dt(c, inf, 0.0));
     SPHB_TRY(do_density(c));
-    SPHB_TRY(do_fused_first_substep(c, true));
-    for (int s = 1; s < n_inner; ++s) SPHB_TRY(do_substep(c, inf, 0.0, true));
+    SPHB_TRY(do_fused_first_substep(c, true, n_inner == 1));
+    for (int s = 1; s < n_inner; ++s) SPHB_TRY(do_substep(c, inf, 0.0, true, s == n_inner - 1));
     if (with_sort) SPHB_TRY(do_sort(c));
     SPHB_TRY(do_neighbor(c));
     SPHB_TRY(do_shear(c));

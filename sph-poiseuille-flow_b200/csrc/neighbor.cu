@@ -11,11 +11,12 @@
 //   k_grid_setup    n_cell_y and cell count (nb:253-258)
 //   k_bin_count     wrap, bin, count real + ghost entries per cell (nb:270-296) + position snapshot
 //   scan            cell_start
-//   k_scatter       entry records into their cell ranges (atomic slot), then
-//   k_cell_canon    rank sort of each cell's range by DEcreasing insertion key: the reference's linked
-//                   list is walked "last inserted first", so a forward scan of the range is its walk order
-//   k_tile_setup    descriptors of the cell tiles (tile.cuh): staged entry ranges and their slots
-//   k_walk_tile     ONE pass per fluid particle over its 3x3 stencil out of shared memory, in the
+//   k_scatter       entry records into their cell ranges (atomic slot: any order inside a cell)
+//   k_walk_tile     one CTA per cell tile: its descriptor (tile.cuh: staged entry ranges and their slots), the
+//                   canonical order of every staged cell on the way into shared memory (rank sort by DEcreasing
+//                   insertion key: the reference's linked list is walked "last inserted first", so a forward scan
+//                   of the range is its walk order; the owner tile writes it to the entry arrays), then
+//                   ONE pass per fluid particle over its 3x3 stencil out of shared memory, in the
 //                   reference's order with its skip rules and its real/ghost dedup (seen_neighbor,
 //                   nb:342,383); rows of 16-bit tile-local entries, eight to a 128-bit store: no count
 //                   pass, no scatter atomics, no row sort
@@ -64,16 +65,6 @@ __device__ __forceinline__ bool row_dead(const NbrParams &P, int i)
     return P.alive != nullptr && i < P.n_fluid && P.alive[i] < 0;
 }
 
-__device__ __forceinline__ long long ordered_key(double d)
-{
-    long long b = __double_as_longlong(d);
-    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
-}
-__device__ __forceinline__ double from_ordered_key(long long k)
-{
-    return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffLL));
-}
-
 __device__ __forceinline__ int wrap_col(int c, int ncx)   // nb:57-67
 {
     c %= ncx;
@@ -100,7 +91,7 @@ __device__ __forceinline__ void spline2d(double r, double h, double sigma, doubl
 
 // Per-channel arguments of a BATCHED list build (ensembles of independent channels, batch.cu): the same
 // kernel bodies run for every channel in one grid, blockIdx.y = channel.
-struct NbrChan {
+struct __align__(16) NbrChan {   // (batch.cu strides its record array by the size rounded up to 16)
     NbrParams P;
     const double2 *pos;
     GridDesc *g;
@@ -111,7 +102,6 @@ struct NbrChan {
     int *cell_of, *ent_of;
     int *tmp_key;
     double2 *tmp_pos;
-    int *tmp_cell;
     int *ent_key;
     double2 *ent_pos;
     TileDesc *tiles;
@@ -169,26 +159,7 @@ __device__ __forceinline__ void yrange_grid_body(const double2 *__restrict__ pos
     __threadfence();
     if (atomicAdd(&g->ticket, 1u) != gridDim.x - 1) return;
     __threadfence();
-    const double y_min = from_ordered_key(atomicMin(&g->ymin_key, LLONG_MAX));
-    const double y_max = from_ordered_key(atomicMax(&g->ymax_key, LLONG_MIN));
-    int ncy = (int)ceil((y_max - y_min + 1e-12) / P.cell) + 1;   // nb:256
-    if (ncy < 1) ncy = 1;
-    if ((long long)ncy * P.ncx > (long long)P.cell_cap) {
-        atomicOr(flags, kErrCellCap);
-        ncy = P.cell_cap / P.ncx;
-        if (ncy < 1) ncy = 1;
-    }
-    g->y_min = y_min;
-    g->y_max = y_max;
-    g->cell = P.cell;
-    g->ncx = P.ncx;
-    g->ncy = ncy;
-    g->ncells = ncy * P.ncx;
-    g->ymin_key = LLONG_MAX;   // re-armed for the next build
-    g->ymax_key = LLONG_MIN;
-    g->ticket = 0u;
-    g->ghost_anomaly = 0u;     // raised again by this build's binning if need be
-    for (int k = 0; k < 8; ++k) totals[k] = 0;
+    grid_derive(g, P.cell, P.ncx, P.cell_cap, flags, totals);
 }
 __global__ void __launch_bounds__(256) k_yrange_grid(const double2 *__restrict__ pos, int n, GridDesc *g, NbrParams P,
                                                     int *flags, int *totals)
@@ -294,8 +265,7 @@ __global__ void __launch_bounds__(kBlock) k_bin_count_batch(const NbrChan *__res
 
 __device__ __forceinline__ void scatter_body(const double2 *__restrict__ pos, NbrParams P, const GridDesc *__restrict__ g,
                                              const int *__restrict__ cell_start, int *__restrict__ cell_fill,
-                                             int *__restrict__ tmp_key, double2 *__restrict__ tmp_pos,
-                                             int *__restrict__ tmp_cell)
+                                             int *__restrict__ tmp_key, double2 *__restrict__ tmp_pos)
 {
     load_counts(P);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,97 +278,51 @@ __device__ __forceinline__ void scatter_body(const double2 *__restrict__ pos, Nb
         const int s = cell_start[c] + atomicAdd(&cell_fill[c], 1);
         tmp_key[s] = (i << 3) | multi | 0;
         tmp_pos[s] = make_double2(b.xw, b.y);
-        tmp_cell[s] = c;
     }
     if (b.gcx_lo >= 0) {
         const int c = row + b.gcx_lo;
         const int s = cell_start[c] + atomicAdd(&cell_fill[c], 1);
         tmp_key[s] = (i << 3) | multi | 1;
         tmp_pos[s] = make_double2(b.xw - P.DL, b.y);
-        tmp_cell[s] = c;
     }
     if (b.gcx_hi >= 0) {
         const int c = row + b.gcx_hi;
         const int s = cell_start[c] + atomicAdd(&cell_fill[c], 1);
         tmp_key[s] = (i << 3) | multi | 2;
         tmp_pos[s] = make_double2(b.xw + P.DL, b.y);
-        tmp_cell[s] = c;
     }
 }
 __global__ void __launch_bounds__(kBlock) k_scatter(const double2 *__restrict__ pos, NbrParams P,
                                                    const GridDesc *__restrict__ g,
                                                    const int *__restrict__ cell_start, int *__restrict__ cell_fill,
-                                                   int *__restrict__ tmp_key, double2 *__restrict__ tmp_pos,
-                                                   int *__restrict__ tmp_cell)
+                                                   int *__restrict__ tmp_key, double2 *__restrict__ tmp_pos)
 {
-    scatter_body(pos, P, g, cell_start, cell_fill, tmp_key, tmp_pos, tmp_cell);
+    scatter_body(pos, P, g, cell_start, cell_fill, tmp_key, tmp_pos);
 }
 __global__ void __launch_bounds__(kBlock) k_scatter_batch(const NbrChan *__restrict__ chan)
 {
     const NbrChan &c = chan[blockIdx.y];
-    scatter_body(c.pos, c.P, c.g, c.cell_start, c.cell_cnt + ((size_t)c.P.cell_cap + 1), c.tmp_key, c.tmp_pos, c.tmp_cell);
-}
-
-// Canonical order inside a cell = DEcreasing insertion key (the reference's linked list is walked "last
-// inserted first", so a forward scan of the range is its walk order).  Rank sort, one thread per entry:
-// the rank of an entry is the number of larger keys in its cell (keys are distinct); every load is
-// independent.  Also records where each particle's REAL entry ends up (rows are indexed by entry).
-__device__ __forceinline__ void cell_canon_body(const GridDesc *__restrict__ g, int ent_cap,
-                                                const int *__restrict__ cell_start, const int *__restrict__ tmp_key,
-                                                const double2 *__restrict__ tmp_pos, const int *__restrict__ tmp_cell,
-                                                int *__restrict__ ent_key, double2 *__restrict__ ent_pos,
-                                                int *__restrict__ ent_of, int *__restrict__ flags)
-{
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = g->n_entries;
-    if (a == 0 && n > ent_cap) atomicOr(flags, kErrCsrCap);
-    if (a >= n || a >= ent_cap) return;
-    const int c = tmp_cell[a];
-    const int s = cell_start[c], e = cell_start[c + 1];
-    const int key = tmp_key[a];
-    int rank = 0;
-    for (int b = s; b < e; ++b) rank += tmp_key[b] > key ? 1 : 0;
-    const int dst = s + rank;
-    if (dst >= ent_cap) return;
-    ent_key[dst] = key;
-    ent_pos[dst] = tmp_pos[a];
-    if ((key & 3) == 0) ent_of[key >> 3] = dst;
-}
-__global__ void __launch_bounds__(kBlock) k_cell_canon(const GridDesc *__restrict__ g, int ent_cap,
-                                                      const int *__restrict__ cell_start,
-                                                      const int *__restrict__ tmp_key,
-                                                      const double2 *__restrict__ tmp_pos,
-                                                      const int *__restrict__ tmp_cell, int *__restrict__ ent_key,
-                                                      double2 *__restrict__ ent_pos, int *__restrict__ ent_of,
-                                                      int *__restrict__ flags)
-{
-    cell_canon_body(g, ent_cap, cell_start, tmp_key, tmp_pos, tmp_cell, ent_key, ent_pos, ent_of, flags);
-}
-__global__ void __launch_bounds__(kBlock) k_cell_canon_batch(const NbrChan *__restrict__ chan)
-{
-    const NbrChan &c = chan[blockIdx.y];
-    cell_canon_body(c.g, (int)c.P.ell_stride, c.cell_start, c.tmp_key, c.tmp_pos, c.tmp_cell, c.ent_key, c.ent_pos, c.ent_of,
-                    c.flags);
+    scatter_body(c.pos, c.P, c.g, c.cell_start, c.cell_cnt + ((size_t)c.P.cell_cap + 1), c.tmp_key, c.tmp_pos);
 }
 
 // One descriptor per tile (tile.cuh): entry ranges of the (kTileRows + 2) x (w + 2) cell neighbourhood and
 // their slots.  One warp per tile: lane (3 r + k) fetches range k of staged row r, the slot offsets are a
-// warp prefix sum, lane 0 writes the rest.
-__device__ __forceinline__ void tile_setup_body(const GridDesc *__restrict__ g, int ncx, int slab, int w, unsigned n_tiles,
-                                                int cap, int ent_cap, const int *__restrict__ cell_start,
-                                                TileDesc *__restrict__ tiles, int *__restrict__ totals,
-                                                int *__restrict__ flags)
+// warp prefix sum, lane 0 writes the rest.  Called by the first warp of the walk's CTA for its own tile (the
+// descriptor is then read by every gather kernel of the step).
+__device__ __forceinline__ void tile_setup_warp(unsigned t, int lane, const GridDesc *__restrict__ g, int ncx, int slab, int w,
+                                                unsigned n_tiles, int cap, int ent_cap, const int *__restrict__ cell_start,
+                                                TileDesc &T, TileDesc *tiles, int *__restrict__ totals, int *__restrict__ flags)
 {
-    const unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (t >= n_tiles) return;
+    if (t >= n_tiles) {   // (never: one CTA per tile)
+        if (lane == 0) T.flags = 0;
+        return;
+    }
     const int ncy = g->ncy;
     const int tpr = tiles_per_row(ncx, w);
     const int cy0 = (int)(t / (unsigned)tpr) * kTileRows, cx0 = (int)(t % (unsigned)tpr) * w;
     const int cx1 = min(cx0 + w, ncx);
     const int a = max(cx0 - 1, 0), b = min(cx1 + 1, ncx);
     const bool valid = cy0 < ncy;
-    TileDesc &T = tiles[t];
     // lane -> (staged row r, range k): 0 main columns a..b-1, 1 wrap column ncx-1, 2 wrap column 0
     int rb = 0, re = 0;
     if (lane < kStageRows * 3) {
@@ -426,7 +350,7 @@ __device__ __forceinline__ void tile_setup_body(const GridDesc *__restrict__ g, 
         if (lane >= d) inc += v;
     }
     const int used = __shfl_sync(0xffffffffu, inc, kStageRows * 3 - 1);
-    const bool fits = __all_sync(0xffffffffu, re <= ent_cap);   // entry overflow is reported by k_cell_canon
+    const bool fits = __all_sync(0xffffffffu, re <= ent_cap);   // (entry overflow itself is reported by the walk)
     if (lane < kStageRows * 3) {
         T.seg[lane].b = rb;
         T.seg[lane].e = re;
@@ -464,22 +388,10 @@ __device__ __forceinline__ void tile_setup_body(const GridDesc *__restrict__ g, 
         T.flags = f;
         if (valid) atomicMax(&totals[3], used + 1);
     }
+    // the descriptor (built in the CTA's shared memory) to the global array the gather kernels read
+    __syncwarp();
+    if (lane < (int)(sizeof(TileDesc) / 16)) reinterpret_cast<int4 *>(tiles + t)[lane] = reinterpret_cast<const int4 *>(&T)[lane];
 }
-__global__ void __launch_bounds__(kBlock) k_tile_setup(const GridDesc *__restrict__ g, int ncx, int slab, int w,
-                                                      unsigned n_tiles, int cap, int ent_cap,
-                                                      const int *__restrict__ cell_start,
-                                                      TileDesc *__restrict__ tiles, int *__restrict__ totals,
-                                                      int *__restrict__ flags)
-{
-    tile_setup_body(g, ncx, slab, w, n_tiles, cap, ent_cap, cell_start, tiles, totals, flags);
-}
-__global__ void __launch_bounds__(kBlock) k_tile_setup_batch(const NbrChan *__restrict__ chan)
-{
-    const NbrChan &c = chan[blockIdx.y];
-    tile_setup_body(c.g, c.P.ncx, c.P.slab, c.tile_w, c.n_tiles, c.tile_cap, (int)c.P.ell_stride, c.cell_start, c.tiles,
-                    c.totals, c.flags);
-}
-
 // nb:357-372 for "particle a (wrapped xa, ya) meets an entry at (ex, ey)": minimum image, cut-off and
 // kernel-support tests with the reference's arithmetic.  m = -1/0/+1 is the minimum-image shift.
 __device__ __forceinline__ bool support_exact(double r2, const NbrParams &P)
@@ -782,58 +694,114 @@ __device__ __forceinline__ int general_walk(const NbrParams &P, const TileDesc &
     return count;
 }
 
+// What the walk needs to do the work of the former k_cell_canon and k_tile_setup launches for its own tile.
+struct WalkSetup {
+    const int *tmp_key;        // entries as scattered: any order inside a cell
+    const double2 *tmp_pos;
+    int *ent_key;              // canonical order (written for the tile's own cells)
+    double2 *ent_pos;
+    int *ent_of;
+    unsigned n_tiles;
+    int slab;
+};
+
+// slot range [sb, se) of the staged cell that holds slot s (main segments: binary search of the entry in the
+// staged cell starts of its row; a wrap segment is one cell)
+__device__ __forceinline__ void staged_cell_of_slot(const TileDesc &T, const TileCellStarts &cs, int s, int &sb, int &se)
+{
+    int k = 0;
+#pragma unroll
+    for (int j = 1; j < kStageRows * 3; ++j) k += (T.seg[j].off <= s) ? 1 : 0;
+    const TileSeg sg = T.seg[k];
+    if (k % 3 != 0) {
+        sb = sg.off;
+        se = sg.off + (sg.e - sg.b);
+        return;
+    }
+    const int r = k / 3;
+    const int e = sg.b + (s - sg.off);
+    int lo = 0, hi = T.b - T.a;   // cs[r][lo] <= e < cs[r][hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (cs[r][mid] <= e) lo = mid;
+        else hi = mid;
+    }
+    sb = sg.off + (cs[r][lo] - sg.b);
+    se = sg.off + (cs[r][lo + 1] - sg.b);
+}
+
 template <bool HALF>
 __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__restrict__ g, TileDesc *tiles, BuildMirrors M,
-                                               int tile_w, const int *__restrict__ cell_start,
+                                               WalkSetup W, int tile_w, const int *__restrict__ cell_start,
                                                const double2 *__restrict__ snap, const int *__restrict__ cell_of,
-                                               const int *__restrict__ ent_key, const double2 *__restrict__ ent_pos,
                                                uint4 *ell_q, int *__restrict__ cnt, int *__restrict__ totals,
                                                int *__restrict__ flags, int cap)
 {
     load_counts(P);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ TileDesc T;
-    double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);
-    int *s_key = reinterpret_cast<int *>(s_xy + cap);
+    double2 *s_xy = reinterpret_cast<double2 *>(smem_raw);           // layout: s_xy, s_rawx, s_key, s_rawk, general-walk rows
+    int *s_key = reinterpret_cast<int *>(s_xy + 2 * (size_t)cap);
     const int ncx = P.ncx, ncy = g->ncy;
     __shared__ TileCellStarts s_cs;
-    const unsigned tile_id = walk_tile_of_block(blockIdx.x, tiles_per_row(ncx, tile_w), gridDim.x);
-    tile_load(T, tiles, tile_id);
+    const int tpr = tiles_per_row(ncx, tile_w);
+    const unsigned tile_id = walk_tile_of_block(blockIdx.x, tpr, gridDim.x);
+    // The first warp builds the tile's descriptor (what k_tile_setup used to write for every tile in a launch of
+    // its own) in shared memory and copies it to the global array; the other warps fetch the cell starts of the
+    // staged rows meanwhile (both only need cell_start).
+    if (threadIdx.x < 32) {
+        tile_setup_warp(tile_id, (int)threadIdx.x, g, ncx, W.slab, tile_w, W.n_tiles, cap, (int)P.ell_stride, cell_start, T,
+                        tiles, totals, flags);
+    } else {
+        const int cy0 = (int)(tile_id / (unsigned)tpr) * kTileRows, cx0 = (int)(tile_id % (unsigned)tpr) * tile_w;
+        const int a = max(cx0 - 1, 0), b = min(min(cx0 + tile_w, ncx) + 1, ncx);
+        for (int k = (int)threadIdx.x - 32; k < kStageRows * (kMaxTileW + 3); k += kTileThreads - 32) {
+            const int r = k / (kMaxTileW + 3), c = k % (kMaxTileW + 3);
+            const int row = cy0 + r - 1;
+            s_cs[r][c] = (row >= 0 && row < ncy && c <= b - a) ? cell_start[(size_t)row * ncx + a + c] : 0;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 32 && g->n_entries > (int)P.ell_stride) atomicOr(flags, kErrCsrCap);
+    }
     __syncthreads();
     if (!(T.flags & kTileValid)) return;
     int walls = 0;   // does the staged neighbourhood hold a wall entry?  (kTileHasWall, read by the gather kernels)
-    for (int k = threadIdx.x; k < kStageRows * (kMaxTileW + 3); k += kTileThreads) {
-        const int r = k / (kMaxTileW + 3), c = k % (kMaxTileW + 3);
-        const int row = T.cy0 + r - 1;
-        s_cs[r][c] = (row >= 0 && row < ncy && c <= T.b - T.a) ? cell_start[(size_t)row * ncx + T.a + c] : 0;
-    }
-#if SPHB_FLAT_STAGING
-    struct StageRec {
-        double2 xy;
-        int key;
-    };
-    tile_stage_flat(
-        T,
-        [&](int e) {
-            StageRec r;
-            r.key = ent_key[e];
-            r.xy = ent_pos[e];
-            return r;
-        },
-        [&](int slot, const StageRec &r) {
-            s_key[slot] = r.key;
-            s_xy[slot] = r.xy;
-            walls |= (r.key >> 3) >= P.n_fluid ? 1 : 0;
-        });
-#else
-    SPHB_TILE_FOR_STAGED(T, e, slot)
+    // Staging with the canonical order made on the way (the former k_cell_canon): inside a cell the reference's
+    // linked list is walked "last inserted first", i.e. by DEcreasing insertion key (keys are distinct), so a
+    // forward scan of the canonical range is its walk order.  Pass A stages keys and positions as scattered; pass B
+    // ranks every entry inside its cell (the number of larger keys) and moves it to the ranked slot, shared memory
+    // to shared memory.  Every tile that stages a cell derives the same order; the tile that OWNS the cell writes
+    // it to the entry arrays the gather kernels stage from.
+    double2 *s_rawx = s_xy + cap;
+    int *s_rawk = s_key + cap;
     {
-        const int key = ent_key[e];
-        s_key[slot] = key;
-        s_xy[slot] = ent_pos[e];
+        struct StageRec {
+            double2 xy;
+            int key;
+        };
+        tile_stage_flat(
+            T,
+            [&](int e) {
+                StageRec r;
+                r.key = W.tmp_key[e];
+                r.xy = W.tmp_pos[e];
+                return r;
+            },
+            [&](int slot, const StageRec &r) {
+                s_rawk[slot] = r.key;
+                s_rawx[slot] = r.xy;
+            });
+    }
+    __syncthreads();
+    for (int slot = (int)threadIdx.x; slot < T.n_staged; slot += kTileThreads) {
+        const int key = s_rawk[slot];
+        int sb, se;
+        staged_cell_of_slot(T, s_cs, slot, sb, se);
+        int rank = 0;
+        for (int b = sb; b < se; ++b) rank += s_rawk[b] > key ? 1 : 0;
+        s_key[sb + rank] = key;
+        s_xy[sb + rank] = s_rawx[slot];
         walls |= (key >> 3) >= P.n_fluid ? 1 : 0;
     }
-#endif
     walls = __syncthreads_or(walls);
     if (walls && threadIdx.x == 0) tiles[tile_id].flags = T.flags | kTileHasWall;
 
@@ -847,7 +815,7 @@ __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__re
     __shared__ int gq_n;
     if (threadIdx.x == 0) gq_n = 0;
     __syncthreads();
-    unsigned short *row_sm = reinterpret_cast<unsigned short *>(s_key + cap) + (size_t)(threadIdx.x >> 5) * P.ell_cap;
+    unsigned short *row_sm = reinterpret_cast<unsigned short *>(s_key + 2 * (size_t)cap) + (size_t)(threadIdx.x >> 5) * P.ell_cap;
     int t_full = 0, t_max = 0;
     const int n_own = tile_own_total(T);
     for (int base = 0; base < n_own; base += kTileThreads) {   // warp-uniform trip count (collectives below)
@@ -858,6 +826,11 @@ __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__re
             tile_own_locate(T, v, orow, ew, slot_i);
             const int key_i = s_key[slot_i];
             const int i = key_i >> 3;
+            if ((size_t)ew < P.ell_stride) {   // the canonical entry arrays of the tile's own cells
+                W.ent_key[ew] = key_i;
+                W.ent_pos[ew] = s_xy[slot_i];
+                if ((key_i & 3) == 0) W.ent_of[i] = ew;
+            }
             // entry-ordered mirrors of the row's velocity and wall weight (BuildMirrors): loaded here, stored
             // after the walk so that the latency hides behind it
             const bool mirror = M.e_vel != nullptr && (key_i & 3) == 0 && (size_t)ew < stride;
@@ -988,24 +961,30 @@ __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__re
     }
 }
 template <bool HALF>
-__global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, const GridDesc *__restrict__ g,
-                                                           TileDesc *tiles, BuildMirrors M, int tile_w,
+__global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, const GridDesc *__restrict__ g, TileDesc *tiles,
+                                                           BuildMirrors M, WalkSetup W, int tile_w,
                                                            const int *__restrict__ cell_start,
                                                            const double2 *__restrict__ snap,
-                                                           const int *__restrict__ cell_of,
-                                                           const int *__restrict__ ent_key,
-                                                           const double2 *__restrict__ ent_pos, uint4 *ell_q,
+                                                           const int *__restrict__ cell_of, uint4 *ell_q,
                                                            int *__restrict__ cnt, int *__restrict__ totals,
                                                            int *__restrict__ flags, int cap)
 {
-    walk_tile_body<HALF>(P, g, tiles, M, tile_w, cell_start, snap, cell_of, ent_key, ent_pos, ell_q, cnt, totals, flags, cap);
+    walk_tile_body<HALF>(P, g, tiles, M, W, tile_w, cell_start, snap, cell_of, ell_q, cnt, totals, flags, cap);
 }
 // full lists only (the half list is the stateless MEX export)
 __global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile_batch(const NbrChan *__restrict__ chan)
 {
     const NbrChan &c = chan[blockIdx.y];
-    walk_tile_body<false>(c.P, c.g, c.tiles, c.M, c.tile_w, c.cell_start, c.snap, c.cell_of, c.ent_key, c.ent_pos, c.ell_q,
-                          c.ell_cnt, c.totals, c.flags, c.tile_cap);
+    WalkSetup W;
+    W.tmp_key = c.tmp_key;
+    W.tmp_pos = c.tmp_pos;
+    W.ent_key = c.ent_key;
+    W.ent_pos = c.ent_pos;
+    W.ent_of = c.ent_of;
+    W.n_tiles = c.n_tiles;
+    W.slab = c.P.slab;
+    walk_tile_body<false>(c.P, c.g, c.tiles, c.M, W, c.tile_w, c.cell_start, c.snap, c.cell_of, c.ell_q, c.ell_cnt, c.totals,
+                          c.flags, c.tile_cap);
 }
 
 // Number of reference half pairs inside a FULL row set (status / export sizing only): entries whose
@@ -1202,7 +1181,7 @@ int set_walk_smem(size_t bytes)
 
 void NeighborWork::release_all()
 {
-    DevBuf *all[] = {&grid, &flags, &snap, &cell_of, &ent_of, &cell_cnt, &cell_start, &tmp_key, &tmp_pos, &tmp_cell,
+    DevBuf *all[] = {&grid, &flags, &snap, &cell_of, &ent_of, &cell_cnt, &cell_start, &tmp_key, &tmp_pos,
                      &ent_key, &ent_pos, &tiles, &ell_cnt, &ell_q, &half_cnt, &half_ptr, &scan_tmp, &totals};
     for (DevBuf *b : all) b->release();
 }
@@ -1278,7 +1257,6 @@ int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL
     SPHB_TRY(w.cell_start.reserve(((size_t)w.cell_cap + 1) * sizeof(int)));
     SPHB_TRY(w.tmp_key.reserve(3 * nt * sizeof(int)));
     SPHB_TRY(w.tmp_pos.reserve(3 * nt * sizeof(double2)));
-    SPHB_TRY(w.tmp_cell.reserve(3 * nt * sizeof(int)));
     SPHB_TRY(w.ent_key.reserve(ecap * sizeof(int)));
     SPHB_TRY(w.ent_pos.reserve(ecap * sizeof(double2)));
     if (resized) {
@@ -1287,6 +1265,12 @@ int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL
     }
     SPHB_TRY(neighbor_reserve_ell(w, max_nbr_hint > 0 ? max_nbr_hint : kDefaultEllRows));
     w.tile_cap_limit = tile_cap_limit > 0 && tile_cap_limit < kMaxSlots ? tile_cap_limit : kMaxSlots;
+    {   // what the walk itself can stage: two copies of (position, key) per slot (as scattered + canonical) beside the
+        // rows under assembly of the general walkers, in 227 KB of shared memory
+        const size_t rows = std::max((size_t)(kTileThreads / 32) * (size_t)w.ell_cap * sizeof(unsigned short), (size_t)16 * 1024);
+        const int walk_limit = (int)((227 * 1024 - 4096 - std::min(rows, (size_t)96 * 1024)) / (2 * kWalkSlotBytes));
+        if (w.tile_cap_limit > walk_limit) w.tile_cap_limit = walk_limit;
+    }
     if (resized || regrid || w.tile_w == 0) {
         w.tile_fitted = false;
         // ~0.9 own entries per thread for a uniformly filled grid; the first exact build narrows the
@@ -1301,6 +1285,22 @@ int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL
         SPHB_TRY(plan_tiles(w, w.tile_w));
     }
     return 0;
+}
+
+GridFuse neighbor_grid_fuse(const NeighborWork &w)
+{
+    GridFuse F;
+    if (w.slab || !w.grid_armed || !w.grid.p || !w.cell_cnt.p) return F;
+    const NbrParams P = make_params(w);
+    F.g = w.grid.as<GridDesc>();
+    F.flags = w.flags.as<int>();
+    F.totals = w.totals.as<int>();
+    F.cell_cnt = w.cell_cnt.as<int>();
+    F.n_cell_ints = 2 * (w.cell_cap + 1);
+    F.cell = P.cell;
+    F.ncx = P.ncx;
+    F.cell_cap = P.cell_cap;
+    return F;
 }
 
 // Builds the list from `pos` (device, double2[n_total]).  A row longer than the list columns or a
@@ -1324,17 +1324,21 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
             k_grid_init<<<1, 1, 0, st>>>(g);
             w.grid_armed = true;
         }
-        int blocks = (nt + 255) / 256;
-        if (blocks > 148 * 4) blocks = 148 * 4;
-        k_yrange_grid<<<blocks, 256, 0, st>>>(pos, nt, g, P, flags, w.totals.as<int>());
-        SPHB_CUDA(cudaMemsetAsync(cell_cnt, 0, 2 * ((size_t)w.cell_cap + 1) * sizeof(int), st));
+        if (!w.grid_ready) {   // (else the caller's continuity kernel has done both: GridFuse)
+            int blocks = (nt + 255) / 256;
+            if (blocks > 148 * 4) blocks = 148 * 4;
+            k_yrange_grid<<<blocks, 256, 0, st>>>(pos, nt, g, P, flags, w.totals.as<int>());
+            SPHB_CUDA(cudaMemsetAsync(cell_cnt, 0, 2 * ((size_t)w.cell_cap + 1) * sizeof(int), st));
+            nl += 1;
+        }
+        w.grid_ready = false;
     }
     {
         ProfScope ps(prof, kPfNbrBin, st);
         k_bin_count<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.snap.as<double2>(), w.cell_of.as<int>(), cell_cnt,
                                                      &g->ghost_anomaly);
     }
-    nl += 2;
+    nl += 1;
     {
         ProfScope ps(prof, kPfNbrScan, st);
         SPHB_TRY(exclusive_scan_i32(cell_cnt, w.cell_start.as<int>(), (size_t)w.cell_cap, w.scan_tmp, &g->n_entries, st,
@@ -1343,39 +1347,37 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
     {
         ProfScope ps(prof, kPfNbrScatter, st);
         k_scatter<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.cell_start.as<int>(), cell_fill, w.tmp_key.as<int>(),
-                                                   w.tmp_pos.as<double2>(), w.tmp_cell.as<int>());
+                                                   w.tmp_pos.as<double2>());
     }
-    {
-        ProfScope ps(prof, kPfNbrCanon, st);
-        k_cell_canon<<<grid_for(w.ell_stride), kBlock, 0, st>>>(g, (int)w.ell_stride, w.cell_start.as<int>(),
-                                                              w.tmp_key.as<int>(), w.tmp_pos.as<double2>(),
-                                                              w.tmp_cell.as<int>(), w.ent_key.as<int>(),
-                                                              w.ent_pos.as<double2>(), w.ent_of.as<int>(), flags);
-    }
-    nl += 2;
+    nl += 1;
+    WalkSetup W;
+    W.tmp_key = w.tmp_key.as<int>();
+    W.tmp_pos = w.tmp_pos.as<double2>();
+    W.ent_key = w.ent_key.as<int>();
+    W.ent_pos = w.ent_pos.as<double2>();
+    W.ent_of = w.ent_of.as<int>();
+    W.slab = P.slab;
 
     for (int attempt = 0; attempt < 8; ++attempt) {
         ProfScope ps(prof, kPfNbrWalk, st);
         if (attempt > 0) SPHB_CUDA(cudaMemsetAsync(w.totals.p, 0, 8 * sizeof(int), st));
-        k_tile_setup<<<grid_for((size_t)w.n_tiles * 32), kBlock, 0, st>>>(g, P.ncx, P.slab, w.tile_w, w.n_tiles, w.tile_cap,
-                                                            (int)w.ell_stride, w.cell_start.as<int>(), w.tiles.as<TileDesc>(),
-                                                            w.totals.as<int>(), flags);
-        const size_t smem = (size_t)w.tile_cap * kWalkSlotBytes + (size_t)(kTileThreads / 32) * w.ell_cap * sizeof(unsigned short);
+        W.n_tiles = w.n_tiles;
+        // staged keys + positions, the rows under assembly of the general walkers, the keys as scattered
+        const size_t smem = 2 * (size_t)w.tile_cap * kWalkSlotBytes + (size_t)(kTileThreads / 32) * w.ell_cap * sizeof(unsigned short);
+        if (smem > (size_t)227 * 1024)
+            return set_error("SPH:Neighbor:entryCapacity", "a tile of %d staged entries with rows of up to %d neighbours "
+                             "exceeds the shared memory of the neighbour walk", w.tile_cap, w.ell_cap);
         SPHB_TRY(set_walk_smem(smem));
-        // one CTA per tile; rows beyond the device-side n_cell_y exit at once
+        // one CTA per tile (descriptor + canonical cell order + walk); rows beyond the device-side n_cell_y exit at once
         if (half_only)
             k_walk_tile<true><<<w.n_tiles, kTileThreads, smem, st>>>(
-                P, g, w.tiles.as<TileDesc>(), BuildMirrors(), w.tile_w, w.cell_start.as<int>(), w.snap.as<double2>(),
-                w.cell_of.as<int>(),
-                w.ent_key.as<int>(), w.ent_pos.as<double2>(), w.ell_q.as<uint4>(), w.ell_cnt.as<int>(),
-                w.totals.as<int>(), flags, w.tile_cap);
+                P, g, w.tiles.as<TileDesc>(), BuildMirrors(), W, w.tile_w, w.cell_start.as<int>(), w.snap.as<double2>(),
+                w.cell_of.as<int>(), w.ell_q.as<uint4>(), w.ell_cnt.as<int>(), w.totals.as<int>(), flags, w.tile_cap);
         else
             k_walk_tile<false><<<w.n_tiles, kTileThreads, smem, st>>>(
-                P, g, w.tiles.as<TileDesc>(), w.mirrors, w.tile_w, w.cell_start.as<int>(), w.snap.as<double2>(),
-                w.cell_of.as<int>(),
-                w.ent_key.as<int>(), w.ent_pos.as<double2>(), w.ell_q.as<uint4>(), w.ell_cnt.as<int>(),
-                w.totals.as<int>(), flags, w.tile_cap);
-        nl += 2;
+                P, g, w.tiles.as<TileDesc>(), w.mirrors, W, w.tile_w, w.cell_start.as<int>(), w.snap.as<double2>(),
+                w.cell_of.as<int>(), w.ell_q.as<uint4>(), w.ell_cnt.as<int>(), w.totals.as<int>(), flags, w.tile_cap);
+        nl += 1;
         if (!exact) break;
         int host[4] = {0, 0, 0, 0};
         SPHB_CUDA(cudaMemcpyAsync(host, w.totals.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1445,7 +1447,6 @@ int neighbor_batch_fill(NeighborWork &w, const double2 *pos, void *host_record, 
     c.ent_of = w.ent_of.as<int>();
     c.tmp_key = w.tmp_key.as<int>();
     c.tmp_pos = w.tmp_pos.as<double2>();
-    c.tmp_cell = w.tmp_cell.as<int>();
     c.ent_key = w.ent_key.as<int>();
     c.ent_pos = w.ent_pos.as<double2>();
     c.tiles = w.tiles.as<TileDesc>();
@@ -1473,20 +1474,21 @@ int neighbor_batch_build(const NbrBatchLaunch &L, long long *launches)
     long long nl = 0;
     int blocks = (nt + 255) / 256;
     if (blocks > 148 * 4) blocks = 148 * 4;
-    k_yrange_grid_batch<<<dim3((unsigned)blocks, ny), 256, 0, L.st>>>(chan);
-    const int n_ints = 2 * (L.cell_cap + 1);
-    k_zero_cells_batch<<<dim3(std::max(1u, std::min(grid_for((size_t)n_ints), 64u)), ny), kBlock, 0, L.st>>>(chan, n_ints);
+    if (!L.grid_ready) {
+        k_yrange_grid_batch<<<dim3((unsigned)blocks, ny), 256, 0, L.st>>>(chan);
+        const int n_ints = 2 * (L.cell_cap + 1);
+        k_zero_cells_batch<<<dim3(std::max(1u, std::min(grid_for((size_t)n_ints), 64u)), ny), kBlock, 0, L.st>>>(chan, n_ints);
+        nl += 2;
+    }
     k_bin_count_batch<<<dim3(grid_for((size_t)nt), ny), kBlock, 0, L.st>>>(chan);
-    nl += 3;
+    nl += 1;
     SPHB_TRY(exclusive_scan_i32_batch(L.scan, L.n_chan, (size_t)L.cell_cap, L.st, &nl));
     k_scatter_batch<<<dim3(grid_for((size_t)nt), ny), kBlock, 0, L.st>>>(chan);
-    k_cell_canon_batch<<<dim3(grid_for(L.ell_stride), ny), kBlock, 0, L.st>>>(chan);
-    k_tile_setup_batch<<<dim3(grid_for((size_t)L.n_tiles * 32), ny), kBlock, 0, L.st>>>(chan);
-    const size_t smem = (size_t)L.tile_cap * kWalkSlotBytes + (size_t)(kTileThreads / 32) * L.ell_cap * sizeof(unsigned short);
+    const size_t smem = 2 * (size_t)L.tile_cap * kWalkSlotBytes + (size_t)(kTileThreads / 32) * L.ell_cap * sizeof(unsigned short);
     static SmemGrant grant;
     SPHB_TRY(grant_smem(grant, k_walk_tile_batch, smem));
     k_walk_tile_batch<<<dim3(L.n_tiles, ny), kTileThreads, smem, L.st>>>(chan);
-    nl += 4;
+    nl += 2;
     SPHB_CUDA(cudaGetLastError());
     if (launches) *launches += nl;
     return 0;

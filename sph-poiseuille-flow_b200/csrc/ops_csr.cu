@@ -1006,11 +1006,19 @@ struct ContinuityK {
     PhysParams P;
     double dt;
     int do_wrap;
+    int track_y;                // GridFuse: reduce the y range of every row for the coming list build
     double speed;
+    long long ykmin, ykmax;     // ordered keys (common.cuh)
     __device__ __forceinline__ int bulk_fields(const TileDesc &) const { return 3; }
     __device__ __forceinline__ const double2 *src(const StateView &S, int f) const
     {
         return f == 0 ? S.ent_pos : (f == 1 ? S.e_vn : S.e_pV);
+    }
+    __device__ __forceinline__ void see_y(double y)
+    {
+        const long long k = ordered_key(y);
+        ykmin = k < ykmin ? k : ykmin;
+        ykmax = k > ykmax ? k : ykmax;
     }
     __device__ __forceinline__ void dummy(unsigned char *buf, int cap, int slot) const
     {
@@ -1055,6 +1063,7 @@ struct ContinuityK {
                 S.drho_dt[i] = 0.0;   // ph:1114-1116
                 S.p[i] = 0.0;         // ph:1449
                 S.vel[i] = make_double2(0.0, 0.0);   // ph:1405-1408, m:270
+                if (track_y) see_y(S.pos[i].y);
                 continue;
             }
             const double2 pi = s_xy[si];
@@ -1086,6 +1095,9 @@ struct ContinuityK {
                 double2 x = S.pos[i];
                 x.x = wrap_x(x.x, P.DL);
                 S.pos[i] = x;
+                if (track_y) see_y(x.y);
+            } else if (track_y) {
+                see_y(S.pos[i].y);
             }
             S.vel[i] = vi;   // nobody reads `vel` in this kernel (neighbours read the staged new velocity): commit in place
             if (i < P.nfo) speed = fmax(speed, sqrt(vi.x * vi.x + vi.y * vi.y));
@@ -1098,14 +1110,18 @@ struct ContinuityK {
 };
 
 __device__ __forceinline__ void continuity_tiles(PhysParams P, const StateView &S, DevScalars *sc, int do_wrap, int advance_clock,
-                                                 unsigned cta, unsigned n_ctas)
+                                                 const GridFuse &F, unsigned cta, unsigned n_ctas)
 {
     load_counts(P);
+    const bool fuse = F.g != nullptr && advance_clock;
     ContinuityK k;
     k.P = P;
     k.dt = sc->dt;
     k.do_wrap = do_wrap;
+    k.track_y = fuse ? 1 : 0;
     k.speed = 0.0;
+    k.ykmin = LLONG_MAX;
+    k.ykmax = LLONG_MIN;
     run_tiles(k, S, cta, n_ctas);
     // grid-wide max |v| over fluid rows: warp shuffle, then one atomicMax per warp and CTA
     double speed = k.speed;
@@ -1113,9 +1129,35 @@ __device__ __forceinline__ void continuity_tiles(PhysParams P, const StateView &
     for (int d = 16; d > 0; d >>= 1) speed = fmax(speed, __shfl_xor_sync(0xffffffffu, speed, d));
     if ((threadIdx.x & 31) == 0 && speed > 0.0)
         atomicMax(&sc->vmax_bits, (unsigned long long)__double_as_longlong(speed));
+    if (fuse) {
+        // for the list build that follows: y range of all rows (one atomic pair per CTA) and zeroed cell counters
+        long long kmin = k.ykmin, kmax = k.ykmax;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const long long a = __shfl_xor_sync(0xffffffffu, kmin, d);
+            const long long b = __shfl_xor_sync(0xffffffffu, kmax, d);
+            kmin = a < kmin ? a : kmin;
+            kmax = b > kmax ? b : kmax;
+        }
+        __shared__ long long s_min[kTileThreads / 32], s_max[kTileThreads / 32];
+        if ((threadIdx.x & 31) == 0) {
+            s_min[threadIdx.x >> 5] = kmin;
+            s_max[threadIdx.x >> 5] = kmax;
+        }
+        for (int j = (int)(cta * kTileThreads + threadIdx.x); j < F.n_cell_ints; j += (int)(n_ctas * kTileThreads)) F.cell_cnt[j] = 0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < kTileThreads / 32; ++w) {
+                kmin = s_min[w] < kmin ? s_min[w] : kmin;
+                kmax = s_max[w] > kmax ? s_max[w] : kmax;
+            }
+            if (kmin != LLONG_MAX) atomicMin(&F.g->ymin_key, kmin);
+            if (kmax != LLONG_MIN) atomicMax(&F.g->ymax_key, kmax);
+        }
+    }
     if (!advance_clock) return;
     // the last CTA to finish advances the clock and publishes max|v| (what k_advance_clock does as a
-    // launch of its own): t += dt, step += 1, m:264-266
+    // launch of its own): t += dt, step += 1, m:264-266 -- and derives the grid of the coming build (nb:253-258)
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -1126,6 +1168,7 @@ __device__ __forceinline__ void continuity_tiles(PhysParams P, const StateView &
             sc->step += 1;
             sc->vmax = __longlong_as_double((long long)atomicAdd(&sc->vmax_bits, 0ull));
             sc->ticket = 0u;
+            if (fuse) grid_derive(F.g, F.cell, F.ncx, F.cell_cap, F.flags, F.totals);
         }
     }
 }
@@ -1133,15 +1176,15 @@ __device__ __forceinline__ void continuity_tiles(PhysParams P, const StateView &
 #define SPHB_CONT_MINCTAS 5   // (6 -> 170 B of spills, 77 us; 5 -> 57.8 us; 4 -> 58.2 us)
 #endif
 __global__ void __launch_bounds__(kTileThreads, SPHB_CONT_MINCTAS) k_continuity(PhysParams P, StateView S, DevScalars *sc,
-                                                                               int do_wrap, int advance_clock)
+                                                                               int do_wrap, int advance_clock, GridFuse F)
 {
-    continuity_tiles(P, S, sc, do_wrap, advance_clock, blockIdx.x, gridDim.x);
+    continuity_tiles(P, S, sc, do_wrap, advance_clock, F, blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(kTileThreads, SPHB_CONT_MINCTAS) k_continuity_batch(const BatchChan *__restrict__ chan, int do_wrap,
-                                                                  int advance_clock)
+                                                                  int advance_clock, int fuse_grid)
 {
     const BatchChan &c = chan[blockIdx.y];
-    continuity_tiles(c.P, c.S, c.sc, do_wrap, advance_clock, blockIdx.x, gridDim.x);
+    continuity_tiles(c.P, c.S, c.sc, do_wrap, advance_clock, fuse_grid ? c.F : GridFuse(), blockIdx.x, gridDim.x);
 }
 
 __global__ void __launch_bounds__(256) k_vmax(int nf, const double2 *__restrict__ vel, DevScalars *sc)
@@ -1433,11 +1476,11 @@ int csr_pressure(const PhysParams &P, const StateView &S, const DevScalars *sc, 
     return 0;
 }
 int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool wrap, bool advance_clock,
-                   cudaStream_t st)
+                   const GridFuse &F, cudaStream_t st)
 {
     const size_t sm = (size_t)S.tile_cap * kContinuitySlot;
     k_continuity<<<persistent_ctas(k_continuity, sm, S.n_tiles), kTileThreads, sm, st>>>(P, S, sc, wrap ? 1 : 0,
-                                                                                         advance_clock ? 1 : 0);
+                                                                                         advance_clock ? 1 : 0, F);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1543,10 +1586,10 @@ int csr_batch_pressure(const BatchLaunch &L)
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
-int csr_batch_continuity(const BatchLaunch &L, bool wrap, bool advance_clock)
+int csr_batch_continuity(const BatchLaunch &L, bool wrap, bool advance_clock, bool fuse_grid)
 {
     k_continuity_batch<<<batch_tile_grid(L), kTileThreads, (size_t)L.tile_cap * kContinuitySlot, L.st>>>(
-        L.chan, wrap ? 1 : 0, advance_clock ? 1 : 0);
+        L.chan, wrap ? 1 : 0, advance_clock ? 1 : 0, fuse_grid ? 1 : 0);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -78,8 +78,9 @@ int csr_visc_transport(const PhysParams &P, const StateView &S, bool do_visc, bo
 int csr_time_step(const PhysParams &P, const StateView &S, DevScalars *sc, double remain, double fixed_dt,
                   cudaStream_t st);
 int csr_pressure(const PhysParams &P, const StateView &S, const DevScalars *sc, cudaStream_t st);    // P4 + kick
+// P5 + finish (+ clock); F.g != NULL: also the y range / grid / zeroed cell counters of the list build that follows
 int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool wrap, bool advance_clock,
-                   cudaStream_t st);                                                             // P5 + finish (+ clock)
+                   const GridFuse &F, cudaStream_t st);
 // dt of the coming substep = min(acoustic, viscous, body, remain) from the device vmax (m:519-527), published BEFORE
 // the density pass of an outer step (which evaluates the half-step pressures with it); fixed_dt > 0 overrides
 int csr_publish_dt(const PhysParams &P, DevScalars *sc, double remain, double fixed_dt, cudaStream_t st);
@@ -104,6 +105,7 @@ struct BatchChan {
     StateView S;
     DevScalars *sc;
     double *shear_partials;
+    GridFuse F;   // of the channel's next list build (used by the step's last continuity pass)
 };
 struct BatchLaunch {
     const BatchChan *chan;   // device array [n_chan]
@@ -121,7 +123,7 @@ int csr_batch_publish_dt(const BatchLaunch &L, double remain, double fixed_dt);
 int csr_batch_force_fused(const BatchLaunch &L, bool add_gravity);
 int csr_batch_time_step(const BatchLaunch &L, double remain, double fixed_dt);
 int csr_batch_pressure(const BatchLaunch &L);
-int csr_batch_continuity(const BatchLaunch &L, bool wrap, bool advance_clock);
+int csr_batch_continuity(const BatchLaunch &L, bool wrap, bool advance_clock, bool fuse_grid);
 int csr_batch_wall_shear(const BatchLaunch &L);
 
 }  // namespace sphb
