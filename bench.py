@@ -69,6 +69,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--inner", type=int, default=1, help="acoustic substeps per outer step (1 = reference loop)")
+    ap.add_argument("--dual-auto", type=int, default=0, metavar="MAX_INNER",
+                    help="N = 1: step with the device-side dual-criteria scheduler (sphb_ctx_run_dual_auto: outer Dt and "
+                         "acoustic dt decided on the device, at most MAX_INNER substeps per outer step); the value counts "
+                         "the substeps actually taken.  With --mu below ~0.02 an outer step takes several.")
+    ap.add_argument("--mu", type=float, default=None, help="dynamic viscosity (default: the reference's 0.1)")
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--dp", type=float, default=0.0025)
     ap.add_argument("--DL", type=float, default=3.0)
@@ -298,7 +303,8 @@ def b200_arm(args):
         return b200_ensemble_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks)
     if world > 1 and args.mode in ("auto", "slab"):
         return b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks)
-    cfg = lp.ChannelConfig(DL=args.DL, dp=args.dp).derive()
+    cfg = (lp.ChannelConfig(DL=args.DL, dp=args.dp) if args.mu is None else
+           lp.ChannelConfig(DL=args.DL, dp=args.dp, mu=args.mu)).derive()
     pt = lp.channel_setup.developed(cfg, seed=args.seed + rank)     # one independent channel per rank
     if not args.no_presort:
         pt = lp.channel_setup.cell_sorted(cfg, pt)   # the row order of a run past its first sort point (m:272)
@@ -309,6 +315,23 @@ def b200_arm(args):
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     # ---- device-resident throughput ----------------------------------------------------------------
+    auto = args.dual_auto if world == 1 else 0
+    if auto:
+        inner = 1          # (the kernel profile and the e2e leg below run the reference schedule)
+        ch.run_dual_auto(max(W, 3), auto)
+        c0 = ch.dual_counts()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            ch.run_dual_auto(K, auto)                   # K outer steps, one CUDA graph each; returns when they are done
+            ev1.record(stream)
+        ch.sync()
+        c1 = ch.dual_counts()
+        auto_ms = ev0.elapsed_time(ev1)
+        auto_line = {"outer_steps": c1["outer_steps"] - c0["outer_steps"], "sub_steps": c1["sub_steps"] - c0["sub_steps"],
+                     "max_inner": auto, "last_Dt": c1["last_Dt"], "ms_per_outer_step": auto_ms / K,
+                     "value": nt * (c1["sub_steps"] - c0["sub_steps"]) / (auto_ms * 1e-3),
+                     "l2": "no flush: consecutive outer steps of one simulation"}
     ch.run_dual(max(W, 3), inner)
     ch.sync()
     l0 = ch.timing()["launches"]
@@ -467,6 +490,8 @@ def b200_arm(args):
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
             "final_state": {"vmax": st["vmax"], "n_half_pairs": st["n_half_pairs"], "t": st["t"]},
         }
+        if auto:
+            line["dual_auto"] = auto_line     # device-side dual-criteria scheduler: particle-substeps/s over the same state
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -73,6 +73,14 @@ SPHB_API int sphb_fp64_peak(int iters, int reps, double *tflops);
 /* ============================== 1. stateless MEX-path entry points ============================== */
 
 /*
+ * sphb_validate_only(1) makes the operator entry points of this section return right after the reference's argument
+ * checks (same order, same identifiers), before any device work and before they touch their output pointers;
+ * sphb_validate_only(0) restores normal operation.  Per calling thread.  The MEX shims use it to run the checks of
+ * ph:125-162 etc. BEFORE they allocate outputs from a caller-supplied n_total, as the reference does.
+ */
+SPHB_API void sphb_validate_only(int on);
+
+/*
  * Neighbour search, replaces mexFunction of mex/sph_neighbor_search_mex.c:185-421.
  * Call sphb_neighbor_search() -> *n_pairs, allocate 7 arrays of *n_pairs doubles (the MEX shim uses
  * mxCreateDoubleMatrix), then sphb_neighbor_fetch() copies device results straight into them and
@@ -228,6 +236,20 @@ SPHB_API int sphb_ctx_run_until(sphb_ctx *ctx, double t_target, double t_end, lo
  * shear monitor.  n_inner = 1 reproduces sphb_ctx_step with remain = inf.  Runs as a CUDA graph.
  */
 SPHB_API int sphb_ctx_run_dual(sphb_ctx *ctx, int n_outer, int n_inner);
+
+/*
+ * Dual-criteria schedule with both criteria evaluated on the device (BASELINE.json north_star (3); scheme of the
+ * reference's README.md:61-65 -- no code at HEAD, so this schedule is not pinned by the reference, only its operators
+ * are).  Per outer step:  Dt = min(0.25 h / max|v|, 0.125 h^2 / nu, 0.25 sqrt(h / |g|), remain);  density + KGC,
+ * viscous force (+ m g) and transport shift once;  acoustic substeps dt = min(0.25 h / (c_f + max|v|), Dt_left) until
+ * Dt is covered -- at most max_inner of them: the launch sequence has a fixed length and the substeps beyond
+ * ceil(Dt / dt) return at once on the device;  [cell sort], list rebuild, wall-shear monitor.  max|v|, Dt, dt and the
+ * substep count never leave the device; one CUDA graph per outer step when remain is infinite.  Returns after the
+ * last outer step has finished (it reads the step counter back).  Not available on slabs of a sharded channel.
+ */
+SPHB_API int sphb_ctx_run_dual_auto(sphb_ctx *ctx, int n_outer, int max_inner, double remain);
+/* outer steps / acoustic substeps taken so far by sphb_ctx_run_dual_auto, and the Dt of the last outer step */
+SPHB_API int sphb_ctx_dual_counts(sphb_ctx *ctx, long long *outer_steps, long long *sub_steps, double *last_Dt);
 
 /*
  * Ensembles of independent channels (swept mu / g, ...): one context per channel, each with its own stream and

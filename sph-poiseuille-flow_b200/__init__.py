@@ -447,6 +447,15 @@ class Channel:
     def run_dual(self, n_outer: int, n_inner: int):
         _check(lib().sphb_ctx_run_dual(self._ctx, C.c_int(n_outer), C.c_int(n_inner)))
 
+    def run_dual_auto(self, n_outer: int, max_inner: int, remain: float = float("inf")):
+        """Dual-criteria schedule with Dt, dt and the substep count decided on the device (sphb_ctx_run_dual_auto)."""
+        _check(lib().sphb_ctx_run_dual_auto(self._ctx, C.c_int(n_outer), C.c_int(max_inner), C.c_double(remain)))
+
+    def dual_counts(self) -> dict:
+        o, s, d = C.c_longlong(0), C.c_longlong(0), C.c_double(0.0)
+        _check(lib().sphb_ctx_dual_counts(self._ctx, C.byref(o), C.byref(s), C.byref(d)))
+        return {"outer_steps": o.value, "sub_steps": s.value, "last_Dt": d.value}
+
     def status(self) -> dict:
         s = _Status()
         _check(lib().sphb_ctx_status(self._ctx, C.byref(s)))

@@ -16,6 +16,7 @@ using namespace sphb;
 
 struct sphb_pairs {
     size_t n_pairs = 0;
+    unsigned long long generation = 0;   // the search this handle belongs to (Stateless::generation)
 };
 
 namespace {
@@ -27,7 +28,12 @@ struct Stateless {
     DevBuf pos2;          // double2 positions for the neighbour search
     NeighborWork nw;
     bool pairs_pending = false;
+    unsigned long long generation = 0;   // bumped by every search: a handle fetches only its own list
 };
+
+// sphb_validate_only(1): the operator entry points return after the reference's argument checks, before any device
+// work (and before they look at their output pointers).  Per calling thread.
+thread_local int g_validate_only = 0;
 
 Stateless &G()
 {
@@ -142,6 +148,7 @@ SPHB_API int sphb_neighbor_search(sphb_mat pos, int n_fluid, int n_total, double
     SPHB_REQUIRE(!(n_total <= 0 || n_fluid <= 0 || n_fluid > n_total || (size_t)n_total != pos.m),
                  "SPH:Neighbor:count", "Invalid n_fluid/n_total or inconsistent pos size.");
     SPHB_REQUIRE(!(h <= 0.0 || DL <= 0.0), "SPH:Neighbor:param", "h and DL must be positive.");
+    if (g_validate_only) return 0;
     SPHB_TRY(ensure_stream(g));
     const size_t n = (size_t)n_total;
     double lo = pos.p[n], hi = pos.p[n];
@@ -167,6 +174,7 @@ SPHB_API int sphb_neighbor_search(sphb_mat pos, int n_fluid, int n_total, double
         return set_error("SPH:Neighbor:entryCapacity", "Cell entry capacity exceeded.");
     sphb_pairs *hnd = new sphb_pairs();
     hnd->n_pairs = (size_t)host[0];
+    hnd->generation = ++g.generation;
     g.pairs_pending = true;
     *handle = hnd;
     *n_pairs = hnd->n_pairs;
@@ -178,7 +186,7 @@ SPHB_API int sphb_neighbor_fetch(sphb_pairs *handle, double *pair_i, double *pai
 {
     ENTER();
     if (!handle) return set_error("SPHB:arg", "null handle");
-    if (!g.pairs_pending) {
+    if (!g.pairs_pending || handle->generation != g.generation) {
         delete handle;
         return set_error("SPHB:state", "the pair list of this handle has been overwritten by a later search");
     }
@@ -203,9 +211,11 @@ SPHB_API void sphb_neighbor_release(sphb_pairs *handle)
 {
     Stateless &g = G();
     std::lock_guard<std::mutex> lock(g.mu);
-    g.pairs_pending = false;
+    if (handle && handle->generation == g.generation) g.pairs_pending = false;   // (an older handle owns nothing any more)
     delete handle;
 }
+
+SPHB_API void sphb_validate_only(int on) { g_validate_only = on ? 1 : 0; }
 
 // ------------------------------------------------------------------------------------------------
 // density_correction (ph:95-374; checks ph:139-162)
@@ -223,6 +233,7 @@ SPHB_API int sphb_density_correction(sphb_mat pair_i, sphb_mat pair_j, sphb_mat 
     SPHB_REQUIRE(n_fluid > 0 && n_total >= n_fluid, "SPH:Physics:density:count", "Invalid n_fluid/n_total.");
     SPHB_REQUIRE((long long)numel(mass) == (long long)n_total, "SPH:Physics:density:mass", "mass size mismatch.");
     SPHB_REQUIRE(rho0 > 0.0 && h > 0.0, "SPH:Physics:density:param", "rho0 and h must be positive.");
+    if (g_validate_only) return 0;
     SPHB_TRY(ensure_stream(g));
     const size_t nt = (size_t)n_total;
     Bump b;
@@ -255,6 +266,7 @@ SPHB_API int sphb_viscous_force(sphb_mat pair_i, sphb_mat pair_j, sphb_mat dx, s
     SPHB_REQUIRE(is_mat(B, nt, 4), "SPH:Physics:viscous:B", "B size mismatch.");
     SPHB_REQUIRE(numel(mass) == nt, "SPH:Physics:viscous:mass", "mass size mismatch.");
     SPHB_REQUIRE(is_mat(wall_vel, nt, 2), "SPH:Physics:viscous:wallvel", "wall_vel size mismatch.");
+    if (g_validate_only) return 0;
     SPHB_TRY(ensure_stream(g));
     const size_t np = numel(pair_i);
     Bump b;
@@ -288,6 +300,7 @@ SPHB_API int sphb_transport_correction(sphb_mat pair_i, sphb_mat pair_j, sphb_ma
     SPHB_REQUIRE(numel(Vol) == nt, "SPH:Physics:transport:Vol", "Vol size mismatch.");
     SPHB_REQUIRE(is_mat(B, nt, 4), "SPH:Physics:transport:B", "B size mismatch.");
     SPHB_REQUIRE(is_mat(pos, nt, 2), "SPH:Physics:transport:pos", "pos size mismatch.");
+    if (g_validate_only) return 0;
     SPHB_TRY(ensure_stream(g));
     const size_t np = numel(pair_i);
     Bump b;
@@ -381,6 +394,7 @@ SPHB_API int sphb_integration_1st(sphb_mat pair_i, sphb_mat pair_j, sphb_mat dx,
     SPHB_REQUIRE(n_total > 0, "SPHB:arg", "n_total must be positive.");
     const size_t nt = (size_t)n_total;
     SPHB_TRY(check_int_inputs(false, nt, Vol, B, rho, mass, pos, vel, drho_dt, force_prior, wall_vel));
+    if (g_validate_only) return 0;
     SPHB_TRY(ensure_stream(g));
     const size_t np = numel(pair_i);
     Bump b;
@@ -425,6 +439,7 @@ SPHB_API int sphb_integration_2nd(sphb_mat pair_i, sphb_mat pair_j, sphb_mat dx,
     SPHB_REQUIRE(is_mat(pos, nt, 2), "SPH:Physics:int2:pos", "pos size mismatch.");
     SPHB_REQUIRE(is_mat(vel, nt, 2), "SPH:Physics:int2:vel", "vel size mismatch.");
     SPHB_REQUIRE(is_mat(wall_vel, nt, 2), "SPH:Physics:int2:wall_vel", "wall_vel size mismatch.");
+    if (g_validate_only) return 0;
     SPHB_TRY(ensure_stream(g));
     const size_t np = numel(pair_i);
     Bump b;
@@ -460,6 +475,7 @@ SPHB_API int sphb_integration_verlet(sphb_mat pair_i, sphb_mat pair_j, sphb_mat 
     const size_t nt = (size_t)n_total;
     SPHB_TRY(check_int_inputs(true, nt, Vol, B, rho, mass, pos, vel, drho_dt, force_prior, wall_vel));
     SPHB_REQUIRE(pairs_consistent(pair_i, pair_j, dx, dy, r, dW), "SPH:Physics:pairs", "Pair arrays must have same length.");
+    if (g_validate_only) return 0;
     SPHB_TRY(ensure_stream(g));
     const size_t np = numel(pair_i);
     Bump b;
@@ -515,6 +531,7 @@ SPHB_API int sphb_advance_shell_step(sphb_mat pair_i, sphb_mat pair_j, sphb_mat 
                  "SPH:Physics:density:pairs", "Pair arrays mismatch.");
     SPHB_REQUIRE(np <= (size_t)INT_MAX, "SPH:Physics:density:pairsize", "Pair count exceeds INT_MAX.");
     SPHB_REQUIRE(rho0 > 0.0 && h > 0.0, "SPH:Physics:density:param", "rho0 and h must be positive.");
+    if (g_validate_only) return 0;
     SPHB_TRY(ensure_stream(g));
     Bump b;
     SPHB_TRY(open_arena(g, 7 * pad4(np) + 24 * pad4(nt) + verlet_work_doubles(n_total) + scratch_doubles(n_total), b));
@@ -565,6 +582,7 @@ SPHB_API int sphb_wall_shear_monitor(sphb_mat pair_i, sphb_mat pair_j, sphb_mat 
     SPHB_REQUIRE(is_mat(wall_vel, nt, 2), "SPH:Physics:wallshear:wall_vel", "wall_vel size mismatch.");
     SPHB_REQUIRE(is_mat(B, nt, 4), "SPH:Physics:wallshear:B", "B size mismatch.");
     SPHB_REQUIRE(nt > 0 && nt <= (size_t)INT_MAX, "SPHB:arg", "Vol must be non-empty.");
+    if (g_validate_only) return 0;
     SPHB_TRY(ensure_stream(g));
     const size_t np = numel(pair_i);
     const int nti = (int)nt;

@@ -319,6 +319,12 @@ SPHB_API int sphb_batch_sync(sphb_batch *b)
     SPHB_CUDA(cudaSetDevice(b->device));
     SPHB_CUDA(cudaStreamSynchronize(b->st));
     SPHB_CUDA(cudaGetLastError());
+    // a member that raised a device flag froze at its last consistent step (step_poisoned): report it
+    int all = 0;
+    SPHB_TRY(sphb_batch_error_flags(b, &all));
+    if (all) return set_error(all & kErrNonFinite ? "SPHB:diverged" : "SPHB:capacity",
+                              "a channel of the batch raised device error flags (OR over the channels: %d); it stands at its last "
+                              "consistent step -- sphb_ctx_status of the members tells which", all);
     return 0;
 }
 

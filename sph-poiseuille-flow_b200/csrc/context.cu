@@ -331,7 +331,7 @@ SPHB_API int sphb_ctx_create(const sphb_params *prm, sphb_ctx **out)
         SPHB_TRY(c->stage.reserve(6 * nt * sizeof(double)));   // three 2-column (or one 4- + one 2-column) arrays in flight
         k_fill<<<grid_for(nt), kBlock, 0, c->st>>>(c->rho.as<double>(), prm->rho0, (int)nt);
         k_fill_identity<<<grid_for(nt), kBlock, 0, c->st>>>(c->B.as<Mat2>(), (int)nt);
-        SPHB_CUDA(cudaMallocHost((void **)&c->h_scalars, sizeof(DevScalars)));
+        SPHB_CUDA(cudaMallocHost((void **)&c->h_scalars, 2 * sizeof(DevScalars)));   // [1]: the copy of flags_watch
         SPHB_CUDA(cudaMallocHost((void **)&c->h_ints, 8 * sizeof(int)));
         for (auto &e : c->ev) SPHB_CUDA(cudaEventCreate(&e));
         SPHB_CUDA(cudaStreamSynchronize(c->st));
@@ -365,6 +365,7 @@ SPHB_API void sphb_ctx_destroy(sphb_ctx *c)
     c->nw.release_all();
     c->sw.release_all();
     c->kprof.release();
+    if (c->flags_ev) cudaEventDestroy(c->flags_ev);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
     if (c->h_ints) cudaFreeHost(c->h_ints);
     for (auto &e : c->ev)
@@ -427,6 +428,7 @@ SPHB_API int sphb_ctx_download(sphb_ctx *c, double *pos, double *vel, double *rh
     clear_error();
     if (!c) return set_error("SPHB:arg", "null context");
     SPHB_TRY(bind_device(c));
+    SPHB_TRY(ctx_flags_poll(c, true));   // an asynchronous run that raised a device flag is recovered (or reported) first
     const int nt = c->prm.n_total;
     const size_t n = (size_t)nt;
     double *stage = c->stage.as<double>();
@@ -752,16 +754,110 @@ int enqueue_outer(sphb_ctx *c, int n_inner, bool with_sort)
 
 }  // namespace
 
+}  // extern "C"
+
+namespace {
+
+// One outer step of the DEVICE-SIDE dual-criteria scheduler: Dt and every dt are computed on the device, the number
+// of acoustic substeps is data dependent -- `max_inner` substeps are enqueued and those beyond ceil(Dt / dt) return at
+// once (DevScalars::sub_on), so the whole outer step is one fixed launch sequence (capturable as a CUDA graph) with
+// no host round trip.
+int enqueue_outer_auto(sphb_ctx *c, int max_inner, double remain, bool with_sort)
+{
+    const double inf = std::numeric_limits<double>::infinity();
+    SPHB_TRY(csr_dual_begin(c->P, c->sc(), remain, c->st));   // Dt, first dt (the density pass evaluates p(half) with it)
+    c->launches += 1;
+    SPHB_TRY(do_density(c));
+    SPHB_TRY(do_fused_first_substep(c, true, false));
+    for (int s = 1; s < max_inner; ++s) SPHB_TRY(do_substep(c, inf, 0.0, true, false));
+    SPHB_TRY(csr_dual_end(c->sc(), c->st));
+    c->launches += 1;
+    if (with_sort) SPHB_TRY(do_sort(c));
+    SPHB_TRY(do_neighbor(c));
+    SPHB_TRY(do_shear(c));
+    return 0;
+}
+
+// Error flags behind asynchronous runs.  The kernels of a step return at once while a flag is up (step_poisoned), so
+// the state of a replayed run stays at the last consistent step; the host learns of it from a 4-byte copy into pinned
+// memory enqueued behind every run (flags_watch) and looked at when the next call comes (flags_poll, non-blocking) or
+// when the caller waits (sphb_ctx_sync / status / download, blocking).  A list that outgrew its fitted capacity is
+// rebuilt with the exact, growing build and the outer steps the poisoned run skipped are taken again; anything else
+// (non-finite state, cell / slab capacity) is returned as an error.
+int flags_watch(sphb_ctx *c)
+{
+    if (!c->planned) return 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    (void)cudaStreamIsCapturing(c->st, &cap);
+    if (cap != cudaStreamCaptureStatusNone) return 0;
+    if (!c->flags_ev) SPHB_CUDA(cudaEventCreateWithFlags(&c->flags_ev, cudaEventDisableTiming));
+    SPHB_CUDA(cudaMemcpyAsync(c->h_ints + 4, c->nw.flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaMemcpyAsync(&c->h_scalars[1], c->sc(), sizeof(DevScalars), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaEventRecord(c->flags_ev, c->st));
+    c->flags_pending = true;
+    return 0;
+}
+
+int flags_handle(sphb_ctx *c)   // the copy of flags_watch has landed
+{
+    c->flags_pending = false;
+    const int f = c->h_ints[4];
+    if (!f) return 0;
+    const long long dev_step = c->h_scalars[1].step;
+    if (f & kErrNonFinite)
+        return set_error("SPHB:diverged", "non-finite density or velocity at step %lld (t = %g): the run is frozen there",
+                         dev_step, c->h_scalars[1].t);
+    if (f & ~(kErrCsrCap | kErrTileCap))
+        return set_error("SPHB:capacity", "device error flags %d at step %lld: the run is frozen there", f, dev_step);
+    if (c->slab.on) return set_error("SPHB:capacity", "neighbour list capacity exceeded in a slab (flags %d) at step %lld", f, dev_step);
+    // list capacity: rebuild exactly (grows the list / the tile slots), then redo what the poisoned run skipped
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    SPHB_TRY(recover_list_capacity(c));
+    drop_graphs(c);
+    const long long missing = c->h_step - dev_step;
+    const int inner = std::max(1, c->last_inner);
+    for (long long o = 0; o < missing / inner; ++o) SPHB_TRY(enqueue_outer(c, inner, false));
+    return 0;
+}
+
+int flags_poll(sphb_ctx *c, bool block)
+{
+    if (!c->flags_pending) return 0;
+    if (block) SPHB_CUDA(cudaEventSynchronize(c->flags_ev));
+    else if (cudaEventQuery(c->flags_ev) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return flags_handle(c);
+}
+
+}  // namespace
+
+int ctx_flags_poll(sphb_ctx *c, bool block) { return flags_poll(c, block); }
+int ctx_flags_watch(sphb_ctx *c) { return flags_watch(c); }
+
+extern "C" {
+
 // Dual-criteria schedule as a replayed CUDA graph (one graph per outer step).
 SPHB_API int sphb_ctx_run_dual(sphb_ctx *c, int n_outer, int n_inner)
 {
     CTX_ENTER(true);
     if (n_inner < 1 || n_outer < 0) return set_error("SPHB:arg", "n_inner >= 1 and n_outer >= 0 required");
+    SPHB_TRY(flags_poll(c, false));   // what an earlier asynchronous run left behind
+    c->last_inner = n_inner;
     const int si = c->prm.sort_interval;
     if (c->graph_inner != n_inner) drop_graphs(c);
     for (int o = 0; o < n_outer; ++o) {
+        if ((o & 63) == 63) {   // long runs: look now and then without stalling the queue
+            SPHB_TRY(flags_watch(c));
+            SPHB_TRY(flags_poll(c, false));
+        }
         c->outer_count += 1;
-        const bool with_sort = si > 0 && c->outer_count % si == 0 && c->outer_count != 1;
+        c->h_step += n_inner;
+        // m:272: mod(step, sort_interval) == 0 && step ~= 1 on the GLOBAL step counter (it survives restarts:
+        // sphb_ctx_set_time seeds h_step); with n_inner > 1 an outer step is n_inner counts of it
+        const long long kstep = c->h_step / n_inner;
+        const bool with_sort = si > 0 && kstep % si == 0 && kstep != 1;
         if (with_sort) {
             // the permutation swaps buffer pointers: run eagerly, then re-capture on the new pointers
             drop_graphs(c);
@@ -796,7 +892,79 @@ SPHB_API int sphb_ctx_run_dual(sphb_ctx *c, int n_outer, int n_inner)
         c->nw.half_valid = false;   // the replayed build rewrote the list
         c->launches += c->graph_launches;
     }
-    c->h_step += (long long)n_outer * n_inner;
+    SPHB_TRY(flags_watch(c));
+    return 0;
+}
+
+// Dual-criteria schedule with the criteria evaluated ON THE DEVICE (BASELINE.json north_star (3); the reference
+// describes the scheme in README.md:61-65 and has no code for it at HEAD -- parity unpinned):
+//   outer step  Dt = min(0.25 h / max|v|, 0.125 h^2 / nu, 0.25 sqrt(h / |g|), remain)      advection / viscous / body
+//   substeps    dt = min(0.25 h / (c_f + max|v|), Dt_left) until Dt is covered, at most max_inner of them
+// density + KGC, viscous force and transport shift once per outer step, the list rebuilt after it.  max|v| comes from
+// the warp-shuffle + atomicMax reduction of the continuity kernel; Dt, dt and the substep count never leave the device.
+// Replayed as one CUDA graph per outer step when remain is infinite.  The counts actually taken are in
+// sphb_ctx_dual_counts.
+SPHB_API int sphb_ctx_run_dual_auto(sphb_ctx *c, int n_outer, int max_inner, double remain)
+{
+    CTX_ENTER(true);
+    if (max_inner < 1 || n_outer < 0) return set_error("SPHB:arg", "max_inner >= 1 and n_outer >= 0 required");
+    if (c->slab.on) return set_error("SPHB:state", "the device-side scheduler is not available on a slab of a sharded channel");
+    SPHB_TRY(flags_poll(c, true));
+    const int si = c->prm.sort_interval;
+    const bool graphable = !(remain < std::numeric_limits<double>::infinity()) && !c->kprof.on;
+    if (c->graph_inner != -max_inner) drop_graphs(c);   // (negative: the auto schedule with this budget)
+    for (int o = 0; o < n_outer; ++o) {
+        c->outer_count += 1;
+        const bool with_sort = si > 0 && c->outer_count % si == 0 && c->outer_count != 1;
+        if (with_sort || !graphable) {
+            if (with_sort) drop_graphs(c);   // the permutation swaps buffer pointers
+            SPHB_TRY(enqueue_outer_auto(c, max_inner, remain, with_sort));
+            if (c->kprof.on) SPHB_TRY(c->kprof.collect(c->st));
+            continue;
+        }
+        if (!c->graph[0]) {
+            const long long l0 = c->launches;
+            cudaGraph_t g = nullptr;
+            SPHB_CUDA(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+            int rc = enqueue_outer_auto(c, max_inner, remain, false);
+            cudaError_t e = cudaStreamEndCapture(c->st, &g);
+            if (rc) {
+                if (g) cudaGraphDestroy(g);
+                return rc;
+            }
+            if (e != cudaSuccess) return set_error("SPHB:cuda", "graph capture failed: %s", cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&c->graph[0], g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return set_error("SPHB:cuda", "graph instantiate failed: %s", cudaGetErrorString(e));
+            c->graph_inner = -max_inner;
+            c->graph_launches = c->launches - l0;
+            c->launches = l0;
+        }
+        SPHB_CUDA(cudaGraphLaunch(c->graph[0], c->st));
+        c->nw.half_valid = false;
+        c->launches += c->graph_launches;
+    }
+    // the host mirror of the step counter follows the device (the substep count is the device's decision)
+    SPHB_CUDA(cudaMemcpyAsync(c->h_scalars, c->sc(), sizeof(DevScalars), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaMemcpyAsync(c->h_ints + 2, c->nw.flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    c->h_step = c->h_scalars->step;
+    if (c->h_ints[2])
+        return set_error(c->h_ints[2] & kErrNonFinite ? "SPHB:diverged" : "SPHB:capacity",
+                         "device error flags %d at step %lld: the run stands at its last consistent step", c->h_ints[2],
+                         c->h_scalars->step);
+    return 0;
+}
+
+// outer steps and acoustic substeps taken so far by sphb_ctx_run_dual_auto, and the last outer step Dt
+SPHB_API int sphb_ctx_dual_counts(sphb_ctx *c, long long *outer_steps, long long *sub_steps, double *last_Dt)
+{
+    CTX_ENTER(false);
+    SPHB_CUDA(cudaMemcpyAsync(c->h_scalars, c->sc(), sizeof(DevScalars), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    if (outer_steps) *outer_steps = c->h_scalars->outer_steps;
+    if (sub_steps) *sub_steps = c->h_scalars->sub_steps;
+    if (last_Dt) *last_Dt = c->h_scalars->Dt;
     return 0;
 }
 
@@ -935,6 +1103,7 @@ SPHB_API int sphb_ctx_set_stream(sphb_ctx *c, void *stream)
 SPHB_API int sphb_ctx_sync(sphb_ctx *c)
 {
     CTX_ENTER(false);
+    SPHB_TRY(flags_poll(c, true));   // an asynchronous run that raised a device flag is recovered (or reported) here
     SPHB_CUDA(cudaStreamSynchronize(c->st));
     SPHB_CUDA(cudaGetLastError());
     return 0;

@@ -63,6 +63,11 @@ struct sphb_ctx {
     int graph_inner = -1;
     long long graph_launches = 0;
     long long outer_count = 0;
+    // error flags of graph-replayed runs: copied to pinned memory behind every sphb_ctx_run_dual, looked at (without
+    // blocking) at the next call and (blocking) by sphb_ctx_sync / status / download
+    cudaEvent_t flags_ev = nullptr;
+    bool flags_pending = false;
+    int last_inner = 1;          // substeps per outer step of the last run_dual (to redo the steps a poisoned run skipped)
 
     StateView view() const
     {
@@ -94,6 +99,7 @@ struct sphb_ctx {
         S.e_b1 = e_b1.as<double2>();
         S.e_b2 = e_b2.as<double2>();
         S.e_vn = e_vn.as<double2>();
+        S.flags = nw.flags.as<int>();
         S.ell_stride = nw.ell_stride;
         S.ell_cap = nw.ell_cap;
         S.tile_cap = nw.tile_cap;
@@ -112,6 +118,8 @@ void ctx_drop_graphs(sphb_ctx *c);
 int ctx_do_neighbor(sphb_ctx *c);
 int ctx_fresh_mirrors(sphb_ctx *c, bool need_pv);   // makes StateView::e_* current (no-op inside a step)
 int ctx_do_shear(sphb_ctx *c);
+int ctx_flags_poll(sphb_ctx *c, bool block);          // device error flags behind asynchronous runs (context.cu)
+int ctx_flags_watch(sphb_ctx *c);
 int ctx_do_sort(sphb_ctx *c);                       // m:272-278 (swaps the state buffers with their alternates)
 int ctx_volumes_from_mass(sphb_ctx *c);             // Vol = m / rho for every row (m:120)
 int ctx_step_physics(sphb_ctx *c, double remain);   // m:254-270: density + KGC, forces, continuity

@@ -223,10 +223,18 @@ __device__ __forceinline__ Bins bin_particle(double2 p, const NbrParams &P, doub
     return b;
 }
 
+// (The kernels of a build return at once while a device error flag is up, like the kernels of the step -- ops_csr.cuh
+// step_poisoned: inside a replayed graph the grid set-up of the build lives in the continuity epilogue, which a
+// poisoned step skips, so a build that ran on would count into stale cell counters.  Binning and scatter are guarded;
+// the walk is not -- it raises capacity flags itself, and the exact build sizes its retry from the totals of ALL its
+// CTAs -- and then merely walks the previous build's entries again.)
+__device__ __forceinline__ bool build_poisoned(const int *flags) { return *reinterpret_cast<const volatile int *>(flags) != 0; }
+
 __device__ __forceinline__ void bin_count_body(const double2 *__restrict__ pos, NbrParams P, const GridDesc *__restrict__ g,
                                                double2 *__restrict__ snap, int *__restrict__ cell_of,
-                                               int *__restrict__ cell_cnt, unsigned int *ghost_anomaly)
+                                               int *__restrict__ cell_cnt, unsigned int *ghost_anomaly, const int *flags)
 {
+    if (build_poisoned(flags)) return;
     load_counts(P);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_total || row_dead(P, i)) return;
@@ -253,20 +261,21 @@ __device__ __forceinline__ void bin_count_body(const double2 *__restrict__ pos, 
 __global__ void __launch_bounds__(kBlock) k_bin_count(const double2 *__restrict__ pos, NbrParams P,
                                                      const GridDesc *__restrict__ g, double2 *__restrict__ snap,
                                                      int *__restrict__ cell_of, int *__restrict__ cell_cnt,
-                                                     unsigned int *ghost_anomaly)
+                                                     unsigned int *ghost_anomaly, const int *flags)
 {
-    bin_count_body(pos, P, g, snap, cell_of, cell_cnt, ghost_anomaly);
+    bin_count_body(pos, P, g, snap, cell_of, cell_cnt, ghost_anomaly, flags);
 }
 __global__ void __launch_bounds__(kBlock) k_bin_count_batch(const NbrChan *__restrict__ chan)
 {
     const NbrChan &c = chan[blockIdx.y];
-    bin_count_body(c.pos, c.P, c.g, c.snap, c.cell_of, c.cell_cnt, &c.g->ghost_anomaly);
+    bin_count_body(c.pos, c.P, c.g, c.snap, c.cell_of, c.cell_cnt, &c.g->ghost_anomaly, c.flags);
 }
 
 __device__ __forceinline__ void scatter_body(const double2 *__restrict__ pos, NbrParams P, const GridDesc *__restrict__ g,
                                              const int *__restrict__ cell_start, int *__restrict__ cell_fill,
-                                             int *__restrict__ tmp_key, double2 *__restrict__ tmp_pos)
+                                             int *__restrict__ tmp_key, double2 *__restrict__ tmp_pos, const int *flags)
 {
+    if (build_poisoned(flags)) return;
     load_counts(P);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_total || row_dead(P, i)) return;
@@ -295,14 +304,14 @@ __device__ __forceinline__ void scatter_body(const double2 *__restrict__ pos, Nb
 __global__ void __launch_bounds__(kBlock) k_scatter(const double2 *__restrict__ pos, NbrParams P,
                                                    const GridDesc *__restrict__ g,
                                                    const int *__restrict__ cell_start, int *__restrict__ cell_fill,
-                                                   int *__restrict__ tmp_key, double2 *__restrict__ tmp_pos)
+                                                   int *__restrict__ tmp_key, double2 *__restrict__ tmp_pos, const int *flags)
 {
-    scatter_body(pos, P, g, cell_start, cell_fill, tmp_key, tmp_pos);
+    scatter_body(pos, P, g, cell_start, cell_fill, tmp_key, tmp_pos, flags);
 }
 __global__ void __launch_bounds__(kBlock) k_scatter_batch(const NbrChan *__restrict__ chan)
 {
     const NbrChan &c = chan[blockIdx.y];
-    scatter_body(c.pos, c.P, c.g, c.cell_start, c.cell_cnt + ((size_t)c.P.cell_cap + 1), c.tmp_key, c.tmp_pos);
+    scatter_body(c.pos, c.P, c.g, c.cell_start, c.cell_cnt + ((size_t)c.P.cell_cap + 1), c.tmp_key, c.tmp_pos, c.flags);
 }
 
 // One descriptor per tile (tile.cuh): entry ranges of the (kTileRows + 2) x (w + 2) cell neighbourhood and
@@ -1336,7 +1345,7 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
     {
         ProfScope ps(prof, kPfNbrBin, st);
         k_bin_count<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.snap.as<double2>(), w.cell_of.as<int>(), cell_cnt,
-                                                     &g->ghost_anomaly);
+                                                     &g->ghost_anomaly, flags);
     }
     nl += 1;
     {
@@ -1347,7 +1356,7 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
     {
         ProfScope ps(prof, kPfNbrScatter, st);
         k_scatter<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.cell_start.as<int>(), cell_fill, w.tmp_key.as<int>(),
-                                                   w.tmp_pos.as<double2>());
+                                                   w.tmp_pos.as<double2>(), flags);
     }
     nl += 1;
     WalkSetup W;

@@ -366,6 +366,7 @@ struct DensityK {
 
 __device__ __forceinline__ void density_tiles(PhysParams P, const StateView &S, const DevScalars *sc, unsigned cta, unsigned n_ctas)
 {
+    if (step_poisoned(S.flags)) return;
     load_counts(P);
     DensityK k;
     k.P = P;
@@ -459,6 +460,7 @@ struct KgcK {
 
 __device__ __forceinline__ void kgc_tiles(PhysParams P, const StateView &S, unsigned cta, unsigned n_ctas)
 {
+    if (step_poisoned(S.flags)) return;
     load_counts(P);
     KgcK k;
     k.P = P;
@@ -549,6 +551,7 @@ __device__ __forceinline__ void visc_transport_rows(const PhysParams &P, const S
 template <bool VISC, bool TRANSP>
 __global__ void __launch_bounds__(kTileThreads) k_visc_transport(PhysParams P, StateView S, int add_gravity)
 {
+    if (step_poisoned(S.flags)) return;
     load_counts(P);
     SPHB_TILE_BEGIN();
     const OwnPre pre = tile_prefetch_own(S, T);
@@ -594,6 +597,11 @@ __global__ void __launch_bounds__(kTileThreads) k_visc_transport(PhysParams P, S
 // neighbour.  Every thread derives the same dt from the device vmax; thread 0 publishes it.
 __device__ __forceinline__ void time_step_rows(PhysParams P, StateView S, DevScalars *sc, double remain, double fixed_dt)
 {
+    if (step_poisoned(S.flags)) return;
+    if (sc->dual_on) {   // device-side dual-criteria scheduler: the substep covers what is left of the outer step
+        if (!sc->sub_on) return;
+        remain = sc->Dt_left;
+    }
     load_counts(P);
     double dt;
     if (fixed_dt > 0.0) {
@@ -699,6 +707,7 @@ __device__ __forceinline__ void pressure_rows(const PhysParams &P, const StateVi
 
 __device__ __forceinline__ void pressure_tile(PhysParams P, StateView S, const DevScalars *__restrict__ sc)
 {
+    if (step_poisoned(S.flags) || (sc->dual_on && !sc->sub_on)) return;
     load_counts(P);
     SPHB_TILE_BEGIN();
     const OwnPre pre = tile_prefetch_own(S, T);
@@ -949,6 +958,7 @@ struct ForceK {
 __device__ __forceinline__ void force_fused_tiles(PhysParams P, const StateView &S, const DevScalars *sc, int add_gravity,
                                                   unsigned cta, unsigned n_ctas)
 {
+    if (step_poisoned(S.flags)) return;
     load_counts(P);
     ForceK k;
     k.P = P;
@@ -980,6 +990,31 @@ __global__ void k_publish_dt(PhysParams P, DevScalars *sc, double remain, double
     sc->dt = device_dt(P, sc, remain, fixed_dt);
     sc->vmax_bits = 0ull;
 }
+// Device-side dual-criteria scheduler (README.md:61-65 of the reference; its constants are those of m:519-527 split
+// by what they bound): the outer step from the advection, viscous and body-force criteria, the first substep from
+// the acoustic one.
+__global__ void k_dual_begin(PhysParams P, DevScalars *sc, double remain)
+{
+    const double vmax = sc->vmax;
+    const double Dt_a = 0.25 * P.h / fmax(vmax, 1e-12);                  // advection
+    const double Dt_v = 0.125 * P.h * P.h / fmax(P.nu, 1e-12);           // viscous diffusion
+    const double Dt_b = 0.25 * sqrt(P.h / fmax(fabs(P.g), 1e-12));       // body force
+    const double Dt = fmax(fmin(fmin(Dt_a, Dt_v), fmin(Dt_b, remain)), 1e-12);
+    const double dt_ac = 0.25 * P.h / fmax(P.c_f + vmax, 1e-12);         // acoustic
+    sc->Dt = Dt;
+    sc->Dt_left = Dt;
+    sc->dt = fmin(dt_ac, Dt);
+    sc->vmax_bits = 0ull;
+    sc->dual_on = 1;
+    sc->sub_on = 1;
+    sc->outer_steps += 1;
+}
+__global__ void k_dual_end(DevScalars *sc)
+{
+    sc->dual_on = 0;
+    sc->sub_on = 0;
+}
+
 // one thread per channel
 __global__ void __launch_bounds__(kBlock) k_publish_dt_batch(const BatchChan *__restrict__ chan, int n_chan, double remain,
                                                             double fixed_dt)
@@ -1101,6 +1136,8 @@ struct ContinuityK {
             }
             S.vel[i] = vi;   // nobody reads `vel` in this kernel (neighbours read the staged new velocity): commit in place
             if (i < P.nfo) speed = fmax(speed, sqrt(vi.x * vi.x + vi.y * vi.y));
+            // a blown-up row (NaN / Inf in density or velocity; fmax above drops a NaN silently): raised once, rare
+            if (!(fabs(rho) <= 1.0e300 && fabs(vi.x) + fabs(vi.y) <= 1.0e300)) atomicOr(S.flags, kErrNonFinite);
         }
     }
     __device__ SPHB_COLD void rows_cold(const StateView &S, const TileDesc &T, const OwnPre &pre, unsigned char *buf, int cap)
@@ -1112,6 +1149,8 @@ struct ContinuityK {
 __device__ __forceinline__ void continuity_tiles(PhysParams P, const StateView &S, DevScalars *sc, int do_wrap, int advance_clock,
                                                  const GridFuse &F, unsigned cta, unsigned n_ctas)
 {
+    if (step_poisoned(S.flags)) return;   // (nobody takes a clock ticket: t and step stay at the last good step)
+    if (sc->dual_on && !sc->sub_on) return;   // device-side scheduler: the outer step is used up
     load_counts(P);
     const bool fuse = F.g != nullptr && advance_clock;
     ContinuityK k;
@@ -1168,6 +1207,11 @@ __device__ __forceinline__ void continuity_tiles(PhysParams P, const StateView &
             sc->step += 1;
             sc->vmax = __longlong_as_double((long long)atomicAdd(&sc->vmax_bits, 0ull));
             sc->ticket = 0u;
+            if (sc->dual_on) {   // device-side scheduler: one more substep unless Dt is covered (to rounding)
+                sc->Dt_left -= sc->dt;
+                sc->sub_steps += 1;
+                sc->sub_on = sc->Dt_left > 1e-9 * sc->Dt ? 1 : 0;
+            }
             if (fuse) grid_derive(F.g, F.cell, F.ncx, F.cell_cap, F.flags, F.totals);
         }
     }
@@ -1489,6 +1533,18 @@ int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool
 int csr_publish_dt(const PhysParams &P, DevScalars *sc, double remain, double fixed_dt, cudaStream_t st)
 {
     k_publish_dt<<<1, 1, 0, st>>>(P, sc, remain, fixed_dt);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_dual_begin(const PhysParams &P, DevScalars *sc, double remain, cudaStream_t st)
+{
+    k_dual_begin<<<1, 1, 0, st>>>(P, sc, remain);
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+int csr_dual_end(DevScalars *sc, cudaStream_t st)
+{
+    k_dual_end<<<1, 1, 0, st>>>(sc);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }

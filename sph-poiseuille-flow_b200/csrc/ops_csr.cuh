@@ -17,6 +17,14 @@ struct DevScalars {
     long long y0_key;
     unsigned int ticket;            // CTAs of the continuity kernel that have finished (clock advance)
     unsigned int shear_ticket;      // CTAs of the wall-shear kernel that have finished (final sum by the last one)
+    // dual-criteria schedule on the device (sphb_ctx_run_dual_auto; README.md:61-65 of the reference): the outer step
+    // Dt from the advection / viscous / body criteria, consumed by acoustic substeps dt = min(acoustic, Dt_left)
+    int dual_on;                    // 1 while an outer step of the device-side scheduler is in flight
+    int sub_on;                     // 0: Dt is used up -- the kernels of the remaining (budgeted) substeps return at once
+    double Dt;                      // outer step of the current outer step
+    double Dt_left;                 // what the substeps still have to cover
+    long long outer_steps;          // outer steps taken by the device-side scheduler
+    long long sub_steps;            // acoustic substeps taken by it
 };
 
 struct PhysParams {
@@ -31,6 +39,8 @@ struct PhysParams {
                              // host never waits for them); NULL = the values above
 };
 #ifdef __CUDACC__
+// every thread reads the same word; callers branch on it CTA-uniformly
+__device__ __forceinline__ bool step_poisoned(const int *flags) { return *reinterpret_cast<const volatile int *>(flags) != 0; }
 __device__ __forceinline__ void load_counts(PhysParams &P)
 {
     if (P.dev_counts) {
@@ -63,6 +73,10 @@ struct StateView {
     double2 *e_pV;            // (half-step pressure, volume; volume < 0 marks a wall entry)  written by k_density
     double2 *e_b1, *e_b2;     // rows of B                                                     written by k_kgc
     double2 *e_vn;            // new velocity (wall entry: wall velocity)                      written by the force kernels
+    // device error flags (sphb_status.error_flags).  Once a flag is up the state-changing kernels of the step return
+    // at once ("poisoned"): inside a replayed graph the state then stays where the last consistent step left it
+    // until the host looks (sphb_ctx_run_dual, sphb_ctx_sync), instead of advancing on a truncated list.
+    int *flags;
     size_t ell_stride;
     int ell_cap;
     int tile_cap;             // shared-memory slots per tile
@@ -84,6 +98,11 @@ int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool
 // dt of the coming substep = min(acoustic, viscous, body, remain) from the device vmax (m:519-527), published BEFORE
 // the density pass of an outer step (which evaluates the half-step pressures with it); fixed_dt > 0 overrides
 int csr_publish_dt(const PhysParams &P, DevScalars *sc, double remain, double fixed_dt, cudaStream_t st);
+// Device-side dual-criteria scheduler: opens an outer step (Dt = min(0.25 h / max|v|, 0.125 h^2 / nu, 0.25 sqrt(h/|g|),
+// remain), first substep dt = min(acoustic, Dt)) / closes it (dual_on = 0).  Between the two the substep kernels
+// (csr_time_step, csr_pressure, csr_continuity) take dt = min(acoustic, Dt_left) and return at once when Dt is used up.
+int csr_dual_begin(const PhysParams &P, DevScalars *sc, double remain, cudaStream_t st);
+int csr_dual_end(DevScalars *sc, cudaStream_t st);
 int csr_force_fused(const PhysParams &P, const StateView &S, const DevScalars *sc, bool add_gravity,
                     cudaStream_t st);                                                            // P2 + P3 + P4 + kick
 int csr_vmax(const PhysParams &P, const double2 *vel, DevScalars *sc, cudaStream_t st);          // standalone reduction

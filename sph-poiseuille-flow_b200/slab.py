@@ -362,6 +362,15 @@ class SlabChannel:
         captured again afterwards (the compaction swaps the state buffers)."""
         torch = self.torch
         squeeze_next = self.compact_every and (self._k + 1) % self.compact_every == 0
+        if squeeze_next:
+            # the compaction step runs eagerly anyway: look at the device error flags now (a slab whose list or
+            # exchange buffers overflowed has been standing still since -- the kernels of a step return at once while
+            # a flag is up -- and must not be mistaken for a running one)
+            st = self.slab.ch.status()
+            if st["error_flags"]:
+                raise SphError("SPHB:capacity", f"slab {self.rank}: device error flags {st['error_flags']} at step "
+                                                f"{st['step']} (list, tile or exchange-buffer capacity); the slab stands "
+                                                f"at its last consistent step")
         if not (self.use_graph and self._graph_ok and remain == float("inf") and self.world > 1) or squeeze_next:
             with torch.cuda.stream(self.stream):
                 self._body(remain)

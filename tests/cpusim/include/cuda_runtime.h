@@ -120,6 +120,9 @@ cudaError_t cudaGraphLaunch(cudaGraphExec_t exec, cudaStream_t st);
 cudaError_t cudaGraphDestroy(cudaGraph_t graph);
 cudaError_t cudaGraphExecDestroy(cudaGraphExec_t exec);
 cudaError_t cudaEventCreate(cudaEvent_t *e);
+enum { cudaEventDisableTiming = 2 };
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }   // launches run synchronously: always complete
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st = nullptr);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);

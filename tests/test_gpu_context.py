@@ -462,3 +462,101 @@ def test_run_until_recovers_from_list_capacity(sphb, H):
     d = ch.download(("pos", "vel", "rho"))
     assert all(np.all(np.isfinite(d[k])) for k in d)
     ch.close()
+
+
+def test_run_dual_freezes_and_recovers_from_list_capacity(sphb, H, oracle_be):
+    """The same overflow inside graph-replayed steps: the kernels of the step return at once while a device flag is
+    up, so the state stays at the last consistent step instead of advancing on a truncated list; the next call that
+    waits (sync / download / run_dual) rebuilds the list with the growing build and takes the skipped steps again.
+    The result equals the oracle's steps from the squeezed state."""
+    prm = H.derive_params(dp=0.05, c_f=10.0)
+    st = H.developed_state(prm, seed=9, jitter=0.1)
+    ch = make_channel(sphb, prm, st)
+    ch.initialise()                                   # capacities fitted to this state
+    ch.run_dual(2, 1)                                 # a cached graph exists
+    ch.sync()
+    d0 = ch.download(("pos", "vel", "rho", "drho_dt"))
+    pos = d0["pos"].copy(order="F")
+    nf = st.n_fluid
+    pos[:nf, 0] = 0.5 * pos[:nf, 0] + 0.25 * prm.DL   # fluid squeezed into the middle half of the channel
+    ref = st.copy()
+    ref.pos, ref.vel, ref.rho, ref.drho_dt = pos.copy(order="F"), d0["vel"].copy(order="F"), d0["rho"].copy(), d0["drho_dt"].copy()
+    H.initialise(oracle_be, ref, prm)                 # list + density for the squeezed state (m:165-173)
+    ref.rho = d0["rho"].copy()                        # (the step recomputes rho from the kernel sum anyway, m:254)
+    ch.upload(pos=pos)
+    ch.neighbor_build()                               # steady-state build: overflows, raises flags
+    s0 = ch.status()
+    assert s0["error_flags"] != 0
+    ch.run_dual(3, 1)                                 # poisoned: nothing advances on the device
+    ch.sync()                                         # ... until the host looks: exact rebuild + the three steps again
+    s = ch.status()
+    assert s["error_flags"] == 0 and s["step"] == s0["step"] + 3
+    for _ in range(3):
+        H.reference_step(oracle_be, ref, prm)
+    d = ch.download()
+    for f in ("pos", "vel", "rho", "p", "drho_dt"):
+        assert_close(d[f], getattr(ref, f), f, 100 * TOL)   # three steps of a violently relaxing (squeezed) state
+    assert s["n_half_pairs"] == ref.pairs[0].size
+    ch.close()
+
+
+def _oracle_outer_auto(H, be, st, prm, max_inner):
+    """One outer step of the device-side dual-criteria scheduler, restated with the oracle's operators (the schedule
+    itself has no reference code, README.md:61-65; every operator is the pinned one): returns (Dt, [dt...])."""
+    import math
+    nf, nt = st.n_fluid, st.n_total
+    pi, pj, dx, dy, r, W, dW = st.pairs
+    vmax = float(np.max(np.hypot(st.vel[:nf, 0], st.vel[:nf, 1])))
+    Dt = max(min(0.25 * prm.h / max(vmax, 1e-12), 0.125 * prm.h * prm.h / max(prm.nu, 1e-12),
+                 0.25 * math.sqrt(prm.h / max(abs(prm.gravity_g), 1e-12))), 1e-12)
+    st.rho, st.Vol, st.B = be.physics("density_correction", pi, pj, dx, dy, r, W, dW, st.mass, nf, nt, prm.rho0, prm.h,
+                                      prm.inv_sigma0, nargout=3)
+    (fp,) = be.physics("viscous_force", pi, pj, dx, dy, r, dW, st.vel, st.Vol, st.B, prm.mu, prm.h, nf, nt, st.mass,
+                       st.wall_vel, nargout=1)
+    fp[:nf, 0] = fp[:nf, 0] + st.mass[:nf] * prm.gravity_g
+    fp[nf:, :] = 0.0
+    st.force_prior = fp
+    (st.pos,) = be.physics("transport_correction", pi, pj, dx, dy, r, dW, st.Vol, st.B, st.pos, prm.h, nf, nt,
+                           prm.transport_coeff, nargout=1)
+    left, dts = Dt, []
+    while len(dts) < max_inner and left > 1e-9 * Dt:
+        dt = H.verlet_time_step(st.vel[:nf], prm.c_f, prm.h, prm.nu, prm.gravity_g, left)
+        st.rho, st.p, st.pos, st.vel, st.drho_dt, st.force = be.physics(
+            "integration_verlet", pi, pj, dx, dy, r, dW, st.Vol, st.B, st.rho, st.mass, st.pos, st.vel, st.drho_dt,
+            st.force_prior, dt, nf, nt, prm.rho0, prm.p0, prm.c_f, st.wall_vel, nargout=6)
+        st.t += dt
+        H.periodic_bounding(st.pos, nf, prm.DL)
+        st.vel[nf:, :] = 0.0
+        left -= dt
+        dts.append(dt)
+    st.pairs = H.build_neighbor_cache(be, st, prm)
+    return Dt, dts
+
+
+@pytest.mark.parametrize("mu,max_inner", [(0.01, 24), (0.02, 4)])
+def test_device_side_dual_criteria_schedule(sphb, H, oracle_be, mu, max_inner):
+    """sphb_ctx_run_dual_auto: outer Dt from the advection / viscous / body criteria and acoustic substeps until Dt is
+    covered, both decided on the device (no host round trip, one CUDA graph per outer step).  At a viscosity low
+    enough for the acoustic limit to bind, an outer step takes several substeps; the budgeted case (max_inner below
+    what Dt needs) stops early.  Checked against the same schedule restated with the oracle's operators."""
+    prm = H.derive_params(dp=0.05, c_f=10.0, mu=mu)
+    st = H.developed_state(prm, seed=17)
+    ref = st.copy()
+    H.initialise(oracle_be, ref, prm)
+    ch = make_channel(sphb, prm, st, sort_interval=0)
+    ch.initialise()
+    n_outer, subs, t = 3, 0, 0.0
+    for _ in range(n_outer):
+        Dt, dts = _oracle_outer_auto(H, oracle_be, ref, prm, max_inner)
+        subs += len(dts)
+        t += sum(dts)
+    assert subs > n_outer, "the case does not exercise substeps"
+    ch.run_dual_auto(n_outer, max_inner)
+    cnt, s = ch.dual_counts(), ch.status()
+    assert cnt["outer_steps"] == n_outer and cnt["sub_steps"] == subs, (cnt, subs)
+    assert s["step"] == subs and abs(s["t"] - t) <= 1e-12 * t and abs(cnt["last_Dt"] - Dt) <= 1e-12 * Dt
+    assert s["error_flags"] == 0 and s["n_half_pairs"] == ref.pairs[0].size
+    d = ch.download()
+    for f in ("pos", "vel", "rho", "p", "drho_dt", "force", "force_prior", "Vol", "B"):
+        assert_close(d[f], getattr(ref, f), f, 10 * TOL)
+    ch.close()
