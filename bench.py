@@ -86,6 +86,9 @@ def parse_args():
                     help="time from the raw lattice order instead of the order after the reference's first cell "
                          "sort (m:272, 529-568)")
     ap.add_argument("--no-graph", action="store_true", help="sharded mode: eager launches instead of one CUDA graph per step")
+    ap.add_argument("--nccl-exchange", action="store_true",
+                    help="sharded mode: move the records with one NCCL all-to-all per step instead of the peer-to-peer "
+                         "mailboxes (the pack kernel storing into the neighbours' memory over NVLink; the default)")
     ap.add_argument("--channels", type=int, default=512,
                     help="--mode ensemble: independent channels PER GPU (BASELINE configs[3]: 4096 in all at 8 GPUs)")
     ap.add_argument("--batched", action="store_true", default=True,
@@ -516,7 +519,7 @@ def b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, su
         pt = lp.channel_setup.cell_sorted(cfg, pt)                    # row order after the reference's cell sort
     K, W = args.steps, max(args.warmup, 3)
     dev = torch.device("cuda", local_rank)
-    sc = slabmod.SlabChannel(cfg, pt, rank, world, dev, use_graph=not args.no_graph)
+    sc = slabmod.SlabChannel(cfg, pt, rank, world, dev, use_graph=not args.no_graph, p2p=not args.nccl_exchange)
     ch = sc.slab.ch
     stream = sc.stream                           # the library's kernels, torch and NCCL share this stream in slab mode
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -559,18 +562,28 @@ def b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, su
     graph_used = bool(sc.use_graph and sc._graph_ok and sc._graph is not None)
     if graph_used:
         launches = launches_per_step * K      # every replay launches the kernels of one (captured) step
-    # ---- end to end: host rows -> upload -> halo exchange -> list -> physics -> download, every step ----
+    # ---- end to end: the rank's rows live in PINNED host memory between steps: upload -> halo exchange -> list ->
+    # physics -> download, every step (sphb_ctx_slab_rows_io: pos, vel, rho, drho_dt of the owned region)
     Ke = max(1, min(args.e2e_steps, K))
-    fields = ("pos", "vel", "rho", "drho_dt")
+    n_rows = n_owned                                   # owned region incl. rows awaiting compaction (they stay dead)
+
+    def pinned(cols):
+        t = torch.empty((cols, n_rows) if cols > 1 else (n_rows,), dtype=torch.float64).pin_memory().numpy()
+        return t.T if cols > 1 else t
+    host = {"pos": pinned(2), "vel": pinned(2), "rho": pinned(1), "drho_dt": pinned(1)}
+    sc.slab.rows_io(True, n_rows, host)
+    ch.sync()
 
     def e2e_step():
-        o = sc.slab.owned(fields + ("p",))                       # D2H of the rank's rows
-        sc.slab.reload(o)                                        # H2D of the owned rows (+ the static walls)
-        sc.exchange()                                            # halo copies over NCCL
-        sc.slab.step_end()                                       # list
-        sc.slab.step_begin()                                     # density .. continuity
-        return o
+        with torch.cuda.stream(stream):
+            sc.slab.rows_io(False, n_rows, host)                 # H2D of the rank's rows
+            sc.slab.step_begin()                                 # density .. continuity
+            sc.exchange()                                        # migrants + halo copies between the ranks
+            sc.slab.step_end()                                   # list + shear
+            sc.slab.rows_io(True, n_rows, host)                  # D2H of the results
+        ch.sync()
 
+    # (rows that migrate in during these steps are appended beyond n_rows and stay on the device: a few per step)
     for _ in range(2):
         e2e_step()
     barrier()
@@ -583,11 +596,8 @@ def b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, su
     barrier()
     e2e_value = pt.n_total * Ke / e2e_s
     nl = n_owned + n_halo + n_wall
-    h2d = int(sum_over_ranks(float(n_owned * (16 + 16 + 8 + 8 + 8 + 4) + n_wall * 40)))
-    d2h = int(sum_over_ranks(float(nl * (16 + 16 + 8 + 8 + 8) + (n_owned + n_halo) * 4)))
-    # bring the slab back to a consistent "after step" state for the profile pass
-    sc.exchange()
-    sc.slab.step_end()
+    h2d = int(sum_over_ranks(float(n_rows * 48)))
+    d2h = int(sum_over_ranks(float(n_rows * 48)))
 
     roof, kernels = None, {}
     peaks = {}
@@ -630,13 +640,17 @@ def b200_slab_arm(args, lp, rank, local_rank, world, barrier, max_over_ranks, su
                        "l2": ("256 MiB memset between timed steps" if flush is not None else
                               "no flush: consecutive steps of one simulation"),
                        "parallelism": f"x-slabs on cell-column boundaries, {slabmod.HALO_COLS} halo columns, one "
-                                      f"exchange per step (migration + halo copies: NCCL send/recv; max|v|, shear: "
-                                      f"all-reduce)",
-                       "step_launch": "one CUDA graph per step (kernels + NCCL all-to-all)" if graph_used else "eager",
+                                      f"exchange per step: " + ("migration + halo copies, max|v| and shear partials in one "
+                                      "uneven NCCL all-to-all" if args.nccl_exchange else "the pack kernel stores migrants, halo "
+                                      "copies, max|v| and shear partials straight into the other ranks' mailboxes over NVLink "
+                                      "(CUDA IPC peer memory, sequence-number arrival flags; no collective)"),
+                       "step_launch": ("one CUDA graph per step (library kernels" + (" + NCCL all-to-all)" if args.nccl_exchange
+                                                                                  else " only)")) if graph_used else "eager",
                        "rows_rank0": {"owned": n_owned, "halo": n_halo, "wall": n_wall}},
             "e2e": {"value": e2e_value, "unit": "particle-substeps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "path": "per rank: download rows -> sphb_ctx_slab_init (H2D) -> exchange -> list -> physics"},
+                    "path": "per rank, pinned host rows: sphb_ctx_slab_rows_io (H2D) -> exchange -> list -> physics -> "
+                            "sphb_ctx_slab_rows_io (D2H)"},
             "gpu_launches": int(total_launches),
             "roofline": roof, "kernels": kernels, "cpu_baseline": None, "clocks": clocks,
             "final_state": {"vmax": st["vmax"], "t": st["t"], "step": st["step"]},

@@ -354,6 +354,34 @@ SPHB_API int sphb_ctx_slab_scalars_reduce_at(sphb_ctx *ctx, const double *gather
                                              int world, double *out_dev3);
 SPHB_API int sphb_ctx_slab_counts(sphb_ctx *ctx, int *n_owned, int *n_halo, int *n_wall);
 
+/*
+ * Peer-to-peer exchange ("mailboxes"): the B200-native form of pack -> all-to-all -> reduce -> unpack.  Every rank
+ * owns a mailbox in its device memory; the pack kernel of a neighbour stores its records straight into it over
+ * NVLink (peer pointer) and publishes a sequence number behind a system-wide fence; the unpack kernel waits for that
+ * number.  max|v| and the wall-shear partials travel the same way to every rank.  No collective and no host
+ * synchronisation: a sharded step is one stream of this library's kernels and can be captured as ONE CUDA graph.
+ *   sphb_ctx_slab_p2p_create   allocates the mailbox (rec_cap records per neighbour), returns its device pointer and a
+ *                              64-byte CUDA IPC handle for ranks in other processes
+ *   sphb_ctx_slab_p2p_connect  makes rank r's mailbox known: its IPC handle (other process) or its device pointer
+ *                              (same process; peer access is enabled when peer_device differs from the context's)
+ *   sphb_ctx_slab_p2p_send     scalars to everybody + pack into the neighbours' mailboxes (and the local send buffers)
+ *   sphb_ctx_slab_p2p_recv     waits for the scalars (imports max|v|) and the neighbours' records, appends them
+ *                              (= sphb_ctx_slab_unpack); sphb_ctx_slab_compact may run between send and recv
+ *   sphb_ctx_slab_p2p_monitors max|v|, tau_bottom, tau_top of the whole channel as of the last exchange
+ * A peer that never arrives raises error flag 32 after ~2 s instead of hanging the device.
+ */
+SPHB_API int sphb_ctx_slab_p2p_create(sphb_ctx *ctx, int rank, int world, int rec_cap, void **mailbox_dev, size_t *bytes,
+                                      unsigned char ipc_handle[64]);
+SPHB_API int sphb_ctx_slab_p2p_connect(sphb_ctx *ctx, int rank, const unsigned char ipc_handle[64], void *same_process_ptr,
+                                       int peer_device);
+SPHB_API int sphb_ctx_slab_p2p_send(sphb_ctx *ctx, double *send_left_dev, double *send_right_dev);
+SPHB_API int sphb_ctx_slab_p2p_recv(sphb_ctx *ctx, const double *sent_left_dev, const double *sent_right_dev);
+SPHB_API int sphb_ctx_slab_p2p_monitors(sphb_ctx *ctx, double *out3);
+/* pos, vel, rho, drho_dt of the rows [0, n_rows) of the owned region to (to_host != 0) or from host arrays (column-major,
+ * ideally pinned); asynchronous on the context's stream.  What a host-resident caller carries from step to step. */
+SPHB_API int sphb_ctx_slab_rows_io(sphb_ctx *ctx, int to_host, int n_rows, double *pos, double *vel, double *rho,
+                                   double *drho_dt);
+
 #ifdef __cplusplus
 }
 #endif

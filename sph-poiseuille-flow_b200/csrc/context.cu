@@ -362,6 +362,10 @@ SPHB_API void sphb_ctx_destroy(sphb_ctx *c)
                       &c->slab.pid, &c->slab.a_pid, &c->slab.sort_flag, &c->slab.sort_ptr})
         b->release();
     if (c->slab.h_counts) cudaFreeHost(c->slab.h_counts);
+    for (int r = 0; r < SlabState::kMaxWorld; ++r)
+        if (c->slab.peer_opened[r] && c->slab.peer[r]) cudaIpcCloseMemHandle(c->slab.peer[r]);
+    if (c->slab.mail) cudaFree(c->slab.mail);
+    c->slab.p2p_state.release();
     c->nw.release_all();
     c->sw.release_all();
     c->kprof.release();
@@ -428,6 +432,7 @@ SPHB_API int sphb_ctx_download(sphb_ctx *c, double *pos, double *vel, double *rh
     clear_error();
     if (!c) return set_error("SPHB:arg", "null context");
     SPHB_TRY(bind_device(c));
+    if (c->have_list && !c->flags_pending) SPHB_TRY(ctx_flags_watch(c));
     SPHB_TRY(ctx_flags_poll(c, true));   // an asynchronous run that raised a device flag is recovered (or reported) first
     const int nt = c->prm.n_total;
     const size_t n = (size_t)nt;
@@ -792,7 +797,6 @@ int flags_watch(sphb_ctx *c)
     if (cap != cudaStreamCaptureStatusNone) return 0;
     if (!c->flags_ev) SPHB_CUDA(cudaEventCreateWithFlags(&c->flags_ev, cudaEventDisableTiming));
     SPHB_CUDA(cudaMemcpyAsync(c->h_ints + 4, c->nw.flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
-    SPHB_CUDA(cudaMemcpyAsync(&c->h_scalars[1], c->sc(), sizeof(DevScalars), cudaMemcpyDeviceToHost, c->st));
     SPHB_CUDA(cudaEventRecord(c->flags_ev, c->st));
     c->flags_pending = true;
     return 0;
@@ -803,6 +807,9 @@ int flags_handle(sphb_ctx *c)   // the copy of flags_watch has landed
     c->flags_pending = false;
     const int f = c->h_ints[4];
     if (!f) return 0;
+    // (rare path) where the device stands: the clock stopped at the last consistent step
+    SPHB_CUDA(cudaMemcpyAsync(&c->h_scalars[1], c->sc(), sizeof(DevScalars), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
     const long long dev_step = c->h_scalars[1].step;
     if (f & kErrNonFinite)
         return set_error("SPHB:diverged", "non-finite density or velocity at step %lld (t = %g): the run is frozen there",
@@ -892,7 +899,9 @@ SPHB_API int sphb_ctx_run_dual(sphb_ctx *c, int n_outer, int n_inner)
         c->nw.half_valid = false;   // the replayed build rewrote the list
         c->launches += c->graph_launches;
     }
-    SPHB_TRY(flags_watch(c));
+    // a 4-byte copy of the flags behind the run, not behind every call of a step-by-step caller (a copy is a stream
+    // operation of its own, ~3 us): every 32nd call, and whenever the caller waits (sphb_ctx_sync / download)
+    if (n_outer > 1 || (++c->watch_skip & 31) == 0) SPHB_TRY(flags_watch(c));
     return 0;
 }
 
@@ -1103,6 +1112,7 @@ SPHB_API int sphb_ctx_set_stream(sphb_ctx *c, void *stream)
 SPHB_API int sphb_ctx_sync(sphb_ctx *c)
 {
     CTX_ENTER(false);
+    if (c->have_list && !c->flags_pending) SPHB_TRY(flags_watch(c));
     SPHB_TRY(flags_poll(c, true));   // an asynchronous run that raised a device flag is recovered (or reported) here
     SPHB_CUDA(cudaStreamSynchronize(c->st));
     SPHB_CUDA(cudaGetLastError());

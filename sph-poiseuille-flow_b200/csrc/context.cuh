@@ -26,6 +26,15 @@ struct SlabState {
     DevBuf counts;                // int[16]: block-scan totals / new row counts (device)
     DevBuf block_tot;             // int[5 * blocks]
     int *h_counts = nullptr;      // pinned mirror
+    // peer-to-peer exchange (slab.cu, "mailboxes"): this rank's receive area, written by the neighbours' pack kernels
+    // over NVLink, and the neighbours' areas this rank's pack kernel writes into
+    static constexpr int kMaxWorld = 64;
+    double *mail = nullptr;       // own mailbox (cudaMalloc: exportable as a CUDA IPC handle)
+    size_t mail_doubles = 0;
+    int p2p_rank = 0, p2p_world = 0, p2p_rec_cap = 0;
+    double *peer[kMaxWorld] = {}; // mailbox of every rank as seen from this device (own one included)
+    bool peer_opened[kMaxWorld] = {};   // mapped with cudaIpcOpenMemHandle (to be closed)
+    DevBuf p2p_state;             // long long seq; unsigned ticket; double red[3] (max|v|, tau sums of the whole channel)
 };
 
 struct sphb_ctx {
@@ -67,6 +76,7 @@ struct sphb_ctx {
     // blocking) at the next call and (blocking) by sphb_ctx_sync / status / download
     cudaEvent_t flags_ev = nullptr;
     bool flags_pending = false;
+    unsigned watch_skip = 0;
     int last_inner = 1;          // substeps per outer step of the last run_dual (to redo the steps a poisoned run skipped)
 
     StateView view() const

@@ -223,18 +223,12 @@ __device__ __forceinline__ Bins bin_particle(double2 p, const NbrParams &P, doub
     return b;
 }
 
-// (The kernels of a build return at once while a device error flag is up, like the kernels of the step -- ops_csr.cuh
-// step_poisoned: inside a replayed graph the grid set-up of the build lives in the continuity epilogue, which a
-// poisoned step skips, so a build that ran on would count into stale cell counters.  Binning and scatter are guarded;
-// the walk is not -- it raises capacity flags itself, and the exact build sizes its retry from the totals of ALL its
-// CTAs -- and then merely walks the previous build's entries again.)
-__device__ __forceinline__ bool build_poisoned(const int *flags) { return *reinterpret_cast<const volatile int *>(flags) != 0; }
-
+// (A build inside a poisoned step -- ops_csr.cuh step_poisoned -- runs on: the state stands still, so it rebuilds the
+// list it already has; the continuity kernel of a poisoned step still zeroes the cell counters the binning counts into.)
 __device__ __forceinline__ void bin_count_body(const double2 *__restrict__ pos, NbrParams P, const GridDesc *__restrict__ g,
                                                double2 *__restrict__ snap, int *__restrict__ cell_of,
                                                int *__restrict__ cell_cnt, unsigned int *ghost_anomaly, const int *flags)
 {
-    if (build_poisoned(flags)) return;
     load_counts(P);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_total || row_dead(P, i)) return;
@@ -275,7 +269,6 @@ __device__ __forceinline__ void scatter_body(const double2 *__restrict__ pos, Nb
                                              const int *__restrict__ cell_start, int *__restrict__ cell_fill,
                                              int *__restrict__ tmp_key, double2 *__restrict__ tmp_pos, const int *flags)
 {
-    if (build_poisoned(flags)) return;
     load_counts(P);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_total || row_dead(P, i)) return;
@@ -1372,10 +1365,17 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
         if (attempt > 0) SPHB_CUDA(cudaMemsetAsync(w.totals.p, 0, 8 * sizeof(int), st));
         W.n_tiles = w.n_tiles;
         // staged keys + positions, the rows under assembly of the general walkers, the keys as scattered
-        const size_t smem = 2 * (size_t)w.tile_cap * kWalkSlotBytes + (size_t)(kTileThreads / 32) * w.ell_cap * sizeof(unsigned short);
-        if (smem > (size_t)227 * 1024)
-            return set_error("SPH:Neighbor:entryCapacity", "a tile of %d staged entries with rows of up to %d neighbours "
-                             "exceeds the shared memory of the neighbour walk", w.tile_cap, w.ell_cap);
+        // shared memory of the walk: two copies of the staged (position, key), the rows under assembly of the general
+        // walkers (they grow with the longest row), ~2.4 KB static.  Rows that have grown shrink what a tile may stage.
+        const size_t rows_bytes = (size_t)(kTileThreads / 32) * w.ell_cap * sizeof(unsigned short);
+        const size_t budget = (size_t)227 * 1024 - 4096;
+        if (rows_bytes + 2 * kWalkSlotBytes * 64 > budget)
+            return set_error("SPH:Neighbor:entryCapacity", "rows of up to %d neighbours exceed the shared memory of the "
+                             "neighbour walk", w.ell_cap);
+        const int stage_limit = (int)((budget - rows_bytes) / (2 * kWalkSlotBytes));
+        if (w.tile_cap_limit > stage_limit) w.tile_cap_limit = stage_limit;
+        if (w.tile_cap > w.tile_cap_limit) w.tile_cap = w.tile_cap_limit;   // (a tile that no longer fits is reported by the walk)
+        const size_t smem = 2 * (size_t)w.tile_cap * kWalkSlotBytes + rows_bytes;
         SPHB_TRY(set_walk_smem(smem));
         // one CTA per tile (descriptor + canonical cell order + walk); rows beyond the device-side n_cell_y exit at once
         if (half_only)
@@ -1387,6 +1387,13 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
                 P, g, w.tiles.as<TileDesc>(), w.mirrors, W, w.tile_w, w.cell_start.as<int>(), w.snap.as<double2>(),
                 w.cell_of.as<int>(), w.ell_q.as<uint4>(), w.ell_cnt.as<int>(), w.totals.as<int>(), flags, w.tile_cap);
         nl += 1;
+        if (exact) {   // (not inside a stream capture)
+            const cudaError_t le = cudaGetLastError();
+            if (le != cudaSuccess)
+                return set_error("SPHB:cuda", "neighbour walk launch failed: %s (%u tiles of width %d, %d slots, rows of %d, "
+                                 "%zu bytes of shared memory)", cudaGetErrorString(le), w.n_tiles, w.tile_w, w.tile_cap,
+                                 w.ell_cap, smem);
+        }
         if (!exact) break;
         int host[4] = {0, 0, 0, 0};
         SPHB_CUDA(cudaMemcpyAsync(host, w.totals.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -1149,7 +1149,13 @@ struct ContinuityK {
 __device__ __forceinline__ void continuity_tiles(PhysParams P, const StateView &S, DevScalars *sc, int do_wrap, int advance_clock,
                                                  const GridFuse &F, unsigned cta, unsigned n_ctas)
 {
-    if (step_poisoned(S.flags)) return;   // (nobody takes a clock ticket: t and step stay at the last good step)
+    if (step_poisoned(S.flags)) {
+        // nobody takes a clock ticket: t and step stay at the last good step.  The list build that follows inside a
+        // replayed graph still counts into the cell counters this kernel was to zero for it (GridFuse): do that much.
+        if (F.g != nullptr && advance_clock)
+            for (int j = (int)(cta * kTileThreads + threadIdx.x); j < F.n_cell_ints; j += (int)(n_ctas * kTileThreads)) F.cell_cnt[j] = 0;
+        return;
+    }
     if (sc->dual_on && !sc->sub_on) return;   // device-side scheduler: the outer step is used up
     load_counts(P);
     const bool fuse = F.g != nullptr && advance_clock;

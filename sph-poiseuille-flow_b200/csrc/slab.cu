@@ -128,6 +128,59 @@ __global__ void __launch_bounds__(1024) k_slab_offsets(int *__restrict__ block_t
     }
 }
 
+// ---- peer-to-peer mailboxes ------------------------------------------------------------------------------------
+// Every rank owns a MAILBOX in its device memory, two parities of
+//     [records from the left neighbour | records from the right neighbour | 4 doubles of scalars per rank]
+// A step's sequence number lives in device memory and is bumped by the first kernel of the exchange, so a replayed
+// CUDA graph needs no host-side argument; parity = seq & 1.  A sender writes the records straight into the
+// receiver's mailbox (peer pointer: NVLink stores), fences system-wide and then writes `seq` into header slot 2; the
+// receiver's kernels spin on that slot (with a time-out that raises kErrSlabCap instead of hanging the GPU).  Two
+// parities suffice: a rank can be at most one exchange ahead of a neighbour, because it needs that neighbour's
+// records (or scalars) of exchange s before it can send exchange s + 1.
+struct MailLayout {
+    int world, rec_cap;
+    __host__ __device__ size_t buf() const { return (size_t)kHdr + (size_t)rec_cap * kRec; }
+    __host__ __device__ size_t parity_stride() const { return 2 * buf() + 4 * (size_t)world; }
+    __host__ __device__ size_t total() const { return 2 * parity_stride(); }
+    __host__ __device__ size_t from_left(int p) const { return (size_t)p * parity_stride(); }
+    __host__ __device__ size_t from_right(int p) const { return (size_t)p * parity_stride() + buf(); }
+    __host__ __device__ size_t scal(int p, int r) const { return (size_t)p * parity_stride() + 2 * buf() + 4 * (size_t)r; }
+};
+struct P2PState {
+    long long seq;
+    unsigned ticket;
+    unsigned pad;
+    double red[3];
+};
+struct P2PSend {
+    P2PState *state;        // NULL: no peer-to-peer push (the caller moves the send buffers itself)
+    double *left_mail;      // mailbox of the left / right neighbour (peer pointers)
+    double *right_mail;
+    MailLayout L;
+};
+
+// loads that bypass L1 (a peer may have written the line while this kernel is resident)
+__device__ __forceinline__ double4 ldcg4(const double4 *p)
+{
+    const double2 a = __ldcg(reinterpret_cast<const double2 *>(p)), b = __ldcg(reinterpret_cast<const double2 *>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+constexpr long long kSpinCycles = 4000000000LL;   // ~2 s at 2 GHz: a peer that never arrives is an error, not a hang
+
+// waits until *slot == seq (a double written by a peer after a system-wide fence); false on time-out
+__device__ __forceinline__ bool mail_wait(const double *slot, double seq)
+{
+    const volatile double *v = slot;
+    const long long t0 = clock64();
+    while (*v != seq) {
+        if (clock64() - t0 > kSpinCycles) return false;
+        __nanosleep(64);
+    }
+    __threadfence_system();
+    return true;
+}
+
 struct SlabArrays {
     double2 *pos, *vel;     // current rows (appended to in place by the unpack)
     double *rho, *drho, *mass, *Vol;
@@ -155,8 +208,18 @@ template <bool SEND>
 __global__ void __launch_bounds__(kSlabBlock) k_slab_scatter(SlabArrays A, SlabGeom G,
                                                             const int *__restrict__ block_off,
                                                             const int *__restrict__ counts, double *send_left,
-                                                            double *send_right, int rec_cap, int *flags)
+                                                            double *send_right, int rec_cap, int *flags, P2PSend X)
 {
+    // peer-to-peer push: every record also goes straight into the neighbour's mailbox (what this rank sends to its
+    // LEFT arrives "from the right" over there), the arrival slot is written by the last CTA to finish
+    double *peer_left = nullptr, *peer_right = nullptr;
+    double seq = 0.0;
+    if (SEND && X.state != nullptr) {
+        seq = (double)X.state->seq;
+        const int par = (int)(X.state->seq & 1LL);
+        peer_left = X.left_mail + X.L.from_right(par);
+        peer_right = X.right_mail + X.L.from_left(par);
+    }
     __shared__ int warp_off[cN][kSlabBlock / 32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -184,10 +247,16 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_scatter(SlabArrays A, SlabG
         send_left[1] = (double)counts[cHaloL];
         send_right[0] = (double)counts[cMigR];
         send_right[1] = (double)counts[cHaloR];
+        if (peer_left) {
+            peer_left[0] = (double)counts[cMigL];
+            peer_left[1] = (double)counts[cHaloL];
+            peer_right[0] = (double)counts[cMigR];
+            peer_right[1] = (double)counts[cHaloR];
+        }
         if (nl > rec_cap || nr > rec_cap) atomicOr(flags, kErrSlabCap);
     }
     m &= SEND ? ~(1u << cStay) : (1u << cStay);
-    if (!m) return;
+    if (m) {
     const double2 x = A.pos[i], v = A.vel[i];
     const double rho = A.rho[i], drho = A.drho[i], mass = A.mass[i], Vol = A.Vol[i];
     const Mat2 B = A.B[i];
@@ -209,12 +278,30 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_scatter(SlabArrays A, SlabG
             const bool left = k == cMigL || k == cHaloL;
             const int base = (k == cHaloL) ? counts[cMigL] : (k == cHaloR ? counts[cMigR] : 0);
             const int slot = base + d;
-            if (slot < rec_cap) write_record((left ? send_left : send_right) + kHdr + (size_t)slot * kRec, x, v, rho, drho, mass, Vol, B, pid);
+            if (slot < rec_cap) {
+                write_record((left ? send_left : send_right) + kHdr + (size_t)slot * kRec, x, v, rho, drho, mass, Vol, B, pid);
+                if (peer_left) write_record((left ? peer_left : peer_right) + kHdr + (size_t)slot * kRec, x, v, rho, drho, mass, Vol, B, pid);
+            }
         }
     }
     // a row that migrates stays where it is, marked dead: the neighbour build skips it, so no kernel of the
     // step ever visits it; sphb_ctx_slab_compact squeezes the dead rows out now and then
     if (SEND && (m & ((1u << cMigL) | (1u << cMigR)))) A.pid[i] = -1;
+    }
+    if (SEND && peer_left) {
+        // arrival: every CTA's stores are fenced system-wide before its ticket; the last CTA publishes the sequence
+        // number in both mailboxes
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (atomicAdd(&X.state->ticket, 1u) == gridDim.x - 1) {
+                __threadfence_system();
+                *reinterpret_cast<volatile double *>(peer_left + 2) = seq;
+                *reinterpret_cast<volatile double *>(peer_right + 2) = seq;
+                X.state->ticket = 0u;
+            }
+        }
+    }
 }
 
 // Compaction in CELL order (the slab form of the reference's periodic cell sort, m:529-568): the rows that
@@ -261,13 +348,27 @@ struct UnpackSrc {
 // mark of the owned rows, or the number of stayers right after a compaction).
 __global__ void __launch_bounds__(kSlabBlock) k_slab_unpack(UnpackSrc U, SlabArrays A, SlabGeom G, int rec_cap,
                                                            int nf_cap, int base_is_stay_count, int *counts,
-                                                           int *flags)
+                                                           int *flags, const P2PState *p2p, const double *mail, MailLayout ML)
 {
+    if (p2p != nullptr) {
+        // peer-to-peer: the received records are in this rank's own mailbox; wait for both neighbours' arrival slots
+        __shared__ int ok;
+        const int par = (int)(p2p->seq & 1LL);
+        U.buf[0] = mail + ML.from_left(par);
+        U.buf[1] = mail + ML.from_right(par);
+        if (threadIdx.x == 0) {
+            const double seq = (double)p2p->seq;
+            ok = mail_wait(U.buf[0] + 2, seq) && mail_wait(U.buf[1] + 2, seq) ? 1 : 0;
+            if (!ok) atomicOr(flags, kErrSlabCap);   // a neighbour never arrived: reported, the step is poisoned
+        }
+        __syncthreads();
+        if (!ok) return;
+    }
     // segment sizes from the headers
     const int n_stay = base_is_stay_count ? counts[cStay] : counts[13];
     int seg_n[6], seg_src[6], seg_first[6];
-    const int nmL = min((int)U.buf[0][0], rec_cap), nhL = min((int)U.buf[0][1], rec_cap - nmL);
-    const int nmR = min((int)U.buf[1][0], rec_cap), nhR = min((int)U.buf[1][1], rec_cap - nmR);
+    const int nmL = min((int)__ldcg(U.buf[0]), rec_cap), nhL = min((int)__ldcg(U.buf[0] + 1), rec_cap - nmL);
+    const int nmR = min((int)__ldcg(U.buf[1]), rec_cap), nhR = min((int)__ldcg(U.buf[1] + 1), rec_cap - nmR);
     const int smL = min((int)U.buf[2][0], rec_cap), smR = min((int)U.buf[3][0], rec_cap);
     seg_n[0] = nmL; seg_src[0] = 0; seg_first[0] = 0;      // migrants from the left   -> owned
     seg_n[1] = nmR; seg_src[1] = 1; seg_first[1] = 0;      // migrants from the right  -> owned
@@ -296,8 +397,8 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_unpack(UnpackSrc U, SlabArr
         const int d = n_stay + t;
         if (d >= nf_cap) continue;
         const double4 *r = reinterpret_cast<const double4 *>(U.buf[seg_src[k]] + kHdr + (size_t)(seg_first[k] + off) * kRec);
-        const double4 a = r[0], b = r[1], c = r[2];
-        A.pid[d] = (int)r[3].x;
+        const double4 a = ldcg4(r), b = ldcg4(r + 1), c = ldcg4(r + 2);   // (L2: a peer may have written them)
+        A.pid[d] = (int)ldcg4(r + 3).x;
         double x = a.x;
         if (k >= 2) {   // a halo copy sits next to the slab: across the periodic seam it is shifted by -+DL
             if (x > x_hi + margin) x -= G.DL;
@@ -380,6 +481,57 @@ __global__ void k_slab_scalars_out(const DevScalars *sc, double *out)
     out[2] = sc->tau_top;
 }
 __global__ void k_slab_vmax_in(DevScalars *sc, const double *in) { sc->vmax = in[0]; }
+
+// peer-to-peer exchange, first kernel: bumps the sequence number and writes this rank's scalars (max|v|, wall-shear
+// partials) into the mailbox of EVERY rank (thread r -> rank r), the sequence number last
+struct PeerList {
+    double *mail[SlabState::kMaxWorld];
+};
+__global__ void __launch_bounds__(64) k_slab_p2p_open(const DevScalars *sc, P2PState *st, PeerList peers, MailLayout L, int me)
+{
+    __shared__ long long s_seq;
+    if (threadIdx.x == 0) {
+        st->seq += 1;
+        s_seq = st->seq;
+    }
+    __syncthreads();
+    const int r = (int)threadIdx.x;
+    if (r >= L.world) return;
+    double *slot = peers.mail[r] + L.scal((int)(s_seq & 1LL), me);
+    slot[0] = sc->vmax;
+    slot[1] = sc->tau_bottom;
+    slot[2] = sc->tau_top;
+    __threadfence_system();
+    *reinterpret_cast<volatile double *>(slot + 3) = (double)s_seq;
+}
+// ... and its counterpart: waits for the scalars of every rank in the own mailbox, reduces them in rank order
+// (MAX / SUM: deterministic), imports max|v| (the time step of the next step, m:519-527)
+__global__ void __launch_bounds__(64) k_slab_p2p_scalars(DevScalars *sc, P2PState *st, const double *mail, MailLayout L, int *flags)
+{
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    const int r = (int)threadIdx.x;
+    const int par = (int)(st->seq & 1LL);
+    if (r < L.world && !mail_wait(mail + L.scal(par, r) + 3, (double)st->seq)) bad = 1;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    if (bad) {
+        atomicOr(flags, kErrSlabCap);
+        return;
+    }
+    double vmax = 0.0, tb = 0.0, tt = 0.0;
+    for (int q = 0; q < L.world; ++q) {
+        const double *t = mail + L.scal(par, q);
+        vmax = fmax(vmax, __ldcg(t));
+        tb += __ldcg(t + 1);
+        tt += __ldcg(t + 2);
+    }
+    sc->vmax = vmax;
+    st->red[0] = vmax;
+    st->red[1] = tb;
+    st->red[2] = tt;
+}
 // the scalars of every rank (triple r at g + off[r], or at g + 3 r when off is NULL) -> max|v| (MAX) and the
 // wall-shear sums (SUM, in rank order: deterministic)
 __global__ void k_slab_scalars_reduce(DevScalars *sc, const double *g, const long long *off, int world, double *out3)
@@ -590,7 +742,7 @@ SPHB_API int sphb_ctx_slab_pack(sphb_ctx *c, double *send_left_dev, double *send
     k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), s.pid.as<int>(), G, bt);
     k_slab_offsets<<<cN, 1024, 0, c->st>>>(bt, (int)blocks, cnt);
     k_slab_scatter<true><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, bt, cnt, send_left_dev, send_right_dev,
-                                                           rec_cap, c->nw.flags.as<int>());
+                                                           rec_cap, c->nw.flags.as<int>(), P2PSend{});
     c->launches += 3;
     SPHB_CUDA(cudaGetLastError());
     return 0;
@@ -622,7 +774,7 @@ SPHB_API int sphb_ctx_slab_compact(sphb_ctx *c)
         ProfScope ps(&c->kprof, kPfSlab, c->st);
         k_slab_scatter<false><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, s.block_tot.as<int>(),
                                                                 s.counts.as<int>(), nullptr, nullptr, 0,
-                                                                c->nw.flags.as<int>());
+                                                                c->nw.flags.as<int>(), P2PSend{});
     }
     c->launches += 1;
     SPHB_CUDA(cudaGetLastError());
@@ -653,8 +805,13 @@ SPHB_API int sphb_ctx_slab_unpack(sphb_ctx *c, const double *recv_left_dev, cons
     const SlabArrays A = arrays_of(c);
     {
         ProfScope ps(&c->kprof, kPfSlab, c->st);
+        MailLayout ML;
+        ML.world = s.p2p_world;
+        ML.rec_cap = s.p2p_rec_cap;
+        const bool p2p = recv_left_dev == nullptr && recv_right_dev == nullptr;   // sphb_ctx_slab_p2p_recv
         k_slab_unpack<<<148 * 2, kSlabBlock, 0, c->st>>>(U, A, G, rec_cap, s.nf_cap, s.squeezed ? 1 : 0, cnt,
-                                                         c->nw.flags.as<int>());
+                                                         c->nw.flags.as<int>(), p2p ? s.p2p_state.as<P2PState>() : nullptr,
+                                                         s.mail, ML);
         // appended rows start at the (possibly squeezed) end of the owned region; the walls follow the halo
         k_slab_walls<<<148 * 2, kSlabBlock, 0, c->st>>>(cnt, s.nf_cap, s.n_wall, s.w_pos.as<double2>(),
                                                         s.w_mass.as<double>(), s.w_wall_vel.as<double2>(), c->prm.rho0,
@@ -667,6 +824,179 @@ SPHB_API int sphb_ctx_slab_unpack(sphb_ctx *c, const double *recv_left_dev, cons
     s.squeezed = false;
     c->have_list = false;
     return 0;   // asynchronous: a capacity overflow raises the device flag (sphb_status.error_flags)
+}
+
+// ---- peer-to-peer exchange (mailboxes) ------------------------------------------------------------------------------
+// Replaces pack -> NCCL all-to-all -> scalar reduction -> unpack by kernels of this library only: the pack kernel stores
+// the records straight into the neighbours' mailboxes over NVLink, the unpack kernel waits for its own mailbox to be
+// filled.  No collective, no host synchronisation: the whole sharded step is one stream of kernels (one CUDA graph).
+SPHB_API int sphb_ctx_slab_p2p_create(sphb_ctx *c, int rank, int world, int rec_cap, void **mailbox_dev, size_t *bytes,
+                                      unsigned char ipc_handle[64])
+{
+    SLAB_ENTER();
+    if (rank < 0 || world < 1 || rank >= world || world > SlabState::kMaxWorld || rec_cap < 1)
+        return set_error("SPHB:arg", "bad peer-to-peer description (at most %d ranks)", SlabState::kMaxWorld);
+    SlabState &s = c->slab;
+    if (s.mail) return set_error("SPHB:state", "the slab already has a mailbox");
+    MailLayout L;
+    L.world = world;
+    L.rec_cap = rec_cap;
+    s.mail_doubles = L.total();
+    SPHB_CUDA(cudaMalloc((void **)&s.mail, s.mail_doubles * sizeof(double)));
+    SPHB_CUDA(cudaMemsetAsync(s.mail, 0, s.mail_doubles * sizeof(double), c->st));
+    SPHB_TRY(s.p2p_state.reserve(sizeof(P2PState)));
+    SPHB_CUDA(cudaMemsetAsync(s.p2p_state.p, 0, sizeof(P2PState), c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    s.p2p_rank = rank;
+    s.p2p_world = world;
+    s.p2p_rec_cap = rec_cap;
+    for (int r = 0; r < SlabState::kMaxWorld; ++r) s.peer[r] = nullptr;
+    s.peer[rank] = s.mail;
+    if (ipc_handle) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+        cudaIpcMemHandle_t h;
+        if (cudaIpcGetMemHandle(&h, s.mail) == cudaSuccess) {
+            std::memcpy(ipc_handle, &h, 64);
+        } else {   // (no IPC on this platform: mailboxes of one process still work through plain pointers)
+            (void)cudaGetLastError();
+            std::memset(ipc_handle, 0, 64);
+        }
+    }
+    if (mailbox_dev) *mailbox_dev = s.mail;
+    if (bytes) *bytes = s.mail_doubles * sizeof(double);
+    return 0;
+}
+
+// The mailbox of rank `rank`: either its CUDA IPC handle (another process) or its device pointer (same process; peer
+// access between the two devices is enabled here when they differ).
+SPHB_API int sphb_ctx_slab_p2p_connect(sphb_ctx *c, int rank, const unsigned char ipc_handle[64], void *same_process_ptr,
+                                       int peer_device)
+{
+    SLAB_ENTER();
+    SlabState &s = c->slab;
+    if (!s.mail) return set_error("SPHB:state", "create the own mailbox first (sphb_ctx_slab_p2p_create)");
+    if (rank < 0 || rank >= s.p2p_world) return set_error("SPHB:arg", "bad rank");
+    if (rank == s.p2p_rank) return 0;
+    if (same_process_ptr) {
+        if (peer_device >= 0 && peer_device != c->device) {
+            int can = 0;
+            SPHB_CUDA(cudaDeviceCanAccessPeer(&can, c->device, peer_device));
+            if (!can) return set_error("SPHB:cuda", "device %d cannot access device %d", c->device, peer_device);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return set_error("SPHB:cuda", "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e));
+            (void)cudaGetLastError();
+        }
+        s.peer[rank] = static_cast<double *>(same_process_ptr);
+        return 0;
+    }
+    if (!ipc_handle) return set_error("SPHB:arg", "neither a handle nor a pointer");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, ipc_handle, 64);
+    void *p = nullptr;
+    SPHB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    s.peer[rank] = static_cast<double *>(p);
+    s.peer_opened[rank] = true;
+    return 0;
+}
+
+// First half of the exchange: sequence number + scalars to every rank, then the pack with the records stored into the
+// neighbours' mailboxes.  The local send buffers are still filled (the unpack reads the rows that left from them).
+SPHB_API int sphb_ctx_slab_p2p_send(sphb_ctx *c, double *send_left_dev, double *send_right_dev)
+{
+    SLAB_ENTER();
+    SlabState &s = c->slab;
+    if (!s.mail) return set_error("SPHB:state", "no mailbox");
+    if (!send_left_dev || !send_right_dev) return set_error("SPHB:arg", "bad send buffers");
+    const int left = (s.p2p_rank + s.p2p_world - 1) % s.p2p_world, right = (s.p2p_rank + 1) % s.p2p_world;
+    PeerList PL;
+    for (int r = 0; r < SlabState::kMaxWorld; ++r) PL.mail[r] = r < s.p2p_world ? s.peer[r] : nullptr;
+    for (int r = 0; r < s.p2p_world; ++r)
+        if (!s.peer[r]) return set_error("SPHB:state", "the mailbox of rank %d is not connected", r);
+    MailLayout L;
+    L.world = s.p2p_world;
+    L.rec_cap = s.p2p_rec_cap;
+    P2PSend X;
+    X.state = s.p2p_state.as<P2PState>();
+    X.left_mail = s.peer[left];
+    X.right_mail = s.peer[right];
+    X.L = L;
+    const SlabGeom G = geom_of(c);
+    const unsigned blocks = std::max(1u, grid_for((size_t)s.nf_cap, kSlabBlock));
+    int *bt = s.block_tot.as<int>(), *cnt = s.counts.as<int>();
+    ProfScope ps(&c->kprof, kPfSlab, c->st);
+    k_slab_p2p_open<<<1, 64, 0, c->st>>>(c->sc(), X.state, PL, L, s.p2p_rank);
+    k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), s.pid.as<int>(), G, bt);
+    k_slab_offsets<<<cN, 1024, 0, c->st>>>(bt, (int)blocks, cnt);
+    k_slab_scatter<true><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, bt, cnt, send_left_dev, send_right_dev,
+                                                           s.p2p_rec_cap, c->nw.flags.as<int>(), X);
+    c->launches += 4;
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Second half: wait for every rank's scalars (max|v| -> the next time step; wall-shear sums), then for the two
+// neighbours' records, and append them (sphb_ctx_slab_unpack's work).  sphb_ctx_slab_compact may run in between.
+SPHB_API int sphb_ctx_slab_p2p_recv(sphb_ctx *c, const double *sent_left_dev, const double *sent_right_dev)
+{
+    SLAB_ENTER();
+    SlabState &s = c->slab;
+    if (!s.mail) return set_error("SPHB:state", "no mailbox");
+    MailLayout L;
+    L.world = s.p2p_world;
+    L.rec_cap = s.p2p_rec_cap;
+    k_slab_p2p_scalars<<<1, 64, 0, c->st>>>(c->sc(), s.p2p_state.as<P2PState>(), s.mail, L, c->nw.flags.as<int>());
+    c->launches += 1;
+    SPHB_CUDA(cudaGetLastError());
+    return sphb_ctx_slab_unpack(c, nullptr, nullptr, sent_left_dev, sent_right_dev, s.p2p_rec_cap);
+}
+
+// max|v| and the wall-shear sums of the WHOLE channel as of the last peer-to-peer exchange (3 doubles, host)
+SPHB_API int sphb_ctx_slab_p2p_monitors(sphb_ctx *c, double *out3)
+{
+    SLAB_ENTER();
+    SlabState &s = c->slab;
+    if (!s.mail || !out3) return set_error("SPHB:state", "no mailbox");
+    P2PState h;
+    SPHB_CUDA(cudaMemcpyAsync(&h, s.p2p_state.p, sizeof(P2PState), cudaMemcpyDeviceToHost, c->st));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    out3[0] = h.red[0];
+    out3[1] = h.red[1];
+    out3[2] = h.red[2];
+    return 0;
+}
+
+// The state a caller on the host needs to carry a slab from one step to the next: pos, vel, rho, drho_dt of the rows
+// [0, n_rows) of the owned region (rows that have left included: they are marked dead on the device and stay so).
+// to_host != 0: device -> host, else host -> device.  Column-major [n_rows x 2] / [n_rows] arrays, ideally pinned;
+// asynchronous on the context's stream (sphb_ctx_sync waits).  The end-to-end leg of bench.py for sharded runs.
+SPHB_API int sphb_ctx_slab_rows_io(sphb_ctx *c, int to_host, int n_rows, double *pos, double *vel, double *rho,
+                                   double *drho_dt)
+{
+    SLAB_ENTER();
+    if (n_rows < 0 || n_rows > c->slab.nf_cap || !pos || !vel || !rho || !drho_dt) return set_error("SPHB:arg", "bad rows");
+    if (n_rows == 0) return 0;
+    const size_t n = (size_t)n_rows;
+    double *stage = c->stage.as<double>();   // 6 * n_total doubles: two 2-column regions used here
+    if (to_host) {
+        launch_unpack2(c->pos.as<double2>(), stage, n_rows, c->st);
+        launch_unpack2(c->vel.as<double2>(), stage + 2 * n, n_rows, c->st);
+        SPHB_CUDA(cudaMemcpyAsync(pos, stage, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        SPHB_CUDA(cudaMemcpyAsync(vel, stage + 2 * n, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        SPHB_CUDA(cudaMemcpyAsync(rho, c->rho.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        SPHB_CUDA(cudaMemcpyAsync(drho_dt, c->drho_dt.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    } else {
+        SPHB_CUDA(cudaMemcpyAsync(stage, pos, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        SPHB_CUDA(cudaMemcpyAsync(stage + 2 * n, vel, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        launch_pack2(stage, c->pos.as<double2>(), n_rows, c->st);
+        launch_pack2(stage + 2 * n, c->vel.as<double2>(), n_rows, c->st);
+        SPHB_CUDA(cudaMemcpyAsync(c->rho.p, rho, n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        SPHB_CUDA(cudaMemcpyAsync(c->drho_dt.p, drho_dt, n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        c->mirrors_stale = true;
+    }
+    c->launches += 2;
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
 }
 
 // first half of a reference step on the slab: density + KGC, forces, continuity (m:254-270)

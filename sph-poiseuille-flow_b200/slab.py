@@ -136,6 +136,39 @@ class Slab:
         if import_vmax:
             _check(L.sphb_ctx_slab_vmax_import(self.ch._ctx, C.c_void_p(self.scal.data_ptr())))
 
+    # -- peer-to-peer exchange (mailboxes; csrc/slab.cu) ------------------------------------------------------------
+    def p2p_create(self, rank: int, world: int):
+        """Allocates this slab's mailbox; returns (device pointer, 64-byte CUDA IPC handle)."""
+        ptr, nbytes = C.c_void_p(0), C.c_size_t(0)
+        handle = (C.c_ubyte * 64)()
+        _check(lib().sphb_ctx_slab_p2p_create(self.ch._ctx, C.c_int(rank), C.c_int(world), C.c_int(self.rec_cap),
+                                              C.byref(ptr), C.byref(nbytes), handle))
+        self.mailbox = ptr.value
+        return ptr.value, bytes(handle)
+
+    def p2p_connect(self, rank: int, handle: bytes = None, pointer: int = None, peer_device: int = -1):
+        h = (C.c_ubyte * 64).from_buffer_copy(handle) if handle is not None else None
+        _check(lib().sphb_ctx_slab_p2p_connect(self.ch._ctx, C.c_int(rank), h, C.c_void_p(pointer or 0),
+                                               C.c_int(peer_device)))
+
+    def p2p_send(self):
+        _check(lib().sphb_ctx_slab_p2p_send(self.ch._ctx, C.c_void_p(self.send_left.data_ptr()),
+                                            C.c_void_p(self.send_right.data_ptr())))
+
+    def p2p_recv(self):
+        _check(lib().sphb_ctx_slab_p2p_recv(self.ch._ctx, C.c_void_p(self.send_left.data_ptr()),
+                                            C.c_void_p(self.send_right.data_ptr())))
+
+    def p2p_monitors(self):
+        out = (C.c_double * 3)()
+        _check(lib().sphb_ctx_slab_p2p_monitors(self.ch._ctx, out))
+        return tuple(out)
+
+    def rows_io(self, to_host: bool, n_rows: int, host: dict):
+        """pos, vel, rho, drho_dt of the first n_rows owned-region rows to / from the (pinned) arrays in `host`."""
+        _check(lib().sphb_ctx_slab_rows_io(self.ch._ctx, C.c_int(1 if to_host else 0), C.c_int(n_rows), _p(host["pos"]),
+                                           _p(host["vel"]), _p(host["rho"]), _p(host["drho_dt"])))
+
     def counts(self):
         """(owned region incl. rows that have left and await compaction, halo copies, wall rows)."""
         a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
@@ -179,12 +212,18 @@ class SlabGroup:
     """All slabs of a channel on ONE GPU, exchanged by device copies: the single-process form of the
     sharded run (parity tests; fewer GPUs than slabs).  Same kernels, same buffers as the NCCL form."""
 
-    def __init__(self, cfg, pt, n_slabs: int, device="cuda:0", compact_every: int = 64, **kw):
+    def __init__(self, cfg, pt, n_slabs: int, device="cuda:0", compact_every: int = 64, p2p: bool = False, **kw):
         cuts = partition_columns(n_columns(cfg), n_slabs)
         self.slabs = [Slab(cfg, pt, lo, hi, device, **kw) for lo, hi in cuts]
         self.n = n_slabs
         self.compact_every, self._k = compact_every, 0
         self.tau = (0.0, 0.0)
+        self.p2p = p2p
+        if p2p:      # mailboxes of one process: plain device pointers, no IPC
+            boxes = [s.p2p_create(r, n_slabs)[0] for r, s in enumerate(self.slabs)]
+            for s in self.slabs:
+                for r, ptr in enumerate(boxes):
+                    s.p2p_connect(r, pointer=ptr)
         self.exchange()
         for s in self.slabs:
             s.step_end()
@@ -193,6 +232,19 @@ class SlabGroup:
         import torch
         S = self.slabs
         self._k += 1
+        if self.p2p:
+            # every slab's pack kernel stores into its neighbours' mailboxes; the unpack kernels find them filled
+            squeeze = self.compact_every and self._k % self.compact_every == 0
+            for s in S:
+                s.p2p_send()
+                if squeeze:
+                    s.compact()
+            for s in S:
+                s.ch.sync()          # (one GPU, one stream per slab: all sends before any receive)
+            for s in S:
+                s.p2p_recv()
+            self.tau = S[0].p2p_monitors()[1:3]
+            return
         for s in S:
             s.pack()
             if self.compact_every and self._k % self.compact_every == 0:
@@ -290,7 +342,7 @@ class SlabChannel:
     replayed as one CUDA graph (use_graph)."""
 
     def __init__(self, cfg, pt, rank: int, world: int, device, compact_every: int = 256, use_graph: bool = False,
-                 **kw):
+                 p2p: bool = False, **kw):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -312,7 +364,18 @@ class SlabChannel:
         self._scal_off = torch.tensor(offs, dtype=torch.int64, device=s.device)
         self._head_idx = torch.tensor(np.concatenate([o + np.arange(3) for o in offs]), dtype=torch.int64,
                                       device=s.device)
-        if world > 1:
+        self.p2p = bool(p2p) and world > 1
+        if self.p2p:
+            # mailboxes: every rank's receive area, mapped into every other rank through CUDA IPC; from then on a step
+            # needs neither NCCL nor the host (the kernels of the library talk over NVLink)
+            _, handle = s.p2p_create(rank, world)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle)
+            for r, h in enumerate(handles):
+                if r != rank:
+                    s.p2p_connect(r, handle=h)
+            dist.barrier()
+        elif world > 1:
             view = lambda t, ol: t[ol[0]:ol[0] + ol[1]]   # noqa: E731
             s.send_left, s.send_right = view(self._xin, lay["send_left"]), view(self._xin, lay["send_right"])
             s.recv_left, s.recv_right = view(self._xout, lay["recv_left"]), view(self._xout, lay["recv_right"])
@@ -321,6 +384,8 @@ class SlabChannel:
 
     @property
     def tau(self):
+        if self.p2p:
+            return self.slab.p2p_monitors()[1:3]
         return tuple(float(v) for v in self._red[1:3].tolist())
 
     def exchange(self):
@@ -331,6 +396,12 @@ class SlabChannel:
         dist, s = self.dist, self.slab
         self._k += 1
         squeeze = self.compact_every and self._k % self.compact_every == 0
+        if self.p2p:
+            s.p2p_send()
+            if squeeze:
+                s.compact()
+            s.p2p_recv()
+            return
         s.pack()
         if self.world == 1:
             if squeeze:

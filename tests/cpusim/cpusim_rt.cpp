@@ -313,7 +313,16 @@ std::recursive_mutex &engine_mutex();
 }
 
 const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "cpusim error"; }
-cudaError_t cudaGetLastError() { return cudaSuccess; }
+namespace cpusim {
+static thread_local cudaError_t g_launch_error = cudaSuccess;
+void set_launch_error() { g_launch_error = cudaErrorInvalidValue; }
+}  // namespace cpusim
+cudaError_t cudaGetLastError()
+{
+    const cudaError_t e = cpusim::g_launch_error;
+    cpusim::g_launch_error = cudaSuccess;
+    return e;
+}
 cudaError_t cudaGetDeviceCount(int *n)
 {
     *n = 1;

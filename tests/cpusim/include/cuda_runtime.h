@@ -132,6 +132,15 @@ inline cudaError_t cudaFuncSetAttribute(K *, cudaFuncAttribute, int)
 {
     return cudaSuccess;
 }
+// peer-to-peer plumbing of slab.cu: one process, one "device": handles are never opened
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorInvalidValue; }
+inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorInvalidValue; }
+inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+inline cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 1; return cudaSuccess; }
+inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+enum { cudaErrorPeerAccessAlreadyEnabled = 704 };
 // persistent launches size their grid from these: the simulator pretends to be a 3-SM device with 2 CTAs per SM, so
 // that every CTA takes several tiles (the pipelined path) on the small test channels
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
@@ -151,10 +160,16 @@ inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K *, in
 namespace cpusim {
 inline dim3 to_dim3(dim3 d) { return d; }
 inline dim3 to_dim3(unsigned long long n) { return dim3((unsigned)n); }
+void set_launch_error();
 template <class K, class G, class B, class... A>
 inline void launch(K *kernel, G grid, B block, size_t smem, cudaStream_t st, A... args)
 {
     const dim3 g = to_dim3(grid), b = to_dim3(block);
+    // what the hardware refuses: more than 227 KB of shared memory per CTA (dynamic + a few KB of static), empty grids
+    if (smem + 3072 > (size_t)227 * 1024 || g.x == 0 || g.y == 0 || b.x == 0 || b.x * b.y * b.z > 1024) {
+        set_launch_error();
+        return;
+    }
     enqueue(st, [=]() { run_grid([=]() { kernel(args...); }, g, b, smem); });
 }
 }  // namespace cpusim
@@ -164,6 +179,16 @@ static inline void __syncthreads() { cpusim::cta_barrier(); }
 static inline int __syncthreads_or(int pred) { return cpusim::cta_barrier_or(pred); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { cpusim::warp_barrier(); }
 static inline void __threadfence() {}
+static inline void __threadfence_system() {}
+static inline void __nanosleep(unsigned) {}
+// advances on every call, so that a device-side spin with a time-out (slab.cu mail_wait) ends instead of hanging
+static inline long long clock64()
+{
+    static long long t = 0;
+    return t += 100000000LL;
+}
+template <class T>
+static inline T __ldcg(const T *p) { return *p; }
 static inline void __threadfence_block() {}
 
 namespace cpusim {

@@ -50,12 +50,15 @@ def _global_rows(s, sl):
     return out
 
 
-@pytest.mark.parametrize("n_slabs,dp,DL", [(2, 0.02, 3.0), (3, 0.01, 2.0)])
-def test_slab_group_matches_single_domain(sphb, n_slabs, dp, DL):
+@pytest.mark.parametrize("n_slabs,dp,DL,p2p", [(2, 0.02, 3.0, False), (3, 0.01, 2.0, False), (2, 0.02, 3.0, True),
+                                               (4, 0.02, 4.0, True)])
+def test_slab_group_matches_single_domain(sphb, n_slabs, dp, DL, p2p):
+    """p2p: the peer-to-peer exchange (the pack kernel stores into the neighbours' mailboxes, the unpack kernel
+    waits for its own; sphb_ctx_slab_p2p_*) instead of copies made by the caller -- the same records either way."""
     cs, slab, cfg, pt = _setup(sphb, dp, DL, seed=11)
     # a fast, seam-crossing flow so that rows migrate within a few steps
     ch = _single(sphb, cfg, pt)
-    grp = slab.SlabGroup(cfg, pt, n_slabs)
+    grp = slab.SlabGroup(cfg, pt, n_slabs, p2p=p2p)
 
     # neighbour sets of the initial list
     row_ptr, col = ch.export_csr()
@@ -112,7 +115,7 @@ def test_slab_rows_migrate_across_the_seam(sphb):
     cs, slab, cfg, pt = _setup(sphb, 0.02, 2.0, seed=5)
     pt.vel[:pt.n_fluid, 0] += 3.0           # strong mean flow: ~0.45 cell columns per 100 steps
     ch = _single(sphb, cfg, pt)
-    grp = slab.SlabGroup(cfg, pt, 2, compact_every=40)     # several compactions inside the run
+    grp = slab.SlabGroup(cfg, pt, 2, compact_every=40, p2p=True)     # several compactions inside the run
     start = [set(sl.owned(("rho",))["ids"].tolist()) for sl in grp.slabs]
     for _ in range(150):
         ch.step()

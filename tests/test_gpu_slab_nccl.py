@@ -1,5 +1,6 @@
-"""Two-rank NCCL run of the x-slab sharded channel against the single-domain run (needs >= 2 GPUs; the
-one-GPU form of the same kernels is covered by test_gpu_slab.py)."""
+"""Two-rank runs of the x-slab sharded channel against the single-domain run (need >= 2 GPUs; the one-GPU form of the
+same kernels is covered by test_gpu_slab.py): the NCCL exchange, and the peer-to-peer mailboxes across processes
+(CUDA IPC, kernels of one GPU storing into the memory of the other, no collective inside the step)."""
 import json
 import os
 import subprocess
@@ -26,7 +27,8 @@ cfg = cs.ChannelConfig(DL=3.0, DH=1.0, dp=0.01, c_f=10.0, sort_interval=0).deriv
 pt = cs.developed(cfg, seed=21, jitter=0.2)
 pt.vel[:pt.n_fluid, 0] += 2.0
 # one CUDA graph per step (library kernels + NCCL all-to-all), compaction + re-capture every 16 steps
-sc = slab.SlabChannel(cfg, pt, rank, world, torch.device("cuda", lr), use_graph=True, compact_every=16)
+sc = slab.SlabChannel(cfg, pt, rank, world, torch.device("cuda", lr), use_graph=True, compact_every=16,
+                      p2p=(sys.argv[2] == "p2p"))
 n_steps = 40
 for _ in range(n_steps):
     sc.step()
@@ -58,14 +60,16 @@ dist.destroy_process_group()
 '''
 
 
-def test_two_rank_nccl_slabs_match_single_domain(tmp_path):
+@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+def test_two_rank_slabs_match_single_domain(tmp_path, mode):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), ROOT],
+                        "--master-addr", "127.0.0.1", "--master-port", "29533" if mode == "nccl" else "29534", str(script),
+                        ROOT, mode],
                        capture_output=True, text=True, timeout=180)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1]
