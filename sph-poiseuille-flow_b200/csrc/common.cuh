@@ -78,7 +78,7 @@ struct SmemGrant {
 template <class Kern>
 inline int grant_smem(SmemGrant &g, Kern *kern, size_t bytes)
 {
-    if (bytes <= 48 * 1024) return 0;
+    if (bytes + 8 * 1024 <= 48 * 1024) return 0;   // (the 48 KB every kernel may use include its static shared memory)
     int dev = 0;
     SPHB_CUDA(cudaGetDevice(&dev));
     const bool cached = dev >= 0 && dev < SmemGrant::kMaxDev;
@@ -165,6 +165,8 @@ struct GridFuse {
     int n_cell_ints = 0;
     double cell = 0.0;
     int ncx = 0, cell_cap = 0;
+    int derive = 1;   // 0 (slab of a sharded channel): rows still arrive after the continuity pass -- the unpack kernels
+                      // add their y and derive the grid (slab.cu)
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -267,7 +267,8 @@ int ctx_step_physics(sphb_ctx *c, double remain)
     c->h_step += 1;
     SPHB_TRY(do_publish_dt(c, remain, 0.0));                  // m:259
     SPHB_TRY(do_density(c));                                  // m:254-255
-    SPHB_TRY(do_fused_first_substep(c, true));                // m:256-270
+    // a slab's list build follows after the exchange: the continuity pass starts its grid set-up (GridFuse, derive = 0)
+    SPHB_TRY(do_fused_first_substep(c, true, c->slab.on));    // m:256-270
     return 0;
 }
 

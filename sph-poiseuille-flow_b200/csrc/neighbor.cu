@@ -26,6 +26,7 @@
 #include "tile.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <climits>
 
@@ -1280,6 +1281,10 @@ int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL
         const double per_cell = w.per_cell_hint > 0.0 ? w.per_cell_hint
                                                       : (double)n_total / std::max(1.0, ncx_d * (ncy_d - 9.0));
         int tw = (int)std::floor(0.955 * kTileThreads / std::max(per_cell * kTileRows, 1e-9));
+        if (const char *env = std::getenv("SPHB_TILE_W")) {   // tuning runs only: force the tile width (cells)
+            const int forced = std::atoi(env);
+            if (forced > 0) tw = forced;
+        }
         SPHB_TRY(plan_tiles(w, std::max(1, std::min(tw, kMaxTileW))));
         const double guess = (double)kStageRows * (w.tile_w + 2) * per_cell * 1.25 + 64.0;
         w.tile_cap = (int)std::min((double)w.tile_cap_limit, guess);
@@ -1292,7 +1297,7 @@ int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL
 GridFuse neighbor_grid_fuse(const NeighborWork &w)
 {
     GridFuse F;
-    if (w.slab || !w.grid_armed || !w.grid.p || !w.cell_cnt.p) return F;
+    if (!w.grid_armed || !w.grid.p || !w.cell_cnt.p) return F;
     const NbrParams P = make_params(w);
     F.g = w.grid.as<GridDesc>();
     F.flags = w.flags.as<int>();
@@ -1302,6 +1307,7 @@ GridFuse neighbor_grid_fuse(const NeighborWork &w)
     F.cell = P.cell;
     F.ncx = P.ncx;
     F.cell_cap = P.cell_cap;
+    F.derive = w.slab ? 0 : 1;
     return F;
 }
 

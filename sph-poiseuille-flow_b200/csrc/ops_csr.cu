@@ -1218,7 +1218,7 @@ __device__ __forceinline__ void continuity_tiles(PhysParams P, const StateView &
                 sc->sub_steps += 1;
                 sc->sub_on = sc->Dt_left > 1e-9 * sc->Dt ? 1 : 0;
             }
-            if (fuse) grid_derive(F.g, F.cell, F.ncx, F.cell_cap, F.flags, F.totals);
+            if (fuse && F.derive) grid_derive(F.g, F.cell, F.ncx, F.cell_cap, F.flags, F.totals);
         }
     }
 }

@@ -30,6 +30,63 @@ constexpr int kHdr = 16;        // doubles of buffer header: [0] migrants, [1] h
 constexpr int kSlabBlock = 256;
 enum { cStay = 0, cMigL, cHaloL, cMigR, cHaloR, cN };
 
+// ---- peer-to-peer mailboxes ------------------------------------------------------------------------------------
+// Every rank owns a MAILBOX in its device memory, two parities of
+//     [records from the left neighbour | records from the right neighbour | 4 doubles of scalars per rank]
+// A step's sequence number lives in device memory and is bumped by the first kernel of the exchange, so a replayed
+// CUDA graph needs no host-side argument; parity = seq & 1.  A sender writes the records straight into the
+// receiver's mailbox (peer pointer: NVLink stores), fences system-wide and then writes `seq` into header slot 2; the
+// receiver's kernels spin on that slot (with a time-out that raises kErrSlabCap instead of hanging the GPU).  Two
+// parities suffice: a rank can be at most one exchange ahead of a neighbour, because it needs that neighbour's
+// records (or scalars) of exchange s before it can send exchange s + 1.
+struct MailLayout {
+    int world, rec_cap;
+    __host__ __device__ size_t buf() const { return (size_t)kHdr + (size_t)rec_cap * kRec; }
+    __host__ __device__ size_t parity_stride() const { return 2 * buf() + 4 * (size_t)world; }
+    __host__ __device__ size_t total() const { return 2 * parity_stride(); }
+    __host__ __device__ size_t from_left(int p) const { return (size_t)p * parity_stride(); }
+    __host__ __device__ size_t from_right(int p) const { return (size_t)p * parity_stride() + buf(); }
+    __host__ __device__ size_t scal(int p, int r) const { return (size_t)p * parity_stride() + 2 * buf() + 4 * (size_t)r; }
+};
+struct P2PState {
+    long long seq;
+    unsigned ticket;
+    unsigned pad;
+    double red[3];
+};
+struct P2PSend {
+    P2PState *state;        // NULL: no peer-to-peer push (the caller moves the send buffers itself)
+    double *left_mail;      // mailbox of the left / right neighbour (peer pointers)
+    double *right_mail;
+    MailLayout L;
+};
+
+// loads that bypass L1 (a peer may have written the line while this kernel is resident)
+__device__ __forceinline__ double4 ldcg4(const double4 *p)
+{
+    const double2 a = __ldcg(reinterpret_cast<const double2 *>(p)), b = __ldcg(reinterpret_cast<const double2 *>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+constexpr long long kSpinCycles = 4000000000LL;   // ~2 s at 2 GHz: a peer that never arrives is an error, not a hang
+
+// waits until *slot == seq (a double written by a peer after a system-wide fence); false on time-out
+__device__ __forceinline__ bool mail_wait(const double *slot, double seq)
+{
+    const volatile double *v = slot;
+    const long long t0 = clock64();
+    while (*v != seq) {
+        if (clock64() - t0 > kSpinCycles) return false;
+        __nanosleep(64);
+    }
+    __threadfence_system();
+    return true;
+}
+
+struct PeerList {
+    double *mail[SlabState::kMaxWorld];
+};
+
 struct SlabGeom {
     int col_lo, width, halo, ncx_g;
     double cell, inv_cell, DL;
@@ -84,9 +141,63 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_count(const double2 *__rest
     if (threadIdx.x < cN) block_tot[threadIdx.x * gridDim.x + blockIdx.x] = tot[threadIdx.x];
 }
 
-// exclusive scan of the block totals of each class (one CTA per class; blocks <= a few thousand), totals -> counts
-__global__ void __launch_bounds__(1024) k_slab_offsets(int *__restrict__ block_tot, int blocks, int *__restrict__ counts)
+// Peer-to-peer exchange, opening move (one CTA of >= world threads): bumps the sequence number and writes this rank's
+// scalars (max|v|, wall-shear partials) into the mailbox of EVERY rank (thread r -> rank r), the sequence number last.
+__device__ __forceinline__ void p2p_open_cta(const DevScalars *sc, P2PState *st, const PeerList &peers, const MailLayout &L, int me)
 {
+    __shared__ long long s_seq;
+    if (threadIdx.x == 0) {
+        st->seq += 1;
+        s_seq = st->seq;
+    }
+    __syncthreads();
+    const int r = (int)threadIdx.x;
+    if (r >= L.world) return;
+    double *slot = peers.mail[r] + L.scal((int)(s_seq & 1LL), me);
+    slot[0] = sc->vmax;
+    slot[1] = sc->tau_bottom;
+    slot[2] = sc->tau_top;
+    __threadfence_system();
+    *reinterpret_cast<volatile double *>(slot + 3) = (double)s_seq;
+}
+// ... and its counterpart (one CTA of >= world threads): waits for the scalars of every rank in the own mailbox,
+// reduces them in rank order (MAX / SUM: deterministic), imports max|v| (the time step of the next step, m:519-527)
+__device__ __forceinline__ void p2p_scalars_cta(DevScalars *sc, P2PState *st, const double *mail, const MailLayout &L, int *flags)
+{
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    const int r = (int)threadIdx.x;
+    const int par = (int)(st->seq & 1LL);
+    if (r < L.world && !mail_wait(mail + L.scal(par, r) + 3, (double)st->seq)) bad = 1;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    if (bad) {
+        atomicOr(flags, kErrSlabCap);
+        return;
+    }
+    double vmax = 0.0, tb = 0.0, tt = 0.0;
+    for (int q = 0; q < L.world; ++q) {
+        const double *t = mail + L.scal(par, q);
+        vmax = fmax(vmax, __ldcg(t));
+        tb += __ldcg(t + 1);
+        tt += __ldcg(t + 2);
+    }
+    sc->vmax = vmax;
+    st->red[0] = vmax;
+    st->red[1] = tb;
+    st->red[2] = tt;
+}
+
+// exclusive scan of the block totals of each class (one CTA per class; blocks <= a few thousand), totals -> counts.
+// With peer-to-peer mailboxes one more CTA (blockIdx.x == cN) opens the exchange meanwhile (p2p_open_cta).
+__global__ void __launch_bounds__(1024) k_slab_offsets(int *__restrict__ block_tot, int blocks, int *__restrict__ counts,
+                                                      const DevScalars *sc, P2PState *p2p, PeerList peers, MailLayout ML, int me)
+{
+    if (blockIdx.x == cN) {
+        if (p2p != nullptr) p2p_open_cta(sc, p2p, peers, ML, me);
+        return;
+    }
     __shared__ int warp_sum[32];
     __shared__ int chunk_total, carry;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -126,59 +237,6 @@ __global__ void __launch_bounds__(1024) k_slab_offsets(int *__restrict__ block_t
         if (threadIdx.x == 0) counts[k] = carry;
         __syncthreads();
     }
-}
-
-// ---- peer-to-peer mailboxes ------------------------------------------------------------------------------------
-// Every rank owns a MAILBOX in its device memory, two parities of
-//     [records from the left neighbour | records from the right neighbour | 4 doubles of scalars per rank]
-// A step's sequence number lives in device memory and is bumped by the first kernel of the exchange, so a replayed
-// CUDA graph needs no host-side argument; parity = seq & 1.  A sender writes the records straight into the
-// receiver's mailbox (peer pointer: NVLink stores), fences system-wide and then writes `seq` into header slot 2; the
-// receiver's kernels spin on that slot (with a time-out that raises kErrSlabCap instead of hanging the GPU).  Two
-// parities suffice: a rank can be at most one exchange ahead of a neighbour, because it needs that neighbour's
-// records (or scalars) of exchange s before it can send exchange s + 1.
-struct MailLayout {
-    int world, rec_cap;
-    __host__ __device__ size_t buf() const { return (size_t)kHdr + (size_t)rec_cap * kRec; }
-    __host__ __device__ size_t parity_stride() const { return 2 * buf() + 4 * (size_t)world; }
-    __host__ __device__ size_t total() const { return 2 * parity_stride(); }
-    __host__ __device__ size_t from_left(int p) const { return (size_t)p * parity_stride(); }
-    __host__ __device__ size_t from_right(int p) const { return (size_t)p * parity_stride() + buf(); }
-    __host__ __device__ size_t scal(int p, int r) const { return (size_t)p * parity_stride() + 2 * buf() + 4 * (size_t)r; }
-};
-struct P2PState {
-    long long seq;
-    unsigned ticket;
-    unsigned pad;
-    double red[3];
-};
-struct P2PSend {
-    P2PState *state;        // NULL: no peer-to-peer push (the caller moves the send buffers itself)
-    double *left_mail;      // mailbox of the left / right neighbour (peer pointers)
-    double *right_mail;
-    MailLayout L;
-};
-
-// loads that bypass L1 (a peer may have written the line while this kernel is resident)
-__device__ __forceinline__ double4 ldcg4(const double4 *p)
-{
-    const double2 a = __ldcg(reinterpret_cast<const double2 *>(p)), b = __ldcg(reinterpret_cast<const double2 *>(p) + 1);
-    return make_double4(a.x, a.y, b.x, b.y);
-}
-
-constexpr long long kSpinCycles = 4000000000LL;   // ~2 s at 2 GHz: a peer that never arrives is an error, not a hang
-
-// waits until *slot == seq (a double written by a peer after a system-wide fence); false on time-out
-__device__ __forceinline__ bool mail_wait(const double *slot, double seq)
-{
-    const volatile double *v = slot;
-    const long long t0 = clock64();
-    while (*v != seq) {
-        if (clock64() - t0 > kSpinCycles) return false;
-        __nanosleep(64);
-    }
-    __threadfence_system();
-    return true;
 }
 
 struct SlabArrays {
@@ -424,10 +482,11 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_walls(const int *__restrict
                                                           const double *__restrict__ w_mass,
                                                           const double2 *__restrict__ w_wall_vel, double rho0,
                                                           double p0, int all_rows, SlabArrays A, double2 *wall_vel,
-                                                          double *p)
+                                                          double *p, GridFuse F)
 {
     const int nf = min(counts[8] + counts[9], nf_cap);
     const int first_new = all_rows ? 0 : counts[10];
+    long long kmin = LLONG_MAX, kmax = LLONG_MIN;   // GridFuse: y range of the appended rows and the walls
     double2 *pos = A.pos, *vel = A.vel;
     double *rho = A.rho, *drho = A.drho, *mass = A.mass, *Vol = A.Vol;
     Mat2 *Bm = A.B;
@@ -435,9 +494,19 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_walls(const int *__restrict
         if (t < nf) {   // EOS of the appended fluid rows (m:172); fluid rows carry no wall velocity
             p[t] = p0 * (rho[t] / rho0 - 1.0);
             wall_vel[t] = make_double2(0.0, 0.0);
+            if (F.g) {
+                const long long k = ordered_key(pos[t].y);
+                kmin = k < kmin ? k : kmin;
+                kmax = k > kmax ? k : kmax;
+            }
             continue;
         }
         const int w = t - nf;
+        if (F.g) {
+            const long long k = ordered_key(w_pos[w].y);
+            kmin = k < kmin ? k : kmin;
+            kmax = k > kmax ? k : kmax;
+        }
         pos[t] = w_pos[w];
         vel[t] = make_double2(0.0, 0.0);
         rho[t] = rho0;
@@ -453,15 +522,34 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_walls(const int *__restrict
         wall_vel[t] = w_wall_vel[w];
         p[t] = 0.0;
     }
+    if (F.g) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const long long a = __shfl_xor_sync(0xffffffffu, kmin, d);
+            const long long b = __shfl_xor_sync(0xffffffffu, kmax, d);
+            kmin = a < kmin ? a : kmin;
+            kmax = b > kmax ? b : kmax;
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (kmin != LLONG_MAX) atomicMin(&F.g->ymin_key, kmin);
+            if (kmax != LLONG_MIN) atomicMax(&F.g->ymax_key, kmax);
+        }
+    }
 }
 
 // the new row counts become current: {nf, nfo, nt} read by every kernel of the next step
-__global__ void k_slab_commit_counts(int *counts, int nf_cap, int n_wall)
+// (64 threads).  With peer-to-peer mailboxes it also waits for every rank's scalars and imports max|v|; with GridFuse it
+// derives the grid of the list build that follows (the y range has been reduced by the continuity and wall kernels).
+__global__ void __launch_bounds__(64) k_slab_commit_counts(int *counts, int nf_cap, int n_wall, DevScalars *sc, P2PState *p2p,
+                                                          const double *mail, MailLayout ML, int *flags, GridFuse F)
 {
+    if (p2p != nullptr) p2p_scalars_cta(sc, p2p, mail, ML, flags);
+    if (threadIdx.x != 0) return;
     const int n_owned = min(counts[8], nf_cap), nf = min(counts[8] + counts[9], nf_cap);
     counts[12] = nf;
     counts[13] = n_owned;
     counts[14] = nf + n_wall;
+    if (F.g != nullptr) grid_derive(F.g, F.cell, F.ncx, F.cell_cap, F.flags, F.totals);
 }
 __global__ void k_slab_set_counts(int *counts, int nf, int nfo, int nt)
 {
@@ -482,56 +570,6 @@ __global__ void k_slab_scalars_out(const DevScalars *sc, double *out)
 }
 __global__ void k_slab_vmax_in(DevScalars *sc, const double *in) { sc->vmax = in[0]; }
 
-// peer-to-peer exchange, first kernel: bumps the sequence number and writes this rank's scalars (max|v|, wall-shear
-// partials) into the mailbox of EVERY rank (thread r -> rank r), the sequence number last
-struct PeerList {
-    double *mail[SlabState::kMaxWorld];
-};
-__global__ void __launch_bounds__(64) k_slab_p2p_open(const DevScalars *sc, P2PState *st, PeerList peers, MailLayout L, int me)
-{
-    __shared__ long long s_seq;
-    if (threadIdx.x == 0) {
-        st->seq += 1;
-        s_seq = st->seq;
-    }
-    __syncthreads();
-    const int r = (int)threadIdx.x;
-    if (r >= L.world) return;
-    double *slot = peers.mail[r] + L.scal((int)(s_seq & 1LL), me);
-    slot[0] = sc->vmax;
-    slot[1] = sc->tau_bottom;
-    slot[2] = sc->tau_top;
-    __threadfence_system();
-    *reinterpret_cast<volatile double *>(slot + 3) = (double)s_seq;
-}
-// ... and its counterpart: waits for the scalars of every rank in the own mailbox, reduces them in rank order
-// (MAX / SUM: deterministic), imports max|v| (the time step of the next step, m:519-527)
-__global__ void __launch_bounds__(64) k_slab_p2p_scalars(DevScalars *sc, P2PState *st, const double *mail, MailLayout L, int *flags)
-{
-    __shared__ int bad;
-    if (threadIdx.x == 0) bad = 0;
-    __syncthreads();
-    const int r = (int)threadIdx.x;
-    const int par = (int)(st->seq & 1LL);
-    if (r < L.world && !mail_wait(mail + L.scal(par, r) + 3, (double)st->seq)) bad = 1;
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    if (bad) {
-        atomicOr(flags, kErrSlabCap);
-        return;
-    }
-    double vmax = 0.0, tb = 0.0, tt = 0.0;
-    for (int q = 0; q < L.world; ++q) {
-        const double *t = mail + L.scal(par, q);
-        vmax = fmax(vmax, __ldcg(t));
-        tb += __ldcg(t + 1);
-        tt += __ldcg(t + 2);
-    }
-    sc->vmax = vmax;
-    st->red[0] = vmax;
-    st->red[1] = tb;
-    st->red[2] = tt;
-}
 // the scalars of every rank (triple r at g + off[r], or at g + 3 r when off is NULL) -> max|v| (MAX) and the
 // wall-shear sums (SUM, in rank order: deterministic)
 __global__ void k_slab_scalars_reduce(DevScalars *sc, const double *g, const long long *off, int world, double *out3)
@@ -740,7 +778,7 @@ SPHB_API int sphb_ctx_slab_pack(sphb_ctx *c, double *send_left_dev, double *send
     int *bt = s.block_tot.as<int>(), *cnt = s.counts.as<int>();
     ProfScope ps(&c->kprof, kPfSlab, c->st);
     k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), s.pid.as<int>(), G, bt);
-    k_slab_offsets<<<cN, 1024, 0, c->st>>>(bt, (int)blocks, cnt);
+    k_slab_offsets<<<cN, 1024, 0, c->st>>>(bt, (int)blocks, cnt, nullptr, nullptr, PeerList{}, MailLayout{}, 0);
     k_slab_scatter<true><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, bt, cnt, send_left_dev, send_right_dev,
                                                            rec_cap, c->nw.flags.as<int>(), P2PSend{});
     c->launches += 3;
@@ -812,12 +850,16 @@ SPHB_API int sphb_ctx_slab_unpack(sphb_ctx *c, const double *recv_left_dev, cons
         k_slab_unpack<<<148 * 2, kSlabBlock, 0, c->st>>>(U, A, G, rec_cap, s.nf_cap, s.squeezed ? 1 : 0, cnt,
                                                          c->nw.flags.as<int>(), p2p ? s.p2p_state.as<P2PState>() : nullptr,
                                                          s.mail, ML);
+        // the grid set-up of the list build that follows: started by the step's continuity pass (y range of the rows it
+        // visited, zeroed cell counters), continued here with the appended rows and the walls, derived by the commit
+        const GridFuse F = c->nw.grid_ready ? neighbor_grid_fuse(c->nw) : GridFuse();
         // appended rows start at the (possibly squeezed) end of the owned region; the walls follow the halo
         k_slab_walls<<<148 * 2, kSlabBlock, 0, c->st>>>(cnt, s.nf_cap, s.n_wall, s.w_pos.as<double2>(),
                                                         s.w_mass.as<double>(), s.w_wall_vel.as<double2>(), c->prm.rho0,
                                                         c->prm.p0, s.squeezed ? 1 : 0, A, c->wall_vel.as<double2>(),
-                                                        c->p.as<double>());
-        k_slab_commit_counts<<<1, 1, 0, c->st>>>(cnt, s.nf_cap, s.n_wall);
+                                                        c->p.as<double>(), F);
+        k_slab_commit_counts<<<1, 64, 0, c->st>>>(cnt, s.nf_cap, s.n_wall, c->sc(), p2p ? s.p2p_state.as<P2PState>() : nullptr,
+                                                  s.mail, ML, c->nw.flags.as<int>(), F);
     }
     c->launches += 3;
     SPHB_CUDA(cudaGetLastError());
@@ -925,12 +967,12 @@ SPHB_API int sphb_ctx_slab_p2p_send(sphb_ctx *c, double *send_left_dev, double *
     const unsigned blocks = std::max(1u, grid_for((size_t)s.nf_cap, kSlabBlock));
     int *bt = s.block_tot.as<int>(), *cnt = s.counts.as<int>();
     ProfScope ps(&c->kprof, kPfSlab, c->st);
-    k_slab_p2p_open<<<1, 64, 0, c->st>>>(c->sc(), X.state, PL, L, s.p2p_rank);
     k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), s.pid.as<int>(), G, bt);
-    k_slab_offsets<<<cN, 1024, 0, c->st>>>(bt, (int)blocks, cnt);
+    // (one more CTA than classes: it bumps the sequence number and sends the scalars to every rank meanwhile)
+    k_slab_offsets<<<cN + 1, 1024, 0, c->st>>>(bt, (int)blocks, cnt, c->sc(), X.state, PL, L, s.p2p_rank);
     k_slab_scatter<true><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, bt, cnt, send_left_dev, send_right_dev,
                                                            s.p2p_rec_cap, c->nw.flags.as<int>(), X);
-    c->launches += 4;
+    c->launches += 3;
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -942,12 +984,7 @@ SPHB_API int sphb_ctx_slab_p2p_recv(sphb_ctx *c, const double *sent_left_dev, co
     SLAB_ENTER();
     SlabState &s = c->slab;
     if (!s.mail) return set_error("SPHB:state", "no mailbox");
-    MailLayout L;
-    L.world = s.p2p_world;
-    L.rec_cap = s.p2p_rec_cap;
-    k_slab_p2p_scalars<<<1, 64, 0, c->st>>>(c->sc(), s.p2p_state.as<P2PState>(), s.mail, L, c->nw.flags.as<int>());
-    c->launches += 1;
-    SPHB_CUDA(cudaGetLastError());
+    // (the scalars of every rank are awaited and reduced by the commit kernel of the unpack)
     return sphb_ctx_slab_unpack(c, nullptr, nullptr, sent_left_dev, sent_right_dev, s.p2p_rec_cap);
 }
 

@@ -76,7 +76,9 @@ def test_slab_group_matches_single_domain(sphb, n_slabs, dp, DL, p2p):
         grp.step()
         a, b = ch.status(), grp.status()
         assert b["error_flags"] == 0 and a["error_flags"] == 0
-        assert abs(a["dt"] - b["dt"]) <= 1e-15 * a["dt"], f"dt differs at step {k}"
+        # dt follows max|v|, and velocities agree to rounding only (the slabs sum in another order): measured 1.7e-15
+        log_observed(f"dt at step {k}", abs(a["dt"] - b["dt"]) / a["dt"], 1e-13)
+        assert abs(a["dt"] - b["dt"]) <= 1e-13 * a["dt"], f"dt differs at step {k}"
     want = ch.download(("pos", "vel", "rho", "p", "drho_dt"))
     got = grp.gather(("pos", "vel", "rho", "p", "drho_dt"))
     assert np.array_equal(got["ids"], np.arange(pt.n_fluid))
@@ -93,7 +95,7 @@ def test_slab_group_matches_single_domain(sphb, n_slabs, dp, DL, p2p):
     log_observed("tau_top", abs(tau_t - sa["tau_top"]) / tau_scale, TOL)
     assert abs(tau_b - sa["tau_bottom"]) <= TOL * tau_scale, (tau_b, sa["tau_bottom"])
     assert abs(tau_t - sa["tau_top"]) <= TOL * tau_scale, (tau_t, sa["tau_top"])
-    assert abs(vmax - sa["vmax"]) <= 1e-13 * sa["vmax"], (vmax, sa["vmax"])
+    assert abs(vmax - sa["vmax"]) <= 1e-12 * sa["vmax"], (vmax, sa["vmax"])
     # final neighbour sets (after migration)
     row_ptr, col = ch.export_csr()
     rows = {}
@@ -175,7 +177,7 @@ def test_slabs_at_size_with_the_sliver_of_the_dl96_channel(sphb):
         grp.step()
         a, b = ch.status(), grp.status()
         assert b["error_flags"] == 0 and a["error_flags"] == 0
-        assert abs(a["dt"] - b["dt"]) <= 1e-15 * a["dt"], f"dt differs at step {k}"
+        assert abs(a["dt"] - b["dt"]) <= 1e-13 * a["dt"], f"dt differs at step {k}"
     end = [set(sl.owned(("rho",))["ids"].tolist()) for sl in grp.slabs]
     assert sum(len(x - y) for x, y in zip(start, end)) > 0, "no row migrated"
     want = ch.download(("pos", "vel", "rho", "p", "drho_dt"))
