@@ -125,6 +125,7 @@ int do_sort(sphb_ctx *c)
 {
     const int nf = c->prm.n_fluid, nt = c->prm.n_total;
     if (nf <= 0 || nf >= nt) return 0;   // m:535-537
+    drop_graphs(c);   // the permutation swaps buffer pointers: a cached graph of the step holds the old ones
     ProfScope ps(&c->kprof, kPfSort, c->st);
     SPHB_TRY(sort_permutation(c->sw, c->pos.as<double2>(), nf, c->prm.DL, c->prm.h, c->sc(), c->nw.flags.as<int>(),
                               c->st, &c->launches));
@@ -727,7 +728,29 @@ SPHB_API int sphb_ctx_run_until(sphb_ctx *c, double t_target, double t_end, long
     long long n = 0;
     sphb_status s{};
     SPHB_TRY(status_light(c, &s));
+    // No criterion of m:519-527 allows a step longer than dt_max (max|v| = 0), so the target cannot cut a step short
+    // (m:259) during the next floor((target - t) / dt_max) - 1 steps: those run as replayed graphs with remain = inf --
+    // the same arithmetic -- without the per-step read-back of the clock; the last few steps before the target go one
+    // by one as the reference loop does.
+    const PhysParams &Pp = c->P;
+    const double dt_max = fmin(fmin(0.25 * Pp.h / fmax(Pp.c_f, 1e-12), 0.125 * Pp.h * Pp.h / fmax(Pp.nu, 1e-12)),
+                               0.25 * sqrt(Pp.h / fmax(fabs(Pp.g), 1e-12)));
     while (s.t < t_target - 1e-12 && (max_steps <= 0 || n < max_steps)) {   // m:250
+        if (!c->slab.on && !c->kprof.on && !c->timing) {
+            double safe_d = floor((fmin(t_target, t_end) - s.t) / dt_max) - 1.0;
+            if (max_steps > 0) safe_d = fmin(safe_d, (double)(max_steps - n));
+            if (safe_d >= 2.0) {
+                const long long step0 = s.step;
+                SPHB_TRY(sphb_ctx_run_dual(c, (int)fmin(safe_d, 4096.0), 1));
+                SPHB_TRY(ctx_flags_watch(c));
+                SPHB_TRY(ctx_flags_poll(c, true));   // a list that outgrew its capacity: rebuilt, the skipped steps redone
+                SPHB_TRY(status_light(c, &s));
+                if (s.error_flags) return set_error("SPHB:capacity", "device error flags %d at step %lld", s.error_flags, s.step);
+                if (s.dt < 1e-14) return set_error("SPHB:diverged", "time step collapsed (dt=%g) at t=%g step=%lld", s.dt, s.t, s.step);
+                n += s.step - step0;
+                continue;
+            }
+        }
         const double remain = fmin(t_target - s.t, t_end - s.t);           // m:252
         SPHB_TRY(sphb_ctx_step(c, remain));
         SPHB_TRY(status_light(c, &s));

@@ -626,9 +626,21 @@ __device__ __forceinline__ int general_walk(const NbrParams &P, const TileDesc &
             const int key = s_key[s];   // entries are stored last-inserted first
             const int j = key >> 3;
             const bool low_fluid = j < P.n_fluid && j < i;
-            if (j != i && !(HALF && low_fluid)) {                                  // nb:353
+            const double2 pe = s_xy[s];
+            // Quick reject.  In a channel of >= 6 columns every pairing of the two particles' entries (real / ghost,
+            // seen from either end) has the same minimum-image separation up to rounding (~1e-16 DL), so a candidate
+            // that is beyond the cut-off by more than that is in nobody's row whatever entry a walk meets first; the
+            // exact decisions below (dedup, replay of the lower index's walk) are kept for the ones in reach.
+            bool far = false;
+            if (ncx >= 6) {
+                double dxq = pi.x - pe.x;
+                if (dxq > P.half_DL) dxq -= P.DL;
+                else if (dxq < -P.half_DL) dxq += P.DL;
+                const double dyq = pi.y - pe.y;
+                far = dxq * dxq + dyq * dyq > P.rc2 * (1.0 + 1e-8);
+            }
+            if (j != i && !far && !(HALF && low_fluid)) {                          // nb:353
                 const bool seam = (key & 4) || (low_fluid && i_multi);
-                const double2 pe = s_xy[s];
                 if (!seam) {
                     acc = accept_entry(pi.x, pi.y, pe.x, pe.y, P, m);
                 } else {

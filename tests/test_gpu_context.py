@@ -287,6 +287,54 @@ def test_run_dual_inner1_equals_reference_steps_bitwise(sphb, H):
         ch.close()
 
 
+def test_run_until_chunks_equal_the_reference_loop_bitwise(sphb, H):
+    """sphb_ctx_run_until takes the steps that the target cannot cut short (none of m:519-527 allows more than dt_max,
+    so the first floor((target - t) / dt_max) - 1 steps are safe) as replayed graphs without reading the clock back,
+    and the last few one by one: same steps, same bits as the reference's loop `while t < target: dt = min(dt,
+    target - t)` (m:250-259) taken step by step, across output points and a cell sort, and with a step budget."""
+    prm = H.derive_params(dp=0.05, c_f=10.0, sort_interval=7)
+    st = H.developed_state(prm, seed=23)
+    a = make_channel(sphb, prm, st, sort_interval=7)
+    b = make_channel(sphb, prm, st, sort_interval=7)
+    a.initialise()
+    b.initialise()
+    t_end = 0.08
+    n_a = n_b = 0
+    for target in (0.0211, 0.0550, t_end):
+        while True:                                     # the reference loop, one step per call
+            t = a.status()["t"]
+            if not t < target - 1e-12:
+                break
+            a.step(min(target - t, t_end - t))
+            n_a += 1
+        n_b += b.run_until(target, t_end)
+        sa, sb = a.status(), b.status()
+        for k in ("t", "dt", "vmax", "tau_bottom", "tau_top", "step", "n_half_pairs"):
+            assert sa[k] == sb[k], (k, target)
+        assert abs(sb["t"] - target) <= 1e-12
+    assert n_a == n_b and n_a > 40
+    da, db = a.download(), b.download()
+    for f in FIELDS:
+        assert np.array_equal(da[f], db[f]), f
+    # a step budget smaller than the safe chunk
+    c = make_channel(sphb, prm, st, sort_interval=7)
+    c.initialise()
+    d = make_channel(sphb, prm, st, sort_interval=7)
+    d.initialise()
+    assert c.run_until(t_end, t_end, max_steps=13) == 13 and c.status()["step"] == 13
+    n_c = 13 + c.run_until(t_end, t_end, max_steps=0)
+    n_d = 0
+    while d.status()["t"] < t_end - 1e-12:
+        d.step(t_end - d.status()["t"])
+        n_d += 1
+    assert n_c == n_d and c.status()["t"] == d.status()["t"]
+    dc, dd = c.download(), d.download()
+    for f in FIELDS:
+        assert np.array_equal(dc[f], dd[f]), f
+    for ch in (a, b, c, d):
+        ch.close()
+
+
 def test_run_dual_inner_substeps_against_oracle(sphb, H, oracle_be):
     """Dual-criteria schedule (no reference code at HEAD: parity unpinned as a SCHEDULE), checked as a
     composition of pinned operators: oracle density/viscous/transport once, then n_inner oracle
