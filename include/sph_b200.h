@@ -382,6 +382,41 @@ SPHB_API int sphb_ctx_slab_p2p_monitors(sphb_ctx *ctx, double *out3);
 SPHB_API int sphb_ctx_slab_rows_io(sphb_ctx *ctx, int to_host, int n_rows, double *pos, double *vel, double *rho,
                                    double *drho_dt);
 
+/* ================== 3b. the sharded channel driven from C: all slabs of a node in one process ==================
+ * The C host of section 3 (csrc/slab_group.cu): cuts the channel into n_slabs x-slabs on cell-column boundaries,
+ * creates one context per slab on devices[r % n_devices] (NULL / 0: all visible devices), connects their peer-to-peer
+ * mailboxes (plain device pointers + peer access) and steps them from one host thread.  With one slab per device a
+ * step is one CUDA graph launch per GPU; slabs that share a device are stepped eagerly (tests, small boxes).  No
+ * Python, torch or NCCL involved -- what `sph_poiseuille_b200 --slabs N` runs (driver/sph_poiseuille_main.c).
+ * Arrays are the column-major n_total-row host arrays of sphb_ctx_upload; prm describes the WHOLE channel
+ * (prm->device and prm->sort_interval are ignored: the slabs' now-and-then compaction is their cell sort).
+ *   sphb_slabs_step        one reference step m:251-283 of the whole channel (remain as in sphb_ctx_step)
+ *   sphb_slabs_run         n steps with remain = inf, no host synchronisation
+ *   sphb_slabs_run_until   the loop m:250-283 up to t_target, as sphb_ctx_run_until
+ *   sphb_slabs_status      clock of the channel, max|v| / wall shear reduced over the slabs (slab order), flags OR-ed
+ *   sphb_slabs_download    rows in the GLOBAL order of the arrays given at creation (fluid rows carry their identity
+ *                          through migrations), static wall rows behind them
+ *   sphb_slabs_member      context of slab r (monitors, per-kernel profile, tests); owned by the group
+ */
+typedef struct sphb_slabs sphb_slabs;
+SPHB_API int sphb_slabs_create(const sphb_params *prm, int n_slabs, const int *devices, int n_devices, const double *pos,
+                               const double *vel, const double *rho, const double *drho_dt, const double *mass,
+                               const double *wall_vel, sphb_slabs **out);
+SPHB_API void sphb_slabs_destroy(sphb_slabs *group);
+SPHB_API int sphb_slabs_count(const sphb_slabs *group);
+SPHB_API int sphb_slabs_set_compaction(sphb_slabs *group, int every_n_steps);   /* default 256; 0 = never */
+SPHB_API sphb_ctx *sphb_slabs_member(sphb_slabs *group, int r, int *col_lo, int *col_hi, int *device);
+SPHB_API int sphb_slabs_step(sphb_slabs *group, double remain);
+SPHB_API int sphb_slabs_run(sphb_slabs *group, long long n_steps);
+SPHB_API int sphb_slabs_run_until(sphb_slabs *group, double t_target, double t_end, long long max_steps,
+                                  long long *steps_done);
+SPHB_API int sphb_slabs_sync(sphb_slabs *group);
+SPHB_API int sphb_slabs_status(sphb_slabs *group, sphb_status *out);
+SPHB_API int sphb_slabs_download(sphb_slabs *group, double *pos, double *vel, double *rho, double *p, double *drho_dt);
+/* binned u(y) of the whole channel (sphb_ctx_profile's arguments; gathers the rows: an output-point operation) */
+SPHB_API int sphb_slabs_profile(sphb_slabs *group, double x0, double half_width, int n_bins, double *u_mean, double *count);
+SPHB_API int sphb_slabs_set_time(sphb_slabs *group, double t, long long step);
+
 #ifdef __cplusplus
 }
 #endif

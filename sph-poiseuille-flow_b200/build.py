@@ -45,6 +45,7 @@ UNITS = {
     "ops_csr.cu": [],
     "context.cu": [],
     "slab.cu": [],
+    "slab_group.cu": [],
     "batch.cu": [],
     "api.cu": [],
 }

@@ -465,6 +465,45 @@ SPHB_API int sphb_slabs_download(sphb_slabs *g, double *pos, double *vel, double
     return 0;
 }
 
+// Binned u(y) monitor of the whole channel (m:579-605; sphb_ctx_profile for one context): the fluid rows are gathered
+// and binned on the host -- an output-point operation, not part of the step.
+SPHB_API int sphb_slabs_profile(sphb_slabs *g, double x0, double half_width, int n_bins, double *u_mean, double *count)
+{
+    clear_error();
+    if (!g || n_bins < 1 || !u_mean) return set_error("SPHB:arg", "bad profile arguments");
+    const int nf = g->prm.n_fluid, nt = g->prm.n_total;
+    const double DL = g->prm.DL, DH = g->prm.DH;
+    std::vector<double> pos(2 * (size_t)nt), vel(2 * (size_t)nt), edges((size_t)n_bins + 1), sum((size_t)n_bins, 0.0),
+        cnt((size_t)n_bins, 0.0);
+    SPHB_TRY(sphb_slabs_download(g, pos.data(), vel.data(), nullptr, nullptr, nullptr));
+    for (int k = 0; k <= n_bins; ++k) edges[(size_t)k] = (k == n_bins) ? DH : (double)k * (DH / (double)n_bins);   // m:581
+    for (int i = 0; i < nf; ++i) {
+        if (x0 >= 0.0) {
+            double xw = pos[(size_t)i];
+            if (!(xw >= 0.0 && xw < DL)) {   // MATLAB mod(x, DL), m:573
+                xw = std::fmod(xw, DL);
+                if (xw < 0.0) xw += DL;
+            }
+            double d = std::fabs(xw - x0);
+            d = std::fmin(d, DL - d);
+            if (!(d <= half_width)) continue;
+        }
+        const double y = pos[(size_t)nt + i];
+        if (!(y >= edges[0] && y <= edges[(size_t)n_bins])) continue;   // discretize(): out of range dropped
+        int b = (int)std::floor((y - edges[0]) / (edges[(size_t)n_bins] - edges[0]) * n_bins);
+        b = std::min(std::max(b, 0), n_bins - 1);
+        while (b > 0 && y < edges[(size_t)b]) --b;
+        while (b < n_bins - 1 && y >= edges[(size_t)b + 1]) ++b;
+        sum[(size_t)b] += vel[(size_t)i];
+        cnt[(size_t)b] += 1.0;
+    }
+    for (int k = 0; k < n_bins; ++k) {
+        u_mean[k] = cnt[(size_t)k] > 0.0 ? sum[(size_t)k] / cnt[(size_t)k] : std::numeric_limits<double>::quiet_NaN();   // m:588-589
+        if (count) count[k] = cnt[(size_t)k];
+    }
+    return 0;
+}
+
 SPHB_API int sphb_slabs_set_time(sphb_slabs *g, double t, long long step)
 {
     clear_error();

@@ -12,7 +12,9 @@
  *   S6  main loop, log lines, output points  :246-302
  *   S7  full-length profile and L2           :617-623, SPH_Poiseuille_postprocess.m:42-48
  *
- * Usage: sph_poiseuille_b200 [config.ini] [--dry-run] [--max-steps N] [--dual N_INNER] [--device D]
+ * Usage: sph_poiseuille_b200 [config.ini] [--dry-run] [--max-steps N] [--dual N_INNER] [--device D] [--slabs N]
+ *   --slabs N   the channel sharded into N x-slabs over the visible GPUs (sphb_slabs_*: peer-to-peer mailboxes,
+ *               one CUDA graph launch per GPU and step; slabs share GPUs when there are fewer than N)
  * Environment overrides as in the reference (m:19-26): SPH_CONFIG_OVERRIDE, SPH_RESTART_PATH_OVERRIDE;
  * SPH_PROFILE_CSV_OVERRIDE names the CSV that replaces the postprocess MAT file.
  */
@@ -217,12 +219,29 @@ static int build_lattice(const cfg_t *c, particles_t *p)
     return 0;
 }
 
+/* the particle loop behind the driver: one resident context, or the sharded channel (--slabs N) */
+typedef struct {
+    sphb_ctx *ctx;
+    sphb_slabs *grp;
+} engine_t;
+
+static int eng_status(engine_t *e, sphb_status *st) { return e->grp ? sphb_slabs_status(e->grp, st) : sphb_ctx_status(e->ctx, st); }
+static int eng_profile(engine_t *e, double x0, double half_width, int n_bins, double *u_mean)
+{
+    return e->grp ? sphb_slabs_profile(e->grp, x0, half_width, n_bins, u_mean, NULL)
+                  : sphb_ctx_profile(e->ctx, x0, half_width, n_bins, u_mean, NULL);
+}
+static int eng_run_until(engine_t *e, double target, double t_end, long long chunk, long long *done)
+{
+    return e->grp ? sphb_slabs_run_until(e->grp, target, t_end, chunk, done) : sphb_ctx_run_until(e->ctx, target, t_end, chunk, done);
+}
+
 /* full-length binned u(y) vs analytic: make_postprocess_data m:617-623 + postprocess:42 */
-static double l2_error(const cfg_t *c, sphb_ctx *ctx, int n_bins, double *u_mean, double *u_exact, double *y_mid)
+static double l2_error(const cfg_t *c, engine_t *eng, int n_bins, double *u_mean, double *u_exact, double *y_mid)
 {
     double num = 0.0, den = 0.0;
     int k;
-    if (sphb_ctx_profile(ctx, -1.0, 0.0, n_bins, u_mean, NULL)) return NAN;
+    if (eng_profile(eng, -1.0, 0.0, n_bins, u_mean)) return NAN;
     for (k = 0; k < n_bins; ++k) {
         const double w = c->DH / n_bins;   /* linspace(0, DH, n_bins + 1), m:581 */
         const double lo = k * w, hi = (k == n_bins - 1) ? c->DH : (k + 1) * w;
@@ -238,16 +257,19 @@ static double l2_error(const cfg_t *c, sphb_ctx *ctx, int n_bins, double *u_mean
 /* restart: magic, signature, n_total, t, step, then pos vel rho p drho_dt force force_prior (m:434-445) */
 static const char RESTART_MAGIC[8] = {'S', 'P', 'H', 'B', 'R', 'S', 'T', '1'};
 
-static int save_restart(const char *path, const cfg_t *c, sphb_ctx *ctx, int nt)
+static int save_restart(const char *path, const cfg_t *c, engine_t *eng, int nt)
 {
     sphb_status st;
     size_t n = (size_t)nt;
-    double *buf = (double *)malloc(11 * n * sizeof(double));
+    double *buf = (double *)calloc(11 * n, sizeof(double));
     FILE *f;
     int rc = 1;
     if (!buf) return 1;
-    if (sphb_ctx_status(ctx, &st) ||
-        sphb_ctx_download(ctx, buf, buf + 2 * n, buf + 4 * n, buf + 5 * n, buf + 6 * n, buf + 7 * n, buf + 9 * n, NULL, NULL))
+    if (eng_status(eng, &st)) goto done;
+    /* (the sharded channel carries pos, vel, rho, drho_dt, p; the force blocks are recomputed outputs and stay zero) */
+    if (eng->grp ? sphb_slabs_download(eng->grp, buf, buf + 2 * n, buf + 4 * n, buf + 5 * n, buf + 6 * n)
+                 : sphb_ctx_download(eng->ctx, buf, buf + 2 * n, buf + 4 * n, buf + 5 * n, buf + 6 * n, buf + 7 * n, buf + 9 * n,
+                                     NULL, NULL))
         goto done;
     f = fopen(path, "wb");
     if (!f) goto done;
@@ -266,7 +288,7 @@ done:
 }
 
 /* returns 0 when a matching restart was loaded (signature and sizes agree, m:132-163) */
-static int load_restart(const char *path, const cfg_t *c, sphb_ctx *ctx, int nt, double *t, long long *step)
+static int load_restart(const char *path, const cfg_t *c, particles_t *p, int nt, double *t, long long *step)
 {
     FILE *f = fopen(path, "rb");
     char magic[8], sig[512];
@@ -288,9 +310,12 @@ static int load_restart(const char *path, const cfg_t *c, sphb_ctx *ctx, int nt,
         goto done;
     buf = (double *)malloc(11 * n * sizeof(double));
     if (!buf || fread(buf, sizeof(double), 11 * n, f) != 11 * n) goto done;
-    /* carried state is pos, vel, rho, drho_dt; p / force are recomputed outputs */
-    if (sphb_ctx_upload(ctx, buf, buf + 2 * n, buf + 4 * n, buf + 6 * n, NULL, NULL)) goto done;
-    if (sphb_ctx_set_time(ctx, *t, *step)) goto done;
+    /* carried state is pos, vel, rho, drho_dt; p / force are recomputed outputs.  The rows replace
+     * the lattice before the engine is created (the sharded channel is cut from them). */
+    memcpy(p->pos, buf, 2 * n * sizeof(double));
+    memcpy(p->vel, buf + 2 * n, 2 * n * sizeof(double));
+    memcpy(p->rho, buf + 4 * n, n * sizeof(double));
+    memcpy(p->drho_dt, buf + 6 * n, n * sizeof(double));
     rc = 0;
 done:
     free(buf);
@@ -317,13 +342,17 @@ int main(int argc, char **argv)
     const char *config_path = env_or("SPH_CONFIG_OVERRIDE", "config.ini");
     const char *restart_path = env_or("SPH_RESTART_PATH_OVERRIDE", "restart.sphb");
     const char *csv_path = env_or("SPH_PROFILE_CSV_OVERRIDE", "SPH_Poiseuille_profile.csv");
-    int dry_run = 0, dual_inner = 0, device = -1, a, k, n_bins;
+    int dry_run = 0, dual_inner = 0, device = -1, n_slabs = 0, a, k, n_bins;
     long long max_steps = 0, steps_total = 0;
     cfg_t c;
     particles_t p;
     sphb_params prm;
     sphb_ctx *ctx = NULL;
+    engine_t eng = {NULL, NULL};
     sphb_status st;
+    double t_restart = 0;
+    long long step_restart = 0;
+    int restarted = 0;
     double tau_target, *u_mean, *u_exact, *y_mid, *mid_profiles = NULL, l2;
     int n_profiles = 0, cap_profiles = 0;
     double *profile_times = NULL;
@@ -333,9 +362,11 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[a], "--max-steps") && a + 1 < argc) max_steps = atoll(argv[++a]);
         else if (!strcmp(argv[a], "--dual") && a + 1 < argc) dual_inner = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--device") && a + 1 < argc) device = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--slabs") && a + 1 < argc) n_slabs = atoi(argv[++a]);
         else if (argv[a][0] != '-') config_path = argv[a];
         else {
-            fprintf(stderr, "usage: %s [config.ini] [--dry-run] [--max-steps N] [--dual N_INNER] [--device D]\n", argv[0]);
+            fprintf(stderr, "usage: %s [config.ini] [--dry-run] [--max-steps N] [--dual N_INNER] [--device D] [--slabs N]\n",
+                    argv[0]);
             return 1;
         }
     }
@@ -367,24 +398,45 @@ int main(int argc, char **argv)
     prm.transport_coeff = c.transport_coeff;
     prm.sort_interval = c.sort_interval;
     prm.device = device;
-    CHECK(sphb_ctx_create(&prm, &ctx));
-    CHECK(sphb_ctx_upload(ctx, p.pos, p.vel, p.rho, p.drho_dt, p.mass, p.wall_vel));
     if (c.restart_from_file) {                                    /* S4 */
-        double t0 = 0;
-        long long s0 = 0;
-        if (load_restart(restart_path, &c, ctx, p.n_total, &t0, &s0) == 0)
-            printf("restart loaded: t=%.6f, step=%lld\n", t0, s0);
-        else
+        if (load_restart(restart_path, &c, &p, p.n_total, &t_restart, &step_restart) == 0) {
+            printf("restart loaded: t=%.6f, step=%lld\n", t_restart, step_restart);
+            restarted = 1;
+        } else {
             printf("no usable restart at %s: starting from t = 0\n", restart_path);
+        }
     }
-    CHECK(sphb_ctx_neighbor_build(ctx));                          /* S5, m:167-173 */
-    CHECK(sphb_ctx_density_correction(ctx));
-    CHECK(sphb_ctx_eos(ctx));
+    if (n_slabs > 1) {
+        if (dual_inner > 1) {
+            fprintf(stderr, "--dual is not available with --slabs (the sharded channel runs the reference schedule)\n");
+            return 1;
+        }
+        /* the sharded channel: cut, first exchange, first list and shear monitor inside (S5 without the density
+         * pass: every step starts with one, m:254) */
+        CHECK(sphb_slabs_create(&prm, n_slabs, device >= 0 ? &device : NULL, device >= 0 ? 1 : 0, p.pos, p.vel, p.rho,
+                                p.drho_dt, p.mass, p.wall_vel, &eng.grp));
+        if (restarted) CHECK(sphb_slabs_set_time(eng.grp, t_restart, step_restart));
+        printf("sharded: %d x-slabs", n_slabs);
+        for (k = 0; k < n_slabs; ++k) {
+            int lo = 0, hi = 0, dev = 0;
+            (void)sphb_slabs_member(eng.grp, k, &lo, &hi, &dev);
+            printf("%s columns [%d, %d) on GPU %d", k ? "," : ":", lo, hi, dev);
+        }
+        printf("\n");
+    } else {
+        CHECK(sphb_ctx_create(&prm, &ctx));
+        eng.ctx = ctx;
+        CHECK(sphb_ctx_upload(ctx, p.pos, p.vel, p.rho, p.drho_dt, p.mass, p.wall_vel));
+        if (restarted) CHECK(sphb_ctx_set_time(ctx, t_restart, step_restart));
+        CHECK(sphb_ctx_neighbor_build(ctx));                      /* S5, m:167-173 */
+        CHECK(sphb_ctx_density_correction(ctx));
+        CHECK(sphb_ctx_eos(ctx));
+    }
 
     u_mean = (double *)malloc(3 * (size_t)n_bins * sizeof(double));
     u_exact = u_mean + n_bins;
     y_mid = u_exact + n_bins;
-    CHECK(sphb_ctx_status(ctx, &st));
+    CHECK(eng_status(&eng, &st));
     for (;;) {                                                    /* S6 */
         double target;
         /* mid-channel profile at every output point, the initial state included (m:241-244, 297-301) */
@@ -393,7 +445,7 @@ int main(int argc, char **argv)
             mid_profiles = (double *)realloc(mid_profiles, (size_t)cap_profiles * n_bins * sizeof(double));
             profile_times = (double *)realloc(profile_times, (size_t)cap_profiles * sizeof(double));
         }
-        CHECK(sphb_ctx_profile(ctx, 0.5 * c.DL, fmax(c.dp, c.h), n_bins, mid_profiles + (size_t)n_profiles * n_bins, NULL));
+        CHECK(eng_profile(&eng, 0.5 * c.DL, fmax(c.dp, c.h), n_bins, mid_profiles + (size_t)n_profiles * n_bins));
         profile_times[n_profiles++] = st.t;
         if (!(st.t < c.t_end - 1e-12) || (max_steps > 0 && steps_total >= max_steps)) break;
         target = fmin(st.t + c.output_interval, c.t_end);         /* m:251 */
@@ -405,10 +457,10 @@ int main(int argc, char **argv)
                 CHECK(sphb_ctx_run_dual(ctx, 1, dual_inner));
                 done = dual_inner;
             } else {
-                CHECK(sphb_ctx_run_until(ctx, target, c.t_end, chunk, &done));
+                CHECK(eng_run_until(&eng, target, c.t_end, chunk, &done));
             }
             steps_total += done;
-            CHECK(sphb_ctx_status(ctx, &st));
+            CHECK(eng_status(&eng, &st));
             if (st.error_flags) {
                 fprintf(stderr, "device error flags %d at step %lld\n", st.error_flags, st.step);
                 return 3;
@@ -421,10 +473,10 @@ int main(int argc, char **argv)
             }
         }
         printf("output point: t=%.6f, step=%lld\n", st.t, st.step);   /* m:294 */
-        if (save_restart(restart_path, &c, ctx, p.n_total)) fprintf(stderr, "warning: could not write %s\n", restart_path);
+        if (save_restart(restart_path, &c, &eng, p.n_total)) fprintf(stderr, "warning: could not write %s\n", restart_path);
     }
 
-    l2 = l2_error(&c, ctx, n_bins, u_mean, u_exact, y_mid);       /* S7 */
+    l2 = l2_error(&c, &eng, n_bins, u_mean, u_exact, y_mid);      /* S7 */
     printf("L2 relative error = %.4f%%\n", 100.0 * l2);
     printf(l2 < 0.05 ? "validation passed: L2_error < 5%%\n" : "validation not met: L2_error >= 5%%\n");
     {
@@ -443,11 +495,12 @@ int main(int argc, char **argv)
             printf("profiles written: %s\n", csv_path);
         }
     }
-    {
+    if (ctx) {
         sphb_timing tm;
         if (sphb_ctx_timing(ctx, &tm) == 0) printf("kernel launches: %lld\n", tm.launches);
     }
     sphb_ctx_destroy(ctx);
+    sphb_slabs_destroy(eng.grp);
     free(u_mean);
     free(mid_profiles);
     free(profile_times);

@@ -308,6 +308,84 @@ class SlabGroup:
             s.close()
 
 
+class NativeSlabGroup:
+    """The sharded channel driven by the library's own C host (sphb_slabs_*, csrc/slab_group.cu): all slabs of a node in
+    this process, one per GPU (or several per GPU), peer-to-peer mailboxes, one CUDA graph launch per GPU and step.
+    No torch, no NCCL: what `sph_poiseuille_b200 --slabs N` runs.  Same interface as SlabGroup where it matters."""
+
+    def __init__(self, cfg, pt, n_slabs: int, devices=None, compact_every: int = 256, **overrides):
+        from . import _Params
+        kw = dict(n_fluid=pt.n_fluid, n_total=pt.n_total, DL=cfg.DL, DH=cfg.DH, dp=cfg.dp, h=cfg.h, rho0=cfg.rho0,
+                  p0=cfg.p0, c_f=cfg.c_f, mu=cfg.mu, gravity_g=cfg.gravity_g, inv_sigma0=cfg.inv_sigma0,
+                  transport_coeff=cfg.transport_coeff, sort_interval=0, device=-1, max_neighbors_hint=0)
+        kw.update(overrides)
+        self.n_fluid, self.n_total = pt.n_fluid, pt.n_total
+        cp = _Params(*[kw[k] for k in ("n_fluid", "n_total", "DL", "DH", "dp", "h", "rho0", "p0", "c_f", "mu", "gravity_g",
+                                       "inv_sigma0", "transport_coeff", "sort_interval", "device", "max_neighbors_hint")])
+        devs = None
+        if devices is not None:
+            devs = (C.c_int * len(devices))(*devices)
+        f = np.asfortranarray
+        self._g = C.c_void_p()
+        _check(lib().sphb_slabs_create(C.byref(cp), C.c_int(n_slabs), devs, C.c_int(len(devices) if devices else 0),
+                                       _p(f(pt.pos)), _p(f(pt.vel)), _p(np.ascontiguousarray(pt.rho)),
+                                       _p(np.ascontiguousarray(pt.drho_dt)), _p(np.ascontiguousarray(pt.mass)),
+                                       _p(f(pt.wall_vel)), C.byref(self._g)))
+        _check(lib().sphb_slabs_set_compaction(self._g, C.c_int(compact_every)))
+        self.n = n_slabs
+
+    def step(self, remain=float("inf")):
+        _check(lib().sphb_slabs_step(self._g, C.c_double(remain)))
+
+    def run(self, n_steps: int):
+        _check(lib().sphb_slabs_run(self._g, C.c_longlong(n_steps)))
+
+    def run_until(self, t_target: float, t_end: float, max_steps: int = 0) -> int:
+        n = C.c_longlong(0)
+        _check(lib().sphb_slabs_run_until(self._g, C.c_double(t_target), C.c_double(t_end), C.c_longlong(max_steps),
+                                          C.byref(n)))
+        return n.value
+
+    def sync(self):
+        _check(lib().sphb_slabs_sync(self._g))
+
+    def status(self):
+        from . import _Status
+        st = _Status()
+        _check(lib().sphb_slabs_status(self._g, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in _Status._fields_}
+
+    def gather(self, fields=("pos", "vel", "rho", "p", "drho_dt")):
+        """Fluid rows by global particle id (the order of the arrays given at creation)."""
+        nt = self.n_total
+        buf = {k: (np.zeros((nt, 2), order="F") if k in ("pos", "vel") else np.zeros(nt)) for k in fields}
+        arg = [_p(buf[k]) if k in buf else None for k in ("pos", "vel", "rho", "p", "drho_dt")]
+        _check(lib().sphb_slabs_download(self._g, *arg))
+        out = {k: v[:self.n_fluid] for k, v in buf.items()}
+        out["ids"] = np.arange(self.n_fluid)
+        return out
+
+    def member_device(self, r: int) -> int:
+        lo, hi, dev = C.c_int(0), C.c_int(0), C.c_int(0)
+        L = lib()
+        L.sphb_slabs_member.restype = C.c_void_p
+        L.sphb_slabs_member(self._g, C.c_int(r), C.byref(lo), C.byref(hi), C.byref(dev))
+        return dev.value
+
+    def close(self):
+        if self._g:
+            L = lib()
+            L.sphb_slabs_destroy.restype = None
+            L.sphb_slabs_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def exchange_layout(rank: int, world: int, nbuf: int, n_scal: int = 4):
     """Layout of the one uneven all-to-all of a sharded step.  The chunk rank `rank` sends to / receives from
     rank d is [n_scal scalars][its "to the left" record buffer if d is its left neighbour][its "to the right"

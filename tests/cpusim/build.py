@@ -25,7 +25,7 @@ LIB = os.path.join(OUT, "libsph_b200_cpusim.so")
 DRIVER = os.path.join(OUT, "sph_poiseuille_cpusim")
 MEXHOST = os.path.join(OUT, "libsphb_mex_stubhost_cpusim.so")
 UNITS = {"misc.cu": [], "scan.cu": [], "neighbor.cu": ["-ffp-contract=off"], "sort.cu": ["-ffp-contract=off"],
-         "ops_pairs.cu": [], "ops_csr.cu": [], "context.cu": [], "slab.cu": [], "batch.cu": [], "api.cu": []}
+         "ops_pairs.cu": [], "ops_csr.cu": [], "context.cu": [], "slab.cu": [], "slab_group.cu": [], "batch.cu": [], "api.cu": []}
 
 
 def _matching(text: str, start: int, open_ch: str, close_ch: str) -> int:

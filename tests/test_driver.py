@@ -114,3 +114,39 @@ def test_driver_run_matches_golden_trajectory(tmp_path, golden):
     r2 = subprocess.run([_driver(), cfg2, "--max-steps", "20"], capture_output=True, text=True, env=env)
     assert r2.returncode == 0, r2.stderr
     assert "restart loaded: t=" in r2.stdout and "step=140," in r2.stdout
+
+
+@pytest.mark.gpu
+def test_driver_sharded_run_matches_the_single_domain_run(tmp_path):
+    """`--slabs 2`: the C host of the sharded channel (sphb_slabs_*, no Python in the loop) against the same driver on
+    one context: same step count and clock, dt / max|v| / wall shear within the print precision, same L2, and a restart
+    written by the sharded run is accepted by a single-context run."""
+    cfgp = _write(tmp_path, dp=0.04, c_f=10.0)
+    out = {}
+    for tag, extra in (("one", []), ("slabs", ["--slabs", "2"])):
+        env = dict(os.environ, SPH_RESTART_PATH_OVERRIDE=str(tmp_path / f"restart_{tag}.sphb"),
+                   SPH_PROFILE_CSV_OVERRIDE=str(tmp_path / f"profile_{tag}.csv"))
+        r = subprocess.run([_driver(), cfgp, "--max-steps", "60"] + extra, capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr + r.stdout[-400:]
+        out[tag] = r.stdout
+    assert "sharded: 2 x-slabs: columns [0, " in out["slabs"]
+    pat = (r"step=(\d+), t=([\d.]+)/[\d.]+, dt=([\d.e+-]+), pairs=(\d+), vmax=([\d.]+)\n"
+           r"  \[thick-wall-noslip\] tau_bot=([-\d.]+), tau_top=([-\d.]+), tau_target=([\d.]+)")
+    a, b = re.findall(pat, out["one"]), re.findall(pat, out["slabs"])
+    assert [int(x[0]) for x in a] == [20, 40, 60] == [int(x[0]) for x in b]
+    for x, y in zip(a, b):
+        assert x[1] == y[1]                                              # t to the printed 1e-6
+        assert abs(float(x[2]) - float(y[2])) <= 2e-4 * float(x[2])      # dt (4 digits printed)
+        assert abs(float(x[4]) - float(y[4])) <= 2e-4                    # max|v|
+        assert abs(float(x[5]) - float(y[5])) <= 2e-4 and abs(float(x[6]) - float(y[6])) <= 2e-4
+    l2 = [float(re.search(r"L2 relative error = ([\d.]+)%", out[k]).group(1)) for k in ("one", "slabs")]
+    assert abs(l2[0] - l2[1]) <= 1e-3
+    pa = np.genfromtxt(tmp_path / "profile_one.csv", delimiter=",", names=True)
+    pb = np.genfromtxt(tmp_path / "profile_slabs.csv", delimiter=",", names=True)
+    assert np.allclose(pa["u_mean"], pb["u_mean"], rtol=0, atol=1e-9)
+    cfg2 = _write(tmp_path, dp=0.04, c_f=10.0, restart=1)
+    env = dict(os.environ, SPH_RESTART_PATH_OVERRIDE=str(tmp_path / "restart_slabs.sphb"),
+               SPH_PROFILE_CSV_OVERRIDE=str(tmp_path / "profile_2.csv"))
+    r2 = subprocess.run([_driver(), cfg2, "--max-steps", "20"], capture_output=True, text=True, env=env)
+    assert r2.returncode == 0, r2.stderr
+    assert "restart loaded: t=" in r2.stdout and "step=80," in r2.stdout

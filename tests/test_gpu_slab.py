@@ -111,6 +111,72 @@ def test_slab_group_matches_single_domain(sphb, n_slabs, dp, DL, p2p):
     _ = owned0
 
 
+@pytest.mark.parametrize("n_slabs,dp,DL", [(3, 0.02, 3.0), (2, 0.01, 2.0)])
+def test_native_c_host_matches_single_domain(sphb, n_slabs, dp, DL):
+    """The sharded channel driven by the library's C host (sphb_slabs_*, csrc/slab_group.cu: cut, mailboxes, stepping --
+    what `sph_poiseuille_b200 --slabs N` runs, no Python in the loop) against the single-domain run: steps with and
+    without a remaining-time cut, then the reference loop up to a target (run_until), with a compaction in between."""
+    cs, slab, cfg, pt = _setup(sphb, dp, DL, seed=21)
+    pt.vel[:pt.n_fluid, 0] += 2.0            # rows migrate within the run
+    ch = _single(sphb, cfg, pt)
+    grp = slab.NativeSlabGroup(cfg, pt, n_slabs, devices=[0], compact_every=9)
+    for k in range(14):
+        remain = float("inf") if k % 5 else 0.6 * ch.status()["dt"]     # now and then the target cuts the step (m:259)
+        ch.step(remain)
+        grp.step(remain)
+        a, b = ch.status(), grp.status()
+        assert a["error_flags"] == 0 and b["error_flags"] == 0
+        assert a["step"] == b["step"] and abs(a["t"] - b["t"]) <= 1e-13 * a["t"]
+        assert abs(a["dt"] - b["dt"]) <= 1e-13 * a["dt"], f"dt differs at step {k}"
+    t_target = ch.status()["t"] + 11.3 * ch.status()["dt"]
+    n_a = ch.run_until(t_target, 1.0)
+    n_b = grp.run_until(t_target, 1.0)
+    assert n_a == n_b and n_a >= 11
+    a, b = ch.status(), grp.status()
+    assert abs(a["t"] - t_target) <= 1e-12 and abs(b["t"] - t_target) <= 1e-12
+    tau_scale = max(abs(a["tau_bottom"]), abs(a["tau_top"]))
+    assert abs(a["tau_bottom"] - b["tau_bottom"]) <= TOL * tau_scale and abs(a["tau_top"] - b["tau_top"]) <= TOL * tau_scale
+    assert abs(a["vmax"] - b["vmax"]) <= 1e-12 * a["vmax"]
+    want = ch.download(("pos", "vel", "rho", "p", "drho_dt"))
+    got = grp.gather(("pos", "vel", "rho", "p", "drho_dt"))
+    nf = pt.n_fluid
+    for f in ("pos", "vel", "rho", "p", "drho_dt"):
+        assert_close(got[f], want[f][:nf], f, TOL)
+    ch.close()
+    grp.close()
+
+
+def test_native_c_host_one_slab_per_gpu(sphb):
+    """One slab per GPU: every slab's step is ONE replayed CUDA graph on its own device, the slabs meet only in each
+    other's mailboxes over NVLink (peer access inside one process).  Needs two GPUs (the driver's 1-GPU box skips it;
+    run by the multi-GPU calls of the round, profiles/README.md)."""
+    import torch
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least two GPUs")
+    n_slabs = min(n_dev, 4)
+    cs, slab, cfg, pt = _setup(sphb, 0.01, 4.0, seed=31)
+    pt.vel[:pt.n_fluid, 0] += 2.0
+    ch = _single(sphb, cfg, pt)
+    grp = slab.NativeSlabGroup(cfg, pt, n_slabs, compact_every=25)
+    assert sorted(grp.member_device(r) for r in range(n_slabs)) == list(range(n_slabs))
+    ch.run_dual(60, 1)
+    grp.run(60)                      # graph replays, two compaction steps in between
+    grp.sync()
+    a, b = ch.status(), grp.status()
+    assert a["error_flags"] == 0 and b["error_flags"] == 0 and a["step"] == b["step"] == 60
+    assert abs(a["t"] - b["t"]) <= 1e-12 * a["t"]
+    want = ch.download(("pos", "vel", "rho", "p", "drho_dt"))
+    got = grp.gather(("pos", "vel", "rho", "p", "drho_dt"))
+    for f in ("pos", "vel", "rho", "p", "drho_dt"):
+        assert_close(got[f], want[f][:pt.n_fluid], f, TOL)
+    t_target = a["t"] + 17.5 * a["dt"]
+    assert ch.run_until(t_target, 1.0) == grp.run_until(t_target, 1.0)
+    assert abs(grp.status()["t"] - t_target) <= 1e-12
+    ch.close()
+    grp.close()
+
+
 def test_slab_rows_migrate_across_the_seam(sphb):
     """Uniform fast drift: within a few hundred steps rows cross slab boundaries and x = DL; the slabs
     keep every particle exactly once and stay equal to the single-domain run."""
