@@ -543,7 +543,7 @@ def test_run_dual_freezes_and_recovers_from_list_capacity(sphb, H, oracle_be):
         H.reference_step(oracle_be, ref, prm)
     d = ch.download()
     for f in ("pos", "vel", "rho", "p", "drho_dt"):
-        assert_close(d[f], getattr(ref, f), f, 100 * TOL)   # three steps of a violently relaxing (squeezed) state
+        assert_close(d[f], getattr(ref, f), f, TOL)   # three steps of a violently relaxing (squeezed) state; measured 3.5e-15
     assert s["n_half_pairs"] == ref.pairs[0].size
     ch.close()
 
@@ -606,5 +606,5 @@ def test_device_side_dual_criteria_schedule(sphb, H, oracle_be, mu, max_inner):
     assert s["error_flags"] == 0 and s["n_half_pairs"] == ref.pairs[0].size
     d = ch.download()
     for f in ("pos", "vel", "rho", "p", "drho_dt", "force", "force_prior", "Vol", "B"):
-        assert_close(d[f], getattr(ref, f), f, 10 * TOL)
+        assert_close(d[f], getattr(ref, f), f, TOL)   # measured 1.0e-13 (r2 call 10)
     ch.close()

@@ -195,9 +195,9 @@ def test_slab_rows_migrate_across_the_seam(sphb):
     want = ch.download(("pos", "vel", "rho"))
     got = grp.gather(("pos", "vel", "rho"))
     nf = pt.n_fluid
-    # 150 steps of independent rounding (different summation orders): looser than the one-step gate
+    # 150 steps of independent rounding (different summation orders); measured on the B200: 2.1e-14 (r2 call 10)
     for f in ("pos", "vel", "rho"):
-        assert_close(got[f], want[f][:nf], f, 1e-9)
+        assert_close(got[f], want[f][:nf], f, TOL)
     assert grp.status()["error_flags"] == 0
     ch.close()
     grp.close()
@@ -221,7 +221,7 @@ def test_halo_towards_the_seam_covers_four_cells_with_a_sliver_last_column(sphb)
     nf = pt.n_fluid
     assert np.array_equal(got["ids"], np.arange(nf))
     for f in ("pos", "vel", "rho", "p", "drho_dt"):
-        assert_close(got[f], want[f][:nf], f, 10 * TOL)
+        assert_close(got[f], want[f][:nf], f, TOL)   # measured 1.2e-13 (r2 call 10)
     ch.close()
     grp.close()
 

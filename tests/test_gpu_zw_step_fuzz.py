@@ -42,13 +42,13 @@ def test_step_fuzz_against_oracle(sphb, H, oracle_be, block):
             ch.step()
             s, d = ch.status(), ch.download()
             assert s["error_flags"] == 0 and s["n_half_pairs"] == ref.pairs[0].size, (what, k)
-            log_observed(f"{what} step {k} dt", abs(s["dt"] - dt) / dt, 1e-11)
-            assert abs(s["dt"] - dt) <= 1e-11 * dt, (what, k)
-            # the tolerance is per step; round-off carried over from earlier steps grows with the flow's own
-            # sensitivity, so later steps get the head-room the multi-step tests use
+            log_observed(f"{what} step {k} dt", abs(s["dt"] - dt) / dt, 1e-12)
+            assert abs(s["dt"] - dt) <= 1e-12 * dt, (what, k)
+            # measured on the B200 (r2 call 10): at most 6.7e-13 over the 600 comparisons of the three blocks, four
+            # steps deep -- the one-step tolerance holds for every step
             for f in FIELDS:
-                log_observed(f"{what} step {k} {f}", _rel(d[f], getattr(ref, f)), TOL * (1 if k == 0 else 10))
-                assert _rel(d[f], getattr(ref, f)) <= TOL * (1 if k == 0 else 10), (what, k, f)
+                log_observed(f"{what} step {k} {f}", _rel(d[f], getattr(ref, f)), TOL)
+                assert _rel(d[f], getattr(ref, f)) <= TOL, (what, k, f)
         ch.close()
 
 

@@ -41,17 +41,18 @@ def _assert_same(a, b):
     """Batched launches run the same __device__ bodies as the single-channel kernels, but they are separate kernels
     to the compiler (arguments from a device record, other register budget), so the last bit of a sum may differ
     on the GPU (FMA contraction is decided per kernel); on the CPU simulator the two are bit-identical.  Fields are
-    held to the one-step tolerance times a small factor for the steps taken, integers and flags exactly."""
+    held to the field tolerance (measured on the B200, r2 call 10: at most 2.0e-13 over all batch tests, clock and
+    monitors included), integers and flags exactly."""
     for k, (x, y) in enumerate(zip(a, b)):
         dx, dy = x.download(), y.download()
         for f in FIELDS:
-            assert_close(dx[f], dy[f], f"channel {k} {f}", 20 * TOL)
+            assert_close(dx[f], dy[f], f"channel {k} {f}", TOL)
         sx, sy = x.status(), y.status()
         for key in ("step", "n_half_pairs", "n_csr_entries"):
             assert sx[key] == sy[key], (k, key, sx[key], sy[key])
         for key in ("t", "dt", "vmax", "tau_bottom", "tau_top"):
-            log_observed(f"channel {k} {key}", abs(sx[key] - sy[key]) / max(abs(sy[key]), 1e-300), 1e-10)
-            assert abs(sx[key] - sy[key]) <= 1e-10 * max(abs(sy[key]), 1e-300), (k, key, sx[key], sy[key])
+            log_observed(f"channel {k} {key}", abs(sx[key] - sy[key]) / max(abs(sy[key]), 1e-300), 1e-12)
+            assert abs(sx[key] - sy[key]) <= 1e-12 * max(abs(sy[key]), 1e-300), (k, key, sx[key], sy[key])
         assert sx["error_flags"] == 0
 
 
