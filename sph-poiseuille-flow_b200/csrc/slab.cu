@@ -260,6 +260,22 @@ __device__ __forceinline__ void write_record(double *rec, double2 x, double2 v, 
     r[3] = make_double4((double)pid, 0.0, 0.0, 0.0);
 }
 
+// arrival of a rank's records at its two neighbours: every CTA's stores are fenced system-wide before its ticket; the
+// last CTA publishes the sequence number in both mailboxes (all threads of the CTA call this)
+__device__ __forceinline__ void p2p_arrive(P2PState *st, double *peer_left, double *peer_right, double seq)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&st->ticket, 1u) == gridDim.x - 1) {
+            __threadfence_system();
+            *reinterpret_cast<volatile double *>(peer_left + 2) = seq;
+            *reinterpret_cast<volatile double *>(peer_right + 2) = seq;
+            st->ticket = 0u;
+        }
+    }
+}
+
 // SEND: migrants and halo copies -> the two send buffers [migrants | copies], migrants marked dead in place;
 // !SEND (now and then, sphb_ctx_slab_compact): the rows that stay -> compacted alternate arrays.
 template <bool SEND>
@@ -346,20 +362,131 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_scatter(SlabArrays A, SlabG
     // step ever visits it; sphb_ctx_slab_compact squeezes the dead rows out now and then
     if (SEND && (m & ((1u << cMigL) | (1u << cMigR)))) A.pid[i] = -1;
     }
-    if (SEND && peer_left) {
-        // arrival: every CTA's stores are fenced system-wide before its ticket; the last CTA publishes the sequence
-        // number in both mailboxes
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (atomicAdd(&X.state->ticket, 1u) == gridDim.x - 1) {
-                __threadfence_system();
-                *reinterpret_cast<volatile double *>(peer_left + 2) = seq;
-                *reinterpret_cast<volatile double *>(peer_right + 2) = seq;
-                X.state->ticket = 0u;
-            }
+    if (SEND && peer_left) p2p_arrive(X.state, peer_left, peer_right, seq);
+}
+
+// ---- pack over the EDGE CANDIDATES only ---------------------------------------------------------------------------
+// A row moves far less than a cell column per step (dt <= 0.25 h / (c_f + max|v|), m:519-527, and a column is 2h), so
+// the only rows that can have anything to send -- migrants and the copies of the `halo` columns next to an edge -- are
+// the ones that sat within halo + 2 columns of an edge when the last list was built.  That build left every row in
+// (cell row, cell column) order (the entry array), so the candidates of one cell row and one side are ONE contiguous
+// entry range: a warp per (cell row, side) instead of a thread per owned row -- ~2 % of the rows, three small launches.
+constexpr int kEdgeBand = 2;     // columns beyond the halo band on the inner side (+1 outwards: the multiply of
+                                 // slab_class can class a row on a column boundary one column off the exact binning)
+constexpr int kEdgeWarps = 4;    // warps (tasks) per CTA
+struct EdgeView {
+    const int *ent_key;      // entry -> (row << 3 | kind) of the last build
+    const int *cell_start;   // exclusive scan of the cell counts, cell = cell row * ncx + local column
+    const GridDesc *g;       // ncy, n_entries of that build
+    int ncx, cell_cap;
+    int a[2], b[2];          // local columns [a, b) of the left / right candidate band
+};
+__device__ __forceinline__ bool edge_range(const EdgeView &E, int task, int &e0, int &e1)
+{
+    const int row = task >> 1, side = task & 1;
+    if (row >= E.g->ncy) return false;
+    const int i0 = row * E.ncx + E.a[side], i1 = row * E.ncx + E.b[side];
+    e0 = i0 < E.cell_cap ? E.cell_start[i0] : E.g->n_entries;
+    e1 = i1 < E.cell_cap ? E.cell_start[i1] : E.g->n_entries;
+    return e1 > e0;
+}
+// class bits (without cStay) of the candidate at entry e, 0 for entries that are not live owned rows
+__device__ __forceinline__ unsigned edge_class(const EdgeView &E, const SlabArrays &A, const SlabGeom &G, int e, int &row)
+{
+    const int key = E.ent_key[e];
+    row = key >> 3;
+    if ((key & 3) != 0 || row >= G.cur[1] || A.pid[row] < 0) return 0u;
+    return slab_class(A.pos[row].x, G) & ~(1u << cStay);
+}
+__global__ void __launch_bounds__(kEdgeWarps * 32) k_slab_edge_count(EdgeView E, SlabArrays A, SlabGeom G, int n_tasks,
+                                                                    int *__restrict__ task_tot)
+{
+    const int lane = threadIdx.x & 31, task = blockIdx.x * kEdgeWarps + (threadIdx.x >> 5);
+    if (task >= n_tasks) return;
+    int tot[cN] = {0, 0, 0, 0, 0};
+    int e0 = 0, e1 = 0;
+    if (edge_range(E, task, e0, e1)) {
+        for (int base = e0; base < e1; base += 32) {
+            int row;
+            const unsigned m = base + lane < e1 ? edge_class(E, A, G, base + lane, row) : 0u;
+#pragma unroll
+            for (int k = 1; k < cN; ++k) tot[k] += __popc(__ballot_sync(0xffffffffu, (m >> k) & 1u));
         }
     }
+    if (lane < cN) task_tot[lane * n_tasks + task] = tot[lane];
+}
+
+// ... and the scatter over the same candidates (task_off: the exclusive scan of the counts per class, k_slab_offsets)
+__global__ void __launch_bounds__(kEdgeWarps * 32) k_slab_edge_scatter(EdgeView E, SlabArrays A, SlabGeom G, int n_tasks,
+                                                                      const int *__restrict__ task_off,
+                                                                      const int *__restrict__ counts, double *send_left,
+                                                                      double *send_right, int rec_cap, int *flags, P2PSend X)
+{
+    double *peer_left = nullptr, *peer_right = nullptr;
+    double seq = 0.0;
+    if (X.state != nullptr) {
+        seq = (double)X.state->seq;
+        const int par = (int)(X.state->seq & 1LL);
+        peer_left = X.left_mail + X.L.from_right(par);
+        peer_right = X.right_mail + X.L.from_left(par);
+    }
+    const int lane = threadIdx.x & 31, task = blockIdx.x * kEdgeWarps + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int nl = counts[cMigL] + counts[cHaloL], nr = counts[cMigR] + counts[cHaloR];
+        send_left[0] = (double)counts[cMigL];
+        send_left[1] = (double)counts[cHaloL];
+        send_right[0] = (double)counts[cMigR];
+        send_right[1] = (double)counts[cHaloR];
+        if (peer_left) {
+            peer_left[0] = (double)counts[cMigL];
+            peer_left[1] = (double)counts[cHaloL];
+            peer_right[0] = (double)counts[cMigR];
+            peer_right[1] = (double)counts[cHaloR];
+        }
+        if (nl > rec_cap || nr > rec_cap) atomicOr(flags, kErrSlabCap);
+    }
+    int e0 = 0, e1 = 0;
+    if (task < n_tasks && edge_range(E, task, e0, e1)) {
+        int off[cN];
+#pragma unroll
+        for (int k = 1; k < cN; ++k) off[k] = task_off[k * n_tasks + task];
+        for (int base = e0; base < e1; base += 32) {
+            int i = 0;
+            const unsigned m = base + lane < e1 ? edge_class(E, A, G, base + lane, i) : 0u;
+            double2 x = make_double2(0.0, 0.0), v = x;
+            double rho = 0.0, drho = 0.0, mass = 0.0, Vol = 0.0;
+            Mat2 B{};
+            int pid = -1;
+            if (m) {
+                x = A.pos[i];
+                v = A.vel[i];
+                rho = A.rho[i];
+                drho = A.drho[i];
+                mass = A.mass[i];
+                Vol = A.Vol[i];
+                B = A.B[i];
+                pid = A.pid[i];
+            }
+#pragma unroll
+            for (int k = 1; k < cN; ++k) {
+                const unsigned b = __ballot_sync(0xffffffffu, (m >> k) & 1u);
+                if ((m >> k) & 1u) {
+                    const bool left = k == cMigL || k == cHaloL;
+                    const int first = (k == cHaloL) ? counts[cMigL] : (k == cHaloR ? counts[cMigR] : 0);
+                    const int slot = first + off[k] + __popc(b & ((1u << lane) - 1u));
+                    if (slot < rec_cap) {
+                        write_record((left ? send_left : send_right) + kHdr + (size_t)slot * kRec, x, v, rho, drho, mass, Vol, B, pid);
+                        if (peer_left)
+                            write_record((left ? peer_left : peer_right) + kHdr + (size_t)slot * kRec, x, v, rho, drho, mass, Vol, B, pid);
+                    }
+                }
+                off[k] += __popc(b);
+            }
+            // a row that migrates stays where it is, marked dead (k_slab_scatter)
+            if (m & ((1u << cMigL) | (1u << cMigR))) A.pid[i] = -1;
+        }
+    }
+    if (peer_left) p2p_arrive(X.state, peer_left, peer_right, seq);
 }
 
 // Compaction in CELL order (the slab form of the reference's periodic cell sort, m:529-568): the rows that
@@ -404,13 +531,29 @@ struct UnpackSrc {
 // new halo rows  = [copies from the left | copies from the right | own rows that left to the left | ... right]
 // The incoming rows are APPENDED to the owned region [0, base): stayers do not move (base = the high-water
 // mark of the owned rows, or the number of stayers right after a compaction).
+//
+// ONE launch for the whole receive side: the appended fluid rows (with their EOS pressure, m:172), the static wall
+// rows behind them, the y range of both for the list build that follows (GridFuse: the step's continuity pass has
+// reduced the rows it visited and zeroed the cell counters) -- and, by the last CTA to finish, what used to be the
+// commit kernel: with peer-to-peer mailboxes the scalars of every rank (max|v| -> the next time step), the new row
+// counts {nf, nfo, nt} every kernel of the next step reads, the grid of the coming build.
+struct WallStore {
+    int n_wall;
+    const double2 *w_pos;
+    const double *w_mass;
+    const double2 *w_wall_vel;
+    double rho0, p0;
+    double2 *wall_vel;   // per-row wall velocity and pressure of the context (not part of a record)
+    double *p;
+};
 __global__ void __launch_bounds__(kSlabBlock) k_slab_unpack(UnpackSrc U, SlabArrays A, SlabGeom G, int rec_cap,
                                                            int nf_cap, int base_is_stay_count, int *counts,
-                                                           int *flags, const P2PState *p2p, const double *mail, MailLayout ML)
+                                                           int *flags, P2PState *p2p, const double *mail, MailLayout ML,
+                                                           WallStore W, DevScalars *sc, GridFuse F)
 {
+    __shared__ int ok;
     if (p2p != nullptr) {
         // peer-to-peer: the received records are in this rank's own mailbox; wait for both neighbours' arrival slots
-        __shared__ int ok;
         const int par = (int)(p2p->seq & 1LL);
         U.buf[0] = mail + ML.from_left(par);
         U.buf[1] = mail + ML.from_right(par);
@@ -438,15 +581,12 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_unpack(UnpackSrc U, SlabArr
     for (int k = 0; k < 6; ++k) total += seg_n[k];
     const int n_owned = n_stay + nmL + nmR;
     const int n_fluid = n_stay + total;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        counts[8] = n_owned;
-        counts[9] = n_fluid - n_owned;
-        counts[10] = n_stay;   // first appended row
-        if (n_fluid > nf_cap) atomicOr(flags, kErrSlabCap);
-    }
+    const int nf = min(n_fluid, nf_cap);
+    const int stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    long long kmin = LLONG_MAX, kmax = LLONG_MIN;   // GridFuse: y range of the appended rows and the walls
     const double x_lo = (double)G.col_lo * G.cell, x_hi = (double)(G.col_lo + G.width) * G.cell;
     const double margin = (double)(G.halo + 2) * G.cell;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    for (int t = tid; t < total; t += stride) {
         int k = 0, off = t;
         while (off >= seg_n[k]) {
             off -= seg_n[k];
@@ -474,53 +614,58 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_unpack(UnpackSrc U, SlabArr
         B.b21 = c.z;
         B.b22 = c.w;
         A.B[d] = B;
-    }
-}
-// wall rows (static) after the fluid rows
-__global__ void __launch_bounds__(kSlabBlock) k_slab_walls(const int *__restrict__ counts, int nf_cap, int n_wall,
-                                                          const double2 *__restrict__ w_pos,
-                                                          const double *__restrict__ w_mass,
-                                                          const double2 *__restrict__ w_wall_vel, double rho0,
-                                                          double p0, int all_rows, SlabArrays A, double2 *wall_vel,
-                                                          double *p, GridFuse F)
-{
-    const int nf = min(counts[8] + counts[9], nf_cap);
-    const int first_new = all_rows ? 0 : counts[10];
-    long long kmin = LLONG_MAX, kmax = LLONG_MIN;   // GridFuse: y range of the appended rows and the walls
-    double2 *pos = A.pos, *vel = A.vel;
-    double *rho = A.rho, *drho = A.drho, *mass = A.mass, *Vol = A.Vol;
-    Mat2 *Bm = A.B;
-    for (int t = first_new + blockIdx.x * blockDim.x + threadIdx.x; t < nf + n_wall; t += gridDim.x * blockDim.x) {
-        if (t < nf) {   // EOS of the appended fluid rows (m:172); fluid rows carry no wall velocity
-            p[t] = p0 * (rho[t] / rho0 - 1.0);
-            wall_vel[t] = make_double2(0.0, 0.0);
-            if (F.g) {
-                const long long k = ordered_key(pos[t].y);
-                kmin = k < kmin ? k : kmin;
-                kmax = k > kmax ? k : kmax;
-            }
-            continue;
+        if (!base_is_stay_count) {   // (after a compaction the loop below visits every fluid row)
+            W.p[d] = W.p0 * (b.x / W.rho0 - 1.0);   // EOS of the appended fluid rows (m:172); fluid rows carry no wall velocity
+            W.wall_vel[d] = make_double2(0.0, 0.0);
         }
-        const int w = t - nf;
         if (F.g) {
-            const long long k = ordered_key(w_pos[w].y);
-            kmin = k < kmin ? k : kmin;
-            kmax = k > kmax ? k : kmax;
+            const long long key = ordered_key(a.y);
+            kmin = key < kmin ? key : kmin;
+            kmax = key > kmax ? key : kmax;
         }
-        pos[t] = w_pos[w];
-        vel[t] = make_double2(0.0, 0.0);
-        rho[t] = rho0;
-        drho[t] = 0.0;
-        mass[t] = w_mass[w];
-        Vol[t] = w_mass[w] / rho0;
+    }
+    if (base_is_stay_count) {
+        // a compaction moved the stayers: pressure and wall velocity are per-row arrays that it does not permute.  The
+        // appended rows are written by other threads of this launch, so their density comes from the record again.
+        for (int t = tid; t < nf; t += stride) {
+            double rho_t;
+            if (t < n_stay) {
+                rho_t = A.rho[t];
+            } else {
+                int k = 0, off = t - n_stay;
+                while (off >= seg_n[k]) {
+                    off -= seg_n[k];
+                    ++k;
+                }
+                rho_t = ldcg4(reinterpret_cast<const double4 *>(U.buf[seg_src[k]] + kHdr + (size_t)(seg_first[k] + off) * kRec) + 1).x;
+            }
+            W.p[t] = W.p0 * (rho_t / W.rho0 - 1.0);
+            W.wall_vel[t] = make_double2(0.0, 0.0);
+        }
+    }
+    // wall rows (static) after the fluid rows
+    for (int w = tid; w < W.n_wall; w += stride) {
+        const int t = nf + w;
+        const double2 xw = W.w_pos[w];
+        if (F.g) {
+            const long long key = ordered_key(xw.y);
+            kmin = key < kmin ? key : kmin;
+            kmax = key > kmax ? key : kmax;
+        }
+        A.pos[t] = xw;
+        A.vel[t] = make_double2(0.0, 0.0);
+        A.rho[t] = W.rho0;
+        A.drho[t] = 0.0;
+        A.mass[t] = W.w_mass[w];
+        A.Vol[t] = W.w_mass[w] / W.rho0;
         Mat2 B;
         B.b11 = 1.0;
         B.b12 = 0.0;
         B.b21 = 0.0;
         B.b22 = 1.0;
-        Bm[t] = B;
-        wall_vel[t] = w_wall_vel[w];
-        p[t] = 0.0;
+        A.B[t] = B;
+        W.wall_vel[t] = W.w_wall_vel[w];
+        W.p[t] = 0.0;
     }
     if (F.g) {
 #pragma unroll
@@ -535,20 +680,24 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_walls(const int *__restrict
             if (kmax != LLONG_MIN) atomicMax(&F.g->ymax_key, kmax);
         }
     }
-}
-
-// the new row counts become current: {nf, nfo, nt} read by every kernel of the next step
-// (64 threads).  With peer-to-peer mailboxes it also waits for every rank's scalars and imports max|v|; with GridFuse it
-// derives the grid of the list build that follows (the y range has been reduced by the continuity and wall kernels).
-__global__ void __launch_bounds__(64) k_slab_commit_counts(int *counts, int nf_cap, int n_wall, DevScalars *sc, P2PState *p2p,
-                                                          const double *mail, MailLayout ML, int *flags, GridFuse F)
-{
+    // ---- commit, by the last CTA to finish (counts[11] = the ticket) ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) ok = atomicAdd(reinterpret_cast<unsigned int *>(counts + 11), 1u) == gridDim.x - 1 ? 1 : 0;
+    __syncthreads();
+    if (!ok) return;
+    __threadfence();
     if (p2p != nullptr) p2p_scalars_cta(sc, p2p, mail, ML, flags);
     if (threadIdx.x != 0) return;
-    const int n_owned = min(counts[8], nf_cap), nf = min(counts[8] + counts[9], nf_cap);
+    counts[8] = n_owned;
+    counts[9] = n_fluid - n_owned;
+    counts[10] = n_stay;   // first appended row
+    if (n_fluid > nf_cap) atomicOr(flags, kErrSlabCap);
+    // the new row counts become current: {nf, nfo, nt} read by every kernel of the next step
     counts[12] = nf;
-    counts[13] = n_owned;
-    counts[14] = nf + n_wall;
+    counts[13] = min(n_owned, nf_cap);
+    counts[14] = nf + W.n_wall;
+    counts[11] = 0;
     if (F.g != nullptr) grid_derive(F.g, F.cell, F.ncx, F.cell_cap, F.flags, F.totals);
 }
 __global__ void k_slab_set_counts(int *counts, int nf, int nfo, int nt)
@@ -625,6 +774,28 @@ SlabArrays arrays_of(sphb_ctx *c)
     return A;
 }
 
+// The candidate bands of the edge pack (k_slab_edge_*) in the local columns of the last list build, or false when the
+// full pack has to run: no list for the current rows, or a slab too narrow for two separate bands.
+bool edge_view_of(const sphb_ctx *c, EdgeView &E, int &n_tasks)
+{
+    const SlabState &s = c->slab;
+    const NeighborWork &w = c->nw;
+    const int width = s.col_hi - s.col_lo, band = s.halo + kEdgeBand;
+    if (!c->have_list || !w.slab || w.ncx_local < 1 || w.cell_cap < 1 || width < 2 * band + 2) return false;
+    const int first = s.col_lo - w.col0;   // local column of the first owned column
+    E.ent_key = w.ent_key.as<int>();
+    E.cell_start = w.cell_start.as<int>();
+    E.g = w.grid.as<GridDesc>();
+    E.ncx = w.ncx_local;
+    E.cell_cap = w.cell_cap;
+    E.a[0] = std::max(first - 1, 0);
+    E.b[0] = std::min(first + band, w.ncx_local);
+    E.a[1] = std::max(first + width - band, 0);
+    E.b[1] = std::min(first + width + 1, w.ncx_local);
+    n_tasks = 2 * (w.cell_cap / w.ncx_local);
+    return n_tasks > 0 && (size_t)cN * (size_t)n_tasks * sizeof(int) <= s.block_tot.bytes;
+}
+
 // Host-side values used for launch sizes and by-value kernel parameters.  In steady state they stay at the
 // CAPACITY (the rows of a slab change every step and the host never waits for the new counts: the kernels
 // read {nf, nfo, nt} from device memory, PhysParams::dev_counts).
@@ -695,6 +866,7 @@ SPHB_API int sphb_ctx_slab_init(sphb_ctx *c, int col_lo, int col_hi, int halo_co
     SPHB_TRY(s.w_mass.reserve((nw + 1) * sizeof(double)));
     SPHB_TRY(s.w_wall_vel.reserve((nw + 1) * sizeof(double2)));
     SPHB_TRY(s.counts.reserve(16 * sizeof(int)));
+    SPHB_CUDA(cudaMemsetAsync(s.counts.p, 0, 16 * sizeof(int), c->st));   // ([11]: the ticket of the unpack's last CTA)
     SPHB_TRY(s.block_tot.reserve((size_t)cN * (grid_for((size_t)nf_cap, kSlabBlock) + 1) * sizeof(int)));
     if (!s.h_counts) SPHB_CUDA(cudaMallocHost((void **)&s.h_counts, 16 * sizeof(int)));
     SPHB_TRY(s.pid.reserve(((size_t)nf_cap + 1) * sizeof(int)));
@@ -758,6 +930,9 @@ SPHB_API int sphb_ctx_slab_init(sphb_ctx *c, int col_lo, int col_hi, int halo_co
         apply_counts(c, nf_cap, 0);
         SPHB_TRY(ctx_plan_lists(c, y_lo, y_hi));
     }
+    // (the per-task totals of the edge pack: two tasks per cell row of the planned grid)
+    SPHB_TRY(s.block_tot.reserve((size_t)cN * std::max((size_t)grid_for((size_t)nf_cap, kSlabBlock) + 1,
+                                                        2 * (size_t)(c->nw.cell_cap / std::max(1, c->nw.ncx_local)) + 2) * sizeof(int)));
     // from here on: launch sizes = capacity, actual counts on the device
     apply_counts(c, nf_cap, 0);
     c->P.nfo = nf_cap;
@@ -777,10 +952,20 @@ SPHB_API int sphb_ctx_slab_pack(sphb_ctx *c, double *send_left_dev, double *send
     const unsigned blocks = std::max(1u, grid_for((size_t)s.nf_cap, kSlabBlock));
     int *bt = s.block_tot.as<int>(), *cnt = s.counts.as<int>();
     ProfScope ps(&c->kprof, kPfSlab, c->st);
-    k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), s.pid.as<int>(), G, bt);
-    k_slab_offsets<<<cN, 1024, 0, c->st>>>(bt, (int)blocks, cnt, nullptr, nullptr, PeerList{}, MailLayout{}, 0);
-    k_slab_scatter<true><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, bt, cnt, send_left_dev, send_right_dev,
-                                                           rec_cap, c->nw.flags.as<int>(), P2PSend{});
+    EdgeView E;
+    int n_tasks = 0;
+    if (edge_view_of(c, E, n_tasks)) {   // steady state: only the rows near the edges (see k_slab_edge_count)
+        const unsigned eb = (unsigned)((n_tasks + kEdgeWarps - 1) / kEdgeWarps);
+        k_slab_edge_count<<<eb, kEdgeWarps * 32, 0, c->st>>>(E, arrays_of(c), G, n_tasks, bt);
+        k_slab_offsets<<<cN, 1024, 0, c->st>>>(bt, n_tasks, cnt, nullptr, nullptr, PeerList{}, MailLayout{}, 0);
+        k_slab_edge_scatter<<<eb, kEdgeWarps * 32, 0, c->st>>>(E, arrays_of(c), G, n_tasks, bt, cnt, send_left_dev,
+                                                              send_right_dev, rec_cap, c->nw.flags.as<int>(), P2PSend{});
+    } else {
+        k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), s.pid.as<int>(), G, bt);
+        k_slab_offsets<<<cN, 1024, 0, c->st>>>(bt, (int)blocks, cnt, nullptr, nullptr, PeerList{}, MailLayout{}, 0);
+        k_slab_scatter<true><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, bt, cnt, send_left_dev, send_right_dev,
+                                                               rec_cap, c->nw.flags.as<int>(), P2PSend{});
+    }
     c->launches += 3;
     SPHB_CUDA(cudaGetLastError());
     return 0;
@@ -803,8 +988,9 @@ SPHB_API int sphb_ctx_slab_compact(sphb_ctx *c)
         const SlabArrays A = arrays_of(c);
         k_slab_sort_flags<<<grid_for((size_t)ent_cap, kSlabBlock), kSlabBlock, 0, c->st>>>(
             c->nw.ent_key.as<int>(), c->nw.grid.as<GridDesc>(), ent_cap, A, G, s.sort_flag.as<int>());
-        SPHB_TRY(exclusive_scan_i32(s.sort_flag.as<int>(), s.sort_ptr.as<int>(), (size_t)ent_cap, c->nw.scan_tmp, nullptr,
-                                    c->st, &c->launches));
+        // (the total = the rows that stay: what the next unpack appends after -- the edge pack does not count them)
+        SPHB_TRY(exclusive_scan_i32(s.sort_flag.as<int>(), s.sort_ptr.as<int>(), (size_t)ent_cap, c->nw.scan_tmp,
+                                    s.counts.as<int>() + cStay, c->st, &c->launches));
         k_slab_sort_move<<<grid_for((size_t)ent_cap, kSlabBlock), kSlabBlock, 0, c->st>>>(
             c->nw.ent_key.as<int>(), s.sort_flag.as<int>(), s.sort_ptr.as<int>(), ent_cap, A);
     } else {
@@ -847,21 +1033,25 @@ SPHB_API int sphb_ctx_slab_unpack(sphb_ctx *c, const double *recv_left_dev, cons
         ML.world = s.p2p_world;
         ML.rec_cap = s.p2p_rec_cap;
         const bool p2p = recv_left_dev == nullptr && recv_right_dev == nullptr;   // sphb_ctx_slab_p2p_recv
-        k_slab_unpack<<<148 * 2, kSlabBlock, 0, c->st>>>(U, A, G, rec_cap, s.nf_cap, s.squeezed ? 1 : 0, cnt,
-                                                         c->nw.flags.as<int>(), p2p ? s.p2p_state.as<P2PState>() : nullptr,
-                                                         s.mail, ML);
         // the grid set-up of the list build that follows: started by the step's continuity pass (y range of the rows it
-        // visited, zeroed cell counters), continued here with the appended rows and the walls, derived by the commit
+        // visited, zeroed cell counters), continued by this launch with the appended rows and the walls, derived by
+        // its last CTA
         const GridFuse F = c->nw.grid_ready ? neighbor_grid_fuse(c->nw) : GridFuse();
+        WallStore W;
+        W.n_wall = s.n_wall;
+        W.w_pos = s.w_pos.as<double2>();
+        W.w_mass = s.w_mass.as<double>();
+        W.w_wall_vel = s.w_wall_vel.as<double2>();
+        W.rho0 = c->prm.rho0;
+        W.p0 = c->prm.p0;
+        W.wall_vel = c->wall_vel.as<double2>();
+        W.p = c->p.as<double>();
         // appended rows start at the (possibly squeezed) end of the owned region; the walls follow the halo
-        k_slab_walls<<<148 * 2, kSlabBlock, 0, c->st>>>(cnt, s.nf_cap, s.n_wall, s.w_pos.as<double2>(),
-                                                        s.w_mass.as<double>(), s.w_wall_vel.as<double2>(), c->prm.rho0,
-                                                        c->prm.p0, s.squeezed ? 1 : 0, A, c->wall_vel.as<double2>(),
-                                                        c->p.as<double>(), F);
-        k_slab_commit_counts<<<1, 64, 0, c->st>>>(cnt, s.nf_cap, s.n_wall, c->sc(), p2p ? s.p2p_state.as<P2PState>() : nullptr,
-                                                  s.mail, ML, c->nw.flags.as<int>(), F);
+        k_slab_unpack<<<148, kSlabBlock, 0, c->st>>>(U, A, G, rec_cap, s.nf_cap, s.squeezed ? 1 : 0, cnt,
+                                                     c->nw.flags.as<int>(), p2p ? s.p2p_state.as<P2PState>() : nullptr,
+                                                     s.mail, ML, W, c->sc(), F);
     }
-    c->launches += 3;
+    c->launches += 1;
     SPHB_CUDA(cudaGetLastError());
     s.squeezed = false;
     c->have_list = false;
@@ -967,11 +1157,21 @@ SPHB_API int sphb_ctx_slab_p2p_send(sphb_ctx *c, double *send_left_dev, double *
     const unsigned blocks = std::max(1u, grid_for((size_t)s.nf_cap, kSlabBlock));
     int *bt = s.block_tot.as<int>(), *cnt = s.counts.as<int>();
     ProfScope ps(&c->kprof, kPfSlab, c->st);
-    k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), s.pid.as<int>(), G, bt);
-    // (one more CTA than classes: it bumps the sequence number and sends the scalars to every rank meanwhile)
-    k_slab_offsets<<<cN + 1, 1024, 0, c->st>>>(bt, (int)blocks, cnt, c->sc(), X.state, PL, L, s.p2p_rank);
-    k_slab_scatter<true><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, bt, cnt, send_left_dev, send_right_dev,
-                                                           s.p2p_rec_cap, c->nw.flags.as<int>(), X);
+    // (k_slab_offsets has one more CTA than classes: it bumps the sequence number and sends the scalars to every rank)
+    EdgeView E;
+    int n_tasks = 0;
+    if (edge_view_of(c, E, n_tasks)) {   // steady state: only the rows near the edges (see k_slab_edge_count)
+        const unsigned eb = (unsigned)((n_tasks + kEdgeWarps - 1) / kEdgeWarps);
+        k_slab_edge_count<<<eb, kEdgeWarps * 32, 0, c->st>>>(E, arrays_of(c), G, n_tasks, bt);
+        k_slab_offsets<<<cN + 1, 1024, 0, c->st>>>(bt, n_tasks, cnt, c->sc(), X.state, PL, L, s.p2p_rank);
+        k_slab_edge_scatter<<<eb, kEdgeWarps * 32, 0, c->st>>>(E, arrays_of(c), G, n_tasks, bt, cnt, send_left_dev,
+                                                              send_right_dev, s.p2p_rec_cap, c->nw.flags.as<int>(), X);
+    } else {
+        k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), s.pid.as<int>(), G, bt);
+        k_slab_offsets<<<cN + 1, 1024, 0, c->st>>>(bt, (int)blocks, cnt, c->sc(), X.state, PL, L, s.p2p_rank);
+        k_slab_scatter<true><<<blocks, kSlabBlock, 0, c->st>>>(arrays_of(c), G, bt, cnt, send_left_dev, send_right_dev,
+                                                               s.p2p_rec_cap, c->nw.flags.as<int>(), X);
+    }
     c->launches += 3;
     SPHB_CUDA(cudaGetLastError());
     return 0;
