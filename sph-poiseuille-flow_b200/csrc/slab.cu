@@ -489,6 +489,157 @@ __global__ void __launch_bounds__(kEdgeWarps * 32) k_slab_edge_scatter(EdgeView 
     if (peer_left) p2p_arrive(X.state, peer_left, peer_right, seq);
 }
 
+// The three launches above as ONE (steady state, at most one CTA per SM so that all of them are resident): count | grid
+// barrier | every warp sums the totals of the tasks before its own | scatter.  With peer-to-peer mailboxes one more CTA
+// opens the exchange before the barrier (sequence number, scalars to every rank) and the last CTA to finish publishes
+// the arrival in both neighbours' mailboxes.  counts[15]: barrier arrivals, counts[7]: finish ticket (both reset by the
+// last CTA).
+__global__ void __launch_bounds__(kEdgeWarps * 32) k_slab_edge_send(EdgeView E, SlabArrays A, SlabGeom G, int n_tasks,
+                                                                   int *task_tot, int *counts, double *send_left,
+                                                                   double *send_right, int rec_cap, int *flags, P2PSend X,
+                                                                   const DevScalars *sc, PeerList peers, int me)
+{
+    const int lane = threadIdx.x & 31, task = blockIdx.x * kEdgeWarps + (threadIdx.x >> 5);
+    const bool open_cta = X.state != nullptr && blockIdx.x == gridDim.x - 1;
+    int e0 = 0, e1 = 0;
+    bool have = false;
+    if (open_cta) {
+        p2p_open_cta(sc, X.state, peers, X.L, me);
+    } else if (task < n_tasks) {
+        // ---- count
+        int tot[cN] = {0, 0, 0, 0, 0};
+        have = edge_range(E, task, e0, e1);
+        if (have) {
+            for (int base = e0; base < e1; base += 32) {
+                int row;
+                const unsigned m = base + lane < e1 ? edge_class(E, A, G, base + lane, row) : 0u;
+#pragma unroll
+                for (int k = 1; k < cN; ++k) tot[k] += __popc(__ballot_sync(0xffffffffu, (m >> k) & 1u));
+            }
+        }
+        if (lane < cN) task_tot[lane * n_tasks + task] = tot[lane];
+    }
+    // ---- grid barrier (every CTA is resident: the host launches at most one per SM)
+    __shared__ int s_ok;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile int *arrive = counts + 15;
+        atomicAdd(counts + 15, 1);
+        const long long t0 = clock64();
+        s_ok = 1;
+        while (*arrive < (int)gridDim.x) {
+            if (clock64() - t0 > kSpinCycles) {
+                s_ok = 0;
+                break;
+            }
+            __nanosleep(32);
+        }
+        if (!s_ok) atomicOr(flags, kErrSlabCap);
+        __threadfence();
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    // ---- offsets: the totals of the tasks before this one, per class, and the class totals
+    double *peer_left = nullptr, *peer_right = nullptr;
+    double seq = 0.0;
+    if (X.state != nullptr) {
+        const long long sq = *reinterpret_cast<volatile long long *>(&X.state->seq);
+        seq = (double)sq;
+        const int par = (int)(sq & 1LL);
+        peer_left = X.left_mail + X.L.from_right(par);
+        peer_right = X.right_mail + X.L.from_left(par);
+    }
+    if (!open_cta && task < n_tasks) {
+        int off[cN] = {0, 0, 0, 0, 0}, all[cN] = {0, 0, 0, 0, 0};
+#pragma unroll
+        for (int k = 1; k < cN; ++k) {
+            int before = 0, total = 0;
+            for (int t = lane; t < n_tasks; t += 32) {
+                const int v = __ldcg(task_tot + k * n_tasks + t);
+                total += v;
+                before += t < task ? v : 0;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                before += __shfl_xor_sync(0xffffffffu, before, d);
+                total += __shfl_xor_sync(0xffffffffu, total, d);
+            }
+            off[k] = before;
+            all[k] = total;
+        }
+        if (task == 0 && lane == 0) {
+            const int nl = all[cMigL] + all[cHaloL], nr = all[cMigR] + all[cHaloR];
+            counts[cStay] = 0;
+#pragma unroll
+            for (int k = 1; k < cN; ++k) counts[k] = all[k];
+            send_left[0] = (double)all[cMigL];
+            send_left[1] = (double)all[cHaloL];
+            send_right[0] = (double)all[cMigR];
+            send_right[1] = (double)all[cHaloR];
+            if (peer_left) {
+                peer_left[0] = (double)all[cMigL];
+                peer_left[1] = (double)all[cHaloL];
+                peer_right[0] = (double)all[cMigR];
+                peer_right[1] = (double)all[cHaloR];
+            }
+            if (nl > rec_cap || nr > rec_cap) atomicOr(flags, kErrSlabCap);
+        }
+        // ---- scatter
+        if (have) {
+            for (int base = e0; base < e1; base += 32) {
+                int i = 0;
+                const unsigned m = base + lane < e1 ? edge_class(E, A, G, base + lane, i) : 0u;
+                double2 x = make_double2(0.0, 0.0), v = x;
+                double rho = 0.0, drho = 0.0, mass = 0.0, Vol = 0.0;
+                Mat2 B{};
+                int pid = -1;
+                if (m) {
+                    x = A.pos[i];
+                    v = A.vel[i];
+                    rho = A.rho[i];
+                    drho = A.drho[i];
+                    mass = A.mass[i];
+                    Vol = A.Vol[i];
+                    B = A.B[i];
+                    pid = A.pid[i];
+                }
+#pragma unroll
+                for (int k = 1; k < cN; ++k) {
+                    const unsigned b = __ballot_sync(0xffffffffu, (m >> k) & 1u);
+                    if ((m >> k) & 1u) {
+                        const bool left = k == cMigL || k == cHaloL;
+                        const int first = (k == cHaloL) ? all[cMigL] : (k == cHaloR ? all[cMigR] : 0);
+                        const int slot = first + off[k] + __popc(b & ((1u << lane) - 1u));
+                        if (slot < rec_cap) {
+                            write_record((left ? send_left : send_right) + kHdr + (size_t)slot * kRec, x, v, rho, drho, mass, Vol, B, pid);
+                            if (peer_left)
+                                write_record((left ? peer_left : peer_right) + kHdr + (size_t)slot * kRec, x, v, rho, drho, mass, Vol, B, pid);
+                        }
+                    }
+                    off[k] += __popc(b);
+                }
+                if (m & ((1u << cMigL) | (1u << cMigR))) A.pid[i] = -1;   // migrants stay in place, marked dead
+            }
+        }
+    }
+    // ---- finish: the last CTA publishes the arrival and re-arms the two counters
+    if (peer_left) __threadfence_system();
+    else __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(counts + 7, 1) == (int)gridDim.x - 1) {
+            if (peer_left) {
+                __threadfence_system();
+                *reinterpret_cast<volatile double *>(peer_left + 2) = seq;
+                *reinterpret_cast<volatile double *>(peer_right + 2) = seq;
+            }
+            counts[7] = 0;
+            counts[15] = 0;
+        }
+    }
+}
+
 // Compaction in CELL order (the slab form of the reference's periodic cell sort, m:529-568): the rows that
 // stay are visited through the cell-sorted entry array of the last list build, so the compacted rows come
 // out sorted by (cell row, cell column) and the staging loads of the gather kernels stay coalesced.
@@ -774,6 +925,20 @@ SlabArrays arrays_of(sphb_ctx *c)
     return A;
 }
 
+// CTAs of k_slab_edge_send that are certainly resident together (its grid barrier needs that): one per SM
+unsigned edge_resident_ctas()
+{
+#ifdef SPHB_CPUSIM
+    return 0u;   // (the functional simulator of tests/cpusim runs the CTAs of a launch one after the other: three launches)
+#endif
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0u;
+    }
+    return sms > 0 ? (unsigned)sms : 0u;
+}
+
 // The candidate bands of the edge pack (k_slab_edge_*) in the local columns of the last list build, or false when the
 // full pack has to run: no list for the current rows, or a slab too narrow for two separate bands.
 bool edge_view_of(const sphb_ctx *c, EdgeView &E, int &n_tasks)
@@ -956,10 +1121,17 @@ SPHB_API int sphb_ctx_slab_pack(sphb_ctx *c, double *send_left_dev, double *send
     int n_tasks = 0;
     if (edge_view_of(c, E, n_tasks)) {   // steady state: only the rows near the edges (see k_slab_edge_count)
         const unsigned eb = (unsigned)((n_tasks + kEdgeWarps - 1) / kEdgeWarps);
-        k_slab_edge_count<<<eb, kEdgeWarps * 32, 0, c->st>>>(E, arrays_of(c), G, n_tasks, bt);
-        k_slab_offsets<<<cN, 1024, 0, c->st>>>(bt, n_tasks, cnt, nullptr, nullptr, PeerList{}, MailLayout{}, 0);
-        k_slab_edge_scatter<<<eb, kEdgeWarps * 32, 0, c->st>>>(E, arrays_of(c), G, n_tasks, bt, cnt, send_left_dev,
-                                                              send_right_dev, rec_cap, c->nw.flags.as<int>(), P2PSend{});
+        if (eb + 1 <= edge_resident_ctas()) {   // one launch (k_slab_edge_send)
+            k_slab_edge_send<<<eb, kEdgeWarps * 32, 0, c->st>>>(E, arrays_of(c), G, n_tasks, bt, cnt, send_left_dev,
+                                                               send_right_dev, rec_cap, c->nw.flags.as<int>(), P2PSend{},
+                                                               c->sc(), PeerList{}, 0);
+            c->launches -= 2;
+        } else {
+            k_slab_edge_count<<<eb, kEdgeWarps * 32, 0, c->st>>>(E, arrays_of(c), G, n_tasks, bt);
+            k_slab_offsets<<<cN, 1024, 0, c->st>>>(bt, n_tasks, cnt, nullptr, nullptr, PeerList{}, MailLayout{}, 0);
+            k_slab_edge_scatter<<<eb, kEdgeWarps * 32, 0, c->st>>>(E, arrays_of(c), G, n_tasks, bt, cnt, send_left_dev,
+                                                                  send_right_dev, rec_cap, c->nw.flags.as<int>(), P2PSend{});
+        }
     } else {
         k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), s.pid.as<int>(), G, bt);
         k_slab_offsets<<<cN, 1024, 0, c->st>>>(bt, (int)blocks, cnt, nullptr, nullptr, PeerList{}, MailLayout{}, 0);
@@ -1162,10 +1334,17 @@ SPHB_API int sphb_ctx_slab_p2p_send(sphb_ctx *c, double *send_left_dev, double *
     int n_tasks = 0;
     if (edge_view_of(c, E, n_tasks)) {   // steady state: only the rows near the edges (see k_slab_edge_count)
         const unsigned eb = (unsigned)((n_tasks + kEdgeWarps - 1) / kEdgeWarps);
-        k_slab_edge_count<<<eb, kEdgeWarps * 32, 0, c->st>>>(E, arrays_of(c), G, n_tasks, bt);
-        k_slab_offsets<<<cN + 1, 1024, 0, c->st>>>(bt, n_tasks, cnt, c->sc(), X.state, PL, L, s.p2p_rank);
-        k_slab_edge_scatter<<<eb, kEdgeWarps * 32, 0, c->st>>>(E, arrays_of(c), G, n_tasks, bt, cnt, send_left_dev,
-                                                              send_right_dev, s.p2p_rec_cap, c->nw.flags.as<int>(), X);
+        if (eb + 1 <= edge_resident_ctas()) {   // one launch (k_slab_edge_send; its last CTA opens the exchange)
+            k_slab_edge_send<<<eb + 1, kEdgeWarps * 32, 0, c->st>>>(E, arrays_of(c), G, n_tasks, bt, cnt, send_left_dev,
+                                                                   send_right_dev, s.p2p_rec_cap, c->nw.flags.as<int>(), X,
+                                                                   c->sc(), PL, s.p2p_rank);
+            c->launches -= 2;
+        } else {
+            k_slab_edge_count<<<eb, kEdgeWarps * 32, 0, c->st>>>(E, arrays_of(c), G, n_tasks, bt);
+            k_slab_offsets<<<cN + 1, 1024, 0, c->st>>>(bt, n_tasks, cnt, c->sc(), X.state, PL, L, s.p2p_rank);
+            k_slab_edge_scatter<<<eb, kEdgeWarps * 32, 0, c->st>>>(E, arrays_of(c), G, n_tasks, bt, cnt, send_left_dev,
+                                                                  send_right_dev, s.p2p_rec_cap, c->nw.flags.as<int>(), X);
+        }
     } else {
         k_slab_count<<<blocks, kSlabBlock, 0, c->st>>>(c->pos.as<double2>(), s.pid.as<int>(), G, bt);
         k_slab_offsets<<<cN + 1, 1024, 0, c->st>>>(bt, (int)blocks, cnt, c->sc(), X.state, PL, L, s.p2p_rank);
