@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(kEdgeWarps * 32) k_slab_edge_send(EdgeView E, 
     int e0 = 0, e1 = 0;
     bool have = false;
     if (open_cta) {
-        p2p_open_cta(sc, X.state, peers, X.L, me);
+        if (threadIdx.x == 0) X.state->seq += 1;   // (the scalars travel after the barrier, beside the scatter)
     } else if (task < n_tasks) {
         // ---- count
         int tot[cN] = {0, 0, 0, 0, 0};
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(kEdgeWarps * 32) k_slab_edge_send(EdgeView E, 
                 for (int k = 1; k < cN; ++k) tot[k] += __popc(__ballot_sync(0xffffffffu, (m >> k) & 1u));
             }
         }
-        if (lane < cN) task_tot[lane * n_tasks + task] = tot[lane];
+        if (lane == 0) reinterpret_cast<int4 *>(task_tot)[task] = make_int4(tot[1], tot[2], tot[3], tot[4]);
     }
     // ---- grid barrier (every CTA is resident: the host launches at most one per SM)
     __shared__ int s_ok;
@@ -550,23 +550,57 @@ __global__ void __launch_bounds__(kEdgeWarps * 32) k_slab_edge_send(EdgeView E, 
         peer_left = X.left_mail + X.L.from_right(par);
         peer_right = X.right_mail + X.L.from_left(par);
     }
+    if (open_cta) {
+        // this rank's scalars (max|v|, wall-shear partials) into the mailbox of EVERY rank (thread r -> rank r), the
+        // sequence number last (p2p_open_cta without the bump)
+        const int r = (int)threadIdx.x;
+        if (r < X.L.world) {
+            double *slot = peers.mail[r] + X.L.scal((int)((long long)seq & 1LL), me);
+            slot[0] = sc->vmax;
+            slot[1] = sc->tau_bottom;
+            slot[2] = sc->tau_top;
+            __threadfence_system();
+            *reinterpret_cast<volatile double *>(slot + 3) = seq;
+        }
+    }
     if (!open_cta && task < n_tasks) {
+        // (one 16-byte record of four class totals per task: independent loads, then one warp reduction)
         int off[cN] = {0, 0, 0, 0, 0}, all[cN] = {0, 0, 0, 0, 0};
-#pragma unroll
-        for (int k = 1; k < cN; ++k) {
-            int before = 0, total = 0;
+        {
+            int4 before = make_int4(0, 0, 0, 0), total = before;
+#pragma unroll 4
             for (int t = lane; t < n_tasks; t += 32) {
-                const int v = __ldcg(task_tot + k * n_tasks + t);
-                total += v;
-                before += t < task ? v : 0;
+                const int4 v = __ldcg(reinterpret_cast<const int4 *>(task_tot) + t);
+                total.x += v.x;
+                total.y += v.y;
+                total.z += v.z;
+                total.w += v.w;
+                if (t < task) {
+                    before.x += v.x;
+                    before.y += v.y;
+                    before.z += v.z;
+                    before.w += v.w;
+                }
             }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) {
-                before += __shfl_xor_sync(0xffffffffu, before, d);
-                total += __shfl_xor_sync(0xffffffffu, total, d);
+                before.x += __shfl_xor_sync(0xffffffffu, before.x, d);
+                before.y += __shfl_xor_sync(0xffffffffu, before.y, d);
+                before.z += __shfl_xor_sync(0xffffffffu, before.z, d);
+                before.w += __shfl_xor_sync(0xffffffffu, before.w, d);
+                total.x += __shfl_xor_sync(0xffffffffu, total.x, d);
+                total.y += __shfl_xor_sync(0xffffffffu, total.y, d);
+                total.z += __shfl_xor_sync(0xffffffffu, total.z, d);
+                total.w += __shfl_xor_sync(0xffffffffu, total.w, d);
             }
-            off[k] = before;
-            all[k] = total;
+            off[1] = before.x;
+            off[2] = before.y;
+            off[3] = before.z;
+            off[4] = before.w;
+            all[1] = total.x;
+            all[2] = total.y;
+            all[3] = total.z;
+            all[4] = total.w;
         }
         if (task == 0 && lane == 0) {
             const int nl = all[cMigL] + all[cHaloL], nr = all[cMigR] + all[cHaloR];
