@@ -436,7 +436,7 @@ def b200_arm(args):
                 "alg_bytes_per_particle": ALG_BYTES_KERNEL[top], "ms_per_launch": kernels[top]["ms_per_call"],
                 "share_of_step": kernels[top]["share"],
                 "step_frac": (value / world) * ALG_BYTES_SUBSTEP / (hbm * 1e9),
-                "fp64_note": "fp64 gather over ~41 neighbours per particle: the FP64 pipe and the shared-memory "
+                "fp64_note": "fp64 gather over ~20 neighbours per particle: the FP64 pipe and the shared-memory "
                              "data pipe bound these kernels, not HBM (profiles/README.md)"}
         # the kernels of the acoustic substep alone (forces + continuity), list rebuild and KGC excluded
         # FP64 roofline of the same kernel: FP64-pipe thread instructions per launch (counted once per profile by
