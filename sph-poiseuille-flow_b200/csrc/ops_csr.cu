@@ -18,6 +18,7 @@
 // kernel's epilogue finishes density/EOS (ph:1440-1446), wraps x (m:570-577) and feeds the grid-wide
 // max|v| reduction (warp shuffle + one atomicMax per warp) that the next dt is computed from on the
 // device (m:519-527).
+#include <cstdlib>
 #include "ops_csr.cuh"
 #include "async_copy.cuh"
 #include "physmath.cuh"
@@ -1103,6 +1104,10 @@ struct ContinuityK {
             }
             const double2 pi = s_xy[si];
             const double2 vi = s_v[si];
+            // the row's own global-memory operands are requested before the row loop, which hides their latency
+            // (they were the long-scoreboard stalls of this kernel: 3.2 per issue in the r2_v2 capture)
+            const double rho_h = S.rp_half[i].x;
+            double2 x = S.pos[i];
             double rate = 0.0;
             SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
                 const Geo g = pair_geometry(pi, s_xy[sl], m, P);
@@ -1119,7 +1124,6 @@ struct ContinuityK {
                 }
                 rate += (ux * g.ex + uy * g.ey) * gj;
             }));
-            const double rho_h = S.rp_half[i].x;
             const double drho = rate * rho_h;          // ph:1112
             double rho = rho_h + drho * (0.5 * dt);    // ph:1441
             if (rho < 1e-10) rho = P.rho0;
@@ -1127,13 +1131,10 @@ struct ContinuityK {
             S.rho[i] = rho;
             S.p[i] = P.p0 * (rho / P.rho0 - 1.0);
             if (do_wrap) {
-                double2 x = S.pos[i];
                 x.x = wrap_x(x.x, P.DL);
                 S.pos[i] = x;
-                if (track_y) see_y(x.y);
-            } else if (track_y) {
-                see_y(S.pos[i].y);
             }
+            if (track_y) see_y(x.y);
             S.vel[i] = vi;   // nobody reads `vel` in this kernel (neighbours read the staged new velocity): commit in place
             if (i < P.nfo) speed = fmax(speed, sqrt(vi.x * vi.x + vi.y * vi.y));
             // a blown-up row (NaN / Inf in density or velocity; fmax above drops a NaN silently): raised once, rare
@@ -1609,7 +1610,23 @@ int csr_batch_configure(int tile_cap)
 }
 static inline dim3 batch_grid(const BatchLaunch &L, unsigned gx) { return dim3(gx, (unsigned)L.n_chan, 1u); }
 // pipelined kernels: a few tiles per CTA, so that the copies of one tile overlap the rows of the one before
-static inline dim3 batch_tile_grid(const BatchLaunch &L) { return dim3((L.n_tiles + 2u) / 3u, (unsigned)L.n_chan, 1u); }
+static unsigned batch_tiles_per_cta()
+{
+    static unsigned n = 0;
+    if (n == 0) {
+        n = 3;
+        if (const char *env = std::getenv("SPHB_BATCH_TILES_PER_CTA")) {   // tuning runs only
+            const int v = std::atoi(env);
+            if (v >= 1 && v <= 64) n = (unsigned)v;
+        }
+    }
+    return n;
+}
+static inline dim3 batch_tile_grid(const BatchLaunch &L)
+{
+    const unsigned per = batch_tiles_per_cta();
+    return dim3((L.n_tiles + per - 1u) / per, (unsigned)L.n_chan, 1u);
+}
 
 int csr_batch_density(const BatchLaunch &L)
 {

@@ -255,9 +255,13 @@ static double l2_error(const cfg_t *c, engine_t *eng, int n_bins, double *u_mean
 }
 
 /* restart: magic, signature, n_total, t, step, then pos vel rho p drho_dt force force_prior (m:434-445) */
-static const char RESTART_MAGIC[8] = {'S', 'P', 'H', 'B', 'R', 'S', 'T', '1'};
+/* format 2: an endianness / version word and n_fluid behind the signature (a file of another byte order, version or
+ * fluid / wall split is refused instead of misread).  Not the reference's MAT v7.3 restart: the two codes cannot
+ * resume each other's runs. */
+static const char RESTART_MAGIC[8] = {'S', 'P', 'H', 'B', 'R', 'S', 'T', '2'};
+static const unsigned RESTART_VERSION = 0x01020304u;   /* reads back as 0x04030201 on the other byte order */
 
-static int save_restart(const char *path, const cfg_t *c, engine_t *eng, int nt)
+static int save_restart(const char *path, const cfg_t *c, engine_t *eng, int nf, int nt)
 {
     sphb_status st;
     size_t n = (size_t)nt;
@@ -277,7 +281,8 @@ static int save_restart(const char *path, const cfg_t *c, engine_t *eng, int nt)
         unsigned sig_len = (unsigned)strlen(c->signature);
         long long step = st.step;
         rc = !(fwrite(RESTART_MAGIC, 1, 8, f) == 8 && fwrite(&sig_len, sizeof(sig_len), 1, f) == 1 &&
-               fwrite(c->signature, 1, sig_len, f) == sig_len && fwrite(&nt, sizeof(nt), 1, f) == 1 &&
+               fwrite(c->signature, 1, sig_len, f) == sig_len && fwrite(&RESTART_VERSION, sizeof(RESTART_VERSION), 1, f) == 1 &&
+               fwrite(&nf, sizeof(nf), 1, f) == 1 && fwrite(&nt, sizeof(nt), 1, f) == 1 &&
                fwrite(&st.t, sizeof(double), 1, f) == 1 && fwrite(&step, sizeof(step), 1, f) == 1 &&
                fwrite(buf, sizeof(double), 11 * n, f) == 11 * n);
     }
@@ -293,7 +298,8 @@ static int load_restart(const char *path, const cfg_t *c, particles_t *p, int nt
     FILE *f = fopen(path, "rb");
     char magic[8], sig[512];
     unsigned sig_len = 0;
-    int nt_file = 0, rc = 1;
+    int nt_file = 0, nf_file = 0, rc = 1;
+    unsigned version = 0;
     size_t n = (size_t)nt;
     double *buf = NULL;
     if (!f) return 1;
@@ -305,7 +311,8 @@ static int load_restart(const char *path, const cfg_t *c, particles_t *p, int nt
         printf("restart signature differs from the current configuration: starting from t = 0\n");
         goto done;
     }
-    if (fread(&nt_file, sizeof(nt_file), 1, f) != 1 || nt_file != nt || fread(t, sizeof(double), 1, f) != 1 ||
+    if (fread(&version, sizeof(version), 1, f) != 1 || version != RESTART_VERSION || fread(&nf_file, sizeof(nf_file), 1, f) != 1 ||
+        nf_file != p->n_fluid || fread(&nt_file, sizeof(nt_file), 1, f) != 1 || nt_file != nt || fread(t, sizeof(double), 1, f) != 1 ||
         fread(step, sizeof(*step), 1, f) != 1)
         goto done;
     buf = (double *)malloc(11 * n * sizeof(double));
@@ -453,7 +460,7 @@ int main(int argc, char **argv)
             /* 20 steps at a time so the log cadence of m:285-291 is kept */
             long long chunk = 20 - (st.step % 20), done = 0;
             if (max_steps > 0 && chunk > max_steps - steps_total) chunk = max_steps - steps_total;
-            if (dual_inner > 1) {
+            if (dual_inner > 1 && st.t + 1.05 * dual_inner * st.dt < target) {
                 CHECK(sphb_ctx_run_dual(ctx, 1, dual_inner));
                 done = dual_inner;
             } else {
@@ -473,7 +480,7 @@ int main(int argc, char **argv)
             }
         }
         printf("output point: t=%.6f, step=%lld\n", st.t, st.step);   /* m:294 */
-        if (save_restart(restart_path, &c, &eng, p.n_total)) fprintf(stderr, "warning: could not write %s\n", restart_path);
+        if (save_restart(restart_path, &c, &eng, p.n_fluid, p.n_total)) fprintf(stderr, "warning: could not write %s\n", restart_path);
     }
 
     l2 = l2_error(&c, &eng, n_bins, u_mean, u_exact, y_mid);      /* S7 */
