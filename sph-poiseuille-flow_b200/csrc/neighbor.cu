@@ -871,7 +871,15 @@ __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__re
                     }
                     cxi = T.a + lo;
                 }
-                const bool interior = cxi >= 1 && cxi <= ncx - 3 && ncx >= 6 && !ghost_anomaly;
+                // Column ncx-2 holds two kinds of walkers: those within the cut-off of x = DL own a ghost entry and meet
+                // the ghosts of column 0 (general walk); the others are to column ncx-1 what a walker of column 1 is to
+                // column 0 -- no entry of their stencil has a second entry inside it, nothing wraps -- and take the
+                // interior walk (with a sliver last column that is about half of them).  The margin keeps the ghosts of
+                // column 0 (at x >= DL) clearly out of their reach: within rounding of the cut-off a pair with a lower
+                // index is decided by THAT particle's walk, which does not reach column ncx-2 (found by the closure fuzz).
+                const bool interior = ncx >= 6 && !ghost_anomaly && cxi >= 1 &&
+                                      (cxi <= ncx - 3 ||
+                                       (cxi == ncx - 2 && !(s_xy[slot_i].x > P.DL - P.cutoff * (1.0 + 1e-9))));
                 if (!seam_tile && !interior) {   // slab mode: a particle clamped into the empty margin columns
                     cnt[ew] = 0;
                 } else if (!interior) {
