@@ -377,7 +377,14 @@ def b200_arm(args):
     # inner > 1 (or a library without that entry point) takes the longer route through run_dual.
     e2e_path = {"uploaded": inner == 1 and hasattr(ch, "step_uploaded")}
 
+    e2e_path["one_call"] = e2e_path["uploaded"] and hasattr(ch, "step_host")
+
     def e2e_step():
+        if e2e_path["one_call"]:      # the same three calls as ONE (the list build overlaps the rest of the upload)
+            ch.step_host(host, outs)
+            for k in host:
+                host[k], outs[k] = outs[k], host[k]
+            return outs
         ch.upload(pos=host["pos"], vel=host["vel"], rho=host["rho"], drho_dt=host["drho_dt"])
         if e2e_path["uploaded"]:
             try:
@@ -486,7 +493,9 @@ def b200_arm(args):
                        "parallelism": f"{world} independent channel(s), one per GPU"},
             "e2e": {"value": e2e_value, "unit": "particle-substeps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "path": ("sphb_ctx_upload -> sphb_ctx_step_uploaded (list + shear + physics) -> sphb_ctx_download, "
+                    "path": ("sphb_ctx_step_host: upload -> list + shear + physics -> download in one call, pinned host "
+                             "(the list build overlaps the rest of the upload)" if e2e_path.get("one_call") else
+                             "sphb_ctx_upload -> sphb_ctx_step_uploaded (list + shear + physics) -> sphb_ctx_download, "
                              "pinned host" if e2e_path["uploaded"] else
                              "sphb_ctx_upload -> neighbor_build -> run_dual(1, inner) -> sphb_ctx_download, pinned host")},
             "gpu_launches": int(total_launches),

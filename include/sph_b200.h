@@ -226,6 +226,14 @@ SPHB_API int sphb_ctx_step(sphb_ctx *ctx, double remain);
  * not rebuilt for the new positions (the next upload would discard it); asynchronous like sphb_ctx_step.
  */
 SPHB_API int sphb_ctx_step_uploaded(sphb_ctx *ctx, double remain);
+/* The same step as ONE call on host arrays (column-major n_total-row arrays as in sphb_ctx_upload / _download; the
+ * inputs are required, any output may be NULL): upload -> list -> shear monitor -> physics -> download with the
+ * transfers overlapped where the data flow allows (the list build runs while rho / drho_dt are on the wire).  Same
+ * results, bit for bit, as sphb_ctx_upload + sphb_ctx_step_uploaded + sphb_ctx_download.  Returns when the outputs
+ * are in place. */
+SPHB_API int sphb_ctx_step_host(sphb_ctx *ctx, double remain, const double *pos, const double *vel, const double *rho,
+                                const double *drho_dt, double *pos_out, double *vel_out, double *rho_out, double *p_out,
+                                double *drho_dt_out, double *force_out);
 /* Reference schedule until t >= t_target - 1e-12 (m:250) or max_steps; returns steps done. */
 SPHB_API int sphb_ctx_run_until(sphb_ctx *ctx, double t_target, double t_end, long long max_steps,
                                 long long *steps_done);

@@ -438,6 +438,22 @@ class Channel:
         list rebuild (sphb_ctx_step_uploaded)."""
         _check(lib().sphb_ctx_step_uploaded(self._ctx, C.c_double(remain)))
 
+    def step_host(self, state: dict, out: dict, remain: float = float("inf")):
+        """One reference step on host arrays in ONE call (sphb_ctx_step_host): `state` holds pos, vel, rho, drho_dt,
+        `out` any of pos, vel, rho, p, drho_dt, force (column-major float64, ideally pinned); transfers overlap the list
+        build.  Bit-identical to upload + step_uploaded + download_into."""
+        nt = self.prm.n_total
+        cols = dict(pos=2, vel=2, rho=1, p=1, drho_dt=1, force=2)
+        for d in (state, out):
+            for k, a in d.items():
+                want = (nt, cols[k]) if cols[k] > 1 else (nt,)
+                if a.dtype != np.float64 or a.shape != want or not (a.flags.f_contiguous or a.ndim == 1):
+                    raise SphError("SPHB:arg", f"step_host: {k} must be a column-major float64 array of shape {want}")
+        _check(lib().sphb_ctx_step_host(
+            self._ctx, C.c_double(remain), _p(state["pos"]), _p(state["vel"]), _p(state["rho"]), _p(state["drho_dt"]),
+            *[(_p(out[k]) if k in out else None) for k in ("pos", "vel", "rho", "p", "drho_dt", "force")]))
+        return out
+
     def run_until(self, t_target: float, t_end: float, max_steps: int = 0) -> int:
         n = C.c_longlong(0)
         _check(lib().sphb_ctx_run_until(self._ctx, C.c_double(t_target), C.c_double(t_end), C.c_longlong(max_steps),

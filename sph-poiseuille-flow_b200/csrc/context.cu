@@ -372,6 +372,8 @@ SPHB_API void sphb_ctx_destroy(sphb_ctx *c)
     c->sw.release_all();
     c->kprof.release();
     if (c->flags_ev) cudaEventDestroy(c->flags_ev);
+    if (c->aux_ev) cudaEventDestroy(c->aux_ev);
+    if (c->aux_st) cudaStreamDestroy(c->aux_st);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
     if (c->h_ints) cudaFreeHost(c->h_ints);
     for (auto &e : c->ev)
@@ -379,6 +381,31 @@ SPHB_API void sphb_ctx_destroy(sphb_ctx *c)
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
 }
+
+namespace {
+void host_y_range(const double *y, size_t n, double &lo, double &hi)
+{
+    double lo8[8], hi8[8];
+    for (int k = 0; k < 8; ++k) lo8[k] = hi8[k] = y[0];
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8)
+        for (int k = 0; k < 8; ++k) {
+            const double v = y[i + k];
+            lo8[k] = v < lo8[k] ? v : lo8[k];
+            hi8[k] = v > hi8[k] ? v : hi8[k];
+        }
+    for (; i < n; ++i) {
+        lo8[0] = y[i] < lo8[0] ? y[i] : lo8[0];
+        hi8[0] = y[i] > hi8[0] ? y[i] : hi8[0];
+    }
+    lo = lo8[0];
+    hi = hi8[0];
+    for (int k = 1; k < 8; ++k) {
+        lo = lo8[k] < lo ? lo8[k] : lo;
+        hi = hi8[k] > hi ? hi8[k] : hi;
+    }
+}
+}  // namespace
 
 SPHB_API int sphb_ctx_upload(sphb_ctx *c, const double *pos, const double *vel, const double *rho,
                              const double *drho_dt, const double *mass, const double *wall_vel)
@@ -420,25 +447,8 @@ SPHB_API int sphb_ctx_upload(sphb_ctx *c, const double *pos, const double *vel, 
         // the copies above are in flight -- this pass over the host array used to sit between the first copy and the
         // rest and cost more than the whole upload (0.8 ms for 489 600 rows as a dependent min / max chain; eight
         // independent chains take a third of that and now overlap the transfer).
-        double lo8[8], hi8[8];
-        const double *y = pos + n;
-        for (int k = 0; k < 8; ++k) lo8[k] = hi8[k] = y[0];
-        size_t i = 0;
-        for (; i + 8 <= n; i += 8)
-            for (int k = 0; k < 8; ++k) {
-                const double v = y[i + k];
-                lo8[k] = v < lo8[k] ? v : lo8[k];
-                hi8[k] = v > hi8[k] ? v : hi8[k];
-            }
-        for (; i < n; ++i) {
-            lo8[0] = y[i] < lo8[0] ? y[i] : lo8[0];
-            hi8[0] = y[i] > hi8[0] ? y[i] : hi8[0];
-        }
-        double lo = lo8[0], hi = hi8[0];
-        for (int k = 1; k < 8; ++k) {
-            lo = lo8[k] < lo ? lo8[k] : lo;
-            hi = hi8[k] > hi ? hi8[k] : hi;
-        }
+        double lo, hi;
+        host_y_range(pos + n, n, lo, hi);
         if (!c->planned || lo < c->y_lo || hi > c->y_hi) {
             SPHB_CUDA(cudaStreamSynchronize(c->st));   // (the staging regions are in use; planning may reallocate)
             drop_graphs(c);
@@ -706,6 +716,51 @@ SPHB_API int sphb_ctx_step_uploaded(sphb_ctx *c, double remain)
     if (!c->have_list) SPHB_TRY(do_neighbor(c));
     SPHB_TRY(do_shear(c));
     return ctx_step_physics(c, remain);
+}
+
+// The same step as ONE call on host arrays (what the reference's script does per step with its two MEX calls, m:280 +
+// the modes of m:254-270): upload -> list for the uploaded positions -> shear monitor -> physics -> download.  The
+// transfers overlap the work where the data flow allows: the list build needs positions and velocities only and runs
+// while rho and drho_dt are still on the wire (a second stream); everything else is sphb_ctx_upload /
+// sphb_ctx_step_uploaded / sphb_ctx_download, with the same results bit for bit.
+SPHB_API int sphb_ctx_step_host(sphb_ctx *c, double remain, const double *pos, const double *vel, const double *rho,
+                                const double *drho_dt, double *pos_out, double *vel_out, double *rho_out, double *p_out,
+                                double *drho_dt_out, double *force_out)
+{
+    clear_error();
+    if (!c || !pos || !vel || !rho || !drho_dt) return set_error("SPHB:arg", "null argument");
+    SPHB_TRY(bind_device(c));
+    if (c->slab.on) return set_error("SPHB:state", "not available on a slab of a sharded channel");
+    if (!c->aux_st) SPHB_CUDA(cudaStreamCreateWithFlags(&c->aux_st, cudaStreamNonBlocking));
+    if (!c->aux_ev) SPHB_CUDA(cudaEventCreateWithFlags(&c->aux_ev, cudaEventDisableTiming));
+    const int nt = c->prm.n_total;
+    const size_t n = (size_t)nt;
+    double *stage = c->stage.as<double>();
+    // (the previous call returned after a synchronisation: nothing on the main stream still reads rho / drho_dt)
+    SPHB_CUDA(cudaMemcpyAsync(c->rho.p, rho, n * sizeof(double), cudaMemcpyHostToDevice, c->aux_st));
+    SPHB_CUDA(cudaMemcpyAsync(c->drho_dt.p, drho_dt, n * sizeof(double), cudaMemcpyHostToDevice, c->aux_st));
+    SPHB_CUDA(cudaEventRecord(c->aux_ev, c->aux_st));
+    SPHB_CUDA(cudaMemcpyAsync(stage, pos, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    launch_pack2(stage, c->pos.as<double2>(), nt, c->st);
+    SPHB_CUDA(cudaMemcpyAsync(stage + 2 * n, vel, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    launch_pack2(stage + 2 * n, c->vel.as<double2>(), nt, c->st);
+    c->have_list = false;
+    c->nw.grid_ready = false;
+    c->mirrors_stale = true;
+    double lo, hi;
+    host_y_range(pos + n, n, lo, hi);
+    if (!c->planned || lo < c->y_lo || hi > c->y_hi) {
+        SPHB_CUDA(cudaStreamSynchronize(c->st));
+        SPHB_CUDA(cudaStreamSynchronize(c->aux_st));
+        drop_graphs(c);
+        SPHB_TRY(plan_lists(c, lo, hi));
+    }
+    SPHB_TRY(csr_vmax(c->P, c->vel.as<double2>(), c->sc(), c->st));
+    SPHB_TRY(do_neighbor(c));                                   // m:280 of the caller's previous step
+    SPHB_CUDA(cudaStreamWaitEvent(c->st, c->aux_ev, 0));
+    SPHB_TRY(do_shear(c));                                      // m:281-283
+    SPHB_TRY(ctx_step_physics(c, remain));                      // m:254-270
+    return sphb_ctx_download(c, pos_out, vel_out, rho_out, p_out, drho_dt_out, force_out, nullptr, nullptr, nullptr);
 }
 
 namespace {

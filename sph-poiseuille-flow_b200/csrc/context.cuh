@@ -43,6 +43,8 @@ struct sphb_ctx {
     int device = 0;
     cudaStream_t st = nullptr;
     cudaStream_t own_st = nullptr;   // the context's own stream while `st` is a stream of the caller
+    cudaStream_t aux_st = nullptr;   // second stream of sphb_ctx_step_host (copies that overlap the list build)
+    cudaEvent_t aux_ev = nullptr;
     // state (+ alternates for the cell-sort permutation)
     DevBuf pos, vel, vel_new, wall_vel, force, force_prior, rho, p, drho_dt, mass, Vol, B;
     DevBuf a_pos, a_vel, a_wall_vel, a_force, a_force_prior, a_rho, a_p, a_drho_dt, a_mass, a_Vol, a_B;

@@ -122,6 +122,7 @@ cudaError_t cudaGraphExecDestroy(cudaGraphExec_t exec);
 cudaError_t cudaEventCreate(cudaEvent_t *e);
 enum { cudaEventDisableTiming = 2 };
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }   // (work runs at enqueue time)
 inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }   // launches run synchronously: always complete
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st = nullptr);

@@ -77,3 +77,35 @@ def test_step_uploaded_keeps_a_valid_list(sphb, H):
     assert ch.timing()["launches"] - l1 > with_list
     assert ch.status()["error_flags"] == 0
     ch.close()
+
+
+def test_step_host_equals_the_three_calls_bitwise(sphb, H):
+    """sphb_ctx_step_host (upload -> list -> shear -> physics -> download in ONE call, the list build overlapping the
+    rest of the upload on a second stream) gives the arrays of upload + step_uploaded + download to the bit, over
+    several passes with the state going through host arrays every time, and with a remaining-time cut."""
+    prm = H.derive_params(dp=0.05, c_f=15.0)
+    st = H.developed_state(prm, seed=79)
+    a = _channel(sphb, prm, st)
+    a.initialise()
+    b = _channel(sphb, prm, st)
+    b.initialise()
+    nt = st.n_total
+    sa = a.download(("pos", "vel", "rho", "drho_dt"))
+    sb = {k: v.copy(order="F") for k, v in sa.items()}
+    names = ("pos", "vel", "rho", "p", "drho_dt", "force")
+    for k in range(4):
+        remain = float("inf") if k != 2 else 0.5 * a.status()["dt"]
+        a.upload(pos=sa["pos"], vel=sa["vel"], rho=sa["rho"], drho_dt=sa["drho_dt"])
+        a.step_uploaded(remain)
+        da = a.download(names)
+        out = {f: (np.zeros((nt, 2), order="F") if f in ("pos", "vel", "force") else np.zeros(nt)) for f in names}
+        b.step_host(sb, out, remain)
+        for f in names:
+            assert np.array_equal(da[f], out[f]), (k, f)
+        ta, tb = a.status(), b.status()
+        for key in ("t", "dt", "vmax", "tau_bottom", "tau_top", "step", "n_half_pairs", "error_flags"):
+            assert ta[key] == tb[key], (k, key)
+        sa = {f: da[f] for f in ("pos", "vel", "rho", "drho_dt")}
+        sb = {f: out[f] for f in ("pos", "vel", "rho", "drho_dt")}
+    a.close()
+    b.close()
