@@ -747,9 +747,14 @@ SPHB_API int sphb_ctx_step_host(sphb_ctx *c, double remain, const double *pos, c
     c->have_list = false;
     c->nw.grid_ready = false;
     c->mirrors_stale = true;
+    // The y range of the uploaded rows is needed for capacity planning only (the grid itself is derived on the device),
+    // and a pass over the host array costs as much as the upload: the list build is enqueued first and the pass runs
+    // beside it; in the rare case that the rows have left the planned range the build is repeated after re-planning
+    // (the first one has only raised the cell-capacity flag, which poisons nothing before the physics).
     double lo, hi;
-    host_y_range(pos + n, n, lo, hi);
-    if (!c->planned || lo < c->y_lo || hi > c->y_hi) {
+    const bool planned_before = c->planned;
+    if (!planned_before) {
+        host_y_range(pos + n, n, lo, hi);
         SPHB_CUDA(cudaStreamSynchronize(c->st));
         SPHB_CUDA(cudaStreamSynchronize(c->aux_st));
         drop_graphs(c);
@@ -757,6 +762,23 @@ SPHB_API int sphb_ctx_step_host(sphb_ctx *c, double remain, const double *pos, c
     }
     SPHB_TRY(csr_vmax(c->P, c->vel.as<double2>(), c->sc(), c->st));
     SPHB_TRY(do_neighbor(c));                                   // m:280 of the caller's previous step
+    if (planned_before) {
+        host_y_range(pos + n, n, lo, hi);
+        if (lo < c->y_lo || hi > c->y_hi) {
+            SPHB_CUDA(cudaStreamSynchronize(c->st));
+            SPHB_CUDA(cudaStreamSynchronize(c->aux_st));
+            int f = 0;
+            SPHB_CUDA(cudaMemcpy(&f, c->nw.flags.p, sizeof(int), cudaMemcpyDeviceToHost));
+            f &= ~(kErrCellCap | kErrCsrCap | kErrTileCap);
+            SPHB_CUDA(cudaMemcpy(c->nw.flags.p, &f, sizeof(int), cudaMemcpyHostToDevice));
+            drop_graphs(c);
+            SPHB_TRY(plan_lists(c, lo, hi));
+            c->have_list = false;
+            c->nw.grid_ready = false;
+            c->list_sized = false;
+            SPHB_TRY(do_neighbor(c));
+        }
+    }
     SPHB_CUDA(cudaStreamWaitEvent(c->st, c->aux_ev, 0));
     SPHB_TRY(do_shear(c));                                      // m:281-283
     SPHB_TRY(ctx_step_physics(c, remain));                      // m:254-270

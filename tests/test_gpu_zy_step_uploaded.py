@@ -107,5 +107,9 @@ def test_step_host_equals_the_three_calls_bitwise(sphb, H):
             assert ta[key] == tb[key], (k, key)
         sa = {f: da[f] for f in ("pos", "vel", "rho", "drho_dt")}
         sb = {f: out[f] for f in ("pos", "vel", "rho", "drho_dt")}
+        if k == 1:      # the rows leave the y range the lists were planned for: both routes plan again
+            for d in (sa, sb):
+                d["pos"] = d["pos"].copy(order="F")
+                d["pos"][:, 1] += 0.83
     a.close()
     b.close()
