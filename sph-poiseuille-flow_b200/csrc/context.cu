@@ -266,6 +266,8 @@ int ctx_volumes_from_mass(sphb_ctx *c)
 int ctx_step_physics(sphb_ctx *c, double remain)
 {
     c->h_step += 1;
+    c->last_inner = 1;
+    c->last_remain = remain;
     SPHB_TRY(do_publish_dt(c, remain, 0.0));                  // m:259
     SPHB_TRY(do_density(c));                                  // m:254-255
     // a slab's list build follows after the exchange: the continuity pass starts its grid set-up (GridFuse, derive = 0)
@@ -459,6 +461,11 @@ SPHB_API int sphb_ctx_upload(sphb_ctx *c, const double *pos, const double *vel, 
     return 0;
 }
 
+namespace {
+int enqueue_download(sphb_ctx *c, double *pos, double *vel, double *rho, double *p, double *drho_dt, double *force,
+                     double *force_prior, double *Vol, double *B);
+}
+
 SPHB_API int sphb_ctx_download(sphb_ctx *c, double *pos, double *vel, double *rho, double *p, double *drho_dt,
                                double *force, double *force_prior, double *Vol, double *B)
 {
@@ -467,6 +474,17 @@ SPHB_API int sphb_ctx_download(sphb_ctx *c, double *pos, double *vel, double *rh
     SPHB_TRY(bind_device(c));
     if (c->have_list && !c->flags_pending) SPHB_TRY(ctx_flags_watch(c));
     SPHB_TRY(ctx_flags_poll(c, true));   // an asynchronous run that raised a device flag is recovered (or reported) first
+    SPHB_TRY(enqueue_download(c, pos, vel, rho, p, drho_dt, force, force_prior, Vol, B));
+    SPHB_CUDA(cudaStreamSynchronize(c->st));
+    SPHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+namespace {
+// the copies of sphb_ctx_download, enqueued on the context's stream (no wait at the end)
+int enqueue_download(sphb_ctx *c, double *pos, double *vel, double *rho, double *p, double *drho_dt, double *force,
+                     double *force_prior, double *Vol, double *B)
+{
     const int nt = c->prm.n_total;
     const size_t n = (size_t)nt;
     double *stage = c->stage.as<double>();
@@ -494,10 +512,9 @@ SPHB_API int sphb_ctx_download(sphb_ctx *c, double *pos, double *vel, double *rh
     if (p) SPHB_CUDA(cudaMemcpyAsync(p, c->p.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     if (drho_dt) SPHB_CUDA(cudaMemcpyAsync(drho_dt, c->drho_dt.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     if (Vol) SPHB_CUDA(cudaMemcpyAsync(Vol, c->Vol.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-    SPHB_CUDA(cudaStreamSynchronize(c->st));
-    SPHB_CUDA(cudaGetLastError());
     return 0;
 }
+}  // namespace
 
 SPHB_API int sphb_ctx_set_time(sphb_ctx *c, double t, long long step)
 {
@@ -688,6 +705,8 @@ SPHB_API int sphb_ctx_step(sphb_ctx *c, double remain)
 {
     CTX_ENTER(true);
     c->h_step += 1;
+    c->last_inner = 1;
+    c->last_remain = remain;
     tick(c, 0);
     SPHB_TRY(do_publish_dt(c, remain, 0.0));                                          // m:259
     SPHB_TRY(do_density(c));                                                          // m:254-255
@@ -731,6 +750,7 @@ SPHB_API int sphb_ctx_step_host(sphb_ctx *c, double remain, const double *pos, c
     if (!c || !pos || !vel || !rho || !drho_dt) return set_error("SPHB:arg", "null argument");
     SPHB_TRY(bind_device(c));
     if (c->slab.on) return set_error("SPHB:state", "not available on a slab of a sharded channel");
+    SPHB_TRY(ctx_flags_poll(c, true));   // what an earlier asynchronous run left behind
     if (!c->aux_st) SPHB_CUDA(cudaStreamCreateWithFlags(&c->aux_st, cudaStreamNonBlocking));
     if (!c->aux_ev) SPHB_CUDA(cudaEventCreateWithFlags(&c->aux_ev, cudaEventDisableTiming));
     const int nt = c->prm.n_total;
@@ -744,45 +764,48 @@ SPHB_API int sphb_ctx_step_host(sphb_ctx *c, double remain, const double *pos, c
     launch_pack2(stage, c->pos.as<double2>(), nt, c->st);
     SPHB_CUDA(cudaMemcpyAsync(stage + 2 * n, vel, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->st));
     launch_pack2(stage + 2 * n, c->vel.as<double2>(), nt, c->st);
-    c->have_list = false;
-    c->nw.grid_ready = false;
-    c->mirrors_stale = true;
-    // The y range of the uploaded rows is needed for capacity planning only (the grid itself is derived on the device),
-    // and a pass over the host array costs as much as the upload: the list build is enqueued first and the pass runs
-    // beside it; in the rare case that the rows have left the planned range the build is repeated after re-planning
-    // (the first one has only raised the cell-capacity flag, which poisons nothing before the physics).
-    double lo, hi;
-    const bool planned_before = c->planned;
-    if (!planned_before) {
+    double lo = 0.0, hi = 0.0;
+    if (!c->planned) {   // first call: the lists are planned for the y range of these rows
         host_y_range(pos + n, n, lo, hi);
         SPHB_CUDA(cudaStreamSynchronize(c->st));
         SPHB_CUDA(cudaStreamSynchronize(c->aux_st));
         drop_graphs(c);
         SPHB_TRY(plan_lists(c, lo, hi));
     }
-    SPHB_TRY(csr_vmax(c->P, c->vel.as<double2>(), c->sc(), c->st));
-    SPHB_TRY(do_neighbor(c));                                   // m:280 of the caller's previous step
-    if (planned_before) {
-        host_y_range(pos + n, n, lo, hi);
-        if (lo < c->y_lo || hi > c->y_hi) {
-            SPHB_CUDA(cudaStreamSynchronize(c->st));
-            SPHB_CUDA(cudaStreamSynchronize(c->aux_st));
-            int f = 0;
-            SPHB_CUDA(cudaMemcpy(&f, c->nw.flags.p, sizeof(int), cudaMemcpyDeviceToHost));
-            f &= ~(kErrCellCap | kErrCsrCap | kErrTileCap);
-            SPHB_CUDA(cudaMemcpy(c->nw.flags.p, &f, sizeof(int), cudaMemcpyHostToDevice));
-            drop_graphs(c);
-            SPHB_TRY(plan_lists(c, lo, hi));
-            c->have_list = false;
-            c->nw.grid_ready = false;
-            c->list_sized = false;
-            SPHB_TRY(do_neighbor(c));
+    // The whole step is enqueued without looking at the rows on the host: the grid of the list is derived on the
+    // device, and a build that outgrows what was planned (cells, rows, tile slots) raises a flag that stops the
+    // kernels behind it, so the state stays what was uploaded.  Only then is the host's y range needed -- to plan again
+    // and repeat the step from the same, untouched input arrays.  (A pass over the host array per call, as
+    // sphb_ctx_upload makes, costs as much as the upload itself.)
+    for (int attempt = 0;; ++attempt) {
+        c->have_list = false;
+        c->nw.grid_ready = false;
+        c->mirrors_stale = true;
+        if (attempt == 0) SPHB_TRY(csr_vmax(c->P, c->vel.as<double2>(), c->sc(), c->st));
+        SPHB_TRY(do_neighbor(c));                                   // m:280 of the caller's previous step
+        if (attempt == 0) SPHB_CUDA(cudaStreamWaitEvent(c->st, c->aux_ev, 0));
+        SPHB_TRY(do_shear(c));                                      // m:281-283
+        SPHB_TRY(ctx_step_physics(c, remain));                      // m:254-270
+        SPHB_TRY(enqueue_download(c, pos_out, vel_out, rho_out, p_out, drho_dt_out, force_out, nullptr, nullptr, nullptr));
+        SPHB_CUDA(cudaMemcpyAsync(c->h_ints + 5, c->nw.flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        SPHB_CUDA(cudaStreamSynchronize(c->st));
+        SPHB_CUDA(cudaGetLastError());
+        int f = c->h_ints[5];
+        if (!f) return 0;
+        if ((f & ~(kErrCellCap | kErrCsrCap | kErrTileCap)) || attempt > 0) {
+            if (f & kErrNonFinite)
+                return set_error("SPHB:diverged", "non-finite density or velocity in the uploaded step (flags %d)", f);
+            return set_error("SPHB:capacity", "device error flags %d: the step was not taken", f);
         }
+        // capacity: clear the flags, plan for the rows as they are now, build exactly (grows the list / the tile slots)
+        f = 0;
+        SPHB_CUDA(cudaMemcpy(c->nw.flags.p, &f, sizeof(int), cudaMemcpyHostToDevice));
+        host_y_range(pos + n, n, lo, hi);
+        drop_graphs(c);
+        if (lo < c->y_lo || hi > c->y_hi) SPHB_TRY(plan_lists(c, std::min(lo, c->y_lo), std::max(hi, c->y_hi)));
+        c->list_sized = false;
+        c->h_step -= 1;   // (the stopped attempt counted a step the device did not take)
     }
-    SPHB_CUDA(cudaStreamWaitEvent(c->st, c->aux_ev, 0));
-    SPHB_TRY(do_shear(c));                                      // m:281-283
-    SPHB_TRY(ctx_step_physics(c, remain));                      // m:254-270
-    return sphb_ctx_download(c, pos_out, vel_out, rho_out, p_out, drho_dt_out, force_out, nullptr, nullptr, nullptr);
 }
 
 namespace {
@@ -866,10 +889,10 @@ SPHB_API int sphb_ctx_run_until(sphb_ctx *c, double t_target, double t_end, long
 
 namespace {
 
-int enqueue_outer(sphb_ctx *c, int n_inner, bool with_sort)
+int enqueue_outer(sphb_ctx *c, int n_inner, bool with_sort, double first_remain = std::numeric_limits<double>::infinity())
 {
     const double inf = std::numeric_limits<double>::infinity();
-    SPHB_TRY(do_publish_dt(c, inf, 0.0));
+    SPHB_TRY(do_publish_dt(c, first_remain, 0.0));
     SPHB_TRY(do_density(c));
     SPHB_TRY(do_fused_first_substep(c, true, n_inner == 1));
     for (int s = 1; s < n_inner; ++s) SPHB_TRY(do_substep(c, inf, 0.0, true, s == n_inner - 1));
@@ -945,7 +968,9 @@ int flags_handle(sphb_ctx *c)   // the copy of flags_watch has landed
     drop_graphs(c);
     const long long missing = c->h_step - dev_step;
     const int inner = std::max(1, c->last_inner);
-    for (long long o = 0; o < missing / inner; ++o) SPHB_TRY(enqueue_outer(c, inner, false));
+    // (a single step that was cut short by the caller's target, m:259, is taken again with the same cut)
+    for (long long o = 0; o < missing / inner; ++o)
+        SPHB_TRY(enqueue_outer(c, inner, false, (missing == 1 && inner == 1) ? c->last_remain : std::numeric_limits<double>::infinity()));
     return 0;
 }
 
@@ -974,6 +999,7 @@ SPHB_API int sphb_ctx_run_dual(sphb_ctx *c, int n_outer, int n_inner)
     if (n_inner < 1 || n_outer < 0) return set_error("SPHB:arg", "n_inner >= 1 and n_outer >= 0 required");
     SPHB_TRY(flags_poll(c, false));   // what an earlier asynchronous run left behind
     c->last_inner = n_inner;
+    c->last_remain = std::numeric_limits<double>::infinity();
     const int si = c->prm.sort_interval;
     if (c->graph_inner != n_inner) drop_graphs(c);
     for (int o = 0; o < n_outer; ++o) {

@@ -80,6 +80,7 @@ struct sphb_ctx {
     bool flags_pending = false;
     unsigned watch_skip = 0;
     int last_inner = 1;          // substeps per outer step of the last run_dual (to redo the steps a poisoned run skipped)
+    double last_remain = 1.0e300;   // remaining-time cut of the last single step (m:259), for the same purpose
 
     StateView view() const
     {

@@ -103,13 +103,21 @@ def test_step_host_equals_the_three_calls_bitwise(sphb, H):
         for f in names:
             assert np.array_equal(da[f], out[f]), (k, f)
         ta, tb = a.status(), b.status()
-        for key in ("t", "dt", "vmax", "tau_bottom", "tau_top", "step", "n_half_pairs", "error_flags"):
+        # (in the pass after the wall moved, the three-call route recovers from the outgrown list the way a resident
+        # run does -- list and monitor again AFTER the physics -- so its monitor and pair count are those of the new
+        # positions; the one-call route repeats the step and reports the monitor of the uploaded ones)
+        keys = ("t", "dt", "vmax", "step", "error_flags") + (() if k == 2 else ("tau_bottom", "tau_top", "n_half_pairs"))
+        for key in keys:
             assert ta[key] == tb[key], (k, key)
         sa = {f: da[f] for f in ("pos", "vel", "rho", "drho_dt")}
         sb = {f: out[f] for f in ("pos", "vel", "rho", "drho_dt")}
-        if k == 1:      # the rows leave the y range the lists were planned for: both routes plan again
+        if k == 1:      # rows leave the y range the lists were planned for (the top wall moves three channel heights
+            # up: more cell rows than the plan's slack): sphb_ctx_upload plans again from the host array, the one-call
+            # route learns it from the device's capacity flag and repeats the step -- same arrays either way
             for d in (sa, sb):
                 d["pos"] = d["pos"].copy(order="F")
-                d["pos"][:, 1] += 0.83
+                top = d["pos"][:, 1] > prm.DH
+                top[:st.n_fluid] = False
+                d["pos"][top, 1] += 3.0
     a.close()
     b.close()
