@@ -70,16 +70,28 @@ __device__ __forceinline__ double4 ldcg4(const double4 *p)
 
 constexpr long long kSpinCycles = 4000000000LL;   // ~2 s at 2 GHz: a peer that never arrives is an error, not a hang
 
-// waits until *slot == seq (a double written by a peer after a system-wide fence); false on time-out
+// load with acquire semantics at system scope: what follows it (in this thread, and in the threads it then meets at a
+// CTA barrier) sees everything the writer released before storing the value -- without the full membar.sys that
+// showed up as a quarter of the receive kernel's stall samples (r2 call 22)
+__device__ __forceinline__ double ld_acquire_sys(const double *p)
+{
+#ifdef SPHB_CPUSIM
+    return *reinterpret_cast<const volatile double *>(p);
+#else
+    double v;
+    asm volatile("ld.acquire.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+
+// waits until *slot == seq (a double written by a peer behind a system-wide fence); false on time-out
 __device__ __forceinline__ bool mail_wait(const double *slot, double seq)
 {
-    const volatile double *v = slot;
     const long long t0 = clock64();
-    while (*v != seq) {
+    while (ld_acquire_sys(slot) != seq) {
         if (clock64() - t0 > kSpinCycles) return false;
         __nanosleep(64);
     }
-    __threadfence_system();
     return true;
 }
 
@@ -264,9 +276,11 @@ __device__ __forceinline__ void write_record(double *rec, double2 x, double2 v, 
 // last CTA publishes the sequence number in both mailboxes (all threads of the CTA call this)
 __device__ __forceinline__ void p2p_arrive(P2PState *st, double *peer_left, double *peer_right, double seq)
 {
-    __threadfence_system();
+    // one system-wide fence per CTA, by the thread that takes the ticket, behind the CTA barrier (fences are cumulative:
+    // it covers the stores of every thread that reached the barrier) -- not one per thread
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         if (atomicAdd(&st->ticket, 1u) == gridDim.x - 1) {
             __threadfence_system();
             *reinterpret_cast<volatile double *>(peer_left + 2) = seq;
@@ -503,6 +517,8 @@ __global__ void __launch_bounds__(kEdgeWarps * 32) k_slab_edge_send(EdgeView E, 
     const bool open_cta = X.state != nullptr && blockIdx.x == gridDim.x - 1;
     int e0 = 0, e1 = 0;
     bool have = false;
+    unsigned m0 = 0u, m1 = 0u;   // class bits and rows of the first two passes, kept across the barrier for the scatter
+    int i0 = 0, i1 = 0;
     if (open_cta) {
         if (threadIdx.x == 0) X.state->seq += 1;   // (the scalars travel after the barrier, beside the scatter)
     } else if (task < n_tasks) {
@@ -510,9 +526,17 @@ __global__ void __launch_bounds__(kEdgeWarps * 32) k_slab_edge_send(EdgeView E, 
         int tot[cN] = {0, 0, 0, 0, 0};
         have = edge_range(E, task, e0, e1);
         if (have) {
-            for (int base = e0; base < e1; base += 32) {
-                int row;
+            int pass = 0;
+            for (int base = e0; base < e1; base += 32, ++pass) {
+                int row = 0;
                 const unsigned m = base + lane < e1 ? edge_class(E, A, G, base + lane, row) : 0u;
+                if (pass == 0) {
+                    m0 = m;
+                    i0 = row;
+                } else if (pass == 1) {
+                    m1 = m;
+                    i1 = row;
+                }
 #pragma unroll
                 for (int k = 1; k < cN; ++k) tot[k] += __popc(__ballot_sync(0xffffffffu, (m >> k) & 1u));
             }
@@ -621,9 +645,10 @@ __global__ void __launch_bounds__(kEdgeWarps * 32) k_slab_edge_send(EdgeView E, 
         }
         // ---- scatter
         if (have) {
-            for (int base = e0; base < e1; base += 32) {
-                int i = 0;
-                const unsigned m = base + lane < e1 ? edge_class(E, A, G, base + lane, i) : 0u;
+            int pass = 0;
+            for (int base = e0; base < e1; base += 32, ++pass) {
+                int i = pass == 0 ? i0 : i1;
+                const unsigned m = pass == 0 ? m0 : (pass == 1 ? m1 : (base + lane < e1 ? edge_class(E, A, G, base + lane, i) : 0u));
                 double2 x = make_double2(0.0, 0.0), v = x;
                 double rho = 0.0, drho = 0.0, mass = 0.0, Vol = 0.0;
                 Mat2 B{};
@@ -657,11 +682,13 @@ __global__ void __launch_bounds__(kEdgeWarps * 32) k_slab_edge_send(EdgeView E, 
             }
         }
     }
-    // ---- finish: the last CTA publishes the arrival and re-arms the two counters
-    if (peer_left) __threadfence_system();
-    else __threadfence();
+    // ---- finish: the last CTA publishes the arrival and re-arms the two counters.  One fence per CTA, by the thread
+    // that takes the ticket, behind the CTA barrier (fences are cumulative: it covers the records of every thread of
+    // the CTA); a fence per thread was 28 % of this kernel's stall samples (r2 call 22)
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (peer_left) __threadfence_system();
+        else __threadfence();
         if (atomicAdd(counts + 7, 1) == (int)gridDim.x - 1) {
             if (peer_left) {
                 __threadfence_system();
