@@ -397,11 +397,18 @@ struct EdgeView {
 };
 __device__ __forceinline__ bool edge_range(const EdgeView &E, int task, int &e0, int &e1)
 {
+    // (cell rows beyond the grid of the last build are empty: the scan covers every planned cell, so their ranges
+    // collapse -- no need to wait for the grid descriptor first)
     const int row = task >> 1, side = task & 1;
-    if (row >= E.g->ncy) return false;
     const int i0 = row * E.ncx + E.a[side], i1 = row * E.ncx + E.b[side];
-    e0 = i0 < E.cell_cap ? E.cell_start[i0] : E.g->n_entries;
-    e1 = i1 < E.cell_cap ? E.cell_start[i1] : E.g->n_entries;
+    if (i1 >= E.cell_cap) {
+        const int n_entries = E.g->n_entries;
+        e0 = i0 < E.cell_cap ? E.cell_start[i0] : n_entries;
+        e1 = n_entries;
+    } else {
+        e0 = E.cell_start[i0];
+        e1 = E.cell_start[i1];
+    }
     return e1 > e0;
 }
 // class bits (without cStay) of the candidate at entry e, 0 for entries that are not live owned rows
