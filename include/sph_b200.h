@@ -184,7 +184,13 @@ SPHB_API int sphb_ctx_neighbor_count(sphb_ctx *ctx, size_t *n_half_pairs, size_t
 /* The reference's half-pair COO list (same order/values as sphb_neighbor_search), 7 x n_half_pairs. */
 SPHB_API int sphb_ctx_neighbor_export_pairs(sphb_ctx *ctx, double *pair_i, double *pair_j, double *dx,
                                             double *dy, double *r, double *W, double *dW);
-/* The full (gather) CSR: row_ptr[n_fluid+1], col[n_csr_entries] (0-based j, ascending per row). */
+/* The full (gather) CSR: row_ptr[n_fluid+1], col[n_csr_entries] (0-based j, ascending per row).  It is the symmetric
+ * closure of the reference's half list with ONE documented exception: a fluid-fluid pair that one end reaches only
+ * through a rounding accident at the periodic seam (a ghost entry in an unusual column, or x_w exactly on a
+ * ghost-insertion threshold, nb:282-294) can be missing from the OTHER end's row.  Such pairs lie within rounding of
+ * r = 2h (measured: |r/2h - 1| < 1e-12 on thousands of adversarial clouds), where W ~ (2 - q)^3 and dW ~ (2 - q)^2
+ * vanish, so no sum of any operator changes; there is never an entry the reference lacks, and the half list
+ * (sphb_ctx_neighbor_export_pairs, sphb_neighbor_search) is exact.  DESIGN.md section 4. */
 SPHB_API int sphb_ctx_neighbor_export_csr(sphb_ctx *ctx, int *row_ptr, int *col);
 
 /* Single operators on the resident state (for operator-level parity tests; P1-P8). */
