@@ -20,6 +20,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <string>
 #include <vector>
 
 using namespace sphb;
@@ -289,8 +290,11 @@ SPHB_API int sphb_slabs_create(const sphb_params *prm, int n_slabs, const int *d
     if (!rc) rc = exchange(g);
     for (int r = 0; r < n_slabs && !rc; ++r) rc = sphb_ctx_slab_step_end(g->s[(size_t)r].ctx);
     if (rc) {
-        // keep the callee's error text across the clean-up
+        // keep the callee's error text across the clean-up (the calls below clear it)
+        const std::string id = sphb_last_error_id() ? sphb_last_error_id() : "SPHB:error";
+        const std::string msg = sphb_last_error_msg() ? sphb_last_error_msg() : "";
         sphb_slabs_destroy(g);
+        set_error(id.c_str(), "%s", msg.c_str());
         return rc;
     }
     *out = g;

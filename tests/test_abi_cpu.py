@@ -144,3 +144,30 @@ def test_batch_entry_points_validate_arguments_without_device():
     assert L.sphb_batch_run_dual(None, 1, 1) != 0 and L.sphb_last_error_id() == b"SPHB:arg"
     assert L.sphb_batch_launches(None) == 0
     L.sphb_batch_destroy(None)
+
+
+def test_slab_group_entry_points_validate_arguments_without_device():
+    """sphb_slabs_* (the C host of the sharded channel): a channel too short for the slab count is refused before any
+    CUDA call; NULL handles are tolerated by the accessors and by destroy."""
+    import importlib
+    sphb = load_product()
+    L = sphb.lib()
+    cs = importlib.import_module("sph_b200.channel_setup")
+    cfg = cs.ChannelConfig(DL=1.0, DH=1.0, dp=0.05, sort_interval=0).derive()    # 8 cell columns: no room for two slabs
+    pt = cs.lattice(cfg)
+    cp = sphb._Params(pt.n_fluid, pt.n_total, cfg.DL, cfg.DH, cfg.dp, cfg.h, cfg.rho0, cfg.p0, cfg.c_f, cfg.mu,
+                      cfg.gravity_g, cfg.inv_sigma0, cfg.transport_coeff, 0, -1, 0)
+    f = np.asfortranarray
+    out = ctypes.c_void_p()
+    p = sphb._p
+    rc = L.sphb_slabs_create(ctypes.byref(cp), ctypes.c_int(2), None, ctypes.c_int(0), p(f(pt.pos)), p(f(pt.vel)),
+                             p(pt.rho), p(pt.drho_dt), p(pt.mass), p(f(pt.wall_vel)), ctypes.byref(out))
+    assert rc != 0 and not out.value
+    assert L.sphb_last_error_id().decode() == "SPHB:arg" and b"do not fit" in L.sphb_last_error_msg()
+    rc = L.sphb_slabs_create(None, ctypes.c_int(2), None, ctypes.c_int(0), None, None, None, None, None, None,
+                             ctypes.byref(out))
+    assert rc != 0 and L.sphb_last_error_id().decode() == "SPHB:arg"
+    assert L.sphb_slabs_count(None) == 0
+    assert L.sphb_slabs_step(None, ctypes.c_double(1.0)) != 0
+    L.sphb_slabs_destroy.restype = None
+    L.sphb_slabs_destroy(None)
