@@ -182,6 +182,8 @@ struct BuildMirrors {
     double inv_rho0 = 0.0;
     double2 *e_vel = nullptr;   // velocity at build time
     double2 *e_w = nullptr;     // (m / rho0, 0) for a wall entry, (-1, 0) for a fluid entry (ph:205)
+    int *ghost_ent = nullptr;   // [2 i + kind - 1] = entry of particle i's ghost of that kind in this build (validated
+                                // against ent_key by its readers: entries of earlier builds are left standing)
 };
 struct NeighborWork {
     int n_fluid = 0, n_total = 0;
@@ -211,6 +213,7 @@ struct NeighborWork {
     DevBuf snap;                 // double2 [n_total]   wrapped x, y at build time
     DevBuf cell_of;              // int [n_total]       home cell of the real entry
     DevBuf ent_of;               // int [n_total]       index of the real entry in the sorted entry array
+    DevBuf ghost_ent;            // int [2 n_total]     entries of the particle's ghosts (BuildMirrors::ghost_ent)
     DevBuf cell_cnt;             // int [2*(cell_cap+1)] counts, then fill cursors
     DevBuf cell_start;           // int [cell_cap+1]
     DevBuf tmp_key, tmp_pos;     // entries as scattered (any order inside a cell)

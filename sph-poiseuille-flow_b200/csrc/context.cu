@@ -149,6 +149,10 @@ int do_sort(sphb_ctx *c)
     for (int k = 0; k < PermuteArrays::kN1; ++k) std::swap(*in1[k], *out1[k]);
     std::swap(c->B, c->a_B);
     c->have_list = false;
+    // the list build reads the rows through these (BuildMirrors): they follow the swap
+    c->nw.mirrors.vel = c->vel.as<double2>();
+    c->nw.mirrors.wall_vel = c->wall_vel.as<double2>();
+    c->nw.mirrors.mass = c->mass.as<double>();
     return 0;
 }
 
@@ -165,6 +169,7 @@ int do_neighbor(sphb_ctx *c)
     c->nw.mirrors.inv_rho0 = c->P.inv_rho0;
     c->nw.mirrors.e_vel = c->e_vel.as<double2>();
     c->nw.mirrors.e_w = c->e_w.as<double2>();
+    c->nw.mirrors.ghost_ent = c->nw.ghost_ent.as<int>();
     SPHB_TRY(neighbor_build(c->nw, c->pos.as<double2>(), false, exact, c->st, &c->launches, &c->kprof));
     if (exact) {
         c->list_sized = true;

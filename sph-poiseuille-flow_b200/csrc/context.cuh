@@ -112,6 +112,7 @@ struct sphb_ctx {
         S.e_b1 = e_b1.as<double2>();
         S.e_b2 = e_b2.as<double2>();
         S.e_vn = e_vn.as<double2>();
+        S.ghost_ent = nw.ghost_ent.as<int>();
         S.flags = nw.flags.as<int>();
         S.ell_stride = nw.ell_stride;
         S.ell_cap = nw.ell_cap;

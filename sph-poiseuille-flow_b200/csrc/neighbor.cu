@@ -848,7 +848,11 @@ __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__re
             }
             // entry-ordered mirrors of the row's velocity and wall weight (BuildMirrors): loaded here, stored
             // after the walk so that the latency hides behind it
-            const bool mirror = M.e_vel != nullptr && (key_i & 3) == 0 && (size_t)ew < stride;
+            // (ghost entries get the same mirror values as the real entry of their particle, so that a seam tile is
+            // staged with the same bulk copies as any other; the ghost's entry index is recorded for the kernels
+            // that produce the other mirrors)
+            const bool mirror = M.e_vel != nullptr && (size_t)ew < stride;
+            if (mirror && (key_i & 3) != 0 && M.ghost_ent != nullptr) M.ghost_ent[2 * i + (key_i & 3) - 1] = ew;
             double2 mv = make_double2(0.0, 0.0);
             double mw = -1.0;
             if (mirror) {
@@ -1204,7 +1208,7 @@ int set_walk_smem(size_t bytes)
 
 void NeighborWork::release_all()
 {
-    DevBuf *all[] = {&grid, &flags, &snap, &cell_of, &ent_of, &cell_cnt, &cell_start, &tmp_key, &tmp_pos,
+    DevBuf *all[] = {&grid, &flags, &snap, &cell_of, &ent_of, &ghost_ent, &cell_cnt, &cell_start, &tmp_key, &tmp_pos,
                      &ent_key, &ent_pos, &tiles, &ell_cnt, &ell_q, &half_cnt, &half_ptr, &scan_tmp, &totals};
     for (DevBuf *b : all) b->release();
 }
@@ -1276,6 +1280,10 @@ int neighbor_plan(NeighborWork &w, int n_fluid, int n_total, double h, double DL
     SPHB_TRY(w.snap.reserve(nt * sizeof(double2)));
     SPHB_TRY(w.cell_of.reserve(nt * sizeof(int)));
     SPHB_TRY(w.ent_of.reserve(nt * sizeof(int)));
+    if (w.ghost_ent.bytes < 2 * nt * sizeof(int)) {
+        SPHB_TRY(w.ghost_ent.reserve(2 * nt * sizeof(int)));
+        SPHB_CUDA(cudaMemset(w.ghost_ent.p, 0xFF, 2 * nt * sizeof(int)));   // -1: no ghost entry known
+    }
     SPHB_TRY(w.cell_cnt.reserve(2 * ((size_t)w.cell_cap + 1) * sizeof(int)));
     SPHB_TRY(w.cell_start.reserve(((size_t)w.cell_cap + 1) * sizeof(int)));
     SPHB_TRY(w.tmp_key.reserve(3 * nt * sizeof(int)));

@@ -104,6 +104,20 @@ __device__ __forceinline__ OwnPre tile_prefetch_own(const StateView &S, const Ti
             if (const int key__ = first__ ? pre.key : S.ent_key[ew]; (key__ & 3) == 0)            \
                 if (const int i = key__ >> 3; true)
 
+// A row within the cut-off of the periodic seam owns ghost entries (key bit 2): the kernel that writes a mirror at the
+// row's own entry writes it at the ghost entries too, so that seam tiles are staged by the same bulk copies as every
+// other tile.  ghost_ent keeps the entry of each ghost as of the build that last had one; it counts only if that entry
+// IS this particle's ghost of that kind in the current list.
+__device__ __forceinline__ void ghost_store(const StateView &S, int key, int i, double2 *mirror, double2 v)
+{
+    if (!(key & 4) || S.ghost_ent == nullptr) return;
+#pragma unroll
+    for (int kind = 1; kind <= 2; ++kind) {
+        const int eg = S.ghost_ent[2 * i + kind - 1];
+        if (eg >= 0 && (size_t)eg < S.ell_stride && S.ent_key[eg] == ((i << 3) | 4 | kind)) mirror[eg] = v;
+    }
+}
+
 // The walker's row: 128-bit words of eight 16-bit entries (padded with the dummy slot), the next word
 // in flight while the current one is processed, four entries per unrolled group.  body(slot, image
 // shift); SHIFT = false skips the decode of the image shift (tiles away from the periodic seam never
@@ -186,21 +200,24 @@ template <class K>
 __device__ __forceinline__ void stage_bulk(const K &k, const StateView &S, const TileDesc &T, unsigned char *buf, int cap,
                                            mbar_t *bar)
 {
-    if ((T.flags & (kTileValid | kTileSeam)) != kTileValid) return;
+    if (!(T.flags & kTileValid)) return;
     if (threadIdx.x >= 32) return;
     const int lane = (int)threadIdx.x;
     const int nf = k.bulk_fields(T);
+    // segments of a staged row: the main range and, for the first / last tile of a tile row, the wrap columns (their
+    // entries -- real and ghost -- carry mirror values like any other: ghost_store)
+    const int segs = (T.flags & kTileSeam) ? kStageRows * 3 : kStageRows;
+    const int step = (T.flags & kTileSeam) ? 1 : 3;
     if (lane == 0) {
         int entries = 0;
-#pragma unroll
-        for (int r = 0; r < kStageRows; ++r) entries += T.seg[3 * r].e - T.seg[3 * r].b;
+        for (int j = 0; j < segs; ++j) entries += T.seg[j * step].e - T.seg[j * step].b;
         mbar_arrive_expect_tx(bar, (unsigned)(entries * nf) * (unsigned)sizeof(double2));
         k.dummy(buf, cap, T.n_staged);
     }
     __syncwarp();
-    for (int c = lane; c < kStageRows * nf; c += 32) {
-        const int r = c / nf, f = c - r * nf;
-        const TileSeg sg = T.seg[3 * r];
+    for (int c = lane; c < segs * nf; c += 32) {
+        const int j = c / nf, f = c - j * nf;
+        const TileSeg sg = T.seg[j * step];
         const int n = sg.e - sg.b;
         if (n > 0)
             bulk_copy_g2s(buf + ((size_t)f * cap + sg.off) * sizeof(double2), k.src(S, f) + sg.b,
@@ -259,16 +276,10 @@ __device__ __forceinline__ void run_tiles(K &k, const StateView &S, unsigned cta
             pre_next = tile_prefetch_own(S, Tn);
         }
         if (T.flags & kTileValid) {
-            if (!(T.flags & kTileSeam)) {
-                mbar_wait(&bars[cur], (parity >> cur) & 1u);
-                parity ^= 1u << cur;
-                if (T.flags & kTileHasWall) k.rows_cold(S, T, pre, buf, cap);
-                else k.template rows<true>(S, T, pre, buf, cap);
-            } else {
-                (void)k.stage_sync(S, T, buf, cap);
-                __syncthreads();
-                k.rows_cold(S, T, pre, buf, cap);
-            }
+            mbar_wait(&bars[cur], (parity >> cur) & 1u);
+            parity ^= 1u << cur;
+            if (T.flags & (kTileHasWall | kTileSeam)) k.rows_cold(S, T, pre, buf, cap);
+            else k.template rows<true>(S, T, pre, buf, cap);
         }
         pre = pre_next;
     }
@@ -287,7 +298,8 @@ struct DensityK {
     static constexpr int kFields = 2;
     PhysParams P;
     double dt;
-    __device__ __forceinline__ int bulk_fields(const TileDesc &T) const { return (T.flags & kTileHasWall) ? 2 : 1; }
+    // (the wall weights are read by the row loop of wall tiles and of seam tiles, which share the cold row loop)
+    __device__ __forceinline__ int bulk_fields(const TileDesc &T) const { return (T.flags & (kTileHasWall | kTileSeam)) ? 2 : 1; }
     __device__ __forceinline__ const double2 *src(const StateView &S, int f) const { return f == 0 ? S.ent_pos : S.e_w; }
     __device__ __forceinline__ void dummy(unsigned char *buf, int cap, int slot) const
     {
@@ -331,6 +343,7 @@ struct DensityK {
                 S.rho[i] = P.rho0;
                 S.Vol[i] = V;
                 S.e_pV[ew] = make_double2(0.0, -V);
+                ghost_store(S, key__, i, S.e_pV, make_double2(0.0, -V));
                 continue;
             }
             const double drho_i = S.drho_dt[i];
@@ -356,7 +369,9 @@ struct DensityK {
             S.Vol[i] = V;
             // half-step pressure of this row for the force kernel's neighbours (ph:857-862)
             const double rho_h = half_step_rho(rho, drho_i, dt, P.rho0);
-            S.e_pV[ew] = make_double2(P.p0 * (rho_h / P.rho0 - 1.0), V);
+            const double2 pV = make_double2(P.p0 * (rho_h / P.rho0 - 1.0), V);
+            S.e_pV[ew] = pV;
+            ghost_store(S, key__, i, S.e_pV, pV);
         }
     }
     __device__ SPHB_COLD void rows_cold(const StateView &S, const TileDesc &T, const OwnPre &pre, unsigned char *buf, int cap)
@@ -449,6 +464,8 @@ struct KgcK {
                 kgc_from_A(a11, a12, a21, a22, B.b11, B.b12, B.b21, B.b22);
                 S.e_b1[ew] = make_double2(B.b11, B.b12);
                 S.e_b2[ew] = make_double2(B.b21, B.b22);
+                ghost_store(S, key__, i, S.e_b1, make_double2(B.b11, B.b12));
+                ghost_store(S, key__, i, S.e_b2, make_double2(B.b21, B.b22));
             }
             S.B[i] = B;
         }
@@ -651,7 +668,9 @@ __device__ __forceinline__ void pressure_rows(const PhysParams &P, const StateVi
         if (i >= P.nf) {   // wall rows: force 0, velocity 0 (ph:958-962, 1405-1408)
             S.force[i] = make_double2(0.0, 0.0);
             S.vel_new[i] = make_double2(0.0, 0.0);
-            S.e_vn[ew] = S.wall_vel[i];   // what the continuity pass stages of a wall neighbour
+            const double2 wv = S.wall_vel[i];   // what the continuity pass stages of a wall neighbour
+            S.e_vn[ew] = wv;
+            ghost_store(S, key__, i, S.e_vn, wv);
             continue;
         }
         const double2 pi = s_xy[si];
@@ -697,6 +716,7 @@ __device__ __forceinline__ void pressure_rows(const PhysParams &P, const StateVi
         vn.y = vi.y + (fp.y + fy) / m_i * dt;
         S.vel_new[i] = vn;
         S.e_vn[ew] = vn;
+        ghost_store(S, key__, i, S.e_vn, vn);
         double2 x = S.pos[i];
         x.x += 0.5 * dt * vi.x;   // ph:863-864
         x.y += 0.5 * dt * vi.y;
@@ -849,7 +869,9 @@ struct ForceK {
                 S.force_prior[i] = make_double2(0.0, 0.0);
                 S.force[i] = make_double2(0.0, 0.0);
                 S.vel_new[i] = make_double2(0.0, 0.0);
-                S.e_vn[ew] = S.wall_vel[i];   // what the continuity pass reads of a wall neighbour (ph:1101-1102)
+                const double2 wv = S.wall_vel[i];   // what the continuity pass reads of a wall neighbour (ph:1101-1102)
+                S.e_vn[ew] = wv;
+                ghost_store(S, key__, i, S.e_vn, wv);
                 continue;
             }
             const double2 pi = s_xy[si];
@@ -943,6 +965,7 @@ struct ForceK {
             vn.y = vi.y + (fp.y + fy) / m_i * dt;
             S.vel_new[i] = vn;
             S.e_vn[ew] = vn;
+            ghost_store(S, key__, i, S.e_vn, vn);
             x.x += 0.5 * dt * vi.x;   // ph:863-864
             x.y += 0.5 * dt * vi.y;
             x.x += 0.5 * dt * vn.x;   // ph:1067-1068

@@ -66,13 +66,15 @@ struct StateView {
     const TileDesc *tiles;    // one descriptor per cell tile
     const int *ell_cnt;       // neighbours of the walker whose real entry is e
     const uint4 *ell_q;       // ell_q[(k / 8) * ell_stride + e]: eight 16-bit (slot | shift) entries
-    // entry-ordered mirrors (index = entry, valid for real entries): what the gather kernels stage with bulk
+    // entry-ordered mirrors (index = entry; ghost entries carry their particle's values): what the gather kernels stage with bulk
     // asynchronous copies instead of gathering it through ent_key (async_copy.cuh, ops_csr.cu)
     double2 *e_vel;           // velocity at list-build time (wall entry: wall velocity)      written by the list build
     double2 *e_w;             // (wall weight m / rho0 or -1 for fluid, 0)                     written by the list build
     double2 *e_pV;            // (half-step pressure, volume; volume < 0 marks a wall entry)  written by k_density
     double2 *e_b1, *e_b2;     // rows of B                                                     written by k_kgc
     double2 *e_vn;            // new velocity (wall entry: wall velocity)                      written by the force kernels
+    const int *ghost_ent;     // [2 i + kind - 1]: entry of particle i's ghost of that kind (validated against ent_key): the
+                              // producers above write the mirrors of a row's ghost entries as well (ghost_store)
     // device error flags (sphb_status.error_flags).  Once a flag is up the state-changing kernels of the step return
     // at once ("poisoned"): inside a replayed graph the state then stays where the last consistent step left it
     // until the host looks (sphb_ctx_run_dual, sphb_ctx_sync), instead of advancing on a truncated list.
