@@ -472,6 +472,7 @@ __device__ __forceinline__ int stencil_rank(int cx, int cxi, int ncx)
 // higher-kind entry first (list order = reverse insertion), first accepted entry wins.  Returns the
 // image shift of x_high as seen from the low particle, or kNoPair when the pair is not accepted.
 constexpr int kNoPair = 99;
+constexpr int kSurvCap = 96;   // survivors of the quick tests a warp buffers between the two passes of a general walk
 __device__ int replay_low_walk(double xl, double yl, int home_l, const Entries &E, double yh, int ncy,
                                const NbrParams &P)
 {
@@ -565,8 +566,8 @@ __device__ __forceinline__ int general_walk(const NbrParams &P, const TileDesc &
                                             const double2 *s_xy,
                                             const int *s_key, const double2 *__restrict__ snap,
                                             const int *__restrict__ cell_of, int ncy, int ew, int slot_i, int orow,
-                                            int cxi, unsigned short *row_sm, uint4 *ell_q, int *__restrict__ cnt,
-                                            int dummy)
+                                            int cxi, unsigned short *row_sm, int *surv, uint4 *ell_q,
+                                            int *__restrict__ cnt, int dummy)
 {
     const int lane = threadIdx.x & 31;
     const int ncx = P.ncx;
@@ -606,40 +607,31 @@ __device__ __forceinline__ int general_walk(const NbrParams &P, const TileDesc &
             total += se - sb;
         }
     }
-    int count = 0;
-    for (int base = 0; base < total; base += 32) {
-        const int t = base + lane;
-        bool acc = false;
-        int s = 0, m = 0;
-        if (t < total) {
-            int cx = 0, cy = 0, pre = 0;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                if (t >= pre && t < pre + rn[k]) {
-                    s = rb[k] + (t - pre);
-                    cx = rcx[k];
-                    cy = cyi + k / 3 - 1;
-                }
-                pre += rn[k];
-            }
-            const int rank_col = stencil_rank(cx, cxi, ncx);
-            const int key = s_key[s];   // entries are stored last-inserted first
-            const int j = key >> 3;
-            const bool low_fluid = j < P.n_fluid && j < i;
-            const double2 pe = s_xy[s];
-            // Quick reject.  In a channel of >= 6 columns every pairing of the two particles' entries (real / ghost,
-            // seen from either end) has the same minimum-image separation up to rounding (~1e-16 DL), so a candidate
-            // that is beyond the cut-off by more than that is in nobody's row whatever entry a walk meets first; the
-            // exact decisions below (dedup, replay of the lower index's walk) are kept for the ones in reach.
-            bool far = false;
-            if (ncx >= 6) {
-                double dxq = pi.x - pe.x;
-                if (dxq > P.half_DL) dxq -= P.DL;
-                else if (dxq < -P.half_DL) dxq += P.DL;
-                const double dyq = pi.y - pe.y;
-                far = dxq * dxq + dyq * dyq > P.rc2 * (1.0 + 1e-8);
-            }
-            if (j != i && !far && !(HALF && low_fluid)) {                          // nb:353
+    // Two passes, so that the lanes of the expensive pass are all busy.  Pass A runs over every candidate of the
+    // stencil: the cheap tests (own entry, lower fluid index of a half list, clearly out of reach) leave about a third,
+    // which a ballot compacts -- in walk order -- into the warp's survivor list.  Pass B makes the exact decisions
+    // (dedup by walk position, replay of the lower index's walk) for the survivors only and compacts the accepted
+    // ones into the row.  The list is flushed through pass B whenever it could overflow.
+    int count = 0, n_surv = 0;
+    auto decide_survivors = [&]() {
+        __syncwarp();
+        for (int base = 0; base < n_surv; base += 32) {
+            const int t = base + lane;
+            bool acc = false;
+            int s = 0, m = 0;
+            if (t < n_surv) {
+                const int code = surv[t];
+                s = code & 0xffff;
+                const int k = code >> 16;
+                int cx = cxi + (k % 3) - 1;
+                if (cx < 0) cx += ncx;
+                else if (cx >= ncx) cx -= ncx;
+                const int cy = cyi + k / 3 - 1;
+                const int rank_col = stencil_rank(cx, cxi, ncx);
+                const int key = s_key[s];   // entries are stored last-inserted first
+                const int j = key >> 3;
+                const bool low_fluid = j < P.n_fluid && j < i;
+                const double2 pe = s_xy[s];
                 const bool seam = (key & 4) || (low_fluid && i_multi);
                 if (!seam) {
                     acc = accept_entry(pi.x, pi.y, pe.x, pe.y, P, m);
@@ -656,10 +648,10 @@ __device__ __forceinline__ int general_walk(const NbrParams &P, const TileDesc &
                         // the pair is decided by j's walk: the first entry of j the walk meets carries it
                         bool first = true;
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            if (k == kind || E.cx[k] < 0) continue;
-                            const int rk = stencil_rank(E.cx[k], cxi, ncx);
-                            if (rk >= 0 && rk * 3 + (2 - k) < rank_cur) first = false;
+                        for (int q = 0; q < 3; ++q) {
+                            if (q == kind || E.cx[q] < 0) continue;
+                            const int rk = stencil_rank(E.cx[q], cxi, ncx);
+                            if (rk >= 0 && rk * 3 + (2 - q) < rank_cur) first = false;
                         }
                         if (first) {
                             const int sh = replay_low_walk(pj.x, pj.y, home_j, Ei, pi.y, ncy, P);
@@ -671,26 +663,67 @@ __device__ __forceinline__ int general_walk(const NbrParams &P, const TileDesc &
                     } else if (accept_entry(pi.x, pi.y, pe.x, pe.y, P, m)) {
                         bool dup = false;
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            if (k == kind || E.cx[k] < 0) continue;
-                            const int rk = stencil_rank(E.cx[k], cxi, ncx);
-                            if (rk >= 0 && rk * 3 + (2 - k) < rank_cur) {
+                        for (int q = 0; q < 3; ++q) {
+                            if (q == kind || E.cx[q] < 0) continue;
+                            const int rk = stencil_rank(E.cx[q], cxi, ncx);
+                            if (rk >= 0 && rk * 3 + (2 - q) < rank_cur) {
                                 int m2;
-                                dup |= accept_entry(pi.x, pi.y, E.x[k], pj.y, P, m2);
+                                dup |= accept_entry(pi.x, pi.y, E.x[q], pj.y, P, m2);
                             }
                         }
                         acc = !dup;
                     }
                 }
             }
+            const unsigned mask = __ballot_sync(0xffffffffu, acc);
+            if (acc) {
+                const int pos = count + __popc(mask & ((1u << lane) - 1u));
+                if (pos < P.ell_cap) row_sm[pos] = (unsigned short)ell_pack(s, m);
+            }
+            count += __popc(mask);
         }
-        const unsigned mask = __ballot_sync(0xffffffffu, acc);
-        if (acc) {
-            const int pos = count + __popc(mask & ((1u << lane) - 1u));
-            if (pos < P.ell_cap) row_sm[pos] = (unsigned short)ell_pack(s, m);
+        __syncwarp();
+        n_surv = 0;
+    };
+    for (int base = 0; base < total; base += 32) {
+        const int t = base + lane;
+        bool keep = false;
+        int code = 0;
+        if (t < total) {
+            int s = 0, kc = 0, pre = 0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                if (t >= pre && t < pre + rn[k]) {
+                    s = rb[k] + (t - pre);
+                    kc = k;
+                }
+                pre += rn[k];
+            }
+            const int key = s_key[s];
+            const int j = key >> 3;
+            const bool low_fluid = j < P.n_fluid && j < i;
+            // Quick reject.  In a channel of >= 6 columns every pairing of the two particles' entries (real / ghost,
+            // seen from either end) has the same minimum-image separation up to rounding (~1e-16 DL), so a candidate
+            // that is beyond the cut-off by more than that is in nobody's row whatever entry a walk meets first; the
+            // exact decisions of pass B (dedup, replay of the lower index's walk) are kept for the ones in reach.
+            bool far = false;
+            if (ncx >= 6) {
+                const double2 pe = s_xy[s];
+                double dxq = pi.x - pe.x;
+                if (dxq > P.half_DL) dxq -= P.DL;
+                else if (dxq < -P.half_DL) dxq += P.DL;
+                const double dyq = pi.y - pe.y;
+                far = dxq * dxq + dyq * dyq > P.rc2 * (1.0 + 1e-8);
+            }
+            keep = j != i && !far && !(HALF && low_fluid);                         // nb:353
+            code = s | (kc << 16);
         }
-        count += __popc(mask);
+        if (n_surv + 32 > kSurvCap) decide_survivors();
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) surv[n_surv + __popc(mask & ((1u << lane) - 1u))] = code;
+        n_surv += __popc(mask);
     }
+    decide_survivors();
     __syncwarp();
     const int nw = min((count + 7) >> 3, P.ell_cap >> 3);
     for (int w = lane; w < nw; w += 32) {
@@ -827,6 +860,7 @@ __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__re
     const int dummy = T.n_staged;
     const int lane = threadIdx.x & 31;
     __shared__ int gq[kTileThreads];   // own-entry indices of the queued general walkers
+    __shared__ int s_surv[kTileThreads / 32][kSurvCap];   // per warp: survivors between the passes of a general walk
     __shared__ int gq_n;
     if (threadIdx.x == 0) gq_n = 0;
     __syncthreads();
@@ -963,7 +997,7 @@ __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__re
                     else hi = mid;
                 }
                 const int n = general_walk<HALF>(P, T, s_cs, s_xy, s_key, snap, cell_of, ncy, w_ew, w_slot, w_orow, T.a + lo,
-                                                 row_sm, ell_q, cnt, dummy);
+                                                 row_sm, s_surv[threadIdx.x >> 5], ell_q, cnt, dummy);
                 if (lane == 0) {
                     t_full += n;
                     t_max = max(t_max, n);
