@@ -179,11 +179,11 @@ __device__ __forceinline__ double half_step_rho(double rho, double drho, double 
 // cp.async.bulk and signalled on an mbarrier (async_copy.cuh) -- no thread gathers through ent_key, and the
 // dependent-load chain that used to open every tile (descriptor -> ent_key -> field -> STS -> barrier) is gone.
 // The next tile's descriptor travels one tile further ahead in registers, the walkers' row heads one tile ahead.
-// Tiles on the periodic seam hold ghost entries, which have no mirror values: they are staged through ent_key as
-// before (stage_sync; first and last tile of a tile row).
+// Tiles on the periodic seam (first and last tile of a tile row) stage their wrap columns with the same copies: ghost
+// entries carry their particle's mirror values (ghost_store).
 //
 // A kernel K provides: kFields (16-byte fields per slot), bulk_fields(T), src(S, f), dummy(buf, cap, slot),
-// stage_sync(S, T, buf, cap) -> "holds wall entries", rows<PLAIN>(S, T, pre, buf, cap).
+// rows<PLAIN>(S, T, pre, buf, cap), rows_cold(...).
 // ================================================================================================
 // The seam-tile staging and the row loops of tiles with wall entries run for a few percent of the tiles.  A/B switch:
 // SPHB_COLD_INLINE=0 keeps them out of line (off the plain path's register allocation, at the price of a stack frame).
@@ -306,31 +306,6 @@ struct DensityK {
         field(buf, cap, 0)[slot] = make_double2(kDummyCoord, kDummyCoord);
         field(buf, cap, 1)[slot] = make_double2(-1.0, 0.0);
     }
-    __device__ SPHB_COLD int stage_sync(const StateView &S, const TileDesc &T, unsigned char *buf, int cap) const
-    {
-        double2 *s_xy = field(buf, cap, 0), *s_w = field(buf, cap, 1);
-        struct Rec {
-            double2 xy;
-            double m;
-            int j;
-        };
-        const PhysParams &Pr = P;
-        tile_stage_flat(
-            T,
-            [&](int e) {
-                Rec r;
-                r.j = S.ent_key[e] >> 3;
-                r.xy = S.ent_pos[e];
-                r.m = S.mass[r.j];
-                return r;
-            },
-            [&](int slot, const Rec &r) {
-                s_xy[slot] = r.xy;
-                s_w[slot] = make_double2(r.j < Pr.nf ? -1.0 : r.m * Pr.inv_rho0, 0.0);
-            });
-        if (threadIdx.x == 0) dummy(buf, cap, T.n_staged);
-        return 1;
-    }
     template <bool PLAIN>
     __device__ __forceinline__ void rows(const StateView &S, const TileDesc &T, const OwnPre &pre, unsigned char *buf, int cap)
     {
@@ -413,28 +388,6 @@ struct KgcK {
     {
         field(buf, cap, 0)[slot] = make_double2(kDummyCoord, kDummyCoord);
         field(buf, cap, 1)[slot] = make_double2(0.0, 0.0);
-    }
-    __device__ SPHB_COLD int stage_sync(const StateView &S, const TileDesc &T, unsigned char *buf, int cap) const
-    {
-        double2 *s_xy = field(buf, cap, 0), *s_pV = field(buf, cap, 1);
-        struct Rec {
-            double2 xy;
-            double V;
-        };
-        tile_stage_flat(
-            T,
-            [&](int e) {
-                Rec r;
-                r.xy = S.ent_pos[e];
-                r.V = S.Vol[S.ent_key[e] >> 3];
-                return r;
-            },
-            [&](int slot, const Rec &r) {
-                s_xy[slot] = r.xy;
-                s_pV[slot] = make_double2(0.0, r.V);
-            });
-        if (threadIdx.x == 0) dummy(buf, cap, T.n_staged);
-        return 1;
     }
     template <bool PLAIN>
     __device__ __forceinline__ void rows(const StateView &S, const TileDesc &T, const OwnPre &pre, unsigned char *buf, int cap)
@@ -816,46 +769,6 @@ struct ForceK {
 #pragma unroll
         for (int f = 1; f < 5; ++f) field(buf, cap, f)[slot] = make_double2(0.0, 0.0);
     }
-    __device__ SPHB_COLD int stage_sync(const StateView &S, const TileDesc &T, unsigned char *buf, int cap) const
-    {
-        double2 *s_xy = field(buf, cap, 0), *s_v = field(buf, cap, 1), *s_pV = field(buf, cap, 2), *s_b1 = field(buf, cap, 3),
-                *s_b2 = field(buf, cap, 4);
-        struct Rec {
-            double2 xy, v;
-            double4 B;
-            double V, rho, drho;
-            int j;
-        };
-        const PhysParams &Pr = P;
-        const double dt_ = dt;
-        tile_stage_flat(
-            T,
-            [&](int e) {
-                Rec r;
-                r.j = S.ent_key[e] >> 3;
-                r.xy = S.ent_pos[e];
-                r.V = S.Vol[r.j];
-                r.v = (r.j < Pr.nf ? S.vel : S.wall_vel)[r.j];   // a wall entry stages its wall velocity
-                r.rho = S.rho[r.j];                              // (wall rows hold valid values too; unused)
-                r.drho = S.drho_dt[r.j];
-                r.B = *reinterpret_cast<const double4 *>(&S.B[r.j]);
-                return r;
-            },
-            [&](int slot, const Rec &r) {
-                s_xy[slot] = r.xy;
-                s_v[slot] = r.v;
-                if (r.j < Pr.nf) {
-                    const double rho_h = half_step_rho(r.rho, r.drho, dt_, Pr.rho0);
-                    s_pV[slot] = make_double2(Pr.p0 * (rho_h / Pr.rho0 - 1.0), r.V);   // ph:862
-                    s_b1[slot] = make_double2(r.B.x, r.B.y);
-                    s_b2[slot] = make_double2(r.B.z, r.B.w);
-                } else {
-                    s_pV[slot] = make_double2(0.0, -r.V);
-                }
-            });
-        if (threadIdx.x == 0) dummy(buf, cap, T.n_staged);
-        return 1;
-    }
     template <bool PLAIN>
     __device__ __forceinline__ void rows(const StateView &S, const TileDesc &T, const OwnPre &pre, unsigned char *buf, int cap)
     {
@@ -1084,33 +997,6 @@ struct ContinuityK {
         field(buf, cap, 0)[slot] = make_double2(kDummyCoord, kDummyCoord);
         field(buf, cap, 1)[slot] = make_double2(0.0, 0.0);
         field(buf, cap, 2)[slot] = make_double2(0.0, 0.0);
-    }
-    __device__ SPHB_COLD int stage_sync(const StateView &S, const TileDesc &T, unsigned char *buf, int cap) const
-    {
-        double2 *s_xy = field(buf, cap, 0), *s_v = field(buf, cap, 1), *s_pV = field(buf, cap, 2);
-        struct Rec {
-            double2 xy, v;
-            double V;
-            int j;
-        };
-        const PhysParams &Pr = P;
-        tile_stage_flat(
-            T,
-            [&](int e) {
-                Rec r;
-                r.j = S.ent_key[e] >> 3;
-                r.xy = S.ent_pos[e];
-                r.V = S.Vol[r.j];
-                r.v = (r.j < Pr.nf ? S.vel_new : S.wall_vel)[r.j];
-                return r;
-            },
-            [&](int slot, const Rec &r) {
-                s_xy[slot] = r.xy;
-                s_v[slot] = r.v;
-                s_pV[slot] = make_double2(0.0, r.j < Pr.nf ? r.V : -r.V);
-            });
-        if (threadIdx.x == 0) dummy(buf, cap, T.n_staged);
-        return 1;
     }
     template <bool PLAIN>
     __device__ __forceinline__ void rows(const StateView &S, const TileDesc &T, const OwnPre &pre, unsigned char *buf, int cap)
