@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
@@ -96,6 +97,52 @@ enum : int { kErrCsrCap = 1, kErrCellCap = 2, kErrSeenCap = 4, kErrNonFinite = 8
 
 // ------------------------------------------------------------------------------------------------
 // cell grid descriptor, lives in device memory, written by the grid-setup kernel (nb:244-258)
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+, CUDA graphs keep it as a programmatic edge): a kernel launched with
+// SPHB_LAUNCH_PDL may be scheduled while its predecessor in the stream is still draining -- its CTAs become resident as
+// the predecessor's finish -- and waits in pdl_wait() (griddepcontrol.wait) for the predecessor's completion and
+// memory flush before it touches anything.  Every kernel launched this way calls pdl_wait() FIRST (then pdl_trigger()
+// for its own successor); a kernel launched the ordinary way returns from both at once.  What it buys is the launch latency and the CTA ramp-up of each of the
+// eleven kernels of a step.  SPHB_PDL=0 in the environment turns it off (A/B runs).
+#ifdef SPHB_CPUSIM
+__device__ inline void pdl_wait() {}
+__device__ inline void pdl_trigger() {}
+#define SPHB_LAUNCH_PDL(kern, grid, block, smem, st, ...) cpusim::launch(kern, grid, block, smem, st, __VA_ARGS__)
+#else
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// lets the NEXT kernel of the stream be scheduled once every CTA of this one has got here (or exited); without it the
+// next kernel is launched only when this one has completed.  Issued right behind pdl_wait(): the dependent's CTAs then
+// take the slots this kernel's CTAs vacate, and wait in their own pdl_wait() for its completion.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+inline bool pdl_enabled()
+{
+    static int on = -1;
+    if (on < 0) {
+        const char *env = std::getenv("SPHB_PDL");
+        on = (env && env[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);   // (errors surface in the caller's cudaGetLastError)
+}
+#define SPHB_LAUNCH_PDL(kern, grid, block, smem, st, ...) ::sphb::launch_pdl(kern, dim3(grid), dim3(block), smem, st, __VA_ARGS__)
+#endif
+
 // ------------------------------------------------------------------------------------------------
 struct GridDesc {
     double y_min, y_max;

@@ -258,6 +258,8 @@ __global__ void __launch_bounds__(kBlock) k_bin_count(const double2 *__restrict_
                                                      int *__restrict__ cell_of, int *__restrict__ cell_cnt,
                                                      unsigned int *ghost_anomaly, const int *flags)
 {
+    pdl_wait();
+    pdl_trigger();
     bin_count_body(pos, P, g, snap, cell_of, cell_cnt, ghost_anomaly, flags);
 }
 __global__ void __launch_bounds__(kBlock) k_bin_count_batch(const NbrChan *__restrict__ chan)
@@ -300,6 +302,8 @@ __global__ void __launch_bounds__(kBlock) k_scatter(const double2 *__restrict__ 
                                                    const int *__restrict__ cell_start, int *__restrict__ cell_fill,
                                                    int *__restrict__ tmp_key, double2 *__restrict__ tmp_pos, const int *flags)
 {
+    pdl_wait();
+    pdl_trigger();
     scatter_body(pos, P, g, cell_start, cell_fill, tmp_key, tmp_pos, flags);
 }
 __global__ void __launch_bounds__(kBlock) k_scatter_batch(const NbrChan *__restrict__ chan)
@@ -1030,6 +1034,8 @@ __global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, cons
                                                            int *__restrict__ cnt, int *__restrict__ totals,
                                                            int *__restrict__ flags, int cap)
 {
+    pdl_wait();
+    pdl_trigger();
     walk_tile_body<HALF>(P, g, tiles, M, W, tile_w, cell_start, snap, cell_of, ell_q, cnt, totals, flags, cap);
 }
 // full lists only (the half list is the stateless MEX export)
@@ -1405,8 +1411,8 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
     }
     {
         ProfScope ps(prof, kPfNbrBin, st);
-        k_bin_count<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.snap.as<double2>(), w.cell_of.as<int>(), cell_cnt,
-                                                     &g->ghost_anomaly, flags);
+        SPHB_LAUNCH_PDL(k_bin_count, grid_for(nt), kBlock, 0, st, pos, P, g, w.snap.as<double2>(), w.cell_of.as<int>(), cell_cnt,
+                        &g->ghost_anomaly, flags);
     }
     nl += 1;
     {
@@ -1416,8 +1422,8 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
     }
     {
         ProfScope ps(prof, kPfNbrScatter, st);
-        k_scatter<<<grid_for(nt), kBlock, 0, st>>>(pos, P, g, w.cell_start.as<int>(), cell_fill, w.tmp_key.as<int>(),
-                                                   w.tmp_pos.as<double2>(), flags);
+        SPHB_LAUNCH_PDL(k_scatter, grid_for(nt), kBlock, 0, st, pos, P, g, w.cell_start.as<int>(), cell_fill, w.tmp_key.as<int>(),
+                        w.tmp_pos.as<double2>(), flags);
     }
     nl += 1;
     WalkSetup W;
@@ -1451,9 +1457,9 @@ int neighbor_build(NeighborWork &w, const double2 *pos, bool half_only, bool exa
                 P, g, w.tiles.as<TileDesc>(), BuildMirrors(), W, w.tile_w, w.cell_start.as<int>(), w.snap.as<double2>(),
                 w.cell_of.as<int>(), w.ell_q.as<uint4>(), w.ell_cnt.as<int>(), w.totals.as<int>(), flags, w.tile_cap);
         else
-            k_walk_tile<false><<<w.n_tiles, kTileThreads, smem, st>>>(
-                P, g, w.tiles.as<TileDesc>(), w.mirrors, W, w.tile_w, w.cell_start.as<int>(), w.snap.as<double2>(),
-                w.cell_of.as<int>(), w.ell_q.as<uint4>(), w.ell_cnt.as<int>(), w.totals.as<int>(), flags, w.tile_cap);
+            SPHB_LAUNCH_PDL(k_walk_tile<false>, w.n_tiles, kTileThreads, smem, st, P, g, w.tiles.as<TileDesc>(), w.mirrors, W,
+                            w.tile_w, w.cell_start.as<int>(), w.snap.as<double2>(), w.cell_of.as<int>(), w.ell_q.as<uint4>(),
+                            w.ell_cnt.as<int>(), w.totals.as<int>(), flags, w.tile_cap);
         nl += 1;
         if (exact) {   // (not inside a stream capture)
             const cudaError_t le = cudaGetLastError();

@@ -369,6 +369,8 @@ __device__ __forceinline__ void density_tiles(PhysParams P, const StateView &S, 
 #endif
 __global__ void __launch_bounds__(kTileThreads, SPHB_DENS_MINCTAS) k_density(PhysParams P, StateView S, const DevScalars *sc)
 {
+    pdl_wait();
+    pdl_trigger();
     density_tiles(P, S, sc, blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(kTileThreads, SPHB_DENS_MINCTAS) k_density_batch(const BatchChan *__restrict__ chan)
@@ -442,6 +444,8 @@ __device__ __forceinline__ void kgc_tiles(PhysParams P, const StateView &S, unsi
 #endif
 __global__ void __launch_bounds__(kTileThreads, SPHB_KGC_MINCTAS) k_kgc(PhysParams P, StateView S)
 {
+    pdl_wait();
+    pdl_trigger();
     kgc_tiles(P, S, blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(kTileThreads, SPHB_KGC_MINCTAS) k_kgc_batch(const BatchChan *__restrict__ chan)
@@ -911,6 +915,8 @@ __device__ __forceinline__ void force_fused_tiles(PhysParams P, const StateView 
 __global__ void __launch_bounds__(kTileThreads, SPHB_FORCE_MINCTAS) k_force_fused(PhysParams P, StateView S,
                                                                                  const DevScalars *sc, int add_gravity)
 {
+    pdl_wait();
+    pdl_trigger();
     force_fused_tiles(P, S, sc, add_gravity, blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(kTileThreads, SPHB_FORCE_MINCTAS) k_force_fused_batch(const BatchChan *__restrict__ chan,
@@ -924,6 +930,8 @@ __global__ void __launch_bounds__(kTileThreads, SPHB_FORCE_MINCTAS) k_force_fuse
 // fused force kernel on the same stream)
 __global__ void k_publish_dt(PhysParams P, DevScalars *sc, double remain, double fixed_dt)
 {
+    pdl_wait();
+    pdl_trigger();
     sc->dt = device_dt(P, sc, remain, fixed_dt);
     sc->vmax_bits = 0ull;
 }
@@ -1138,6 +1146,8 @@ __device__ __forceinline__ void continuity_tiles(PhysParams P, const StateView &
 __global__ void __launch_bounds__(kTileThreads, SPHB_CONT_MINCTAS) k_continuity(PhysParams P, StateView S, DevScalars *sc,
                                                                                int do_wrap, int advance_clock, GridFuse F)
 {
+    pdl_wait();
+    pdl_trigger();
     continuity_tiles(P, S, sc, do_wrap, advance_clock, F, blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(kTileThreads, SPHB_CONT_MINCTAS) k_continuity_batch(const BatchChan *__restrict__ chan, int do_wrap,
@@ -1290,6 +1300,8 @@ __device__ __forceinline__ void wall_shear_tiles(PhysParams P, const StateView &
 }
 __global__ void __launch_bounds__(kTileThreads) k_wall_shear(PhysParams P, StateView S, double *partials, DevScalars *sc)
 {
+    pdl_wait();
+    pdl_trigger();
     wall_shear_tiles(P, S, partials, sc, blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(kTileThreads, 6) k_wall_shear_batch(const BatchChan *__restrict__ chan)
@@ -1400,14 +1412,14 @@ int csr_configure(int tile_cap)
 int csr_density(const PhysParams &P, const StateView &S, const DevScalars *sc, cudaStream_t st)
 {
     const size_t sm = (size_t)S.tile_cap * kDensitySlot;
-    k_density<<<persistent_ctas(k_density, sm, S.n_tiles), kTileThreads, sm, st>>>(P, S, sc);
+    SPHB_LAUNCH_PDL(k_density, persistent_ctas(k_density, sm, S.n_tiles), kTileThreads, sm, st, P, S, sc);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
 int csr_kgc(const PhysParams &P, const StateView &S, cudaStream_t st)
 {
     const size_t sm = (size_t)S.tile_cap * kKgcSlot;
-    k_kgc<<<persistent_ctas(k_kgc, sm, S.n_tiles), kTileThreads, sm, st>>>(P, S);
+    SPHB_LAUNCH_PDL(k_kgc, persistent_ctas(k_kgc, sm, S.n_tiles), kTileThreads, sm, st, P, S);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1439,8 +1451,8 @@ int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool
                    const GridFuse &F, cudaStream_t st)
 {
     const size_t sm = (size_t)S.tile_cap * kContinuitySlot;
-    k_continuity<<<persistent_ctas(k_continuity, sm, S.n_tiles), kTileThreads, sm, st>>>(P, S, sc, wrap ? 1 : 0,
-                                                                                         advance_clock ? 1 : 0, F);
+    SPHB_LAUNCH_PDL(k_continuity, persistent_ctas(k_continuity, sm, S.n_tiles), kTileThreads, sm, st, P, S, sc, wrap ? 1 : 0,
+                    advance_clock ? 1 : 0, F);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1448,7 +1460,7 @@ int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool
 // outer step, which evaluates the half-step pressures with it
 int csr_publish_dt(const PhysParams &P, DevScalars *sc, double remain, double fixed_dt, cudaStream_t st)
 {
-    k_publish_dt<<<1, 1, 0, st>>>(P, sc, remain, fixed_dt);
+    SPHB_LAUNCH_PDL(k_publish_dt, 1, 1, 0, st, P, sc, remain, fixed_dt);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1469,7 +1481,7 @@ int csr_dual_end(DevScalars *sc, cudaStream_t st)
 int csr_force_fused(const PhysParams &P, const StateView &S, const DevScalars *sc, bool add_gravity, cudaStream_t st)
 {
     const size_t sm = (size_t)S.tile_cap * kForceSlot;
-    k_force_fused<<<persistent_ctas(k_force_fused, sm, S.n_tiles), kTileThreads, sm, st>>>(P, S, sc, add_gravity ? 1 : 0);
+    SPHB_LAUNCH_PDL(k_force_fused, persistent_ctas(k_force_fused, sm, S.n_tiles), kTileThreads, sm, st, P, S, sc, add_gravity ? 1 : 0);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1500,7 +1512,7 @@ static unsigned shear_ctas(unsigned n_tiles, int ncx, int tile_w)
 }
 int csr_wall_shear(const PhysParams &P, const StateView &S, DevScalars *sc, double *partials, cudaStream_t st)
 {
-    k_wall_shear<<<shear_ctas(S.n_tiles, S.ncx, S.tile_w), kTileThreads, (size_t)S.tile_cap * kShearSlot, st>>>(P, S, partials, sc);
+    SPHB_LAUNCH_PDL(k_wall_shear, shear_ctas(S.n_tiles, S.ncx, S.tile_w), kTileThreads, (size_t)S.tile_cap * kShearSlot, st, P, S, partials, sc);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }

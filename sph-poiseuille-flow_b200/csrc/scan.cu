@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles(const int *__restrict
                                                           int *__restrict__ tile_totals, size_t n,
                                                           int *__restrict__ total_out)
 {
+    pdl_wait();
+    pdl_trigger();
     scan_tiles_body(in, out, tile_totals, n, total_out);
 }
 __global__ void __launch_bounds__(kScanThreads) scan_tiles_batch(const ScanChan *__restrict__ chan, size_t n)
@@ -117,6 +119,8 @@ __device__ __forceinline__ void scan_finish_body(int *__restrict__ out, const in
 __global__ void __launch_bounds__(kScanThreads) scan_finish(int *__restrict__ out, const int *__restrict__ tile_totals,
                                                            size_t n, int *__restrict__ total_out)
 {
+    pdl_wait();
+    pdl_trigger();
     scan_finish_body(out, tile_totals, n, total_out);
 }
 __global__ void __launch_bounds__(kScanThreads) scan_finish_batch(const ScanChan *__restrict__ chan, size_t n)
@@ -138,8 +142,8 @@ int exclusive_scan_i32(const int *in, int *out, size_t n, DevBuf &tmp, int *tota
     const size_t n_tiles = (n + kTile - 1) / kTile;
     SPHB_TRY(tmp.reserve(n_tiles * sizeof(int)));
     int *totals = tmp.as<int>();
-    scan_tiles<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(in, out, totals, n, total_out_dev);
-    if (n_tiles > 1) scan_finish<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(out, totals, n, total_out_dev);
+    SPHB_LAUNCH_PDL(scan_tiles, (unsigned)n_tiles, kScanThreads, 0, st, in, out, totals, n, total_out_dev);
+    if (n_tiles > 1) SPHB_LAUNCH_PDL(scan_finish, (unsigned)n_tiles, kScanThreads, 0, st, out, totals, n, total_out_dev);
     if (launches) *launches += (n_tiles > 1) ? 2 : 1;
     SPHB_CUDA(cudaGetLastError());
     return 0;
