@@ -103,10 +103,15 @@ enum : int { kErrCsrCap = 1, kErrCellCap = 2, kErrSeenCap = 4, kErrNonFinite = 8
 // the predecessor's finish -- and waits in pdl_wait() (griddepcontrol.wait) for the predecessor's completion and
 // memory flush before it touches anything.  Every kernel launched this way calls pdl_wait() FIRST (then pdl_trigger()
 // for its own successor); a kernel launched the ordinary way returns from both at once.  What it buys is the launch latency and the CTA ramp-up of each of the
-// eleven kernels of a step.  SPHB_PDL=0 in the environment turns it off (A/B runs).
+// eleven kernels of a step.  MEASURED (r2 calls 28 / 29, 489 600 particles, replayed graph): with the trigger at the
+// top of every kernel the step is SLOWER, 0.395 against 0.365 ms (the successor's waiting CTAs share the SMs with the
+// tail of the running kernel); with the trigger behind the work, or without one, 0.365 against 0.365-0.367 ms: a
+// replayed graph has no launch latency left to hide.  So it is OFF unless SPHB_PDL=1 is set in the environment, and
+// the kernels trigger behind their work (SPHB_PDL_TRIGGER=2).
 #ifdef SPHB_CPUSIM
 __device__ inline void pdl_wait() {}
-__device__ inline void pdl_trigger() {}
+__device__ inline void pdl_trigger_top() {}
+__device__ inline void pdl_trigger_end() {}
 #define SPHB_LAUNCH_PDL(kern, grid, block, smem, st, ...) cpusim::launch(kern, grid, block, smem, st, __VA_ARGS__)
 #else
 #ifdef __CUDACC__
@@ -115,13 +120,21 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // next kernel is launched only when this one has completed.  Issued right behind pdl_wait(): the dependent's CTAs then
 // take the slots this kernel's CTAs vacate, and wait in their own pdl_wait() for its completion.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// where a kernel issues it: at its top (SPHB_PDL_TRIGGER=1: the successor's CTAs take every slot this kernel vacates) or
+// behind its work (SPHB_PDL_TRIGGER=2: only the successor's launch latency is hidden); 0: never (the successor is
+// launched when this kernel has completed)
+#ifndef SPHB_PDL_TRIGGER
+#define SPHB_PDL_TRIGGER 2
+#endif
+__device__ __forceinline__ void pdl_trigger_top() { if (SPHB_PDL_TRIGGER == 1) pdl_trigger(); }
+__device__ __forceinline__ void pdl_trigger_end() { if (SPHB_PDL_TRIGGER == 2) pdl_trigger(); }
 #endif
 inline bool pdl_enabled()
 {
     static int on = -1;
     if (on < 0) {
         const char *env = std::getenv("SPHB_PDL");
-        on = (env && env[0] == '0') ? 0 : 1;
+        on = (env && env[0] == '1') ? 1 : 0;   // off unless asked for: measured no gain (below)
     }
     return on != 0;
 }

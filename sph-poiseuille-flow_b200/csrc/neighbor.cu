@@ -259,8 +259,9 @@ __global__ void __launch_bounds__(kBlock) k_bin_count(const double2 *__restrict_
                                                      unsigned int *ghost_anomaly, const int *flags)
 {
     pdl_wait();
-    pdl_trigger();
+    pdl_trigger_top();
     bin_count_body(pos, P, g, snap, cell_of, cell_cnt, ghost_anomaly, flags);
+    pdl_trigger_end();
 }
 __global__ void __launch_bounds__(kBlock) k_bin_count_batch(const NbrChan *__restrict__ chan)
 {
@@ -303,8 +304,9 @@ __global__ void __launch_bounds__(kBlock) k_scatter(const double2 *__restrict__ 
                                                    int *__restrict__ tmp_key, double2 *__restrict__ tmp_pos, const int *flags)
 {
     pdl_wait();
-    pdl_trigger();
+    pdl_trigger_top();
     scatter_body(pos, P, g, cell_start, cell_fill, tmp_key, tmp_pos, flags);
+    pdl_trigger_end();
 }
 __global__ void __launch_bounds__(kBlock) k_scatter_batch(const NbrChan *__restrict__ chan)
 {
@@ -1035,8 +1037,9 @@ __global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, cons
                                                            int *__restrict__ flags, int cap)
 {
     pdl_wait();
-    pdl_trigger();
+    pdl_trigger_top();
     walk_tile_body<HALF>(P, g, tiles, M, W, tile_w, cell_start, snap, cell_of, ell_q, cnt, totals, flags, cap);
+    pdl_trigger_end();
 }
 // full lists only (the half list is the stateless MEX export)
 __global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile_batch(const NbrChan *__restrict__ chan)

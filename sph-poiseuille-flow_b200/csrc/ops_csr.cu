@@ -370,8 +370,9 @@ __device__ __forceinline__ void density_tiles(PhysParams P, const StateView &S, 
 __global__ void __launch_bounds__(kTileThreads, SPHB_DENS_MINCTAS) k_density(PhysParams P, StateView S, const DevScalars *sc)
 {
     pdl_wait();
-    pdl_trigger();
+    pdl_trigger_top();
     density_tiles(P, S, sc, blockIdx.x, gridDim.x);
+    pdl_trigger_end();
 }
 __global__ void __launch_bounds__(kTileThreads, SPHB_DENS_MINCTAS) k_density_batch(const BatchChan *__restrict__ chan)
 {
@@ -445,8 +446,9 @@ __device__ __forceinline__ void kgc_tiles(PhysParams P, const StateView &S, unsi
 __global__ void __launch_bounds__(kTileThreads, SPHB_KGC_MINCTAS) k_kgc(PhysParams P, StateView S)
 {
     pdl_wait();
-    pdl_trigger();
+    pdl_trigger_top();
     kgc_tiles(P, S, blockIdx.x, gridDim.x);
+    pdl_trigger_end();
 }
 __global__ void __launch_bounds__(kTileThreads, SPHB_KGC_MINCTAS) k_kgc_batch(const BatchChan *__restrict__ chan)
 {
@@ -916,8 +918,9 @@ __global__ void __launch_bounds__(kTileThreads, SPHB_FORCE_MINCTAS) k_force_fuse
                                                                                  const DevScalars *sc, int add_gravity)
 {
     pdl_wait();
-    pdl_trigger();
+    pdl_trigger_top();
     force_fused_tiles(P, S, sc, add_gravity, blockIdx.x, gridDim.x);
+    pdl_trigger_end();
 }
 __global__ void __launch_bounds__(kTileThreads, SPHB_FORCE_MINCTAS) k_force_fused_batch(const BatchChan *__restrict__ chan,
                                                                                        int add_gravity)
@@ -931,9 +934,10 @@ __global__ void __launch_bounds__(kTileThreads, SPHB_FORCE_MINCTAS) k_force_fuse
 __global__ void k_publish_dt(PhysParams P, DevScalars *sc, double remain, double fixed_dt)
 {
     pdl_wait();
-    pdl_trigger();
+    pdl_trigger_top();
     sc->dt = device_dt(P, sc, remain, fixed_dt);
     sc->vmax_bits = 0ull;
+    pdl_trigger_end();
 }
 // Device-side dual-criteria scheduler (README.md:61-65 of the reference; its constants are those of m:519-527 split
 // by what they bound): the outer step from the advection, viscous and body-force criteria, the first substep from
@@ -1147,8 +1151,9 @@ __global__ void __launch_bounds__(kTileThreads, SPHB_CONT_MINCTAS) k_continuity(
                                                                                int do_wrap, int advance_clock, GridFuse F)
 {
     pdl_wait();
-    pdl_trigger();
+    pdl_trigger_top();
     continuity_tiles(P, S, sc, do_wrap, advance_clock, F, blockIdx.x, gridDim.x);
+    pdl_trigger_end();
 }
 __global__ void __launch_bounds__(kTileThreads, SPHB_CONT_MINCTAS) k_continuity_batch(const BatchChan *__restrict__ chan, int do_wrap,
                                                                   int advance_clock, int fuse_grid)
@@ -1301,8 +1306,9 @@ __device__ __forceinline__ void wall_shear_tiles(PhysParams P, const StateView &
 __global__ void __launch_bounds__(kTileThreads) k_wall_shear(PhysParams P, StateView S, double *partials, DevScalars *sc)
 {
     pdl_wait();
-    pdl_trigger();
+    pdl_trigger_top();
     wall_shear_tiles(P, S, partials, sc, blockIdx.x, gridDim.x);
+    pdl_trigger_end();
 }
 __global__ void __launch_bounds__(kTileThreads, 6) k_wall_shear_batch(const BatchChan *__restrict__ chan)
 {

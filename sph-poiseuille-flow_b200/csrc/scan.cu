@@ -76,8 +76,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles(const int *__restrict
                                                           int *__restrict__ total_out)
 {
     pdl_wait();
-    pdl_trigger();
+    pdl_trigger_top();
     scan_tiles_body(in, out, tile_totals, n, total_out);
+    pdl_trigger_end();
 }
 __global__ void __launch_bounds__(kScanThreads) scan_tiles_batch(const ScanChan *__restrict__ chan, size_t n)
 {
@@ -120,8 +121,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_finish(int *__restrict__ ou
                                                            size_t n, int *__restrict__ total_out)
 {
     pdl_wait();
-    pdl_trigger();
+    pdl_trigger_top();
     scan_finish_body(out, tile_totals, n, total_out);
+    pdl_trigger_end();
 }
 __global__ void __launch_bounds__(kScanThreads) scan_finish_batch(const ScanChan *__restrict__ chan, size_t n)
 {
