@@ -353,8 +353,6 @@ struct ScanChan {
     int *total_out;     // may be NULL
 };
 size_t scan_workspace_ints(size_t n);
-int *scan_totals(const DevBuf &ws);     // where the tile totals of a scan live inside its workspace
-int scan_reserve(DevBuf &ws, size_t n); // grow the workspace (a new allocation starts zeroed)
 int exclusive_scan_i32_batch(const ScanChan *chan_dev, int n_chan, size_t n, cudaStream_t st, long long *launches);
 
 // batched list build over an ensemble of channels (neighbor.cu; used by batch.cu)

@@ -1526,7 +1526,7 @@ int neighbor_batch_fill(NeighborWork &w, const double2 *pos, void *host_record, 
     if (w.slab) return set_error("SPHB:batch", "slabs of a sharded channel cannot be batched");
     if (!w.grid_armed || !w.ell_q.p || !w.tiles.p)
         return set_error("SPHB:batch", "every channel needs its first (exact) list build before it joins a batch");
-    SPHB_TRY(scan_reserve(w.scan_tmp, (size_t)w.cell_cap));
+    SPHB_TRY(w.scan_tmp.reserve(scan_workspace_ints((size_t)w.cell_cap) * sizeof(int)));
     NbrChan c;
     c.P = make_params(w);
     c.pos = pos;
@@ -1552,7 +1552,7 @@ int neighbor_batch_fill(NeighborWork &w, const double2 *pos, void *host_record, 
     std::memcpy(host_record, &c, sizeof(NbrChan));
     host_scan->in = c.cell_cnt;
     host_scan->out = c.cell_start;
-    host_scan->tile_totals = scan_totals(w.scan_tmp);
+    host_scan->tile_totals = w.scan_tmp.as<int>();
     host_scan->total_out = &c.g->n_entries;
     return 0;
 }

@@ -6,8 +6,6 @@
 // Used for cell starts (N1), half-pair and CSR row pointers (N6) and the cell sort of particles (S1).
 #include "common.cuh"
 
-#include <algorithm>
-
 namespace sphb {
 
 namespace {
@@ -15,10 +13,6 @@ namespace {
 constexpr int kScanThreads = 1024;
 constexpr int kItems = 4;
 constexpr int kTile = kScanThreads * kItems;
-// workspace: [kOnePassMax flags | ticket | pad][tile totals ...] -- the flags of the one-pass form live in a region of
-// their own that no other scan writes, zeroed when the workspace is (re)allocated (scan_reserve)
-constexpr int kOnePassMax = 256;
-constexpr int kWsHeader = 512;
 
 __device__ __forceinline__ int warp_inclusive_scan(int v)
 {
@@ -92,76 +86,6 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_batch(const ScanChan 
     scan_tiles_body(c.in, c.out, c.tile_totals, n, c.total_out);
 }
 
-// ONE launch when every tile's CTA is resident at once (n_tiles <= the SM count; the cell grid of a 490 000-particle
-// channel is 19 tiles): a CTA scans its tile in registers, publishes the tile total behind a flag, waits for the flags
-// of the tiles before it (they never wait for a later one), sums their totals and writes its elements with the offset
-// already added.  The last CTA to finish re-arms the flags.  ws: [n_tiles totals | n_tiles flags | ticket], zeroed when
-// it is allocated.
-__global__ void __launch_bounds__(kScanThreads) scan_one_pass(const int *__restrict__ in, int *__restrict__ out, int *ws,
-                                                             size_t n, int *__restrict__ total_out)
-{
-    pdl_wait();
-    __shared__ int total_sh, off_sh;
-    __shared__ int warp_part[32];
-    const unsigned nt = gridDim.x, b = blockIdx.x;
-    volatile int *totals = ws + kWsHeader, *flag = ws;
-    const size_t base = (size_t)b * kTile + (size_t)threadIdx.x * kItems;
-    int v[kItems];
-    int sum = 0;
-#pragma unroll
-    for (int k = 0; k < kItems; ++k) {
-        v[k] = (base + k < n) ? in[base + k] : 0;
-        sum += v[k];
-    }
-    int pre = block_exclusive_scan(sum, &total_sh);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        totals[b] = total_sh;
-        __threadfence();
-        flag[b] = 1;
-    }
-    int part = 0;
-    for (unsigned i = threadIdx.x; i < b; i += kScanThreads) {
-        while (flag[i] == 0) {
-        }
-        __threadfence();
-        part += totals[i];
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = part;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        int t = warp_part[threadIdx.x];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
-        if (threadIdx.x == 0) off_sh = t;
-    }
-    __syncthreads();
-    const int off = off_sh;
-    pre += off;
-#pragma unroll
-    for (int k = 0; k < kItems; ++k) {
-        if (base + k < n) out[base + k] = pre;
-        pre += v[k];
-    }
-    if (b == nt - 1 && threadIdx.x == 0) {
-        const int total = off + total_sh;
-        out[n] = total;
-        if (total_out) *total_out = total;
-    }
-    // re-arm: the last CTA to finish clears the flags (every CTA has read what it needed before its ticket)
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(ws + kOnePassMax, 1) == (int)nt - 1) {
-            for (unsigned i = 0; i < nt; ++i) flag[i] = 0;
-            ws[kOnePassMax] = 0;
-        }
-    }
-    pdl_trigger_end();
-}
-
 // Every tile sums the totals of the tiles before it (a few hundred values at most) and adds the offset
 // to its elements; the last tile also writes the grand total.  No separate "scan of the totals" launch.
 __device__ __forceinline__ void scan_finish_body(int *__restrict__ out, const int *__restrict__ tile_totals, size_t n,
@@ -209,17 +133,6 @@ __global__ void __launch_bounds__(kScanThreads) scan_finish_batch(const ScanChan
 
 }  // namespace
 
-// tiles of the one-pass form: every CTA (1024 threads) must be resident at once -- one per SM
-static size_t one_pass_limit()
-{
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-        (void)cudaGetLastError();
-        return 0;
-    }
-    return sms > 0 ? std::min((size_t)sms, (size_t)kOnePassMax) : 0;
-}
-
 int exclusive_scan_i32(const int *in, int *out, size_t n, DevBuf &tmp, int *total_out_dev, cudaStream_t st,
                        long long *launches)
 {
@@ -229,17 +142,8 @@ int exclusive_scan_i32(const int *in, int *out, size_t n, DevBuf &tmp, int *tota
         return 0;
     }
     const size_t n_tiles = (n + kTile - 1) / kTile;
-    if (tmp.bytes < scan_workspace_ints(n) * sizeof(int)) {
-        SPHB_CUDA(cudaStreamSynchronize(st));   // (an earlier scan may still be using the old workspace)
-        SPHB_TRY(scan_reserve(tmp, n));
-    }
-    int *totals = scan_totals(tmp);
-    if (n_tiles > 1 && n_tiles <= one_pass_limit()) {
-        SPHB_LAUNCH_PDL(scan_one_pass, (unsigned)n_tiles, kScanThreads, 0, st, in, out, tmp.as<int>(), n, total_out_dev);
-        if (launches) *launches += 1;
-        SPHB_CUDA(cudaGetLastError());
-        return 0;
-    }
+    SPHB_TRY(tmp.reserve(n_tiles * sizeof(int)));
+    int *totals = tmp.as<int>();
     SPHB_LAUNCH_PDL(scan_tiles, (unsigned)n_tiles, kScanThreads, 0, st, in, out, totals, n, total_out_dev);
     if (n_tiles > 1) SPHB_LAUNCH_PDL(scan_finish, (unsigned)n_tiles, kScanThreads, 0, st, out, totals, n, total_out_dev);
     if (launches) *launches += (n_tiles > 1) ? 2 : 1;
@@ -247,17 +151,7 @@ int exclusive_scan_i32(const int *in, int *out, size_t n, DevBuf &tmp, int *tota
     return 0;
 }
 
-size_t scan_workspace_ints(size_t n) { return (size_t)kWsHeader + (n == 0 ? 1 : (n + kTile - 1) / kTile); }
-int *scan_totals(const DevBuf &ws) { return ws.as<int>() + kWsHeader; }
-// grows the workspace for scans of n elements; a new allocation starts zeroed (flags of the one-pass form)
-int scan_reserve(DevBuf &ws, size_t n)
-{
-    const size_t need = scan_workspace_ints(n) * sizeof(int);
-    if (ws.bytes >= need) return 0;
-    SPHB_TRY(ws.reserve(need));
-    SPHB_CUDA(cudaMemset(ws.p, 0, ws.bytes));
-    return 0;
-}
+size_t scan_workspace_ints(size_t n) { return n == 0 ? 1 : (n + kTile - 1) / kTile; }
 
 int exclusive_scan_i32_batch(const ScanChan *chan_dev, int n_chan, size_t n, cudaStream_t st, long long *launches)
 {

@@ -130,7 +130,7 @@ int sort_plan(SortWork &w, int nf, double DL, double h, double y_span_hint)
     SPHB_TRY(w.cnt.reserve(((size_t)w.key_cap + 1) * sizeof(int)));
     SPHB_TRY(w.start.reserve(((size_t)w.key_cap + 1) * sizeof(int)));
     SPHB_TRY(w.fill.reserve(((size_t)w.key_cap + 1) * sizeof(int)));
-    SPHB_TRY(scan_reserve(w.scan_tmp, (size_t)w.key_cap));
+    SPHB_TRY(w.scan_tmp.reserve(((size_t)w.key_cap / 4096 + 2) * sizeof(int)));
     return 0;
 }
 
