@@ -73,6 +73,14 @@ def test_slab_group_on_the_simulator(simlib):
     assert " passed" in out, out
 
 
+def test_c_host_of_the_sharded_channel_on_the_simulator(simlib):
+    """sphb_slabs_* (csrc/slab_group.cu: cut, mailboxes, stepping, run_until, download -- no Python in the loop) against
+    the single-domain run, three slabs sharing the simulator's one device; the same host drives one slab per GPU on a
+    multi-GPU box (tests/test_gpu_slab.py::test_native_c_host_one_slab_per_gpu)."""
+    out = _run(simlib, ["tests/test_gpu_slab.py"], k="native_c_host_matches and 3-0.02")
+    assert " passed" in out, out
+
+
 def test_parity_suite_subset_on_the_simulator(simlib):
     """The quick part of the device-resident and MEX-path parity tests (bit-exact neighbour lists, 1e-11 fields):
     guards the simulator itself and, with it, every later kernel change made without a GPU.  The fibers of a CTA are
