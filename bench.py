@@ -343,6 +343,9 @@ def b200_arm(args):
     ch.run_dual(max(W, 3), inner)
     ch.sync()
     l0 = ch.timing()["launches"]
+    step0 = int(ch.status()["step"]) // max(inner, 1)   # outer steps so far: which timed steps carry a cell sort (m:272)
+    si = int(cfg.sort_interval)
+    sorts_timed = sum(1 for k in range(step0 + 1, step0 + K + 1) if si > 0 and k % si == 0 and k != 1)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     sampler = ClockSampler(local_rank)
     barrier()
@@ -491,6 +494,7 @@ def b200_arm(args):
             "config": {"workload": workload_name(cfg, pt, inner), "inner_substeps": inner,
                        "list_rebuild": "every outer step (device counting sort + tile-local 16-bit lists)",
                        "cell_sort_interval": cfg.sort_interval,
+                       "cell_sorts_in_timed_steps": sorts_timed,
                        "row_order": ("raw lattice" if args.no_presort else
                                      "after the reference's cell sort (m:529-568), as in a run past its first sort point"),
                        "l2": ("256 MiB memset between timed steps" if flush is not None else
