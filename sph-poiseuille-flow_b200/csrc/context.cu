@@ -687,6 +687,8 @@ SPHB_API int sphb_ctx_status(sphb_ctx *c, sphb_status *out)
     SPHB_CUDA(cudaMemcpyAsync(c->h_scalars, c->sc(), sizeof(DevScalars), cudaMemcpyDeviceToHost, c->st));
     c->h_ints[0] = c->h_ints[1] = c->h_ints[2] = 0;
     if (c->planned) {
+        // (a slab's step may be replayed by a graph of its caller, which rebuilds the list behind this library's back)
+        if (c->slab.on) c->nw.half_valid = false;
         if (c->have_list) SPHB_TRY(neighbor_half_total(c->nw, c->st));
         SPHB_CUDA(cudaMemcpyAsync(c->h_ints, c->nw.totals.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
         SPHB_CUDA(cudaMemcpyAsync(c->h_ints + 2, c->nw.flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
