@@ -73,10 +73,6 @@ int plan_lists(sphb_ctx *c, double y_lo, double y_hi)
                            csr_max_tile_slots()));
     SPHB_TRY(csr_configure(c->nw.tile_cap));
     SPHB_TRY(c->shear_partials.reserve(2 * (size_t)c->nw.n_tiles * sizeof(double)));
-    if (!c->tile_queue.p) {
-        SPHB_TRY(c->tile_queue.reserve(4 * sizeof(unsigned)));
-        SPHB_CUDA(cudaMemset(c->tile_queue.p, 0, 4 * sizeof(unsigned)));
-    }
     for (DevBuf *b : {&c->e_vel, &c->e_w, &c->e_pV, &c->e_b1, &c->e_b2, &c->e_vn})   // entry-ordered mirrors
         if (b->bytes < c->nw.ell_stride * sizeof(double2)) {
             SPHB_TRY(b->reserve(c->nw.ell_stride * sizeof(double2)));
@@ -368,7 +364,7 @@ SPHB_API void sphb_ctx_destroy(sphb_ctx *c)
     DevBuf *all[] = {&c->pos, &c->vel, &c->vel_new, &c->wall_vel, &c->force, &c->force_prior, &c->rho, &c->p,
                      &c->drho_dt, &c->mass, &c->Vol, &c->B, &c->a_pos, &c->a_vel, &c->a_wall_vel, &c->a_force,
                      &c->a_force_prior, &c->a_rho, &c->a_p, &c->a_drho_dt, &c->a_mass, &c->a_Vol, &c->a_B,
-                     &c->scalars, &c->shear_partials, &c->stage, &c->prof, &c->rp_half, &c->tile_queue,
+                     &c->scalars, &c->shear_partials, &c->stage, &c->prof, &c->rp_half,
                      &c->e_vel, &c->e_w, &c->e_pV, &c->e_b1, &c->e_b2, &c->e_vn};
     for (DevBuf *b : all) b->release();
     for (DevBuf *b : {&c->slab.w_pos, &c->slab.w_mass, &c->slab.w_wall_vel, &c->slab.counts, &c->slab.block_tot,

@@ -225,23 +225,6 @@ __device__ __forceinline__ void stage_bulk(const K &k, const StateView &S, const
     }
 }
 
-#ifndef SPHB_DYNAMIC_TILES
-#define SPHB_DYNAMIC_TILES 1
-#endif
-// Every CTA of a pipelined kernel passes here exactly once, whatever path it took (worked through tiles, found the
-// step stopped by an error flag, had no tile): the last one re-arms the tile queue for the next launch.
-__device__ __forceinline__ void tiles_leave(const StateView &S, unsigned n_ctas)
-{
-#if SPHB_DYNAMIC_TILES
-    if (threadIdx.x == 0 && S.tile_queue != nullptr) {
-        __threadfence();
-        if (atomicAdd(S.tile_queue + 1, 1u) == n_ctas - 1) {
-            S.tile_queue[0] = 0u;
-            S.tile_queue[1] = 0u;
-        }
-    }
-#endif
-}
 template <class K>
 __device__ __forceinline__ void run_tiles(K &k, const StateView &S, unsigned cta, unsigned n_ctas)
 {
@@ -254,66 +237,36 @@ __device__ __forceinline__ void run_tiles(K &k, const StateView &S, unsigned cta
     const int cap = S.tile_cap;
     const size_t buf_bytes = (size_t)cap * K::kFields * sizeof(double2);
     const unsigned n_tiles = S.n_tiles;
-    if (cta >= n_tiles) {
-        tiles_leave(S, n_ctas);
-        return;
-    }
+    if (cta >= n_tiles) return;
     const int tid = (int)threadIdx.x;
     if (tid == 0) {
         mbar_init(&bars[0], 1u);
         mbar_init(&bars[1], 1u);
         mbar_init_fence();
     }
-    // Which tile a CTA takes next.  SPHB_DYNAMIC_TILES: the first is its own index, the following ones come off a
-    // ticket counter (StateView::tile_queue), two tiles ahead of the rows being walked so that the descriptor and the
-    // bulk copies of the next tile are in flight as before -- CTAs that drew cheap tiles (plain, sparsely filled) take
-    // more of them instead of idling behind the ones that drew wall / seam tiles.  Which CTA computes a tile does not
-    // change what it computes.  Off: the static round robin cta, cta + n_ctas, ...
-#if SPHB_DYNAMIC_TILES
-    __shared__ unsigned s_id[2];
-    unsigned *ctr = S.tile_queue;
-    if (tid == 0) {
-        s_id[0] = n_ctas + atomicAdd(ctr, 1u);
-        s_id[1] = n_ctas + atomicAdd(ctr, 1u);
-    }
-#endif
     int4 dnext = make_int4(0, 0, 0, 0);   // descriptor of the tile after the next one (threads 0 .. kDescWords-1)
-    if (tid < kDescWords) reinterpret_cast<int4 *>(&Ts[0])[tid] = reinterpret_cast<const int4 *>(S.tiles + cta)[tid];
+    if (tid < kDescWords) {
+        reinterpret_cast<int4 *>(&Ts[0])[tid] = reinterpret_cast<const int4 *>(S.tiles + cta)[tid];
+        if (cta + n_ctas < n_tiles) dnext = reinterpret_cast<const int4 *>(S.tiles + cta + n_ctas)[tid];
+    }
     __syncthreads();
-#if SPHB_DYNAMIC_TILES
-    unsigned tn = s_id[0], tnn = s_id[1];
-    int slot = 0;
-#else
-    unsigned tn = cta + n_ctas, tnn = cta + 2 * n_ctas;
-#endif
-    if (tid < kDescWords && tn < n_tiles) dnext = reinterpret_cast<const int4 *>(S.tiles + tn)[tid];
     stage_bulk(k, S, Ts[0], smem_raw, cap, &bars[0]);
     OwnPre pre = tile_prefetch_own(S, Ts[0]);
     unsigned parity = 0u;   // bit b = phase of bars[b] to wait for next
     int cur = 0, dcur = 0;
-    for (unsigned t = cta; t < n_tiles; cur ^= 1, dcur = dcur == 2 ? 0 : dcur + 1) {
+    for (unsigned t = cta; t < n_tiles; t += n_ctas, cur ^= 1, dcur = dcur == 2 ? 0 : dcur + 1) {
         const TileDesc &T = Ts[dcur];
         TileDesc &Tn = Ts[dcur == 2 ? 0 : dcur + 1];
         unsigned char *buf = smem_raw + (size_t)cur * buf_bytes;
         unsigned char *bufn = smem_raw + (size_t)(cur ^ 1) * buf_bytes;
+        const unsigned tn = t + n_ctas;
         const bool has_next = tn < n_tiles;
         if (tid < kDescWords) {
             if (has_next) reinterpret_cast<int4 *>(&Tn)[tid] = dnext;
-            if (tnn < n_tiles) dnext = reinterpret_cast<const int4 *>(S.tiles + tnn)[tid];
+            if (tn + n_ctas < n_tiles) dnext = reinterpret_cast<const int4 *>(S.tiles + tn + n_ctas)[tid];
         }
-#if SPHB_DYNAMIC_TILES
-        // the ticket of the tile after tnn: written before the barrier, read behind it (the slot written two iterations
-        // from now is this one again -- another barrier lies in between)
-        if (tid == 0) s_id[slot] = tnn < n_tiles ? n_ctas + atomicAdd(ctr, 1u) : 0xffffffffu;
-#endif
-        async_proxy_fence();   // (generic-proxy stores into the other buffer -- the dummy slot -- before the copies below)
+        async_proxy_fence();   // this thread's stores into the other buffer (a seam tile staged by hand) before the copies below
         __syncthreads();       // Tn is visible; every thread has left the rows of the previous tile: the other buffer is free
-#if SPHB_DYNAMIC_TILES
-        const unsigned tnnn = s_id[slot];
-        slot ^= 1;
-#else
-        const unsigned tnnn = tnn + n_ctas;
-#endif
         OwnPre pre_next;
         pre_next.key = 3;
         pre_next.n = 0;
@@ -329,11 +282,7 @@ __device__ __forceinline__ void run_tiles(K &k, const StateView &S, unsigned cta
             else k.template rows<true>(S, T, pre, buf, cap);
         }
         pre = pre_next;
-        t = tn;
-        tn = tnn;
-        tnn = tnnn;
     }
-    tiles_leave(S, n_ctas);
 }
 
 // fields of a staging buffer: field f of slot s at buf + (f * cap + s) * 16
@@ -408,10 +357,7 @@ struct DensityK {
 
 __device__ __forceinline__ void density_tiles(PhysParams P, const StateView &S, const DevScalars *sc, unsigned cta, unsigned n_ctas)
 {
-    if (step_poisoned(S.flags)) {
-        tiles_leave(S, n_ctas);
-        return;
-    }
+    if (step_poisoned(S.flags)) return;
     load_counts(P);
     DensityK k;
     k.P = P;
@@ -488,10 +434,7 @@ struct KgcK {
 
 __device__ __forceinline__ void kgc_tiles(PhysParams P, const StateView &S, unsigned cta, unsigned n_ctas)
 {
-    if (step_poisoned(S.flags)) {
-        tiles_leave(S, n_ctas);
-        return;
-    }
+    if (step_poisoned(S.flags)) return;
     load_counts(P);
     KgcK k;
     k.P = P;
@@ -958,10 +901,7 @@ struct ForceK {
 __device__ __forceinline__ void force_fused_tiles(PhysParams P, const StateView &S, const DevScalars *sc, int add_gravity,
                                                   unsigned cta, unsigned n_ctas)
 {
-    if (step_poisoned(S.flags)) {
-        tiles_leave(S, n_ctas);
-        return;
-    }
+    if (step_poisoned(S.flags)) return;
     load_counts(P);
     ForceK k;
     k.P = P;
@@ -1136,13 +1076,9 @@ __device__ __forceinline__ void continuity_tiles(PhysParams P, const StateView &
         // replayed graph still counts into the cell counters this kernel was to zero for it (GridFuse): do that much.
         if (F.g != nullptr && advance_clock)
             for (int j = (int)(cta * kTileThreads + threadIdx.x); j < F.n_cell_ints; j += (int)(n_ctas * kTileThreads)) F.cell_cnt[j] = 0;
-        tiles_leave(S, n_ctas);
         return;
     }
-    if (sc->dual_on && !sc->sub_on) {   // device-side scheduler: the outer step is used up
-        tiles_leave(S, n_ctas);
-        return;
-    }
+    if (sc->dual_on && !sc->sub_on) return;   // device-side scheduler: the outer step is used up
     load_counts(P);
     const bool fuse = F.g != nullptr && advance_clock;
     ContinuityK k;

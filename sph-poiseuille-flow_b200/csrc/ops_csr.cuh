@@ -79,7 +79,6 @@ struct StateView {
     // at once ("poisoned"): inside a replayed graph the state then stays where the last consistent step left it
     // until the host looks (sphb_ctx_run_dual, sphb_ctx_sync), instead of advancing on a truncated list.
     int *flags;
-    unsigned *tile_queue;     // [next tile ticket, CTAs done] of the persistent gather kernels (zero between launches)
     size_t ell_stride;
     int ell_cap;
     int tile_cap;             // shared-memory slots per tile
