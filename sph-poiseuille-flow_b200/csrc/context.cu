@@ -96,13 +96,14 @@ int fresh_mirrors(sphb_ctx *c, bool need_pv)
     return 0;
 }
 
-int do_density(sphb_ctx *c)
+// publish_dt: the density launch opens a reference step (do_publish_dt folded into it)
+int do_density(sphb_ctx *c, bool publish_dt = false, double remain = 0.0)
 {
     SPHB_TRY(fresh_mirrors(c, false));
     const StateView S = c->view();
     {
         ProfScope ps(&c->kprof, kPfDensity, c->st);
-        SPHB_TRY(csr_density(c->P, S, c->sc(), c->st));
+        SPHB_TRY(csr_density(c->P, S, c->sc(), c->st, publish_dt, remain));
     }
     {
         ProfScope ps(&c->kprof, kPfKgc, c->st);
@@ -185,6 +186,7 @@ int do_neighbor(sphb_ctx *c)
 
 int do_shear(sphb_ctx *c)
 {
+    SPHB_TRY(fresh_mirrors(c, false));   // the monitor stages the wall entries' weights and velocities from the mirrors
     ProfScope ps(&c->kprof, kPfShear, c->st);
     SPHB_TRY(csr_wall_shear(c->P, c->view(), c->sc(), c->shear_partials.as<double>(), c->st));
     c->launches += 1;
@@ -219,17 +221,7 @@ int do_substep(sphb_ctx *c, double remain, double fixed_dt, bool wrap, bool buil
     return 0;
 }
 
-// the time step of the outer step's first substep (m:259): published before the density pass, which evaluates the
-// half-step pressures of every row with it
-int do_publish_dt(sphb_ctx *c, double remain, double fixed_dt)
-{
-    ProfScope ps(&c->kprof, kPfTimeStep, c->st);
-    SPHB_TRY(csr_publish_dt(c->P, c->sc(), remain, fixed_dt, c->st));
-    c->launches += 1;
-    return 0;
-}
-
-// first substep of an outer step (after do_publish_dt and do_density): viscous + transport + pressure in one
+// first substep of an outer step (after do_density, which published the step's dt): viscous + transport + pressure in one
 // gather, then continuity
 int do_fused_first_substep(sphb_ctx *c, bool wrap, bool build_follows = false)
 {
@@ -273,8 +265,7 @@ int ctx_step_physics(sphb_ctx *c, double remain)
     c->h_step += 1;
     c->last_inner = 1;
     c->last_remain = remain;
-    SPHB_TRY(do_publish_dt(c, remain, 0.0));                  // m:259
-    SPHB_TRY(do_density(c));                                  // m:254-255
+    SPHB_TRY(do_density(c, true, remain));                    // m:259 (dt), m:254-255
     // a slab's list build follows after the exchange: the continuity pass starts its grid set-up (GridFuse, derive = 0)
     SPHB_TRY(do_fused_first_substep(c, true, c->slab.on));    // m:256-270
     return 0;
@@ -715,8 +706,7 @@ SPHB_API int sphb_ctx_step(sphb_ctx *c, double remain)
     c->last_inner = 1;
     c->last_remain = remain;
     tick(c, 0);
-    SPHB_TRY(do_publish_dt(c, remain, 0.0));                                          // m:259
-    SPHB_TRY(do_density(c));                                                          // m:254-255
+    SPHB_TRY(do_density(c, true, remain));                                            // m:259 (dt), m:254-255
     tick(c, 1);
     tick(c, 2);
     SPHB_TRY(do_fused_first_substep(c, true, true));                                  // m:256-269
@@ -899,8 +889,7 @@ namespace {
 int enqueue_outer(sphb_ctx *c, int n_inner, bool with_sort, double first_remain = std::numeric_limits<double>::infinity())
 {
     const double inf = std::numeric_limits<double>::infinity();
-    SPHB_TRY(do_publish_dt(c, first_remain, 0.0));
-    SPHB_TRY(do_density(c));
+    SPHB_TRY(do_density(c, true, first_remain));   // (publishes the step's dt: m:259)
     SPHB_TRY(do_fused_first_substep(c, true, n_inner == 1));
     for (int s = 1; s < n_inner; ++s) SPHB_TRY(do_substep(c, inf, 0.0, true, s == n_inner - 1));
     if (with_sort) SPHB_TRY(do_sort(c));

@@ -1027,8 +1027,11 @@ __device__ __forceinline__ void walk_tile_body(NbrParams P, const GridDesc *__re
         if (t_max > P.ell_cap) atomicOr(flags, kErrCsrCap);
     }
 }
+#ifndef SPHB_WALK_MINCTAS
+#define SPHB_WALK_MINCTAS 8   // resident CTAs per SM the walk is compiled for (r2 call 36, walk alone: 4 -> 102.5 us (128 registers), 5 -> 93.0, 6 -> 88.5 (80 registers), 8 -> 82.3 (64 registers, 112 B of spills))
+#endif
 template <bool HALF>
-__global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, const GridDesc *__restrict__ g, TileDesc *tiles,
+__global__ void __launch_bounds__(kTileThreads, SPHB_WALK_MINCTAS) k_walk_tile(NbrParams P, const GridDesc *__restrict__ g, TileDesc *tiles,
                                                            BuildMirrors M, WalkSetup W, int tile_w,
                                                            const int *__restrict__ cell_start,
                                                            const double2 *__restrict__ snap,
@@ -1042,7 +1045,7 @@ __global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile(NbrParams P, cons
     pdl_trigger_end();
 }
 // full lists only (the half list is the stateless MEX export)
-__global__ void __launch_bounds__(kTileThreads, 6) k_walk_tile_batch(const NbrChan *__restrict__ chan)
+__global__ void __launch_bounds__(kTileThreads, SPHB_WALK_MINCTAS) k_walk_tile_batch(const NbrChan *__restrict__ chan)
 {
     const NbrChan &c = chan[blockIdx.y];
     WalkSetup W;

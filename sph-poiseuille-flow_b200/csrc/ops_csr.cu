@@ -291,6 +291,17 @@ __device__ __forceinline__ double2 *field(unsigned char *buf, int cap, int f)
     return reinterpret_cast<double2 *>(buf) + (size_t)f * cap;
 }
 
+// the time step of a reference step (m:519-527)
+__device__ __forceinline__ double device_dt(const PhysParams &P, const DevScalars *sc, double remain, double fixed_dt)
+{
+    if (fixed_dt > 0.0) return fixed_dt;
+    const double vmax = sc->vmax;
+    const double dt_a = 0.25 * P.h / fmax(P.c_f + vmax, 1e-12);
+    const double dt_v = 0.125 * P.h * P.h / fmax(P.nu, 1e-12);
+    const double dt_b = 0.25 * sqrt(P.h / fmax(fabs(P.g), 1e-12));
+    return fmax(fmin(fmin(dt_a, dt_v), fmin(dt_b, remain)), 1e-12);
+}
+
 // ---------------------------------------------------------------- P1 pass 1: sigma sums -> rho, Vol
 // staged per slot: position; tiles with wall entries also (m_j / rho0, 0) for a wall entry (ph:205), (-1, 0) for a
 // fluid entry.  Also writes the entry-ordered (half-step pressure, volume) pair the later kernels stage.
@@ -355,29 +366,44 @@ struct DensityK {
     }
 };
 
-__device__ __forceinline__ void density_tiles(PhysParams P, const StateView &S, const DevScalars *sc, unsigned cta, unsigned n_ctas)
+// publish != 0: this launch opens a reference step -- every thread derives the step's dt from max|v| itself (what the
+// one-thread k_publish_dt launch used to do in front of this kernel: ~4 us of an otherwise idle device per step), and
+// one thread publishes it for the kernels behind and re-arms the max|v| reduction.
+__device__ __forceinline__ void density_tiles(PhysParams P, const StateView &S, DevScalars *sc, unsigned cta, unsigned n_ctas,
+                                              int publish, double remain)
 {
+    double dt;
+    if (publish) {
+        dt = device_dt(P, sc, remain, 0.0);
+        if (cta == 0 && threadIdx.x == 0) {
+            sc->dt = dt;
+            sc->vmax_bits = 0ull;
+        }
+    } else {
+        dt = sc->dt;
+    }
     if (step_poisoned(S.flags)) return;
     load_counts(P);
     DensityK k;
     k.P = P;
-    k.dt = sc->dt;
+    k.dt = dt;
     run_tiles(k, S, cta, n_ctas);
 }
 #ifndef SPHB_DENS_MINCTAS
 #define SPHB_DENS_MINCTAS 6   // (r2 calls 3-4: 8 -> 150 B of spills, 53 us; 6 -> 43 us; 5 -> 44 us)
 #endif
-__global__ void __launch_bounds__(kTileThreads, SPHB_DENS_MINCTAS) k_density(PhysParams P, StateView S, const DevScalars *sc)
+__global__ void __launch_bounds__(kTileThreads, SPHB_DENS_MINCTAS) k_density(PhysParams P, StateView S, DevScalars *sc, int publish,
+                                                                            double remain)
 {
     pdl_wait();
     pdl_trigger_top();
-    density_tiles(P, S, sc, blockIdx.x, gridDim.x);
+    density_tiles(P, S, sc, blockIdx.x, gridDim.x, publish, remain);
     pdl_trigger_end();
 }
 __global__ void __launch_bounds__(kTileThreads, SPHB_DENS_MINCTAS) k_density_batch(const BatchChan *__restrict__ chan)
 {
     const BatchChan &c = chan[blockIdx.y];
-    density_tiles(c.P, c.S, c.sc, blockIdx.x, gridDim.x);
+    density_tiles(c.P, c.S, c.sc, blockIdx.x, gridDim.x, 0, 0.0);
 }
 
 // ---------------------------------------------------------------- P1 pass 2: A -> B (ph:239-366)
@@ -745,20 +771,10 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_pressure_batch(const BatchC
 // (virtual wall pressure ph:929-934 and the kick ph:1402-1403).  One row walk therefore serves all
 // three operators: 80 B gathered per neighbour once instead of 72 B + 88 B.  Walkers with wall
 // neighbours take a second, short walk over their wall entries once F_prior is complete.  The time
-// step (m:519-527) is published by k_publish_dt before the density pass, which evaluates every row's
+// step (m:519-527) is published by the density pass (density_tiles), which evaluates every row's
 // half-step pressure (ph:857-862) into the entry-ordered (p, V) pairs this kernel stages.
 // staged per slot: position, velocity (wall entry: wall velocity), (half-step pressure, volume; volume < 0 = wall
 // entry), the two rows of B.
-__device__ __forceinline__ double device_dt(const PhysParams &P, const DevScalars *sc, double remain, double fixed_dt)
-{
-    if (fixed_dt > 0.0) return fixed_dt;
-    const double vmax = sc->vmax;
-    const double dt_a = 0.25 * P.h / fmax(P.c_f + vmax, 1e-12);
-    const double dt_v = 0.125 * P.h * P.h / fmax(P.nu, 1e-12);
-    const double dt_b = 0.25 * sqrt(P.h / fmax(fabs(P.g), 1e-12));
-    return fmax(fmin(fmin(dt_a, dt_v), fmin(dt_b, remain)), 1e-12);
-}
-
 struct ForceK {
     static constexpr int kFields = 5;
     PhysParams P;
@@ -905,7 +921,7 @@ __device__ __forceinline__ void force_fused_tiles(PhysParams P, const StateView 
     load_counts(P);
     ForceK k;
     k.P = P;
-    k.dt = sc->dt;   // published by k_publish_dt on the same stream
+    k.dt = sc->dt;   // published by the density launch that opened the step
     k.add_gravity = add_gravity;
     run_tiles(k, S, cta, n_ctas);
 }
@@ -929,16 +945,6 @@ __global__ void __launch_bounds__(kTileThreads, SPHB_FORCE_MINCTAS) k_force_fuse
     force_fused_tiles(c.P, c.S, c.sc, add_gravity, blockIdx.x, gridDim.x);
 }
 
-// publishes the time step of the substep and re-arms the max|v| reduction (one thread; runs before the
-// fused force kernel on the same stream)
-__global__ void k_publish_dt(PhysParams P, DevScalars *sc, double remain, double fixed_dt)
-{
-    pdl_wait();
-    pdl_trigger_top();
-    sc->dt = device_dt(P, sc, remain, fixed_dt);
-    sc->vmax_bits = 0ull;
-    pdl_trigger_end();
-}
 // Device-side dual-criteria scheduler (README.md:61-65 of the reference; its constants are those of m:519-527 split
 // by what they bound): the outer step from the advection, viscous and body-force criteria, the first substep from
 // the acoustic one.
@@ -1207,9 +1213,8 @@ __device__ __forceinline__ void wall_shear_tiles(PhysParams P, const StateView &
     const GridDesc *g = S.grid;
     const int tpr = tiles_per_row(S.ncx, S.tile_w);
     const int n_trows = (int)(S.n_tiles / (unsigned)tpr);
-    const int cyb = (int)floor((0.0 - g->y_min) / g->cell), cyt = (int)floor((P.DH - g->y_min) / g->cell);
-    const int nb = cyb + 1 < 0 ? 0 : min(n_trows, (cyb + 1) / kTileRows + 1);
-    const int t0 = max(nb, cyt - kTileRows <= 0 ? 0 : (cyt - 1) / kTileRows);
+    int nb, t0;
+    wall_tile_rows(g, P.DH, n_trows, nb, t0);
     const int ncand = (nb + max(0, n_trows - t0)) * tpr;
     double sb = 0.0, st = 0.0;
     for (int q = (int)cta; q < ncand; q += (int)n_ctas) {
@@ -1219,33 +1224,53 @@ __device__ __forceinline__ void wall_shear_tiles(PhysParams P, const StateView &
         __syncthreads();   // the previous tile's readers are done with T and the staging arrays
         tile_load(T, S.tiles, (unsigned)(tr * tpr + tc));
         __syncthreads();
-        if (!(T.flags & kTileValid)) continue;
+        // (the walk of this build has marked the tiles whose neighbourhood holds a wall entry)
+        if (!(T.flags & kTileValid) || !(T.flags & kTileHasWall)) continue;
         const OwnPre pre = tile_prefetch_own(S, T);
-        int walls = 0;
-        SPHB_TILE_FOR_STAGED(T, e, slot)
+        // the walker's own operands are requested before the staging, whose latency hides theirs
+        double own_vx = 0.0, own_V = 0.0;
+        Mat2 own_B;
+        own_B.b11 = own_B.b12 = own_B.b21 = own_B.b22 = 0.0;
+        if ((pre.key & 3) == 0 && (pre.key >> 3) < P.nfo) {
+            own_vx = S.vel[pre.key >> 3].x;
+            own_B = S.B[pre.key >> 3];
+            own_V = S.Vol[pre.key >> 3];
+        }
+        // Staged from the entry-ordered mirrors of the build (position; wall weight m / rho0 = the wall entry's volume,
+        // -1 for a fluid entry; wall velocity): three independent coalesced loads per slot instead of the chain
+        // ent_key -> Vol[j], wall_vel[j] segment by segment, which was a third of this latency-bound kernel's time.
         {
-            const int j = S.ent_key[e] >> 3;
-            s_xy[slot] = S.ent_pos[e];
-            if (j >= P.nf) {
-                s_V[slot] = -S.Vol[j];
-                s_wvx[slot] = S.wall_vel[j].x;
-                walls = 1;
-            } else {
-                s_V[slot] = 1.0;
-            }
+            struct StageRec {
+                double2 xy;
+                double w, wvx;
+            };
+            tile_stage_flat(
+                T,
+                [&](int e) {
+                    StageRec r;
+                    r.xy = S.ent_pos[e];
+                    r.w = S.e_w[e].x;
+                    r.wvx = S.e_vel[e].x;
+                    return r;
+                },
+                [&](int slot, const StageRec &r) {
+                    s_xy[slot] = r.xy;
+                    s_V[slot] = r.w < 0.0 ? 1.0 : -r.w;   // > 0: skipped like the dummy; wall: minus its volume
+                    s_wvx[slot] = r.wvx;
+                });
         }
         if (threadIdx.x == 0) {
             s_xy[T.n_staged] = make_double2(kDummyCoord, kDummyCoord);
             s_V[T.n_staged] = 1.0;   // skipped like a fluid neighbour
         }
-        if (!__syncthreads_or(walls)) continue;
+        __syncthreads();
         SPHB_TILE_WALKERS(ew, si, i)
         {
             if (i >= P.nfo) continue;   // wall rows and halo copies of a slab
             const double2 pi = s_xy[si];
-            const double vx = S.vel[i].x;
-            const Mat2 Bi = S.B[i];
-            const double Vi = S.Vol[i];
+            const double vx = first__ ? own_vx : S.vel[i].x;
+            const Mat2 Bi = first__ ? own_B : S.B[i];
+            const double Vi = first__ ? own_V : S.Vol[i];
             SPHB_ROW(true, ([&](const int sl, const int m) {
                 const double Vs = s_V[sl];
                 if (Vs > 0.0) return;
@@ -1415,10 +1440,10 @@ int csr_configure(int tile_cap)
     return 0;
 }
 
-int csr_density(const PhysParams &P, const StateView &S, const DevScalars *sc, cudaStream_t st)
+int csr_density(const PhysParams &P, const StateView &S, DevScalars *sc, cudaStream_t st, bool publish_dt, double remain)
 {
     const size_t sm = (size_t)S.tile_cap * kDensitySlot;
-    SPHB_LAUNCH_PDL(k_density, persistent_ctas(k_density, sm, S.n_tiles), kTileThreads, sm, st, P, S, sc);
+    SPHB_LAUNCH_PDL(k_density, persistent_ctas(k_density, sm, S.n_tiles), kTileThreads, sm, st, P, S, sc, publish_dt ? 1 : 0, remain);
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1462,14 +1487,6 @@ int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
-// the time step of the coming substep (m:519-527) and the re-armed max|v| reduction: before the density pass of an
-// outer step, which evaluates the half-step pressures with it
-int csr_publish_dt(const PhysParams &P, DevScalars *sc, double remain, double fixed_dt, cudaStream_t st)
-{
-    SPHB_LAUNCH_PDL(k_publish_dt, 1, 1, 0, st, P, sc, remain, fixed_dt);
-    SPHB_CUDA(cudaGetLastError());
-    return 0;
-}
 int csr_dual_begin(const PhysParams &P, DevScalars *sc, double remain, cudaStream_t st)
 {
     k_dual_begin<<<1, 1, 0, st>>>(P, sc, remain);
@@ -1482,8 +1499,8 @@ int csr_dual_end(DevScalars *sc, cudaStream_t st)
     SPHB_CUDA(cudaGetLastError());
     return 0;
 }
-// viscous + transport + pressure + kick in one gather (the first substep of an outer step; after csr_publish_dt
-// and csr_density of the same outer step)
+// viscous + transport + pressure + kick in one gather (the first substep of an outer step; after the csr_density that
+// published the step's dt)
 int csr_force_fused(const PhysParams &P, const StateView &S, const DevScalars *sc, bool add_gravity, cudaStream_t st)
 {
     const size_t sm = (size_t)S.tile_cap * kForceSlot;

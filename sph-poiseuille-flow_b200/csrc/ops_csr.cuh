@@ -86,7 +86,10 @@ struct StateView {
     unsigned n_tiles;
 };
 
-int csr_density(const PhysParams &P, const StateView &S, const DevScalars *sc, cudaStream_t st);   // P1 pass 1 (+ half-step p)
+// publish_dt: the launch opens a reference step -- it derives dt from max|v| (m:519-527, cut by `remain`, m:259),
+// publishes it and re-arms the max|v| reduction (csr_publish_dt folded in)
+int csr_density(const PhysParams &P, const StateView &S, DevScalars *sc, cudaStream_t st, bool publish_dt = false,
+                double remain = 0.0);   // P1 pass 1 (+ half-step p)
 int csr_kgc(const PhysParams &P, const StateView &S, cudaStream_t st);                           // P1 pass 2
 int csr_visc_transport(const PhysParams &P, const StateView &S, bool do_visc, bool add_gravity, bool do_transport,
                        cudaStream_t st);                                                         // P2 + P3
@@ -97,9 +100,6 @@ int csr_pressure(const PhysParams &P, const StateView &S, const DevScalars *sc, 
 // P5 + finish (+ clock); F.g != NULL: also the y range / grid / zeroed cell counters of the list build that follows
 int csr_continuity(const PhysParams &P, const StateView &S, DevScalars *sc, bool wrap, bool advance_clock,
                    const GridFuse &F, cudaStream_t st);
-// dt of the coming substep = min(acoustic, viscous, body, remain) from the device vmax (m:519-527), published BEFORE
-// the density pass of an outer step (which evaluates the half-step pressures with it); fixed_dt > 0 overrides
-int csr_publish_dt(const PhysParams &P, DevScalars *sc, double remain, double fixed_dt, cudaStream_t st);
 // Device-side dual-criteria scheduler: opens an outer step (Dt = min(0.25 h / max|v|, 0.125 h^2 / nu, 0.25 sqrt(h/|g|),
 // remain), first substep dt = min(acoustic, Dt)) / closes it (dual_on = 0).  Between the two the substep kernels
 // (csr_time_step, csr_pressure, csr_continuity) take dt = min(acoustic, Dt_left) and return at once when Dt is used up.

@@ -61,6 +61,15 @@ static_assert(sizeof(TileDesc) % 16 == 0, "TileDesc is copied as int4");
 __host__ __device__ inline int tiles_per_row(int ncx, int w) { return (ncx + w - 1) / w; }
 __host__ __device__ inline int tile_rows(int ncy) { return (ncy + kTileRows - 1) / kTileRows; }
 
+// Tile rows whose walkers can have wall neighbours -- the candidates of the wall-shear monitor: [0, nb) and
+// [t0, n_trows), i.e. cy0 - 1 <= cyb (bottom wall, y <= 0) or cy0 + kTileRows >= cyt (top wall, y >= DH).
+__device__ __forceinline__ void wall_tile_rows(const GridDesc *g, double DH, int n_trows, int &nb, int &t0)
+{
+    const int cyb = (int)floor((0.0 - g->y_min) / g->cell), cyt = (int)floor((DH - g->y_min) / g->cell);
+    nb = cyb + 1 < 0 ? 0 : min(n_trows, (cyb + 1) / kTileRows + 1);
+    t0 = max(nb, cyt - kTileRows <= 0 ? 0 : (cyt - 1) / kTileRows);
+}
+
 __device__ __forceinline__ unsigned ell_pack(int slot, int m) { return (unsigned)slot | ((unsigned)(m + kShiftBias) << kSlotBits); }
 __device__ __forceinline__ int ell_slot(unsigned c) { return (int)(c & kSlotMask); }
 __device__ __forceinline__ int ell_shift(unsigned c) { return (int)((c >> kSlotBits) & 7u) - kShiftBias; }

@@ -38,7 +38,7 @@ def test_library_is_sm_100a_only_and_holds_every_step_kernel():
     assert archs == {"sm_100a"}, archs
     # (canonical cell order and tile descriptors are made inside the walk's CTA since round 2: no kernels of their own)
     step = ["k_yrange_grid", "k_bin_count", "scan_tiles", "scan_finish", "k_scatter",
-            "k_walk_tile", "k_density", "k_kgc", "k_force_fused", "k_publish_dt", "k_continuity", "k_time_step",
+            "k_walk_tile", "k_density", "k_kgc", "k_force_fused", "k_continuity", "k_time_step",
             "k_pressure", "k_wall_shear"]
     for name in step:
         assert name in k, f"{name} missing from libsph_b200.so"
@@ -67,7 +67,7 @@ def test_gather_kernels_keep_their_register_budget_and_do_not_spill():
                        "k_pressure_batch": 96, "k_wall_shear_batch": 96}.items():
         for rec in k[name]:
             assert rec["reg"] <= regs and rec["stack"] <= 64 and rec["local"] == 0, (name, rec)
-    # the walk is capped at 80 registers for 6 resident CTAs (__launch_bounds__(128, 6)); a few spilled words are
-    # the known price, more than that is a regression
+    # the walk is capped at 64 registers for 8 resident CTAs (__launch_bounds__(128, 8): measured faster than 6 CTAs
+    # of 80 registers, r2 call 36, although it spills ~30 words); more than that is a regression
     for rec in k["k_walk_tile"] + k["k_walk_tile_batch"]:
-        assert rec["reg"] <= 80 and rec["stack"] <= 80, rec
+        assert rec["reg"] <= 64 and rec["stack"] <= 144, rec
