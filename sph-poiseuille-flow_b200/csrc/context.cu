@@ -73,7 +73,7 @@ int plan_lists(sphb_ctx *c, double y_lo, double y_hi)
                            csr_max_tile_slots()));
     SPHB_TRY(csr_configure(c->nw.tile_cap));
     SPHB_TRY(c->shear_partials.reserve(2 * (size_t)c->nw.n_tiles * sizeof(double)));
-    for (DevBuf *b : {&c->e_vel, &c->e_w, &c->e_pV, &c->e_b1, &c->e_b2, &c->e_vn})   // entry-ordered mirrors
+    for (DevBuf *b : {&c->e_vel, &c->e_w, &c->e_pV, &c->e_b1, &c->e_b2, &c->e_vn, &c->e_rm})   // entry-ordered mirrors
         if (b->bytes < c->nw.ell_stride * sizeof(double2)) {
             SPHB_TRY(b->reserve(c->nw.ell_stride * sizeof(double2)));
             SPHB_CUDA(cudaMemsetAsync(b->p, 0, c->nw.ell_stride * sizeof(double2), c->st));
@@ -356,7 +356,7 @@ SPHB_API void sphb_ctx_destroy(sphb_ctx *c)
                      &c->drho_dt, &c->mass, &c->Vol, &c->B, &c->a_pos, &c->a_vel, &c->a_wall_vel, &c->a_force,
                      &c->a_force_prior, &c->a_rho, &c->a_p, &c->a_drho_dt, &c->a_mass, &c->a_Vol, &c->a_B,
                      &c->scalars, &c->shear_partials, &c->stage, &c->prof, &c->rp_half,
-                     &c->e_vel, &c->e_w, &c->e_pV, &c->e_b1, &c->e_b2, &c->e_vn};
+                     &c->e_vel, &c->e_w, &c->e_pV, &c->e_b1, &c->e_b2, &c->e_vn, &c->e_rm};
     for (DevBuf *b : all) b->release();
     for (DevBuf *b : {&c->slab.w_pos, &c->slab.w_mass, &c->slab.w_wall_vel, &c->slab.counts, &c->slab.block_tot,
                       &c->slab.pid, &c->slab.a_pid, &c->slab.sort_flag, &c->slab.sort_ptr})

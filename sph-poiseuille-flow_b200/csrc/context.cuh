@@ -49,7 +49,7 @@ struct sphb_ctx {
     DevBuf pos, vel, vel_new, wall_vel, force, force_prior, rho, p, drho_dt, mass, Vol, B;
     DevBuf a_pos, a_vel, a_wall_vel, a_force, a_force_prior, a_rho, a_p, a_drho_dt, a_mass, a_Vol, a_B;
     DevBuf scalars, shear_partials, stage, prof, rp_half;
-    DevBuf e_vel, e_w, e_pV, e_b1, e_b2, e_vn;   // entry-ordered mirrors (StateView), nw.ell_stride double2 each
+    DevBuf e_vel, e_w, e_pV, e_b1, e_b2, e_vn, e_rm;   // entry-ordered mirrors (StateView), nw.ell_stride double2 each
     NeighborWork nw;
     SlabState slab;
     SortWork sw;
@@ -112,6 +112,7 @@ struct sphb_ctx {
         S.e_b1 = e_b1.as<double2>();
         S.e_b2 = e_b2.as<double2>();
         S.e_vn = e_vn.as<double2>();
+        S.e_rm = e_rm.as<double2>();
         S.ghost_ent = nw.ghost_ent.as<int>();
         S.flags = nw.flags.as<int>();
         S.ell_stride = nw.ell_stride;

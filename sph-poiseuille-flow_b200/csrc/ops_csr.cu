@@ -81,19 +81,23 @@ __device__ __forceinline__ double spline_dW(double r, const PhysParams &P)
 struct OwnPre {
     int key, n;
     uint4 q0;
+    double2 rm;   // StateView::e_rm of the walker (only the kernels that ask for it: K::kOwnRm)
 };
+template <bool RM = false>
 __device__ __forceinline__ OwnPre tile_prefetch_own(const StateView &S, const TileDesc &T)
 {
     OwnPre p;
     p.key = 3;   // "not a real entry"
     p.n = 0;
     p.q0 = make_uint4(0u, 0u, 0u, 0u);
+    p.rm = make_double2(0.0, 0.0);
     if ((int)threadIdx.x < tile_own_total(T)) {
         int orow, ew, si;
         tile_own_locate(T, (int)threadIdx.x, orow, ew, si);
         p.key = S.ent_key[ew];
         p.n = S.ell_cnt[ew];
         p.q0 = S.ell_q[ew];
+        if (RM) p.rm = S.e_rm[ew];
     }
     return p;
 }
@@ -251,7 +255,7 @@ __device__ __forceinline__ void run_tiles(K &k, const StateView &S, unsigned cta
     }
     __syncthreads();
     stage_bulk(k, S, Ts[0], smem_raw, cap, &bars[0]);
-    OwnPre pre = tile_prefetch_own(S, Ts[0]);
+    OwnPre pre = tile_prefetch_own<K::kOwnRm>(S, Ts[0]);
     unsigned parity = 0u;   // bit b = phase of bars[b] to wait for next
     int cur = 0, dcur = 0;
     for (unsigned t = cta; t < n_tiles; t += n_ctas, cur ^= 1, dcur = dcur == 2 ? 0 : dcur + 1) {
@@ -271,9 +275,10 @@ __device__ __forceinline__ void run_tiles(K &k, const StateView &S, unsigned cta
         pre_next.key = 3;
         pre_next.n = 0;
         pre_next.q0 = make_uint4(0u, 0u, 0u, 0u);
+        pre_next.rm = make_double2(0.0, 0.0);
         if (has_next) {
             stage_bulk(k, S, Tn, bufn, cap, &bars[cur ^ 1]);
-            pre_next = tile_prefetch_own(S, Tn);
+            pre_next = tile_prefetch_own<K::kOwnRm>(S, Tn);
         }
         if (T.flags & kTileValid) {
             mbar_wait(&bars[cur], (parity >> cur) & 1u);
@@ -306,6 +311,7 @@ __device__ __forceinline__ double device_dt(const PhysParams &P, const DevScalar
 // staged per slot: position; tiles with wall entries also (m_j / rho0, 0) for a wall entry (ph:205), (-1, 0) for a
 // fluid entry.  Also writes the entry-ordered (half-step pressure, volume) pair the later kernels stage.
 struct DensityK {
+    static constexpr bool kOwnRm = false;
     static constexpr int kFields = 2;
     PhysParams P;
     double dt;
@@ -356,6 +362,7 @@ struct DensityK {
             // half-step pressure of this row for the force kernel's neighbours (ph:857-862)
             const double rho_h = half_step_rho(rho, drho_i, dt, P.rho0);
             const double2 pV = make_double2(P.p0 * (rho_h / P.rho0 - 1.0), V);
+            S.e_rm[ew] = make_double2(rho_h, m_i);   // the force kernel's own-row operands, with its row head
             S.e_pV[ew] = pV;
             ghost_store(S, key__, i, S.e_pV, pV);
         }
@@ -409,6 +416,7 @@ __global__ void __launch_bounds__(kTileThreads, SPHB_DENS_MINCTAS) k_density_bat
 // ---------------------------------------------------------------- P1 pass 2: A -> B (ph:239-366)
 // staged per slot: position, (-, volume).  Also writes the entry-ordered rows of B.
 struct KgcK {
+    static constexpr bool kOwnRm = false;
     static constexpr int kFields = 2;
     PhysParams P;
     __device__ __forceinline__ int bulk_fields(const TileDesc &) const { return 2; }
@@ -776,6 +784,7 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_pressure_batch(const BatchC
 // staged per slot: position, velocity (wall entry: wall velocity), (half-step pressure, volume; volume < 0 = wall
 // entry), the two rows of B.
 struct ForceK {
+    static constexpr bool kOwnRm = true;   // the walker's (half-step density, mass) travels with its row head
     static constexpr int kFields = 5;
     PhysParams P;
     double dt;
@@ -813,9 +822,12 @@ struct ForceK {
             const double2 vi = s_v[si];
             const double2 bi1 = s_b1[si], bi2 = s_b2[si];
             const double2 pVi = s_pV[si];                      // (half-step p, volume)
-            const double Vi = pVi.y, m_i = S.mass[i];
+            // (half-step density ph:857-861, mass): what the density pass of this step computed for this row, bit for
+            // bit, fetched with the row head one tile ahead instead of three loads through the row index here
+            const double2 rm = first__ ? pre.rm : S.e_rm[ew];
+            const double Vi = pVi.y, m_i = rm.y;
             const double p_i = pVi.x;
-            const double rho_i = half_step_rho(S.rho[i], S.drho_dt[i], dt, P.rho0);   // ph:857-861 (own row: exact)
+            const double rho_i = rm.x;
             double ax = 0.0, ay = 0.0, ix = 0.0, iy = 0.0, fx = 0.0, fy = 0.0;
             bool has_wall = false;
             SPHB_ROW(!PLAIN, ([&](const int sl, const int m) {
@@ -992,6 +1004,7 @@ __device__ __forceinline__ double wrap_x(double x, double DL)   // MATLAB mod(x,
 // ---------------------------------------------------------------- P5 + density/EOS finish + wrap + max|v|
 // staged per slot: position, new velocity (a wall entry: its wall velocity), (-, volume; volume < 0 = wall entry)
 struct ContinuityK {
+    static constexpr bool kOwnRm = false;
     static constexpr int kFields = 3;
     PhysParams P;
     double dt;
@@ -1361,6 +1374,7 @@ __global__ void __launch_bounds__(kBlock) k_refresh_mirrors(PhysParams P, StateV
     S.e_b1[e] = make_double2(B.b11, B.b12);
     S.e_b2[e] = make_double2(B.b21, B.b22);
     S.e_vn[e] = (fluid ? S.vel_new : S.wall_vel)[j];
+    S.e_rm[e] = make_double2(fluid ? S.rp_half[j].x : 0.0, S.mass[j]);
 }
 
 // ---------------------------------------------------------------- binned u(y) monitor (m:579-605)

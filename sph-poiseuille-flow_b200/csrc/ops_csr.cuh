@@ -73,6 +73,7 @@ struct StateView {
     double2 *e_pV;            // (half-step pressure, volume; volume < 0 marks a wall entry)  written by k_density
     double2 *e_b1, *e_b2;     // rows of B                                                     written by k_kgc
     double2 *e_vn;            // new velocity (wall entry: wall velocity)                      written by the force kernels
+    double2 *e_rm;            // (half-step density, mass) of a fluid walker                   written by the density kernel
     const int *ghost_ent;     // [2 i + kind - 1]: entry of particle i's ghost of that kind (validated against ent_key): the
                               // producers above write the mirrors of a row's ghost entries as well (ghost_store)
     // device error flags (sphb_status.error_flags).  Once a flag is up the state-changing kernels of the step return
